@@ -1,0 +1,183 @@
+"""Mission / world input formats of the reference and the synthetic swarm generators.
+
+Host-side data loading only (numpy); mirrors what the reference's ``Mission::readMissionFile``
+(reference src/mission.cpp:94-200) and ``MapManager::updateOctreeFromCSV`` (src/map_manager.cpp:264-316)
+read.  Coordinates are parsed to float32 exactly like ``GetFloat()`` does (src/mission.cpp:111-112, 163-189).
+"""
+import json
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class PlannerConfig:
+    """Launch-file parameter sets (reference launch/*.launch)."""
+    M: int = 5
+    n: int = 5
+    phi: int = 3
+    dim: int = 3
+    use_sfc: bool = False
+    dt: float = 0.2
+    world_res: float = 0.1
+    grid_res: float = 0.5
+    z_2d: float = 1.0
+    comm_range: float = -1.0
+    w_control: float = 0.01
+    w_terminal: float = 1.0
+    reset_threshold: float = 0.5
+
+    @staticmethod
+    def empty():      # launch/testall_DLSCGC_empty.launch
+        return PlannerConfig(M=5, dim=3, use_sfc=False, comm_range=-1.0)
+
+    @staticmethod
+    def forest3d():   # launch/testall_DLSCGC_3D.launch
+        return PlannerConfig(M=10, dim=3, use_sfc=True, comm_range=3.0)
+
+    @staticmethod
+    def maze2d():     # launch/simulation.launch
+        return PlannerConfig(M=10, dim=2, use_sfc=True, comm_range=3.0)
+
+
+@dataclass
+class Mission:
+    world_min: np.ndarray
+    world_max: np.ndarray
+    start: np.ndarray          # [N,3] float32
+    goal: np.ndarray           # [N,3] float32
+    radius: np.ndarray         # [N] float64
+    downwash: np.ndarray
+    max_vel: np.ndarray
+    max_acc: np.ndarray
+    nominal_vel: np.ndarray
+    boxes: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.float32))  # cx,cy,cz,sx,sy,sz
+
+    @property
+    def n_agents(self):
+        return int(self.start.shape[0])
+
+
+def load_mission(path, dim=3, z_2d=1.0):
+    """Parse a reference mission JSON (missions/readme.txt)."""
+    with open(path) as f:
+        doc = json.load(f)
+    d = doc["world"][0]["dimension"]
+    wmin = np.array(d[:3], np.float32)
+    wmax = np.array(d[3:], np.float32)
+    quads = doc["quadrotors"]
+    start, goal, rad, dw, mv, ma, nv = [], [], [], [], [], [], []
+    for ag in doc["agents"]:
+        q = quads[ag["type"]]
+        s = [float(x) for x in ag["start"]]
+        g = [float(x) for x in ag["goal"]]
+        if dim == 2:
+            s[2] = z_2d
+            g[2] = z_2d
+        start.append(s)
+        goal.append(g)
+        rad.append(float(ag.get("radius", q["radius"])) if "size" in ag else float(q["radius"]))
+        dw.append(float(ag.get("downwash", q["downwash"])))
+        mv.append(float(q["max_vel"][0]))          # first element only, src/mission.cpp:120-124
+        ma.append(float(q["max_acc"][0]))
+        nv.append(float(q["nominal_velocity"]))
+    f64 = lambda x: np.array(x, np.float64)
+    return Mission(wmin, wmax, np.array(start, np.float32), np.array(goal, np.float32), f64(rad), f64(dw),
+                   f64(mv), f64(ma), f64(nv))
+
+
+def load_world_csv(path):
+    """Rows ``cx,cy,cz,sx,sy,sz`` (src/map_manager.cpp:267-283; tokens go through stod then float)."""
+    rows = []
+    with open(path) as f:
+        for line in f:
+            tok = [t for t in line.strip().split(",") if t != ""]
+            if len(tok) < 6:
+                continue
+            rows.append([float(t) for t in tok[:6]])
+    return np.array(rows, np.float32).reshape(-1, 6)
+
+
+def lattice_step_waypoints(pos, goal, grid_res=0.5, occupied=None):
+    """Documented stand-in for the PIBT waypoint provider (reference src/grid_based_planner.cpp:64-94):
+    one greedy step on the ``grid_res`` lattice from the current waypoint toward the goal, axis with the
+    largest remaining distance first, skipping lattice nodes in ``occupied`` (a set of integer node keys).
+    Identical waypoints are fed to the oracle and to the GPU path, so parity is independent of it."""
+    pos = np.asarray(pos, np.float32)
+    goal = np.asarray(goal, np.float32)
+    out = pos.copy()
+    for a in range(pos.shape[0]):
+        delta = goal[a].astype(np.float64) - pos[a].astype(np.float64)
+        order = np.argsort(-np.abs(delta))
+        for k in order:
+            if abs(delta[k]) < 0.5 * grid_res:
+                continue
+            cand = pos[a].astype(np.float64).copy()
+            cand[k] += np.sign(delta[k]) * grid_res
+            key = tuple(int(round(c / grid_res)) for c in cand)
+            if occupied is not None and key in occupied:
+                continue
+            out[a] = cand.astype(np.float32)
+            break
+    return out
+
+
+def synthetic_forest(n_agents=4096, half_extent=32.0, height=2.5, tree_density=0.1, seed=4096,
+                     grid_res=0.5, z=1.0):
+    """square world [-h,h]^2 x [0,height], trees 0.5x0.5xheight boxes at
+    ``tree_density`` per m^2, distinct start / goal lattice nodes (0.5 m xy lattice at height z) that keep
+    1.0 m (xy, Chebyshev) clearance from every tree centre.  Deviation from the survey text: numpy's PCG64
+    replaces std::mt19937_64 (no bit-compatible generator in numpy); seeds are fixed so every run,
+    oracle or GPU, sees the same world."""
+    rng = np.random.default_rng(seed)
+    h = float(half_extent)
+    n_trees = int(round(tree_density * (2 * h) ** 2 / 10.0) * 10) if tree_density > 0 else 0
+    n_trees = int(round(tree_density * (2 * h) ** 2))
+    nodes_1d = np.arange(-h + 1.0, h - 1.0 + 1e-9, grid_res)
+    gx, gy = np.meshgrid(nodes_1d, nodes_1d, indexing="ij")
+    nodes = np.stack([gx.ravel(), gy.ravel()], 1)
+    # trees on the 0.1 m grid so the box edges are cell aligned
+    tc = np.round(rng.uniform(-h + 1.0, h - 1.0, size=(n_trees, 2)) * 10.0) / 10.0 + 0.05
+    # nodes with clearance
+    free = np.ones(nodes.shape[0], bool)
+    for t in range(n_trees):
+        free &= np.max(np.abs(nodes - tc[t]), axis=1) >= 1.0
+    free_idx = np.nonzero(free)[0]
+    if free_idx.size < n_agents:
+        raise ValueError("world too small for %d agents" % n_agents)
+    rng2 = np.random.default_rng(seed + 1)
+    s_idx = rng2.choice(free_idx, n_agents, replace=False)
+    g_idx = rng2.choice(free_idx, n_agents, replace=False)
+    start = np.concatenate([nodes[s_idx], np.full((n_agents, 1), z)], 1).astype(np.float32)
+    goal = np.concatenate([nodes[g_idx], np.full((n_agents, 1), z)], 1).astype(np.float32)
+    boxes = np.zeros((n_trees, 6), np.float32)
+    boxes[:, 0:2] = tc
+    boxes[:, 2] = height / 2
+    boxes[:, 3:5] = 0.5
+    boxes[:, 5] = height
+    full = lambda v: np.full(n_agents, v, np.float64)
+    return Mission(np.array([-h, -h, 0.0], np.float32), np.array([h, h, height], np.float32), start, goal,
+                   full(0.15), full(2.0), full(1.0), full(2.0), full(1.0), boxes)
+
+
+def synthetic_empty(n_agents=70, half_extent=None, seed=7, grid_res=0.5):
+    """Obstacle-free 3-D swarm shaped like missions/empty*/multi_random_*agents_*.json: distinct start and
+    goal nodes on the 0.5/0.5/1.0 m lattice of a box world."""
+    rng = np.random.default_rng(seed)
+    if half_extent is None:
+        half_extent = max(1.5, 0.5 * np.ceil(np.cbrt(n_agents * 4.0)))
+    h = float(half_extent)
+    xs = np.arange(-h + 0.5, h - 0.5 + 1e-9, grid_res)
+    zs = np.arange(0.5, 2.0 + 1e-9, 1.0) if h <= 2.0 else np.arange(0.5, 2 * h - 0.5 + 1e-9, 1.0)
+    gx, gy, gz = np.meshgrid(xs, xs, zs, indexing="ij")
+    nodes = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], 1)
+    if nodes.shape[0] < n_agents:
+        raise ValueError("world too small")
+    s = nodes[rng.choice(nodes.shape[0], n_agents, replace=False)]
+    g = nodes[rng.choice(nodes.shape[0], n_agents, replace=False)]
+    full = lambda v: np.full(n_agents, v, np.float64)
+    zmax = 2.5 if h <= 2.0 else 2 * h
+    return Mission(np.array([-h, -h, 0.0], np.float32), np.array([h, h, zmax], np.float32),
+                   s.astype(np.float32), g.astype(np.float32), full(0.15), full(2.0), full(1.0), full(2.0),
+                   full(1.0))
