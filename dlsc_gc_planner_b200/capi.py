@@ -1,0 +1,299 @@
+"""ctypes binding of libdlsc_b200.so (include/dlsc_b200.h) and the `SwarmPlanner` host object.
+
+`SwarmPlanner` mirrors, for a whole agent block at once, what the reference keeps per agent in
+AgentManager + TrajPlanner (reference src/agent_manager.cpp:4-108, src/traj_planner.cpp:35-63):
+`plan()` = TrajPlanner::plan for every agent, `advance()` = AgentManager::doStep for every agent.
+
+There is no CPU path here: the loader opens the in-tree CUDA library and raises when it is missing
+or when no CUDA device is usable.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdlsc_b200.so")
+
+OK, QP_MAXITER, QP_NUMERIC, SFC_INIT_FAILED, GOAL_INFEASIBLE, SFC_REUSED, NBR_OVERFLOW = 0, 1, 2, 4, 8, 16, 32
+STAGE_PREDICT, STAGE_NBR, STAGE_LSC, STAGE_SFC, STAGE_GOAL, STAGE_QP, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
+STAGE_NAMES = ("predict", "nbr", "lsc", "sfc", "goal", "qp")
+FAIL_MASK = QP_MAXITER | QP_NUMERIC | SFC_INIT_FAILED | GOAL_INFEASIBLE
+
+
+class DlscParams(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("n", C.c_int32), ("phi", C.c_int32), ("dim", C.c_int32),
+        ("use_sfc", C.c_int32), ("max_nbr", C.c_int32),
+        ("dt", C.c_double),
+        ("world_min", C.c_double * 3), ("world_max", C.c_double * 3),
+        ("world_res", C.c_double), ("grid_res", C.c_double), ("z_2d", C.c_double),
+        ("comm_range", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
+        ("reset_threshold", C.c_double),
+        ("qp_max_iter", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class DlscAgents(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("vel", C.c_void_p), ("acc", C.c_void_p), ("waypoint", C.c_void_p),
+                ("disturbed", C.c_void_p)]
+
+
+class DlscAgentProps(C.Structure):
+    _fields_ = [("radius", C.c_void_p), ("downwash", C.c_void_p), ("max_vel", C.c_void_p),
+                ("max_acc", C.c_void_p), ("nominal_vel", C.c_void_p)]
+
+
+EXPORTS = (
+    "dlsc_last_error dlsc_abi_version dlsc_device_count dlsc_create dlsc_destroy dlsc_set_stream dlsc_get_stream "
+    "dlsc_set_edt dlsc_set_agent_props dlsc_reset dlsc_set_agents dlsc_records_device dlsc_record_floats "
+    "dlsc_bind_records dlsc_set_records dlsc_get_records dlsc_step dlsc_run_stages dlsc_advance "
+    "dlsc_publish_records dlsc_sync dlsc_get_seq dlsc_set_seq dlsc_get_traj dlsc_get_qp_x dlsc_get_cost "
+    "dlsc_get_violation dlsc_get_qp_iters dlsc_get_status dlsc_get_goal dlsc_get_state dlsc_get_init_traj "
+    "dlsc_get_pred_traj dlsc_get_neighbours dlsc_get_lsc dlsc_get_sfc dlsc_set_sfc dlsc_enable_timing "
+    "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device").split()
+
+
+def build_library(force=False):
+    """Compile libdlsc_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.check_call(["make", "-C", src, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", src, "all"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def _declare(lib):
+    lib.dlsc_last_error.restype = C.c_char_p
+    for name in ("dlsc_records_device", "dlsc_get_stream", "dlsc_waypoint_device", "dlsc_traj_device"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_void_p
+            getattr(lib, name).argtypes = [C.c_void_p]
+    if hasattr(lib, "dlsc_launch_count"):
+        lib.dlsc_launch_count.restype = C.c_int64
+        lib.dlsc_launch_count.argtypes = [C.c_void_p]
+    return lib
+
+
+_LIB = None
+
+
+def load_library(path=None):
+    """Open the CUDA library.  Raises (no fallback) when it has not been built."""
+    global _LIB
+    if path is None:
+        if _LIB is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError("libdlsc_b200.so is not built: run `python -c 'import __graft_entry__ as g; "
+                                   "g.build()'` or `make -C dlsc_gc_planner_b200/csrc` (no CPU fallback exists)")
+            _LIB = _declare(C.CDLL(LIB_PATH))
+        return _LIB
+    return _declare(C.CDLL(path))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0):
+    """cfg: missions.PlannerConfig."""
+    p = DlscParams()
+    p.M, p.n, p.phi, p.dim, p.use_sfc, p.max_nbr = cfg.M, cfg.n, cfg.phi, cfg.dim, int(cfg.use_sfc), int(max_nbr)
+    p.dt = cfg.dt
+    for k in range(3):
+        p.world_min[k] = float(np.float32(world_min[k]))
+        p.world_max[k] = float(np.float32(world_max[k]))
+    p.world_res, p.grid_res, p.z_2d = cfg.world_res, cfg.grid_res, cfg.z_2d
+    p.comm_range, p.w_control, p.w_terminal = cfg.comm_range, cfg.w_control, cfg.w_terminal
+    p.reset_threshold = cfg.reset_threshold
+    p.qp_max_iter = qp_max_iter
+    return p
+
+
+class DlscError(RuntimeError):
+    pass
+
+
+class SwarmPlanner:
+    """One context = the agent block [begin, begin+n_local) of a swarm of n_agents on one GPU."""
+
+    def __init__(self, cfg, mission, max_nbr=None, begin=0, n_local=None, device=0, lib=None, qp_max_iter=0):
+        self.lib = lib if lib is not None else load_library()
+        self.cfg = cfg
+        self.N = int(mission.n_agents)
+        self.begin = int(begin)
+        self.NL = int(n_local if n_local is not None else self.N - begin)
+        self.M, self.P, self.D = cfg.M, cfg.n + 1, cfg.dim
+        self.K = int(max_nbr if max_nbr is not None else max(self.N - 1, 1))
+        self.params = make_params(cfg, mission.world_min, mission.world_max, self.K, qp_max_iter)
+        self.ctx = C.c_void_p()
+        self._ck(self.lib.dlsc_create(C.byref(self.params), self.N, self.begin, self.NL, int(device), C.byref(self.ctx)))
+        sl = slice(self.begin, self.begin + self.NL)
+        f64 = lambda x: np.ascontiguousarray(x[sl], np.float64)
+        self._props = [f64(mission.radius), f64(mission.downwash), f64(mission.max_vel), f64(mission.max_acc),
+                       f64(mission.nominal_vel)]
+        pr = DlscAgentProps(*[a.ctypes.data for a in self._props])
+        self._ck(self.lib.dlsc_set_agent_props(self.ctx, C.byref(pr)))
+        start = np.ascontiguousarray(mission.start[sl], np.float32).copy()
+        if cfg.dim == 2:
+            start[:, 2] = np.float32(cfg.z_2d)
+        self.start = start
+        self._ck(self.lib.dlsc_reset(self.ctx, _p(start)))
+        self.rec_floats = int(self.lib.dlsc_record_floats(self.ctx))
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise DlscError((self.lib.dlsc_last_error() or b"?").decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.dlsc_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs ---------------------------------------------------------------------------------
+    def set_edt(self, dist, obst, dims, min_key, res):
+        dist = np.ascontiguousarray(dist, np.float32)
+        obst = np.ascontiguousarray(obst, np.int32)
+        d3 = (C.c_int32 * 3)(*[int(x) for x in dims])
+        k3 = (C.c_int32 * 3)(*[int(x) for x in min_key])
+        self._ck(self.lib.dlsc_set_edt(self.ctx, _p(dist), _p(obst), d3, k3, C.c_double(res)))
+
+    def set_agents(self, pos=None, vel=None, acc=None, waypoint=None, disturbed=None):
+        f = lambda x: None if x is None else np.ascontiguousarray(x, np.float32)
+        keep = [f(pos), f(vel), f(acc), f(waypoint),
+                None if disturbed is None else np.ascontiguousarray(disturbed, np.uint8)]
+        a = DlscAgents(*[None if x is None else x.ctypes.data for x in keep])
+        self._ck(self.lib.dlsc_set_agents(self.ctx, C.byref(a)))
+        self._ck(self.lib.dlsc_sync(self.ctx))     # host arrays may go away after return
+
+    def set_agents_async(self, agents_struct):
+        """Caller keeps the (pinned) arrays alive; no synchronisation."""
+        self._ck(self.lib.dlsc_set_agents(self.ctx, C.byref(agents_struct)))
+
+    def set_records(self, first, rec):
+        rec = np.ascontiguousarray(rec, np.float32)
+        self._ck(self.lib.dlsc_set_records(self.ctx, int(first), int(rec.shape[0]), _p(rec)))
+
+    def get_records(self, first=0, count=None):
+        count = self.N - first if count is None else count
+        out = np.zeros((count, self.rec_floats), np.float32)
+        self._ck(self.lib.dlsc_get_records(self.ctx, int(first), int(count), _p(out)))
+        return out
+
+    def set_sfc(self, sfc=None, init_flag=None):
+        sfc = None if sfc is None else np.ascontiguousarray(sfc, np.float32)
+        fl = None if init_flag is None else np.ascontiguousarray(init_flag, np.uint8)
+        self._ck(self.lib.dlsc_set_sfc(self.ctx, _p(sfc), _p(fl)))
+
+    # -- the path -------------------------------------------------------------------------------
+    def plan(self):
+        """One replan of every agent of the block (stream ordered, asynchronous)."""
+        self._ck(self.lib.dlsc_step(self.ctx))
+
+    def run_stages(self, mask):
+        self._ck(self.lib.dlsc_run_stages(self.ctx, int(mask)))
+
+    def advance(self):
+        self._ck(self.lib.dlsc_advance(self.ctx))
+
+    def publish_records(self):
+        self._ck(self.lib.dlsc_publish_records(self.ctx))
+
+    def sync(self):
+        self._ck(self.lib.dlsc_sync(self.ctx))
+
+    @property
+    def seq(self):
+        return int(self.lib.dlsc_get_seq(self.ctx))
+
+    @seq.setter
+    def seq(self, v):
+        self._ck(self.lib.dlsc_set_seq(self.ctx, int(v)))
+
+    # -- outputs --------------------------------------------------------------------------------
+    def _get(self, fn, shape, dtype):
+        out = np.zeros(shape, dtype)
+        self._ck(fn(self.ctx, _p(out)))
+        return out
+
+    def traj(self):
+        return self._get(self.lib.dlsc_get_traj, (self.NL, self.M, self.P, 3), np.float32)
+
+    def qp_x(self):
+        return self._get(self.lib.dlsc_get_qp_x, (self.NL, self.D, self.M, self.P), np.float64)
+
+    def cost(self):
+        return self._get(self.lib.dlsc_get_cost, (self.NL,), np.float64)
+
+    def violation(self):
+        return self._get(self.lib.dlsc_get_violation, (self.NL,), np.float64)
+
+    def qp_iters(self):
+        return self._get(self.lib.dlsc_get_qp_iters, (self.NL,), np.int32)
+
+    def status(self):
+        return self._get(self.lib.dlsc_get_status, (self.NL,), np.int32)
+
+    def goal(self):
+        return self._get(self.lib.dlsc_get_goal, (self.NL, 3), np.float32)
+
+    def init_traj(self):
+        return self._get(self.lib.dlsc_get_init_traj, (self.NL, self.M, self.P, 3), np.float32)
+
+    def pred_traj(self):
+        return self._get(self.lib.dlsc_get_pred_traj, (self.N, self.M, self.P, 3), np.float32)
+
+    def sfc(self):
+        return self._get(self.lib.dlsc_get_sfc, (self.NL, self.M, 6), np.float32)
+
+    def state(self):
+        pos = np.zeros((self.NL, 3), np.float32)
+        vel = np.zeros((self.NL, 3), np.float32)
+        acc = np.zeros((self.NL, 3), np.float32)
+        self._ck(self.lib.dlsc_get_state(self.ctx, _p(pos), _p(vel), _p(acc)))
+        return pos, vel, acc
+
+    def neighbours(self):
+        idx = np.zeros((self.NL, self.K), np.int32)
+        cnt = np.zeros(self.NL, np.int32)
+        self._ck(self.lib.dlsc_get_neighbours(self.ctx, _p(idx), _p(cnt)))
+        return idx, cnt
+
+    def lsc(self, with_anchor=True):
+        normal = np.zeros((self.NL, self.K, self.M, 3), np.float32)
+        d = np.zeros((self.NL, self.K, self.M, self.P), np.float64)
+        anchor = np.zeros((self.NL, self.K, self.M, self.P, 3), np.float32) if with_anchor else None
+        self._ck(self.lib.dlsc_get_lsc(self.ctx, _p(normal), _p(anchor), _p(d)))
+        return normal, anchor, d
+
+    def counters(self):
+        out = np.zeros(8, np.int64)
+        self._ck(self.lib.dlsc_get_counters(self.ctx, _p(out)))
+        return dict(pairs=int(out[0]), gjk_iters=int(out[1]), edt_lookups=int(out[2]), qp_iters=int(out[3]),
+                    qp_rows=int(out[4]))
+
+    def enable_timing(self, on=True):
+        self._ck(self.lib.dlsc_enable_timing(self.ctx, int(on)))
+
+    def timings(self):
+        ms = (C.c_double * 6)()
+        n = C.c_int(0)
+        self._ck(self.lib.dlsc_get_timings(self.ctx, ms, C.byref(n)))
+        return dict(zip(STAGE_NAMES, [float(x) for x in ms])), n.value
+
+    def launch_count(self):
+        return int(self.lib.dlsc_launch_count(self.ctx))
+
+    def records_device_ptr(self):
+        return int(self.lib.dlsc_records_device(self.ctx))
+
+    def bind_records(self, device_ptr):
+        self._ck(self.lib.dlsc_bind_records(self.ctx, C.c_void_p(int(device_ptr))))

@@ -1,0 +1,477 @@
+// dlsc_api.cu -- context management and the C ABI of libdlsc_b200.so (include/dlsc_b200.h).
+// No CPU fallback: every entry point requires a usable CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dlsc_b200.h"
+#include "dlsc_kernels.h"
+#include "dlsc_qp_tables.h"
+#include "dlsc_types.h"
+
+using namespace dlsc;
+
+static thread_local std::string g_err;
+
+struct dlsc_ctx {
+    dlsc_params hp;
+    DevParams P;
+    DevState S;
+    RecLayout rl;
+    QpTabHost th;
+    QpTab T;
+    QpLaunch qpl;
+    void* tab_blob = nullptr;
+    int device = 0;
+    int seq = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool rec_owned = false;
+    bool have_edt = false;
+    float* edt_dist = nullptr;      // staging (freed after pack)
+    int4* edt_cells = nullptr;
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[DLSC_N_STAGES + 1];
+    double t_ms[DLSC_N_STAGES];
+    int t_steps = 0;
+    std::vector<void*> allocs;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+static int fail(const char* msg) { g_err = msg; return -1; }
+
+template <class T>
+static int dev_alloc(dlsc_ctx* c, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+    CK(cudaMemset(q, 0, (n ? n : 1) * sizeof(T)));
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+extern "C" {
+
+const char* dlsc_last_error(void) { return g_err.c_str(); }
+int dlsc_abi_version(void) { return DLSC_ABI_VERSION; }
+int dlsc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static int upload_tables(dlsc_ctx* c) {
+    const QpTabHost& h = c->th;
+    // serialise every table into one blob (256-byte aligned sections)
+    struct Sec { const void* src; size_t bytes; size_t off; };
+    std::vector<Sec> secs;
+    size_t off = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        Sec s{src, bytes, off};
+        secs.push_back(s);
+        off += (bytes + 255) / 256 * 256;
+        return secs.size() - 1;
+    };
+#define SEC(v) add(h.v.data(), h.v.size() * sizeof(h.v[0]))
+    const size_t i_xm_nv = SEC(xm_nv), i_xm_cidx = SEC(xm_cidx), i_xm_idx = SEC(xm_idx), i_xm_coef = SEC(xm_coef);
+    const size_t i_pr_fam = SEC(pr_fam), i_pr_axis = SEC(pr_axis), i_pr_nnz = SEC(pr_nnz), i_pr_pt = SEC(pr_pt);
+    const size_t i_pr_idx = SEC(pr_idx), i_pr_val = SEC(pr_val), i_pr_cc = SEC(pr_cc);
+    const size_t i_yi_ptr = SEC(yi_ptr), i_yi_row = SEC(yi_row), i_yi_coef = SEC(yi_coef);
+    const size_t i_yp_ptr = SEC(yp_ptr), i_yp_pt = SEC(yp_pt), i_yp_coef = SEC(yp_coef);
+    const size_t i_wi_ptr = SEC(wi_ptr), i_wi_row = SEC(wi_row), i_wi_coef = SEC(wi_coef);
+    const size_t i_wp_ptr = SEC(wp_ptr), i_wp_pt = SEC(wp_pt), i_wp_coef = SEC(wp_coef);
+    const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2);
+#undef SEC
+    std::vector<char> blob(off ? off : 256, 0);
+    for (auto& s : secs) memcpy(blob.data() + s.off, s.src, s.bytes);
+    CK(cudaMalloc(&c->tab_blob, blob.size()));
+    CK(cudaMemcpy(c->tab_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    char* base = (char*)c->tab_blob;
+    QpTab& T = c->T;
+    T.D = h.D; T.M = h.M; T.nyd = h.nyd; T.ny = h.ny; T.npt = h.npt; T.nx = h.nx; T.np = h.np; T.ntri = h.ntri;
+    T.ntri_local = h.ntri_local; T.use_comm = h.use_comm;
+#define PTR(type, i) (const type*)(base + secs[i].off)
+    T.xm_nv = PTR(int8_t, i_xm_nv); T.xm_cidx = PTR(int8_t, i_xm_cidx); T.xm_idx = PTR(int16_t, i_xm_idx);
+    T.xm_coef = PTR(double, i_xm_coef);
+    T.pr_fam = PTR(uint8_t, i_pr_fam); T.pr_axis = PTR(uint8_t, i_pr_axis); T.pr_nnz = PTR(uint8_t, i_pr_nnz);
+    T.pr_pt = PTR(int16_t, i_pr_pt); T.pr_idx = PTR(int16_t, i_pr_idx); T.pr_val = PTR(double, i_pr_val);
+    T.pr_cc = PTR(double, i_pr_cc);
+    T.yi_ptr = PTR(int, i_yi_ptr); T.yi_row = PTR(int16_t, i_yi_row); T.yi_coef = PTR(double, i_yi_coef);
+    T.yp_ptr = PTR(int, i_yp_ptr); T.yp_pt = PTR(int16_t, i_yp_pt); T.yp_coef = PTR(double, i_yp_coef);
+    T.wi_ptr = PTR(int, i_wi_ptr); T.wi_row = PTR(int16_t, i_wi_row); T.wi_coef = PTR(double, i_wi_coef);
+    T.wp_ptr = PTR(int, i_wp_ptr); T.wp_pt = PTR(int16_t, i_wp_pt); T.wp_coef = PTR(double, i_wp_coef);
+    T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2);
+#undef PTR
+    return 0;
+}
+
+int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_local, int device, dlsc_ctx** out) {
+    if (!hp || !out) return fail("dlsc_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail("dlsc_create: no CUDA device available (libdlsc_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("dlsc_create: bad device index");
+    if (hp->n != 5 || hp->phi != 3) return fail("dlsc_create: only traj/n = 5, traj/phi = 3 are supported");
+    if (hp->dim != 2 && hp->dim != 3) return fail("dlsc_create: world/dimension must be 2 or 3");
+    if (hp->M < 2 || hp->M > kMaxM) return fail("dlsc_create: traj/M out of range [2,16]");
+    if (hp->dim * (3 * hp->M - 2) > 128) return fail("dlsc_create: dim*(3M-2) must be <= 128");
+    if (hp->max_nbr < 1) return fail("dlsc_create: max_nbr must be >= 1");
+    if (n_agents < 1 || agent_begin < 0 || n_local < 1 || agent_begin + n_local > n_agents)
+        return fail("dlsc_create: bad agent block");
+    if (!(hp->dt > 0) || !(hp->world_res > 0)) return fail("dlsc_create: dt and world_res must be positive");
+    CK(cudaSetDevice(device));
+    dlsc_ctx* c = new dlsc_ctx();
+    c->hp = *hp;
+    c->device = device;
+    DevParams& P = c->P;
+    memset(&P, 0, sizeof(P));
+    P.M = hp->M; P.D = hp->dim; P.use_sfc = hp->use_sfc; P.K = hp->max_nbr;
+    P.N = n_agents; P.begin = agent_begin; P.NL = n_local;
+    c->rl = rec_layout(hp->M);
+    P.rec = c->rl.size;
+    P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
+    P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
+    P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
+    P.reset_threshold = hp->reset_threshold;
+    for (int k = 0; k < 3; k++) {
+        P.world_min[k] = (double)(float)hp->world_min[k];
+        P.world_max[k] = (double)(float)hp->world_max[k];
+    }
+    {   // trajectory.cpp:84-90: time += dt/n after every control point
+        double time = 0;
+        for (int e = 0; e < hp->M * kP; e++) { P.tk[e] = (float)time; time += hp->dt / hp->n; }
+    }
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    memset(c->t_ms, 0, sizeof(c->t_ms));
+
+    DevState& S = c->S;
+    memset(&S, 0, sizeof(S));
+    const size_t N = n_agents, NL = n_local, K = hp->max_nbr, M = hp->M, npt = M * kP;
+    int rc = 0;
+    rc |= dev_alloc(c, &S.rec, N * P.rec);
+    c->rec_owned = true;
+    rc |= dev_alloc(c, &S.acc, NL * 3);
+    rc |= dev_alloc(c, &S.waypoint, NL * 3);
+    rc |= dev_alloc(c, &S.disturbed, NL);
+    rc |= dev_alloc(c, &S.sfc_init, NL);
+    rc |= dev_alloc(c, &S.radius, NL); rc |= dev_alloc(c, &S.downwash, NL); rc |= dev_alloc(c, &S.max_vel, NL);
+    rc |= dev_alloc(c, &S.max_acc, NL); rc |= dev_alloc(c, &S.nominal_vel, NL);
+    rc |= dev_alloc(c, &S.pred_traj, N * npt * 3);
+    rc |= dev_alloc(c, &S.init_traj, NL * npt * 3);
+    rc |= dev_alloc(c, &S.nbr_idx, NL * K);
+    rc |= dev_alloc(c, &S.nbr_cnt, NL);
+    rc |= dev_alloc(c, &S.lsc_normal, NL * K * M * 3);
+    rc |= dev_alloc(c, &S.lsc_d, NL * K * M * kP);
+    rc |= dev_alloc(c, &S.lsc_anchor_last, NL * K * 3);
+    rc |= dev_alloc(c, &S.sfc, NL * M * 6);
+    rc |= dev_alloc(c, &S.traj, NL * npt * 3);
+    rc |= dev_alloc(c, &S.qp_x, NL * (size_t)hp->dim * npt);
+    rc |= dev_alloc(c, &S.cost, NL); rc |= dev_alloc(c, &S.viol, NL);
+    rc |= dev_alloc(c, &S.qp_iters, NL); rc |= dev_alloc(c, &S.status, NL);
+    rc |= dev_alloc(c, &S.counters, 8);
+    rc |= dev_alloc(c, &S.qp_next, 1);
+    if (rc) { dlsc_destroy(c); return -1; }
+
+    build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->comm_range > 0, c->th);
+    if (upload_tables(c)) { dlsc_destroy(c); return -1; }
+    c->qpl = qp_launch_config(P, c->T, device);
+    if (c->qpl.smem > 227 * 1024) { dlsc_destroy(c); return fail("dlsc_create: QP shared memory exceeds 227 KB"); }
+    if (dev_alloc(c, &S.qp_scratch, (size_t)c->qpl.ctas * c->qpl.scratch_doubles)) { dlsc_destroy(c); return -1; }
+    {   // a 1-cell "free space" grid so the SFC kernel is well defined before dlsc_set_edt
+        S.edt.dims[0] = S.edt.dims[1] = S.edt.dims[2] = 0;
+        S.edt.res = hp->world_res; S.edt.inv_res = 1.0 / hp->world_res; S.edt.cells = nullptr;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); dlsc_destroy(c); return -1; }
+    *out = c;
+    return 0;
+}
+
+void dlsc_destroy(dlsc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->tab_blob) cudaFree(c->tab_blob);
+    if (c->edt_cells) cudaFree(c->edt_cells);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int dlsc_set_stream(dlsc_ctx* c, void* s) {
+    if (!c) return fail("null ctx");
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return 0;
+}
+void* dlsc_get_stream(dlsc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int32_t dims[3],
+                 const int32_t min_key[3], double res) {
+    if (!c || !dist || !obst) return fail("dlsc_set_edt: null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+    if (nc == 0) return fail("dlsc_set_edt: empty grid");
+    float* d_dist = nullptr; int32_t* d_obst = nullptr;
+    CK(cudaMalloc(&d_dist, nc * sizeof(float)));
+    CK(cudaMalloc(&d_obst, nc * 3 * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(d_dist, dist, nc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_obst, obst, nc * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (c->edt_cells) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_cells); c->edt_cells = nullptr; }
+    CK(cudaMalloc(&c->edt_cells, nc * sizeof(int4)));
+    launch_edt_pack(d_dist, d_obst, c->edt_cells, nc, c->stream);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_dist); cudaFree(d_obst);
+    EdtDev& E = c->S.edt;
+    for (int k = 0; k < 3; k++) { E.dims[k] = dims[k]; E.min_key[k] = min_key[k]; }
+    E.res = res; E.inv_res = 1.0 / res; E.cells = c->edt_cells;
+    c->have_edt = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
+    if (!c || !p) return fail("dlsc_set_agent_props: null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->P.NL * sizeof(double);
+    if (p->radius) CK(cudaMemcpyAsync(c->S.radius, p->radius, b, cudaMemcpyHostToDevice, c->stream));
+    if (p->downwash) CK(cudaMemcpyAsync(c->S.downwash, p->downwash, b, cudaMemcpyHostToDevice, c->stream));
+    if (p->max_vel) CK(cudaMemcpyAsync(c->S.max_vel, p->max_vel, b, cudaMemcpyHostToDevice, c->stream));
+    if (p->max_acc) CK(cudaMemcpyAsync(c->S.max_acc, p->max_acc, b, cudaMemcpyHostToDevice, c->stream));
+    if (p->nominal_vel) CK(cudaMemcpyAsync(c->S.nominal_vel, p->nominal_vel, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dlsc_reset(dlsc_ctx* c, const float* start) {
+    if (!c || !start) return fail("dlsc_reset: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->S.init_traj, start, (size_t)c->P.NL * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    launch_reset(c->P, c->S, c->S.init_traj, c->stream);
+    c->launches++;
+    c->seq = 0;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
+    if (!c || !a) return fail("dlsc_set_agents: null argument");
+    CK(cudaSetDevice(c->device));
+    const DevParams& P = c->P;
+    float* rec0 = c->S.rec + (size_t)P.begin * P.rec + c->rl.pos;
+    const size_t pitch = (size_t)P.rec * sizeof(float);
+    if (a->pos) CK(cudaMemcpy2DAsync(rec0, pitch, a->pos, 12, 12, P.NL, cudaMemcpyHostToDevice, c->stream));
+    if (a->vel) CK(cudaMemcpy2DAsync(rec0 + 3, pitch, a->vel, 12, 12, P.NL, cudaMemcpyHostToDevice, c->stream));
+    if (a->acc) CK(cudaMemcpyAsync(c->S.acc, a->acc, (size_t)P.NL * 12, cudaMemcpyHostToDevice, c->stream));
+    if (a->waypoint) CK(cudaMemcpyAsync(c->S.waypoint, a->waypoint, (size_t)P.NL * 12, cudaMemcpyHostToDevice, c->stream));
+    if (a->disturbed) CK(cudaMemcpyAsync(c->S.disturbed, a->disturbed, (size_t)P.NL, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+float* dlsc_records_device(dlsc_ctx* c) { return c ? c->S.rec : nullptr; }
+int dlsc_record_floats(const dlsc_ctx* c) { return c ? c->P.rec : 0; }
+int dlsc_bind_records(dlsc_ctx* c, float* p) {
+    if (!c || !p) return fail("dlsc_bind_records: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(p, c->S.rec, (size_t)c->P.N * c->P.rec * sizeof(float), cudaMemcpyDeviceToDevice));
+    c->S.rec = p;
+    c->rec_owned = false;
+    return 0;
+}
+int dlsc_set_records(dlsc_ctx* c, int first, int count, const float* host) {
+    if (!c || !host || first < 0 || count < 0 || first + count > c->P.N) return fail("dlsc_set_records: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->S.rec + (size_t)first * c->P.rec, host, (size_t)count * c->P.rec * sizeof(float),
+                       cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dlsc_get_records(dlsc_ctx* c, int first, int count, float* host) {
+    if (!c || !host || first < 0 || count < 0 || first + count > c->P.N) return fail("dlsc_get_records: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(host, c->S.rec + (size_t)first * c->P.rec, (size_t)count * c->P.rec * sizeof(float),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dlsc_run_stages(dlsc_ctx* c, int mask) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && !c->have_edt) return fail("dlsc_run_stages: use_sfc set but no EDT grid (dlsc_set_edt)");
+    cudaStream_t st = c->stream;
+    const int seq = c->seq + 1;     // planner_seq after the increment in TrajPlanner::plan (traj_planner.cpp:40)
+    const bool tm = c->timing;
+    if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
+        CK(cudaMemsetAsync(c->S.counters, 0, 8 * sizeof(unsigned long long), st));
+    if (tm) CK(cudaEventRecord(c->ev[0], st));
+    if (mask & DLSC_STAGE_PREDICT) { launch_predict(c->P, c->S, seq, st); c->launches++; }
+    if (tm) CK(cudaEventRecord(c->ev[1], st));
+    if (mask & DLSC_STAGE_NBR) { launch_neighbours(c->P, c->S, st); c->launches++; }
+    if (tm) CK(cudaEventRecord(c->ev[2], st));
+    if (mask & DLSC_STAGE_LSC) { launch_lsc(c->P, c->S, st); c->launches++; }
+    if (tm) CK(cudaEventRecord(c->ev[3], st));
+    if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc) { launch_sfc(c->P, c->S, st); c->launches++; }
+    if (tm) CK(cudaEventRecord(c->ev[4], st));
+    if (mask & DLSC_STAGE_GOAL) { launch_goal(c->P, c->S, st); c->launches++; }
+    if (tm) CK(cudaEventRecord(c->ev[5], st));
+    if (mask & DLSC_STAGE_QP) { launch_qp(c->P, c->S, c->T, c->qpl, st); c->launches++; }
+    if (tm) {
+        CK(cudaEventRecord(c->ev[6], st));
+        CK(cudaEventSynchronize(c->ev[6]));
+        for (int i = 0; i < DLSC_N_STAGES; i++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+            c->t_ms[i] += ms;
+        }
+        c->t_steps++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dlsc_step(dlsc_ctx* c) {
+    const int rc = dlsc_run_stages(c, DLSC_STAGE_ALL);
+    if (rc == 0) c->seq++;
+    return rc;
+}
+
+int dlsc_advance(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    launch_advance(c->P, c->S, true, c->stream);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int dlsc_publish_records(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    launch_advance(c->P, c->S, false, c->stream);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int dlsc_sync(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dlsc_get_seq(const dlsc_ctx* c) { return c ? c->seq : -1; }
+int dlsc_set_seq(dlsc_ctx* c, int seq) { if (!c) return fail("null ctx"); c->seq = seq; return 0; }
+
+static int d2h(dlsc_ctx* c, void* host, const void* dev, size_t bytes) {
+    if (!c || !host) return fail("null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dlsc_get_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.traj, (size_t)c->P.NL * c->P.M * kP * 12) : fail("null ctx"); }
+int dlsc_get_qp_x(dlsc_ctx* c, double* x) { return c ? d2h(c, x, c->S.qp_x, (size_t)c->P.NL * c->T.nx * 8) : fail("null ctx"); }
+int dlsc_get_cost(dlsc_ctx* c, double* v) { return c ? d2h(c, v, c->S.cost, (size_t)c->P.NL * 8) : fail("null ctx"); }
+int dlsc_get_violation(dlsc_ctx* c, double* v) { return c ? d2h(c, v, c->S.viol, (size_t)c->P.NL * 8) : fail("null ctx"); }
+int dlsc_get_qp_iters(dlsc_ctx* c, int32_t* v) { return c ? d2h(c, v, c->S.qp_iters, (size_t)c->P.NL * 4) : fail("null ctx"); }
+int dlsc_get_status(dlsc_ctx* c, int32_t* v) { return c ? d2h(c, v, c->S.status, (size_t)c->P.NL * 4) : fail("null ctx"); }
+int dlsc_get_init_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.init_traj, (size_t)c->P.NL * c->P.M * kP * 12) : fail("null ctx"); }
+int dlsc_get_pred_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.pred_traj, (size_t)c->P.N * c->P.M * kP * 12) : fail("null ctx"); }
+int dlsc_get_sfc(dlsc_ctx* c, float* s) { return c ? d2h(c, s, c->S.sfc, (size_t)c->P.NL * c->P.M * 24) : fail("null ctx"); }
+
+int dlsc_get_goal(dlsc_ctx* c, float* goal) {
+    if (!c || !goal) return fail("null argument");
+    CK(cudaSetDevice(c->device));
+    const DevParams& P = c->P;
+    CK(cudaMemcpy2DAsync(goal, 12, c->S.rec + (size_t)P.begin * P.rec + c->rl.goal, (size_t)P.rec * 4, 12, P.NL,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dlsc_get_state(dlsc_ctx* c, float* pos, float* vel, float* acc) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    const DevParams& P = c->P;
+    const float* rec0 = c->S.rec + (size_t)P.begin * P.rec + c->rl.pos;
+    if (pos) CK(cudaMemcpy2DAsync(pos, 12, rec0, (size_t)P.rec * 4, 12, P.NL, cudaMemcpyDeviceToHost, c->stream));
+    if (vel) CK(cudaMemcpy2DAsync(vel, 12, rec0 + 3, (size_t)P.rec * 4, 12, P.NL, cudaMemcpyDeviceToHost, c->stream));
+    if (acc) CK(cudaMemcpyAsync(acc, c->S.acc, (size_t)P.NL * 12, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dlsc_get_neighbours(dlsc_ctx* c, int32_t* idx, int32_t* cnt) {
+    if (!c) return fail("null ctx");
+    if (idx && d2h(c, idx, c->S.nbr_idx, (size_t)c->P.NL * c->P.K * 4)) return -1;
+    if (cnt && d2h(c, cnt, c->S.nbr_cnt, (size_t)c->P.NL * 4)) return -1;
+    return 0;
+}
+int dlsc_get_lsc(dlsc_ctx* c, float* normal, float* anchor, double* d) {
+    if (!c) return fail("null ctx");
+    const DevParams& P = c->P;
+    const size_t pairs = (size_t)P.NL * P.K;
+    if (normal && d2h(c, normal, c->S.lsc_normal, pairs * P.M * 12)) return -1;
+    if (d && d2h(c, d, c->S.lsc_d, pairs * P.M * kP * 8)) return -1;
+    if (anchor) {
+        float* tmp = nullptr;
+        const size_t bytes = pairs * P.M * kP * 12;
+        CK(cudaMalloc(&tmp, bytes));
+        launch_expand_anchor(P, c->S, tmp, c->stream);
+        c->launches++;
+        const int rc = d2h(c, anchor, tmp, bytes);
+        cudaFree(tmp);
+        if (rc) return -1;
+    }
+    return 0;
+}
+int dlsc_set_sfc(dlsc_ctx* c, const float* sfc, const uint8_t* init_flag) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    if (sfc) CK(cudaMemcpyAsync(c->S.sfc, sfc, (size_t)c->P.NL * c->P.M * 24, cudaMemcpyHostToDevice, c->stream));
+    if (init_flag) CK(cudaMemcpyAsync(c->S.sfc_init, init_flag, (size_t)c->P.NL, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dlsc_enable_timing(dlsc_ctx* c, int on) {
+    if (!c) return fail("null ctx");
+    c->timing = on != 0;
+    memset(c->t_ms, 0, sizeof(c->t_ms));
+    c->t_steps = 0;
+    return 0;
+}
+int dlsc_get_timings(dlsc_ctx* c, double ms[DLSC_N_STAGES], int* n_steps) {
+    if (!c || !ms) return fail("null argument");
+    for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = c->t_steps ? c->t_ms[i] / c->t_steps : 0.0;
+    if (n_steps) *n_steps = c->t_steps;
+    memset(c->t_ms, 0, sizeof(c->t_ms));
+    c->t_steps = 0;
+    return 0;
+}
+int64_t dlsc_launch_count(const dlsc_ctx* c) { return c ? c->launches : 0; }
+int dlsc_get_counters(dlsc_ctx* c, int64_t counters[8]) {
+    return c ? d2h(c, counters, c->S.counters, 8 * sizeof(int64_t)) : fail("null ctx");
+}
+float* dlsc_waypoint_device(dlsc_ctx* c) { return c ? c->S.waypoint : nullptr; }
+float* dlsc_traj_device(dlsc_ctx* c) { return c ? c->S.traj : nullptr; }
+
+}  // extern "C"

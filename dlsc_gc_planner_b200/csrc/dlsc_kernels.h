@@ -1,0 +1,54 @@
+// dlsc_kernels.h -- launch interface between the context (dlsc_api.cu) and the two kernel
+// translation units: dlsc_kernels_exact.cu (-fmad=false: bit-exact float32/float64 stages) and
+// dlsc_kernels_qp.cu (FP64 interior-point QP).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dlsc_qp_tables.h"
+#include "dlsc_types.h"
+
+namespace dlsc {
+
+// device arrays of one context (local block unless noted)
+struct DevState {
+    float* rec;                // [N][rec]  (all agents)
+    float* acc;                // [NL][3]
+    float* waypoint;           // [NL][3]
+    uint8_t* disturbed;        // [NL]
+    uint8_t* sfc_init;         // [NL]
+    double *radius, *downwash, *max_vel, *max_acc, *nominal_vel;   // [NL]
+    float* pred_traj;          // [N][M][P][3]
+    float* init_traj;          // [NL][M][P][3]
+    int32_t* nbr_idx;          // [NL][K]
+    int32_t* nbr_cnt;          // [NL]
+    float* lsc_normal;         // [NL][K][M][3]
+    double* lsc_d;             // [NL][K][M][P]
+    float* lsc_anchor_last;    // [NL][K][3]
+    float* sfc;                // [NL][M][6]
+    float* traj;               // [NL][M][P][3]  QP result (or failsafe)
+    double* qp_x;              // [NL][D][M][P]
+    double *cost, *viol;       // [NL]
+    int32_t *qp_iters, *status;
+    unsigned long long* counters;   // [8]
+    double* qp_scratch;        // [qp_ctas][qp_scratch_doubles]
+    int* qp_next;              // dynamic work counter
+    EdtDev edt;
+};
+
+struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; };
+
+void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
+void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);
+void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);
+void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st);
+void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st);
+void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st);
+void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st);
+void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);
+void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
+
+QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device);
+void launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);
+
+}  // namespace dlsc

@@ -1,0 +1,206 @@
+// dlsc_kernels_exact.cu -- sm_100a kernels of the bit-exact stages (compile with -fmad=false):
+//   k_predict      horizon shift / constant-velocity initial guess        thread per control point
+//   k_neighbours   comm-range neighbour list, built on device             warp per agent (ballot compaction)
+//   k_lsc          LSC separating planes: GJK hull-vs-origin + margins    thread per (agent, neighbour, segment)
+//   k_sfc          SFC greedy box expansion over the 16-byte EDT records  warp per agent (vote any)
+//   k_goal         intermediate goal line search (closed-form 1-var LP)   thread per agent
+//   k_advance      state step at t = dt + record refresh                  thread per agent
+// All arithmetic lives in dlsc_stages.cuh / dlsc_math.cuh.
+#include "dlsc_kernels.h"
+#include "dlsc_stages.cuh"
+
+namespace dlsc {
+
+// DevParams / DevState travel as __grid_constant__ kernel parameters (constant bank, ~0.8 KB).
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_predict(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, int seq) {
+    const int npt = P.M * kP;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.N * npt) return;
+    const int a = (int)(gid / npt), pt = (int)(gid - (long long)a * npt);
+    const float* rec = S.rec + (size_t)a * P.rec;
+    const int la = a - P.begin;
+    const bool local = la >= 0 && la < P.NL;
+    predict_point(P, rec, seq, pt, local ? (S.disturbed[la] != 0) : false, S.pred_traj + (size_t)a * npt * 3,
+                  local ? S.init_traj + (size_t)la * npt * 3 : nullptr);
+    if (local && pt == 0) S.status[la] = 0;
+}
+
+void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st) {
+    const long long n = (long long)P.N * P.M * kP;
+    k_predict<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, S, seq);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_neighbours(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= P.NL) return;
+    Group g; g.lane = threadIdx.x & 31; g.width = 32;
+    const int cnt = neighbours_agent(g, P, S.rec, P.begin + warp, S.nbr_idx + (size_t)warp * P.K);
+    if (g.lane == 0) {
+        S.nbr_cnt[warp] = cnt < P.K ? cnt : P.K;
+        if (cnt > P.K) atomicOr(S.status + warp, kStNbrOverflow);
+        atomicAdd(S.counters + 0, (unsigned long long)(cnt < P.K ? cnt : P.K));
+    }
+}
+
+void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
+    const int warps_per_block = 8;
+    k_neighbours<<<(P.NL + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(P, S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// thread per (agent, slot, segment): consecutive threads = consecutive segments of one pair, so a warp
+// covers ~3 pairs of the same agent (similar geometry -> similar GJK depth)
+__global__ void __launch_bounds__(128) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int M = P.M, npt = M * kP;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P.NL * P.K * M;
+    int it = 0;
+    if (gid < total) {
+        const int m = (int)(gid % M);
+        const long long pr = gid / M;
+        const int c = (int)(pr % P.K), la = (int)(pr / P.K);
+        if (c < S.nbr_cnt[la]) {
+            const int j = S.nbr_idx[(size_t)la * P.K + c];
+            const float* rec_a = S.rec + (size_t)(P.begin + la) * P.rec;
+            const float* rec_j = S.rec + (size_t)j * P.rec;
+            const int og = npt * 3 + 6;
+            lsc_segment(P, S.init_traj + (size_t)la * npt * 3, S.pred_traj + (size_t)j * npt * 3,
+                        v3_load(rec_a + og), v3_load(rec_j + og), S.radius[la], S.downwash[la], rec_j[og + 3],
+                        rec_j[og + 4], m, S.lsc_normal + ((size_t)pr * M + m) * 3,
+                        S.lsc_d + ((size_t)pr * M + m) * kP, S.lsc_anchor_last + (size_t)pr * 3, &it);
+        }
+    }
+    const int tot = __reduce_add_sync(0xffffffffu, it);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(S.counters + 1, (unsigned long long)tot);
+}
+
+void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
+    const long long n = (long long)P.NL * P.K * P.M;
+    k_lsc<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, S);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= P.NL) return;
+    Group g; g.lane = threadIdx.x & 31; g.width = 32;
+    const int la = warp, npt = P.M * kP;
+    const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    const bool init = S.sfc_init[la] != 0 || S.disturbed[la] != 0;       // traj_planner.cpp:439, 693-695
+    long long lookups = 0;
+    const int st = sfc_agent(g, P, S.edt, init, v3_load(rec + npt * 3), S.init_traj + (size_t)la * npt * 3,
+                             v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3), S.radius[la],
+                             S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &lookups);
+    if (g.lane == 0) {
+        S.sfc_init[la] = 0;
+        if (st) atomicOr(S.status + la, st);
+        atomicAdd(S.counters + 2, (unsigned long long)lookups);
+    }
+}
+
+void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st) {
+    const int warps_per_block = 4;
+    k_sfc<<<(P.NL + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(P, S);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_goal(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    if (la >= P.NL) return;
+    const int npt = P.M * kP;
+    float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    V3 goal = v3_load(rec + npt * 3 + 6);
+    const size_t pr = (size_t)la * P.K;
+    const int st = goal_agent(P, S.disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(S.waypoint + la * 3),
+                              S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.nbr_cnt[la],
+                              S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, goal);
+    v3_store(rec + npt * 3 + 6, goal);
+    if (st) atomicOr(S.status + la, st);
+}
+
+void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st) {
+    k_goal<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// move: state := traj(dt) (AgentManager::doStep); always: record.traj := traj (prev_traj, traj_planner.cpp:57)
+__global__ void __launch_bounds__(128) k_advance(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, int move) {
+    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    if (la >= P.NL) return;
+    const int npt = P.M * kP;
+    float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    const float* tr = S.traj + (size_t)la * npt * 3;
+    if (move) {
+        float st[9];
+        state_at(P, tr, P.dt, st);
+        for (int k = 0; k < 3; k++) { rec[npt * 3 + k] = st[k]; rec[npt * 3 + 3 + k] = st[3 + k]; S.acc[la * 3 + k] = st[6 + k]; }
+    }
+    for (int e = 0; e < npt * 3; e++) rec[e] = tr[e];
+}
+
+void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st) {
+    k_advance<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S, move ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell) return;
+    int4 r;
+    r.x = __float_as_int(dist[i]); r.y = obst[3 * i]; r.z = obst[3 * i + 1]; r.w = obst[3 * i + 2];
+    cells[i] = r;
+}
+void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st) {
+    k_edt_pack<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(dist, obst, cells, ncell);
+}
+
+// LSC anchors in the reference layout [NL][K][M][P][3]: predicted control points, or the segment-case
+// witness point for the last segment (traj_planner.cpp:638, 657)
+__global__ void k_expand_anchor(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, float* out) {
+    const int npt = P.M * kP;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P.NL * P.K * npt;
+    if (gid >= total) return;
+    const int pt = (int)(gid % npt);
+    const long long pr = gid / npt;
+    const int c = (int)(pr % P.K), la = (int)(pr / P.K);
+    float v[3] = {0.f, 0.f, 0.f};
+    if (c < S.nbr_cnt[la]) {
+        const int j = S.nbr_idx[(size_t)la * P.K + c];
+        const float* src = (pt / kP < P.M - 1) ? S.pred_traj + ((size_t)j * npt + pt) * 3 : S.lsc_anchor_last + (size_t)pr * 3;
+        v[0] = src[0]; v[1] = src[1]; v[2] = src[2];
+    }
+    out[gid * 3] = v[0]; out[gid * 3 + 1] = v[1]; out[gid * 3 + 2] = v[2];
+}
+void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st) {
+    const long long n = (long long)P.NL * P.K * P.M * kP;
+    k_expand_anchor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, S, anchor_out);
+}
+
+// planner state reset (agent_manager.cpp:4-32): record = {traj: start everywhere, pos = start, vel = 0,
+// goal = start, radius, downwash}; waypoint = start; acc = 0; initialize_sfc = true
+__global__ void k_reset(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, const float* start) {
+    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    if (la >= P.NL) return;
+    const int npt = P.M * kP;
+    float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    const float s0 = start[la * 3], s1 = start[la * 3 + 1], s2 = start[la * 3 + 2];
+    for (int e = 0; e < npt; e++) { rec[e * 3] = s0; rec[e * 3 + 1] = s1; rec[e * 3 + 2] = s2; }
+    const int o = npt * 3;
+    rec[o] = s0; rec[o + 1] = s1; rec[o + 2] = s2;
+    rec[o + 3] = 0.f; rec[o + 4] = 0.f; rec[o + 5] = 0.f;
+    rec[o + 6] = s0; rec[o + 7] = s1; rec[o + 8] = s2;
+    rec[o + 9] = (float)S.radius[la]; rec[o + 10] = (float)S.downwash[la];
+    for (int e = o + 11; e < P.rec; e++) rec[e] = 0.f;
+    for (int k = 0; k < 3; k++) { S.acc[la * 3 + k] = 0.f; S.waypoint[la * 3 + k] = start[la * 3 + k]; }
+    S.disturbed[la] = 0; S.sfc_init[la] = 1; S.status[la] = 0;
+    for (int e = 0; e < npt * 3; e++) S.traj[(size_t)la * npt * 3 + e] = rec[e];
+}
+void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st) {
+    k_reset<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S, start_dev);
+}
+
+}  // namespace dlsc

@@ -1,0 +1,80 @@
+// dlsc_kernels_qp.cu -- sm_100a kernel of the batched min-jerk QP (interior point, FP64 pipe).
+// Persistent CTAs: grid = SMs x resident CTAs, each CTA pulls agents from a device-side counter
+// (agents differ widely in neighbour count, hence in row count) and reuses one global scratch slab.
+#include "dlsc_kernels.h"
+#include "dlsc_qp.cuh"
+
+namespace dlsc {
+
+constexpr int kQpThreads = 128;
+constexpr int kQpGroup = 8;      // lanes cooperating on one control point in the LSC passes
+
+__global__ void __launch_bounds__(kQpThreads) k_qp(const __grid_constant__ DevParams P,
+                                                   const __grid_constant__ DevState S,
+                                                   const __grid_constant__ QpTab T, size_t scratch_doubles) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_agent;
+    QpSmem sm;
+    qp_smem_carve(T, P.K, smem, sm);
+    Cta c; c.tid = threadIdx.x; c.nthr = blockDim.x; c.red = sm.red;
+    double* scratch = S.qp_scratch + (size_t)blockIdx.x * scratch_doubles;
+    const int npt = P.M * kP;
+    unsigned long long it_sum = 0, row_sum = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_agent = atomicAdd(S.qp_next, 1);
+        __syncthreads();
+        const int la = s_agent;
+        __syncthreads();
+        if (la >= P.NL) break;
+        const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+        QpIn in;
+        in.pos = v3_load(rec + npt * 3); in.vel = v3_load(rec + npt * 3 + 3);
+        in.acc = v3_load(S.acc + la * 3); in.goal = v3_load(rec + npt * 3 + 6);
+        in.wp = v3_load(S.waypoint + la * 3);
+        in.radius = S.radius[la]; in.max_vel = S.max_vel[la]; in.max_acc = S.max_acc[la];
+        in.nominal_vel = S.nominal_vel[la];
+        in.sfc = S.sfc + (size_t)la * P.M * 6;
+        in.init_traj = S.init_traj + (size_t)la * npt * 3;
+        in.K = S.nbr_cnt[la];
+        const size_t pr = (size_t)la * P.K;
+        in.nbr_idx = S.nbr_idx + pr;
+        in.normal = S.lsc_normal + pr * P.M * 3;
+        in.d = S.lsc_d + pr * P.M * kP;
+        in.anchor_last = S.lsc_anchor_last + pr * 3;
+        in.pred_traj = S.pred_traj;
+        long long rows = 0;
+        QpOut out;
+        out.traj = S.traj + (size_t)la * npt * 3;
+        out.x = S.qp_x + (size_t)la * T.nx;
+        out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;
+        out.rows = (threadIdx.x == 0) ? &rows : nullptr;
+        qp_agent(c, kQpGroup, P, T, in, out, sm, scratch);
+        if (threadIdx.x == 0) { it_sum += (unsigned long long)S.qp_iters[la]; row_sum += (unsigned long long)rows; }
+    }
+    if (threadIdx.x == 0) {
+        if (it_sum) atomicAdd(S.counters + 3, it_sum);
+        if (row_sum) atomicAdd(S.counters + 4, row_sum);
+    }
+}
+
+QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
+    QpLaunch L;
+    L.threads = kQpThreads;
+    L.smem = qp_smem_bytes(T, P.K);
+    cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    int per_sm = 1, sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp, kQpThreads, L.smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (per_sm < 1) per_sm = 1;
+    L.ctas = sms * per_sm;
+    L.scratch_doubles = qp_scratch_doubles(T, P.K);
+    return L;
+}
+
+void launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st) {
+    cudaMemsetAsync(S.qp_next, 0, sizeof(int), st);
+    const int ctas = L.ctas < P.NL ? L.ctas : P.NL;
+    k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles);
+}
+
+}  // namespace dlsc

@@ -1,0 +1,622 @@
+// dlsc_qp.cuh -- batched piecewise-Bernstein min-jerk QP, one CTA per agent.
+//
+// Replaces TrajOptimizer::solve / populatebyrow + CPLEX (reference src/traj_optimizer.cpp:18-165,
+// 225-527).  Same problem, different machinery:
+//   * equality rows are eliminated analytically (dlsc_qp_tables.h) -> ny = D(3M-2) unknowns;
+//   * dense primal-dual interior point (Mehrotra predictor-corrector) on  min 1/2 y'Hy + g'y,  G y <= h;
+//   * the reduced KKT matrix  W = H + G' diag(z/s) G  (ny <= 128) lives in shared memory as a packed
+//     lower triangle, is assembled by table-driven gathers (no atomics), factorised in place as
+//     L D L' (one __syncthreads per column) and solved by one warp with register-resident right-hand
+//     sides and warp shuffles;  FP64 pipe, no tensor cores (systems of 39..84 unknowns).
+//   * row state (slack s, dual z, corrector term) of all inequality rows stays in a per-CTA global
+//     scratch slab that is reused for every agent the CTA processes (L1/L2 resident).
+//
+// The core is __host__ __device__: the device build runs it with a 128-thread CTA, the test-only host
+// simulator with a single "thread" (tests/hostsim), so the arithmetic can be checked without a GPU.
+#pragma once
+#include "dlsc_math.cuh"
+#include "dlsc_qp_tables.h"
+#include "dlsc_types.h"
+
+namespace dlsc {
+
+// ------------------------------------------------------------------------------------------------
+// CTA abstraction
+// ------------------------------------------------------------------------------------------------
+struct Cta {
+    int tid, nthr;
+    double* red;     // >= 3 * 32 doubles of shared scratch
+    DLSC_HD void sync() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
+    // op: 0 sum, 1 max, 2 min.  Deterministic (fixed tree).  All threads get the result.
+    DLSC_HD void reduce3(double& a, int opa, double& b, int opb, double& c, int opc) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ta = __shfl_xor_sync(0xffffffffu, a, o);
+            const double tb = __shfl_xor_sync(0xffffffffu, b, o);
+            const double tc = __shfl_xor_sync(0xffffffffu, c, o);
+            a = comb(a, ta, opa); b = comb(b, tb, opb); c = comb(c, tc, opc);
+        }
+        const int w = tid >> 5, nw = nthr >> 5;
+        __syncthreads();
+        if ((tid & 31) == 0) { red[w] = a; red[32 + w] = b; red[64 + w] = c; }
+        __syncthreads();
+        a = red[0]; b = red[32]; c = red[64];
+        for (int i = 1; i < nw; i++) { a = comb(a, red[i], opa); b = comb(b, red[32 + i], opb); c = comb(c, red[64 + i], opc); }
+#endif
+    }
+    static DLSC_HD double comb(double x, double y, int op) {
+        return op == 0 ? x + y : (op == 1 ? (x < y ? y : x) : (y < x ? y : x));
+    }
+};
+
+// sum over a group of G (power of two <= 32) adjacent lanes; every lane of the warp must call it
+DLSC_HD double group_sum(double v, int G) {
+#ifdef __CUDA_ARCH__
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-agent inputs / outputs
+// ------------------------------------------------------------------------------------------------
+struct QpIn {
+    V3 pos, vel, acc, goal, wp;
+    double radius, max_vel, max_acc, nominal_vel;
+    const float* sfc;          // [M][6]
+    const float* init_traj;    // [M][P][3]
+    int K;                     // neighbour count
+    const int32_t* nbr_idx;    // [K] global indices
+    const float* normal;       // [K][M][3]
+    const double* d;           // [K][M][P]
+    const float* anchor_last;  // [K][3]
+    const float* pred_traj;    // [N][M][P][3] (anchors of segments < M-1)
+};
+struct QpOut {
+    float* traj;               // [M][P][3]
+    double* x;                 // [D][M][P] or null
+    double* cost; double* viol; int32_t* iters; int32_t* status;
+    long long* rows;           // active inequality rows (one-sided count) or null
+};
+
+// shared-memory carve-up (doubles unless noted)
+struct QpSmem {
+    double *W, *invp, *y, *dy, *rd, *rhs, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
+    uint8_t* act;              // [M][Kcap]
+};
+DLSC_HD size_t qp_smem_doubles(const QpTab& T) {
+    return (size_t)T.ntri + 5 * (size_t)T.ny + 4 * (size_t)T.nx + 3 * (size_t)T.np + 6 * (size_t)T.npt + 16 + 96;
+}
+DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
+    return qp_smem_doubles(T) * sizeof(double) + (((size_t)T.M * Kcap + 15) / 16) * 16;
+}
+DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
+    double* p = base;
+    s.W = p; p += T.ntri;
+    s.invp = p; p += T.ny; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny; s.rhs = p; p += T.ny;
+    s.x = p; p += T.nx; s.dx = p; p += T.nx; s.ax1 = p; p += T.nx; s.ax2 = p; p += T.nx;
+    s.V1 = p; p += T.np; s.V2 = p; p += T.np; s.DD = p; p += T.np;
+    s.S = p; p += 6 * T.npt;
+    s.cst = p; p += 16;
+    s.red = p; p += 96;
+    s.act = reinterpret_cast<uint8_t*>(p);
+    (void)Kcap;
+}
+// per-CTA global scratch (doubles): LSC rows [npt][Kcap] x {s,z,corr,b,ds,dz} ; pair rows [np] x 12
+DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) { return 6 * (size_t)T.npt * Kcap + 12 * (size_t)T.np; }
+
+// ------------------------------------------------------------------------------------------------
+// L D L' of the packed lower triangle W (row-major: (i,k) at i(i+1)/2+k), in place.
+// After the call column j holds the unscaled entries Lt(i,j) = l_ij * d_j and invp[j] = 1/d_j.
+// Returns false (uniformly) when a pivot is not positive.
+// ------------------------------------------------------------------------------------------------
+DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, int ny) {
+    const int tx = c.tid & 15, ty = c.tid >> 4, nty = (c.nthr + 15) >> 4;
+    const int sx = (c.nthr >= 16) ? 16 : c.nthr;
+    for (int j = 0; j < ny; j++) {
+        const double piv = W[j * (j + 1) / 2 + j];
+        if (!(piv > 0)) return false;
+        const double ip = 1.0 / piv;
+        if (c.tid == 0) invp[j] = ip;
+        for (int i = j + 1 + ty; i < ny; i += nty) {
+            const int row = i * (i + 1) / 2;
+            const double lij = W[row + j] * ip;
+            for (int k = j + 1 + tx; k <= i; k += sx) W[row + k] -= lij * W[k * (k + 1) / 2 + j];
+        }
+        c.sync();
+    }
+    return true;
+}
+
+// Solve (L D L') w = b in place.  Device: warp 0 only (caller syncs before and after).
+DLSC_HD void ldl_solve(const Cta& c, const double* W, const double* invp, double* b, int ny) {
+#ifdef __CUDA_ARCH__
+    if (c.tid >= 32) return;
+    const int lane = c.tid;
+    double r0 = (lane < ny) ? b[lane] : 0.0, r1 = (lane + 32 < ny) ? b[lane + 32] : 0.0;
+    double r2 = (lane + 64 < ny) ? b[lane + 64] : 0.0, r3 = (lane + 96 < ny) ? b[lane + 96] : 0.0;
+    const int i0 = lane, i1 = lane + 32, i2 = lane + 64, i3 = lane + 96;
+    const int o0 = i0 * (i0 + 1) / 2, o1 = i1 * (i1 + 1) / 2, o2 = i2 * (i2 + 1) / 2, o3 = i3 * (i3 + 1) / 2;
+    // forward: z_i = r_i - sum_{j<i} Lt(i,j) invp_j z_j
+    for (int j = 0; j < ny; j++) {
+        const int src = j & 31, t = j >> 5;
+        const double zj = __shfl_sync(0xffffffffu, t == 0 ? r0 : (t == 1 ? r1 : (t == 2 ? r2 : r3)), src);
+        const double q = zj * invp[j];
+        if (i0 > j && i0 < ny) r0 -= W[o0 + j] * q;
+        if (i1 > j && i1 < ny) r1 -= W[o1 + j] * q;
+        if (i2 > j && i2 < ny) r2 -= W[o2 + j] * q;
+        if (i3 > j && i3 < ny) r3 -= W[o3 + j] * q;
+    }
+    // backward: w_i = invp_i (z_i - sum_{k>i} Lt(k,i) w_k)
+    for (int i = ny - 1; i >= 0; i--) {
+        const int src = i & 31, t = i >> 5;
+        const double ai = __shfl_sync(0xffffffffu, t == 0 ? r0 : (t == 1 ? r1 : (t == 2 ? r2 : r3)), src);
+        const double wi = ai * invp[i];
+        const int row = i * (i + 1) / 2;
+        if (i0 < i) r0 -= W[row + i0] * wi;
+        if (i1 < i) r1 -= W[row + i1] * wi;
+        if (i2 < i) r2 -= W[row + i2] * wi;
+        if (i3 < i) r3 -= W[row + i3] * wi;
+    }
+    if (i0 < ny) b[i0] = r0 * invp[i0];
+    if (i1 < ny) b[i1] = r1 * invp[i1];
+    if (i2 < ny) b[i2] = r2 * invp[i2];
+    if (i3 < ny) b[i3] = r3 * invp[i3];
+#else
+    for (int j = 0; j < ny; j++) {
+        const double q = b[j] * invp[j];
+        for (int i = j + 1; i < ny; i++) b[i] -= W[i * (i + 1) / 2 + j] * q;
+    }
+    for (int i = ny - 1; i >= 0; i--) {
+        const double wi = b[i] * invp[i];
+        for (int k = 0; k < i; k++) b[k] -= W[i * (i + 1) / 2 + k] * wi;
+    }
+    for (int i = 0; i < ny; i++) b[i] *= invp[i];
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// the solver
+// ------------------------------------------------------------------------------------------------
+DLSC_HD int sym_idx(int k, int kk) { return k >= kk ? k * (k + 1) / 2 + kk : kk * (kk + 1) / 2 + k; }
+
+// x = c + T y  (or dx = T dy when cst == nullptr)
+DLSC_HD void map_x(const Cta& c, const QpTab& T, const double* y, const double* cst, double* x) {
+    for (int e = c.tid; e < T.nx; e += c.nthr) {
+        const int k = e / T.npt, pt = e - k * T.npt;
+        double v = 0.0;
+        const int ci = T.xm_cidx[pt];
+        if (cst && ci >= 0) v = cst[k * 3 + ci];
+        const int nv = T.xm_nv[pt];
+        for (int t = 0; t < nv; t++) v += T.xm_coef[pt * 3 + t] * y[k * T.nyd + T.xm_idx[pt * 3 + t]];
+        x[e] = v;
+    }
+}
+
+// uy[p] = sum_{pair rows} coef V[row] + sum_{points} coef ax[k][pt]
+DLSC_HD double gather_y(const QpTab& T, int p, const double* V, const double* ax) {
+    double v = 0.0;
+    for (int e = T.yi_ptr[p]; e < T.yi_ptr[p + 1]; e++) v += T.yi_coef[e] * V[T.yi_row[e]];
+    const int k = p / T.nyd, a = p - k * T.nyd;
+    for (int e = T.yp_ptr[a]; e < T.yp_ptr[a + 1]; e++) v += T.yp_coef[e] * ax[k * T.npt + T.yp_pt[e]];
+    return v;
+}
+
+struct QpConst {
+    double hi_v, hi_a, hi_c, wpr;
+    int ts;
+};
+
+DLSC_HD void pair_bounds(const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, int r,
+                         double& lo, double& hi) {
+    const int fam = T.pr_fam[r], k = T.pr_axis[r];
+    if (fam == 0) {
+        const int pt = T.pr_pt[r], m = pt / kP, i = pt - m * kP;
+        hi = P.world_max[k]; lo = P.world_min[k];
+        if (P.use_sfc) {
+            const double bl = (double)in.sfc[m * 6 + k], bh = (double)in.sfc[m * 6 + 3 + k];
+            if (bl > lo) lo = bl;
+            if (bh < hi) hi = bh;
+        }
+        if (T.use_comm && i == kP - 1) {
+            const double w = (double)v3_get(in.wp, k);
+            if (w - qc.wpr > lo) lo = w - qc.wpr;
+            if (w + qc.wpr < hi) hi = w + qc.wpr;
+        }
+    } else if (fam == 1) { hi = qc.hi_v; lo = -qc.hi_v; }
+    else if (fam == 2) { hi = qc.hi_a; lo = -qc.hi_a; }
+    else { hi = qc.hi_c; lo = -qc.hi_c; }
+}
+
+DLSC_HD double pair_act(const QpTab& T, int r, const double* y, const double* cst) {
+    double v = 0.0;
+    const int nnz = T.pr_nnz[r];
+    for (int t = 0; t < nnz; t++) v += T.pr_val[r * 6 + t] * y[T.pr_idx[r * 6 + t]];
+    if (cst) {
+        const int k = T.pr_axis[r];
+        v += T.pr_cc[r * 3] * cst[k * 3] + T.pr_cc[r * 3 + 1] * cst[k * 3 + 1] + T.pr_cc[r * 3 + 2] * cst[k * 3 + 2];
+    }
+    return v;
+}
+
+// one agent.  G = lanes cooperating on one control point in the LSC passes (power of two, divides 32).
+struct LscRow { int pt, m, cc; size_t o; double nk[3]; double act, gd; };
+
+DLSC_HD void qp_agent(const Cta& c, int G, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
+                      const QpSmem& sm, double* scratch) {
+    const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, nx = T.nx, np = T.np, Kc = P.K;
+    const int K = in.K;
+    const int n = kP - 1;
+    const size_t LS = (size_t)npt * Kc;
+    double *lsc_s = scratch, *lsc_z = scratch + LS, *lsc_c = scratch + 2 * LS, *lsc_b = scratch + 3 * LS,
+           *lsc_ds = scratch + 4 * LS, *lsc_dz = scratch + 5 * LS;
+    double* pr = scratch + 6 * LS;
+    double *ps_hi = pr, *pz_hi = pr + np, *pc_hi = pr + 2 * np, *ps_lo = pr + 3 * np, *pz_lo = pr + 4 * np,
+           *pc_lo = pr + 5 * np, *pb_hi = pr + 6 * np, *pb_lo = pr + 7 * np, *pd_sh = pr + 8 * np,
+           *pd_zh = pr + 9 * np, *pd_sl = pr + 10 * np, *pd_zl = pr + 11 * np;
+    const int gid = c.tid / G, gl = c.tid - gid * G, ngr = c.nthr / G;
+
+    // visit every active LSC row once; f(row) gets the row activity -n.x and direction activity -n.dx
+    auto lsc_rows = [&](auto&& f) {
+        for (int base = 0; base < npt; base += ngr) {
+            const int pt = base + gid;
+            if (pt < npt && pt >= 3) {
+                const int m = pt / kP;
+                for (int cc = gl; cc < K; cc += G) {
+                    if (!sm.act[m * Kc + cc]) continue;
+                    const float* nr = in.normal + ((size_t)cc * M + m) * 3;
+                    LscRow r; r.pt = pt; r.m = m; r.cc = cc; r.o = (size_t)pt * Kc + cc;
+                    r.nk[0] = r.nk[1] = r.nk[2] = 0.0; r.act = 0.0; r.gd = 0.0;
+                    for (int k = 0; k < D; k++) {
+                        r.nk[k] = (double)nr[k];
+                        r.act -= r.nk[k] * sm.x[k * npt + pt];
+                        r.gd -= r.nk[k] * sm.dx[k * npt + pt];
+                    }
+                    f(r);
+                }
+            }
+        }
+    };
+
+    // ---- constants of this agent ----
+    QpConst qc;
+    qc.hi_v = in.max_vel; qc.hi_a = in.max_acc; qc.hi_c = 0.5 * P.comm_range - in.radius;
+    qc.wpr = 0.5 * P.comm_range - kEpsF;
+    {
+        const double ideal = v3_norm(in.goal - in.pos) / in.nominal_vel;              // traj_optimizer.cpp:543-551
+        int ts = (int)((M * P.dt - ideal + kEps) / P.dt);
+        if (ts < 1) ts = 1;
+        if (ts > M) ts = M;
+        qc.ts = ts;
+    }
+    for (int k = c.tid; k < D; k += c.nthr) {                                         // :335-352
+        const double c0 = (double)v3_get(in.pos, k);
+        const double c1 = c0 + (double)v3_get(in.vel, k) * P.dt / n;
+        const double c2 = (double)v3_get(in.acc, k) * P.dt * P.dt / (n * (n - 1)) + 2 * c1 - c0;
+        sm.cst[k * 3] = c0; sm.cst[k * 3 + 1] = c1; sm.cst[k * 3 + 2] = c2;
+    }
+    // active LSC (m, c) pairs: neighbour present and normal not ~0 (:422-424)
+    for (int e = c.tid; e < M * Kc; e += c.nthr) {
+        const int m = e / Kc, cc = e - m * Kc;
+        uint8_t a = 0;
+        if (cc < K) a = !(v3_norm(v3_load(in.normal + ((size_t)cc * M + m) * 3)) < kEpsF);
+        sm.act[e] = a;
+    }
+    for (int p = c.tid; p < ny; p += c.nthr) sm.y[p] = 0.0;
+    for (int e = c.tid; e < nx; e += c.nthr) sm.dx[e] = 0.0;
+    c.sync();
+
+    const double wT = P.w_terminal, wT2 = 2.0 * P.w_terminal;
+    auto grad_x = [&](const double* x, int e) -> double {       // d/dx of  w_u x'Qx + w_T (x_n - goal)^2
+        const int k = e / npt, pt = e - k * npt, m = pt / kP, i = pt - m * kP;
+        const double* xs = x + k * npt + m * kP;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < kP; j++) v += T.Q2[i * kP + j] * xs[j];
+        if (i == n && m >= M - qc.ts) v += wT2 * (xs[n] - (double)v3_get(in.goal, k));
+        return v;
+    };
+    // ---- g_inf: gradient of the objective at y = 0 ----
+    map_x(c, T, sm.y, sm.cst, sm.x);
+    c.sync();
+    for (int e = c.tid; e < nx; e += c.nthr) sm.ax1[e] = grad_x(sm.x, e);
+    for (int r = c.tid; r < np; r += c.nthr) sm.V1[r] = 0.0;
+    c.sync();
+    double g_inf = 0.0;
+    for (int p = c.tid; p < ny; p += c.nthr) { const double v = fabs(gather_y(T, p, sm.V1, sm.ax1)); if (v > g_inf) g_inf = v; }
+    { double d0 = 0.0, d1 = 0.0; c.reduce3(g_inf, 1, d0, 0, d1, 0); }
+
+    // ---- starting point: free control points of the initial trajectory ----
+    for (int p = c.tid; p < ny; p += c.nthr) {
+        const int k = p / nyd, a = p - k * nyd;
+        const int m = a / 3, j = (m == M - 1) ? 2 : a - 3 * m;
+        sm.y[p] = (double)in.init_traj[(m * kP + 3 + j) * 3 + k];
+    }
+    c.sync();
+    map_x(c, T, sm.y, sm.cst, sm.x);
+    c.sync();
+
+    // ---- rows: bounds, slack / dual initialisation ----
+    double n_rows = 0.0;
+    for (int r = c.tid; r < np; r += c.nthr) {
+        double lo, hi;
+        pair_bounds(P, T, in, qc, r, lo, hi);
+        const double act = pair_act(T, r, sm.y, sm.cst);
+        pb_hi[r] = hi; pb_lo[r] = lo;
+        double s = hi - act; if (s < 1e-2) s = 1e-2;
+        ps_hi[r] = s; pz_hi[r] = 1.0 / s * 1e-2;
+        s = act - lo; if (s < 1e-2) s = 1e-2;
+        ps_lo[r] = s; pz_lo[r] = 1.0 / s * 1e-2;
+        n_rows += 2.0;
+    }
+    lsc_rows([&](const LscRow& r) {
+        const int i = r.pt - r.m * kP;
+        const float* nr = in.normal + ((size_t)r.cc * M + r.m) * 3;
+        const float* an = (r.m < M - 1) ? in.pred_traj + ((size_t)in.nbr_idx[r.cc] * npt + r.pt) * 3
+                                        : in.anchor_last + r.cc * 3;
+        double b = -in.d[((size_t)r.cc * M + r.m) * kP + i];                          // -n.x <= -(n.anchor + d)
+        for (int k = 0; k < D; k++) b -= (double)nr[k] * (double)an[k];
+        double s = b - r.act; if (s < 1e-2) s = 1e-2;
+        lsc_b[r.o] = b; lsc_s[r.o] = s; lsc_z[r.o] = 1.0 / s * 1e-2;
+        n_rows += 1.0;
+    });
+    { double d0 = 0.0, d1 = 0.0; c.reduce3(n_rows, 0, d0, 0, d1, 0); }
+    if (out.rows && c.tid == 0) *out.rows = (long long)n_rows;
+    const double inv_rows = n_rows > 0 ? 1.0 / n_rows : 0.0;
+
+    int status = kStQpMaxIter;
+    int it = 0;
+    const int max_it = P.qp_max_iter;
+    for (it = 0; it < max_it; it++) {
+        // ================= pass 1: residuals, G'z, affine rhs, D = z/s =================
+        for (int e = c.tid; e < nx; e += c.nthr) { sm.ax1[e] = grad_x(sm.x, e); sm.ax2[e] = 0.0; }
+        c.sync();
+        double rp_inf = 0.0, mu = 0.0;
+        for (int r = c.tid; r < np; r += c.nthr) {
+            const double act = pair_act(T, r, sm.y, sm.cst);
+            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+            const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
+            rp_inf = fmax(rp_inf, fmax(fabs(rph), fabs(rpl)));
+            mu += sh * zh + sl * zl;
+            sm.V1[r] = zh - zl;
+            sm.V2[r] = (-(sh * zh) + zh * rph) / sh - (-(sl * zl) + zl * rpl) / sl;
+            sm.DD[r] = zh / sh + zl / sl;
+        }
+        for (int base = 0; base < npt; base += ngr) {
+            const int pt = base + gid;
+            const bool valid = pt < npt && pt >= 3;
+            double u1[3] = {0, 0, 0}, u2[3] = {0, 0, 0}, S[6] = {0, 0, 0, 0, 0, 0};
+            if (valid) {
+                const int m = pt / kP;
+                for (int cc = gl; cc < K; cc += G) {
+                    if (!sm.act[m * Kc + cc]) continue;
+                    const float* nr = in.normal + ((size_t)cc * M + m) * 3;
+                    const size_t o = (size_t)pt * Kc + cc;
+                    const double s = lsc_s[o], z = lsc_z[o];
+                    double nk[3] = {0, 0, 0}, act = 0.0;
+                    for (int k = 0; k < D; k++) { nk[k] = (double)nr[k]; act -= nk[k] * sm.x[k * npt + pt]; }
+                    const double rp = act + s - lsc_b[o];
+                    rp_inf = fmax(rp_inf, fabs(rp));
+                    mu += s * z;
+                    const double cv = (-(s * z) + z * rp) / s, dd = z / s;
+                    for (int k = 0; k < D; k++) { u1[k] -= nk[k] * z; u2[k] -= nk[k] * cv; }
+                    S[0] += dd * nk[0] * nk[0]; S[1] += dd * nk[1] * nk[0]; S[2] += dd * nk[1] * nk[1];
+                    S[3] += dd * nk[2] * nk[0]; S[4] += dd * nk[2] * nk[1]; S[5] += dd * nk[2] * nk[2];
+                }
+            }
+            for (int k = 0; k < 3; k++) { u1[k] = group_sum(u1[k], G); u2[k] = group_sum(u2[k], G); }
+            for (int q = 0; q < 6; q++) S[q] = group_sum(S[q], G);
+            if (valid && gl == 0) {
+                for (int k = 0; k < D; k++) { sm.ax1[k * npt + pt] += u1[k]; sm.ax2[k * npt + pt] += u2[k]; }
+                for (int q = 0; q < 6; q++) sm.S[pt * 6 + q] = S[q];
+            }
+        }
+        for (int e = c.tid; e < 18; e += c.nthr) sm.S[e] = 0.0;   // points 0..2 of segment 0 carry no rows
+        c.sync();
+        double rd_inf = 0.0;
+        for (int p = c.tid; p < ny; p += c.nthr) {
+            const double r1 = gather_y(T, p, sm.V1, sm.ax1);
+            const double r2 = gather_y(T, p, sm.V2, sm.ax2);
+            sm.rd[p] = r1;
+            sm.dy[p] = -r1 - r2;
+            rd_inf = fmax(rd_inf, fabs(r1));
+        }
+        c.reduce3(rp_inf, 1, mu, 0, rd_inf, 1);
+        mu *= inv_rows;
+#if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
+        printf("it %d rp %.3e rd %.3e mu %.3e ginf %.3e rows %.0f\n", it, rp_inf, rd_inf, mu, g_inf, n_rows);
+#endif
+        if (rp_inf <= kQpTolRp && rd_inf <= kQpTolRd * (1.0 + g_inf) && mu <= kQpTolMu) { status = 0; break; }
+
+        // ================= W = H + G' D G  (packed lower triangle) =================
+        for (int e = c.tid; e < T.ntri; e += c.nthr) {
+            int p = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);       // e -> (p, q), p >= q
+            while (p * (p + 1) / 2 > e) p--;
+            while ((p + 1) * (p + 2) / 2 <= e) p++;
+            const int q = e - p * (p + 1) / 2;
+            const int k = p / nyd, a = p - k * nyd, kk = q / nyd, b = q - kk * nyd;
+            double v = 0.0;
+            if (k == kk) {
+                v = T.H1[a * nyd + b];
+                if (a == b) {
+                    const int m = a / 3;
+                    if ((m == M - 1 || a - 3 * m == 2) && m >= M - qc.ts) v += wT2;
+                }
+                for (int t = T.wi_ptr[e]; t < T.wi_ptr[e + 1]; t++) v += T.wi_coef[t] * sm.DD[T.wi_row[t]];
+            }
+            const int el = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
+            const int si = sym_idx(k, kk);
+            for (int t = T.wp_ptr[el]; t < T.wp_ptr[el + 1]; t++) v += T.wp_coef[t] * sm.S[T.wp_pt[t] * 6 + si];
+            sm.W[e] = v;
+        }
+        c.sync();
+        if (!ldl_factor(c, sm.W, sm.invp, ny)) { status = kStQpNumeric; break; }
+
+        // ================= predictor =================
+        ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
+        c.sync();
+        map_x(c, T, sm.dy, nullptr, sm.dx);
+        c.sync();
+        double a_aff = 1.0;
+        for (int r = c.tid; r < np; r += c.nthr) {
+            const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
+            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+            const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
+            const double dzh = (-(sh * zh) - zh * dsh) / sh, dzl = (-(sl * zl) - zl * dsl) / sl;
+            if (dsh < 0) a_aff = fmin(a_aff, -sh / dsh);
+            if (dzh < 0) a_aff = fmin(a_aff, -zh / dzh);
+            if (dsl < 0) a_aff = fmin(a_aff, -sl / dsl);
+            if (dzl < 0) a_aff = fmin(a_aff, -zl / dzl);
+            pd_sh[r] = dsh; pd_zh[r] = dzh; pd_sl[r] = dsl; pd_zl[r] = dzl;
+        }
+        lsc_rows([&](const LscRow& r) {
+            const double s = lsc_s[r.o], z = lsc_z[r.o];
+            const double ds = -(r.act + s - lsc_b[r.o]) - r.gd;
+            const double dz = (-(s * z) - z * ds) / s;
+            if (ds < 0) a_aff = fmin(a_aff, -s / ds);
+            if (dz < 0) a_aff = fmin(a_aff, -z / dz);
+            lsc_ds[r.o] = ds; lsc_dz[r.o] = dz;
+        });
+        { double d0 = 0.0, d1 = 0.0; c.reduce3(a_aff, 2, d0, 0, d1, 0); }
+        double mu_aff = 0.0;
+        for (int r = c.tid; r < np; r += c.nthr) {
+            const double dsh = pd_sh[r], dzh = pd_zh[r], dsl = pd_sl[r], dzl = pd_zl[r];
+            mu_aff += (ps_hi[r] + a_aff * dsh) * (pz_hi[r] + a_aff * dzh) + (ps_lo[r] + a_aff * dsl) * (pz_lo[r] + a_aff * dzl);
+            pc_hi[r] = dsh * dzh; pc_lo[r] = dsl * dzl;
+        }
+        lsc_rows([&](const LscRow& r) {
+            const double ds = lsc_ds[r.o], dz = lsc_dz[r.o];
+            mu_aff += (lsc_s[r.o] + a_aff * ds) * (lsc_z[r.o] + a_aff * dz);
+            lsc_c[r.o] = ds * dz;
+        });
+        { double d0 = 0.0, d1 = 0.0; c.reduce3(mu_aff, 0, d0, 0, d1, 0); }
+        mu_aff *= inv_rows;
+        const double ratio = mu > 0 ? mu_aff / mu : 0.0;
+        const double sig_mu = ratio * ratio * ratio * mu;
+
+        // ================= corrector =================
+        for (int e = c.tid; e < nx; e += c.nthr) sm.ax2[e] = 0.0;
+        c.sync();
+        for (int r = c.tid; r < np; r += c.nthr) {
+            const double act = pair_act(T, r, sm.y, sm.cst);
+            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+            const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
+            const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
+            sm.V2[r] = (-rch + zh * rph) / sh - (-rcl + zl * rpl) / sl;
+        }
+        for (int base = 0; base < npt; base += ngr) {
+            const int pt = base + gid;
+            const bool valid = pt < npt && pt >= 3;
+            double u2[3] = {0, 0, 0};
+            if (valid) {
+                const int m = pt / kP;
+                for (int cc = gl; cc < K; cc += G) {
+                    if (!sm.act[m * Kc + cc]) continue;
+                    const float* nr = in.normal + ((size_t)cc * M + m) * 3;
+                    const size_t o = (size_t)pt * Kc + cc;
+                    const double s = lsc_s[o], z = lsc_z[o];
+                    double nk[3] = {0, 0, 0}, act = 0.0;
+                    for (int k = 0; k < D; k++) { nk[k] = (double)nr[k]; act -= nk[k] * sm.x[k * npt + pt]; }
+                    const double rp = act + s - lsc_b[o];
+                    const double rc = s * z + lsc_c[o] - sig_mu;
+                    const double cv = (-rc + z * rp) / s;
+                    for (int k = 0; k < D; k++) u2[k] -= nk[k] * cv;
+                }
+            }
+            for (int k = 0; k < 3; k++) u2[k] = group_sum(u2[k], G);
+            if (valid && gl == 0)
+                for (int k = 0; k < D; k++) sm.ax2[k * npt + pt] += u2[k];
+        }
+        c.sync();
+        for (int p = c.tid; p < ny; p += c.nthr) sm.dy[p] = -sm.rd[p] - gather_y(T, p, sm.V2, sm.ax2);
+        c.sync();
+        ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
+        c.sync();
+        map_x(c, T, sm.dy, nullptr, sm.dx);
+        c.sync();
+        double a_st = 1.0;
+        for (int r = c.tid; r < np; r += c.nthr) {
+            const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
+            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+            const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
+            const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
+            const double dzh = (-rch - zh * dsh) / sh, dzl = (-rcl - zl * dsl) / sl;
+            if (dsh < 0) a_st = fmin(a_st, -sh / dsh);
+            if (dzh < 0) a_st = fmin(a_st, -zh / dzh);
+            if (dsl < 0) a_st = fmin(a_st, -sl / dsl);
+            if (dzl < 0) a_st = fmin(a_st, -zl / dzl);
+            pd_sh[r] = dsh; pd_zh[r] = dzh; pd_sl[r] = dsl; pd_zl[r] = dzl;
+        }
+        lsc_rows([&](const LscRow& r) {
+            const double s = lsc_s[r.o], z = lsc_z[r.o];
+            const double rc = s * z + lsc_c[r.o] - sig_mu;
+            const double ds = -(r.act + s - lsc_b[r.o]) - r.gd;
+            const double dz = (-rc - z * ds) / s;
+            if (ds < 0) a_st = fmin(a_st, -s / ds);
+            if (dz < 0) a_st = fmin(a_st, -z / dz);
+            lsc_ds[r.o] = ds; lsc_dz[r.o] = dz;
+        });
+        { double d0 = 0.0, d1 = 0.0; c.reduce3(a_st, 2, d0, 0, d1, 0); }
+        a_st = fmin(1.0, 0.995 * a_st);
+#if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
+        printf("      a_aff %.3e mu_aff %.3e sig_mu %.3e a %.3e\n", a_aff, mu_aff, sig_mu, a_st);
+#endif
+        // ================= update =================
+        for (int r = c.tid; r < np; r += c.nthr) {
+            ps_hi[r] += a_st * pd_sh[r]; pz_hi[r] += a_st * pd_zh[r];
+            ps_lo[r] += a_st * pd_sl[r]; pz_lo[r] += a_st * pd_zl[r];
+        }
+        lsc_rows([&](const LscRow& r) {
+            lsc_s[r.o] += a_st * lsc_ds[r.o];
+            lsc_z[r.o] += a_st * lsc_dz[r.o];
+        });
+        for (int p = c.tid; p < ny; p += c.nthr) sm.y[p] += a_st * sm.dy[p];
+        c.sync();
+        map_x(c, T, sm.y, sm.cst, sm.x);
+        c.sync();
+    }
+
+    // ---- outputs: objective in x-space (constant included, like IloCplex::getObjValue :109) ----
+    double obj = 0.0, viol = 0.0;
+    for (int e = c.tid; e < nx; e += c.nthr) {
+        const int k = e / npt, pt = e - k * npt, m = pt / kP, i = pt - m * kP;
+        const double* xs = sm.x + k * npt + m * kP;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < kP; j++) v += T.Q2[i * kP + j] * xs[j];
+        obj += 0.5 * v * xs[i];
+        if (i == n && m >= M - qc.ts) {
+            const double g = (double)v3_get(in.goal, k);
+            obj += wT * xs[n] * xs[n] - wT2 * g * xs[n] + wT * g * g;
+        }
+    }
+    for (int r = c.tid; r < np; r += c.nthr) {
+        const double act = pair_act(T, r, sm.y, sm.cst);
+        viol = fmax(viol, fmax(act - pb_hi[r], pb_lo[r] - act));
+    }
+    lsc_rows([&](const LscRow& r) { viol = fmax(viol, r.act - lsc_b[r.o]); });
+    { double d1 = 0.0; c.reduce3(obj, 0, viol, 1, d1, 0); }
+    if (c.tid == 0) {
+        *out.cost = obj; *out.viol = viol; *out.iters = it; *out.status |= status;
+    }
+    const bool ok = (status == 0);
+    for (int e = c.tid; e < npt; e += c.nthr) {
+        float* o = out.traj + e * 3;
+        if (ok) {                                                                     // :71-83
+            o[0] = (float)sm.x[e]; o[1] = (float)sm.x[npt + e];
+            o[2] = (D == 3) ? (float)sm.x[2 * npt + e] : (float)P.z_2d;
+        } else {                                                                      // failsafe traj_planner.cpp:775-776
+            o[0] = in.init_traj[e * 3]; o[1] = in.init_traj[e * 3 + 1]; o[2] = in.init_traj[e * 3 + 2];
+        }
+    }
+    if (out.x)
+        for (int e = c.tid; e < nx; e += c.nthr) out.x[e] = sm.x[e];
+    c.sync();
+}
+
+}  // namespace dlsc

@@ -1,0 +1,484 @@
+// dlsc_stages.cuh -- per-agent / per-pair cores of the "exact" stages of the replan hot path:
+// horizon shift, neighbour list, LSC, SFC box expansion, goal line search, state step.
+//
+// The cores are __host__ __device__ so that the same source runs (a) inside the sm_100a kernels
+// of dlsc_kernels_exact.cu and (b) in the test-only host simulator (tests/hostsim), which lets
+// the arithmetic be checked against the oracle without a GPU.  Cooperative cores take a Group
+// (one warp on the device, a single lane on the host).
+//
+// Must be compiled with FMA contraction off (-fmad=false / -ffp-contract=off).
+#pragma once
+#include "dlsc_math.cuh"
+#include "dlsc_types.h"
+
+namespace dlsc {
+
+// ------------------------------------------------------------------------------------------------
+// cooperative group abstraction: a warp on the device, one lane in the host simulator
+// ------------------------------------------------------------------------------------------------
+struct Group {
+    int lane, width;
+    DLSC_HD bool any(bool p) const {
+#ifdef __CUDA_ARCH__
+        return __any_sync(0xffffffffu, p) != 0;
+#else
+        return p;
+#endif
+    }
+    DLSC_HD unsigned ballot(bool p) const {
+#ifdef __CUDA_ARCH__
+        return __ballot_sync(0xffffffffu, p);
+#else
+        return p ? 1u : 0u;
+#endif
+    }
+};
+DLSC_HD int popc_u32(unsigned v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// horizon shift (traj_planner.cpp:290-336, 409-441 ; trajectory.cpp:79-91)
+// one call = one control point `pt` (= m*P + i) of one agent
+// ------------------------------------------------------------------------------------------------
+DLSC_HD V3 shifted_point(const DevParams& P, const float* rec, int seq, int pt) {
+    const V3 pos = v3_load(rec + P.M * kP * 3), vel = v3_load(rec + P.M * kP * 3 + 3);
+    if (seq < 2) return pos + vel * P.tk[pt];                                  // planConstVelTraj
+    const int m = pt / kP, i = pt - m * kP;
+    const int src = (m == P.M - 1) ? ((P.M - 1) * kP + (kP - 1)) : ((m + 1) * kP + i);   // :304-314
+    return v3_load(rec + src * 3);
+}
+
+// pred: how the other agents see this one (checkObstacleDisturbance :329-336)
+// init: the agent's own initial trajectory (initialTrajPlanningCheck :435-441)
+DLSC_HD void predict_point(const DevParams& P, const float* rec, int seq, int pt, bool disturbed,
+                           float* pred_out, float* init_out) {
+    const V3 pos = v3_load(rec + P.M * kP * 3);
+    const V3 q = shifted_point(P, rec, seq, pt);
+    const V3 first = shifted_point(P, rec, seq, 0);
+    const bool reset = v3_norm(first - pos) > P.reset_threshold;
+    if (pred_out) v3_store(pred_out + pt * 3, reset ? (pos + v3(0.f, 0.f, 0.f) * P.tk[pt]) : q);
+    if (init_out) v3_store(init_out + pt * 3, disturbed ? (pos + v3(0.f, 0.f, 0.f) * P.tk[pt]) : q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbour list by Chebyshev range, ascending index (multi_sync_simulator.cpp:481-503)
+// ------------------------------------------------------------------------------------------------
+DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* rec, int a_global,
+                             int32_t* idx_out) {
+    const int off = P.M * kP * 3;
+    const V3 pa = v3_load(rec + (size_t)a_global * P.rec + off);
+    int count = 0;
+    for (int base = 0; base < P.N; base += g.width) {
+        const int j = base + g.lane;
+        bool in = false;
+        if (j < P.N && j != a_global) {
+            const double dist = linf_distance(pa, v3_load(rec + (size_t)j * P.rec + off));
+            in = !(P.comm_range > 0 && dist > P.comm_range);
+        }
+        const unsigned mask = g.ballot(in);
+        const int pos = count + popc_u32(mask & ((1u << g.lane) - 1u));
+        if (in && pos < P.K) idx_out[pos] = j;
+        count += popc_u32(mask);
+    }
+    return count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSC for one (agent, neighbour, segment) -- traj_planner.cpp:603-666, 1102-1127, 1150-1161
+//   init_a : own initial trajectory [M][P][3], pred_j : neighbour's predicted trajectory
+//   r_j / dw_j arrive as float (agent_manager.cpp:256-258)
+//   normal_out[3], d_out[P]; anchor_last_out[3] written only for m == M-1
+// ------------------------------------------------------------------------------------------------
+DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* pred_j, const V3& goal_a,
+                         const V3& goal_j, double r_a, double dw_a, float r_j_f, float dw_j_f, int m,
+                         float* normal_out, double* d_out, float* anchor_last_out, int* gjk_iters) {
+    const double r_j = (double)r_j_f, dw_j = (double)dw_j_f;
+    const double collision_dist = r_j + r_a;                                   // :605
+    const double downwash = (dw_a * r_a + dw_j * r_j) / (r_a + r_j);           // :1153-1154
+    const float dwf = (float)downwash;                                         // trajectory.cpp:214
+    if (m < P.M - 1) {
+        V3 rel[kP];
+        gjk::D3 c[kP];
+#pragma unroll
+        for (int i = 0; i < kP; i++) {
+            V3 a = v3_load(init_a + (m * kP + i) * 3); a.z = a.z / dwf;
+            V3 b = v3_load(pred_j + (m * kP + i) * 3); b.z = b.z / dwf;
+            rel[i] = a - b;
+            c[i] = gjk::d3((double)rel[i].x, (double)rel[i].y, (double)rel[i].z);   // util.hpp:113-125
+        }
+        int it = 0;
+        const gjk::D3 v = gjk::hull_origin<kP>(c, &it);
+        if (gjk_iters) *gjk_iters = it;
+        const V3 cp2 = v3(0.f, 0.f, 0.f) + v3((float)v.x, (float)v.y, (float)v.z);   // geometry.hpp:302
+        const V3 nt = v3_normalized(cp2);                                             // :1118
+        normal_out[0] = nt.x; normal_out[1] = nt.y;
+        normal_out[2] = (float)((double)nt.z / downwash);                             // :630-632
+#pragma unroll
+        for (int i = 0; i < kP; i++) d_out[i] = 0.5 * (collision_dist + v3_dot(rel[i], nt));   // :636-637
+    } else {
+        const int last = (P.M - 1) * kP + (kP - 1);
+        V3 o_last = v3_load(pred_j + last * 3); o_last.z = o_last.z / dwf;
+        V3 a_last = v3_load(init_a + last * 3); a_last.z = a_last.z / dwf;
+        V3 og = goal_j; og.z = (float)((double)og.z / downwash);                      // :1183-1187
+        V3 ag = goal_a; ag.z = (float)((double)ag.z / downwash);
+        const Closest cp = closest_segments(o_last, og, a_last, ag);                  // :642-644
+        const V3 nt = v3_normalized(cp.p2 - cp.p1);
+        const double dd = 0.5 * (collision_dist + cp.dist);                           // :650
+        normal_out[0] = nt.x; normal_out[1] = nt.y;
+        normal_out[2] = (float)((double)nt.z / downwash);
+        anchor_last_out[0] = cp.p1.x; anchor_last_out[1] = cp.p1.y;
+        anchor_last_out[2] = (float)((double)cp.p1.z * downwash);                     // :657
+#pragma unroll
+        for (int i = 0; i < kP; i++) d_out[i] = dd;
+        if (gjk_iters) *gjk_iters = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SFC -- collision_constraints.cpp:435-452, 502-536, 781-901, 1023-1093
+// ------------------------------------------------------------------------------------------------
+struct Box { V3 lo, hi; };
+DLSC_HD Box box_load(const float* s) { Box b; b.lo = v3_load(s); b.hi = v3_load(s + 3); return b; }
+DLSC_HD void box_store(float* s, const Box& b) { v3_store(s, b.lo); v3_store(s + 3, b.hi); }
+
+DLSC_HD bool point_in_box(const Box& b, const V3& q) {     // collision_constraints.cpp:109-116
+    return q.x > b.lo.x - kEpsF && q.y > b.lo.y - kEpsF && q.z > b.lo.z - kEpsF &&
+           q.x < b.hi.x + kEpsF && q.y < b.hi.y + kEpsF && q.z < b.hi.z + kEpsF;
+}
+DLSC_HD bool box_includes(const Box& b, const Box& o) { return point_in_box(b, o.lo) && point_in_box(b, o.hi); }
+DLSC_HD bool superset_of_hull(const Box& b, const V3* pts, int np) {   // :163-178
+    for (int i = 0; i < 3; i++) {
+        float mn = v3_get(pts[0], i), mx = mn;
+        for (int k = 1; k < np; k++) {
+            const float c = v3_get(pts[k], i);
+            mn = (c < mn) ? c : mn;
+            mx = (mx < c) ? c : mx;
+        }
+        if (mn < v3_get(b.lo, i) - kEpsF || mx > v3_get(b.hi, i) + kEpsF) return false;
+    }
+    return true;
+}
+
+// DynamicEDTOctomap::getDistanceAndClosestObstacle + the per-vertex test of isObstacleInSFC (:876-886)
+DLSC_HD bool vertex_blocked(const EdtDev& E, const V3& q, double margin, float half_res) {
+    const int cx = (int)floor(E.inv_res * (double)q.x) - E.min_key[0];
+    const int cy = (int)floor(E.inv_res * (double)q.y) - E.min_key[1];
+    const int cz = (int)floor(E.inv_res * (double)q.z) - E.min_key[2];
+    float dist = -1.0f;
+    V3 cl = v3(0.f, 0.f, 0.f);
+    if (cx >= 0 && cx < E.dims[0] && cy >= 0 && cy < E.dims[1] && cz >= 0 && cz < E.dims[2]) {
+        const size_t idx = ((size_t)cx * E.dims[1] + cy) * E.dims[2] + cz;
+#ifdef __CUDA_ARCH__
+        const int4 rec = __ldg(E.cells + idx);
+#else
+        const int4 rec = E.cells[idx];
+#endif
+#ifdef __CUDA_ARCH__
+        dist = __int_as_float(rec.x);
+#else
+        { union { int i; float f; } u; u.i = rec.x; dist = u.f; }
+#endif
+        if (rec.y >= 0) {
+            cl.x = (float)(((double)(rec.y + E.min_key[0]) + 0.5) * E.res);
+            cl.y = (float)(((double)(rec.z + E.min_key[1]) + 0.5) * E.res);
+            cl.z = (float)(((double)(rec.w + E.min_key[2]) + 0.5) * E.res);
+        }
+    }
+    if (!(dist < 1)) return false;
+    const V3 d3v = v3(half_res, half_res, half_res);
+    const V3 lo = cl - d3v, hi = cl + d3v;
+    V3 cq = q;                                                  // Box::closestPoint :226-237
+    if (q.x < lo.x) cq.x = lo.x; else if (q.x > hi.x) cq.x = hi.x;
+    if (q.y < lo.y) cq.y = lo.y; else if (q.y > hi.y) cq.y = hi.y;
+    if (q.z < lo.z) cq.z = lo.z; else if (q.z > hi.z) cq.z = hi.z;
+    return linf_distance(cq, q) < margin + kEpsF;
+}
+
+// isObstacleInSFC (:862-892): any lattice vertex of the box blocked?
+DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
+                             long long* lookups) {
+    const double res = P.world_res;
+    const float half_res = (float)(0.5 * res);
+    const int m0 = (int)floor(((b.hi.x - b.lo.x) + kEpsF) / res) + 1;
+    const int m1 = (int)floor(((b.hi.y - b.lo.y) + kEpsF) / res) + 1;
+    const int m2 = (int)floor(((b.hi.z - b.lo.z) + kEpsF) / res) + 1;
+    if (m0 <= 0 || m1 <= 0 || m2 <= 0) return false;
+    const int total = m0 * m1 * m2;
+    for (int base = 0; base < total; base += g.width) {
+        const int idx = base + g.lane;
+        bool hit = false;
+        if (idx < total) {
+            const int iz = idx % m2, t = idx / m2;
+            const int iy = t % m1, ix = t / m1;
+            const V3 q = v3((float)(b.lo.x + ix * res), (float)(b.lo.y + iy * res), (float)(b.lo.z + iz * res));
+            hit = vertex_blocked(E, q, margin, half_res);
+        }
+        if (lookups) *lookups += (total - base < g.width) ? (total - base) : g.width;
+        if (g.any(hit)) return true;
+    }
+    return false;
+}
+
+// isSFCInBoundary (:894-901), margin 0 at the only call site
+DLSC_HD bool box_in_boundary(const DevParams& P, const Box& b) {
+    for (int k = 0; k < 3; k++) {
+        if (!(v3_get(b.lo, k) > P.world_min[k] + 0.0 - kEpsF)) return false;
+        if (!(v3_get(b.hi, k) < P.world_max[k] - 0.0 + kEpsF)) return false;
+    }
+    return true;
+}
+
+// expandSFCIncrementally (:1023-1093)
+DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtDev& E, const Box& init,
+                                  double margin, double max_vel, Box& out, long long* lookups) {
+    const double res = P.world_res;
+    if (obstacle_in_box(g, P, E, init, margin, lookups)) return false;
+    int axes = 0x543210;              // packed axis list, 4 bits each: -x -y -z +x +y +z
+    int n_axes = 6;
+    int iters[6] = {0, 0, 0, 0, 0, 0};
+    const double span = (2 * P.grid_res < max_vel * P.dt) ? max_vel * P.dt : 2 * P.grid_res;
+    const int max_iter = (int)round(span / res) + 1;
+    int i = -1;
+    Box sfc = init, cand = init, upd = init;
+    while (n_axes > 0) {
+        cand = sfc; upd = sfc;
+        while (box_in_boundary(P, upd) && !obstacle_in_box(g, P, E, upd, margin, lookups)) {
+            i++;
+            if (i >= n_axes) i = 0;
+            const int ax = (axes >> (4 * i)) & 0xf;
+            sfc = cand; upd = cand;
+            if (ax < 3) {
+                v3_set(upd.hi, ax, v3_get(cand.lo, ax));
+                v3_set(cand.lo, ax, (float)(v3_get(cand.lo, ax) - res));
+                v3_set(upd.lo, ax, v3_get(cand.lo, ax));
+            } else {
+                v3_set(upd.lo, ax - 3, v3_get(cand.hi, ax - 3));
+                v3_set(cand.hi, ax - 3, (float)(v3_get(cand.hi, ax - 3) + res));
+                v3_set(upd.hi, ax - 3, v3_get(cand.hi, ax - 3));
+            }
+            bool over = false;
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (t == ax) { iters[t]++; over = iters[t] > max_iter; }
+            if (over) break;
+        }
+        if (i < 0) return false;      // start box outside the world (the reference would erase begin()-1)
+        // erase axes[i]
+        const int low = axes & ((1 << (4 * i)) - 1);
+        const int high = (axes >> (4 * (i + 1))) << (4 * i);
+        axes = low | high;
+        n_axes--;
+        if (i > 0) i--; else i = n_axes - 1;
+    }
+    const double delta = margin - ((int)(margin / res) * res);     // :1081
+    for (int k = 0; k < 3; k++) {
+        if (v3_get(sfc.lo, k) > P.world_min[k] + kEpsF) v3_set(sfc.lo, k, (float)(v3_get(sfc.lo, k) - delta));
+        if (v3_get(sfc.hi, k) < P.world_max[k] - kEpsF) v3_set(sfc.hi, k, (float)(v3_get(sfc.hi, k) + delta));
+    }
+    out = sfc;
+    return true;
+}
+
+DLSC_HD Box hull_aabb(const V3* pts, int np) {
+    Box b; b.lo = pts[0]; b.hi = pts[0];
+    for (int t = 0; t < np; t++)
+        for (int k = 0; k < 3; k++) {
+            const float c = v3_get(pts[t], k);
+            if (c < v3_get(b.lo, k)) v3_set(b.lo, k, c);
+            if (c > v3_get(b.hi, k)) v3_set(b.hi, k, c);
+        }
+    return b;
+}
+
+// One agent's SFC update (init: :435-452 ; else :502-536 with the two expandSFCFromConvexHull overloads
+// :781-860).  sfc [M][6] in/out.  Returns status bits.
+DLSC_HD int sfc_agent(const Group& g, const DevParams& P, const EdtDev& E, bool init, const V3& pos,
+                      const float* init_traj, const V3& goal, const V3& wp, double radius, double max_vel,
+                      float* sfc, long long* lookups) {
+    const int M = P.M;
+    const double res = P.world_res;
+    int status = 0;
+    if (init) {
+        Box b;
+        for (int k = 0; k < 3; k++) {
+            v3_set(b.lo, k, (float)(floor(v3_get(pos, k) / res) * res));
+            v3_set(b.hi, k, (float)(ceil(v3_get(pos, k) / res) * res));
+        }
+        Box out;
+        if (!expand_incrementally(g, P, E, b, radius, max_vel, out, lookups)) {
+            status = kStSfcInitFailed;
+            out = b;
+        }
+        for (int m = g.lane; m < M; m += g.width) box_store(sfc + m * 6, out);
+        return status;
+    }
+    // shift + refinement (:506-516) -- serial dependency along m, done redundantly by every lane
+    Box cur[kMaxM];
+    for (int m = 0; m < M - 1; m++) cur[m] = box_load(sfc + (m + 1) * 6);
+    const Box prev = box_load(sfc + (M - 1) * 6);
+    for (int m = 0; m < M - 2; m++) {
+        V3 cps[kP];
+        for (int i = 0; i < kP; i++) cps[i] = v3_load(init_traj + (m * kP + i) * 3);
+        if (superset_of_hull(cur[m + 1], cps, kP)) cur[m] = cur[m + 1];
+    }
+    V3 hull[3];
+    hull[0] = v3_load(init_traj + ((M - 1) * kP + (kP - 1)) * 3); hull[1] = goal; hull[2] = wp;
+    Box upd;
+    // expandSFCFromConvexHull(convex_hull) :781-815
+    Box b = hull_aabb(hull, 3);
+    for (int k = 0; k < 3; k++) {
+        v3_set(b.lo, k, (float)(round(v3_get(b.lo, k) / res) * res));
+        v3_set(b.hi, k, (float)(round(v3_get(b.hi, k) / res) * res));
+    }
+    bool ok = expand_incrementally(g, P, E, b, radius, max_vel, upd, lookups);
+    if (ok && !superset_of_hull(upd, hull, 3)) ok = false;
+    if (!ok) {
+        // expandSFCFromConvexHull(convex_hull, sfc_prev) :817-860
+        b = hull_aabb(hull, 2);
+        for (int k = 0; k < 3; k++) {
+            v3_set(b.lo, k, (float)(floor(v3_get(b.lo, k) / res) * res));
+            v3_set(b.hi, k, (float)(ceil(v3_get(b.hi, k) / res) * res));
+        }
+        if (!box_includes(prev, b)) {
+            Box r;
+            for (int k = 0; k < 3; k++) {
+                const float l0 = v3_get(prev.lo, k), l1 = v3_get(b.lo, k);
+                const float h0 = v3_get(prev.hi, k), h1 = v3_get(b.hi, k);
+                v3_set(r.lo, k, (l0 < l1) ? l1 : l0);
+                v3_set(r.hi, k, (h1 < h0) ? h1 : h0);
+            }
+            for (int k = 0; k < 3; k++) {
+                v3_set(b.lo, k, (float)(ceil((v3_get(r.lo, k) - kEpsF) / res) * res));
+                v3_set(b.hi, k, (float)(floor((v3_get(r.hi, k) + kEpsF) / res) * res));
+            }
+        }
+        ok = expand_incrementally(g, P, E, b, radius, max_vel, upd, lookups);
+        if (!ok) { upd = prev; status |= kStSfcReused; }
+    }
+    cur[M - 1] = upd;
+    for (int m = g.lane; m < M; m += g.width) box_store(sfc + m * 6, cur[m]);
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// goal line search: closed form of the 1-variable LP (goal_optimizer.cpp:7-136, 138-198)
+//   min t in [0, 1+1e-5]  s.t.  a_r t + b_r >= 0 ; row activity tolerance 1e-6 (CPLEX default)
+// LSC arrays of this agent: normal [K][M][3], d [K][M][P], anchor_last [K][3]
+// ------------------------------------------------------------------------------------------------
+struct GoalRows {
+    const DevParams* P; const float* sfc_last; int K;
+    const float* normal; const double* d; const float* anchor_last;
+};
+DLSC_HD int goal_num_rows(const GoalRows& R) { return (R.P->use_sfc ? 2 * R.P->D : 0) + R.K; }
+// row r -> (a, b); returns false for skipped rows (zero normal, goal_optimizer.cpp:182-184)
+DLSC_HD bool goal_row(const GoalRows& R, int r, const V3& gw, const V3& wp, double& a, double& b) {
+    const DevParams& P = *R.P;
+    float nrm[3] = {0.f, 0.f, 0.f}, anc[3] = {0.f, 0.f, 0.f};
+    double dd;
+    const int nb = P.use_sfc ? 2 * P.D : 0;
+    if (r < nb) {                                               // Box::convertToLSCs :66-87
+        const int i = r >> 1;
+        if ((r & 1) == 0) { nrm[i] = 1.f; dd = (double)R.sfc_last[i]; }
+        else { nrm[i] = -1.f; dd = -(double)R.sfc_last[3 + i]; }
+    } else {
+        const int oi = r - nb;
+        const float* n = R.normal + ((size_t)oi * P.M + (P.M - 1)) * 3;
+        nrm[0] = n[0]; nrm[1] = n[1]; nrm[2] = n[2];
+        if (v3_norm(v3(nrm[0], nrm[1], nrm[2])) < kEpsF) return false;
+        anc[0] = R.anchor_last[oi * 3]; anc[1] = R.anchor_last[oi * 3 + 1]; anc[2] = R.anchor_last[oi * 3 + 2];
+        dd = R.d[((size_t)oi * P.M + (P.M - 1)) * kP + (kP - 1)];
+    }
+    a = 0; b = 0;
+    for (int k = 0; k < P.D; k++) {
+        a += (double)nrm[k] * (double)v3_get(gw, k);
+        b += (double)nrm[k] * ((double)v3_get(wp, k) - (double)anc[k]);
+    }
+    b = b - dd;
+    return true;
+}
+
+DLSC_HD int goal_agent(const DevParams& P, bool disturbed, const V3& pos, const V3& wp, const float* sfc_last,
+                       int K, const float* normal, const double* d, const float* anchor_last, V3& goal) {
+    if (disturbed) { goal = pos; return 0; }                          // traj_planner.cpp:447-450
+    if (v3_distance(goal, wp) < kEpsF) { goal = wp; return 0; }       // goal_optimizer.cpp:12-14
+    const V3 gw = goal - wp;                                          // float coefficients :165
+    GoalRows R; R.P = &P; R.sfc_last = sfc_last; R.K = K; R.normal = normal; R.d = d; R.anchor_last = anchor_last;
+    const int nr = goal_num_rows(R);
+    double tlo = 0.0;
+    for (int r = 0; r < nr; r++) {
+        double a, b;
+        if (!goal_row(R, r, gw, wp, a, b)) continue;
+        if (a > 0) { const double c = -b / a; tlo = (tlo < c) ? c : tlo; }
+    }
+    const double t = (1.0 + kEpsF < tlo) ? 1.0 + kEpsF : tlo;
+    bool feasible = true;
+    const double tol = 1e-6;
+    for (int r = 0; r < nr; r++) {
+        double a, b;
+        if (!goal_row(R, r, gw, wp, a, b)) continue;
+        if (a * t + b < -tol) feasible = false;
+    }
+    if (feasible) { goal = gw * (float)t + wp; return 0; }            // :51
+    // infeasible: "numerical error" rule :55-81
+    bool numerical_error = true;
+    if (P.use_sfc) {
+        const Box b = box_load(sfc_last);
+        if (!point_in_box(b, goal)) numerical_error = false;
+    }
+    for (int oi = 0; oi < K; oi++) {
+        const V3 nv = v3_load(normal + ((size_t)oi * P.M + (P.M - 1)) * 3);
+        if (v3_norm(nv) < kEpsF) continue;
+        const V3 anc = v3_load(anchor_last + oi * 3);
+        const double dd = d[((size_t)oi * P.M + (P.M - 1)) * kP + (kP - 1)];
+        const double delta = v3_dot(nv, goal - anc) - dd;             // :73
+        if (delta < -kEpsF) numerical_error = false;
+    }
+    return numerical_error ? 0 : kStGoalInfeasible;                   // keep goal :80
+}
+
+// ------------------------------------------------------------------------------------------------
+// state step: AgentManager::doStep -> Trajectory::getStateAt(t) (trajectory.cpp:111-170, 183-199)
+// state[9] = pos, vel, acc.  Powers are formed by repeated multiplication: exact for the
+// normalised time 0 or 1, i.e. for t = k*dt, which is the only way the replan loop calls it.
+// ------------------------------------------------------------------------------------------------
+DLSC_HD double ipow(double x, int e) { double r = 1.0; for (int i = 0; i < e; i++) r *= x; return r; }
+DLSC_HD int binom(int n, int k) {                     // polynomial.hpp:9-20
+    if (k > n) return 0;
+    if (k * 2 > n) k = n - k;
+    if (k == 0) return 1;
+    int r = n;
+    for (int i = 2; i <= k; i++) { r *= (n - i + 1); r /= i; }
+    return r;
+}
+DLSC_HD void state_at(const DevParams& P, const float* traj, double time, float* state) {
+    const int M = P.M;
+    int mm = -1;
+    double tn = 0, seg_end = 0;
+    for (int idx = 0; idx < M; idx++) {
+        seg_end += P.dt;
+        if (time < seg_end) { mm = idx; tn = 1 - (seg_end - time) / P.dt; break; }
+    }
+    if (mm == -1 && time < seg_end + kEpsF) { mm = M - 1; tn = 1.0; }
+    V3 cur[kP];
+    for (int i = 0; i < kP; i++) cur[i] = (mm >= 0) ? v3_load(traj + (mm * kP + i) * 3) : v3(0.f, 0.f, 0.f);
+    int n = kP - 1;
+    for (int order = 0; order < 3; order++) {
+        V3 point = v3(0.f, 0.f, 0.f);
+        if (mm >= 0) {
+            for (int i = 0; i < n + 1; i++) {
+                const double b = binom(n, i) * ipow(tn, i) * ipow(1 - tn, n - i);
+                point = point + cur[i] * (float)b;
+            }
+        }
+        v3_store(state + 3 * order, point);
+        for (int i = 0; i < n; i++) cur[i] = (cur[i + 1] - cur[i]) * (float)(n / P.dt);
+        cur[n] = v3(0.f, 0.f, 0.f);
+        n -= 1;
+    }
+}
+
+}  // namespace dlsc

@@ -181,3 +181,130 @@ def synthetic_empty(n_agents=70, half_extent=None, seed=7, grid_res=0.5):
     return Mission(np.array([-h, -h, 0.0], np.float32), np.array([h, h, zmax], np.float32),
                    s.astype(np.float32), g.astype(np.float32), full(0.15), full(2.0), full(1.0), full(2.0),
                    full(1.0))
+
+
+def occupied_nodes(boxes, grid_res=0.5, inflate=0.2):
+    """Integer (ix, iy) keys of the ``grid_res`` lattice nodes that lie inside an obstacle box inflated by
+    ``inflate`` metres in x/y (what the reference's GridBasedPlanner marks as blocked from the EDT,
+    src/grid_based_planner.cpp:94-164, restated geometrically)."""
+    occ = set()
+    for b in np.asarray(boxes, np.float64).reshape(-1, 6):
+        lo = b[0:2] - 0.5 * b[3:5] - inflate
+        hi = b[0:2] + 0.5 * b[3:5] + inflate
+        i0, i1 = int(np.ceil(lo[0] / grid_res - 1e-9)), int(np.floor(hi[0] / grid_res + 1e-9))
+        j0, j1 = int(np.ceil(lo[1] / grid_res - 1e-9)), int(np.floor(hi[1] / grid_res + 1e-9))
+        for i in range(i0, i1 + 1):
+            for j in range(j0, j1 + 1):
+                occ.add((i, j))
+    return occ
+
+
+class LatticeRouter:
+    """Per-agent breadth-first distance-to-goal fields on the x/y lattice (4-connected, obstacle nodes
+    removed).  Stand-in for the single-agent part of the reference's grid planner; used for small swarms
+    in walled worlds (maze), where a greedy step toward the goal would stop at the first wall."""
+
+    def __init__(self, world_min, world_max, grid_res, occupied, goals):
+        g = float(grid_res)
+        self.g = g
+        self.i0 = int(np.ceil(float(world_min[0]) / g - 1e-9))
+        self.j0 = int(np.ceil(float(world_min[1]) / g - 1e-9))
+        self.ni = int(np.floor(float(world_max[0]) / g + 1e-9)) - self.i0 + 1
+        self.nj = int(np.floor(float(world_max[1]) / g + 1e-9)) - self.j0 + 1
+        free = np.ones((self.ni, self.nj), bool)
+        for (i, j) in (occupied or ()):
+            if 0 <= i - self.i0 < self.ni and 0 <= j - self.j0 < self.nj:
+                free[i - self.i0, j - self.j0] = False
+        self.free = free
+        self.fields = []
+        for q in np.asarray(goals, np.float64):
+            self.fields.append(self._bfs(int(round(q[0] / g)) - self.i0, int(round(q[1] / g)) - self.j0))
+
+    def _bfs(self, gi, gj):
+        INF = 1 << 30
+        d = np.full((self.ni, self.nj), INF, np.int64)
+        if not (0 <= gi < self.ni and 0 <= gj < self.nj):
+            return d
+        d[gi, gj] = 0
+        frontier = [(gi, gj)]
+        while frontier:
+            nxt = []
+            for (i, j) in frontier:
+                for di, dj in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+                    a, b = i + di, j + dj
+                    if 0 <= a < self.ni and 0 <= b < self.nj and self.free[a, b] and d[a, b] == INF:
+                        d[a, b] = d[i, j] + 1
+                        nxt.append((a, b))
+            frontier = nxt
+        return d
+
+    def candidates(self, agent, cur):
+        """Lattice neighbours of `cur` ordered by distance-to-goal (closer first), only improving ones."""
+        g, d = self.g, self.fields[agent]
+        i, j = int(round(cur[0] / g)) - self.i0, int(round(cur[1] / g)) - self.j0
+        here = d[i, j] if (0 <= i < self.ni and 0 <= j < self.nj) else 1 << 30
+        out = []
+        for di, dj in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            a, b = i + di, j + dj
+            if 0 <= a < self.ni and 0 <= b < self.nj and d[a, b] < here:
+                c = np.array(cur, np.float64)
+                c[0] += di * g
+                c[1] += dj * g
+                out.append((d[a, b], len(out), c))
+        out.sort(key=lambda t: (t[0], t[1]))
+        return [c for _, _, c in out]
+
+
+def next_waypoints(waypoint, goal_cur, goal_des, traj, pos, cfg, occupied=None, router=None):
+    """Documented stand-in for the reference's waypoint provider (PIBT on the lattice + the update rules of
+    MultiSyncSimulator::decentralizedMAPP, src/multi_sync_simulator.cpp:308-466).  It keeps the update
+    rules that matter to the hot path and replaces the multi-agent search by a single-agent step:
+      * a waypoint only moves once the agent's current goal point has reached it (:407-413);
+      * the new waypoint is one lattice step (grid_res in x/y, 2*grid_res in z) from the old one: along the
+        breadth-first shortest path when a `router` is given, else toward the desired goal, largest
+        remaining axis first; never onto an obstacle node or another agent's waypoint (:418-447);
+      * with a communication range R it must stay within R/2 - 1e-5 (Chebyshev) of every segment start
+        point and of the end point of the agent's current trajectory (:386-404).
+    The same waypoints are fed to the oracle and to the GPU path, so parity does not depend on it."""
+    wp = np.asarray(waypoint, np.float32).copy()
+    goal_cur = np.asarray(goal_cur, np.float32)
+    goal_des = np.asarray(goal_des, np.float32)
+    N = wp.shape[0]
+    g = float(cfg.grid_res)
+    steps = np.array([g, g, 2.0 * g])
+    key = lambda q: (int(round(q[0] / g)), int(round(q[1] / g)), int(round(q[2] / g)))
+    taken = {key(wp[a].astype(np.float64)): a for a in range(N)}
+    reached = np.max(np.abs(goal_cur - wp), axis=1) < 1e-4
+    R = float(cfg.comm_range)
+    for a in np.nonzero(reached)[0]:
+        cur = wp[a].astype(np.float64)
+        delta = goal_des[a].astype(np.float64) - cur
+        cands = []
+        if router is not None:
+            cands = router.candidates(a, cur)
+        else:
+            naxes = 3 if cfg.dim == 3 else 2
+            for k in np.argsort(-np.abs(delta[:naxes]), kind="stable"):
+                if abs(delta[k]) < 0.5 * steps[k]:
+                    continue
+                c = cur.copy()
+                c[k] += np.sign(delta[k]) * steps[k]
+                cands.append(c)
+        for cand in cands:
+            if occupied is not None and (int(round(cand[0] / g)), int(round(cand[1] / g))) in occupied:
+                continue
+            kc = key(cand)
+            if kc in taken and taken[kc] != a:
+                continue
+            if R > 0:
+                if traj is None:
+                    pts = np.asarray(pos[a], np.float64)[None, :]
+                else:
+                    pts = np.concatenate([traj[a][:, 0, :], traj[a][-1:, -1, :]], 0).astype(np.float64)
+                if np.max(np.abs(pts - cand[None, :])) > 0.5 * R - 1e-5:
+                    break
+            taken.pop(key(cur), None)
+            taken[kc] = a
+            wp[a] = cand.astype(np.float32)
+            break
+    return wp

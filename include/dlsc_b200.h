@@ -1,0 +1,192 @@
+/*
+ * dlsc_b200.h -- C ABI of libdlsc_b200.so: the B200-native (sm_100a) replan hot path of
+ * dlsc_gc_planner:  horizon shift -> neighbour list -> LSC (batched GJK) -> SFC box expansion
+ * -> intermediate-goal line search -> piecewise-Bernstein min-jerk QP -> state step.
+ *
+ * This is the drop-in boundary.  The reference runs the path serially per agent on the CPU:
+ *   TrajPlanner::plan / planImpl                      (reference src/traj_planner.cpp:35-63, 108-133)
+ *   TrajPlanner::generateDLSCGC                       (src/traj_planner.cpp:603-666)
+ *   CollisionConstraints::constructSFCFromInitialTraj (src/collision_constraints.cpp:502-536)
+ *   GoalOptimizer::solve                              (src/goal_optimizer.cpp:7-136)
+ *   TrajOptimizer::solve                              (src/traj_optimizer.cpp:18-165)
+ *   AgentManager::doStep / getAgent                   (src/agent_manager.cpp:34-69, 249-263)
+ * Here every agent of a lock-step replan is processed by one dlsc_step() call.  Plain pointers
+ * and sizes only; int status returns (0 = ok, <0 = error, text via dlsc_last_error); no
+ * exceptions cross the ABI.  Host buffers are caller-owned, device buffers context-owned.
+ * There is no CPU fallback: every entry point fails when no CUDA device is usable.
+ *
+ * Multi-GPU: one context per process/GPU owns the contiguous agent block
+ * [agent_begin, agent_begin + n_local) of a swarm of n_agents.  The per-agent "record" (what
+ * AgentManager::getAgent exports to the other agents) lives in one device array of n_agents
+ * fixed-size records; between steps the caller all-gathers it in place over NCCL
+ * (dlsc_records_device / dlsc_record_floats give pointer and stride).
+ */
+#ifndef DLSC_B200_H
+#define DLSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLSC_ABI_VERSION 1
+
+/* Planner parameters: the subset of MATP::Param / MATP::Mission the hot path reads
+ * (reference src/param.cpp:5-117, src/mission.cpp:104-112; launch-file values SURVEY.md s5). */
+typedef struct dlsc_params {
+    int32_t M;              /* traj/M   segments (2..16)                                   */
+    int32_t n;              /* traj/n   polynomial degree; only 5 is supported             */
+    int32_t phi;            /* traj/phi; only 3 is supported                               */
+    int32_t dim;            /* world/dimension 2|3                                         */
+    int32_t use_sfc;        /* world/use_octomap                                           */
+    int32_t max_nbr;        /* capacity of the per-agent neighbour list (K)                */
+    double dt;              /* traj/dt == multisim/time_step                               */
+    double world_min[3];    /* mission world box (float32-representable)                   */
+    double world_max[3];
+    double world_res;       /* world/resolution                                            */
+    double grid_res;        /* grid/resolution                                             */
+    double z_2d;            /* world/z_2d                                                  */
+    double comm_range;      /* communication/range; <= 0: unlimited                        */
+    double w_control;       /* opt/control_input_weight                                    */
+    double w_terminal;      /* opt/terminal_weight                                         */
+    double reset_threshold; /* plan/reset_threshold                                        */
+    int32_t qp_max_iter;    /* interior-point iteration cap (0 -> 80)                      */
+    int32_t reserved;
+} dlsc_params;
+
+/* per-agent status bits (dlsc_get_status) */
+#define DLSC_OK               0
+#define DLSC_QP_MAXITER       1   /* -> TrajPlanner failsafe: desired_traj = initial_traj  (traj_planner.cpp:749-777) */
+#define DLSC_QP_NUMERIC       2
+#define DLSC_SFC_INIT_FAILED  4   /* "Invalid initial SFC" (collision_constraints.cpp:445-447) */
+#define DLSC_GOAL_INFEASIBLE  8   /* PlanningReport::QPFAILED from GoalOptimizer (goal_optimizer.cpp:122,132) */
+#define DLSC_SFC_REUSED      16   /* informational: previous box kept (collision_constraints.cpp:529-532) */
+#define DLSC_NBR_OVERFLOW    32   /* more neighbours in range than max_nbr */
+
+/* stage bits for dlsc_run_stages / indices for dlsc_get_timings */
+#define DLSC_STAGE_PREDICT  1   /* obstacle prediction + initial trajectory (traj_planner.cpp:290-336, 409-441) */
+#define DLSC_STAGE_NBR      2   /* comm-range neighbour list (multi_sync_simulator.cpp:481-503) */
+#define DLSC_STAGE_LSC      4
+#define DLSC_STAGE_SFC      8
+#define DLSC_STAGE_GOAL    16
+#define DLSC_STAGE_QP      32
+#define DLSC_STAGE_ALL     63
+#define DLSC_N_STAGES       6
+
+typedef struct dlsc_ctx dlsc_ctx;
+
+/* Per-step inputs of the local agent block, SoA, host memory.  NULL members keep the device
+ * copy (e.g. after dlsc_advance()).  Mirrors the Agent struct handed to TrajPlanner::plan
+ * (include/sp_const.hpp:141-160) plus is_disturbed. */
+typedef struct dlsc_agents {
+    const float* pos;          /* [n_local][3] current_state.position   */
+    const float* vel;          /* [n_local][3]                          */
+    const float* acc;          /* [n_local][3]                          */
+    const float* waypoint;     /* [n_local][3] next_waypoint            */
+    const uint8_t* disturbed;  /* [n_local]                             */
+} dlsc_agents;
+
+/* Constant per-agent properties (mission JSON "quadrotors"), local block, host memory. */
+typedef struct dlsc_agent_props {
+    const double* radius;       /* [n_local] */
+    const double* downwash;
+    const double* max_vel;
+    const double* max_acc;      /* first element of the JSON array only (mission.cpp:123-124) */
+    const double* nominal_vel;
+} dlsc_agent_props;
+
+const char* dlsc_last_error(void);
+int dlsc_abi_version(void);
+int dlsc_device_count(void);
+
+/* Create a context on CUDA device `device` for agents [agent_begin, agent_begin+n_local) of a
+ * swarm of n_agents.  Replaces the per-agent TrajPlanner/TrajOptimizer/CollisionConstraints
+ * constructors (traj_planner.cpp:4-33, traj_optimizer.cpp:4-16). */
+int dlsc_create(const dlsc_params* params, int n_agents, int agent_begin, int n_local, int device,
+                dlsc_ctx** out);
+void dlsc_destroy(dlsc_ctx* ctx);
+
+/* Run on an existing CUDA stream (cudaStream_t as void*); default: a context-owned stream. */
+int dlsc_set_stream(dlsc_ctx* ctx, void* cuda_stream);
+void* dlsc_get_stream(dlsc_ctx* ctx);
+
+/* Distance grid: what DynamicEDTOctomap::getDistanceAndClosestObstacle serves
+ * (call site collision_constraints.cpp:880; built in map_manager.cpp:61-82).
+ * dist [ncell] metres, obst [ncell][3] map-cell index of the nearest occupied cell or -1;
+ * cell (x,y,z) -> (x*dims[1]+y)*dims[2]+z; map x = floor(coord/res) - min_key. */
+int dlsc_set_edt(dlsc_ctx* ctx, const float* dist, const int32_t* obst, const int32_t dims[3],
+                 const int32_t min_key[3], double res);
+
+int dlsc_set_agent_props(dlsc_ctx* ctx, const dlsc_agent_props* props);
+
+/* Reset planner state of the local block (planner_seq = 0, initialize_sfc = true,
+ * current_goal_point = start, next_waypoint = start: agent_manager.cpp:4-32) and write the
+ * local records.  start [n_local][3]. */
+int dlsc_reset(dlsc_ctx* ctx, const float* start);
+
+/* Upload this step's agent states / waypoints (TrajPlanner::plan arguments + setNextWaypoint). */
+int dlsc_set_agents(dlsc_ctx* ctx, const dlsc_agents* agents);
+
+/* Records: n_agents x dlsc_record_floats() float32, layout
+ *   [0, M*P*3) previous desired trajectory | pos 3 | vel 3 | current_goal 3 | radius | downwash | pad.
+ * Single GPU: nothing to do.  Multi GPU: all-gather the local slice
+ * (records + agent_begin*stride, n_local*stride floats) in place between steps. */
+float* dlsc_records_device(dlsc_ctx* ctx);
+int dlsc_record_floats(const dlsc_ctx* ctx);
+/* Use caller-allocated device memory for the records (e.g. a torch tensor that NCCL gathers). */
+int dlsc_bind_records(dlsc_ctx* ctx, float* device_ptr);
+/* Host -> device / device -> host copy of `count` records starting at agent `first` (global index). */
+int dlsc_set_records(dlsc_ctx* ctx, int first, int count, const float* host);
+int dlsc_get_records(dlsc_ctx* ctx, int first, int count, float* host);
+
+/* One replan of every local agent (= TrajPlanner::plan for each agent of the block).  Stream
+ * ordered; returns after enqueueing.  dlsc_step == dlsc_run_stages(DLSC_STAGE_ALL) + seq++. */
+int dlsc_step(dlsc_ctx* ctx);
+int dlsc_run_stages(dlsc_ctx* ctx, int stage_mask);
+/* AgentManager::doStep (agent_manager.cpp:34-69): state := desired_traj.getStateAt(dt) on the
+ * device, and refresh the local records (prev_traj, pos, vel, goal) for the next step. */
+int dlsc_advance(dlsc_ctx* ctx);
+/* Refresh the local records from the current device state without moving the agents (used when
+ * the host supplies the next states through dlsc_set_agents). */
+int dlsc_publish_records(dlsc_ctx* ctx);
+int dlsc_sync(dlsc_ctx* ctx);
+int dlsc_get_seq(const dlsc_ctx* ctx);
+int dlsc_set_seq(dlsc_ctx* ctx, int seq);
+
+/* Results of the last step, local block, to host memory (blocking). */
+int dlsc_get_traj(dlsc_ctx* ctx, float* traj /* [n_local][M][P][3] */);
+int dlsc_get_qp_x(dlsc_ctx* ctx, double* x /* [n_local][dim][M][P] */);
+int dlsc_get_cost(dlsc_ctx* ctx, double* cost /* [n_local] */);
+int dlsc_get_violation(dlsc_ctx* ctx, double* viol /* [n_local] */);
+int dlsc_get_qp_iters(dlsc_ctx* ctx, int32_t* iters /* [n_local] */);
+int dlsc_get_status(dlsc_ctx* ctx, int32_t* status /* [n_local] */);
+int dlsc_get_goal(dlsc_ctx* ctx, float* goal /* [n_local][3] current_goal_point */);
+int dlsc_get_state(dlsc_ctx* ctx, float* pos, float* vel, float* acc /* each [n_local][3] or NULL */);
+int dlsc_get_init_traj(dlsc_ctx* ctx, float* traj /* [n_local][M][P][3] */);
+int dlsc_get_pred_traj(dlsc_ctx* ctx, float* traj /* [n_agents][M][P][3] */);
+int dlsc_get_neighbours(dlsc_ctx* ctx, int32_t* idx /* [n_local][K] */, int32_t* cnt /* [n_local] */);
+/* LSCs in the oracle / reference layout: normal [n_local][K][M][3], anchor [n_local][K][M][P][3],
+ * d [n_local][K][M][P]  (CollisionConstraints::getLSC, collision_constraints.cpp:600-626). */
+int dlsc_get_lsc(dlsc_ctx* ctx, float* normal, float* anchor, double* d);
+int dlsc_get_sfc(dlsc_ctx* ctx, float* sfc /* [n_local][M][6] min xyz, max xyz */);
+int dlsc_set_sfc(dlsc_ctx* ctx, const float* sfc, const uint8_t* init_flag /* [n_local] or NULL */);
+/* mean device milliseconds per stage over the steps since the last call (CUDA events; only
+ * recorded while dlsc_enable_timing(ctx,1)); order: predict, nbr, lsc, sfc, goal, qp. */
+int dlsc_enable_timing(dlsc_ctx* ctx, int on);
+int dlsc_get_timings(dlsc_ctx* ctx, double ms[DLSC_N_STAGES], int* n_steps);
+/* kernels launched by this context so far */
+int64_t dlsc_launch_count(const dlsc_ctx* ctx);
+/* work counters of the last step summed over the local block (for roofline arithmetic):
+ * [0] neighbour pairs, [1] GJK iterations, [2] EDT lookups, [3] QP iterations, [4] QP rows */
+int dlsc_get_counters(dlsc_ctx* ctx, int64_t counters[8]);
+
+/* Device pointers of per-step input / output arrays, for callers that keep data on the GPU. */
+float* dlsc_waypoint_device(dlsc_ctx* ctx);   /* [n_local][3] */
+float* dlsc_traj_device(dlsc_ctx* ctx);       /* [n_local][M][P][3] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLSC_B200_H */

@@ -36,6 +36,13 @@
 #include <functional>
 #include <thread>
 
+#ifndef ORC_QP_TOL_RD
+#define ORC_QP_TOL_RD 1e-13
+#endif
+#ifndef ORC_QP_TOL_MU
+#define ORC_QP_TOL_MU 1e-12
+#endif
+
 namespace {
 
 constexpr double kEps = 1e-9;        // SP_EPSILON        include/sp_const.hpp:3
@@ -957,7 +964,7 @@ int ipm_solve(int ny, const std::vector<double>& H, const std::vector<double>& g
         for (int r = 0; r < m; r++) { rp[r] = Gy[r] + s[r] - rows[r].rhs; rp_inf = std::max(rp_inf, std::fabs(rp[r])); mu += s[r] * z[r]; }
         for (int i = 0; i < ny; i++) { rd_inf = std::max(rd_inf, std::fabs(rd[i])); g_inf = std::max(g_inf, std::fabs(g[i])); }
         if (m > 0) mu /= m;
-        if (rp_inf <= 1e-10 && rd_inf <= 1e-9 * (1.0 + g_inf) && mu <= 1e-11) { status = ORC_OK; break; }
+        if (rp_inf <= 1e-10 && rd_inf <= ORC_QP_TOL_RD * (1.0 + g_inf) && mu <= ORC_QP_TOL_MU) { status = ORC_OK; break; }
         // W = H + G' diag(z/s) G
         W = H;
         for (int r = 0; r < m; r++) {

@@ -1,0 +1,358 @@
+// hostsim.cu -- TEST INFRASTRUCTURE ONLY (never loaded by the product package).
+//
+// Runs the very same __host__ __device__ cores the sm_100a kernels execute (dlsc_stages.cuh,
+// dlsc_qp.cuh) serially on the CPU, one "lane" / one "thread" per cooperative group, behind the same
+// C-ABI names as libdlsc_b200.so.  Purpose: check the kernel arithmetic against the oracle in the
+// CPU-only test tier (-m "not gpu"), so that a GPU box is only needed for what a GPU adds
+// (SIMT mapping, synchronisation, shuffles).  It is not a fallback: the product loader
+// (dlsc_gc_planner_b200/capi.py) only ever opens libdlsc_b200.so.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dlsc_b200.h"
+#include "../../dlsc_gc_planner_b200/csrc/dlsc_qp.cuh"
+#include "../../dlsc_gc_planner_b200/csrc/dlsc_stages.cuh"
+
+using namespace dlsc;
+
+static std::string g_err;
+static int fail(const char* m) { g_err = m; return -1; }
+
+struct dlsc_ctx {
+    DevParams P;
+    RecLayout rl;
+    QpTabHost th;
+    QpTab T;
+    int seq = 0;
+    std::vector<float> rec, acc, waypoint, pred_traj, init_traj, lsc_normal, lsc_anchor_last, sfc, traj;
+    std::vector<uint8_t> disturbed, sfc_init;
+    std::vector<double> radius, downwash, max_vel, max_acc, nominal_vel, lsc_d, qp_x, cost, viol, scratch, smem;
+    std::vector<int32_t> nbr_idx, nbr_cnt, qp_iters, status;
+    std::vector<int4> cells;
+    EdtDev edt;
+    bool have_edt = false;
+    int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+extern "C" {
+
+const char* dlsc_last_error(void) { return g_err.c_str(); }
+int dlsc_abi_version(void) { return DLSC_ABI_VERSION; }
+int dlsc_device_count(void) { return 0; }
+
+int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_local, int device, dlsc_ctx** out) {
+    (void)device;
+    if (hp->n != 5 || hp->phi != 3) return fail("only n = 5, phi = 3");
+    if (hp->dim * (3 * hp->M - 2) > 128 || hp->M > kMaxM || hp->M < 2) return fail("bad M");
+    dlsc_ctx* c = new dlsc_ctx();
+    DevParams& P = c->P;
+    memset(&P, 0, sizeof(P));
+    P.M = hp->M; P.D = hp->dim; P.use_sfc = hp->use_sfc; P.K = hp->max_nbr;
+    P.N = n_agents; P.begin = agent_begin; P.NL = n_local;
+    c->rl = rec_layout(hp->M);
+    P.rec = c->rl.size;
+    P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
+    P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
+    P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
+    P.reset_threshold = hp->reset_threshold;
+    for (int k = 0; k < 3; k++) {
+        P.world_min[k] = (double)(float)hp->world_min[k];
+        P.world_max[k] = (double)(float)hp->world_max[k];
+    }
+    double time = 0;
+    for (int e = 0; e < hp->M * kP; e++) { P.tk[e] = (float)time; time += hp->dt / hp->n; }
+    const size_t N = n_agents, NL = n_local, K = hp->max_nbr, M = hp->M, npt = M * kP;
+    c->rec.assign(N * P.rec, 0.f); c->acc.assign(NL * 3, 0.f); c->waypoint.assign(NL * 3, 0.f);
+    c->disturbed.assign(NL, 0); c->sfc_init.assign(NL, 1);
+    c->radius.assign(NL, 0); c->downwash.assign(NL, 0); c->max_vel.assign(NL, 0); c->max_acc.assign(NL, 0);
+    c->nominal_vel.assign(NL, 0);
+    c->pred_traj.assign(N * npt * 3, 0.f); c->init_traj.assign(NL * npt * 3, 0.f);
+    c->nbr_idx.assign(NL * K, 0); c->nbr_cnt.assign(NL, 0);
+    c->lsc_normal.assign(NL * K * M * 3, 0.f); c->lsc_d.assign(NL * K * M * kP, 0.0);
+    c->lsc_anchor_last.assign(NL * K * 3, 0.f);
+    c->sfc.assign(NL * M * 6, 0.f); c->traj.assign(NL * npt * 3, 0.f);
+    c->qp_x.assign(NL * hp->dim * npt, 0.0); c->cost.assign(NL, 0); c->viol.assign(NL, 0);
+    c->qp_iters.assign(NL, 0); c->status.assign(NL, 0);
+    build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->comm_range > 0, c->th);
+    const QpTabHost& h = c->th;
+    QpTab& T = c->T;
+    T.D = h.D; T.M = h.M; T.nyd = h.nyd; T.ny = h.ny; T.npt = h.npt; T.nx = h.nx; T.np = h.np; T.ntri = h.ntri;
+    T.ntri_local = h.ntri_local; T.use_comm = h.use_comm;
+    T.xm_nv = h.xm_nv.data(); T.xm_cidx = h.xm_cidx.data(); T.xm_idx = h.xm_idx.data(); T.xm_coef = h.xm_coef.data();
+    T.pr_fam = h.pr_fam.data(); T.pr_axis = h.pr_axis.data(); T.pr_nnz = h.pr_nnz.data(); T.pr_pt = h.pr_pt.data();
+    T.pr_idx = h.pr_idx.data(); T.pr_val = h.pr_val.data(); T.pr_cc = h.pr_cc.data();
+    T.yi_ptr = h.yi_ptr.data(); T.yi_row = h.yi_row.data(); T.yi_coef = h.yi_coef.data();
+    T.yp_ptr = h.yp_ptr.data(); T.yp_pt = h.yp_pt.data(); T.yp_coef = h.yp_coef.data();
+    T.wi_ptr = h.wi_ptr.data(); T.wi_row = h.wi_row.data(); T.wi_coef = h.wi_coef.data();
+    T.wp_ptr = h.wp_ptr.data(); T.wp_pt = h.wp_pt.data(); T.wp_coef = h.wp_coef.data();
+    T.H1 = h.H1.data(); T.Q2 = h.Q2.data();
+    c->scratch.assign(qp_scratch_doubles(T, P.K), 0.0);
+    c->smem.assign(qp_smem_bytes(T, P.K) / 8 + 8, 0.0);
+    memset(&c->edt, 0, sizeof(c->edt));
+    c->edt.res = hp->world_res; c->edt.inv_res = 1.0 / hp->world_res;
+    *out = c;
+    return 0;
+}
+void dlsc_destroy(dlsc_ctx* c) { delete c; }
+
+int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int32_t dims[3],
+                 const int32_t min_key[3], double res) {
+    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+    c->cells.resize(nc);
+    for (size_t i = 0; i < nc; i++) {
+        union { float f; int i; } u; u.f = dist[i];
+        c->cells[i].x = u.i; c->cells[i].y = obst[3 * i]; c->cells[i].z = obst[3 * i + 1]; c->cells[i].w = obst[3 * i + 2];
+    }
+    for (int k = 0; k < 3; k++) { c->edt.dims[k] = dims[k]; c->edt.min_key[k] = min_key[k]; }
+    c->edt.res = res; c->edt.inv_res = 1.0 / res; c->edt.cells = c->cells.data();
+    c->have_edt = true;
+    return 0;
+}
+
+int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
+    const size_t NL = c->P.NL;
+    if (p->radius) c->radius.assign(p->radius, p->radius + NL);
+    if (p->downwash) c->downwash.assign(p->downwash, p->downwash + NL);
+    if (p->max_vel) c->max_vel.assign(p->max_vel, p->max_vel + NL);
+    if (p->max_acc) c->max_acc.assign(p->max_acc, p->max_acc + NL);
+    if (p->nominal_vel) c->nominal_vel.assign(p->nominal_vel, p->nominal_vel + NL);
+    return 0;
+}
+
+int dlsc_reset(dlsc_ctx* c, const float* start) {
+    const DevParams& P = c->P;
+    const int npt = P.M * kP;
+    for (int la = 0; la < P.NL; la++) {
+        float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+        for (int e = 0; e < npt; e++) for (int k = 0; k < 3; k++) rec[e * 3 + k] = start[la * 3 + k];
+        const int o = npt * 3;
+        for (int k = 0; k < 3; k++) { rec[o + k] = start[la * 3 + k]; rec[o + 3 + k] = 0.f; rec[o + 6 + k] = start[la * 3 + k]; }
+        rec[o + 9] = (float)c->radius[la]; rec[o + 10] = (float)c->downwash[la];
+        for (int e = o + 11; e < P.rec; e++) rec[e] = 0.f;
+        for (int k = 0; k < 3; k++) { c->acc[la * 3 + k] = 0.f; c->waypoint[la * 3 + k] = start[la * 3 + k]; }
+        c->disturbed[la] = 0; c->sfc_init[la] = 1; c->status[la] = 0;
+        for (int e = 0; e < npt * 3; e++) c->traj[(size_t)la * npt * 3 + e] = rec[e];
+    }
+    c->seq = 0;
+    return 0;
+}
+
+int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
+    const DevParams& P = c->P;
+    for (int la = 0; la < P.NL; la++) {
+        float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec + c->rl.pos;
+        for (int k = 0; k < 3; k++) {
+            if (a->pos) rec[k] = a->pos[la * 3 + k];
+            if (a->vel) rec[3 + k] = a->vel[la * 3 + k];
+            if (a->acc) c->acc[la * 3 + k] = a->acc[la * 3 + k];
+            if (a->waypoint) c->waypoint[la * 3 + k] = a->waypoint[la * 3 + k];
+        }
+        if (a->disturbed) c->disturbed[la] = a->disturbed[la];
+    }
+    return 0;
+}
+
+float* dlsc_records_device(dlsc_ctx* c) { return c->rec.data(); }
+int dlsc_record_floats(const dlsc_ctx* c) { return c->P.rec; }
+int dlsc_set_records(dlsc_ctx* c, int first, int count, const float* host) {
+    memcpy(c->rec.data() + (size_t)first * c->P.rec, host, (size_t)count * c->P.rec * 4);
+    return 0;
+}
+int dlsc_get_records(dlsc_ctx* c, int first, int count, float* host) {
+    memcpy(host, c->rec.data() + (size_t)first * c->P.rec, (size_t)count * c->P.rec * 4);
+    return 0;
+}
+
+int dlsc_run_stages(dlsc_ctx* c, int mask) {
+    const DevParams& P = c->P;
+    const int M = P.M, npt = M * kP, K = P.K;
+    const int seq = c->seq + 1;
+    Group g; g.lane = 0; g.width = 1;
+    if ((mask & DLSC_STAGE_SFC) && P.use_sfc && !c->have_edt) return fail("no EDT");
+    if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP)) memset(c->counters, 0, sizeof(c->counters));
+    if (mask & DLSC_STAGE_PREDICT)
+        for (int a = 0; a < P.N; a++) {
+            const int la = a - P.begin;
+            const bool local = la >= 0 && la < P.NL;
+            for (int pt = 0; pt < npt; pt++)
+                predict_point(P, c->rec.data() + (size_t)a * P.rec, seq, pt, local ? c->disturbed[la] != 0 : false,
+                              c->pred_traj.data() + (size_t)a * npt * 3,
+                              local ? c->init_traj.data() + (size_t)la * npt * 3 : nullptr);
+            if (local) c->status[la] = 0;
+        }
+    if (mask & DLSC_STAGE_NBR)
+        for (int la = 0; la < P.NL; la++) {
+            const int cnt = neighbours_agent(g, P, c->rec.data(), P.begin + la, c->nbr_idx.data() + (size_t)la * K);
+            c->nbr_cnt[la] = cnt < K ? cnt : K;
+            if (cnt > K) c->status[la] |= kStNbrOverflow;
+            c->counters[0] += c->nbr_cnt[la];
+        }
+    if (mask & DLSC_STAGE_LSC)
+        for (int la = 0; la < P.NL; la++)
+            for (int cc = 0; cc < c->nbr_cnt[la]; cc++) {
+                const int j = c->nbr_idx[(size_t)la * K + cc];
+                const float* rec_a = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+                const float* rec_j = c->rec.data() + (size_t)j * P.rec;
+                const int og = npt * 3 + 6;
+                const size_t pr = (size_t)la * K + cc;
+                for (int m = 0; m < M; m++) {
+                    int it = 0;
+                    lsc_segment(P, c->init_traj.data() + (size_t)la * npt * 3, c->pred_traj.data() + (size_t)j * npt * 3,
+                                v3_load(rec_a + og), v3_load(rec_j + og), c->radius[la], c->downwash[la], rec_j[og + 3],
+                                rec_j[og + 4], m, c->lsc_normal.data() + (pr * M + m) * 3,
+                                c->lsc_d.data() + (pr * M + m) * kP, c->lsc_anchor_last.data() + pr * 3, &it);
+                    c->counters[1] += it;
+                }
+            }
+    if ((mask & DLSC_STAGE_SFC) && P.use_sfc)
+        for (int la = 0; la < P.NL; la++) {
+            const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+            const bool init = c->sfc_init[la] != 0 || c->disturbed[la] != 0;
+            long long lookups = 0;
+            const int st = sfc_agent(g, P, c->edt, init, v3_load(rec + npt * 3), c->init_traj.data() + (size_t)la * npt * 3,
+                                     v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3), c->radius[la],
+                                     c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &lookups);
+            c->sfc_init[la] = 0;
+            c->status[la] |= st;
+            c->counters[2] += lookups;
+        }
+    if (mask & DLSC_STAGE_GOAL)
+        for (int la = 0; la < P.NL; la++) {
+            float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+            V3 goal = v3_load(rec + npt * 3 + 6);
+            const size_t pr = (size_t)la * K;
+            const int st = goal_agent(P, c->disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(c->waypoint.data() + la * 3),
+                                      c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->nbr_cnt[la],
+                                      c->lsc_normal.data() + pr * M * 3, c->lsc_d.data() + pr * M * kP,
+                                      c->lsc_anchor_last.data() + pr * 3, goal);
+            v3_store(rec + npt * 3 + 6, goal);
+            c->status[la] |= st;
+        }
+    if (mask & DLSC_STAGE_QP) {
+        QpSmem sm;
+        qp_smem_carve(c->T, K, c->smem.data(), sm);
+        Cta cta; cta.tid = 0; cta.nthr = 1; cta.red = sm.red;
+        for (int la = 0; la < P.NL; la++) {
+            const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+            QpIn in;
+            in.pos = v3_load(rec + npt * 3); in.vel = v3_load(rec + npt * 3 + 3);
+            in.acc = v3_load(c->acc.data() + la * 3); in.goal = v3_load(rec + npt * 3 + 6);
+            in.wp = v3_load(c->waypoint.data() + la * 3);
+            in.radius = c->radius[la]; in.max_vel = c->max_vel[la]; in.max_acc = c->max_acc[la];
+            in.nominal_vel = c->nominal_vel[la];
+            in.sfc = c->sfc.data() + (size_t)la * M * 6;
+            in.init_traj = c->init_traj.data() + (size_t)la * npt * 3;
+            in.K = c->nbr_cnt[la];
+            const size_t pr = (size_t)la * K;
+            in.nbr_idx = c->nbr_idx.data() + pr;
+            in.normal = c->lsc_normal.data() + pr * M * 3;
+            in.d = c->lsc_d.data() + pr * M * kP;
+            in.anchor_last = c->lsc_anchor_last.data() + pr * 3;
+            in.pred_traj = c->pred_traj.data();
+            long long rows = 0;
+            QpOut out;
+            out.traj = c->traj.data() + (size_t)la * npt * 3;
+            out.x = c->qp_x.data() + (size_t)la * c->T.nx;
+            out.cost = &c->cost[la]; out.viol = &c->viol[la]; out.iters = &c->qp_iters[la]; out.status = &c->status[la];
+            out.rows = &rows;
+            qp_agent(cta, 1, P, c->T, in, out, sm, c->scratch.data());
+            c->counters[3] += c->qp_iters[la];
+            c->counters[4] += rows;
+        }
+    }
+    return 0;
+}
+
+int dlsc_step(dlsc_ctx* c) {
+    const int rc = dlsc_run_stages(c, DLSC_STAGE_ALL);
+    if (rc == 0) c->seq++;
+    return rc;
+}
+
+static void advance_impl(dlsc_ctx* c, bool move) {
+    const DevParams& P = c->P;
+    const int npt = P.M * kP;
+    for (int la = 0; la < P.NL; la++) {
+        float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+        const float* tr = c->traj.data() + (size_t)la * npt * 3;
+        if (move) {
+            float st[9];
+            state_at(P, tr, P.dt, st);
+            for (int k = 0; k < 3; k++) { rec[npt * 3 + k] = st[k]; rec[npt * 3 + 3 + k] = st[3 + k]; c->acc[la * 3 + k] = st[6 + k]; }
+        }
+        for (int e = 0; e < npt * 3; e++) rec[e] = tr[e];
+    }
+}
+int dlsc_advance(dlsc_ctx* c) { advance_impl(c, true); return 0; }
+int dlsc_publish_records(dlsc_ctx* c) { advance_impl(c, false); return 0; }
+int dlsc_sync(dlsc_ctx*) { return 0; }
+int dlsc_get_seq(const dlsc_ctx* c) { return c->seq; }
+int dlsc_set_seq(dlsc_ctx* c, int s) { c->seq = s; return 0; }
+
+#define GET(name, type, vec) int name(dlsc_ctx* c, type* o) { memcpy(o, c->vec.data(), c->vec.size() * sizeof(type)); return 0; }
+GET(dlsc_get_traj, float, traj)
+GET(dlsc_get_qp_x, double, qp_x)
+GET(dlsc_get_cost, double, cost)
+GET(dlsc_get_violation, double, viol)
+GET(dlsc_get_qp_iters, int32_t, qp_iters)
+GET(dlsc_get_status, int32_t, status)
+GET(dlsc_get_init_traj, float, init_traj)
+GET(dlsc_get_pred_traj, float, pred_traj)
+GET(dlsc_get_sfc, float, sfc)
+#undef GET
+
+int dlsc_get_goal(dlsc_ctx* c, float* goal) {
+    const DevParams& P = c->P;
+    for (int la = 0; la < P.NL; la++)
+        for (int k = 0; k < 3; k++) goal[la * 3 + k] = c->rec[(size_t)(P.begin + la) * P.rec + c->rl.goal + k];
+    return 0;
+}
+int dlsc_get_state(dlsc_ctx* c, float* pos, float* vel, float* acc) {
+    const DevParams& P = c->P;
+    for (int la = 0; la < P.NL; la++)
+        for (int k = 0; k < 3; k++) {
+            if (pos) pos[la * 3 + k] = c->rec[(size_t)(P.begin + la) * P.rec + c->rl.pos + k];
+            if (vel) vel[la * 3 + k] = c->rec[(size_t)(P.begin + la) * P.rec + c->rl.vel + k];
+            if (acc) acc[la * 3 + k] = c->acc[la * 3 + k];
+        }
+    return 0;
+}
+int dlsc_get_neighbours(dlsc_ctx* c, int32_t* idx, int32_t* cnt) {
+    if (idx) memcpy(idx, c->nbr_idx.data(), c->nbr_idx.size() * 4);
+    if (cnt) memcpy(cnt, c->nbr_cnt.data(), c->nbr_cnt.size() * 4);
+    return 0;
+}
+int dlsc_get_lsc(dlsc_ctx* c, float* normal, float* anchor, double* d) {
+    const DevParams& P = c->P;
+    const int npt = P.M * kP;
+    if (normal) memcpy(normal, c->lsc_normal.data(), c->lsc_normal.size() * 4);
+    if (d) memcpy(d, c->lsc_d.data(), c->lsc_d.size() * 8);
+    if (anchor)
+        for (int la = 0; la < P.NL; la++)
+            for (int cc = 0; cc < P.K; cc++)
+                for (int pt = 0; pt < npt; pt++) {
+                    const size_t pr = (size_t)la * P.K + cc;
+                    float v[3] = {0.f, 0.f, 0.f};
+                    if (cc < c->nbr_cnt[la]) {
+                        const int j = c->nbr_idx[pr];
+                        const float* src = (pt / kP < P.M - 1) ? c->pred_traj.data() + ((size_t)j * npt + pt) * 3
+                                                               : c->lsc_anchor_last.data() + pr * 3;
+                        v[0] = src[0]; v[1] = src[1]; v[2] = src[2];
+                    }
+                    for (int k = 0; k < 3; k++) anchor[(pr * npt + pt) * 3 + k] = v[k];
+                }
+    return 0;
+}
+int dlsc_set_sfc(dlsc_ctx* c, const float* sfc, const uint8_t* init_flag) {
+    if (sfc) memcpy(c->sfc.data(), sfc, c->sfc.size() * 4);
+    if (init_flag) memcpy(c->sfc_init.data(), init_flag, c->sfc_init.size());
+    return 0;
+}
+int dlsc_get_counters(dlsc_ctx* c, int64_t counters[8]) { memcpy(counters, c->counters, sizeof(c->counters)); return 0; }
+int64_t dlsc_launch_count(const dlsc_ctx*) { return 0; }
+int dlsc_enable_timing(dlsc_ctx*, int) { return 0; }
+int dlsc_get_timings(dlsc_ctx*, double ms[DLSC_N_STAGES], int* n) { for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = 0; if (n) *n = 0; return 0; }
+
+}  // extern "C"
