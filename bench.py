@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py -- agent-replans/s of the replan hot path (LSC + SFC + goal + QP for every agent) on the
+synthetic 4096-agent 3-D forest swarm of BASELINE.json (configs[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--agents 4096]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one replan of all agents.  The swarm is rolled out for `--settle` untimed steps first so that the
+timed steps are in-transit replans (non-trivial LSC / SFC / QP active sets), and the per-step waypoints of
+the whole run are recorded by an untimed pilot rollout (the waypoint provider is host-side and out of the
+hot path's scope).  The path is deterministic, so the timed replays see exactly the pilot's states.
+
+  value : agents * K / t, inputs resident in HBM (device-chained plan -> advance [-> NCCL all-gather]),
+          timed with CUDA events on the launching stream, max over ranks.
+  e2e   : same metric through the host-facing C-ABI calls with HOST buffers: every step uploads pos / vel /
+          acc / waypoint of every agent from pinned memory (dlsc_set_agents), runs dlsc_step and reads every
+          trajectory back (dlsc_get_traj).
+  scaling: strong (the 4096-agent swarm is sharded over the ranks; one all-gather of the agent records
+          per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from dlsc_gc_planner_b200 import capi, edt as edtmod, missions  # noqa: E402
+
+METRIC = "agent-replans/sec (LSC+SFC+QP), synthetic 4096-agent 3D forest"
+UNIT = "agent-replans/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents", type=int, default=4096)
+    ap.add_argument("--half-extent", type=float, default=None, help="world half size in m (default: 1 agent/m^2)")
+    ap.add_argument("--max-nbr", type=int, default=96)
+    ap.add_argument("--settle", type=int, default=25, help="untimed rollout steps before the timed region")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+def make_world(args):
+    cfg = missions.PlannerConfig.forest3d()
+    h = args.half_extent if args.half_extent else 0.5 * float(np.sqrt(args.agents))
+    m = missions.synthetic_forest(n_agents=args.agents, half_extent=h, seed=4096)
+    dist, obst, dims, mk = edtmod.build_edt(m.world_min, m.world_max, cfg.world_res, m.boxes)
+    return cfg, m, (dist, obst, dims, mk)
+
+
+class Clocks:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip() == "Active":
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def pinned(shape, dtype):
+    import torch
+    t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+    return t, t.numpy()
+
+
+# ------------------------------------------------------------------------------------------------------
+def pilot_rollout(cfg, m, edt, args, device, n_steps):
+    """Untimed: roll the whole swarm out on this rank's GPU, recording per-step waypoints and host states,
+    and the planner state at the start of the timed region."""
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr, device=device)
+    pl.set_edt(*edt, cfg.world_res)
+    occupied = missions.occupied_nodes(m.boxes, cfg.grid_res)
+    N = m.n_agents
+    wp = pl.start.copy()
+    goal_des = m.goal.astype(np.float32)
+    rec = {"wp": [], "pos": [], "vel": [], "acc": []}
+    snap = None
+    traj = None
+    fails = 0
+    for t in range(args.settle + n_steps):
+        pos, vel, acc = pl.state()
+        goal_cur = pl.goal()
+        wp = missions.next_waypoints(wp, goal_cur, goal_des, traj, pos, cfg, occupied)
+        if t == args.settle:
+            snap = {"records": pl.get_records(), "sfc": pl.sfc(), "acc": acc.copy(), "seq": pl.seq}
+        if t >= args.settle:
+            rec["wp"].append(wp.copy()); rec["pos"].append(pos); rec["vel"].append(vel); rec["acc"].append(acc)
+        pl.set_agents(waypoint=wp)
+        pl.plan()
+        traj = pl.traj()
+        st = pl.status()
+        fails += int(((st & capi.FAIL_MASK) != 0).sum())
+        pl.advance()
+    snap["final_traj"] = traj
+    snap["nbr_overflow"] = int(((st & capi.NBR_OVERFLOW) != 0).sum())
+    snap["fails"] = fails
+    snap["dist_to_goal"] = float(np.mean(np.max(np.abs(pl.state()[0] - goal_des), axis=1)))
+    pl.close()
+    return {k: np.array(v) for k, v in rec.items()}, snap
+
+
+def restore(pl, snap, sl):
+    pl.set_records(0, snap["records"])
+    pl.set_sfc(snap["sfc"][sl], np.zeros(pl.NL, np.uint8))
+    pl.set_agents(acc=snap["acc"][sl])
+    pl.seq = snap["seq"]
+
+
+def qp_flops(cfg, nbr_cnt, iters, np_rows_nnz):
+    """iterations x [assemble 9 R_pt + 4 nnz(dyn, comm) + factor n^3/3 + 2*2 n^2 solves]."""
+    M, P, D = cfg.M, cfg.n + 1, cfg.dim
+    ny = D * (3 * M - 2)
+    r_pt = nbr_cnt.astype(np.float64) * (M * P - 3) + 2 * D * (M * P - 3)
+    per_iter = 9.0 * r_pt + 4.0 * np_rows_nnz + ny ** 3 / 3.0 + 4.0 * ny ** 2
+    return float(np.sum(iters.astype(np.float64) * per_iter))
+
+
+def pair_nnz(cfg):
+    """non-zeros of the velocity / acceleration / comm-range rows in x-space, both sides"""
+    M, n, D = cfg.M, cfg.n, cfg.dim
+    vel = D * (M * n - 2) * 2 * 2
+    acc = D * (M * (n - 1) - 1) * 3 * 2
+    comm = D * (M * (M + 1) // 2) * 2 * 2 if cfg.comm_range > 0 else 0
+    return vel + acc + comm
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    W, K = max(args.warmup, 3), args.steps
+    cfg, m, edt = make_world(args)
+    N = m.n_agents
+    assert N % world == 0, "agents must divide over the ranks"
+    NL, begin = N // world, rank * (N // world)
+    sl = slice(begin, begin + NL)
+
+    rec, snap = pilot_rollout(cfg, m, edt, args, dev.index, W + K)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr, begin=begin, n_local=NL, device=dev.index)
+    pl.set_edt(*edt, cfg.world_res)
+    pl.set_stream(torch.cuda.current_stream().cuda_stream)
+    rec_t = torch.zeros(N * pl.rec_floats, dtype=torch.float32, device=dev)
+    pl.bind_records(rec_t.data_ptr())
+    rec_local = rec_t[begin * pl.rec_floats:(begin + NL) * pl.rec_floats]
+    wp_dev = torch.from_numpy(np.ascontiguousarray(rec["wp"][:, sl])).to(dev)        # [T][NL][3] resident
+    peak_fp64 = pl.measure_fp64_peak()
+
+    def gather():
+        if world > 1:
+            dist.all_gather_into_tensor(rec_t, rec_local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident: plan -> advance -> all-gather, everything on the device ----------------
+    restore(pl, snap, sl)
+    barrier()
+    for t in range(W):
+        pl.set_waypoints_device(wp_dev[t].data_ptr())
+        pl.plan(); pl.advance(); gather()
+    barrier()
+    launches0 = pl.launch_count()
+    pl.enable_timing(True)
+    clocks = Clocks(dev.index)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record()
+    for t in range(K):
+        pl.set_waypoints_device(wp_dev[W + t].data_ptr())
+        pl.plan(); pl.advance(); gather()
+        ev[t + 1].record()
+    barrier()
+    clk = clocks.stop()
+    stage_ms, n_timed = pl.timings()
+    pl.enable_timing(False)
+    launches = pl.launch_count() - launches0
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    total_ms = ev[0].elapsed_time(ev[K])
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    resident_final = pl.traj()
+    replay_exact = bool(np.array_equal(resident_final, snap["final_traj"][sl]))
+
+    # ---------------- work counters of the timed region (untimed replay, deterministic) ----------------
+    restore(pl, snap, sl)
+    flops, gjk_iters, edt_lookups, qp_iter_sum, pairs = 0.0, 0, 0, 0, 0
+    nnz = pair_nnz(cfg)
+    n_prof = min(K, 10)
+    for t in range(W + n_prof):
+        pl.set_waypoints_device(wp_dev[t].data_ptr())
+        pl.plan()
+        if t >= W:
+            c = pl.counters()
+            _, cnt = pl.neighbours()
+            it = pl.qp_iters()
+            flops += qp_flops(cfg, cnt, it, nnz)
+            gjk_iters += c["gjk_iters"]; edt_lookups += c["edt_lookups"]; qp_iter_sum += c["qp_iters"]; pairs += c["pairs"]
+        pl.advance(); gather()
+    flops /= n_prof
+    qp_ms = stage_ms["qp"]
+    achieved_tf = flops / (qp_ms * 1e-3) / 1e12 if qp_ms > 0 else 0.0
+
+    # ---------------- e2e: host buffers in, host buffers out, every step ----------------
+    restore(pl, snap, sl)
+    hb = {k: pinned(rec[k][:, sl].shape, torch.float32) for k in ("pos", "vel", "acc", "wp")}
+    for k in hb:
+        hb[k][1][...] = rec[k][:, sl]
+    traj_t, traj_h = pinned((NL, cfg.M, cfg.n + 1, 3), torch.float32)
+    structs = [capi.DlscAgents(hb["pos"][1][t].ctypes.data, hb["vel"][1][t].ctypes.data, hb["acc"][1][t].ctypes.data,
+                               hb["wp"][1][t].ctypes.data, None) for t in range(W + K)]
+    import ctypes as C
+
+    def e2e_step(t):
+        pl.set_agents_async(structs[t])
+        gather()
+        pl.plan()
+        pl.publish_records()
+        pl._ck(pl.lib.dlsc_get_traj(pl.ctx, C.c_void_p(traj_h.ctypes.data)))     # D2H + stream sync
+
+    barrier()
+    for t in range(W):
+        e2e_step(t)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for t in range(K):
+        e2e_step(W + t)
+    e1.record()
+    barrier()
+    t_host = (time.perf_counter() - t_host0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    tt = torch.tensor([e2e_ms, t_host], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tt[0].item())
+    e2e_exact = bool(np.array_equal(traj_h, snap["final_traj"][sl]))
+    h2d = int(4 * NL * 12 * world)
+    d2h = int(NL * cfg.M * (cfg.n + 1) * 12 * world)
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tot_stage = sum(stage_ms.values())
+        out = {
+            "metric": METRIC, "value": N * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "p50_step_ms": statistics.median(step_ms), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic %d-agent 3D random-forest swarm (BASELINE configs[3]): M=10 n=5 dim=3, "
+                                   "SFC on a %dx%dx%d EDT grid, comm range 3, max_nbr %d" % (
+                                       N, edt[2][0], edt[2][1], edt[2][2], args.max_nbr),
+                       "agents": N, "agents_per_gpu": NL, "settle_steps": args.settle, "parallelism": "agents sharded x%d, "
+                       "NCCL all-gather of %d-float records per step" % (world, pl.rec_floats),
+                       "l2": "per-step working set (EDT grid %.0f MB + scratch) exceeds L2; inputs change every step" % (
+                           edt[0].size * 16 / 1e6)},
+            "e2e": {"value": N * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K, "replay_exact": e2e_exact},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_qp", "bound": "fp64", "achieved": achieved_tf, "peak": peak_fp64, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_fp64 if peak_fp64 > 0 else None, "traffic": None,
+                         "peak_source": "dlsc_measure_fp64_peak (DFMA chains, measured in this run; MEASURED_PEAKS.json "
+                                        "has no FP64 figure)",
+                         "flops_per_launch": flops, "kernel_ms": qp_ms,
+                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "stages_ms": stage_ms, "qp_share": qp_ms / tot_stage if tot_stage > 0 else None,
+            "work_per_step": {"pairs": pairs / n_prof, "gjk_iters": gjk_iters / n_prof, "edt_lookups": edt_lookups / n_prof,
+                              "qp_iters": qp_iter_sum / n_prof},
+            "pilot": {"qp_failsafe_agents": snap["fails"], "nbr_overflow_agents": snap["nbr_overflow"],
+                      "mean_dist_to_goal_m": snap["dist_to_goal"], "replay_exact": replay_exact},
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(cfg, m, edt, rec, snap, args, steps=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    pl.close()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------
+def oracle_swarm(cfg, m, edt, snap, rec, args, n_threads):
+    """The CPU oracle (oracle/: test infrastructure, here only as the timed CPU baseline) loaded with the
+    planner state at the start of the timed region."""
+    from oracle import oracle_py as O
+    O.build()
+    p = O.make_params(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, use_sfc=cfg.use_sfc, dt=cfg.dt,
+                      world_min=m.world_min, world_max=m.world_max, world_res=cfg.world_res, grid_res=cfg.grid_res,
+                      z_2d=cfg.z_2d, comm_range=cfg.comm_range, w_control=cfg.w_control, w_terminal=cfg.w_terminal,
+                      reset_threshold=cfg.reset_threshold)
+    e = O.Edt(p, edt[0], edt[1], edt[2], edt[3])
+    sw = O.Swarm(p, m.start, m.goal, m.radius, m.downwash, m.max_vel, m.max_acc, m.nominal_vel, edt=e,
+                 max_nbr=args.max_nbr, n_threads=n_threads)
+    N, o = m.n_agents, cfg.M * (cfg.n + 1) * 3
+    r = snap["records"]
+    sw.traj[...] = r[:, :o].reshape(sw.traj.shape)
+    sw.pos[...] = r[:, o:o + 3]; sw.vel[...] = r[:, o + 3:o + 6]; sw.goal_cur[...] = r[:, o + 6:o + 9]
+    sw.acc[...] = snap["acc"]; sw.sfc[...] = snap["sfc"]; sw.sfc_init[...] = 0
+    sw.waypoint[...] = rec["wp"][0]
+    sw.seq = snap["seq"]
+    return sw
+
+
+def cpu_baseline(cfg, m, edt, rec, snap, args, steps=1):
+    cores = os.cpu_count() or 1
+    sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
+    N = m.n_agents
+    probe = min(N, 4 * cores)
+    seq0 = sw.seq
+    t0 = time.perf_counter(); sw.step(0, probe); t_probe = time.perf_counter() - t0
+    sw.seq = seq0
+    n = int(min(N, max(probe, args.cpu_seconds / max(t_probe / probe, 1e-9))))
+    n = max(cores, (n // cores) * cores)
+    sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
+    t0 = time.perf_counter(); sw.step(0, n); t = time.perf_counter() - t0
+    ok = int(((sw.status[:n] & capi.FAIL_MASK) == 0).sum())
+    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "agents [0,%d) of the same %d-agent swarm at the first timed step, one replan each, one agent per "
+                      "thread on %d threads (oracle/ C++ port; the reference itself needs ROS+CPLEX and cannot run here); "
+                      "%d/%d QPs converged; %.1f s" % (n, N, cores, ok, n, t),
+            "stage_seconds": [float(x) for x in sw.stage_seconds]}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (here: the oracle port, see DESIGN.md --
+    the literal ROS + CPLEX build is impossible in this image) on all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, K = max(args.warmup, 1), args.steps
+    cfg, m, edt = make_world(args)
+    N = m.n_agents
+    # state at the start of the timed region: produced by the GPU pilot when a GPU is there, else a cold start
+    try:
+        lib = capi.load_library()
+        have_gpu = lib.dlsc_device_count() > 0
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        rec, snap = pilot_rollout(cfg, m, edt, args, 0, 1)
+    else:
+        start = m.start.astype(np.float32)
+        o = cfg.M * (cfg.n + 1) * 3
+        records = np.zeros((N, o + 12), np.float32)
+        records[:, :o] = np.tile(start, (1, cfg.M * (cfg.n + 1)))
+        records[:, o:o + 3] = start; records[:, o + 6:o + 9] = start
+        snap = {"records": records, "sfc": np.zeros((N, cfg.M, 6), np.float32), "acc": np.zeros((N, 3), np.float32), "seq": 0}
+        rec = {"wp": start[None]}
+    cores = os.cpu_count() or 1
+    sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
+    if not have_gpu:
+        sw.sfc_init[...] = 1
+    probe = min(N, 4 * cores)
+    t0 = time.perf_counter(); sw.step(0, probe); t_probe = time.perf_counter() - t0
+    budget = 120.0 / (W + K)                              # whole run within a few minutes
+    n = int(min(N, max(cores, budget / max(t_probe / probe, 1e-9))))
+    n = max(cores, (n // cores) * cores)
+    times = []
+    for s in range(W + K):
+        sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
+        if not have_gpu:
+            sw.sfc_init[...] = 1
+        t0 = time.perf_counter(); sw.step(0, n); dt = time.perf_counter() - t0
+        if s >= W:
+            times.append(dt)
+    total = sum(times)
+    val = n * K / total
+    sample = ("each step: agents [0,%d) of the %d-agent swarm, one replan each, one agent per thread on %d host threads" % (
+        n, N, cores))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": total / K * 1e3 * (N / n), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %d-agent 3D random-forest swarm (BASELINE configs[3])" % N, "agents": N},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "ms_per_step is extrapolated from the bounded sample to the full swarm",
+    }))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -52,7 +52,8 @@ EXPORTS = (
     "dlsc_publish_records dlsc_sync dlsc_get_seq dlsc_set_seq dlsc_get_traj dlsc_get_qp_x dlsc_get_cost "
     "dlsc_get_violation dlsc_get_qp_iters dlsc_get_status dlsc_get_goal dlsc_get_state dlsc_get_init_traj "
     "dlsc_get_pred_traj dlsc_get_neighbours dlsc_get_lsc dlsc_get_sfc dlsc_set_sfc dlsc_enable_timing "
-    "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device").split()
+    "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device "
+    "dlsc_set_waypoints_device dlsc_measure_fp64_peak").split()
 
 
 def build_library(force=False):
@@ -291,6 +292,17 @@ class SwarmPlanner:
 
     def launch_count(self):
         return int(self.lib.dlsc_launch_count(self.ctx))
+
+    def set_waypoints_device(self, device_ptr):
+        self._ck(self.lib.dlsc_set_waypoints_device(self.ctx, C.c_void_p(int(device_ptr))))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.dlsc_set_stream(self.ctx, C.c_void_p(int(cuda_stream))))
+
+    def measure_fp64_peak(self):
+        v = C.c_double(0)
+        self._ck(self.lib.dlsc_measure_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
 
     def records_device_ptr(self):
         return int(self.lib.dlsc_records_device(self.ctx))

@@ -36,7 +36,8 @@ struct dlsc_ctx {
     int4* edt_cells = nullptr;
     int64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev[DLSC_N_STAGES + 1];
+    std::vector<cudaEvent_t> evpool;   // (DLSC_N_STAGES + 1) events per timed step, resolved lazily
+    int ev_used = 0;                   // steps recorded since the last dlsc_get_timings
     double t_ms[DLSC_N_STAGES];
     int t_steps = 0;
     std::vector<void*> allocs;
@@ -157,7 +158,6 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
-    for (auto& e : c->ev) CK(cudaEventCreate(&e));
     memset(c->t_ms, 0, sizeof(c->t_ms));
 
     DevState& S = c->S;
@@ -210,7 +210,7 @@ void dlsc_destroy(dlsc_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->tab_blob) cudaFree(c->tab_blob);
     if (c->edt_cells) cudaFree(c->edt_cells);
-    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->evpool) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -323,30 +323,27 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
     cudaStream_t st = c->stream;
     const int seq = c->seq + 1;     // planner_seq after the increment in TrajPlanner::plan (traj_planner.cpp:40)
     const bool tm = c->timing;
+    cudaEvent_t* ev = nullptr;
+    if (tm) {
+        const size_t need = (size_t)(c->ev_used + 1) * (DLSC_N_STAGES + 1);
+        while (c->evpool.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->evpool.push_back(e); }
+        ev = c->evpool.data() + (size_t)c->ev_used * (DLSC_N_STAGES + 1);
+    }
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
         CK(cudaMemsetAsync(c->S.counters, 0, 8 * sizeof(unsigned long long), st));
-    if (tm) CK(cudaEventRecord(c->ev[0], st));
+    if (tm) CK(cudaEventRecord(ev[0], st));
     if (mask & DLSC_STAGE_PREDICT) { launch_predict(c->P, c->S, seq, st); c->launches++; }
-    if (tm) CK(cudaEventRecord(c->ev[1], st));
+    if (tm) CK(cudaEventRecord(ev[1], st));
     if (mask & DLSC_STAGE_NBR) { launch_neighbours(c->P, c->S, st); c->launches++; }
-    if (tm) CK(cudaEventRecord(c->ev[2], st));
+    if (tm) CK(cudaEventRecord(ev[2], st));
     if (mask & DLSC_STAGE_LSC) { launch_lsc(c->P, c->S, st); c->launches++; }
-    if (tm) CK(cudaEventRecord(c->ev[3], st));
+    if (tm) CK(cudaEventRecord(ev[3], st));
     if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc) { launch_sfc(c->P, c->S, st); c->launches++; }
-    if (tm) CK(cudaEventRecord(c->ev[4], st));
+    if (tm) CK(cudaEventRecord(ev[4], st));
     if (mask & DLSC_STAGE_GOAL) { launch_goal(c->P, c->S, st); c->launches++; }
-    if (tm) CK(cudaEventRecord(c->ev[5], st));
+    if (tm) CK(cudaEventRecord(ev[5], st));
     if (mask & DLSC_STAGE_QP) { launch_qp(c->P, c->S, c->T, c->qpl, st); c->launches++; }
-    if (tm) {
-        CK(cudaEventRecord(c->ev[6], st));
-        CK(cudaEventSynchronize(c->ev[6]));
-        for (int i = 0; i < DLSC_N_STAGES; i++) {
-            float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
-            c->t_ms[i] += ms;
-        }
-        c->t_steps++;
-    }
+    if (tm) { CK(cudaEventRecord(ev[6], st)); c->ev_used++; }
     CK(cudaGetLastError());
     return 0;
 }
@@ -457,10 +454,25 @@ int dlsc_enable_timing(dlsc_ctx* c, int on) {
     c->timing = on != 0;
     memset(c->t_ms, 0, sizeof(c->t_ms));
     c->t_steps = 0;
+    c->ev_used = 0;
     return 0;
 }
 int dlsc_get_timings(dlsc_ctx* c, double ms[DLSC_N_STAGES], int* n_steps) {
     if (!c || !ms) return fail("null argument");
+    CK(cudaSetDevice(c->device));
+    if (c->ev_used > 0) {
+        CK(cudaStreamSynchronize(c->stream));
+        for (int s2 = 0; s2 < c->ev_used; s2++) {
+            cudaEvent_t* ev = c->evpool.data() + (size_t)s2 * (DLSC_N_STAGES + 1);
+            for (int i = 0; i < DLSC_N_STAGES; i++) {
+                float t = 0.f;
+                CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+                c->t_ms[i] += t;
+            }
+            c->t_steps++;
+        }
+        c->ev_used = 0;
+    }
     for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = c->t_steps ? c->t_ms[i] / c->t_steps : 0.0;
     if (n_steps) *n_steps = c->t_steps;
     memset(c->t_ms, 0, sizeof(c->t_ms));
@@ -470,6 +482,20 @@ int dlsc_get_timings(dlsc_ctx* c, double ms[DLSC_N_STAGES], int* n_steps) {
 int64_t dlsc_launch_count(const dlsc_ctx* c) { return c ? c->launches : 0; }
 int dlsc_get_counters(dlsc_ctx* c, int64_t counters[8]) {
     return c ? d2h(c, counters, c->S.counters, 8 * sizeof(int64_t)) : fail("null ctx");
+}
+int dlsc_set_waypoints_device(dlsc_ctx* c, const float* p) {
+    if (!c || !p) return fail("dlsc_set_waypoints_device: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->S.waypoint, p, (size_t)c->P.NL * 12, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int dlsc_measure_fp64_peak(dlsc_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail("dlsc_measure_fp64_peak: null argument");
+    CK(cudaSetDevice(c->device));
+    *tflops = measure_fp64_peak(c->device, c->stream);
+    c->launches += 4;
+    CK(cudaGetLastError());
+    return 0;
 }
 float* dlsc_waypoint_device(dlsc_ctx* c) { return c ? c->S.waypoint : nullptr; }
 float* dlsc_traj_device(dlsc_ctx* c) { return c ? c->S.traj : nullptr; }

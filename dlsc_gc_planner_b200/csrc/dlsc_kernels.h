@@ -48,6 +48,7 @@ void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t
 void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
 
+double measure_fp64_peak(int device, cudaStream_t st);
 QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device);
 void launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);
 

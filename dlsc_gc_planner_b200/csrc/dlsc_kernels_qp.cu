@@ -77,4 +77,40 @@ void launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLa
     k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles);
 }
 
+// ---- FP64 FMA peak probe: 8 independent dependent-FMA chains per thread, 1024 threads, 2 CTAs per SM ----
+__global__ void __launch_bounds__(1024) k_fp64_peak(double* sink, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, b = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+
+double measure_fp64_peak(int device, cudaStream_t st) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    double* sink = nullptr;
+    cudaMalloc(&sink, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000, ctas = sms * 2;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, st);
+        k_fp64_peak<<<ctas, 1024, 0, st>>>(sink, iters);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * 1024.0 * ctas / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
 }  // namespace dlsc

@@ -172,8 +172,9 @@ int dlsc_get_neighbours(dlsc_ctx* ctx, int32_t* idx /* [n_local][K] */, int32_t*
 int dlsc_get_lsc(dlsc_ctx* ctx, float* normal, float* anchor, double* d);
 int dlsc_get_sfc(dlsc_ctx* ctx, float* sfc /* [n_local][M][6] min xyz, max xyz */);
 int dlsc_set_sfc(dlsc_ctx* ctx, const float* sfc, const uint8_t* init_flag /* [n_local] or NULL */);
-/* mean device milliseconds per stage over the steps since the last call (CUDA events; only
- * recorded while dlsc_enable_timing(ctx,1)); order: predict, nbr, lsc, sfc, goal, qp. */
+/* mean device milliseconds per stage over the steps since the last call (CUDA events recorded on the
+ * context's stream around every stage while dlsc_enable_timing(ctx,1); resolved, with one
+ * synchronisation, by dlsc_get_timings); order: predict, nbr, lsc, sfc, goal, qp. */
 int dlsc_enable_timing(dlsc_ctx* ctx, int on);
 int dlsc_get_timings(dlsc_ctx* ctx, double ms[DLSC_N_STAGES], int* n_steps);
 /* kernels launched by this context so far */
@@ -181,6 +182,12 @@ int64_t dlsc_launch_count(const dlsc_ctx* ctx);
 /* work counters of the last step summed over the local block (for roofline arithmetic):
  * [0] neighbour pairs, [1] GJK iterations, [2] EDT lookups, [3] QP iterations, [4] QP rows */
 int dlsc_get_counters(dlsc_ctx* ctx, int64_t counters[8]);
+
+/* Waypoints already resident on the device ([n_local][3] float32): stream-ordered device copy. */
+int dlsc_set_waypoints_device(dlsc_ctx* ctx, const float* device_ptr);
+/* Sustained FP64 FMA rate of the device in TFLOP/s (dependent DFMA chains on every SM for ~ms): the
+ * denominator of the FP64 roofline of the LSC and QP kernels (MEASURED_PEAKS.json has no FP64 figure). */
+int dlsc_measure_fp64_peak(dlsc_ctx* ctx, double* tflops);
 
 /* Device pointers of per-step input / output arrays, for callers that keep data on the GPU. */
 float* dlsc_waypoint_device(dlsc_ctx* ctx);   /* [n_local][3] */

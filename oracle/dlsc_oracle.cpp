@@ -1392,8 +1392,14 @@ int orc_qp_solve(const orc_params* p, const float pos[3], const float vel[3], co
 }
 
 // traj_planner.cpp:108-133 for every agent, agents in index order (multi_sync_simulator.cpp:516-524)
-void orc_step(const orc_params* p, orc_step_io* io) {
+void orc_step(const orc_params* p, orc_step_io* io) { orc_step_range(p, io, 0, io->N); }
+
+// Same as orc_step, but only the agents [a_begin, a_end) are replanned (prediction and neighbour lists are
+// still built for the whole swarm, they are inputs of the replanned agents).  Used for bounded CPU-baseline
+// samples of large swarms.
+void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end) {
     const int N = io->N, M = p->M, P = P_of(p), K = io->max_nbr;
+    const int NR = a_end - a_begin;
     const size_t L = traj_len(p);
     double t0 = now_s();
     for (int a = 0; a < N; a++) io->status[a] = ORC_OK;
@@ -1402,7 +1408,8 @@ void orc_step(const orc_params* p, orc_step_io* io) {
         for (int a = 0; a < N; a++) io->status[a] |= ORC_NBR_OVERFLOW;
     double t1 = now_s();
     const int nt = io->n_threads > 1 ? io->n_threads : 1;
-    parallel_for(N, nt, [&](int a) {
+    parallel_for(NR, nt, [&](int ar) {
+        const int a = a_begin + ar;
         for (int c = 0; c < io->nbr_cnt[a]; c++) {
             int j = io->nbr_idx[(size_t)a * K + c];
             size_t pr = (size_t)a * K + c;
@@ -1413,7 +1420,8 @@ void orc_step(const orc_params* p, orc_step_io* io) {
     });
     double t2 = now_s();
     if (p->use_sfc) {
-        parallel_for(N, nt, [&](int a) {
+        parallel_for(NR, nt, [&](int ar) {
+            const int a = a_begin + ar;
             bool init = io->sfc_init_flag[a] != 0 || (io->disturbed && io->disturbed[a]);   // traj_planner.cpp:439, 693-695
             int st = sfc_agent(p, io->edt, init, vec3f(io->pos + 3 * a), io->init_traj + L * a,
                                vec3f(io->goal_cur + 3 * a), vec3f(io->waypoint + 3 * a), io->radius[a],
@@ -1425,7 +1433,7 @@ void orc_step(const orc_params* p, orc_step_io* io) {
     double t3 = now_s();
     // goal planning must see every neighbour's PREVIOUS goal in the LSC stage above; update after it.
     std::vector<float> new_goal(io->goal_cur, io->goal_cur + (size_t)3 * N);
-    for (int a = 0; a < N; a++) {
+    for (int a = a_begin; a < a_end; a++) {
         vec3f g(io->goal_cur + 3 * a);
         size_t pr = (size_t)a * K;
         int st = goal_agent(p, io->disturbed && io->disturbed[a], vec3f(io->pos + 3 * a), vec3f(io->waypoint + 3 * a),
@@ -1438,7 +1446,8 @@ void orc_step(const orc_params* p, orc_step_io* io) {
     std::memcpy(io->goal_cur, new_goal.data(), sizeof(float) * 3 * N);
     double t4 = now_s();
     const int nxa = p->dim * M * P;
-    parallel_for(N, nt, [&](int a) {
+    parallel_for(NR, nt, [&](int ar) {
+        const int a = a_begin + ar;
         size_t pr = (size_t)a * K;
         std::vector<float> out(L);
         double cost = 0, viol = 0;

@@ -149,6 +149,8 @@ typedef struct orc_step_io {
     double* stage_seconds;   /* [5]: predict+nbr, lsc, sfc, goal, qp (wall) or NULL */
 } orc_step_io;
 void orc_step(const orc_params* p, orc_step_io* io);
+/* replan only agents [a_begin, a_end) (bounded CPU-baseline samples of large swarms) */
+void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end);
 
 /* Trajectory::getStateAt (trajectory.cpp:111-170): state[9] = pos, vel, acc (float) */
 void orc_state_at(const orc_params* p, const float* traj, double t, float state[9]);

@@ -222,8 +222,8 @@ class Swarm:
         self.status = np.zeros(N, np.int32)
         self.stage_seconds = np.zeros(5)
 
-    def step(self):
-        """One replan of every agent (TrajPlanner::plan for all agents)."""
+    def step(self, a_begin=None, a_end=None):
+        """One replan of every agent (TrajPlanner::plan for all agents), or of agents [a_begin, a_end)."""
         self.seq += 1
         io = OrcStepIO()
         io.N, io.seq, io.max_nbr, io.n_threads = self.N, self.seq, self.K, self.n_threads
@@ -235,7 +235,10 @@ class Swarm:
         io.prev_traj = self.traj.ctypes.data
         io.sfc_init_flag = self.sfc_init.ctypes.data
         io.edt = C.addressof(self.edt.c) if self.edt is not None else None
-        lib().orc_step(C.byref(self.p), C.byref(io))
+        if a_begin is None:
+            lib().orc_step(C.byref(self.p), C.byref(io))
+        else:
+            lib().orc_step_range(C.byref(self.p), C.byref(io), C.c_int(a_begin), C.c_int(a_end))
         return self.status
 
     def advance(self):

@@ -355,4 +355,12 @@ int64_t dlsc_launch_count(const dlsc_ctx*) { return 0; }
 int dlsc_enable_timing(dlsc_ctx*, int) { return 0; }
 int dlsc_get_timings(dlsc_ctx*, double ms[DLSC_N_STAGES], int* n) { for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = 0; if (n) *n = 0; return 0; }
 
+int dlsc_set_waypoints_device(dlsc_ctx* c, const float* p) { memcpy(c->waypoint.data(), p, c->waypoint.size() * 4); return 0; }
+int dlsc_measure_fp64_peak(dlsc_ctx*, double* t) { *t = 0.0; return 0; }
+int dlsc_set_stream(dlsc_ctx*, void*) { return 0; }
+void* dlsc_get_stream(dlsc_ctx*) { return nullptr; }
+int dlsc_bind_records(dlsc_ctx*, float*) { return fail("hostsim: not supported"); }
+float* dlsc_waypoint_device(dlsc_ctx* c) { return c->waypoint.data(); }
+float* dlsc_traj_device(dlsc_ctx* c) { return c->traj.data(); }
+
 }  // extern "C"
