@@ -94,7 +94,7 @@ static int upload_tables(dlsc_ctx* c) {
     const size_t i_yp_ptr = SEC(yp_ptr), i_yp_pt = SEC(yp_pt), i_yp_coef = SEC(yp_coef);
     const size_t i_wi_ptr = SEC(wi_ptr), i_wi_row = SEC(wi_row), i_wi_coef = SEC(wi_coef);
     const size_t i_wp_ptr = SEC(wp_ptr), i_wp_pt = SEC(wp_pt), i_wp_coef = SEC(wp_coef);
-    const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2);
+    const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2), i_tri = SEC(tri_p);
 #undef SEC
     std::vector<char> blob(off ? off : 256, 0);
     for (auto& s : secs) memcpy(blob.data() + s.off, s.src, s.bytes);
@@ -114,7 +114,7 @@ static int upload_tables(dlsc_ctx* c) {
     T.yp_ptr = PTR(int, i_yp_ptr); T.yp_pt = PTR(int16_t, i_yp_pt); T.yp_coef = PTR(double, i_yp_coef);
     T.wi_ptr = PTR(int, i_wi_ptr); T.wi_row = PTR(int16_t, i_wi_row); T.wi_coef = PTR(double, i_wi_coef);
     T.wp_ptr = PTR(int, i_wp_ptr); T.wp_pt = PTR(int16_t, i_wp_pt); T.wp_coef = PTR(double, i_wp_coef);
-    T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2);
+    T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2); T.tri_p = PTR(uint8_t, i_tri);
 #undef PTR
     return 0;
 }
@@ -145,6 +145,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     c->rl = rec_layout(hp->M);
     P.rec = c->rl.size;
     P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
+    P.qp_screen = hp->qp_screen_slack == 0.0 ? 0.5 : hp->qp_screen_slack;
     P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
     P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
     P.reset_threshold = hp->reset_threshold;

@@ -7,7 +7,6 @@
 namespace dlsc {
 
 constexpr int kQpThreads = 128;
-constexpr int kQpGroup = 8;      // lanes cooperating on one control point in the LSC passes
 
 __global__ void __launch_bounds__(kQpThreads) k_qp(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ DevState S,
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(kQpThreads) k_qp(const __grid_constant__ DevPa
         out.x = S.qp_x + (size_t)la * T.nx;
         out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;
         out.rows = (threadIdx.x == 0) ? &rows : nullptr;
-        qp_agent(c, kQpGroup, P, T, in, out, sm, scratch);
+        qp_agent(c, P, T, in, out, sm, scratch);
         if (threadIdx.x == 0) { it_sum += (unsigned long long)S.qp_iters[la]; row_sum += (unsigned long long)rows; }
     }
     if (threadIdx.x == 0) {

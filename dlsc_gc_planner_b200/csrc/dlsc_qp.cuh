@@ -8,8 +8,13 @@
 //     lower triangle, is assembled by table-driven gathers (no atomics), factorised in place as
 //     L D L' (one __syncthreads per column) and solved by one warp with register-resident right-hand
 //     sides and warp shuffles;  FP64 pipe, no tensor cores (systems of 39..84 unknowns).
-//   * row state (slack s, dual z, corrector term) of all inequality rows stays in a per-CTA global
-//     scratch slab that is reused for every agent the CTA processes (L1/L2 resident).
+//   * LSC rows (57 x neighbours per agent, almost none active) go through an exact working-set screen:
+//     the QP is solved on the rows whose slack at the starting point is below a threshold, every row is
+//     then checked at the solution and, if one is violated, the solve is repeated on a wider set.  A
+//     relaxed optimum that is feasible for the full problem is the full optimum, so nothing is approximated.
+//   * row state (slack s, dual z, directions) stays in a per-CTA global scratch slab that is reused for
+//     every agent the CTA processes (L1/L2 resident); the compact LSC row list is sorted by control point
+//     so that its contributions are accumulated per point without atomics (deterministic).
 //
 // The core is __host__ __device__: the device build runs it with a 128-thread CTA, the test-only host
 // simulator with a single "thread" (tests/hostsim), so the arithmetic can be checked without a GPU.
@@ -54,14 +59,6 @@ struct Cta {
     }
 };
 
-// sum over a group of G (power of two <= 32) adjacent lanes; every lane of the warp must call it
-DLSC_HD double group_sum(double v, int G) {
-#ifdef __CUDA_ARCH__
-    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-#endif
-    return v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // per-agent inputs / outputs
 // ------------------------------------------------------------------------------------------------
@@ -86,11 +83,13 @@ struct QpOut {
 
 // shared-memory carve-up (doubles unless noted)
 struct QpSmem {
-    double *W, *invp, *y, *dy, *rd, *rhs, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
+    double *W, *invp, *y, *dy, *rd, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
+    int* off;                  // [npt + 2] segment offsets of the LSC row list (+ scratch word)
     uint8_t* act;              // [M][Kcap]
 };
 DLSC_HD size_t qp_smem_doubles(const QpTab& T) {
-    return (size_t)T.ntri + 5 * (size_t)T.ny + 4 * (size_t)T.nx + 3 * (size_t)T.np + 6 * (size_t)T.npt + 16 + 96;
+    return (size_t)T.ntri + 4 * (size_t)T.ny + 4 * (size_t)T.nx + 3 * (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
+           ((size_t)T.npt + 4) / 2 + 1;
 }
 DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
     return qp_smem_doubles(T) * sizeof(double) + (((size_t)T.M * Kcap + 15) / 16) * 16;
@@ -98,17 +97,22 @@ DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
 DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     double* p = base;
     s.W = p; p += T.ntri;
-    s.invp = p; p += T.ny; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny; s.rhs = p; p += T.ny;
+    s.invp = p; p += T.ny; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny;
     s.x = p; p += T.nx; s.dx = p; p += T.nx; s.ax1 = p; p += T.nx; s.ax2 = p; p += T.nx;
     s.V1 = p; p += T.np; s.V2 = p; p += T.np; s.DD = p; p += T.np;
     s.S = p; p += 6 * T.npt;
     s.cst = p; p += 16;
     s.red = p; p += 96;
+    s.off = reinterpret_cast<int*>(p); p += (T.npt + 4) / 2 + 1;
     s.act = reinterpret_cast<uint8_t*>(p);
     (void)Kcap;
 }
-// per-CTA global scratch (doubles): LSC rows [npt][Kcap] x {s,z,corr,b,ds,dz} ; pair rows [np] x 12
-DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) { return 6 * (size_t)T.npt * Kcap + 12 * (size_t)T.np; }
+// per-CTA global scratch (doubles): LSC row list [npt*Kcap] x {n0,n1,n2,b,s,z,c,ds,dz} + point index (int);
+// pair rows [np] x 12
+DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) {
+    const size_t LS = (size_t)T.npt * Kcap;
+    return 9 * LS + (LS + 1) / 2 + 12 * (size_t)T.np;
+}
 
 // ------------------------------------------------------------------------------------------------
 // L D L' of the packed lower triangle W (row-major: (i,k) at i(i+1)/2+k), in place.
@@ -187,15 +191,15 @@ DLSC_HD int sym_idx(int k, int kk) { return k >= kk ? k * (k + 1) / 2 + kk : kk 
 
 // x = c + T y  (or dx = T dy when cst == nullptr)
 DLSC_HD void map_x(const Cta& c, const QpTab& T, const double* y, const double* cst, double* x) {
-    for (int e = c.tid; e < T.nx; e += c.nthr) {
-        const int k = e / T.npt, pt = e - k * T.npt;
-        double v = 0.0;
-        const int ci = T.xm_cidx[pt];
-        if (cst && ci >= 0) v = cst[k * 3 + ci];
-        const int nv = T.xm_nv[pt];
-        for (int t = 0; t < nv; t++) v += T.xm_coef[pt * 3 + t] * y[k * T.nyd + T.xm_idx[pt * 3 + t]];
-        x[e] = v;
-    }
+    for (int k = 0; k < T.D; k++)
+        for (int pt = c.tid; pt < T.npt; pt += c.nthr) {
+            double v = 0.0;
+            const int ci = T.xm_cidx[pt];
+            if (cst && ci >= 0) v = cst[k * 3 + ci];
+            const int nv = T.xm_nv[pt];
+            for (int t = 0; t < nv; t++) v += T.xm_coef[pt * 3 + t] * y[k * T.nyd + T.xm_idx[pt * 3 + t]];
+            x[k * T.npt + pt] = v;
+        }
 }
 
 // uy[p] = sum_{pair rows} coef V[row] + sum_{points} coef ax[k][pt]
@@ -244,44 +248,39 @@ DLSC_HD double pair_act(const QpTab& T, int r, const double* y, const double* cs
     return v;
 }
 
-// one agent.  G = lanes cooperating on one control point in the LSC passes (power of two, divides 32).
-struct LscRow { int pt, m, cc; size_t o; double nk[3]; double act, gd; };
+// LSC row (pt, cc) of this agent:  -n.x <= b  with  b = -(n.anchor + d)   (traj_optimizer.cpp:412-450)
+struct LscRowData { double n0, n1, n2, b; };
+DLSC_HD LscRowData lsc_row_data(const DevParams& P, const QpIn& in, int pt, int cc) {
+    const int m = pt / kP, i = pt - m * kP;
+    const float* nr = in.normal + ((size_t)cc * P.M + m) * 3;
+    const float* an = (m < P.M - 1) ? in.pred_traj + ((size_t)in.nbr_idx[cc] * (P.M * kP) + pt) * 3
+                                    : in.anchor_last + cc * 3;
+    LscRowData r;
+    r.n0 = (double)nr[0]; r.n1 = (double)nr[1]; r.n2 = (P.D == 3) ? (double)nr[2] : 0.0;
+    double b = -in.d[((size_t)cc * P.M + m) * kP + i];
+    b -= r.n0 * (double)an[0];
+    b -= r.n1 * (double)an[1];
+    if (P.D == 3) b -= r.n2 * (double)an[2];
+    r.b = b;
+    return r;
+}
 
-DLSC_HD void qp_agent(const Cta& c, int G, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
+// one agent
+DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
                       const QpSmem& sm, double* scratch) {
     const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, nx = T.nx, np = T.np, Kc = P.K;
     const int K = in.K;
     const int n = kP - 1;
+    const bool D3 = (D == 3);
     const size_t LS = (size_t)npt * Kc;
-    double *lsc_s = scratch, *lsc_z = scratch + LS, *lsc_c = scratch + 2 * LS, *lsc_b = scratch + 3 * LS,
-           *lsc_ds = scratch + 4 * LS, *lsc_dz = scratch + 5 * LS;
-    double* pr = scratch + 6 * LS;
+    double *l_n0 = scratch, *l_n1 = scratch + LS, *l_n2 = scratch + 2 * LS, *l_b = scratch + 3 * LS,
+           *l_s = scratch + 4 * LS, *l_z = scratch + 5 * LS, *l_c = scratch + 6 * LS, *l_ds = scratch + 7 * LS,
+           *l_dz = scratch + 8 * LS;
+    int* l_pt = reinterpret_cast<int*>(scratch + 9 * LS);
+    double* pr = scratch + 9 * LS + (LS + 1) / 2;
     double *ps_hi = pr, *pz_hi = pr + np, *pc_hi = pr + 2 * np, *ps_lo = pr + 3 * np, *pz_lo = pr + 4 * np,
            *pc_lo = pr + 5 * np, *pb_hi = pr + 6 * np, *pb_lo = pr + 7 * np, *pd_sh = pr + 8 * np,
            *pd_zh = pr + 9 * np, *pd_sl = pr + 10 * np, *pd_zl = pr + 11 * np;
-    const int gid = c.tid / G, gl = c.tid - gid * G, ngr = c.nthr / G;
-
-    // visit every active LSC row once; f(row) gets the row activity -n.x and direction activity -n.dx
-    auto lsc_rows = [&](auto&& f) {
-        for (int base = 0; base < npt; base += ngr) {
-            const int pt = base + gid;
-            if (pt < npt && pt >= 3) {
-                const int m = pt / kP;
-                for (int cc = gl; cc < K; cc += G) {
-                    if (!sm.act[m * Kc + cc]) continue;
-                    const float* nr = in.normal + ((size_t)cc * M + m) * 3;
-                    LscRow r; r.pt = pt; r.m = m; r.cc = cc; r.o = (size_t)pt * Kc + cc;
-                    r.nk[0] = r.nk[1] = r.nk[2] = 0.0; r.act = 0.0; r.gd = 0.0;
-                    for (int k = 0; k < D; k++) {
-                        r.nk[k] = (double)nr[k];
-                        r.act -= r.nk[k] * sm.x[k * npt + pt];
-                        r.gd -= r.nk[k] * sm.dx[k * npt + pt];
-                    }
-                    f(r);
-                }
-            }
-        }
-    };
 
     // ---- constants of this agent ----
     QpConst qc;
@@ -300,7 +299,7 @@ DLSC_HD void qp_agent(const Cta& c, int G, const DevParams& P, const QpTab& T, c
         const double c2 = (double)v3_get(in.acc, k) * P.dt * P.dt / (n * (n - 1)) + 2 * c1 - c0;
         sm.cst[k * 3] = c0; sm.cst[k * 3 + 1] = c1; sm.cst[k * 3 + 2] = c2;
     }
-    // active LSC (m, c) pairs: neighbour present and normal not ~0 (:422-424)
+    // usable LSC (m, c) pairs: neighbour present and normal not ~0 (:422-424)
     for (int e = c.tid; e < M * Kc; e += c.nthr) {
         const int m = e / Kc, cc = e - m * Kc;
         uint8_t a = 0;
@@ -308,12 +307,11 @@ DLSC_HD void qp_agent(const Cta& c, int G, const DevParams& P, const QpTab& T, c
         sm.act[e] = a;
     }
     for (int p = c.tid; p < ny; p += c.nthr) sm.y[p] = 0.0;
-    for (int e = c.tid; e < nx; e += c.nthr) sm.dx[e] = 0.0;
     c.sync();
 
     const double wT = P.w_terminal, wT2 = 2.0 * P.w_terminal;
-    auto grad_x = [&](const double* x, int e) -> double {       // d/dx of  w_u x'Qx + w_T (x_n - goal)^2
-        const int k = e / npt, pt = e - k * npt, m = pt / kP, i = pt - m * kP;
+    auto grad_x = [&](const double* x, int k, int pt) -> double {   // d/dx of  w_u x'Qx + w_T (x_n - goal)^2
+        const int m = pt / kP, i = pt - m * kP;
         const double* xs = x + k * npt + m * kP;
         double v = 0.0;
 #pragma unroll
@@ -324,292 +322,341 @@ DLSC_HD void qp_agent(const Cta& c, int G, const DevParams& P, const QpTab& T, c
     // ---- g_inf: gradient of the objective at y = 0 ----
     map_x(c, T, sm.y, sm.cst, sm.x);
     c.sync();
-    for (int e = c.tid; e < nx; e += c.nthr) sm.ax1[e] = grad_x(sm.x, e);
+    for (int k = 0; k < D; k++)
+        for (int pt = c.tid; pt < npt; pt += c.nthr) sm.ax1[k * npt + pt] = grad_x(sm.x, k, pt);
     for (int r = c.tid; r < np; r += c.nthr) sm.V1[r] = 0.0;
     c.sync();
     double g_inf = 0.0;
     for (int p = c.tid; p < ny; p += c.nthr) { const double v = fabs(gather_y(T, p, sm.V1, sm.ax1)); if (v > g_inf) g_inf = v; }
     { double d0 = 0.0, d1 = 0.0; c.reduce3(g_inf, 1, d0, 0, d1, 0); }
-
-    // ---- starting point: free control points of the initial trajectory ----
-    for (int p = c.tid; p < ny; p += c.nthr) {
-        const int k = p / nyd, a = p - k * nyd;
-        const int m = a / 3, j = (m == M - 1) ? 2 : a - 3 * m;
-        sm.y[p] = (double)in.init_traj[(m * kP + 3 + j) * 3 + k];
-    }
-    c.sync();
-    map_x(c, T, sm.y, sm.cst, sm.x);
-    c.sync();
-
-    // ---- rows: bounds, slack / dual initialisation ----
-    double n_rows = 0.0;
+    // pair-row bounds
     for (int r = c.tid; r < np; r += c.nthr) {
         double lo, hi;
         pair_bounds(P, T, in, qc, r, lo, hi);
-        const double act = pair_act(T, r, sm.y, sm.cst);
         pb_hi[r] = hi; pb_lo[r] = lo;
-        double s = hi - act; if (s < 1e-2) s = 1e-2;
-        ps_hi[r] = s; pz_hi[r] = 1.0 / s * 1e-2;
-        s = act - lo; if (s < 1e-2) s = 1e-2;
-        ps_lo[r] = s; pz_lo[r] = 1.0 / s * 1e-2;
-        n_rows += 2.0;
     }
-    lsc_rows([&](const LscRow& r) {
-        const int i = r.pt - r.m * kP;
-        const float* nr = in.normal + ((size_t)r.cc * M + r.m) * 3;
-        const float* an = (r.m < M - 1) ? in.pred_traj + ((size_t)in.nbr_idx[r.cc] * npt + r.pt) * 3
-                                        : in.anchor_last + r.cc * 3;
-        double b = -in.d[((size_t)r.cc * M + r.m) * kP + i];                          // -n.x <= -(n.anchor + d)
-        for (int k = 0; k < D; k++) b -= (double)nr[k] * (double)an[k];
-        double s = b - r.act; if (s < 1e-2) s = 1e-2;
-        lsc_b[r.o] = b; lsc_s[r.o] = s; lsc_z[r.o] = 1.0 / s * 1e-2;
-        n_rows += 1.0;
-    });
-    { double d0 = 0.0, d1 = 0.0; c.reduce3(n_rows, 0, d0, 0, d1, 0); }
-    if (out.rows && c.tid == 0) *out.rows = (long long)n_rows;
-    const double inv_rows = n_rows > 0 ? 1.0 / n_rows : 0.0;
 
     int status = kStQpMaxIter;
-    int it = 0;
+    int it_total = 0;
+    double viol_lsc = 0.0;
+    long long rows_total = 0;
+    double tau = P.qp_screen;
     const int max_it = P.qp_max_iter;
-    for (it = 0; it < max_it; it++) {
-        // ================= pass 1: residuals, G'z, affine rhs, D = z/s =================
-        for (int e = c.tid; e < nx; e += c.nthr) { sm.ax1[e] = grad_x(sm.x, e); sm.ax2[e] = 0.0; }
-        c.sync();
-        double rp_inf = 0.0, mu = 0.0;
-        for (int r = c.tid; r < np; r += c.nthr) {
-            const double act = pair_act(T, r, sm.y, sm.cst);
-            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
-            const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
-            rp_inf = fmax(rp_inf, fmax(fabs(rph), fabs(rpl)));
-            mu += sh * zh + sl * zl;
-            sm.V1[r] = zh - zl;
-            sm.V2[r] = (-(sh * zh) + zh * rph) / sh - (-(sl * zl) + zl * rpl) / sl;
-            sm.DD[r] = zh / sh + zl / sl;
-        }
-        for (int base = 0; base < npt; base += ngr) {
-            const int pt = base + gid;
-            const bool valid = pt < npt && pt >= 3;
-            double u1[3] = {0, 0, 0}, u2[3] = {0, 0, 0}, S[6] = {0, 0, 0, 0, 0, 0};
-            if (valid) {
-                const int m = pt / kP;
-                for (int cc = gl; cc < K; cc += G) {
-                    if (!sm.act[m * Kc + cc]) continue;
-                    const float* nr = in.normal + ((size_t)cc * M + m) * 3;
-                    const size_t o = (size_t)pt * Kc + cc;
-                    const double s = lsc_s[o], z = lsc_z[o];
-                    double nk[3] = {0, 0, 0}, act = 0.0;
-                    for (int k = 0; k < D; k++) { nk[k] = (double)nr[k]; act -= nk[k] * sm.x[k * npt + pt]; }
-                    const double rp = act + s - lsc_b[o];
-                    rp_inf = fmax(rp_inf, fabs(rp));
-                    mu += s * z;
-                    const double cv = (-(s * z) + z * rp) / s, dd = z / s;
-                    for (int k = 0; k < D; k++) { u1[k] -= nk[k] * z; u2[k] -= nk[k] * cv; }
-                    S[0] += dd * nk[0] * nk[0]; S[1] += dd * nk[1] * nk[0]; S[2] += dd * nk[1] * nk[1];
-                    S[3] += dd * nk[2] * nk[0]; S[4] += dd * nk[2] * nk[1]; S[5] += dd * nk[2] * nk[2];
-                }
-            }
-            for (int k = 0; k < 3; k++) { u1[k] = group_sum(u1[k], G); u2[k] = group_sum(u2[k], G); }
-            for (int q = 0; q < 6; q++) S[q] = group_sum(S[q], G);
-            if (valid && gl == 0) {
-                for (int k = 0; k < D; k++) { sm.ax1[k * npt + pt] += u1[k]; sm.ax2[k * npt + pt] += u2[k]; }
-                for (int q = 0; q < 6; q++) sm.S[pt * 6 + q] = S[q];
-            }
-        }
-        for (int e = c.tid; e < 18; e += c.nthr) sm.S[e] = 0.0;   // points 0..2 of segment 0 carry no rows
-        c.sync();
-        double rd_inf = 0.0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const bool all_rows = !(tau > 0) || attempt == 3;
+        // ---- starting point: free control points of the initial trajectory ----
         for (int p = c.tid; p < ny; p += c.nthr) {
-            const double r1 = gather_y(T, p, sm.V1, sm.ax1);
-            const double r2 = gather_y(T, p, sm.V2, sm.ax2);
-            sm.rd[p] = r1;
-            sm.dy[p] = -r1 - r2;
-            rd_inf = fmax(rd_inf, fabs(r1));
+            const int k = p / nyd, a = p - k * nyd;
+            const int m = a / 3, j = (m == M - 1) ? 2 : a - 3 * m;
+            sm.y[p] = (double)in.init_traj[(m * kP + 3 + j) * 3 + k];
         }
-        c.reduce3(rp_inf, 1, mu, 0, rd_inf, 1);
-        mu *= inv_rows;
-#if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
-        printf("it %d rp %.3e rd %.3e mu %.3e ginf %.3e rows %.0f\n", it, rp_inf, rd_inf, mu, g_inf, n_rows);
-#endif
-        if (rp_inf <= kQpTolRp && rd_inf <= kQpTolRd * (1.0 + g_inf) && mu <= kQpTolMu) { status = 0; break; }
-
-        // ================= W = H + G' D G  (packed lower triangle) =================
-        for (int e = c.tid; e < T.ntri; e += c.nthr) {
-            int p = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);       // e -> (p, q), p >= q
-            while (p * (p + 1) / 2 > e) p--;
-            while ((p + 1) * (p + 2) / 2 <= e) p++;
-            const int q = e - p * (p + 1) / 2;
-            const int k = p / nyd, a = p - k * nyd, kk = q / nyd, b = q - kk * nyd;
-            double v = 0.0;
-            if (k == kk) {
-                v = T.H1[a * nyd + b];
-                if (a == b) {
-                    const int m = a / 3;
-                    if ((m == M - 1 || a - 3 * m == 2) && m >= M - qc.ts) v += wT2;
-                }
-                for (int t = T.wi_ptr[e]; t < T.wi_ptr[e + 1]; t++) v += T.wi_coef[t] * sm.DD[T.wi_row[t]];
-            }
-            const int el = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
-            const int si = sym_idx(k, kk);
-            for (int t = T.wp_ptr[el]; t < T.wp_ptr[el + 1]; t++) v += T.wp_coef[t] * sm.S[T.wp_pt[t] * 6 + si];
-            sm.W[e] = v;
-        }
-        c.sync();
-        if (!ldl_factor(c, sm.W, sm.invp, ny)) { status = kStQpNumeric; break; }
-
-        // ================= predictor =================
-        ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
-        c.sync();
-        map_x(c, T, sm.dy, nullptr, sm.dx);
-        c.sync();
-        double a_aff = 1.0;
-        for (int r = c.tid; r < np; r += c.nthr) {
-            const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
-            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
-            const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
-            const double dzh = (-(sh * zh) - zh * dsh) / sh, dzl = (-(sl * zl) - zl * dsl) / sl;
-            if (dsh < 0) a_aff = fmin(a_aff, -sh / dsh);
-            if (dzh < 0) a_aff = fmin(a_aff, -zh / dzh);
-            if (dsl < 0) a_aff = fmin(a_aff, -sl / dsl);
-            if (dzl < 0) a_aff = fmin(a_aff, -zl / dzl);
-            pd_sh[r] = dsh; pd_zh[r] = dzh; pd_sl[r] = dsl; pd_zl[r] = dzl;
-        }
-        lsc_rows([&](const LscRow& r) {
-            const double s = lsc_s[r.o], z = lsc_z[r.o];
-            const double ds = -(r.act + s - lsc_b[r.o]) - r.gd;
-            const double dz = (-(s * z) - z * ds) / s;
-            if (ds < 0) a_aff = fmin(a_aff, -s / ds);
-            if (dz < 0) a_aff = fmin(a_aff, -z / dz);
-            lsc_ds[r.o] = ds; lsc_dz[r.o] = dz;
-        });
-        { double d0 = 0.0, d1 = 0.0; c.reduce3(a_aff, 2, d0, 0, d1, 0); }
-        double mu_aff = 0.0;
-        for (int r = c.tid; r < np; r += c.nthr) {
-            const double dsh = pd_sh[r], dzh = pd_zh[r], dsl = pd_sl[r], dzl = pd_zl[r];
-            mu_aff += (ps_hi[r] + a_aff * dsh) * (pz_hi[r] + a_aff * dzh) + (ps_lo[r] + a_aff * dsl) * (pz_lo[r] + a_aff * dzl);
-            pc_hi[r] = dsh * dzh; pc_lo[r] = dsl * dzl;
-        }
-        lsc_rows([&](const LscRow& r) {
-            const double ds = lsc_ds[r.o], dz = lsc_dz[r.o];
-            mu_aff += (lsc_s[r.o] + a_aff * ds) * (lsc_z[r.o] + a_aff * dz);
-            lsc_c[r.o] = ds * dz;
-        });
-        { double d0 = 0.0, d1 = 0.0; c.reduce3(mu_aff, 0, d0, 0, d1, 0); }
-        mu_aff *= inv_rows;
-        const double ratio = mu > 0 ? mu_aff / mu : 0.0;
-        const double sig_mu = ratio * ratio * ratio * mu;
-
-        // ================= corrector =================
-        for (int e = c.tid; e < nx; e += c.nthr) sm.ax2[e] = 0.0;
-        c.sync();
-        for (int r = c.tid; r < np; r += c.nthr) {
-            const double act = pair_act(T, r, sm.y, sm.cst);
-            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
-            const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
-            const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
-            sm.V2[r] = (-rch + zh * rph) / sh - (-rcl + zl * rpl) / sl;
-        }
-        for (int base = 0; base < npt; base += ngr) {
-            const int pt = base + gid;
-            const bool valid = pt < npt && pt >= 3;
-            double u2[3] = {0, 0, 0};
-            if (valid) {
-                const int m = pt / kP;
-                for (int cc = gl; cc < K; cc += G) {
-                    if (!sm.act[m * Kc + cc]) continue;
-                    const float* nr = in.normal + ((size_t)cc * M + m) * 3;
-                    const size_t o = (size_t)pt * Kc + cc;
-                    const double s = lsc_s[o], z = lsc_z[o];
-                    double nk[3] = {0, 0, 0}, act = 0.0;
-                    for (int k = 0; k < D; k++) { nk[k] = (double)nr[k]; act -= nk[k] * sm.x[k * npt + pt]; }
-                    const double rp = act + s - lsc_b[o];
-                    const double rc = s * z + lsc_c[o] - sig_mu;
-                    const double cv = (-rc + z * rp) / s;
-                    for (int k = 0; k < D; k++) u2[k] -= nk[k] * cv;
-                }
-            }
-            for (int k = 0; k < 3; k++) u2[k] = group_sum(u2[k], G);
-            if (valid && gl == 0)
-                for (int k = 0; k < D; k++) sm.ax2[k * npt + pt] += u2[k];
-        }
-        c.sync();
-        for (int p = c.tid; p < ny; p += c.nthr) sm.dy[p] = -sm.rd[p] - gather_y(T, p, sm.V2, sm.ax2);
-        c.sync();
-        ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
-        c.sync();
-        map_x(c, T, sm.dy, nullptr, sm.dx);
-        c.sync();
-        double a_st = 1.0;
-        for (int r = c.tid; r < np; r += c.nthr) {
-            const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
-            const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
-            const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
-            const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
-            const double dzh = (-rch - zh * dsh) / sh, dzl = (-rcl - zl * dsl) / sl;
-            if (dsh < 0) a_st = fmin(a_st, -sh / dsh);
-            if (dzh < 0) a_st = fmin(a_st, -zh / dzh);
-            if (dsl < 0) a_st = fmin(a_st, -sl / dsl);
-            if (dzl < 0) a_st = fmin(a_st, -zl / dzl);
-            pd_sh[r] = dsh; pd_zh[r] = dzh; pd_sl[r] = dsl; pd_zl[r] = dzl;
-        }
-        lsc_rows([&](const LscRow& r) {
-            const double s = lsc_s[r.o], z = lsc_z[r.o];
-            const double rc = s * z + lsc_c[r.o] - sig_mu;
-            const double ds = -(r.act + s - lsc_b[r.o]) - r.gd;
-            const double dz = (-rc - z * ds) / s;
-            if (ds < 0) a_st = fmin(a_st, -s / ds);
-            if (dz < 0) a_st = fmin(a_st, -z / dz);
-            lsc_ds[r.o] = ds; lsc_dz[r.o] = dz;
-        });
-        { double d0 = 0.0, d1 = 0.0; c.reduce3(a_st, 2, d0, 0, d1, 0); }
-        a_st = fmin(1.0, 0.995 * a_st);
-#if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
-        printf("      a_aff %.3e mu_aff %.3e sig_mu %.3e a %.3e\n", a_aff, mu_aff, sig_mu, a_st);
-#endif
-        // ================= update =================
-        for (int r = c.tid; r < np; r += c.nthr) {
-            ps_hi[r] += a_st * pd_sh[r]; pz_hi[r] += a_st * pd_zh[r];
-            ps_lo[r] += a_st * pd_sl[r]; pz_lo[r] += a_st * pd_zl[r];
-        }
-        lsc_rows([&](const LscRow& r) {
-            lsc_s[r.o] += a_st * lsc_ds[r.o];
-            lsc_z[r.o] += a_st * lsc_dz[r.o];
-        });
-        for (int p = c.tid; p < ny; p += c.nthr) sm.y[p] += a_st * sm.dy[p];
         c.sync();
         map_x(c, T, sm.y, sm.cst, sm.x);
         c.sync();
+        // ---- working set of LSC rows, sorted by control point ----
+        for (int pt = c.tid; pt < npt; pt += c.nthr) {
+            int cnt = 0;
+            if (pt >= 3) {
+                const int m = pt / kP;
+                const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
+                for (int cc = 0; cc < K; cc++) {
+                    if (!sm.act[m * Kc + cc]) continue;
+                    const LscRowData r = lsc_row_data(P, in, pt, cc);
+                    const double s0 = r.b + (r.n0 * x0 + r.n1 * x1 + r.n2 * x2);
+                    if (all_rows || s0 < tau) cnt++;
+                }
+            }
+            sm.off[pt + 1] = cnt;
+        }
+        c.sync();
+        if (c.tid == 0) {
+            sm.off[0] = 0;
+            for (int pt = 0; pt < npt; pt++) sm.off[pt + 1] += sm.off[pt];
+        }
+        c.sync();
+        const int nl = sm.off[npt];
+        for (int pt = c.tid; pt < npt; pt += c.nthr) {
+            if (pt < 3 || sm.off[pt + 1] == sm.off[pt]) continue;
+            const int m = pt / kP;
+            int o = sm.off[pt];
+            const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
+            for (int cc = 0; cc < K; cc++) {
+                if (!sm.act[m * Kc + cc]) continue;
+                const LscRowData r = lsc_row_data(P, in, pt, cc);
+                const double act = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2);
+                double s0 = r.b - act;
+                if (!(all_rows || s0 < tau)) continue;
+                if (s0 < 1e-2) s0 = 1e-2;
+                l_n0[o] = r.n0; l_n1[o] = r.n1; l_n2[o] = r.n2; l_b[o] = r.b; l_s[o] = s0; l_z[o] = 1.0 / s0 * 1e-2;
+                l_pt[o] = pt;
+                o++;
+            }
+        }
+        // ---- pair rows: slack / dual initialisation ----
+        for (int r = c.tid; r < np; r += c.nthr) {
+            const double act = pair_act(T, r, sm.y, sm.cst);
+            double s = pb_hi[r] - act; if (s < 1e-2) s = 1e-2;
+            ps_hi[r] = s; pz_hi[r] = 1.0 / s * 1e-2;
+            s = act - pb_lo[r]; if (s < 1e-2) s = 1e-2;
+            ps_lo[r] = s; pz_lo[r] = 1.0 / s * 1e-2;
+        }
+        const double n_rows = 2.0 * np + nl;
+        rows_total += (long long)n_rows;
+        const double inv_rows = 1.0 / n_rows;
+        c.sync();
+
+        status = kStQpMaxIter;
+        int it = 0;
+        for (it = 0; it < max_it; it++) {
+            // ============ pass 1: residuals, G'z, affine rhs, D = z/s ============
+            for (int k = 0; k < D; k++)
+                for (int pt = c.tid; pt < npt; pt += c.nthr) { sm.ax1[k * npt + pt] = grad_x(sm.x, k, pt); sm.ax2[k * npt + pt] = 0.0; }
+            double rp_inf = 0.0, mu = 0.0;
+            for (int r = c.tid; r < np; r += c.nthr) {
+                const double act = pair_act(T, r, sm.y, sm.cst);
+                const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+                const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
+                rp_inf = fmax(rp_inf, fmax(fabs(rph), fabs(rpl)));
+                mu += sh * zh + sl * zl;
+                const double dh = zh / sh, dl = zl / sl;
+                sm.V1[r] = zh - zl;
+                sm.V2[r] = dh * (rph - sh) - dl * (rpl - sl);      // (-s z + z rp)/s = (z/s)(rp - s)
+                sm.DD[r] = dh + dl;
+            }
+            for (int r = c.tid; r < nl; r += c.nthr) {
+                const int pt = l_pt[r];
+                const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
+                const double rp = act + s - l_b[r];
+                rp_inf = fmax(rp_inf, fabs(rp));
+                mu += s * z;
+                const double dd = z / s;
+                l_ds[r] = dd * (rp - s);      // c_aff (temporary)
+                l_dz[r] = dd;                 // D      (temporary)
+            }
+            c.sync();
+            for (int pt = c.tid; pt < npt; pt += c.nthr) {
+                double u10 = 0, u11 = 0, u12 = 0, u20 = 0, u21 = 0, u22 = 0, S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0;
+                for (int r = sm.off[pt]; r < sm.off[pt + 1]; r++) {
+                    const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], z = l_z[r], cv = l_ds[r], dd = l_dz[r];
+                    u10 -= n0 * z; u11 -= n1 * z; u12 -= n2 * z;
+                    u20 -= n0 * cv; u21 -= n1 * cv; u22 -= n2 * cv;
+                    S0 += dd * n0 * n0; S1 += dd * n1 * n0; S2 += dd * n1 * n1;
+                    S3 += dd * n2 * n0; S4 += dd * n2 * n1; S5 += dd * n2 * n2;
+                }
+                sm.ax1[pt] += u10; sm.ax1[npt + pt] += u11;
+                sm.ax2[pt] += u20; sm.ax2[npt + pt] += u21;
+                if (D3) { sm.ax1[2 * npt + pt] += u12; sm.ax2[2 * npt + pt] += u22; }
+                double* Sp = sm.S + pt * 6;
+                Sp[0] = S0; Sp[1] = S1; Sp[2] = S2; Sp[3] = S3; Sp[4] = S4; Sp[5] = S5;
+            }
+            c.sync();
+            double rd_inf = 0.0;
+            for (int p = c.tid; p < ny; p += c.nthr) {
+                const double r1 = gather_y(T, p, sm.V1, sm.ax1);
+                const double r2 = gather_y(T, p, sm.V2, sm.ax2);
+                sm.rd[p] = r1;
+                sm.dy[p] = -r1 - r2;
+                rd_inf = fmax(rd_inf, fabs(r1));
+            }
+            c.reduce3(rp_inf, 1, mu, 0, rd_inf, 1);
+            mu *= inv_rows;
+#if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
+            printf("att %d it %d rp %.3e rd %.3e mu %.3e ginf %.3e rows %.0f\n", attempt, it, rp_inf, rd_inf, mu, g_inf, n_rows);
+#endif
+            if (rp_inf <= kQpTolRp && rd_inf <= kQpTolRd * (1.0 + g_inf) && mu <= kQpTolMu) { status = 0; break; }
+
+            // ============ W = H + G' D G  (packed lower triangle) ============
+            for (int e = c.tid; e < T.ntri; e += c.nthr) {
+                const int p = T.tri_p[e], q = e - p * (p + 1) / 2;
+                const int k = p / nyd, a = p - k * nyd, kk = q / nyd, b = q - kk * nyd;
+                double v = 0.0;
+                if (k == kk) {
+                    v = T.H1[a * nyd + b];
+                    if (a == b) {
+                        const int m = a / 3;
+                        if ((m == M - 1 || a - 3 * m == 2) && m >= M - qc.ts) v += wT2;
+                    }
+                    for (int t = T.wi_ptr[e]; t < T.wi_ptr[e + 1]; t++) v += T.wi_coef[t] * sm.DD[T.wi_row[t]];
+                }
+                const int el = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
+                const int si = sym_idx(k, kk);
+                for (int t = T.wp_ptr[el]; t < T.wp_ptr[el + 1]; t++) v += T.wp_coef[t] * sm.S[T.wp_pt[t] * 6 + si];
+                sm.W[e] = v;
+            }
+            c.sync();
+            if (!ldl_factor(c, sm.W, sm.invp, ny)) { status = kStQpNumeric; break; }
+
+            // ============ predictor ============
+            ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
+            c.sync();
+            map_x(c, T, sm.dy, nullptr, sm.dx);
+            c.sync();
+            double a_aff = 1.0;
+            for (int r = c.tid; r < np; r += c.nthr) {
+                const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
+                const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+                const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
+                const double dzh = -zh - (zh / sh) * dsh, dzl = -zl - (zl / sl) * dsl;   // (-s z - z ds)/s
+                if (dsh < 0) a_aff = fmin(a_aff, -sh / dsh);
+                if (dzh < 0) a_aff = fmin(a_aff, -zh / dzh);
+                if (dsl < 0) a_aff = fmin(a_aff, -sl / dsl);
+                if (dzl < 0) a_aff = fmin(a_aff, -zl / dzl);
+                pd_sh[r] = dsh; pd_zh[r] = dzh; pd_sl[r] = dsl; pd_zl[r] = dzl;
+            }
+            for (int r = c.tid; r < nl; r += c.nthr) {
+                const int pt = l_pt[r];
+                const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
+                const double gd = -(n0 * sm.dx[pt] + n1 * sm.dx[npt + pt] + (D3 ? n2 * sm.dx[2 * npt + pt] : 0.0));
+                const double ds = -(act + s - l_b[r]) - gd;
+                const double dz = -z - l_dz[r] * ds;          // l_dz still holds D = z/s
+                if (ds < 0) a_aff = fmin(a_aff, -s / ds);
+                if (dz < 0) a_aff = fmin(a_aff, -z / dz);
+                l_ds[r] = ds; l_c[r] = dz;                    // affine directions (l_c as temporary)
+            }
+            { double d0 = 0.0, d1 = 0.0; c.reduce3(a_aff, 2, d0, 0, d1, 0); }
+            double mu_aff = 0.0;
+            for (int r = c.tid; r < np; r += c.nthr) {
+                const double dsh = pd_sh[r], dzh = pd_zh[r], dsl = pd_sl[r], dzl = pd_zl[r];
+                mu_aff += (ps_hi[r] + a_aff * dsh) * (pz_hi[r] + a_aff * dzh) + (ps_lo[r] + a_aff * dsl) * (pz_lo[r] + a_aff * dzl);
+                pc_hi[r] = dsh * dzh; pc_lo[r] = dsl * dzl;
+            }
+            for (int r = c.tid; r < nl; r += c.nthr) {
+                const double ds = l_ds[r], dz = l_c[r];
+                mu_aff += (l_s[r] + a_aff * ds) * (l_z[r] + a_aff * dz);
+                l_c[r] = ds * dz;
+            }
+            { double d0 = 0.0, d1 = 0.0; c.reduce3(mu_aff, 0, d0, 0, d1, 0); }
+            mu_aff *= inv_rows;
+            const double ratio = mu > 0 ? mu_aff / mu : 0.0;
+            const double sig_mu = ratio * ratio * ratio * mu;
+
+            // ============ corrector ============
+            for (int r = c.tid; r < np; r += c.nthr) {
+                const double act = pair_act(T, r, sm.y, sm.cst);
+                const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+                const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
+                const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
+                sm.V2[r] = (-rch + zh * rph) / sh - (-rcl + zl * rpl) / sl;
+            }
+            for (int r = c.tid; r < nl; r += c.nthr) {
+                const int pt = l_pt[r];
+                const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
+                const double rp = act + s - l_b[r];
+                const double rc = s * z + l_c[r] - sig_mu;
+                l_ds[r] = (-rc + z * rp) / s;                 // c_corr (temporary); l_c keeps rc's corrector part
+            }
+            c.sync();
+            for (int pt = c.tid; pt < npt; pt += c.nthr) {
+                double u20 = 0, u21 = 0, u22 = 0;
+                for (int r = sm.off[pt]; r < sm.off[pt + 1]; r++) {
+                    const double cv = l_ds[r];
+                    u20 -= l_n0[r] * cv; u21 -= l_n1[r] * cv; u22 -= l_n2[r] * cv;
+                }
+                sm.ax2[pt] = u20; sm.ax2[npt + pt] = u21;
+                if (D3) sm.ax2[2 * npt + pt] = u22;
+            }
+            c.sync();
+            for (int p = c.tid; p < ny; p += c.nthr) sm.dy[p] = -sm.rd[p] - gather_y(T, p, sm.V2, sm.ax2);
+            c.sync();
+            ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
+            c.sync();
+            map_x(c, T, sm.dy, nullptr, sm.dx);
+            c.sync();
+            double a_st = 1.0;
+            for (int r = c.tid; r < np; r += c.nthr) {
+                const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
+                const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
+                const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
+                const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
+                const double dzh = (-rch - zh * dsh) / sh, dzl = (-rcl - zl * dsl) / sl;
+                if (dsh < 0) a_st = fmin(a_st, -sh / dsh);
+                if (dzh < 0) a_st = fmin(a_st, -zh / dzh);
+                if (dsl < 0) a_st = fmin(a_st, -sl / dsl);
+                if (dzl < 0) a_st = fmin(a_st, -zl / dzl);
+                pd_sh[r] = dsh; pd_zh[r] = dzh; pd_sl[r] = dsl; pd_zl[r] = dzl;
+            }
+            for (int r = c.tid; r < nl; r += c.nthr) {
+                const int pt = l_pt[r];
+                const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
+                const double gd = -(n0 * sm.dx[pt] + n1 * sm.dx[npt + pt] + (D3 ? n2 * sm.dx[2 * npt + pt] : 0.0));
+                const double rc = s * z + l_c[r] - sig_mu;
+                const double ds = -(act + s - l_b[r]) - gd;
+                const double dz = (-rc - z * ds) / s;
+                if (ds < 0) a_st = fmin(a_st, -s / ds);
+                if (dz < 0) a_st = fmin(a_st, -z / dz);
+                l_ds[r] = ds; l_dz[r] = dz;
+            }
+            { double d0 = 0.0, d1 = 0.0; c.reduce3(a_st, 2, d0, 0, d1, 0); }
+            a_st = fmin(1.0, 0.995 * a_st);
+#if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
+            printf("      a_aff %.3e mu_aff %.3e sig_mu %.3e a %.3e\n", a_aff, mu_aff, sig_mu, a_st);
+#endif
+            // ============ update ============
+            for (int r = c.tid; r < np; r += c.nthr) {
+                ps_hi[r] += a_st * pd_sh[r]; pz_hi[r] += a_st * pd_zh[r];
+                ps_lo[r] += a_st * pd_sl[r]; pz_lo[r] += a_st * pd_zl[r];
+            }
+            for (int r = c.tid; r < nl; r += c.nthr) { l_s[r] += a_st * l_ds[r]; l_z[r] += a_st * l_dz[r]; }
+            for (int p = c.tid; p < ny; p += c.nthr) sm.y[p] += a_st * sm.dy[p];
+            c.sync();
+            map_x(c, T, sm.y, sm.cst, sm.x);
+            c.sync();
+        }
+        it_total += it;
+        if (status != 0) break;
+        // ---- check EVERY LSC row at the solution (the screen is exact only if none is violated) ----
+        viol_lsc = 0.0;
+        for (int pt = c.tid; pt < npt; pt += c.nthr) {
+            if (pt < 3) continue;
+            const int m = pt / kP;
+            const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
+            for (int cc = 0; cc < K; cc++) {
+                if (!sm.act[m * Kc + cc]) continue;
+                const LscRowData r = lsc_row_data(P, in, pt, cc);
+                const double v = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2) - r.b;
+                viol_lsc = fmax(viol_lsc, v);
+            }
+        }
+        { double d0 = 0.0, d1 = 0.0; c.reduce3(viol_lsc, 1, d0, 0, d1, 0); }
+        if (all_rows || viol_lsc <= 1e-9) break;
+        tau *= 4.0;
+        status = kStQpMaxIter;
     }
 
     // ---- outputs: objective in x-space (constant included, like IloCplex::getObjValue :109) ----
-    double obj = 0.0, viol = 0.0;
-    for (int e = c.tid; e < nx; e += c.nthr) {
-        const int k = e / npt, pt = e - k * npt, m = pt / kP, i = pt - m * kP;
-        const double* xs = sm.x + k * npt + m * kP;
-        double v = 0.0;
+    double obj = 0.0, viol = viol_lsc;
+    for (int k = 0; k < D; k++)
+        for (int pt = c.tid; pt < npt; pt += c.nthr) {
+            const int m = pt / kP, i = pt - m * kP;
+            const double* xs = sm.x + k * npt + m * kP;
+            double v = 0.0;
 #pragma unroll
-        for (int j = 0; j < kP; j++) v += T.Q2[i * kP + j] * xs[j];
-        obj += 0.5 * v * xs[i];
-        if (i == n && m >= M - qc.ts) {
-            const double g = (double)v3_get(in.goal, k);
-            obj += wT * xs[n] * xs[n] - wT2 * g * xs[n] + wT * g * g;
+            for (int j = 0; j < kP; j++) v += T.Q2[i * kP + j] * xs[j];
+            obj += 0.5 * v * xs[i];
+            if (i == n && m >= M - qc.ts) {
+                const double g = (double)v3_get(in.goal, k);
+                obj += wT * xs[n] * xs[n] - wT2 * g * xs[n] + wT * g * g;
+            }
         }
-    }
     for (int r = c.tid; r < np; r += c.nthr) {
         const double act = pair_act(T, r, sm.y, sm.cst);
         viol = fmax(viol, fmax(act - pb_hi[r], pb_lo[r] - act));
     }
-    lsc_rows([&](const LscRow& r) { viol = fmax(viol, r.act - lsc_b[r.o]); });
     { double d1 = 0.0; c.reduce3(obj, 0, viol, 1, d1, 0); }
     if (c.tid == 0) {
-        *out.cost = obj; *out.viol = viol; *out.iters = it; *out.status |= status;
+        *out.cost = obj; *out.viol = viol; *out.iters = it_total; *out.status |= status;
+        if (out.rows) *out.rows = rows_total;
     }
     const bool ok = (status == 0);
     for (int e = c.tid; e < npt; e += c.nthr) {
         float* o = out.traj + e * 3;
         if (ok) {                                                                     // :71-83
             o[0] = (float)sm.x[e]; o[1] = (float)sm.x[npt + e];
-            o[2] = (D == 3) ? (float)sm.x[2 * npt + e] : (float)P.z_2d;
+            o[2] = D3 ? (float)sm.x[2 * npt + e] : (float)P.z_2d;
         } else {                                                                      // failsafe traj_planner.cpp:775-776
             o[0] = in.init_traj[e * 3]; o[1] = in.init_traj[e * 3 + 1]; o[2] = in.init_traj[e * 3 + 2];
         }

@@ -155,6 +155,10 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
             for (int i = 0; i < 3; i++) T.pr_cc[(size_t)g * 3 + i] = rows[r].e.cc[i];
         }
 
+    T.tri_p.assign(T.ntri, 0);
+    for (int p = 0; p < T.ny; p++)
+        for (int q = 0; q <= p; q++) T.tri_p[p * (p + 1) / 2 + q] = (uint8_t)p;
+
     // incidence of pair rows per global y, and per global lower-triangular W entry
     std::vector<std::vector<std::pair<int, double>>> yi(T.ny), wi(T.ntri);
     for (int g = 0; g < T.np; g++) {

@@ -38,6 +38,7 @@ struct QpTabHost {
     std::vector<int> yp_ptr;  std::vector<int16_t> yp_pt;   std::vector<double> yp_coef;   // points per local y
     std::vector<int> wi_ptr;  std::vector<int16_t> wi_row;  std::vector<double> wi_coef;   // pair rows per W entry (global lower tri)
     std::vector<int> wp_ptr;  std::vector<int16_t> wp_pt;   std::vector<double> wp_coef;   // points per local (a>=b)
+    std::vector<uint8_t> tri_p;                   // [ntri] row index p of packed lower-triangle entry e
     std::vector<double> H1;                       // [nyd][nyd]  2*w_u*sum_m T_m' Q T_m
     std::vector<double> Q2;                       // [6][6]      2*w_u*Q
     std::vector<double> Qb;                       // [6][6]      Q_base
@@ -62,6 +63,7 @@ struct QpTab {
     const int *yp_ptr; const int16_t* yp_pt; const double* yp_coef;
     const int *wi_ptr; const int16_t* wi_row; const double* wi_coef;
     const int *wp_ptr; const int16_t* wp_pt; const double* wp_coef;
+    const uint8_t* tri_p;
     const double *H1, *Q2;
 };
 

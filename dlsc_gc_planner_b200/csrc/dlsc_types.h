@@ -14,6 +14,7 @@ struct DevParams {
     int N, begin, NL;                // swarm size, first local agent, local count
     int rec;                         // floats per record
     int qp_max_iter;
+    double qp_screen;                // LSC working-set screen [m]; <= 0: all rows
     double dt, world_res, grid_res, z_2d, comm_range, w_control, w_terminal, reset_threshold;
     double world_min[3], world_max[3];       // double(float(x))
     float tk[kMaxPts];               // (float) of the time accumulated by `time += dt/n` (trajectory.cpp:84-90)

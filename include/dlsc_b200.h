@@ -54,6 +54,8 @@ typedef struct dlsc_params {
     double reset_threshold; /* plan/reset_threshold                                        */
     int32_t qp_max_iter;    /* interior-point iteration cap (0 -> 80)                      */
     int32_t reserved;
+    double qp_screen_slack; /* LSC working-set screen: rows with initial slack below this [m] enter the
+                               first solve (0 -> 0.5; < 0 -> all rows).  Exact: see dlsc_qp.cuh.           */
 } dlsc_params;
 
 /* per-agent status bits (dlsc_get_status) */

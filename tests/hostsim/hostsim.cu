@@ -54,6 +54,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     c->rl = rec_layout(hp->M);
     P.rec = c->rl.size;
     P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
+    P.qp_screen = hp->qp_screen_slack == 0.0 ? 0.5 : hp->qp_screen_slack;
     P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
     P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
     P.reset_threshold = hp->reset_threshold;
@@ -87,7 +88,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     T.yp_ptr = h.yp_ptr.data(); T.yp_pt = h.yp_pt.data(); T.yp_coef = h.yp_coef.data();
     T.wi_ptr = h.wi_ptr.data(); T.wi_row = h.wi_row.data(); T.wi_coef = h.wi_coef.data();
     T.wp_ptr = h.wp_ptr.data(); T.wp_pt = h.wp_pt.data(); T.wp_coef = h.wp_coef.data();
-    T.H1 = h.H1.data(); T.Q2 = h.Q2.data();
+    T.H1 = h.H1.data(); T.Q2 = h.Q2.data(); T.tri_p = h.tri_p.data();
     c->scratch.assign(qp_scratch_doubles(T, P.K), 0.0);
     c->smem.assign(qp_smem_bytes(T, P.K) / 8 + 8, 0.0);
     memset(&c->edt, 0, sizeof(c->edt));
@@ -257,7 +258,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             out.x = c->qp_x.data() + (size_t)la * c->T.nx;
             out.cost = &c->cost[la]; out.viol = &c->viol[la]; out.iters = &c->qp_iters[la]; out.status = &c->status[la];
             out.rows = &rows;
-            qp_agent(cta, 1, P, c->T, in, out, sm, c->scratch.data());
+            qp_agent(cta, P, c->T, in, out, sm, c->scratch.data());
             c->counters[3] += c->qp_iters[la];
             c->counters[4] += rows;
         }
