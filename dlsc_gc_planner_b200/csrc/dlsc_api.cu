@@ -32,8 +32,8 @@ struct dlsc_ctx {
     bool own_stream = false;
     bool rec_owned = false;
     bool have_edt = false;
-    float* edt_dist = nullptr;      // staging (freed after pack)
     int4* edt_cells = nullptr;
+    float* edt_centre = nullptr;
     int64_t launches = 0;
     bool timing = false;
     std::vector<cudaEvent_t> evpool;   // (DLSC_N_STAGES + 1) events per timed step, resolved lazily
@@ -211,6 +211,7 @@ void dlsc_destroy(dlsc_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->tab_blob) cudaFree(c->tab_blob);
     if (c->edt_cells) cudaFree(c->edt_cells);
+    if (c->edt_centre) cudaFree(c->edt_centre);
     for (auto& e : c->evpool) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -245,6 +246,17 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
     EdtDev& E = c->S.edt;
     for (int k = 0; k < 3; k++) { E.dims[k] = dims[k]; E.min_key[k] = min_key[k]; }
     E.res = res; E.inv_res = 1.0 / res; E.cells = c->edt_cells;
+    {   // cell-centre coordinate of every cell index along each axis (what DynamicEDTOctomap returns as the
+        // closest obstacle: keyToCoord = (key + 0.5) * res), same double arithmetic as the per-vertex formula
+        std::vector<float> centre((size_t)dims[0] + dims[1] + dims[2]);
+        size_t o = 0;
+        for (int k = 0; k < 3; k++)
+            for (int i = 0; i < dims[k]; i++) centre[o++] = (float)(((double)(i + min_key[k]) + 0.5) * res);
+        if (c->edt_centre) { cudaFree(c->edt_centre); c->edt_centre = nullptr; }
+        CK(cudaMalloc(&c->edt_centre, centre.size() * sizeof(float)));
+        CK(cudaMemcpy(c->edt_centre, centre.data(), centre.size() * sizeof(float), cudaMemcpyHostToDevice));
+        E.centre[0] = c->edt_centre; E.centre[1] = c->edt_centre + dims[0]; E.centre[2] = c->edt_centre + dims[0] + dims[1];
+    }
     c->have_edt = true;
     CK(cudaGetLastError());
     return 0;

@@ -36,7 +36,7 @@ void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t
 __global__ void __launch_bounds__(256) k_neighbours(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= P.NL) return;
-    Group g; g.lane = threadIdx.x & 31; g.width = 32;
+    Group g; g.lane = threadIdx.x & 31; g.width = 32; g.block = false;
     const int cnt = neighbours_agent(g, P, S.rec, P.begin + warp, S.nbr_idx + (size_t)warp * P.K);
     if (g.lane == 0) {
         S.nbr_cnt[warp] = cnt < P.K ? cnt : P.K;
@@ -83,27 +83,32 @@ void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// one CTA per agent: the greedy control flow is replicated in every thread (uniform), the vertex tests of a
+// box are spread over the 128 threads and combined with barrier votes (__syncthreads_or)
 __global__ void __launch_bounds__(128) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= P.NL) return;
-    Group g; g.lane = threadIdx.x & 31; g.width = 32;
-    const int la = warp, npt = P.M * kP;
+    __shared__ SfcTab tab;
+    __shared__ unsigned s_look[4];
+    const int la = blockIdx.x;
+    Group g; g.lane = threadIdx.x; g.width = blockDim.x; g.block = true;
+    const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     const bool init = S.sfc_init[la] != 0 || S.disturbed[la] != 0;       // traj_planner.cpp:439, 693-695
     long long lookups = 0;
     const int st = sfc_agent(g, P, S.edt, init, v3_load(rec + npt * 3), S.init_traj + (size_t)la * npt * 3,
                              v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3), S.radius[la],
-                             S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &lookups);
-    if (g.lane == 0) {
+                             S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &tab, &lookups);
+    const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)lookups);
+    if ((threadIdx.x & 31) == 0) s_look[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
         S.sfc_init[la] = 0;
         if (st) atomicOr(S.status + la, st);
-        atomicAdd(S.counters + 2, (unsigned long long)lookups);
+        atomicAdd(S.counters + 2, (unsigned long long)s_look[0] + s_look[1] + s_look[2] + s_look[3]);
     }
 }
 
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st) {
-    const int warps_per_block = 4;
-    k_sfc<<<(P.NL + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(P, S);
+    k_sfc<<<P.NL, 128, 0, st>>>(P, S);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ namespace dlsc {
 
 constexpr int kQpThreads = 128;
 
-__global__ void __launch_bounds__(kQpThreads) k_qp(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ DevState S,
                                                    const __grid_constant__ QpTab T, size_t scratch_doubles) {
     extern __shared__ __align__(16) double smem[];

@@ -83,12 +83,13 @@ struct QpOut {
 
 // shared-memory carve-up (doubles unless noted)
 struct QpSmem {
-    double *W, *invp, *y, *dy, *rd, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
+    double *W, *invp, *pan, *y, *dy, *rd, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
     int* off;                  // [npt + 2] segment offsets of the LSC row list (+ scratch word)
     uint8_t* act;              // [M][Kcap]
 };
 DLSC_HD size_t qp_smem_doubles(const QpTab& T) {
-    return (size_t)T.ntri + 4 * (size_t)T.ny + 4 * (size_t)T.nx + 3 * (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
+    const size_t v12 = (2 * (size_t)T.np > 8 * (size_t)T.ny) ? 2 * (size_t)T.np : 8 * (size_t)T.ny;   // V1|V2, aliased by pan
+    return (size_t)T.ntri + 4 * (size_t)T.ny + 4 * (size_t)T.nx + v12 + (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
            ((size_t)T.npt + 4) / 2 + 1;
 }
 DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
@@ -99,7 +100,11 @@ DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     s.W = p; p += T.ntri;
     s.invp = p; p += T.ny; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny;
     s.x = p; p += T.nx; s.dx = p; p += T.nx; s.ax1 = p; p += T.nx; s.ax2 = p; p += T.nx;
-    s.V1 = p; p += T.np; s.V2 = p; p += T.np; s.DD = p; p += T.np;
+    {   // V1 and V2 are dead while W is being factorised: the panel buffers of ldl_factor alias them
+        const size_t v12 = (2 * (size_t)T.np > 8 * (size_t)T.ny) ? 2 * (size_t)T.np : 8 * (size_t)T.ny;
+        s.V1 = p; s.V2 = p + T.np; s.pan = p; p += v12;
+    }
+    s.DD = p; p += T.np;
     s.S = p; p += 6 * T.npt;
     s.cst = p; p += 16;
     s.red = p; p += 96;
@@ -108,29 +113,94 @@ DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     (void)Kcap;
 }
 // per-CTA global scratch (doubles): LSC row list [npt*Kcap] x {n0,n1,n2,b,s,z,c,ds,dz} + point index (int);
-// pair rows [np] x 12
+// pair rows [np] x 13
 DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) {
     const size_t LS = (size_t)T.npt * Kcap;
-    return 9 * LS + (LS + 1) / 2 + 12 * (size_t)T.np;
+    return 9 * LS + (LS + 1) / 2 + 13 * (size_t)T.np;
 }
 
 // ------------------------------------------------------------------------------------------------
-// L D L' of the packed lower triangle W (row-major: (i,k) at i(i+1)/2+k), in place.
+// L D L' of the packed lower triangle W (row-major: (i,k) at i(i+1)/2+k), in place, rank-4 panels.
 // After the call column j holds the unscaled entries Lt(i,j) = l_ij * d_j and invp[j] = 1/d_j.
-// Returns false (uniformly) when a pivot is not positive.
+//   panel   : every thread owns one row i >= j0 of the 4-column panel and eliminates it against the
+//             4x4 diagonal block, which it factors redundantly from shared memory (no barrier inside
+//             the panel); unscaled and scaled panel rows go to pu / ps (4 doubles per row).
+//   trailing: A(i,k) -= sum_t pu(i,t) ps(k,t), one warp per row, lanes over k  (4 FMA per load/store).
+// Two barriers per 4 columns.  Returns false (uniformly) when a pivot is not positive.
+// pan: 8*ny doubles of shared scratch.
 // ------------------------------------------------------------------------------------------------
-DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, int ny) {
-    const int tx = c.tid & 15, ty = c.tid >> 4, nty = (c.nthr + 15) >> 4;
-    const int sx = (c.nthr >= 16) ? 16 : c.nthr;
-    for (int j = 0; j < ny; j++) {
-        const double piv = W[j * (j + 1) / 2 + j];
-        if (!(piv > 0)) return false;
-        const double ip = 1.0 / piv;
-        if (c.tid == 0) invp[j] = ip;
-        for (int i = j + 1 + ty; i < ny; i += nty) {
+DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, double* pan, int ny) {
+    double* pu = pan;
+    double* ps = pan + 4 * ny;
+#ifdef __CUDA_ARCH__
+    const int lane = c.tid & 31, warp = c.tid >> 5, nwarp = c.nthr >> 5;
+#else
+    const int lane = 0, warp = 0, nwarp = 1;
+#endif
+    const int lanes = (c.nthr >= 32) ? 32 : 1;
+    for (int j0 = 0; j0 < ny; j0 += 4) {
+        const int nb = (ny - j0 < 4) ? ny - j0 : 4;
+        // ---- 4x4 diagonal block (redundant in every thread) ----
+        double d[4][4];     // d[s][t], s >= t: unscaled block columns ; p[t] pivots
+        double ip[4];
+        bool ok = true;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; s2++)
+#pragma unroll
+            for (int t = 0; t <= s2; t++) d[s2][t] = (s2 < nb) ? W[(j0 + s2) * (j0 + s2 + 1) / 2 + j0 + t] : (s2 == t ? 1.0 : 0.0);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            // d[s][t] -= sum_{u<t} d[s][u] * d[t][u] * ip[u]
+#pragma unroll
+            for (int s2 = t; s2 < 4; s2++) {
+                double v = d[s2][t];
+#pragma unroll
+                for (int u = 0; u < t; u++) v -= d[s2][u] * (d[t][u] * ip[u]);
+                d[s2][t] = v;
+            }
+            if (!(d[t][t] > 0)) ok = false;
+            ip[t] = 1.0 / d[t][t];
+        }
+        if (!ok) return false;
+        // ---- panel rows ----
+        for (int i = j0 + c.tid; i < ny; i += c.nthr) {
+            const int row = i * (i + 1) / 2 + j0;
+            double a[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) a[t] = (t < nb && j0 + t <= i) ? W[row + t] : 0.0;
+#pragma unroll
+            for (int t = 1; t < 4; t++) {
+                double v = a[t];
+#pragma unroll
+                for (int u = 0; u < t; u++) v -= a[u] * (d[t][u] * ip[u]);
+                a[t] = v;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                // rows inside the diagonal block are written after the barrier (other threads may still be
+                // reading the block from W)
+                if (t < nb && i >= j0 + nb) W[row + t] = a[t];
+                const bool below = i > j0 + t;          // strictly below the diagonal of column j0+t
+                pu[i * 4 + t] = (below && t < nb) ? a[t] : 0.0;
+                ps[i * 4 + t] = (below && t < nb) ? a[t] * ip[t] : 0.0;
+            }
+            if (i < j0 + nb) invp[i] = ip[i - j0];
+        }
+        c.sync();
+#pragma unroll
+        for (int s2 = 0; s2 < 4; s2++)
+#pragma unroll
+            for (int t = 0; t <= s2; t++)
+                if (s2 < nb && (s2 % c.nthr) == c.tid) W[(j0 + s2) * (j0 + s2 + 1) / 2 + j0 + t] = d[s2][t];
+        // ---- trailing update: rows i >= j0+nb, columns j0+nb <= k <= i ----
+        const int k0 = j0 + nb;
+        for (int i = k0 + warp; i < ny; i += nwarp) {
             const int row = i * (i + 1) / 2;
-            const double lij = W[row + j] * ip;
-            for (int k = j + 1 + tx; k <= i; k += sx) W[row + k] -= lij * W[k * (k + 1) / 2 + j];
+            const double u0 = pu[i * 4], u1 = pu[i * 4 + 1], u2 = pu[i * 4 + 2], u3 = pu[i * 4 + 3];
+            for (int k = k0 + lane; k <= i; k += lanes) {
+                const double* q = ps + k * 4;
+                W[row + k] -= u0 * q[0] + u1 * q[1] + u2 * q[2] + u3 * q[3];
+            }
         }
         c.sync();
     }
@@ -280,7 +350,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     double* pr = scratch + 9 * LS + (LS + 1) / 2;
     double *ps_hi = pr, *pz_hi = pr + np, *pc_hi = pr + 2 * np, *ps_lo = pr + 3 * np, *pz_lo = pr + 4 * np,
            *pc_lo = pr + 5 * np, *pb_hi = pr + 6 * np, *pb_lo = pr + 7 * np, *pd_sh = pr + 8 * np,
-           *pd_zh = pr + 9 * np, *pd_sl = pr + 10 * np, *pd_zl = pr + 11 * np;
+           *pd_zh = pr + 9 * np, *pd_sl = pr + 10 * np, *pd_zl = pr + 11 * np, *p_act = pr + 12 * np;
 
     // ---- constants of this agent ----
     QpConst qc;
@@ -414,6 +484,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             double rp_inf = 0.0, mu = 0.0;
             for (int r = c.tid; r < np; r += c.nthr) {
                 const double act = pair_act(T, r, sm.y, sm.cst);
+                p_act[r] = act;                 // row activity of this iterate, reused by the later passes
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
                 rp_inf = fmax(rp_inf, fmax(fabs(rph), fabs(rpl)));
@@ -485,7 +556,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 sm.W[e] = v;
             }
             c.sync();
-            if (!ldl_factor(c, sm.W, sm.invp, ny)) { status = kStQpNumeric; break; }
+            if (!ldl_factor(c, sm.W, sm.invp, sm.pan, ny)) { status = kStQpNumeric; break; }
 
             // ============ predictor ============
             ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
@@ -494,7 +565,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             c.sync();
             double a_aff = 1.0;
             for (int r = c.tid; r < np; r += c.nthr) {
-                const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
+                const double act = p_act[r], gd = pair_act(T, r, sm.dy, nullptr);
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
                 const double dzh = -zh - (zh / sh) * dsh, dzl = -zl - (zl / sl) * dsl;   // (-s z - z ds)/s
@@ -534,7 +605,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
 
             // ============ corrector ============
             for (int r = c.tid; r < np; r += c.nthr) {
-                const double act = pair_act(T, r, sm.y, sm.cst);
+                const double act = p_act[r];
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
                 const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
@@ -567,7 +638,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             c.sync();
             double a_st = 1.0;
             for (int r = c.tid; r < np; r += c.nthr) {
-                const double act = pair_act(T, r, sm.y, sm.cst), gd = pair_act(T, r, sm.dy, nullptr);
+                const double act = p_act[r], gd = pair_act(T, r, sm.dy, nullptr);
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
                 const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;

@@ -18,14 +18,20 @@ namespace dlsc {
 // ------------------------------------------------------------------------------------------------
 struct Group {
     int lane, width;
+    bool block;      // device: true = the whole CTA cooperates (barrier votes), false = one warp
     DLSC_HD bool any(bool p) const {
 #ifdef __CUDA_ARCH__
-        return __any_sync(0xffffffffu, p) != 0;
+        return block ? (__syncthreads_or(p ? 1 : 0) != 0) : (__any_sync(0xffffffffu, p) != 0);
 #else
         return p;
 #endif
     }
-    DLSC_HD unsigned ballot(bool p) const {
+    DLSC_HD void sync() const {
+#ifdef __CUDA_ARCH__
+        if (block) __syncthreads(); else __syncwarp();
+#endif
+    }
+    DLSC_HD unsigned ballot(bool p) const {     // warp mode only
 #ifdef __CUDA_ARCH__
         return __ballot_sync(0xffffffffu, p);
 #else
@@ -200,8 +206,47 @@ DLSC_HD bool vertex_blocked(const EdtDev& E, const V3& q, double margin, float h
 }
 
 // isObstacleInSFC (:862-892): any lattice vertex of the box blocked?
+// Per call the cooperating threads first tabulate, per axis, the float lattice coordinates of the box and
+// the grid cell each falls into (exactly the reference's float -> double -> floor arithmetic, done once per
+// coordinate instead of once per vertex); the vertex loop is then integer indexing + one 16-byte load.
+// Note: no vertex may be skipped because "it was tested before" -- coordinates regenerated from a moved
+// box corner differ in the last float bit about half the time and sit exactly on cell boundaries, so the
+// reference's decision depends on that bit; the whole sequence of tests is reproduced.
+constexpr int kSfcTabMax = 96;
+constexpr int kSfcUnroll = 2;
+struct SfcTab {
+    float q[3][kSfcTabMax];
+    int c[3][kSfcTabMax];
+};
+
+DLSC_HD bool vertex_blocked_tab(const EdtDev& E, float qx, float qy, float qz, int cx, int cy, int cz,
+                                double margin, float half_res) {
+    float dist = -1.0f;
+    V3 cl = v3(0.f, 0.f, 0.f);
+    if (cx >= 0 && cy >= 0 && cz >= 0) {
+        const size_t idx = ((size_t)cx * E.dims[1] + cy) * E.dims[2] + cz;
+#ifdef __CUDA_ARCH__
+        const int4 rec = __ldg(E.cells + idx);
+        dist = __int_as_float(rec.x);
+#else
+        const int4 rec = E.cells[idx];
+        { union { int i; float f; } u; u.i = rec.x; dist = u.f; }
+#endif
+        if (!(dist < 1)) return false;
+        if (rec.y >= 0) { cl.x = E.centre[0][rec.y]; cl.y = E.centre[1][rec.z]; cl.z = E.centre[2][rec.w]; }
+    }
+    const V3 q = v3(qx, qy, qz);
+    const V3 d3v = v3(half_res, half_res, half_res);
+    const V3 lo = cl - d3v, hi = cl + d3v;
+    V3 cq = q;                                                  // Box::closestPoint :226-237
+    if (q.x < lo.x) cq.x = lo.x; else if (q.x > hi.x) cq.x = hi.x;
+    if (q.y < lo.y) cq.y = lo.y; else if (q.y > hi.y) cq.y = hi.y;
+    if (q.z < lo.z) cq.z = lo.z; else if (q.z > hi.z) cq.z = hi.z;
+    return linf_distance(cq, q) < margin + kEpsF;
+}
+
 DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
-                             long long* lookups) {
+                             SfcTab* tab, long long* lookups) {
     const double res = P.world_res;
     const float half_res = (float)(0.5 * res);
     const int m0 = (int)floor(((b.hi.x - b.lo.x) + kEpsF) / res) + 1;
@@ -209,18 +254,51 @@ DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E
     const int m2 = (int)floor(((b.hi.z - b.lo.z) + kEpsF) / res) + 1;
     if (m0 <= 0 || m1 <= 0 || m2 <= 0) return false;
     const int total = m0 * m1 * m2;
-    for (int base = 0; base < total; base += g.width) {
-        const int idx = base + g.lane;
-        bool hit = false;
-        if (idx < total) {
-            const int iz = idx % m2, t = idx / m2;
-            const int iy = t % m1, ix = t / m1;
-            const V3 q = v3((float)(b.lo.x + ix * res), (float)(b.lo.y + iy * res), (float)(b.lo.z + iz * res));
-            hit = vertex_blocked(E, q, margin, half_res);
+    if (m0 > kSfcTabMax || m1 > kSfcTabMax || m2 > kSfcTabMax) {
+        // oversized box: direct evaluation
+        for (int base = 0; base < total; base += g.width) {
+            const int idx = base + g.lane;
+            bool hit = false;
+            if (idx < total) {
+                const int iz = idx % m2, t = idx / m2;
+                const int iy = t % m1, ix = t / m1;
+                const V3 q = v3((float)(b.lo.x + ix * res), (float)(b.lo.y + iy * res), (float)(b.lo.z + iz * res));
+                hit = vertex_blocked(E, q, margin, half_res);
+                if (lookups) *lookups += 1;
+            }
+            if (g.any(hit)) return true;
         }
-        if (lookups) *lookups += (total - base < g.width) ? (total - base) : g.width;
+        return false;
+    }
+    // per-axis tables: coordinate (float)(lo + i*res) and cell floor(inv_res * coord) - min_key (or -1)
+    for (int e = g.lane; e < m0 + m1 + m2; e += g.width) {
+        const int ax = (e < m0) ? 0 : (e < m0 + m1 ? 1 : 2);
+        const int i = e - (ax == 0 ? 0 : (ax == 1 ? m0 : m0 + m1));
+        const float lo = (ax == 0) ? b.lo.x : (ax == 1 ? b.lo.y : b.lo.z);
+        const float q = (float)(lo + i * res);
+        int c = (int)floor(E.inv_res * (double)q) - E.min_key[ax];
+        if (c < 0 || c >= E.dims[ax]) c = -1;
+        tab->q[ax][i] = q;
+        tab->c[ax][i] = c;
+    }
+    g.sync();
+    const int m12 = m1 * m2;
+    for (int base = 0; base < total; base += g.width * kSfcUnroll) {
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < kSfcUnroll; u++) {
+            const int idx = base + u * g.width + g.lane;
+            if (idx < total) {
+                const int ix = idx / m12, r = idx - ix * m12;
+                const int iy = r / m2, iz = r - iy * m2;
+                hit = vertex_blocked_tab(E, tab->q[0][ix], tab->q[1][iy], tab->q[2][iz], tab->c[0][ix], tab->c[1][iy],
+                                         tab->c[2][iz], margin, half_res) || hit;
+                if (lookups) *lookups += 1;
+            }
+        }
         if (g.any(hit)) return true;
     }
+    g.sync();
     return false;
 }
 
@@ -235,9 +313,9 @@ DLSC_HD bool box_in_boundary(const DevParams& P, const Box& b) {
 
 // expandSFCIncrementally (:1023-1093)
 DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtDev& E, const Box& init,
-                                  double margin, double max_vel, Box& out, long long* lookups) {
+                                  double margin, double max_vel, Box& out, SfcTab* memo, long long* lookups) {
     const double res = P.world_res;
-    if (obstacle_in_box(g, P, E, init, margin, lookups)) return false;
+    if (obstacle_in_box(g, P, E, init, margin, memo, lookups)) return false;
     int axes = 0x543210;              // packed axis list, 4 bits each: -x -y -z +x +y +z
     int n_axes = 6;
     int iters[6] = {0, 0, 0, 0, 0, 0};
@@ -247,7 +325,7 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
     Box sfc = init, cand = init, upd = init;
     while (n_axes > 0) {
         cand = sfc; upd = sfc;
-        while (box_in_boundary(P, upd) && !obstacle_in_box(g, P, E, upd, margin, lookups)) {
+        while (box_in_boundary(P, upd) && !obstacle_in_box(g, P, E, upd, margin, memo, lookups)) {
             i++;
             if (i >= n_axes) i = 0;
             const int ax = (axes >> (4 * i)) & 0xf;
@@ -298,7 +376,7 @@ DLSC_HD Box hull_aabb(const V3* pts, int np) {
 // :781-860).  sfc [M][6] in/out.  Returns status bits.
 DLSC_HD int sfc_agent(const Group& g, const DevParams& P, const EdtDev& E, bool init, const V3& pos,
                       const float* init_traj, const V3& goal, const V3& wp, double radius, double max_vel,
-                      float* sfc, long long* lookups) {
+                      float* sfc, SfcTab* memo, long long* lookups) {
     const int M = P.M;
     const double res = P.world_res;
     int status = 0;
@@ -309,7 +387,7 @@ DLSC_HD int sfc_agent(const Group& g, const DevParams& P, const EdtDev& E, bool 
             v3_set(b.hi, k, (float)(ceil(v3_get(pos, k) / res) * res));
         }
         Box out;
-        if (!expand_incrementally(g, P, E, b, radius, max_vel, out, lookups)) {
+        if (!expand_incrementally(g, P, E, b, radius, max_vel, out, memo, lookups)) {
             status = kStSfcInitFailed;
             out = b;
         }
@@ -334,7 +412,7 @@ DLSC_HD int sfc_agent(const Group& g, const DevParams& P, const EdtDev& E, bool 
         v3_set(b.lo, k, (float)(round(v3_get(b.lo, k) / res) * res));
         v3_set(b.hi, k, (float)(round(v3_get(b.hi, k) / res) * res));
     }
-    bool ok = expand_incrementally(g, P, E, b, radius, max_vel, upd, lookups);
+    bool ok = expand_incrementally(g, P, E, b, radius, max_vel, upd, memo, lookups);
     if (ok && !superset_of_hull(upd, hull, 3)) ok = false;
     if (!ok) {
         // expandSFCFromConvexHull(convex_hull, sfc_prev) :817-860
@@ -356,10 +434,11 @@ DLSC_HD int sfc_agent(const Group& g, const DevParams& P, const EdtDev& E, bool 
                 v3_set(b.hi, k, (float)(floor((v3_get(r.hi, k) + kEpsF) / res) * res));
             }
         }
-        ok = expand_incrementally(g, P, E, b, radius, max_vel, upd, lookups);
+        ok = expand_incrementally(g, P, E, b, radius, max_vel, upd, memo, lookups);
         if (!ok) { upd = prev; status |= kStSfcReused; }
     }
     cur[M - 1] = upd;
+    g.sync();
     for (int m = g.lane; m < M; m += g.width) box_store(sfc + m * 6, cur[m]);
     return status;
 }

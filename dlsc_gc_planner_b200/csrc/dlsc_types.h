@@ -43,6 +43,7 @@ struct EdtDev {
     int min_key[3];
     double res, inv_res;
     const int4* cells;
+    const float* centre[3];      // centre[ax][c] = (float)(((double)(c + min_key[ax]) + 0.5) * res)
 };
 #endif
 

@@ -31,6 +31,7 @@ struct dlsc_ctx {
     std::vector<double> radius, downwash, max_vel, max_acc, nominal_vel, lsc_d, qp_x, cost, viol, scratch, smem;
     std::vector<int32_t> nbr_idx, nbr_cnt, qp_iters, status;
     std::vector<int4> cells;
+    std::vector<float> centre;
     EdtDev edt;
     bool have_edt = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -108,6 +109,11 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
     }
     for (int k = 0; k < 3; k++) { c->edt.dims[k] = dims[k]; c->edt.min_key[k] = min_key[k]; }
     c->edt.res = res; c->edt.inv_res = 1.0 / res; c->edt.cells = c->cells.data();
+    c->centre.clear();
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < dims[k]; i++) c->centre.push_back((float)(((double)(i + min_key[k]) + 0.5) * res));
+    c->edt.centre[0] = c->centre.data(); c->edt.centre[1] = c->centre.data() + dims[0];
+    c->edt.centre[2] = c->centre.data() + dims[0] + dims[1];
     c->have_edt = true;
     return 0;
 }
@@ -170,7 +176,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
     const DevParams& P = c->P;
     const int M = P.M, npt = M * kP, K = P.K;
     const int seq = c->seq + 1;
-    Group g; g.lane = 0; g.width = 1;
+    Group g; g.lane = 0; g.width = 1; g.block = false;
     if ((mask & DLSC_STAGE_SFC) && P.use_sfc && !c->have_edt) return fail("no EDT");
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP)) memset(c->counters, 0, sizeof(c->counters));
     if (mask & DLSC_STAGE_PREDICT)
@@ -212,9 +218,10 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             const bool init = c->sfc_init[la] != 0 || c->disturbed[la] != 0;
             long long lookups = 0;
+            SfcTab memo;
             const int st = sfc_agent(g, P, c->edt, init, v3_load(rec + npt * 3), c->init_traj.data() + (size_t)la * npt * 3,
                                      v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3), c->radius[la],
-                                     c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &lookups);
+                                     c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &memo, &lookups);
             c->sfc_init[la] = 0;
             c->status[la] |= st;
             c->counters[2] += lookups;
