@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from dlsc_gc_planner_b200 import capi, edt as edtmod, missions  # noqa: E402
+from dlsc_gc_planner_b200 import capi, edt as edtmod, missions, sharding  # noqa: E402
 
 METRIC = "agent-replans/sec (LSC+SFC+QP), synthetic 4096-agent 3D forest"
 UNIT = "agent-replans/s"
@@ -190,23 +190,18 @@ def run_ours(args):
     W, K = max(args.warmup, 3), args.steps
     cfg, m, edt = make_world(args)
     N = m.n_agents
-    assert N % world == 0, "agents must divide over the ranks"
-    NL, begin = N // world, rank * (N // world)
+    begin, NL = sharding.agent_block(N, world, rank)
     sl = slice(begin, begin + NL)
 
     rec, snap = pilot_rollout(cfg, m, edt, args, dev.index, W + K)
     pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr, begin=begin, n_local=NL, device=dev.index)
     pl.set_edt(*edt, cfg.world_res)
     pl.set_stream(torch.cuda.current_stream().cuda_stream)
-    rec_t = torch.zeros(N * pl.rec_floats, dtype=torch.float32, device=dev)
-    pl.bind_records(rec_t.data_ptr())
-    rec_local = rec_t[begin * pl.rec_floats:(begin + NL) * pl.rec_floats]
+    exchange = sharding.RecordExchange(pl, world, rank, device=dev)     # records live in a torch tensor NCCL gathers in place
     wp_dev = torch.from_numpy(np.ascontiguousarray(rec["wp"][:, sl])).to(dev)        # [T][NL][3] resident
     peak_fp64 = pl.measure_fp64_peak()
 
-    def gather():
-        if world > 1:
-            dist.all_gather_into_tensor(rec_t, rec_local)
+    gather = exchange.gather
 
     def barrier():
         if world > 1:
@@ -297,8 +292,8 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_ms = float(tt[0].item())
     e2e_exact = bool(np.array_equal(traj_h, snap["final_traj"][sl]))
-    h2d = int(4 * NL * 12 * world)
-    d2h = int(NL * cfg.M * (cfg.n + 1) * 12 * world)
+    h2d = int(4 * N * 12)
+    d2h = int(N * cfg.M * (cfg.n + 1) * 12)
 
     out = None
     if rank == 0:

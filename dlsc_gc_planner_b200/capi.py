@@ -53,7 +53,8 @@ EXPORTS = (
     "dlsc_get_violation dlsc_get_qp_iters dlsc_get_status dlsc_get_goal dlsc_get_state dlsc_get_init_traj "
     "dlsc_get_pred_traj dlsc_get_neighbours dlsc_get_lsc dlsc_get_sfc dlsc_set_sfc dlsc_enable_timing "
     "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device "
-    "dlsc_set_waypoints_device dlsc_measure_fp64_peak").split()
+    "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
+    "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc").split()
 
 
 def build_library(force=False):

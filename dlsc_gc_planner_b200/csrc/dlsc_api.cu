@@ -94,7 +94,7 @@ static int upload_tables(dlsc_ctx* c) {
     const size_t i_yp_ptr = SEC(yp_ptr), i_yp_pt = SEC(yp_pt), i_yp_coef = SEC(yp_coef);
     const size_t i_wi_ptr = SEC(wi_ptr), i_wi_row = SEC(wi_row), i_wi_coef = SEC(wi_coef);
     const size_t i_wp_ptr = SEC(wp_ptr), i_wp_pt = SEC(wp_pt), i_wp_coef = SEC(wp_coef);
-    const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2), i_tri = SEC(tri_p);
+    const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2), i_tri = SEC(tri_p), i_nz = SEC(nz_e);
 #undef SEC
     std::vector<char> blob(off ? off : 256, 0);
     for (auto& s : secs) memcpy(blob.data() + s.off, s.src, s.bytes);
@@ -115,6 +115,7 @@ static int upload_tables(dlsc_ctx* c) {
     T.wi_ptr = PTR(int, i_wi_ptr); T.wi_row = PTR(int16_t, i_wi_row); T.wi_coef = PTR(double, i_wi_coef);
     T.wp_ptr = PTR(int, i_wp_ptr); T.wp_pt = PTR(int16_t, i_wp_pt); T.wp_coef = PTR(double, i_wp_coef);
     T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2); T.tri_p = PTR(uint8_t, i_tri);
+    T.nz_e = PTR(uint16_t, i_nz); T.nnzw = h.nnzw;
 #undef PTR
     return 0;
 }
@@ -169,6 +170,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     c->rec_owned = true;
     rc |= dev_alloc(c, &S.acc, NL * 3);
     rc |= dev_alloc(c, &S.waypoint, NL * 3);
+    rc |= dev_alloc(c, &S.goal_new, NL * 3);
     rc |= dev_alloc(c, &S.disturbed, NL);
     rc |= dev_alloc(c, &S.sfc_init, NL);
     rc |= dev_alloc(c, &S.radius, NL); rc |= dev_alloc(c, &S.downwash, NL); rc |= dev_alloc(c, &S.max_vel, NL);
@@ -329,10 +331,35 @@ int dlsc_get_records(dlsc_ctx* c, int first, int count, float* host) {
     return 0;
 }
 
+static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& P, const DevState& S);
+
 int dlsc_run_stages(dlsc_ctx* c, int mask) {
     if (!c) return fail("null ctx");
+    return run_stages_impl(c, mask, c->P, c->S);
+}
+
+int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
+    if (!c) return fail("null ctx");
+    if (first < 0 || count < 1 || first + count > c->P.NL) return fail("dlsc_run_stages_subset: bad range");
+    DevParams P = c->P;
+    DevState S = c->S;
+    const size_t f = (size_t)first, K = P.K, M = P.M, npt = (size_t)P.M * kP;
+    P.begin += first; P.NL = count;
+    S.acc += f * 3; S.waypoint += f * 3; S.goal_new += f * 3; S.disturbed += f; S.sfc_init += f;
+    S.radius += f; S.downwash += f; S.max_vel += f; S.max_acc += f; S.nominal_vel += f;
+    S.init_traj += f * npt * 3; S.nbr_idx += f * K; S.nbr_cnt += f;
+    S.lsc_normal += f * K * M * 3; S.lsc_d += f * K * M * kP; S.lsc_anchor_last += f * K * 3;
+    S.sfc += f * M * 6; S.traj += f * npt * 3; S.qp_x += f * (size_t)P.D * npt;
+    S.cost += f; S.viol += f; S.qp_iters += f; S.status += f;
+    return run_stages_impl(c, mask, P, S);
+}
+
+static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const DevState& Sr) {
     CK(cudaSetDevice(c->device));
     if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && !c->have_edt) return fail("dlsc_run_stages: use_sfc set but no EDT grid (dlsc_set_edt)");
+    DevState Sfix = Sr;
+    Sfix.edt = c->S.edt;            // the grid may have been (re)set after a subset view was built
+    const DevState& Sx = Sfix;
     cudaStream_t st = c->stream;
     const int seq = c->seq + 1;     // planner_seq after the increment in TrajPlanner::plan (traj_planner.cpp:40)
     const bool tm = c->timing;
@@ -345,17 +372,18 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
         CK(cudaMemsetAsync(c->S.counters, 0, 8 * sizeof(unsigned long long), st));
     if (tm) CK(cudaEventRecord(ev[0], st));
-    if (mask & DLSC_STAGE_PREDICT) { launch_predict(c->P, c->S, seq, st); c->launches++; }
+    if (mask & DLSC_STAGE_PREDICT) { launch_predict(Pr, Sx, seq, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[1], st));
-    if (mask & DLSC_STAGE_NBR) { launch_neighbours(c->P, c->S, st); c->launches++; }
+    if (mask & DLSC_STAGE_NBR) { launch_neighbours(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[2], st));
-    if (mask & DLSC_STAGE_LSC) { launch_lsc(c->P, c->S, st); c->launches++; }
+    if (mask & DLSC_STAGE_LSC) { launch_lsc(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[3], st));
-    if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc) { launch_sfc(c->P, c->S, st); c->launches++; }
+    if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc) { launch_sfc(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[4], st));
-    if (mask & DLSC_STAGE_GOAL) { launch_goal(c->P, c->S, st); c->launches++; }
+    if (mask & DLSC_STAGE_GOAL) { launch_goal(Pr, Sx, st); c->launches++; }
+    else if (mask & DLSC_STAGE_QP) { launch_goal_copy(Pr, Sx, st); c->launches++; }   // QP alone: goal from the record
     if (tm) CK(cudaEventRecord(ev[5], st));
-    if (mask & DLSC_STAGE_QP) { launch_qp(c->P, c->S, c->T, c->qpl, st); c->launches++; }
+    if (mask & DLSC_STAGE_QP) { launch_qp(Pr, Sx, c->T, c->qpl, st); c->launches++; }
     if (tm) { CK(cudaEventRecord(ev[6], st)); c->ev_used++; }
     CK(cudaGetLastError());
     return 0;
@@ -410,15 +438,7 @@ int dlsc_get_init_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.init_t
 int dlsc_get_pred_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.pred_traj, (size_t)c->P.N * c->P.M * kP * 12) : fail("null ctx"); }
 int dlsc_get_sfc(dlsc_ctx* c, float* s) { return c ? d2h(c, s, c->S.sfc, (size_t)c->P.NL * c->P.M * 24) : fail("null ctx"); }
 
-int dlsc_get_goal(dlsc_ctx* c, float* goal) {
-    if (!c || !goal) return fail("null argument");
-    CK(cudaSetDevice(c->device));
-    const DevParams& P = c->P;
-    CK(cudaMemcpy2DAsync(goal, 12, c->S.rec + (size_t)P.begin * P.rec + c->rl.goal, (size_t)P.rec * 4, 12, P.NL,
-                         cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
-}
+int dlsc_get_goal(dlsc_ctx* c, float* goal) { return c ? d2h(c, goal, c->S.goal_new, (size_t)c->P.NL * 12) : fail("null ctx"); }
 int dlsc_get_state(dlsc_ctx* c, float* pos, float* vel, float* acc) {
     if (!c) return fail("null ctx");
     CK(cudaSetDevice(c->device));
@@ -453,6 +473,27 @@ int dlsc_get_lsc(dlsc_ctx* c, float* normal, float* anchor, double* d) {
         if (rc) return -1;
     }
     return 0;
+}
+static int h2d(dlsc_ctx* c, void* dev, const void* host, size_t bytes) {
+    if (!c || !host) return fail("null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dlsc_set_init_traj(dlsc_ctx* c, const float* t) { return c ? h2d(c, c->S.init_traj, t, (size_t)c->P.NL * c->P.M * kP * 12) : fail("null ctx"); }
+int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { return c ? h2d(c, c->S.pred_traj, t, (size_t)c->P.N * c->P.M * kP * 12) : fail("null ctx"); }
+int dlsc_set_neighbours(dlsc_ctx* c, const int32_t* idx, const int32_t* cnt) {
+    if (!c) return fail("null ctx");
+    if (h2d(c, c->S.nbr_idx, idx, (size_t)c->P.NL * c->P.K * 4)) return -1;
+    return h2d(c, c->S.nbr_cnt, cnt, (size_t)c->P.NL * 4);
+}
+int dlsc_set_lsc(dlsc_ctx* c, const float* normal, const float* anchor_last, const double* d) {
+    if (!c) return fail("null ctx");
+    const size_t pairs = (size_t)c->P.NL * c->P.K;
+    if (h2d(c, c->S.lsc_normal, normal, pairs * c->P.M * 12)) return -1;
+    if (h2d(c, c->S.lsc_anchor_last, anchor_last, pairs * 12)) return -1;
+    return h2d(c, c->S.lsc_d, d, pairs * c->P.M * kP * 8);
 }
 int dlsc_set_sfc(dlsc_ctx* c, const float* sfc, const uint8_t* init_flag) {
     if (!c) return fail("null ctx");

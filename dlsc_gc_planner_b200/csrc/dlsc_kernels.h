@@ -15,6 +15,8 @@ struct DevState {
     float* rec;                // [N][rec]  (all agents)
     float* acc;                // [NL][3]
     float* waypoint;           // [NL][3]
+    float* goal_new;           // [NL][3] current_goal_point after this step's goal stage (committed to the
+                               //         records by dlsc_advance / dlsc_publish_records)
     uint8_t* disturbed;        // [NL]
     uint8_t* sfc_init;         // [NL]
     double *radius, *downwash, *max_vel, *max_acc, *nominal_vel;   // [NL]
@@ -43,6 +45,7 @@ void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st);
+void launch_goal_copy(const DevParams& P, const DevState& S, cudaStream_t st);   // goal_new := record goal
 void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st);
 void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st);
 void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);

@@ -116,18 +116,29 @@ __global__ void __launch_bounds__(128) k_goal(const __grid_constant__ DevParams 
     const int la = blockIdx.x * blockDim.x + threadIdx.x;
     if (la >= P.NL) return;
     const int npt = P.M * kP;
-    float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     V3 goal = v3_load(rec + npt * 3 + 6);
     const size_t pr = (size_t)la * P.K;
     const int st = goal_agent(P, S.disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(S.waypoint + la * 3),
                               S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.nbr_cnt[la],
                               S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, goal);
-    v3_store(rec + npt * 3 + 6, goal);
+    v3_store(S.goal_new + la * 3, goal);     // the record keeps the previous goal until the step is published:
+                                             // the other agents' LSCs of this step must see it (broadcast semantics)
     if (st) atomicOr(S.status + la, st);
 }
 
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st) {
     k_goal<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S);
+}
+
+__global__ void k_goal_copy(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    if (la >= P.NL) return;
+    const float* rec = S.rec + (size_t)(P.begin + la) * P.rec + P.M * kP * 3 + 6;
+    for (int k = 0; k < 3; k++) S.goal_new[la * 3 + k] = rec[k];
+}
+void launch_goal_copy(const DevParams& P, const DevState& S, cudaStream_t st) {
+    k_goal_copy<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -144,6 +155,7 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ DevPara
         for (int k = 0; k < 3; k++) { rec[npt * 3 + k] = st[k]; rec[npt * 3 + 3 + k] = st[3 + k]; S.acc[la * 3 + k] = st[6 + k]; }
     }
     for (int e = 0; e < npt * 3; e++) rec[e] = tr[e];
+    for (int k = 0; k < 3; k++) rec[npt * 3 + 6 + k] = S.goal_new[la * 3 + k];
 }
 
 void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st) {
@@ -200,7 +212,7 @@ __global__ void k_reset(const __grid_constant__ DevParams P, const __grid_consta
     rec[o + 6] = s0; rec[o + 7] = s1; rec[o + 8] = s2;
     rec[o + 9] = (float)S.radius[la]; rec[o + 10] = (float)S.downwash[la];
     for (int e = o + 11; e < P.rec; e++) rec[e] = 0.f;
-    for (int k = 0; k < 3; k++) { S.acc[la * 3 + k] = 0.f; S.waypoint[la * 3 + k] = start[la * 3 + k]; }
+    for (int k = 0; k < 3; k++) { S.acc[la * 3 + k] = 0.f; S.waypoint[la * 3 + k] = start[la * 3 + k]; S.goal_new[la * 3 + k] = start[la * 3 + k]; }
     S.disturbed[la] = 0; S.sfc_init[la] = 1; S.status[la] = 0;
     for (int e = 0; e < npt * 3; e++) S.traj[(size_t)la * npt * 3 + e] = rec[e];
 }

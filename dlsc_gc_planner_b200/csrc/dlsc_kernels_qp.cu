@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ De
         const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
         QpIn in;
         in.pos = v3_load(rec + npt * 3); in.vel = v3_load(rec + npt * 3 + 3);
-        in.acc = v3_load(S.acc + la * 3); in.goal = v3_load(rec + npt * 3 + 6);
+        in.acc = v3_load(S.acc + la * 3); in.goal = v3_load(S.goal_new + la * 3);
         in.wp = v3_load(S.waypoint + la * 3);
         in.radius = S.radius[la]; in.max_vel = S.max_vel[la]; in.max_acc = S.max_acc[la];
         in.nominal_vel = S.nominal_vel[la];

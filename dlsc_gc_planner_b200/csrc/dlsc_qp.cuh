@@ -89,7 +89,7 @@ struct QpSmem {
 };
 DLSC_HD size_t qp_smem_doubles(const QpTab& T) {
     const size_t v12 = (2 * (size_t)T.np > 8 * (size_t)T.ny) ? 2 * (size_t)T.np : 8 * (size_t)T.ny;   // V1|V2, aliased by pan
-    return (size_t)T.ntri + 4 * (size_t)T.ny + 4 * (size_t)T.nx + v12 + (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
+    return (size_t)T.ntri + 4 * (size_t)T.ny + 16 + 4 * (size_t)T.nx + v12 + (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
            ((size_t)T.npt + 4) / 2 + 1;
 }
 DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
@@ -98,7 +98,7 @@ DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
 DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     double* p = base;
     s.W = p; p += T.ntri;
-    s.invp = p; p += T.ny; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny;
+    s.invp = p; p += T.ny + 16; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny;
     s.x = p; p += T.nx; s.dx = p; p += T.nx; s.ax1 = p; p += T.nx; s.ax2 = p; p += T.nx;
     {   // V1 and V2 are dead while W is being factorised: the panel buffers of ldl_factor alias them
         const size_t v12 = (2 * (size_t)T.np > 8 * (size_t)T.ny) ? 2 * (size_t)T.np : 8 * (size_t)T.ny;
@@ -132,6 +132,7 @@ DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) {
 DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, double* pan, int ny) {
     double* pu = pan;
     double* ps = pan + 4 * ny;
+    double* blk = invp + ny;          // 16 doubles: [0..9] eliminated block (row-major lower), [10..13] 1/pivot, [14] ok
 #ifdef __CUDA_ARCH__
     const int lane = c.tid & 31, warp = c.tid >> 5, nwarp = c.nthr >> 5;
 #else
@@ -140,28 +141,43 @@ DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, double* pan, int 
     const int lanes = (c.nthr >= 32) ? 32 : 1;
     for (int j0 = 0; j0 < ny; j0 += 4) {
         const int nb = (ny - j0 < 4) ? ny - j0 : 4;
-        // ---- 4x4 diagonal block (redundant in every thread) ----
-        double d[4][4];     // d[s][t], s >= t: unscaled block columns ; p[t] pivots
+        // ---- 4x4 diagonal block: eliminated by one thread, broadcast through shared memory ----
+        double d[4][4];     // d[s][t], s >= t: unscaled block columns
         double ip[4];
-        bool ok = true;
+        if (c.tid == 0) {
+            bool ok = true;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; s2++)
+#pragma unroll
+                for (int t = 0; t <= s2; t++) d[s2][t] = (s2 < nb) ? W[(j0 + s2) * (j0 + s2 + 1) / 2 + j0 + t] : (s2 == t ? 1.0 : 0.0);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+#pragma unroll
+                for (int s2 = t; s2 < 4; s2++) {
+                    double v = d[s2][t];
+#pragma unroll
+                    for (int u = 0; u < t; u++) v -= d[s2][u] * (d[t][u] * ip[u]);
+                    d[s2][t] = v;
+                }
+                if (!(d[t][t] > 0)) ok = false;
+                ip[t] = 1.0 / d[t][t];
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < 4; s2++)
+#pragma unroll
+                for (int t = 0; t <= s2; t++) blk[s2 * (s2 + 1) / 2 + t] = d[s2][t];
+#pragma unroll
+            for (int t = 0; t < 4; t++) blk[10 + t] = ip[t];
+            blk[14] = ok ? 1.0 : 0.0;
+        }
+        c.sync();
 #pragma unroll
         for (int s2 = 0; s2 < 4; s2++)
 #pragma unroll
-            for (int t = 0; t <= s2; t++) d[s2][t] = (s2 < nb) ? W[(j0 + s2) * (j0 + s2 + 1) / 2 + j0 + t] : (s2 == t ? 1.0 : 0.0);
+            for (int t = 0; t <= s2; t++) d[s2][t] = blk[s2 * (s2 + 1) / 2 + t];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            // d[s][t] -= sum_{u<t} d[s][u] * d[t][u] * ip[u]
-#pragma unroll
-            for (int s2 = t; s2 < 4; s2++) {
-                double v = d[s2][t];
-#pragma unroll
-                for (int u = 0; u < t; u++) v -= d[s2][u] * (d[t][u] * ip[u]);
-                d[s2][t] = v;
-            }
-            if (!(d[t][t] > 0)) ok = false;
-            ip[t] = 1.0 / d[t][t];
-        }
-        if (!ok) return false;
+        for (int t = 0; t < 4; t++) ip[t] = blk[10 + t];
+        if (blk[14] == 0.0) return false;
         // ---- panel rows ----
         for (int i = j0 + c.tid; i < ny; i += c.nthr) {
             const int row = i * (i + 1) / 2 + j0;
@@ -538,7 +554,10 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             if (rp_inf <= kQpTolRp && rd_inf <= kQpTolRd * (1.0 + g_inf) && mu <= kQpTolMu) { status = 0; break; }
 
             // ============ W = H + G' D G  (packed lower triangle) ============
-            for (int e = c.tid; e < T.ntri; e += c.nthr) {
+            for (int e = c.tid; e < T.ntri; e += c.nthr) sm.W[e] = 0.0;
+            c.sync();
+            for (int ei = c.tid; ei < T.nnzw; ei += c.nthr) {
+                const int e = T.nz_e[ei];
                 const int p = T.tri_p[e], q = e - p * (p + 1) / 2;
                 const int k = p / nyd, a = p - k * nyd, kk = q / nyd, b = q - kk * nyd;
                 double v = 0.0;

@@ -197,6 +197,19 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
         }
     flatten(yp, T.yp_ptr, T.yp_pt, T.yp_coef);
     flatten(wp, T.wp_ptr, T.wp_pt, T.wp_coef);
+
+    // structurally non-zero entries of W = H + G'DG (everything else is only fill-in of the factorisation)
+    T.nz_e.clear();
+    for (int p = 0; p < T.ny; p++)
+        for (int q = 0; q <= p; q++) {
+            const int e = p * (p + 1) / 2 + q;
+            const int k = p / nyd, a = p % nyd, kk = q / nyd, b = q % nyd;
+            const int el = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
+            bool nz = !wp[el].empty();
+            if (k == kk) nz = nz || a == b || T.H1[(size_t)a * nyd + b] != 0.0 || !wi[e].empty();
+            if (nz) T.nz_e.push_back((uint16_t)e);
+        }
+    T.nnzw = (int)T.nz_e.size();
 }
 
 }  // namespace dlsc

@@ -39,6 +39,8 @@ struct QpTabHost {
     std::vector<int> wi_ptr;  std::vector<int16_t> wi_row;  std::vector<double> wi_coef;   // pair rows per W entry (global lower tri)
     std::vector<int> wp_ptr;  std::vector<int16_t> wp_pt;   std::vector<double> wp_coef;   // points per local (a>=b)
     std::vector<uint8_t> tri_p;                   // [ntri] row index p of packed lower-triangle entry e
+    std::vector<uint16_t> nz_e;                   // packed indices e of the structurally non-zero entries of W
+    int nnzw = 0;
     std::vector<double> H1;                       // [nyd][nyd]  2*w_u*sum_m T_m' Q T_m
     std::vector<double> Q2;                       // [6][6]      2*w_u*Q
     std::vector<double> Qb;                       // [6][6]      Q_base
@@ -64,6 +66,8 @@ struct QpTab {
     const int *wi_ptr; const int16_t* wi_row; const double* wi_coef;
     const int *wp_ptr; const int16_t* wp_pt; const double* wp_coef;
     const uint8_t* tri_p;
+    const uint16_t* nz_e;
+    int nnzw;
     const double *H1, *Q2;
 };
 

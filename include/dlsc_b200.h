@@ -153,6 +153,9 @@ int dlsc_advance(dlsc_ctx* ctx);
 /* Refresh the local records from the current device state without moving the agents (used when
  * the host supplies the next states through dlsc_set_agents). */
 int dlsc_publish_records(dlsc_ctx* ctx);
+/* Run the given stages for the local agents [first, first+count) only (used by the per-agent
+ * compatibility classes when the caller replans one agent at a time). */
+int dlsc_run_stages_subset(dlsc_ctx* ctx, int stage_mask, int first, int count);
 int dlsc_sync(dlsc_ctx* ctx);
 int dlsc_get_seq(const dlsc_ctx* ctx);
 int dlsc_set_seq(dlsc_ctx* ctx, int seq);
@@ -174,6 +177,15 @@ int dlsc_get_neighbours(dlsc_ctx* ctx, int32_t* idx /* [n_local][K] */, int32_t*
 int dlsc_get_lsc(dlsc_ctx* ctx, float* normal, float* anchor, double* d);
 int dlsc_get_sfc(dlsc_ctx* ctx, float* sfc /* [n_local][M][6] min xyz, max xyz */);
 int dlsc_set_sfc(dlsc_ctx* ctx, const float* sfc, const uint8_t* init_flag /* [n_local] or NULL */);
+/* Stage inputs for single-stage use (per-kernel tests; TrajOptimizer::solve / CollisionConstraints of the
+ * compatibility layer): overwrite what the earlier stages would have produced.  Host arrays. */
+int dlsc_set_init_traj(dlsc_ctx* ctx, const float* traj /* [n_local][M][P][3] */);
+int dlsc_set_pred_traj(dlsc_ctx* ctx, const float* traj /* [n_agents][M][P][3] */);
+int dlsc_set_neighbours(dlsc_ctx* ctx, const int32_t* idx /* [n_local][K] */, const int32_t* cnt /* [n_local] */);
+/* normal [n_local][K][M][3], anchor_last [n_local][K][3] (anchor of segment M-1), d [n_local][K][M][P];
+ * anchors of the segments < M-1 are the neighbours' predicted control points (dlsc_set_pred_traj). */
+int dlsc_set_lsc(dlsc_ctx* ctx, const float* normal, const float* anchor_last, const double* d);
+
 /* mean device milliseconds per stage over the steps since the last call (CUDA events recorded on the
  * context's stream around every stage while dlsc_enable_timing(ctx,1); resolved, with one
  * synchronisation, by dlsc_get_timings); order: predict, nbr, lsc, sfc, goal, qp. */

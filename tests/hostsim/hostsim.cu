@@ -26,7 +26,7 @@ struct dlsc_ctx {
     QpTabHost th;
     QpTab T;
     int seq = 0;
-    std::vector<float> rec, acc, waypoint, pred_traj, init_traj, lsc_normal, lsc_anchor_last, sfc, traj;
+    std::vector<float> rec, acc, waypoint, goal_new, pred_traj, init_traj, lsc_normal, lsc_anchor_last, sfc, traj;
     std::vector<uint8_t> disturbed, sfc_init;
     std::vector<double> radius, downwash, max_vel, max_acc, nominal_vel, lsc_d, qp_x, cost, viol, scratch, smem;
     std::vector<int32_t> nbr_idx, nbr_cnt, qp_iters, status;
@@ -66,7 +66,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     double time = 0;
     for (int e = 0; e < hp->M * kP; e++) { P.tk[e] = (float)time; time += hp->dt / hp->n; }
     const size_t N = n_agents, NL = n_local, K = hp->max_nbr, M = hp->M, npt = M * kP;
-    c->rec.assign(N * P.rec, 0.f); c->acc.assign(NL * 3, 0.f); c->waypoint.assign(NL * 3, 0.f);
+    c->rec.assign(N * P.rec, 0.f); c->acc.assign(NL * 3, 0.f); c->waypoint.assign(NL * 3, 0.f); c->goal_new.assign(NL * 3, 0.f);
     c->disturbed.assign(NL, 0); c->sfc_init.assign(NL, 1);
     c->radius.assign(NL, 0); c->downwash.assign(NL, 0); c->max_vel.assign(NL, 0); c->max_acc.assign(NL, 0);
     c->nominal_vel.assign(NL, 0);
@@ -89,7 +89,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     T.yp_ptr = h.yp_ptr.data(); T.yp_pt = h.yp_pt.data(); T.yp_coef = h.yp_coef.data();
     T.wi_ptr = h.wi_ptr.data(); T.wi_row = h.wi_row.data(); T.wi_coef = h.wi_coef.data();
     T.wp_ptr = h.wp_ptr.data(); T.wp_pt = h.wp_pt.data(); T.wp_coef = h.wp_coef.data();
-    T.H1 = h.H1.data(); T.Q2 = h.Q2.data(); T.tri_p = h.tri_p.data();
+    T.H1 = h.H1.data(); T.Q2 = h.Q2.data(); T.tri_p = h.tri_p.data(); T.nz_e = h.nz_e.data(); T.nnzw = h.nnzw;
     c->scratch.assign(qp_scratch_doubles(T, P.K), 0.0);
     c->smem.assign(qp_smem_bytes(T, P.K) / 8 + 8, 0.0);
     memset(&c->edt, 0, sizeof(c->edt));
@@ -138,7 +138,7 @@ int dlsc_reset(dlsc_ctx* c, const float* start) {
         for (int k = 0; k < 3; k++) { rec[o + k] = start[la * 3 + k]; rec[o + 3 + k] = 0.f; rec[o + 6 + k] = start[la * 3 + k]; }
         rec[o + 9] = (float)c->radius[la]; rec[o + 10] = (float)c->downwash[la];
         for (int e = o + 11; e < P.rec; e++) rec[e] = 0.f;
-        for (int k = 0; k < 3; k++) { c->acc[la * 3 + k] = 0.f; c->waypoint[la * 3 + k] = start[la * 3 + k]; }
+        for (int k = 0; k < 3; k++) { c->acc[la * 3 + k] = 0.f; c->waypoint[la * 3 + k] = start[la * 3 + k]; c->goal_new[la * 3 + k] = start[la * 3 + k]; }
         c->disturbed[la] = 0; c->sfc_init[la] = 1; c->status[la] = 0;
         for (int e = 0; e < npt * 3; e++) c->traj[(size_t)la * npt * 3 + e] = rec[e];
     }
@@ -228,16 +228,19 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
         }
     if (mask & DLSC_STAGE_GOAL)
         for (int la = 0; la < P.NL; la++) {
-            float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+            const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             V3 goal = v3_load(rec + npt * 3 + 6);
             const size_t pr = (size_t)la * K;
             const int st = goal_agent(P, c->disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(c->waypoint.data() + la * 3),
                                       c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->nbr_cnt[la],
                                       c->lsc_normal.data() + pr * M * 3, c->lsc_d.data() + pr * M * kP,
                                       c->lsc_anchor_last.data() + pr * 3, goal);
-            v3_store(rec + npt * 3 + 6, goal);
+            v3_store(c->goal_new.data() + la * 3, goal);
             c->status[la] |= st;
         }
+    else if (mask & DLSC_STAGE_QP)
+        for (int la = 0; la < P.NL; la++)
+            for (int k = 0; k < 3; k++) c->goal_new[la * 3 + k] = c->rec[(size_t)(P.begin + la) * P.rec + npt * 3 + 6 + k];
     if (mask & DLSC_STAGE_QP) {
         QpSmem sm;
         qp_smem_carve(c->T, K, c->smem.data(), sm);
@@ -246,7 +249,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             QpIn in;
             in.pos = v3_load(rec + npt * 3); in.vel = v3_load(rec + npt * 3 + 3);
-            in.acc = v3_load(c->acc.data() + la * 3); in.goal = v3_load(rec + npt * 3 + 6);
+            in.acc = v3_load(c->acc.data() + la * 3); in.goal = v3_load(c->goal_new.data() + la * 3);
             in.wp = v3_load(c->waypoint.data() + la * 3);
             in.radius = c->radius[la]; in.max_vel = c->max_vel[la]; in.max_acc = c->max_acc[la];
             in.nominal_vel = c->nominal_vel[la];
@@ -291,6 +294,7 @@ static void advance_impl(dlsc_ctx* c, bool move) {
             for (int k = 0; k < 3; k++) { rec[npt * 3 + k] = st[k]; rec[npt * 3 + 3 + k] = st[3 + k]; c->acc[la * 3 + k] = st[6 + k]; }
         }
         for (int e = 0; e < npt * 3; e++) rec[e] = tr[e];
+        for (int k = 0; k < 3; k++) rec[npt * 3 + 6 + k] = c->goal_new[la * 3 + k];
     }
 }
 int dlsc_advance(dlsc_ctx* c) { advance_impl(c, true); return 0; }
@@ -311,12 +315,7 @@ GET(dlsc_get_pred_traj, float, pred_traj)
 GET(dlsc_get_sfc, float, sfc)
 #undef GET
 
-int dlsc_get_goal(dlsc_ctx* c, float* goal) {
-    const DevParams& P = c->P;
-    for (int la = 0; la < P.NL; la++)
-        for (int k = 0; k < 3; k++) goal[la * 3 + k] = c->rec[(size_t)(P.begin + la) * P.rec + c->rl.goal + k];
-    return 0;
-}
+int dlsc_get_goal(dlsc_ctx* c, float* goal) { memcpy(goal, c->goal_new.data(), c->goal_new.size() * 4); return 0; }
 int dlsc_get_state(dlsc_ctx* c, float* pos, float* vel, float* acc) {
     const DevParams& P = c->P;
     for (int la = 0; la < P.NL; la++)
@@ -363,6 +362,17 @@ int64_t dlsc_launch_count(const dlsc_ctx*) { return 0; }
 int dlsc_enable_timing(dlsc_ctx*, int) { return 0; }
 int dlsc_get_timings(dlsc_ctx*, double ms[DLSC_N_STAGES], int* n) { for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = 0; if (n) *n = 0; return 0; }
 
+int dlsc_run_stages_subset(dlsc_ctx*, int, int, int) { return fail("hostsim: not supported"); }
+int dlsc_set_init_traj(dlsc_ctx* c, const float* t) { memcpy(c->init_traj.data(), t, c->init_traj.size() * 4); return 0; }
+int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { memcpy(c->pred_traj.data(), t, c->pred_traj.size() * 4); return 0; }
+int dlsc_set_neighbours(dlsc_ctx* c, const int32_t* idx, const int32_t* cnt) {
+    memcpy(c->nbr_idx.data(), idx, c->nbr_idx.size() * 4); memcpy(c->nbr_cnt.data(), cnt, c->nbr_cnt.size() * 4); return 0;
+}
+int dlsc_set_lsc(dlsc_ctx* c, const float* normal, const float* anchor_last, const double* d) {
+    memcpy(c->lsc_normal.data(), normal, c->lsc_normal.size() * 4);
+    memcpy(c->lsc_anchor_last.data(), anchor_last, c->lsc_anchor_last.size() * 4);
+    memcpy(c->lsc_d.data(), d, c->lsc_d.size() * 8); return 0;
+}
 int dlsc_set_waypoints_device(dlsc_ctx* c, const float* p) { memcpy(c->waypoint.data(), p, c->waypoint.size() * 4); return 0; }
 int dlsc_measure_fp64_peak(dlsc_ctx*, double* t) { *t = 0.0; return 0; }
 int dlsc_set_stream(dlsc_ctx*, void*) { return 0; }
