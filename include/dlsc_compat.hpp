@@ -300,7 +300,9 @@ public:
     // replan agent i (or everybody when all agents were staged); fills the result cache
     void plan(int i) {
         step_open = true;
-        const bool all = std::all_of(staged.begin(), staged.end(), [](uint8_t s) { return s != 0; });
+        // one batched launch only when every agent was announced before the first plan() of the step
+        const bool none_planned = std::none_of(planned.begin(), planned.end(), [](uint8_t s) { return s != 0; });
+        const bool all = (batch_done || none_planned) && std::all_of(staged.begin(), staged.end(), [](uint8_t s) { return s != 0; });
         if (all && !batch_done) {
             upload();
             check(dlsc_step(ctx), "dlsc_step");

@@ -101,7 +101,7 @@ int main(int argc, char** argv) {
         obs[0].type = ObstacleType::AGENT; obs[0].id = 1; obs[0].position = point3d(1.5f, 0.f, 1.f);
         cons.initializeLSC(obs);
         for (int m = 0; m < param.M; m++)
-            for (int i = 0; i <= param.n; i++) cons.setLSC(0, m, i, LSC(point3d(1.5f, 0.f, 1.f), point3d(1.f, 0.f, 0.f), 0.15));
+            for (int i = 0; i <= param.n; i++) cons.setLSC(0, m, i, LSC(point3d(1.5f, 0.f, 1.f), point3d(1.f, 0.f, 0.f), 0.4));   // x >= 1.9: active (free optimum ends at 1.878)
         traj_t init(param.M, param.n, param.dt);
         for (int m = 0; m < param.M; m++)
             for (int i = 0; i <= param.n; i++) init[m][i] = a.current_state.position;
