@@ -95,6 +95,7 @@ static int upload_tables(dlsc_ctx* c) {
     const size_t i_wi_ptr = SEC(wi_ptr), i_wi_row = SEC(wi_row), i_wi_coef = SEC(wi_coef);
     const size_t i_wp_ptr = SEC(wp_ptr), i_wp_pt = SEC(wp_pt), i_wp_coef = SEC(wp_coef);
     const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2), i_tri = SEC(tri_p), i_nz = SEC(nz_e);
+    const size_t i_desc = SEC(pr_desc), i_hdr = SEC(nz_hdr), i_nzh = SEC(nz_h);
 #undef SEC
     std::vector<char> blob(off ? off : 256, 0);
     for (auto& s : secs) memcpy(blob.data() + s.off, s.src, s.bytes);
@@ -116,6 +117,12 @@ static int upload_tables(dlsc_ctx* c) {
     T.wp_ptr = PTR(int, i_wp_ptr); T.wp_pt = PTR(int16_t, i_wp_pt); T.wp_coef = PTR(double, i_wp_coef);
     T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2); T.tri_p = PTR(uint8_t, i_tri);
     T.nz_e = PTR(uint16_t, i_nz); T.nnzw = h.nnzw;
+    T.pr_desc = PTR(uint32_t, i_desc); T.nz_hdr = PTR(uint4, i_hdr); T.nz_h = PTR(double, i_nzh);
+    {
+        const int M = h.M, MP = M * kP;
+        T.row_npl = h.np / h.D; T.row_bv = MP - 3; T.row_ba = T.row_bv + (M * 5 - 2); T.row_bc = T.row_ba + (M * 4 - 1);
+        T.scv = h.scv; T.sca = h.sca;
+    }
 #undef PTR
     return 0;
 }

@@ -129,16 +129,10 @@ DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) {
 // Two barriers per 4 columns.  Returns false (uniformly) when a pivot is not positive.
 // pan: 8*ny doubles of shared scratch.
 // ------------------------------------------------------------------------------------------------
-DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, double* pan, int ny) {
+DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, double* pan, int ny, const uint8_t* tri_p) {
     double* pu = pan;
     double* ps = pan + 4 * ny;
     double* blk = invp + ny;          // 16 doubles: [0..9] eliminated block (row-major lower), [10..13] 1/pivot, [14] ok
-#ifdef __CUDA_ARCH__
-    const int lane = c.tid & 31, warp = c.tid >> 5, nwarp = c.nthr >> 5;
-#else
-    const int lane = 0, warp = 0, nwarp = 1;
-#endif
-    const int lanes = (c.nthr >= 32) ? 32 : 1;
     for (int j0 = 0; j0 < ny; j0 += 4) {
         const int nb = (ny - j0 < 4) ? ny - j0 : 4;
         // ---- 4x4 diagonal block: eliminated by one thread, broadcast through shared memory ----
@@ -207,15 +201,35 @@ DLSC_HD bool ldl_factor(const Cta& c, double* W, double* invp, double* pan, int 
         for (int s2 = 0; s2 < 4; s2++)
 #pragma unroll
             for (int t = 0; t <= s2; t++)
-                if (s2 < nb && (s2 % c.nthr) == c.tid) W[(j0 + s2) * (j0 + s2 + 1) / 2 + j0 + t] = d[s2][t];
-        // ---- trailing update: rows i >= j0+nb, columns j0+nb <= k <= i ----
+                if (s2 < nb && (c.nthr == 1 || c.tid == s2)) W[(j0 + s2) * (j0 + s2 + 1) / 2 + j0 + t] = d[s2][t];
+        // ---- trailing update: one 4x4 tile of A(i,k) -= sum_t pu(i,t) ps(k,t) per thread (64 FMA per
+        //      16 loads of W; the panel rows of the tile's 4 rows / 4 columns sit in registers) ----
         const int k0 = j0 + nb;
-        for (int i = k0 + warp; i < ny; i += nwarp) {
-            const int row = i * (i + 1) / 2;
-            const double u0 = pu[i * 4], u1 = pu[i * 4 + 1], u2 = pu[i * 4 + 2], u3 = pu[i * 4 + 3];
-            for (int k = k0 + lane; k <= i; k += lanes) {
-                const double* q = ps + k * 4;
-                W[row + k] -= u0 * q[0] + u1 * q[1] + u2 * q[2] + u3 * q[3];
+        if (k0 < ny) {
+            const int I0 = k0 >> 2, nT = ((ny + 3) >> 2) - I0, ntile = nT * (nT + 1) / 2;
+            for (int t = c.tid; t < ntile; t += c.nthr) {
+                const int Ir = tri_p[t], Kr = t - Ir * (Ir + 1) / 2;
+                const int i0 = (I0 + Ir) << 2, kk0 = (I0 + Kr) << 2;
+                double u[4][4], q[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int t2 = 0; t2 < 4; t2++) {
+                        u[r][t2] = (i0 + r < ny) ? pu[(i0 + r) * 4 + t2] : 0.0;
+                        q[r][t2] = (kk0 + r < ny) ? ps[(kk0 + r) * 4 + t2] : 0.0;
+                    }
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int i = i0 + r;
+                    if (i < ny) {
+                        const int row = i * (i + 1) / 2;
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++) {
+                            const int k = kk0 + cc;
+                            if (k <= i) W[row + k] -= u[r][0] * q[cc][0] + u[r][1] * q[cc][1] + u[r][2] * q[cc][2] + u[r][3] * q[cc][3];
+                        }
+                    }
+                }
             }
         }
         c.sync();
@@ -275,26 +289,38 @@ DLSC_HD void ldl_solve(const Cta& c, const double* W, const double* invp, double
 // ------------------------------------------------------------------------------------------------
 DLSC_HD int sym_idx(int k, int kk) { return k >= kk ? k * (k + 1) / 2 + kk : kk * (kk + 1) / 2 + k; }
 
-// x = c + T y  (or dx = T dy when cst == nullptr)
+// x = c + T y  (or dx = T dy when cst == nullptr); T hard-wired from the elimination in dlsc_qp_tables.h:
+//   x[m][3+j] = y[3m+j] (m < M-1), x[M-1][3..5] = y[3(M-1)], x[m][0] = y5(m-1), x[m][1] = 2 y5 - y4,
+//   x[m][2] = 4 y5 - 4 y4 + y3 (m >= 1), x[0][0..2] = c0, c1, c2
 DLSC_HD void map_x(const Cta& c, const QpTab& T, const double* y, const double* cst, double* x) {
-    for (int k = 0; k < T.D; k++)
-        for (int pt = c.tid; pt < T.npt; pt += c.nthr) {
-            double v = 0.0;
-            const int ci = T.xm_cidx[pt];
-            if (cst && ci >= 0) v = cst[k * 3 + ci];
-            const int nv = T.xm_nv[pt];
-            for (int t = 0; t < nv; t++) v += T.xm_coef[pt * 3 + t] * y[k * T.nyd + T.xm_idx[pt * 3 + t]];
-            x[k * T.npt + pt] = v;
+    const int M = T.M, nyd = T.nyd, npt = T.npt;
+    for (int k = 0; k < T.D; k++) {
+        const double* yk = y + k * nyd;
+        for (int pt = c.tid; pt < npt; pt += c.nthr) {
+            const int m = pt / kP, i = pt - m * kP;
+            double v;
+            if (i >= 3) v = (m == M - 1) ? yk[3 * (M - 1)] : yk[3 * m + i - 3];
+            else if (m == 0) v = cst ? cst[k * 3 + i] : 0.0;
+            else {
+                const double* q = yk + 3 * (m - 1);
+                v = (i == 0) ? q[2] : (i == 1 ? 2.0 * q[2] - q[1] : 4.0 * q[2] - 4.0 * q[1] + q[0]);
+            }
+            x[k * npt + pt] = v;
         }
+    }
 }
 
-// uy[p] = sum_{pair rows} coef V[row] + sum_{points} coef ax[k][pt]
-DLSC_HD double gather_y(const QpTab& T, int p, const double* V, const double* ax) {
-    double v = 0.0;
-    for (int e = T.yi_ptr[p]; e < T.yi_ptr[p + 1]; e++) v += T.yi_coef[e] * V[T.yi_row[e]];
-    const int k = p / T.nyd, a = p - k * T.nyd;
-    for (int e = T.yp_ptr[a]; e < T.yp_ptr[a + 1]; e++) v += T.yp_coef[e] * ax[k * T.npt + T.yp_pt[e]];
-    return v;
+// uy[p] = (T' ax)[p] for global unknown p
+DLSC_HD double gather_y(const QpTab& T, int p, const double* ax) {
+    const int M = T.M, nyd = T.nyd, npt = T.npt;
+    const int k = p / nyd, a = p - k * nyd;
+    const double* xk = ax + k * npt;
+    if (a == 3 * (M - 1)) { const double* q = xk + (M - 1) * kP; return q[3] + q[4] + q[5]; }
+    const int m = a / 3, j = a - 3 * m;
+    const double* q = xk + m * kP;          // q[6..8] = points 0..2 of segment m+1
+    if (j == 0) return q[3] + q[8];
+    if (j == 1) return q[4] - q[7] - 4.0 * q[8];
+    return q[5] + q[6] + 2.0 * q[7] + 4.0 * q[8];
 }
 
 struct QpConst {
@@ -302,11 +328,51 @@ struct QpConst {
     int ts;
 };
 
-DLSC_HD void pair_bounds(const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, int r,
+// ---- two-sided rows with constant patterns, evaluated by stencil arithmetic in x-space ----
+// row index inside an axis (see dlsc_qp_tables.cpp): box | velocity | acceleration | comm
+struct PairRow { int fam, pa, pb; };
+DLSC_HD PairRow pair_decode(const QpTab& T, int idx) {
+    PairRow r; r.pb = 0;
+    if (idx < T.row_bv) { r.fam = 0; r.pa = idx + 3; }
+    else if (idx < T.row_ba) { const int t = idx - T.row_bv + 2; r.fam = 1; r.pa = (t / 5) * kP + t % 5; }
+    else if (idx < T.row_bc) { const int t = idx - T.row_ba + 1; r.fam = 2; r.pa = (t / 4) * kP + t % 4; }
+    else {
+        int t = idx - T.row_bc, mi = 0;
+        while (t >= T.M - mi) { t -= T.M - mi; mi++; }
+        r.fam = 3; r.pa = (mi + t) * kP + (kP - 1); r.pb = mi * kP;
+    }
+    return r;
+}
+DLSC_HD double pair_eval(const QpTab& T, const PairRow& r, const double* xk) {
+    if (r.fam == 0) return xk[r.pa];
+    if (r.fam == 1) return T.scv * (xk[r.pa + 1] - xk[r.pa]);
+    if (r.fam == 2) return T.sca * (xk[r.pa + 2] - 2.0 * xk[r.pa + 1] + xk[r.pa]);
+    return xk[r.pa] - xk[r.pb];
+}
+// (G_pair' V) at point pt of one axis; Vk = V + k*row_npl
+DLSC_HD double pair_transpose(const QpTab& T, const double* Vk, int pt) {
+    const int M = T.M, m = pt / kP, i = pt - m * kP;
+    double v = 0.0;
+    if (pt >= 3) v += Vk[pt - 3];
+    const double* vv = Vk + T.row_bv + 5 * m - 2;       // velocity row (m, j) at vv[j], valid unless m == 0 && j < 2
+    if (i >= 1 && (m > 0 || i - 1 >= 2)) v += T.scv * vv[i - 1];
+    if (i <= 4 && (m > 0 || i >= 2)) v -= T.scv * vv[i];
+    const double* va = Vk + T.row_ba + 4 * m - 1;       // acceleration row (m, j) at va[j], valid unless m == 0 && j == 0
+    if (i >= 2 && (m > 0 || i - 2 >= 1)) v += T.sca * va[i - 2];
+    if (i >= 1 && i <= 4 && (m > 0 || i - 1 >= 1)) v -= 2.0 * T.sca * va[i - 1];
+    if (i <= 3 && (m > 0 || i >= 1)) v += T.sca * va[i];
+    if (T.use_comm) {
+        const double* vc = Vk + T.row_bc;               // comm row (mi, m') at vc[mi*M - mi(mi-1)/2 + m' - mi]
+        if (i == kP - 1) for (int mi = 0; mi <= m; mi++) v += vc[mi * M - mi * (mi - 1) / 2 + m - mi];
+        if (i == 0) for (int m2 = m; m2 < M; m2++) v -= vc[m * M - m * (m - 1) / 2 + m2 - m];
+    }
+    return v;
+}
+
+DLSC_HD void pair_bounds(const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, int k, const PairRow& r,
                          double& lo, double& hi) {
-    const int fam = T.pr_fam[r], k = T.pr_axis[r];
-    if (fam == 0) {
-        const int pt = T.pr_pt[r], m = pt / kP, i = pt - m * kP;
+    if (r.fam == 0) {
+        const int m = r.pa / kP, i = r.pa - m * kP;
         hi = P.world_max[k]; lo = P.world_min[k];
         if (P.use_sfc) {
             const double bl = (double)in.sfc[m * 6 + k], bh = (double)in.sfc[m * 6 + 3 + k];
@@ -318,20 +384,9 @@ DLSC_HD void pair_bounds(const DevParams& P, const QpTab& T, const QpIn& in, con
             if (w - qc.wpr > lo) lo = w - qc.wpr;
             if (w + qc.wpr < hi) hi = w + qc.wpr;
         }
-    } else if (fam == 1) { hi = qc.hi_v; lo = -qc.hi_v; }
-    else if (fam == 2) { hi = qc.hi_a; lo = -qc.hi_a; }
+    } else if (r.fam == 1) { hi = qc.hi_v; lo = -qc.hi_v; }
+    else if (r.fam == 2) { hi = qc.hi_a; lo = -qc.hi_a; }
     else { hi = qc.hi_c; lo = -qc.hi_c; }
-}
-
-DLSC_HD double pair_act(const QpTab& T, int r, const double* y, const double* cst) {
-    double v = 0.0;
-    const int nnz = T.pr_nnz[r];
-    for (int t = 0; t < nnz; t++) v += T.pr_val[r * 6 + t] * y[T.pr_idx[r * 6 + t]];
-    if (cst) {
-        const int k = T.pr_axis[r];
-        v += T.pr_cc[r * 3] * cst[k * 3] + T.pr_cc[r * 3 + 1] * cst[k * 3 + 1] + T.pr_cc[r * 3 + 2] * cst[k * 3 + 2];
-    }
-    return v;
 }
 
 // LSC row (pt, cc) of this agent:  -n.x <= b  with  b = -(n.anchor + d)   (traj_optimizer.cpp:412-450)
@@ -359,14 +414,17 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     const int n = kP - 1;
     const bool D3 = (D == 3);
     const size_t LS = (size_t)npt * Kc;
-    double *l_n0 = scratch, *l_n1 = scratch + LS, *l_n2 = scratch + 2 * LS, *l_b = scratch + 3 * LS,
-           *l_s = scratch + 4 * LS, *l_z = scratch + 5 * LS, *l_c = scratch + 6 * LS, *l_ds = scratch + 7 * LS,
-           *l_dz = scratch + 8 * LS;
-    int* l_pt = reinterpret_cast<int*>(scratch + 9 * LS);
+    double* __restrict__ l_n0 = scratch; double* __restrict__ l_n1 = scratch + LS; double* __restrict__ l_n2 = scratch + 2 * LS;
+    double* __restrict__ l_b = scratch + 3 * LS; double* __restrict__ l_s = scratch + 4 * LS; double* __restrict__ l_z = scratch + 5 * LS;
+    double* __restrict__ l_c = scratch + 6 * LS; double* __restrict__ l_ds = scratch + 7 * LS; double* __restrict__ l_dz = scratch + 8 * LS;
+    int* __restrict__ l_pt = reinterpret_cast<int*>(scratch + 9 * LS);
     double* pr = scratch + 9 * LS + (LS + 1) / 2;
-    double *ps_hi = pr, *pz_hi = pr + np, *pc_hi = pr + 2 * np, *ps_lo = pr + 3 * np, *pz_lo = pr + 4 * np,
-           *pc_lo = pr + 5 * np, *pb_hi = pr + 6 * np, *pb_lo = pr + 7 * np, *pd_sh = pr + 8 * np,
-           *pd_zh = pr + 9 * np, *pd_sl = pr + 10 * np, *pd_zl = pr + 11 * np, *p_act = pr + 12 * np;
+    double* __restrict__ ps_hi = pr; double* __restrict__ pz_hi = pr + np; double* __restrict__ pc_hi = pr + 2 * np;
+    double* __restrict__ ps_lo = pr + 3 * np; double* __restrict__ pz_lo = pr + 4 * np; double* __restrict__ pc_lo = pr + 5 * np;
+    double* __restrict__ pb_hi = pr + 6 * np; double* __restrict__ pb_lo = pr + 7 * np; double* __restrict__ pd_sh = pr + 8 * np;
+    double* __restrict__ pd_zh = pr + 9 * np; double* __restrict__ pd_sl = pr + 10 * np; double* __restrict__ pd_zl = pr + 11 * np;
+    double* __restrict__ p_act = pr + 12 * np;
+    const int npl = T.row_npl;
 
     // ---- constants of this agent ----
     QpConst qc;
@@ -410,17 +468,17 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     c.sync();
     for (int k = 0; k < D; k++)
         for (int pt = c.tid; pt < npt; pt += c.nthr) sm.ax1[k * npt + pt] = grad_x(sm.x, k, pt);
-    for (int r = c.tid; r < np; r += c.nthr) sm.V1[r] = 0.0;
     c.sync();
     double g_inf = 0.0;
-    for (int p = c.tid; p < ny; p += c.nthr) { const double v = fabs(gather_y(T, p, sm.V1, sm.ax1)); if (v > g_inf) g_inf = v; }
+    for (int p = c.tid; p < ny; p += c.nthr) { const double v = fabs(gather_y(T, p, sm.ax1)); if (v > g_inf) g_inf = v; }
     { double d0 = 0.0, d1 = 0.0; c.reduce3(g_inf, 1, d0, 0, d1, 0); }
     // pair-row bounds
-    for (int r = c.tid; r < np; r += c.nthr) {
-        double lo, hi;
-        pair_bounds(P, T, in, qc, r, lo, hi);
-        pb_hi[r] = hi; pb_lo[r] = lo;
-    }
+    for (int k = 0; k < D; k++)
+        for (int idx = c.tid; idx < npl; idx += c.nthr) {
+            double lo, hi;
+            pair_bounds(P, T, in, qc, k, pair_decode(T, idx), lo, hi);
+            pb_hi[k * npl + idx] = hi; pb_lo[k * npl + idx] = lo;
+        }
 
     int status = kStQpMaxIter;
     int it_total = 0;
@@ -479,8 +537,10 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             }
         }
         // ---- pair rows: slack / dual initialisation ----
-        for (int r = c.tid; r < np; r += c.nthr) {
-            const double act = pair_act(T, r, sm.y, sm.cst);
+        for (int k = 0; k < D; k++)
+        for (int idx = c.tid; idx < npl; idx += c.nthr) {
+            const int r = k * npl + idx;
+            const double act = pair_eval(T, pair_decode(T, idx), sm.x + k * npt);
             double s = pb_hi[r] - act; if (s < 1e-2) s = 1e-2;
             ps_hi[r] = s; pz_hi[r] = 1.0 / s * 1e-2;
             s = act - pb_lo[r]; if (s < 1e-2) s = 1e-2;
@@ -495,11 +555,11 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
         int it = 0;
         for (it = 0; it < max_it; it++) {
             // ============ pass 1: residuals, G'z, affine rhs, D = z/s ============
-            for (int k = 0; k < D; k++)
-                for (int pt = c.tid; pt < npt; pt += c.nthr) { sm.ax1[k * npt + pt] = grad_x(sm.x, k, pt); sm.ax2[k * npt + pt] = 0.0; }
             double rp_inf = 0.0, mu = 0.0;
-            for (int r = c.tid; r < np; r += c.nthr) {
-                const double act = pair_act(T, r, sm.y, sm.cst);
+            for (int k = 0; k < D; k++)
+            for (int idx = c.tid; idx < npl; idx += c.nthr) {
+                const int r = k * npl + idx;
+                const double act = pair_eval(T, pair_decode(T, idx), sm.x + k * npt);
                 p_act[r] = act;                 // row activity of this iterate, reused by the later passes
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double rph = act + sh - pb_hi[r], rpl = -act + sl + pb_lo[r];
@@ -531,17 +591,23 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                     S0 += dd * n0 * n0; S1 += dd * n1 * n0; S2 += dd * n1 * n1;
                     S3 += dd * n2 * n0; S4 += dd * n2 * n1; S5 += dd * n2 * n2;
                 }
-                sm.ax1[pt] += u10; sm.ax1[npt + pt] += u11;
-                sm.ax2[pt] += u20; sm.ax2[npt + pt] += u21;
-                if (D3) { sm.ax1[2 * npt + pt] += u12; sm.ax2[2 * npt + pt] += u22; }
+                // x-space accumulators of this point: objective gradient + pair rows + LSC rows
+                sm.ax1[pt] = grad_x(sm.x, 0, pt) + pair_transpose(T, sm.V1, pt) + u10;
+                sm.ax2[pt] = pair_transpose(T, sm.V2, pt) + u20;
+                sm.ax1[npt + pt] = grad_x(sm.x, 1, pt) + pair_transpose(T, sm.V1 + npl, pt) + u11;
+                sm.ax2[npt + pt] = pair_transpose(T, sm.V2 + npl, pt) + u21;
+                if (D3) {
+                    sm.ax1[2 * npt + pt] = grad_x(sm.x, 2, pt) + pair_transpose(T, sm.V1 + 2 * npl, pt) + u12;
+                    sm.ax2[2 * npt + pt] = pair_transpose(T, sm.V2 + 2 * npl, pt) + u22;
+                }
                 double* Sp = sm.S + pt * 6;
                 Sp[0] = S0; Sp[1] = S1; Sp[2] = S2; Sp[3] = S3; Sp[4] = S4; Sp[5] = S5;
             }
             c.sync();
             double rd_inf = 0.0;
             for (int p = c.tid; p < ny; p += c.nthr) {
-                const double r1 = gather_y(T, p, sm.V1, sm.ax1);
-                const double r2 = gather_y(T, p, sm.V2, sm.ax2);
+                const double r1 = gather_y(T, p, sm.ax1);
+                const double r2 = gather_y(T, p, sm.ax2);
                 sm.rd[p] = r1;
                 sm.dy[p] = -r1 - r2;
                 rd_inf = fmax(rd_inf, fabs(r1));
@@ -557,25 +623,22 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             for (int e = c.tid; e < T.ntri; e += c.nthr) sm.W[e] = 0.0;
             c.sync();
             for (int ei = c.tid; ei < T.nnzw; ei += c.nthr) {
-                const int e = T.nz_e[ei];
-                const int p = T.tri_p[e], q = e - p * (p + 1) / 2;
-                const int k = p / nyd, a = p - k * nyd, kk = q / nyd, b = q - kk * nyd;
-                double v = 0.0;
-                if (k == kk) {
-                    v = T.H1[a * nyd + b];
-                    if (a == b) {
-                        const int m = a / 3;
-                        if ((m == M - 1 || a - 3 * m == 2) && m >= M - qc.ts) v += wT2;
-                    }
-                    for (int t = T.wi_ptr[e]; t < T.wi_ptr[e + 1]; t++) v += T.wi_coef[t] * sm.DD[T.wi_row[t]];
-                }
-                const int el = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
+#ifdef __CUDA_ARCH__
+                const uint4 h = __ldg(T.nz_hdr + ei);
+#else
+                const uint4 h = T.nz_hdr[ei];
+#endif
+                double v = T.nz_h[ei];
+                const int e = h.x & 0xffff, k = (h.x >> 16) & 3, kk = (h.x >> 18) & 3;
+                if (((h.x >> 20) & 1) && (int)h.w >= M - qc.ts) v += wT2;
+                const int wo = h.y & 0xffffff, wn = h.y >> 24, po = h.z & 0xffffff, pn = h.z >> 24;
+                for (int t = 0; t < wn; t++) v += T.wi_coef[wo + t] * sm.DD[T.wi_row[wo + t]];
                 const int si = sym_idx(k, kk);
-                for (int t = T.wp_ptr[el]; t < T.wp_ptr[el + 1]; t++) v += T.wp_coef[t] * sm.S[T.wp_pt[t] * 6 + si];
+                for (int t = 0; t < pn; t++) v += T.wp_coef[po + t] * sm.S[T.wp_pt[po + t] * 6 + si];
                 sm.W[e] = v;
             }
             c.sync();
-            if (!ldl_factor(c, sm.W, sm.invp, sm.pan, ny)) { status = kStQpNumeric; break; }
+            if (!ldl_factor(c, sm.W, sm.invp, sm.pan, ny, T.tri_p)) { status = kStQpNumeric; break; }
 
             // ============ predictor ============
             ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
@@ -583,8 +646,10 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             map_x(c, T, sm.dy, nullptr, sm.dx);
             c.sync();
             double a_aff = 1.0;
-            for (int r = c.tid; r < np; r += c.nthr) {
-                const double act = p_act[r], gd = pair_act(T, r, sm.dy, nullptr);
+            for (int k = 0; k < D; k++)
+            for (int idx = c.tid; idx < npl; idx += c.nthr) {
+                const int r = k * npl + idx;
+                const double act = p_act[r], gd = pair_eval(T, pair_decode(T, idx), sm.dx + k * npt);
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
                 const double dzh = -zh - (zh / sh) * dsh, dzl = -zl - (zl / sl) * dsl;   // (-s z - z ds)/s
@@ -645,19 +710,22 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                     const double cv = l_ds[r];
                     u20 -= l_n0[r] * cv; u21 -= l_n1[r] * cv; u22 -= l_n2[r] * cv;
                 }
-                sm.ax2[pt] = u20; sm.ax2[npt + pt] = u21;
-                if (D3) sm.ax2[2 * npt + pt] = u22;
+                sm.ax2[pt] = pair_transpose(T, sm.V2, pt) + u20;
+                sm.ax2[npt + pt] = pair_transpose(T, sm.V2 + npl, pt) + u21;
+                if (D3) sm.ax2[2 * npt + pt] = pair_transpose(T, sm.V2 + 2 * npl, pt) + u22;
             }
             c.sync();
-            for (int p = c.tid; p < ny; p += c.nthr) sm.dy[p] = -sm.rd[p] - gather_y(T, p, sm.V2, sm.ax2);
+            for (int p = c.tid; p < ny; p += c.nthr) sm.dy[p] = -sm.rd[p] - gather_y(T, p, sm.ax2);
             c.sync();
             ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
             c.sync();
             map_x(c, T, sm.dy, nullptr, sm.dx);
             c.sync();
             double a_st = 1.0;
-            for (int r = c.tid; r < np; r += c.nthr) {
-                const double act = p_act[r], gd = pair_act(T, r, sm.dy, nullptr);
+            for (int k = 0; k < D; k++)
+            for (int idx = c.tid; idx < npl; idx += c.nthr) {
+                const int r = k * npl + idx;
+                const double act = p_act[r], gd = pair_eval(T, pair_decode(T, idx), sm.dx + k * npt);
                 const double sh = ps_hi[r], zh = pz_hi[r], sl = ps_lo[r], zl = pz_lo[r];
                 const double rch = sh * zh + pc_hi[r] - sig_mu, rcl = sl * zl + pc_lo[r] - sig_mu;
                 const double dsh = -(act + sh - pb_hi[r]) - gd, dsl = -(-act + sl + pb_lo[r]) + gd;
@@ -732,10 +800,12 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 obj += wT * xs[n] * xs[n] - wT2 * g * xs[n] + wT * g * g;
             }
         }
-    for (int r = c.tid; r < np; r += c.nthr) {
-        const double act = pair_act(T, r, sm.y, sm.cst);
-        viol = fmax(viol, fmax(act - pb_hi[r], pb_lo[r] - act));
-    }
+    for (int k = 0; k < D; k++)
+        for (int idx = c.tid; idx < npl; idx += c.nthr) {
+            const int r = k * npl + idx;
+            const double act = pair_eval(T, pair_decode(T, idx), sm.x + k * npt);
+            viol = fmax(viol, fmax(act - pb_hi[r], pb_lo[r] - act));
+        }
     { double d1 = 0.0; c.reduce3(obj, 0, viol, 1, d1, 0); }
     if (c.tid == 0) {
         *out.cost = obj; *out.viol = viol; *out.iters = it_total; *out.status |= status;

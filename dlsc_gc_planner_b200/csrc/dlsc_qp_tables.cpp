@@ -121,19 +121,22 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
             rows.push_back({0, m * kP + i, lin({{m * kP + i, 1.0}})});
         }
     const double scv = std::pow(dt, -1) * n, sca = std::pow(dt, -2) * n * (n - 1);
-    for (int m = 0; m < M; m++) {
+    T.scv = scv; T.sca = sca;
+    // family-major order inside an axis so that row indices are closed-form (dlsc_qp.cuh: row_* helpers):
+    //   box  idx = pt - 3 | vel idx = bv + 5m + i - 2 | acc idx = ba + 4m + i - 1 | comm idx = bc + mi*M - mi(mi-1)/2 + m - mi
+    for (int m = 0; m < M; m++)
         for (int i = 0; i < n; i++) {                                       // velocity
             if (m == 0 && (i == 0 || i == 1)) continue;
-            rows.push_back({1, -1, lin({{m * kP + i + 1, scv}, {m * kP + i, -scv}})});
+            rows.push_back({1, m * kP + i, lin({{m * kP + i + 1, scv}, {m * kP + i, -scv}})});
         }
+    for (int m = 0; m < M; m++)
         for (int i = 0; i < n - 1; i++) {                                   // acceleration
             if (m == 0 && i == 0) continue;
-            rows.push_back({2, -1, lin({{m * kP + i + 2, sca}, {m * kP + i + 1, -2 * sca}, {m * kP + i, sca}})});
+            rows.push_back({2, m * kP + i, lin({{m * kP + i + 2, sca}, {m * kP + i + 1, -2 * sca}, {m * kP + i, sca}})});
         }
-    }
     if (use_comm)
         for (int mi = 0; mi < M; mi++)
-            for (int m = mi; m < M; m++) rows.push_back({3, -1, lin({{m * kP + n, 1.0}, {mi * kP + 0, -1.0}})});
+            for (int m = mi; m < M; m++) rows.push_back({3, (m * kP + n) | ((mi * kP) << 8), lin({{m * kP + n, 1.0}, {mi * kP + 0, -1.0}})});
 
     const int npl = (int)rows.size();
     T.np = npl * D;
@@ -143,7 +146,9 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
     for (int k = 0; k < D; k++)
         for (int r = 0; r < npl; r++) {
             const int g = k * npl + r;
-            T.pr_fam[g] = (uint8_t)rows[r].fam; T.pr_axis[g] = (uint8_t)k; T.pr_pt[g] = (int16_t)rows[r].pt;
+            T.pr_fam[g] = (uint8_t)rows[r].fam; T.pr_axis[g] = (uint8_t)k; T.pr_pt[g] = (int16_t)(rows[r].pt & 0xff);
+            T.pr_desc.push_back((uint32_t)rows[r].fam | ((uint32_t)k << 2) | ((uint32_t)(rows[r].pt & 0xff) << 4) |
+                                ((uint32_t)((rows[r].pt >> 8) & 0xff) << 12));
             int nnz = 0;
             for (auto& t : rows[r].e.t) {
                 if (t.coef == 0.0) continue;
@@ -198,8 +203,9 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
     flatten(yp, T.yp_ptr, T.yp_pt, T.yp_coef);
     flatten(wp, T.wp_ptr, T.wp_pt, T.wp_coef);
 
-    // structurally non-zero entries of W = H + G'DG (everything else is only fill-in of the factorisation)
-    T.nz_e.clear();
+    // structurally non-zero entries of W = H + G'DG (everything else is only fill-in of the factorisation),
+    // one 16-byte header + the H value per entry: {e | k<<16 | kk<<18 | y5flag<<20, wi_off | wi_cnt<<24, wp_off | wp_cnt<<24, seg}
+    T.nz_e.clear(); T.nz_hdr.clear(); T.nz_h.clear();
     for (int p = 0; p < T.ny; p++)
         for (int q = 0; q <= p; q++) {
             const int e = p * (p + 1) / 2 + q;
@@ -207,7 +213,15 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
             const int el = (a >= b) ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a;
             bool nz = !wp[el].empty();
             if (k == kk) nz = nz || a == b || T.H1[(size_t)a * nyd + b] != 0.0 || !wi[e].empty();
-            if (nz) T.nz_e.push_back((uint16_t)e);
+            if (nz) {
+                T.nz_e.push_back((uint16_t)e);
+                const int is_y5 = (k == kk && a == b && (a / 3 == M - 1 || a % 3 == 2)) ? 1 : 0;
+                T.nz_hdr.push_back((uint32_t)e | ((uint32_t)k << 16) | ((uint32_t)kk << 18) | ((uint32_t)is_y5 << 20));
+                T.nz_hdr.push_back((k == kk) ? ((uint32_t)T.wi_ptr[e] | ((uint32_t)(T.wi_ptr[e + 1] - T.wi_ptr[e]) << 24)) : 0u);
+                T.nz_hdr.push_back((uint32_t)T.wp_ptr[el] | ((uint32_t)(T.wp_ptr[el + 1] - T.wp_ptr[el]) << 24));
+                T.nz_hdr.push_back((uint32_t)(a / 3));
+                T.nz_h.push_back((k == kk) ? T.H1[(size_t)a * nyd + b] : 0.0);
+            }
         }
     T.nnzw = (int)T.nz_e.size();
 }

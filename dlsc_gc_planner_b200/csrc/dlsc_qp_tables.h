@@ -20,6 +20,9 @@
 #pragma once
 #include <stdint.h>
 #include <vector>
+#ifndef __CUDACC__
+struct uint4;
+#endif
 
 namespace dlsc {
 
@@ -39,8 +42,12 @@ struct QpTabHost {
     std::vector<int> wi_ptr;  std::vector<int16_t> wi_row;  std::vector<double> wi_coef;   // pair rows per W entry (global lower tri)
     std::vector<int> wp_ptr;  std::vector<int16_t> wp_pt;   std::vector<double> wp_coef;   // points per local (a>=b)
     std::vector<uint8_t> tri_p;                   // [ntri] row index p of packed lower-triangle entry e
+    std::vector<uint32_t> pr_desc;                // [np] fam | axis<<2 | pa<<4 | pb<<12 (points of the row's stencil)
+    std::vector<uint32_t> nz_hdr;                 // [nnzw][4] header of a structurally non-zero entry of W
+    std::vector<double> nz_h;                     // [nnzw] its H value
     std::vector<uint16_t> nz_e;                   // packed indices e of the structurally non-zero entries of W
     int nnzw = 0;
+    double scv = 0, sca = 0;                      // velocity / acceleration row scales n/dt, n(n-1)/dt^2
     std::vector<double> H1;                       // [nyd][nyd]  2*w_u*sum_m T_m' Q T_m
     std::vector<double> Q2;                       // [6][6]      2*w_u*Q
     std::vector<double> Qb;                       // [6][6]      Q_base
@@ -67,7 +74,12 @@ struct QpTab {
     const int *wp_ptr; const int16_t* wp_pt; const double* wp_coef;
     const uint8_t* tri_p;
     const uint16_t* nz_e;
+    const uint32_t* pr_desc;
+    const uint4* nz_hdr;
+    const double* nz_h;
     int nnzw;
+    int row_npl, row_bv, row_ba, row_bc;   // rows per axis, first velocity / acceleration / comm row inside an axis
+    double scv, sca;                       // n/dt, n(n-1)/dt^2
     const double *H1, *Q2;
 };
 

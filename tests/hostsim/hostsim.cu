@@ -90,6 +90,12 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     T.wi_ptr = h.wi_ptr.data(); T.wi_row = h.wi_row.data(); T.wi_coef = h.wi_coef.data();
     T.wp_ptr = h.wp_ptr.data(); T.wp_pt = h.wp_pt.data(); T.wp_coef = h.wp_coef.data();
     T.H1 = h.H1.data(); T.Q2 = h.Q2.data(); T.tri_p = h.tri_p.data(); T.nz_e = h.nz_e.data(); T.nnzw = h.nnzw;
+    T.pr_desc = h.pr_desc.data(); T.nz_hdr = reinterpret_cast<const uint4*>(h.nz_hdr.data()); T.nz_h = h.nz_h.data();
+    {
+        const int M = h.M, MP = M * kP;
+        T.row_npl = h.np / h.D; T.row_bv = MP - 3; T.row_ba = T.row_bv + (M * 5 - 2); T.row_bc = T.row_ba + (M * 4 - 1);
+        T.scv = h.scv; T.sca = h.sca;
+    }
     c->scratch.assign(qp_scratch_doubles(T, P.K), 0.0);
     c->smem.assign(qp_smem_bytes(T, P.K) / 8 + 8, 0.0);
     memset(&c->edt, 0, sizeof(c->edt));
