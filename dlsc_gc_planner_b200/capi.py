@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdlsc_b200.so")
 
-OK, QP_MAXITER, QP_NUMERIC, SFC_INIT_FAILED, GOAL_INFEASIBLE, SFC_REUSED, NBR_OVERFLOW = 0, 1, 2, 4, 8, 16, 32
+OK, QP_MAXITER, QP_NUMERIC, SFC_INIT_FAILED, GOAL_INFEASIBLE, SFC_REUSED, NBR_OVERFLOW, QP_IPM_USED = 0, 1, 2, 4, 8, 16, 32, 64
 STAGE_PREDICT, STAGE_NBR, STAGE_LSC, STAGE_SFC, STAGE_GOAL, STAGE_QP, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
 STAGE_NAMES = ("predict", "nbr", "lsc", "sfc", "goal", "qp")
 FAIL_MASK = QP_MAXITER | QP_NUMERIC | SFC_INIT_FAILED | GOAL_INFEASIBLE
@@ -31,7 +31,7 @@ class DlscParams(C.Structure):
         ("world_res", C.c_double), ("grid_res", C.c_double), ("z_2d", C.c_double),
         ("comm_range", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
         ("reset_threshold", C.c_double),
-        ("qp_max_iter", C.c_int32), ("reserved", C.c_int32), ("qp_screen_slack", C.c_double),
+        ("qp_max_iter", C.c_int32), ("qp_solver", C.c_int32), ("qp_screen_slack", C.c_double),
     ]
 
 
@@ -98,7 +98,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0, qp_screen_slack=0.0):
+def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0, qp_screen_slack=0.0, qp_solver=0):
     """cfg: missions.PlannerConfig."""
     p = DlscParams()
     p.M, p.n, p.phi, p.dim, p.use_sfc, p.max_nbr = cfg.M, cfg.n, cfg.phi, cfg.dim, int(cfg.use_sfc), int(max_nbr)
@@ -111,6 +111,7 @@ def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0, qp_screen_sla
     p.reset_threshold = cfg.reset_threshold
     p.qp_max_iter = qp_max_iter
     p.qp_screen_slack = qp_screen_slack
+    p.qp_solver = qp_solver
     return p
 
 
@@ -122,7 +123,7 @@ class SwarmPlanner:
     """One context = the agent block [begin, begin+n_local) of a swarm of n_agents on one GPU."""
 
     def __init__(self, cfg, mission, max_nbr=None, begin=0, n_local=None, device=0, lib=None, qp_max_iter=0,
-                 qp_screen_slack=0.0):
+                 qp_screen_slack=0.0, qp_solver=0):
         self.lib = lib if lib is not None else load_library()
         self.cfg = cfg
         self.N = int(mission.n_agents)
@@ -130,7 +131,7 @@ class SwarmPlanner:
         self.NL = int(n_local if n_local is not None else self.N - begin)
         self.M, self.P, self.D = cfg.M, cfg.n + 1, cfg.dim
         self.K = int(max_nbr if max_nbr is not None else max(self.N - 1, 1))
-        self.params = make_params(cfg, mission.world_min, mission.world_max, self.K, qp_max_iter, qp_screen_slack)
+        self.params = make_params(cfg, mission.world_min, mission.world_max, self.K, qp_max_iter, qp_screen_slack, qp_solver)
         self.ctx = C.c_void_p()
         self._ck(self.lib.dlsc_create(C.byref(self.params), self.N, self.begin, self.NL, int(device), C.byref(self.ctx)))
         sl = slice(self.begin, self.begin + self.NL)

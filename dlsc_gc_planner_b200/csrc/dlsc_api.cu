@@ -95,7 +95,7 @@ static int upload_tables(dlsc_ctx* c) {
     const size_t i_wi_ptr = SEC(wi_ptr), i_wi_row = SEC(wi_row), i_wi_coef = SEC(wi_coef);
     const size_t i_wp_ptr = SEC(wp_ptr), i_wp_pt = SEC(wp_pt), i_wp_coef = SEC(wp_coef);
     const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2), i_tri = SEC(tri_p), i_nz = SEC(nz_e);
-    const size_t i_desc = SEC(pr_desc), i_hdr = SEC(nz_hdr), i_nzh = SEC(nz_h);
+    const size_t i_desc = SEC(pr_desc), i_hdr = SEC(nz_hdr), i_nzh = SEC(nz_h), i_hinv = SEC(Hinv);
 #undef SEC
     std::vector<char> blob(off ? off : 256, 0);
     for (auto& s : secs) memcpy(blob.data() + s.off, s.src, s.bytes);
@@ -117,7 +117,7 @@ static int upload_tables(dlsc_ctx* c) {
     T.wp_ptr = PTR(int, i_wp_ptr); T.wp_pt = PTR(int16_t, i_wp_pt); T.wp_coef = PTR(double, i_wp_coef);
     T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2); T.tri_p = PTR(uint8_t, i_tri);
     T.nz_e = PTR(uint16_t, i_nz); T.nnzw = h.nnzw;
-    T.pr_desc = PTR(uint32_t, i_desc); T.nz_hdr = PTR(uint4, i_hdr); T.nz_h = PTR(double, i_nzh);
+    T.pr_desc = PTR(uint32_t, i_desc); T.nz_hdr = PTR(uint4, i_hdr); T.nz_h = PTR(double, i_nzh); T.Hinv = PTR(double, i_hinv);
     {
         const int M = h.M, MP = M * kP;
         T.row_npl = h.np / h.D; T.row_bv = MP - 3; T.row_ba = T.row_bv + (M * 5 - 2); T.row_bc = T.row_ba + (M * 4 - 1);
@@ -154,6 +154,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     P.rec = c->rl.size;
     P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
     P.qp_screen = hp->qp_screen_slack == 0.0 ? 0.5 : hp->qp_screen_slack;
+    P.qp_solver = hp->qp_solver;
     P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
     P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
     P.reset_threshold = hp->reset_threshold;
@@ -198,7 +199,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.qp_next, 1);
     if (rc) { dlsc_destroy(c); return -1; }
 
-    build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->comm_range > 0, c->th);
+    build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->w_terminal, hp->comm_range > 0, c->th);
     if (upload_tables(c)) { dlsc_destroy(c); return -1; }
     c->qpl = qp_launch_config(P, c->T, device);
     if (c->qpl.smem > 227 * 1024) { dlsc_destroy(c); return fail("dlsc_create: QP shared memory exceeds 227 KB"); }

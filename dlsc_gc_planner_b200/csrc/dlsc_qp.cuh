@@ -87,9 +87,36 @@ struct QpSmem {
     int* off;                  // [npt + 2] segment offsets of the LSC row list (+ scratch word)
     uint8_t* act;              // [M][Kcap]
 };
+// dual active-set (Goldfarb-Idnani, Schur-complement form) working storage; aliases the W region
+constexpr int kGiQ = 32;                               // max simultaneously active rows
+constexpr int kGiTri = kGiQ * (kGiQ + 1) / 2;
+struct GiSmem {
+    double *Hinv;                                      // [nyd][nyd] of this agent's terminal-segment count
+    double *Ls, *Sm;                                   // packed lower: Cholesky of S = A H^-1 A', and S itself
+    double *yc;                                        // [kGiQ+1][9] y-space coefficients of the active rows (+ candidate)
+    double *bq, *u, *r, *v, *l;                        // [kGiQ+1]
+    double *ty;                                        // scalars: [0] step, [1] flag
+    int16_t* yi;                                       // [kGiQ+1][9] y indices (-1 = unused)
+    int* id;                                           // [kGiQ+1] row ids
+};
+DLSC_HD size_t gi_doubles(const QpTab& T) {
+    return (size_t)T.nyd * T.nyd + 2 * kGiTri + 9 * (kGiQ + 1) + 5 * (kGiQ + 1) + 8 + (9 * (kGiQ + 1) + 3) / 4 + (kGiQ + 2) / 2 + 2;
+}
+DLSC_HD void gi_carve(const QpTab& T, double* base, GiSmem& g) {
+    double* p = base;
+    g.Hinv = p; p += T.nyd * T.nyd;
+    g.Ls = p; p += kGiTri; g.Sm = p; p += kGiTri;
+    g.yc = p; p += 9 * (kGiQ + 1);
+    g.bq = p; p += kGiQ + 1; g.u = p; p += kGiQ + 1; g.r = p; p += kGiQ + 1; g.v = p; p += kGiQ + 1; g.l = p; p += kGiQ + 1;
+    g.ty = p; p += 8;
+    g.yi = reinterpret_cast<int16_t*>(p); p += (9 * (kGiQ + 1) + 3) / 4;
+    g.id = reinterpret_cast<int*>(p);
+}
+DLSC_HD size_t qp_w_doubles(const QpTab& T) { return (size_t)T.ntri > gi_doubles(T) ? (size_t)T.ntri : gi_doubles(T); }
+
 DLSC_HD size_t qp_smem_doubles(const QpTab& T) {
     const size_t v12 = (2 * (size_t)T.np > 8 * (size_t)T.ny) ? 2 * (size_t)T.np : 8 * (size_t)T.ny;   // V1|V2, aliased by pan
-    return (size_t)T.ntri + 4 * (size_t)T.ny + 16 + 4 * (size_t)T.nx + v12 + (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
+    return qp_w_doubles(T) + 4 * (size_t)T.ny + 16 + 4 * (size_t)T.nx + v12 + (size_t)T.np + 6 * (size_t)T.npt + 16 + 96 +
            ((size_t)T.npt + 4) / 2 + 1;
 }
 DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
@@ -97,7 +124,7 @@ DLSC_HD size_t qp_smem_bytes(const QpTab& T, int Kcap) {
 }
 DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     double* p = base;
-    s.W = p; p += T.ntri;
+    s.W = p; p += qp_w_doubles(T);
     s.invp = p; p += T.ny + 16; s.y = p; p += T.ny; s.dy = p; p += T.ny; s.rd = p; p += T.ny;
     s.x = p; p += T.nx; s.dx = p; p += T.nx; s.ax1 = p; p += T.nx; s.ax2 = p; p += T.nx;
     {   // V1 and V2 are dead while W is being factorised: the panel buffers of ldl_factor alias them
@@ -406,6 +433,237 @@ DLSC_HD LscRowData lsc_row_data(const DevParams& P, const QpIn& in, int pt, int 
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dual active-set solver (Goldfarb & Idnani 1983, range-space / Schur-complement form).
+//   min 1/2 y'Hy + g'y  s.t.  a_i'y <= b_i.   H = blockdiag_k(H1 + terminal) is constant per terminal-segment
+//   count, so H^-1 (one nyd x nyd block) is tabulated; starting from y0 = -H^-1 g (all rows inactive) the
+//   most violated row p is driven to its bound along  z = H^-1 (a_p - A' r),  r = S^-1 A H^-1 a_p,
+//   S = A H^-1 A' over the active rows A (q <= 32; Cholesky of S updated by one appended row per added
+//   constraint, refactored on the rare drop).  The replan QPs have ~1 active row at the optimum (median 0),
+//   so this needs a handful of O(n*nyd) steps instead of interior-point iterations with an n^3 factorisation.
+// Returns 0 = optimal, kStQpMaxIter = infeasible, -1 = give up (caller falls back to the interior point).
+// y in sm.y, x in sm.x on return.  Row cache: l_n0/l_n1/l_n2/l_b [npt*Kc] (b = +inf for unused rows).
+// ------------------------------------------------------------------------------------------------
+DLSC_HD int qp_dual_active_set(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
+                               const QpSmem& sm, const double* __restrict__ l_n0, const double* __restrict__ l_n1,
+                               const double* __restrict__ l_n2, const double* __restrict__ l_b,
+                               const double* __restrict__ pb_hi, const double* __restrict__ pb_lo, int* iters_out,
+                               double* viol_out) {
+    const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, np = T.np, npl = T.row_npl, Kc = P.K, K = in.K;
+    const bool D3 = (D == 3);
+    GiSmem g;
+    gi_carve(T, sm.W, g);
+    const double tol = 1e-9;
+    // H^-1 block of this agent; g = T' grad f(x(0)) was left in sm.rd by the caller
+    {
+        const double* src = T.Hinv + (size_t)(qc.ts - 1) * nyd * nyd;
+        for (int e = c.tid; e < nyd * nyd; e += c.nthr) g.Hinv[e] = src[e];
+    }
+    c.sync();
+    for (int p = c.tid; p < ny; p += c.nthr) {                 // y0 = -H^-1 g
+        const int k = p / nyd, a = p - k * nyd;
+        const double* hr = g.Hinv + a * nyd;
+        const double* gk = sm.rd + k * nyd;
+        double v = 0.0;
+        for (int b = 0; b < nyd; b++) v += hr[b] * gk[b];
+        sm.y[p] = -v;
+    }
+    int q = 0, iters = 0, status = -1;
+    double viol_p = 0.0, u_p = 0.0;
+    bool same_p = false;
+    c.sync();
+    for (int guard = 0; guard < 400; guard++) {
+        if (!same_p) {
+            // ---- most violated row ----
+            map_x(c, T, sm.y, sm.cst, sm.x);
+            c.sync();
+            double best = -1e300, best_id = 1e300;
+            for (int k = 0; k < D; k++)
+                for (int idx = c.tid; idx < npl; idx += c.nthr) {
+                    const int r = k * npl + idx;
+                    const double act = pair_eval(T, pair_decode(T, idx), sm.x + k * npt);
+                    const double vh = act - pb_hi[r], vl = pb_lo[r] - act;
+                    if (vh > best) { best = vh; best_id = 2.0 * r; }
+                    if (vl > best) { best = vl; best_id = 2.0 * r + 1.0; }
+                }
+            for (int pt = 3; pt < npt; pt++) {
+                const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
+                for (int cc = c.tid; cc < K; cc += c.nthr) {
+                    const int o = pt * Kc + cc;
+                    const double v = -(l_n0[o] * x0 + l_n1[o] * x1 + l_n2[o] * x2) - l_b[o];
+                    if (v > best) { best = v; best_id = 2.0 * np + o; }
+                }
+            }
+            double vmax = best, d0 = 0.0, d1 = 0.0;
+            c.reduce3(vmax, 1, d0, 0, d1, 0);
+            double idsel = (best == vmax) ? best_id : 1e300;
+            d0 = 0.0; d1 = 0.0;
+            c.reduce3(idsel, 2, d0, 0, d1, 0);
+            *viol_out = vmax;
+            if (!(vmax > tol)) { status = 0; break; }
+            // ---- candidate row p: x-space form -> y-space form (thread 0) ----
+            if (c.tid == 0) {
+                const int id = (int)idsel;
+                int xi[3] = {0, 0, 0}; double xc[3] = {0, 0, 0}; int nxe = 0; double bp;
+                if (id < 2 * np) {
+                    const int r = id >> 1, side = id & 1, k = r / npl, idx = r - k * npl;
+                    const PairRow pr = pair_decode(T, idx);
+                    const double sg = side ? -1.0 : 1.0;
+                    const int base = k * npt;
+                    if (pr.fam == 0) { xi[0] = base + pr.pa; xc[0] = sg; nxe = 1; }
+                    else if (pr.fam == 1) { xi[0] = base + pr.pa + 1; xc[0] = sg * T.scv; xi[1] = base + pr.pa; xc[1] = -sg * T.scv; nxe = 2; }
+                    else if (pr.fam == 2) {
+                        xi[0] = base + pr.pa + 2; xc[0] = sg * T.sca; xi[1] = base + pr.pa + 1; xc[1] = -2.0 * sg * T.sca;
+                        xi[2] = base + pr.pa; xc[2] = sg * T.sca; nxe = 3;
+                    } else { xi[0] = base + pr.pa; xc[0] = sg; xi[1] = base + pr.pb; xc[1] = -sg; nxe = 2; }
+                    bp = side ? -pb_lo[r] : pb_hi[r];
+                } else {
+                    const int o = id - 2 * np, pt = o / Kc;
+                    xi[0] = pt; xc[0] = -l_n0[o]; xi[1] = npt + pt; xc[1] = -l_n1[o]; nxe = 2;
+                    if (D3) { xi[2] = 2 * npt + pt; xc[2] = -l_n2[o]; nxe = 3; }
+                    bp = l_b[o];
+                }
+                double* yc = g.yc + 9 * kGiQ; int16_t* yi = g.yi + 9 * kGiQ;
+                int nt = 0;
+                for (int e = 0; e < nxe; e++) {
+                    const int k = xi[e] / npt, pt = xi[e] - k * npt, m = pt / kP, i = pt - m * kP, yb = k * nyd;
+                    const double cf = xc[e];
+                    if (i >= 3) { yi[nt] = (int16_t)(yb + ((m == M - 1) ? 3 * (M - 1) : 3 * m + i - 3)); yc[nt++] = cf; }
+                    else if (m > 0) {
+                        const int q3 = yb + 3 * (m - 1);
+                        if (i == 0) { yi[nt] = (int16_t)(q3 + 2); yc[nt++] = cf; }
+                        else if (i == 1) { yi[nt] = (int16_t)(q3 + 2); yc[nt++] = 2.0 * cf; yi[nt] = (int16_t)(q3 + 1); yc[nt++] = -cf; }
+                        else { yi[nt] = (int16_t)(q3 + 2); yc[nt++] = 4.0 * cf; yi[nt] = (int16_t)(q3 + 1); yc[nt++] = -4.0 * cf;
+                               yi[nt] = (int16_t)q3; yc[nt++] = cf; }
+                    }
+                }
+                for (; nt < 9; nt++) { yi[nt] = -1; yc[nt] = 0.0; }
+                g.bq[kGiQ] = bp; g.id[kGiQ] = id;
+            }
+            viol_p = vmax; u_p = 0.0;
+            c.sync();
+            // ---- w = H^-1 a_p (into sm.dy) ----
+            for (int p = c.tid; p < ny; p += c.nthr) {
+                const int k = p / nyd, a = p - k * nyd;
+                const double* hr = g.Hinv + a * nyd;
+                const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+                double v = 0.0;
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    const int j = yi[t];
+                    if (j >= 0 && j / nyd == k) v += yc[t] * hr[j - k * nyd];
+                }
+                sm.dy[p] = v;
+            }
+            c.sync();
+        }
+        iters++;
+        // ---- small dense step (thread 0): r, step lengths, active-set update; t_y = A' r into sm.ax1[0..ny) ----
+        if (c.tid == 0) {
+            const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+            double apw = 0.0;
+            for (int t = 0; t < 9; t++) if (yi[t] >= 0) apw += yc[t] * sm.dy[yi[t]];
+            double ll = 0.0;
+            for (int j = 0; j < q; j++) {
+                double vj = 0.0;
+                for (int t = 0; t < 9; t++) { const int jj = g.yi[9 * j + t]; if (jj >= 0) vj += g.yc[9 * j + t] * sm.dy[jj]; }
+                g.v[j] = vj;
+                double a = vj;
+                for (int k = 0; k < j; k++) a -= g.Ls[j * (j + 1) / 2 + k] * g.l[k];
+                a /= g.Ls[j * (j + 1) / 2 + j];
+                g.l[j] = a; ll += a * a;
+            }
+            for (int j = q - 1; j >= 0; j--) {
+                double a = g.l[j];
+                for (int k = j + 1; k < q; k++) a -= g.Ls[k * (k + 1) / 2 + j] * g.r[k];
+                g.r[j] = a / g.Ls[j * (j + 1) / 2 + j];
+            }
+            const double zn = apw - ll;
+            double t1 = 1e300; int kdrop = -1;
+            for (int j = 0; j < q; j++)
+                if (g.r[j] > 0) { const double tt = g.u[j] / g.r[j]; if (tt < t1) { t1 = tt; kdrop = j; } }
+            const bool dependent = !(zn > 1e-12 * (apw > 1e-300 ? apw : 1e-300));
+            const double t2 = dependent ? 1e300 : viol_p / zn;
+            const double t = t1 < t2 ? t1 : t2;
+            double flag;             // 0: full step, new scan | 1: partial, same p | 2: infeasible | 3: give up
+            if (!(t < 1e299)) flag = 2.0;
+            else {
+                for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
+                u_p += t;
+                for (int e = 0; e < ny; e++) sm.ax1[e] = 0.0;
+                for (int j = 0; j < q; j++)
+                    for (int tt = 0; tt < 9; tt++) { const int jj = g.yi[9 * j + tt]; if (jj >= 0) sm.ax1[jj] += g.r[j] * g.yc[9 * j + tt]; }
+                if (t2 <= t1) {
+                    // full step: p becomes active
+                    if (q == kGiQ) flag = 3.0;
+                    else {
+                        for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
+                        g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
+                        for (int tt = 0; tt < 9; tt++) { g.yc[9 * q + tt] = yc[tt]; g.yi[9 * q + tt] = yi[tt]; }
+                        g.bq[q] = g.bq[kGiQ]; g.id[q] = g.id[kGiQ]; g.u[q] = u_p;
+                        flag = 0.0;
+                    }
+                } else {
+                    // partial step: row kdrop leaves the active set; S loses a row/column, refactor
+                    for (int j = kdrop; j < q - 1; j++) {
+                        for (int tt = 0; tt < 9; tt++) { g.yc[9 * j + tt] = g.yc[9 * (j + 1) + tt]; g.yi[9 * j + tt] = g.yi[9 * (j + 1) + tt]; }
+                        g.bq[j] = g.bq[j + 1]; g.id[j] = g.id[j + 1]; g.u[j] = g.u[j + 1];
+                    }
+                    for (int i2 = 0, ii = 0; i2 < q; i2++) {
+                        if (i2 == kdrop) continue;
+                        for (int k2 = 0, kk = 0; k2 <= i2; k2++) {
+                            if (k2 == kdrop) continue;
+                            g.Ls[ii * (ii + 1) / 2 + kk] = g.Sm[i2 * (i2 + 1) / 2 + k2];     // Ls as temp for the shrunk S
+                            kk++;
+                        }
+                        ii++;
+                    }
+                    for (int e = 0; e < (q - 1) * q / 2; e++) g.Sm[e] = g.Ls[e];
+                    bool okf = true;
+                    for (int j = 0; j < q - 1 && okf; j++) {
+                        double dj = g.Sm[j * (j + 1) / 2 + j];
+                        for (int k = 0; k < j; k++) dj -= g.Ls[j * (j + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
+                        if (!(dj > 0)) { okf = false; break; }
+                        dj = sqrt(dj);
+                        g.Ls[j * (j + 1) / 2 + j] = dj;
+                        for (int i2 = j + 1; i2 < q - 1; i2++) {
+                            double a = g.Sm[i2 * (i2 + 1) / 2 + j];
+                            for (int k = 0; k < j; k++) a -= g.Ls[i2 * (i2 + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
+                            g.Ls[i2 * (i2 + 1) / 2 + j] = a / dj;
+                        }
+                    }
+                    flag = okf ? 1.0 : 3.0;
+                }
+            }
+            g.ty[0] = dependent ? 0.0 : t;      // primal step length
+            g.ty[1] = flag;
+            g.ty[2] = zn;
+        }
+        c.sync();
+        const double tp = g.ty[0], flag = g.ty[1];
+        if (flag == 2.0) { status = kStQpMaxIter; break; }
+        if (flag == 3.0) { status = -1; break; }
+        // ---- y -= t (w - H^-1 A' r) ----
+        if (tp != 0.0)
+            for (int p = c.tid; p < ny; p += c.nthr) {
+                const int k = p / nyd, a = p - k * nyd;
+                const double* hr = g.Hinv + a * nyd;
+                const double* tk = sm.ax1 + k * nyd;
+                double hz = 0.0;
+                if (q > 0 || flag == 1.0)
+                    for (int b = 0; b < nyd; b++) hz += hr[b] * tk[b];
+                sm.y[p] -= tp * (sm.dy[p] - hz);
+            }
+        if (flag == 0.0) { q++; same_p = false; }
+        else { q--; same_p = true; viol_p -= tp * g.ty[2]; }
+        c.sync();
+    }
+    map_x(c, T, sm.y, sm.cst, sm.x);
+    c.sync();
+    *iters_out = iters;
+    return status;
+}
+
 // one agent
 DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
                       const QpSmem& sm, double* scratch) {
@@ -470,7 +728,11 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
         for (int pt = c.tid; pt < npt; pt += c.nthr) sm.ax1[k * npt + pt] = grad_x(sm.x, k, pt);
     c.sync();
     double g_inf = 0.0;
-    for (int p = c.tid; p < ny; p += c.nthr) { const double v = fabs(gather_y(T, p, sm.ax1)); if (v > g_inf) g_inf = v; }
+    for (int p = c.tid; p < ny; p += c.nthr) {
+        const double gp = gather_y(T, p, sm.ax1);
+        sm.rd[p] = gp;                              // linear term g of 1/2 y'Hy + g'y
+        if (fabs(gp) > g_inf) g_inf = fabs(gp);
+    }
     { double d0 = 0.0, d1 = 0.0; c.reduce3(g_inf, 1, d0, 0, d1, 0); }
     // pair-row bounds
     for (int k = 0; k < D; k++)
@@ -486,7 +748,31 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     long long rows_total = 0;
     double tau = P.qp_screen;
     const int max_it = P.qp_max_iter;
-    for (int attempt = 0; attempt < 4; attempt++) {
+
+    // ---- primary solver: dual active set on all rows (LSC rows cached as (n, b) per (point, neighbour)) ----
+    bool solved = false, solved_by_gi = false;
+    if (P.qp_solver != 1) {
+        for (int pt = 3; pt < npt; pt++) {
+            const int m = pt / kP;
+            for (int cc = c.tid; cc < K; cc += c.nthr) {
+                const int o = pt * Kc + cc;
+                if (sm.act[m * Kc + cc]) {
+                    const LscRowData r = lsc_row_data(P, in, pt, cc);
+                    l_n0[o] = r.n0; l_n1[o] = r.n1; l_n2[o] = r.n2; l_b[o] = r.b;
+                } else { l_n0[o] = 0.0; l_n1[o] = 0.0; l_n2[o] = 0.0; l_b[o] = 1e300; }
+            }
+        }
+        c.sync();
+        int gi_it = 0;
+        double gi_viol = 0.0;
+        const int st = qp_dual_active_set(c, P, T, in, qc, sm, l_n0, l_n1, l_n2, l_b, pb_hi, pb_lo, &gi_it, &gi_viol);
+        it_total += gi_it;
+        rows_total += 2LL * np + (long long)K * (npt - 3);
+        if (st >= 0) { status = st; solved = true; solved_by_gi = true; viol_lsc = gi_viol > 0 ? gi_viol : 0.0; }
+        c.sync();
+    }
+    // ---- fallback: interior point on the screened working set ----
+    for (int attempt = 0; attempt < 4 && !solved; attempt++) {
         const bool all_rows = !(tau > 0) || attempt == 3;
         // ---- starting point: free control points of the initial trajectory ----
         for (int p = c.tid; p < ny; p += c.nthr) {
@@ -553,6 +839,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
 
         status = kStQpMaxIter;
         int it = 0;
+        bool acceptable = false;
         for (it = 0; it < max_it; it++) {
             // ============ pass 1: residuals, G'z, affine rhs, D = z/s ============
             double rp_inf = 0.0, mu = 0.0;
@@ -618,6 +905,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             printf("att %d it %d rp %.3e rd %.3e mu %.3e ginf %.3e rows %.0f\n", attempt, it, rp_inf, rd_inf, mu, g_inf, n_rows);
 #endif
             if (rp_inf <= kQpTolRp && rd_inf <= kQpTolRd * (1.0 + g_inf) && mu <= kQpTolMu) { status = 0; break; }
+            if (rp_inf <= 1e-10 && rd_inf <= 1e-9 * (1.0 + g_inf) && mu <= 1e-11) acceptable = true;   // as in the oracle
 
             // ============ W = H + G' D G  (packed lower triangle) ============
             for (int e = c.tid; e < T.ntri; e += c.nthr) sm.W[e] = 0.0;
@@ -638,7 +926,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 sm.W[e] = v;
             }
             c.sync();
-            if (!ldl_factor(c, sm.W, sm.invp, sm.pan, ny, T.tri_p)) { status = kStQpNumeric; break; }
+            if (!ldl_factor(c, sm.W, sm.invp, sm.pan, ny, T.tri_p)) { status = acceptable ? 0 : kStQpNumeric; break; }
 
             // ============ predictor ============
             ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
@@ -765,6 +1053,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             c.sync();
         }
         it_total += it;
+        if (status == kStQpMaxIter && acceptable) status = 0;
         if (status != 0) break;
         // ---- check EVERY LSC row at the solution (the screen is exact only if none is violated) ----
         viol_lsc = 0.0;
@@ -808,7 +1097,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
         }
     { double d1 = 0.0; c.reduce3(obj, 0, viol, 1, d1, 0); }
     if (c.tid == 0) {
-        *out.cost = obj; *out.viol = viol; *out.iters = it_total; *out.status |= status;
+        *out.cost = obj; *out.viol = viol; *out.iters = it_total; *out.status |= status | ((P.qp_solver != 1 && !solved_by_gi) ? kStQpIpmUsed : 0);
         if (out.rows) *out.rows = rows_total;
     }
     const bool ok = (status == 0);

@@ -57,7 +57,7 @@ void build_q_base(double dt, double Q[36]) {
         }
 }
 
-void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, QpTabHost& T) {
+void build_qp_tables(int M, int D, double dt, double w_control, double w_terminal, bool use_comm, QpTabHost& T) {
     const int n = kP - 1;
     T = QpTabHost();
     T.D = D; T.M = M; T.nyd = 3 * M - 2; T.ny = D * T.nyd; T.npt = M * kP; T.nx = D * T.npt;
@@ -102,6 +102,41 @@ void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, Q
                 for (auto& a : xe[m * kP + i].t)
                     for (auto& b : xe[m * kP + j].t) T.H1[(size_t)a.idx * nyd + b.idx] += q * a.coef * b.coef;
             }
+
+    // H^-1 of one axis block for every number ts of terminal segments (traj_optimizer.cpp:543-551): the dual
+    // active-set solver starts from the unconstrained optimum y0 = -H^-1 g and only ever needs H^-1 products
+    T.Hinv.assign((size_t)M * nyd * nyd, 0.0);
+    for (int ts = 1; ts <= M; ts++) {
+        std::vector<double> A((size_t)nyd * nyd), L((size_t)nyd * nyd, 0.0);
+        for (int i = 0; i < nyd * nyd; i++) A[i] = T.H1[i];
+        for (int m = M - ts; m < M; m++) { const int a = yid(m, 2); A[(size_t)a * nyd + a] += 2.0 * w_terminal; }
+        for (int j = 0; j < nyd; j++) {                      // Cholesky A = L L'
+            double d = A[(size_t)j * nyd + j];
+            for (int k = 0; k < j; k++) d -= L[(size_t)j * nyd + k] * L[(size_t)j * nyd + k];
+            d = std::sqrt(d);
+            L[(size_t)j * nyd + j] = d;
+            for (int i = j + 1; i < nyd; i++) {
+                double v = A[(size_t)i * nyd + j];
+                for (int k = 0; k < j; k++) v -= L[(size_t)i * nyd + k] * L[(size_t)j * nyd + k];
+                L[(size_t)i * nyd + j] = v / d;
+            }
+        }
+        double* Hi = T.Hinv.data() + (size_t)(ts - 1) * nyd * nyd;
+        std::vector<double> e(nyd);
+        for (int col = 0; col < nyd; col++) {                // solve A x = e_col
+            for (int i = 0; i < nyd; i++) {
+                double v = (i == col) ? 1.0 : 0.0;
+                for (int k = 0; k < i; k++) v -= L[(size_t)i * nyd + k] * e[k];
+                e[i] = v / L[(size_t)i * nyd + i];
+            }
+            for (int i = nyd - 1; i >= 0; i--) {
+                double v = e[i];
+                for (int k = i + 1; k < nyd; k++) v -= L[(size_t)k * nyd + i] * e[k];
+                e[i] = v / L[(size_t)i * nyd + i];
+            }
+            for (int i = 0; i < nyd; i++) Hi[(size_t)i * nyd + col] = e[i];
+        }
+    }
 
     // pair rows: (axis-local expression) replicated per axis
     struct Row { int fam, pt; Expr e; };

@@ -49,12 +49,13 @@ struct QpTabHost {
     int nnzw = 0;
     double scv = 0, sca = 0;                      // velocity / acceleration row scales n/dt, n(n-1)/dt^2
     std::vector<double> H1;                       // [nyd][nyd]  2*w_u*sum_m T_m' Q T_m
+    std::vector<double> Hinv;                     // [M][nyd][nyd]  inverse of the per-axis Hessian H1 + 2 w_T sum_{m >= M-ts} e e', ts = 1..M
     std::vector<double> Q2;                       // [6][6]      2*w_u*Q
     std::vector<double> Qb;                       // [6][6]      Q_base
 };
 
 // M, D, dt, weights, comm_range>0 ?
-void build_qp_tables(int M, int D, double dt, double w_control, bool use_comm, QpTabHost& T);
+void build_qp_tables(int M, int D, double dt, double w_control, double w_terminal, bool use_comm, QpTabHost& T);
 
 // Q_base = B Z B' dt^(-2 phi + 1)  (traj_optimizer.cpp:172-187, polynomial.hpp:280-293), n = 5, phi = 3
 void build_q_base(double dt, double Q[36]);
@@ -80,7 +81,7 @@ struct QpTab {
     int nnzw;
     int row_npl, row_bv, row_ba, row_bc;   // rows per axis, first velocity / acceleration / comm row inside an axis
     double scv, sca;                       // n/dt, n(n-1)/dt^2
-    const double *H1, *Q2;
+    const double *H1, *Q2, *Hinv;
 };
 
 }  // namespace dlsc

@@ -15,6 +15,7 @@ struct DevParams {
     int rec;                         // floats per record
     int qp_max_iter;
     double qp_screen;                // LSC working-set screen [m]; <= 0: all rows
+    int qp_solver;                   // 0: dual active set with interior-point fallback, 1: interior point only
     double dt, world_res, grid_res, z_2d, comm_range, w_control, w_terminal, reset_threshold;
     double world_min[3], world_max[3];       // double(float(x))
     float tk[kMaxPts];               // (float) of the time accumulated by `time += dt/n` (trajectory.cpp:84-90)
@@ -59,6 +60,6 @@ constexpr double kQpTolRp = 1e-10, kQpTolRd = DLSC_QP_TOL_RD, kQpTolMu = DLSC_QP
 
 // status bits (mirror include/dlsc_b200.h)
 constexpr int kStQpMaxIter = 1, kStQpNumeric = 2, kStSfcInitFailed = 4, kStGoalInfeasible = 8,
-              kStSfcReused = 16, kStNbrOverflow = 32;
+              kStSfcReused = 16, kStNbrOverflow = 32, kStQpIpmUsed = 64;
 
 }  // namespace dlsc

@@ -53,7 +53,7 @@ typedef struct dlsc_params {
     double w_terminal;      /* opt/terminal_weight                                         */
     double reset_threshold; /* plan/reset_threshold                                        */
     int32_t qp_max_iter;    /* interior-point iteration cap (0 -> 80)                      */
-    int32_t reserved;
+    int32_t qp_solver;      /* 0: dual active set, interior-point fallback (default); 1: interior point only */
     double qp_screen_slack; /* LSC working-set screen: rows with initial slack below this [m] enter the
                                first solve (0 -> 0.5; < 0 -> all rows).  Exact: see dlsc_qp.cuh.           */
 } dlsc_params;
@@ -66,6 +66,7 @@ typedef struct dlsc_params {
 #define DLSC_GOAL_INFEASIBLE  8   /* PlanningReport::QPFAILED from GoalOptimizer (goal_optimizer.cpp:122,132) */
 #define DLSC_SFC_REUSED      16   /* informational: previous box kept (collision_constraints.cpp:529-532) */
 #define DLSC_NBR_OVERFLOW    32   /* more neighbours in range than max_nbr */
+#define DLSC_QP_IPM_USED     64   /* informational: the active-set solver gave up, interior point solved it */
 
 /* stage bits for dlsc_run_stages / indices for dlsc_get_timings */
 #define DLSC_STAGE_PREDICT  1   /* obstacle prediction + initial trajectory (traj_planner.cpp:290-336, 409-441) */

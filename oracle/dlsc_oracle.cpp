@@ -950,6 +950,7 @@ int ipm_solve(int ny, const std::vector<double>& H, const std::vector<double>& g
     int status = ORC_QP_MAXITER;
     int it = 0;
     const int max_it = 80;
+    bool acceptable = false;
     for (it = 0; it < max_it; it++) {
         mulG(y, Gy);
         // residuals
@@ -965,6 +966,10 @@ int ipm_solve(int ny, const std::vector<double>& H, const std::vector<double>& g
         for (int i = 0; i < ny; i++) { rd_inf = std::max(rd_inf, std::fabs(rd[i])); g_inf = std::max(g_inf, std::fabs(g[i])); }
         if (m > 0) mu /= m;
         if (rp_inf <= 1e-10 && rd_inf <= ORC_QP_TOL_RD * (1.0 + g_inf) && mu <= ORC_QP_TOL_MU) { status = ORC_OK; break; }
+        // "acceptable" level: if the factorisation breaks down (or the cap is hit) after this level was reached,
+        // the iterate is returned as converged (the tight target above is at the edge of what fp64 Cholesky of
+        // the barrier-scaled system can deliver)
+        if (rp_inf <= 1e-10 && rd_inf <= 1e-9 * (1.0 + g_inf) && mu <= 1e-11) acceptable = true;
         // W = H + G' diag(z/s) G
         W = H;
         for (int r = 0; r < m; r++) {
@@ -988,7 +993,7 @@ int ipm_solve(int ny, const std::vector<double>& H, const std::vector<double>& g
                 L[i * ny + j] = a / dj;
             }
         }
-        if (!ok) { status = ORC_QP_NUMERIC; break; }
+        if (!ok) { status = acceptable ? ORC_OK : ORC_QP_NUMERIC; break; }
         auto solve = [&](std::vector<double>& b) {
             for (int i = 0; i < ny; i++) {
                 double a = b[i];
@@ -1040,6 +1045,7 @@ int ipm_solve(int ny, const std::vector<double>& H, const std::vector<double>& g
         for (int r = 0; r < m; r++) { s[r] += a * ds[r]; z[r] += a * dz[r]; }
     }
     (void)hscale;
+    if (status == ORC_QP_MAXITER && acceptable) status = ORC_OK;
     if (iters_out) *iters_out = it;
     return status;
 }

@@ -56,6 +56,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     P.rec = c->rl.size;
     P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
     P.qp_screen = hp->qp_screen_slack == 0.0 ? 0.5 : hp->qp_screen_slack;
+    P.qp_solver = hp->qp_solver;
     P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
     P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
     P.reset_threshold = hp->reset_threshold;
@@ -77,7 +78,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     c->sfc.assign(NL * M * 6, 0.f); c->traj.assign(NL * npt * 3, 0.f);
     c->qp_x.assign(NL * hp->dim * npt, 0.0); c->cost.assign(NL, 0); c->viol.assign(NL, 0);
     c->qp_iters.assign(NL, 0); c->status.assign(NL, 0);
-    build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->comm_range > 0, c->th);
+    build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->w_terminal, hp->comm_range > 0, c->th);
     const QpTabHost& h = c->th;
     QpTab& T = c->T;
     T.D = h.D; T.M = h.M; T.nyd = h.nyd; T.ny = h.ny; T.npt = h.npt; T.nx = h.nx; T.np = h.np; T.ntri = h.ntri;
@@ -90,7 +91,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     T.wi_ptr = h.wi_ptr.data(); T.wi_row = h.wi_row.data(); T.wi_coef = h.wi_coef.data();
     T.wp_ptr = h.wp_ptr.data(); T.wp_pt = h.wp_pt.data(); T.wp_coef = h.wp_coef.data();
     T.H1 = h.H1.data(); T.Q2 = h.Q2.data(); T.tri_p = h.tri_p.data(); T.nz_e = h.nz_e.data(); T.nnzw = h.nnzw;
-    T.pr_desc = h.pr_desc.data(); T.nz_hdr = reinterpret_cast<const uint4*>(h.nz_hdr.data()); T.nz_h = h.nz_h.data();
+    T.pr_desc = h.pr_desc.data(); T.nz_hdr = reinterpret_cast<const uint4*>(h.nz_hdr.data()); T.nz_h = h.nz_h.data(); T.Hinv = h.Hinv.data();
     {
         const int M = h.M, MP = M * kP;
         T.row_npl = h.np / h.D; T.row_bv = MP - 3; T.row_ba = T.row_bv + (M * 5 - 2); T.row_bc = T.row_ba + (M * 4 - 1);
