@@ -4,12 +4,14 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/dlsc_b200.h"
 #include "dlsc_kernels.h"
+#include "dlsc_stages.cuh"
 #include "dlsc_qp_tables.h"
 #include "dlsc_types.h"
 
@@ -34,6 +36,9 @@ struct dlsc_ctx {
     bool have_edt = false;
     int4* edt_cells = nullptr;
     float* edt_centre = nullptr;
+    uint8_t* edt_mask = nullptr;       // lattice-vertex mask of the SFC vertex test (built lazily for margin_host)
+    bool mask_dirty = false;
+    double margin_host = 0.0;          // radius of the first local agent (all BASELINE missions: 0.15 for every agent)
     int64_t launches = 0;
     bool timing = false;
     std::vector<cudaEvent_t> evpool;   // (DLSC_N_STAGES + 1) events per timed step, resolved lazily
@@ -222,6 +227,7 @@ void dlsc_destroy(dlsc_ctx* c) {
     if (c->tab_blob) cudaFree(c->tab_blob);
     if (c->edt_cells) cudaFree(c->edt_cells);
     if (c->edt_centre) cudaFree(c->edt_centre);
+    if (c->edt_mask) cudaFree(c->edt_mask);
     for (auto& e : c->evpool) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -268,6 +274,33 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
         E.centre[0] = c->edt_centre; E.centre[1] = c->edt_centre + dims[0]; E.centre[2] = c->edt_centre + dims[0] + dims[1];
     }
     c->have_edt = true;
+    c->mask_dirty = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// (Re)build the lattice-vertex mask for the current grid and margin.  The mask is dropped (record path only)
+// when a tabulated decision is not robust (edt_vertex_mask) or the grid is too tall for the z tables.
+static int build_vertex_mask(dlsc_ctx* c) {
+    EdtDev& E = c->S.edt;
+    c->mask_dirty = false;
+    if (c->edt_mask) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_mask); c->edt_mask = nullptr; }
+    E.vmask = nullptr; E.zs = edt_mask_zs(E.dims[2]); E.mask_margin = c->margin_host;
+    const char* env = getenv("DLSC_SFC_MASK");
+    if ((env && env[0] == '0') || E.zs > kSfcZsMax || !E.cells) return 0;
+    const size_t n = (size_t)(E.dims[0] + 1) * (E.dims[1] + 1) * E.zs;
+    int* d_unsafe = nullptr;
+    CK(cudaMalloc(&c->edt_mask, n));
+    CK(cudaMalloc(&d_unsafe, sizeof(int)));
+    CK(cudaMemsetAsync(d_unsafe, 0, sizeof(int), c->stream));
+    launch_edt_mask(E, c->margin_host, c->edt_mask, d_unsafe, c->stream);
+    c->launches++;
+    int unsafe = 1;
+    CK(cudaMemcpyAsync(&unsafe, d_unsafe, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_unsafe);
+    if (unsafe) { cudaFree(c->edt_mask); c->edt_mask = nullptr; }
+    E.vmask = c->edt_mask;
     CK(cudaGetLastError());
     return 0;
 }
@@ -276,7 +309,10 @@ int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
     if (!c || !p) return fail("dlsc_set_agent_props: null argument");
     CK(cudaSetDevice(c->device));
     const size_t b = (size_t)c->P.NL * sizeof(double);
-    if (p->radius) CK(cudaMemcpyAsync(c->S.radius, p->radius, b, cudaMemcpyHostToDevice, c->stream));
+    if (p->radius) {
+        CK(cudaMemcpyAsync(c->S.radius, p->radius, b, cudaMemcpyHostToDevice, c->stream));
+        if (p->radius[0] != c->margin_host) { c->margin_host = p->radius[0]; c->mask_dirty = true; }
+    }
     if (p->downwash) CK(cudaMemcpyAsync(c->S.downwash, p->downwash, b, cudaMemcpyHostToDevice, c->stream));
     if (p->max_vel) CK(cudaMemcpyAsync(c->S.max_vel, p->max_vel, b, cudaMemcpyHostToDevice, c->stream));
     if (p->max_acc) CK(cudaMemcpyAsync(c->S.max_acc, p->max_acc, b, cudaMemcpyHostToDevice, c->stream));
@@ -365,6 +401,7 @@ int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
 static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const DevState& Sr) {
     CK(cudaSetDevice(c->device));
     if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && !c->have_edt) return fail("dlsc_run_stages: use_sfc set but no EDT grid (dlsc_set_edt)");
+    if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && c->mask_dirty && build_vertex_mask(c)) return -1;
     DevState Sfix = Sr;
     Sfix.edt = c->S.edt;            // the grid may have been (re)set after a subset view was built
     const DevState& Sx = Sfix;

@@ -2,7 +2,7 @@
 //   k_predict      horizon shift / constant-velocity initial guess        thread per control point
 //   k_neighbours   comm-range neighbour list, built on device             warp per agent (ballot compaction)
 //   k_lsc          LSC separating planes: GJK hull-vs-origin + margins    thread per (agent, neighbour, segment)
-//   k_sfc          SFC greedy box expansion over the 16-byte EDT records  warp per agent (vote any)
+//   k_sfc          SFC greedy box expansion over the lattice-vertex mask  warp per agent (vote any)
 //   k_goal         intermediate goal line search (closed-form 1-var LP)   thread per agent
 //   k_advance      state step at t = dt + record refresh                  thread per agent
 // All arithmetic lives in dlsc_stages.cuh / dlsc_math.cuh.
@@ -83,32 +83,35 @@ void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// one CTA per agent: the greedy control flow is replicated in every thread (uniform), the vertex tests of a
-// box are spread over the 128 threads and combined with barrier votes (__syncthreads_or)
-__global__ void __launch_bounds__(128) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    __shared__ SfcTab tab;
-    __shared__ unsigned s_look[4];
-    const int la = blockIdx.x;
-    Group g; g.lane = threadIdx.x; g.width = blockDim.x; g.block = true;
+// one warp per agent: the greedy control flow is replicated in every lane (uniform), the lattice columns of
+// a box test are spread over the lanes (one 16-byte load of the vertex mask = 16 vertices) and combined with
+// a warp vote.  4096 agents = 4096 warps: the whole swarm is resident in one wave.
+constexpr int kSfcWarps = 4;
+__global__ void __launch_bounds__(kSfcWarps * 32, 8) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    __shared__ SfcTab tabs[kSfcWarps];
+    const int w = threadIdx.x >> 5;
+    const int la = blockIdx.x * kSfcWarps + w;
+    if (la >= P.NL) return;
+    Group g; g.lane = threadIdx.x & 31; g.width = 32; g.block = false;
     const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     const bool init = S.sfc_init[la] != 0 || S.disturbed[la] != 0;       // traj_planner.cpp:439, 693-695
-    long long lookups = 0;
+    long long look[3] = {0, 0, 0};
     const int st = sfc_agent(g, P, S.edt, init, v3_load(rec + npt * 3), S.init_traj + (size_t)la * npt * 3,
                              v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3), S.radius[la],
-                             S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &tab, &lookups);
-    const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)lookups);
-    if ((threadIdx.x & 31) == 0) s_look[threadIdx.x >> 5] = tot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+                             S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &tabs[w], look);
+    const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)look[0]);
+    if (g.lane == 0) {
         S.sfc_init[la] = 0;
         if (st) atomicOr(S.status + la, st);
-        atomicAdd(S.counters + 2, (unsigned long long)s_look[0] + s_look[1] + s_look[2] + s_look[3]);
+        atomicAdd(S.counters + 2, (unsigned long long)tot);
+        if (look[1]) atomicAdd(S.counters + 5, (unsigned long long)look[1]);
+        if (look[2]) atomicAdd(S.counters + 6, (unsigned long long)look[2]);
     }
 }
 
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st) {
-    k_sfc<<<P.NL, 128, 0, st>>>(P, S);
+    k_sfc<<<(P.NL + kSfcWarps - 1) / kSfcWarps, kSfcWarps * 32, 0, st>>>(P, S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -172,6 +175,27 @@ __global__ void k_edt_pack(const float* dist, const int32_t* obst, int4* cells, 
 }
 void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st) {
     k_edt_pack<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(dist, obst, cells, ncell);
+}
+
+// lattice-vertex mask of the SFC vertex test (dlsc_stages.cuh edt_vertex_mask): thread per (vx, vy, vz)
+__global__ void __launch_bounds__(256) k_edt_mask(const __grid_constant__ EdtDev E, double margin, uint8_t* mask, int* unsafe) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)(E.dims[0] + 1) * (E.dims[1] + 1) * E.zs;
+    if (i >= n) return;
+    const int vz = (int)(i % E.zs);
+    const size_t t = i / E.zs;
+    const int vy = (int)(t % (E.dims[1] + 1)), vx = (int)(t / (E.dims[1] + 1));
+    uint8_t b = 0;
+    if (vz <= E.dims[2]) {
+        bool u = false;
+        b = edt_vertex_mask(E, vx, vy, vz, margin, &u);
+        if (u) *unsafe = 1;
+    }
+    mask[i] = b;
+}
+void launch_edt_mask(const EdtDev& E, double margin, uint8_t* mask, int* unsafe, cudaStream_t st) {
+    const size_t n = (size_t)(E.dims[0] + 1) * (E.dims[1] + 1) * E.zs;
+    k_edt_mask<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, margin, mask, unsafe);
 }
 
 // LSC anchors in the reference layout [NL][K][M][P][3]: predicted control points, or the segment-case

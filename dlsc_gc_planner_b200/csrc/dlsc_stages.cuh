@@ -8,6 +8,8 @@
 //
 // Must be compiled with FMA contraction off (-fmad=false / -ffp-contract=off).
 #pragma once
+#include <string.h>
+
 #include "dlsc_math.cuh"
 #include "dlsc_types.h"
 
@@ -214,7 +216,7 @@ DLSC_HD bool vertex_blocked(const EdtDev& E, const V3& q, double margin, float h
 // reference's decision depends on that bit; the whole sequence of tests is reproduced.
 constexpr int kSfcTabMax = 96;
 constexpr int kSfcUnroll = 2;
-struct SfcTab {
+struct alignas(16) SfcTab {
     float q[3][kSfcTabMax];
     int c[3][kSfcTabMax];
 };
@@ -245,6 +247,140 @@ DLSC_HD bool vertex_blocked_tab(const EdtDev& E, float qx, float qy, float qz, i
     return linf_distance(cq, q) < margin + kEpsF;
 }
 
+// ---- lattice-vertex mask -------------------------------------------------------------------------
+// Every vertex the reference tests is a point of the res-lattice (box corners are grid-aligned, :440-441,
+// :803-806, :840-852, :1058-1063) whose float coordinate sits within a few ulp of a cell boundary, so
+// floor(coord / res) picks either cell v or cell v-1 on each axis -- that bit is reproduced exactly per
+// coordinate (per-axis tables below).  Given the cell, the vertex test (:876-886) compares an L-infinity
+// distance that is a multiple of res (+- float noise) with margin + 1e-5; when no such multiple is within
+// kMaskGuard of the threshold the outcome is a function of (lattice vertex, cell choice) only and is
+// tabulated once per grid: 8 outcomes = one byte per vertex instead of a 16-byte record per test.
+// edt_vertex_mask reports any decision closer than kMaskGuard to the threshold; the mask is then not used.
+constexpr double kMaskGuard = 1e-3;
+constexpr int kSfcZsMax = 256;
+DLSC_HD int edt_mask_zs(int dims2) { return ((dims2 + 1) + 15) / 16 * 16; }
+
+DLSC_HD uint8_t edt_vertex_mask(const EdtDev& E, int vx, int vy, int vz, double margin, bool* unsafe) {
+    const float half_res = (float)(0.5 * E.res);
+    const float qx = (float)((double)(vx + E.min_key[0]) * E.res);
+    const float qy = (float)((double)(vy + E.min_key[1]) * E.res);
+    const float qz = (float)((double)(vz + E.min_key[2]) * E.res);
+    const V3 q = v3(qx, qy, qz);
+    const V3 d3v = v3(half_res, half_res, half_res);
+    uint8_t bits = 0;
+    for (int s = 0; s < 8; s++) {
+        const int cx = vx - (s & 1), cy = vy - ((s >> 1) & 1), cz = vz - (s >> 2);
+        if (cx < 0 || cx >= E.dims[0] || cy < 0 || cy >= E.dims[1] || cz < 0 || cz >= E.dims[2]) continue;
+        const size_t idx = ((size_t)cx * E.dims[1] + cy) * E.dims[2] + cz;
+        const int4 rec = E.cells[idx];
+        float dist;
+#ifdef __CUDA_ARCH__
+        dist = __int_as_float(rec.x);
+#else
+        { union { int i; float f; } u; u.i = rec.x; dist = u.f; }
+#endif
+        if (!(dist < 1)) continue;
+        V3 cl = v3(0.f, 0.f, 0.f);
+        if (rec.y >= 0) { cl.x = E.centre[0][rec.y]; cl.y = E.centre[1][rec.z]; cl.z = E.centre[2][rec.w]; }
+        const V3 lo = cl - d3v, hi = cl + d3v;
+        V3 cq = q;
+        if (q.x < lo.x) cq.x = lo.x; else if (q.x > hi.x) cq.x = hi.x;
+        if (q.y < lo.y) cq.y = lo.y; else if (q.y > hi.y) cq.y = hi.y;
+        if (q.z < lo.z) cq.z = lo.z; else if (q.z > hi.z) cq.z = hi.z;
+        const double li = linf_distance(cq, q), thr = margin + kEpsF;
+        if (li < thr) bits |= (uint8_t)(1u << s);
+        if (fabs(li - thr) < kMaskGuard) *unsafe = true;
+    }
+    return bits;
+}
+
+struct U4 { uint32_t x, y, z, w; };
+
+// isObstacleInSFC through the vertex mask.  Returns 0 / 1, or -1 when this box cannot use the mask (a corner
+// off the lattice, ambiguous cell choice) -> the caller runs the record path.
+// One work item = 16 consecutive z-vertices of one (x, y) lattice column: one 16-byte load.
+// A coordinate outside the grid ("oob", e.g. z = -1e-9 under the world floor) makes the accessor return
+// dist = -1 and obstacle (0,0,0) (vertex_blocked_tab): the test is then the separable predicate
+// near_x & near_y & near_z with near = (|q - clamp(q, +-res/2)| < margin + 1e-5), evaluated per axis here.
+// Per-axis table entry: v << 3 | near << 2 | oob << 1 | s   (v = lattice index, s = v - cell in {0,1}).
+DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
+                                 int m0, int m1, int m2, SfcTab* tab, long long* lookups) {
+    const double res = P.world_res;
+    const float half_res = (float)(0.5 * res);
+    const double thr = margin + kEpsF;
+    bool bad = false, nz_all = false, nz_oob = false;
+    for (int e = g.lane; e < m0 + m1 + m2; e += g.width) {
+        const int ax = (e < m0) ? 0 : (e < m0 + m1 ? 1 : 2);
+        const int i = e - (ax == 0 ? 0 : (ax == 1 ? m0 : m0 + m1));
+        const float lo = (ax == 0) ? b.lo.x : (ax == 1 ? b.lo.y : b.lo.z);
+        const float q = (float)(lo + i * res);
+        const double t = E.inv_res * (double)q;
+        const int c = (int)floor(t) - E.min_key[ax];
+        const double vr = rint(t);
+        int v = (int)vr - E.min_key[ax];
+        int s = v - c;
+        const bool oob = c < 0 || c >= E.dims[ax];
+        if (fabs(t - vr) > 1e-2 || (!oob && (s < 0 || s > 1))) bad = true;
+        if (oob) { v = 0; s = 0; }
+        const float olo = 0.f - half_res, ohi = 0.f + half_res;          // obstacle (0,0,0) +- res/2
+        const float cq = (q < olo) ? olo : (q > ohi ? ohi : q);
+        const bool near = (double)fabsf(cq - q) < thr;
+        if (ax == 2 && near) { nz_all = true; if (oob) nz_oob = true; }
+        tab->c[ax][i] = (v << 3) | (near ? 4 : 0) | (oob ? 2 : 0) | (s & 1);
+    }
+    if (g.any(bad)) return -1;            // (barrier: the tables are complete)
+    nz_all = g.any(nz_all);
+    nz_oob = g.any(nz_oob);
+    const int zs = E.zs;
+    uint32_t* zm = reinterpret_cast<uint32_t*>(tab->q[0]);
+    for (int e = g.lane; e < (zs >> 2); e += g.width) zm[e] = 0u;
+    g.sync();
+    uint8_t* zb = reinterpret_cast<uint8_t*>(zm);
+    for (int i = g.lane; i < m2; i += g.width) {
+        const int ez = tab->c[2][i];
+        if (!(ez & 2)) zb[ez >> 3] = (ez & 1) ? 0xF0 : 0x0F;
+    }
+    g.sync();
+    int vz0 = tab->c[2][0] >> 3, vz1 = tab->c[2][m2 - 1] >> 3;
+    if (tab->c[2][0] & 2) vz0 = 0;                      // oob below: the in-grid entries start at 0 or later
+    if (tab->c[2][m2 - 1] & 2) vz1 = E.dims[2];         // oob above
+    const int ch0 = vz0 >> 4, nch = (vz1 >> 4) - ch0 + 1;
+    const int per_x = m1 * nch, items = m0 * per_x;
+    const size_t sy = (size_t)zs, sx = (size_t)(E.dims[1] + 1) * zs;
+    if (lookups && g.lane == 0) *lookups += (long long)m0 * m1 * m2;
+    constexpr int U = 4;
+    for (int base = 0; base < items; base += g.width * U) {
+        uint32_t hit = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int idx = base + u * g.width + g.lane;
+            if (idx < items) {
+                const int ix = idx / per_x, r = idx - ix * per_x;
+                const int iy = r / nch, ch = ch0 + (r - iy * nch);
+                const int ex = tab->c[0][ix], ey = tab->c[1][iy];
+                const bool near_xy = (ex & ey & 4) != 0;
+                if ((ex | ey) & 2) {
+                    if (near_xy && nz_all) hit |= 1u;       // whole column outside the grid
+                } else {
+                    const uint8_t* p = E.vmask + (size_t)(ex >> 3) * sx + (size_t)(ey >> 3) * sy + (size_t)ch * 16;
+#ifdef __CUDA_ARCH__
+                    const uint4 B = __ldg(reinterpret_cast<const uint4*>(p));
+#else
+                    U4 B; memcpy(&B, p, 16);
+#endif
+                    const uint32_t* z4 = zm + ch * 4;
+                    const uint32_t sel = 0x11111111u << ((ex & 1) | ((ey & 1) << 1));
+                    hit |= ((B.x & z4[0]) | (B.y & z4[1]) | (B.z & z4[2]) | (B.w & z4[3])) & sel;
+                    if (near_xy && nz_oob) hit |= 1u;       // the column's out-of-grid z entries
+                }
+            }
+        }
+        if (g.any(hit != 0)) return 1;
+    }
+    g.sync();
+    return 0;
+}
+
 DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
                              SfcTab* tab, long long* lookups) {
     const double res = P.world_res;
@@ -254,6 +390,15 @@ DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E
     const int m2 = (int)floor(((b.hi.z - b.lo.z) + kEpsF) / res) + 1;
     if (m0 <= 0 || m1 <= 0 || m2 <= 0) return false;
     const int total = m0 * m1 * m2;
+    // lookups: [0] lattice vertices of the tested boxes, [1] box tests through the vertex mask, [2] through the records
+    if (E.vmask && margin == E.mask_margin && m0 <= kSfcTabMax && m1 <= kSfcTabMax && m2 <= kSfcTabMax) {
+        const int r = obstacle_in_box_mask(g, P, E, b, margin, m0, m1, m2, tab, lookups);
+        if (r >= 0) {
+            if (lookups && g.lane == 0) lookups[1] += 1;
+            return r != 0;
+        }
+    }
+    if (lookups && g.lane == 0) lookups[2] += 1;
     if (m0 > kSfcTabMax || m1 > kSfcTabMax || m2 > kSfcTabMax) {
         // oversized box: direct evaluation
         for (int base = 0; base < total; base += g.width) {

@@ -45,6 +45,12 @@ struct EdtDev {
     double res, inv_res;
     const int4* cells;
     const float* centre[3];      // centre[ax][c] = (float)(((double)(c + min_key[ax]) + 0.5) * res)
+    // Lattice-vertex mask (dlsc_stages.cuh, edt_vertex_mask): one byte per lattice vertex v, bit s = outcome of
+    // the isObstacleInSFC vertex test when the vertex coordinate falls into cell v - (s&1, s>>1&1, s>>2).
+    // Layout [dims0+1][dims1+1][zs], zs = dims2+1 rounded up to 16.  nullptr = not built / not usable.
+    const uint8_t* vmask;
+    int zs;
+    double mask_margin;          // the margin (agent radius) the mask was built for
 };
 #endif
 

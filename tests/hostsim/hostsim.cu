@@ -32,6 +32,8 @@ struct dlsc_ctx {
     std::vector<int32_t> nbr_idx, nbr_cnt, qp_iters, status;
     std::vector<int4> cells;
     std::vector<float> centre;
+    std::vector<uint8_t> vmask;
+    bool mask_dirty = false;
     EdtDev edt;
     bool have_edt = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -122,12 +124,29 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
     c->edt.centre[0] = c->centre.data(); c->edt.centre[1] = c->centre.data() + dims[0];
     c->edt.centre[2] = c->centre.data() + dims[0] + dims[1];
     c->have_edt = true;
+    c->mask_dirty = true;
     return 0;
+}
+
+// same lazy build as dlsc_api.cu build_vertex_mask
+static void build_vertex_mask(dlsc_ctx* c) {
+    EdtDev& E = c->edt;
+    c->mask_dirty = false;
+    E.vmask = nullptr; E.zs = edt_mask_zs(E.dims[2]); E.mask_margin = c->radius.empty() ? 0.0 : c->radius[0];
+    const char* env = getenv("DLSC_SFC_MASK");
+    if ((env && env[0] == '0') || E.zs > kSfcZsMax || !E.cells) return;
+    c->vmask.assign((size_t)(E.dims[0] + 1) * (E.dims[1] + 1) * E.zs, 0);
+    bool unsafe = false;
+    for (int vx = 0; vx <= E.dims[0]; vx++)
+        for (int vy = 0; vy <= E.dims[1]; vy++)
+            for (int vz = 0; vz <= E.dims[2]; vz++)
+                c->vmask[((size_t)vx * (E.dims[1] + 1) + vy) * E.zs + vz] = edt_vertex_mask(E, vx, vy, vz, E.mask_margin, &unsafe);
+    if (!unsafe) E.vmask = c->vmask.data();
 }
 
 int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
     const size_t NL = c->P.NL;
-    if (p->radius) c->radius.assign(p->radius, p->radius + NL);
+    if (p->radius) { c->radius.assign(p->radius, p->radius + NL); c->mask_dirty = true; }
     if (p->downwash) c->downwash.assign(p->downwash, p->downwash + NL);
     if (p->max_vel) c->max_vel.assign(p->max_vel, p->max_vel + NL);
     if (p->max_acc) c->max_acc.assign(p->max_acc, p->max_acc + NL);
@@ -220,18 +239,19 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
                     c->counters[1] += it;
                 }
             }
+    if ((mask & DLSC_STAGE_SFC) && P.use_sfc && c->mask_dirty) build_vertex_mask(c);
     if ((mask & DLSC_STAGE_SFC) && P.use_sfc)
         for (int la = 0; la < P.NL; la++) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             const bool init = c->sfc_init[la] != 0 || c->disturbed[la] != 0;
-            long long lookups = 0;
+            long long lookups[3] = {0, 0, 0};
             SfcTab memo;
             const int st = sfc_agent(g, P, c->edt, init, v3_load(rec + npt * 3), c->init_traj.data() + (size_t)la * npt * 3,
                                      v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3), c->radius[la],
-                                     c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &memo, &lookups);
+                                     c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &memo, lookups);
             c->sfc_init[la] = 0;
             c->status[la] |= st;
-            c->counters[2] += lookups;
+            c->counters[2] += lookups[0]; c->counters[5] += lookups[1]; c->counters[6] += lookups[2];
         }
     if (mask & DLSC_STAGE_GOAL)
         for (int la = 0; la < P.NL; la++) {
