@@ -100,7 +100,7 @@ static int upload_tables(dlsc_ctx* c) {
     const size_t i_wi_ptr = SEC(wi_ptr), i_wi_row = SEC(wi_row), i_wi_coef = SEC(wi_coef);
     const size_t i_wp_ptr = SEC(wp_ptr), i_wp_pt = SEC(wp_pt), i_wp_coef = SEC(wp_coef);
     const size_t i_H1 = SEC(H1), i_Q2 = SEC(Q2), i_tri = SEC(tri_p), i_nz = SEC(nz_e);
-    const size_t i_desc = SEC(pr_desc), i_hdr = SEC(nz_hdr), i_nzh = SEC(nz_h), i_hinv = SEC(Hinv);
+    const size_t i_desc = SEC(pr_desc), i_hdr = SEC(nz_hdr), i_nzh = SEC(nz_h), i_hinv = SEC(Hinv), i_y0 = SEC(Y0);
 #undef SEC
     std::vector<char> blob(off ? off : 256, 0);
     for (auto& s : secs) memcpy(blob.data() + s.off, s.src, s.bytes);
@@ -122,7 +122,7 @@ static int upload_tables(dlsc_ctx* c) {
     T.wp_ptr = PTR(int, i_wp_ptr); T.wp_pt = PTR(int16_t, i_wp_pt); T.wp_coef = PTR(double, i_wp_coef);
     T.H1 = PTR(double, i_H1); T.Q2 = PTR(double, i_Q2); T.tri_p = PTR(uint8_t, i_tri);
     T.nz_e = PTR(uint16_t, i_nz); T.nnzw = h.nnzw;
-    T.pr_desc = PTR(uint32_t, i_desc); T.nz_hdr = PTR(uint4, i_hdr); T.nz_h = PTR(double, i_nzh); T.Hinv = PTR(double, i_hinv);
+    T.pr_desc = PTR(uint32_t, i_desc); T.nz_hdr = PTR(uint4, i_hdr); T.nz_h = PTR(double, i_nzh); T.Hinv = PTR(double, i_hinv); T.Y0 = PTR(double, i_y0);
     {
         const int M = h.M, MP = M * kP;
         T.row_npl = h.np / h.D; T.row_bv = MP - 3; T.row_ba = T.row_bv + (M * 5 - 2); T.row_bc = T.row_ba + (M * 4 - 1);
@@ -201,7 +201,8 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.cost, NL); rc |= dev_alloc(c, &S.viol, NL);
     rc |= dev_alloc(c, &S.qp_iters, NL); rc |= dev_alloc(c, &S.status, NL);
     rc |= dev_alloc(c, &S.counters, 8);
-    rc |= dev_alloc(c, &S.qp_next, 1);
+    rc |= dev_alloc(c, &S.qp_next, 4);
+    rc |= dev_alloc(c, &S.qp_list, NL);
     if (rc) { dlsc_destroy(c); return -1; }
 
     build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->w_terminal, hp->comm_range > 0, c->th);
@@ -428,7 +429,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     if (mask & DLSC_STAGE_GOAL) { launch_goal(Pr, Sx, st); c->launches++; }
     else if (mask & DLSC_STAGE_QP) { launch_goal_copy(Pr, Sx, st); c->launches++; }   // QP alone: goal from the record
     if (tm) CK(cudaEventRecord(ev[5], st));
-    if (mask & DLSC_STAGE_QP) { launch_qp(Pr, Sx, c->T, c->qpl, st); c->launches++; }
+    if (mask & DLSC_STAGE_QP) c->launches += launch_qp(Pr, Sx, c->T, c->qpl, st);
     if (tm) { CK(cudaEventRecord(ev[6], st)); c->ev_used++; }
     CK(cudaGetLastError());
     return 0;

@@ -34,11 +34,12 @@ struct DevState {
     int32_t *qp_iters, *status;
     unsigned long long* counters;   // [8]
     double* qp_scratch;        // [qp_ctas][qp_scratch_doubles]
-    int* qp_next;              // dynamic work counter
+    int* qp_next;              // [4]: [1] length of qp_list, [2] work counter of the fallback kernel
+    int* qp_list;              // [NL] agents queued for the interior-point fallback
     EdtDev edt;
 };
 
-struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; };
+struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; };
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
 void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);
@@ -54,6 +55,6 @@ void launch_reset(const DevParams& P, const DevState& S, const float* start_dev,
 
 double measure_fp64_peak(int device, cudaStream_t st);
 QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device);
-void launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);
+int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);
 
 }  // namespace dlsc

@@ -2,52 +2,89 @@
 // Persistent CTAs: grid = SMs x resident CTAs, each CTA pulls agents from a device-side counter
 // (agents differ widely in neighbour count, hence in row count) and reuses one global scratch slab.
 #include "dlsc_kernels.h"
-#include "dlsc_qp.cuh"
+#include "dlsc_qp_gi.cuh"
 
 namespace dlsc {
 
-constexpr int kQpThreads = 128;
+constexpr int kQpThreads = 128;     // interior-point fallback kernel
+#ifndef DLSC_GI_THREADS
+#define DLSC_GI_THREADS 64
+#endif
+constexpr int kGiThreads = DLSC_GI_THREADS;
 
+__device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState& S, const QpTab& T, int la, QpIn& in, QpOut& out) {
+    const int npt = P.M * kP;
+    const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    in.pos = v3_load(rec + npt * 3); in.vel = v3_load(rec + npt * 3 + 3);
+    in.acc = v3_load(S.acc + la * 3); in.goal = v3_load(S.goal_new + la * 3);
+    in.wp = v3_load(S.waypoint + la * 3);
+    in.radius = S.radius[la]; in.max_vel = S.max_vel[la]; in.max_acc = S.max_acc[la];
+    in.nominal_vel = S.nominal_vel[la];
+    in.sfc = S.sfc + (size_t)la * P.M * 6;
+    in.init_traj = S.init_traj + (size_t)la * npt * 3;
+    in.K = S.nbr_cnt[la];
+    const size_t pr = (size_t)la * P.K;
+    in.nbr_idx = S.nbr_idx + pr;
+    in.normal = S.lsc_normal + pr * P.M * 3;
+    in.d = S.lsc_d + pr * P.M * kP;
+    in.anchor_last = S.lsc_anchor_last + pr * 3;
+    in.pred_traj = S.pred_traj;
+    out.traj = S.traj + (size_t)la * npt * 3;
+    out.x = S.qp_x + (size_t)la * T.nx;
+    out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;
+    out.rows = nullptr;
+}
+
+// Primary kernel: one small CTA per agent, dual active set off the constraint arrays (dlsc_qp_gi.cuh).
+// Agents it cannot finish are appended to S.qp_list for k_qp.
+__global__ void __launch_bounds__(kGiThreads) k_qp_gi(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
+                                                       const __grid_constant__ QpTab T) {
+    extern __shared__ __align__(16) double smem[];
+    QpSmem sm;
+    gi_smem_carve(T, smem, sm);
+    Cta c; c.tid = threadIdx.x; c.nthr = blockDim.x; c.red = sm.red;
+    const int la = blockIdx.x;
+    QpIn in; QpOut out;
+    qp_load_agent(P, S, T, la, in, out);
+    long long rows = 0;
+    if (threadIdx.x == 0) out.rows = &rows;
+    const bool done = qp_agent_gi(c, P, T, in, out, sm);
+    if (threadIdx.x == 0) {
+        if (!done) S.qp_list[atomicAdd(S.qp_next + 1, 1)] = la;
+        else {
+            const int it = S.qp_iters[la];
+            if (it) atomicAdd(S.counters + 3, (unsigned long long)it);
+            atomicAdd(S.counters + 4, (unsigned long long)rows);
+        }
+    }
+}
+
+// Fallback kernel (interior point, dlsc_qp.cuh): persistent CTAs pull agents from S.qp_list (or, with
+// all_agents, every agent: qp_solver = 1).
 __global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ DevState S,
-                                                   const __grid_constant__ QpTab T, size_t scratch_doubles) {
+                                                   const __grid_constant__ QpTab T, size_t scratch_doubles, int all_agents) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_agent;
+    const int n_list = all_agents ? P.NL : S.qp_next[1];
+    if (n_list == 0) return;
     QpSmem sm;
     qp_smem_carve(T, P.K, smem, sm);
     Cta c; c.tid = threadIdx.x; c.nthr = blockDim.x; c.red = sm.red;
     double* scratch = S.qp_scratch + (size_t)blockIdx.x * scratch_doubles;
-    const int npt = P.M * kP;
     unsigned long long it_sum = 0, row_sum = 0;
     for (;;) {
-        if (threadIdx.x == 0) s_agent = atomicAdd(S.qp_next, 1);
+        if (threadIdx.x == 0) s_agent = atomicAdd(S.qp_next + 2, 1);
         __syncthreads();
-        const int la = s_agent;
+        const int i = s_agent;
         __syncthreads();
-        if (la >= P.NL) break;
-        const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
-        QpIn in;
-        in.pos = v3_load(rec + npt * 3); in.vel = v3_load(rec + npt * 3 + 3);
-        in.acc = v3_load(S.acc + la * 3); in.goal = v3_load(S.goal_new + la * 3);
-        in.wp = v3_load(S.waypoint + la * 3);
-        in.radius = S.radius[la]; in.max_vel = S.max_vel[la]; in.max_acc = S.max_acc[la];
-        in.nominal_vel = S.nominal_vel[la];
-        in.sfc = S.sfc + (size_t)la * P.M * 6;
-        in.init_traj = S.init_traj + (size_t)la * npt * 3;
-        in.K = S.nbr_cnt[la];
-        const size_t pr = (size_t)la * P.K;
-        in.nbr_idx = S.nbr_idx + pr;
-        in.normal = S.lsc_normal + pr * P.M * 3;
-        in.d = S.lsc_d + pr * P.M * kP;
-        in.anchor_last = S.lsc_anchor_last + pr * 3;
-        in.pred_traj = S.pred_traj;
+        if (i >= n_list) break;
+        const int la = all_agents ? i : S.qp_list[i];
+        QpIn in; QpOut out;
+        qp_load_agent(P, S, T, la, in, out);
         long long rows = 0;
-        QpOut out;
-        out.traj = S.traj + (size_t)la * npt * 3;
-        out.x = S.qp_x + (size_t)la * T.nx;
-        out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;
-        out.rows = (threadIdx.x == 0) ? &rows : nullptr;
-        qp_agent(c, P, T, in, out, sm, scratch);
+        if (threadIdx.x == 0) out.rows = &rows;
+        qp_agent(c, P, T, in, out, sm, scratch, !all_agents);
         if (threadIdx.x == 0) { it_sum += (unsigned long long)S.qp_iters[la]; row_sum += (unsigned long long)rows; }
     }
     if (threadIdx.x == 0) {
@@ -61,6 +98,8 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     L.threads = kQpThreads;
     L.smem = qp_smem_bytes(T, P.K);
     cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    L.gi_smem = gi_smem_doubles(T) * sizeof(double);
+    cudaFuncSetAttribute(k_qp_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
     int per_sm = 1, sms = 148;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp, kQpThreads, L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -70,10 +109,14 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     return L;
 }
 
-void launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st) {
-    cudaMemsetAsync(S.qp_next, 0, sizeof(int), st);
+// returns the number of kernels launched
+int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st) {
+    cudaMemsetAsync(S.qp_next, 0, 4 * sizeof(int), st);
     const int ctas = L.ctas < P.NL ? L.ctas : P.NL;
-    k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles);
+    const int all = (P.qp_solver == 1) ? 1 : 0;
+    if (!all) k_qp_gi<<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T);
+    k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
+    return all ? 1 : 2;
 }
 
 // ---- FP64 FMA peak probe: 8 independent dependent-FMA chains per thread, 1024 threads, 2 CTAs per SM ----

@@ -665,8 +665,9 @@ DLSC_HD int qp_dual_active_set(const Cta& c, const DevParams& P, const QpTab& T,
 }
 
 // one agent
+// skip_gi: the dual active set already ran on this agent (dlsc_qp_gi.cuh) and gave up
 DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
-                      const QpSmem& sm, double* scratch) {
+                      const QpSmem& sm, double* scratch, bool skip_gi = false) {
     const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, nx = T.nx, np = T.np, Kc = P.K;
     const int K = in.K;
     const int n = kP - 1;
@@ -751,7 +752,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
 
     // ---- primary solver: dual active set on all rows (LSC rows cached as (n, b) per (point, neighbour)) ----
     bool solved = false, solved_by_gi = false;
-    if (P.qp_solver != 1) {
+    if (P.qp_solver != 1 && !skip_gi) {
         for (int pt = 3; pt < npt; pt++) {
             const int m = pt / kP;
             for (int cc = c.tid; cc < K; cc += c.nthr) {

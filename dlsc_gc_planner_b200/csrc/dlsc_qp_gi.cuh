@@ -1,0 +1,354 @@
+// dlsc_qp_gi.cuh -- primary QP path: dual active set (Goldfarb-Idnani, Schur form) straight off the LSC / SFC
+// arrays, one small CTA per agent.
+//
+// Same problem as TrajOptimizer::populatebyrow (reference src/traj_optimizer.cpp:225-527).  What the replan
+// QPs look like in practice (4096-agent forest, measured): 60 % of the agents have NO active inequality at
+// the optimum, 28 % have one, the maximum is ~11.  So the work per agent is
+//   (A) y0 = -H^-1 g, the unconstrained optimum.  g is linear in (c0, c1, c2, goal) per axis, so y0 is a
+//       tabulated [nyd x 4] map per terminal-segment count (QpTab::Y0) -- 4 FMAs per unknown;
+//   (B) one pass over every inequality row to find the most violated one.  Rows are evaluated from their
+//       sources (two-sided pattern rows by stencil arithmetic, LSC rows from normal / d / anchor arrays in a
+//       flat neighbour-major index space so that consecutive threads read consecutive control points);
+//       nothing is cached or copied per agent;
+//   (C) only if something is violated: the H^-1 block is staged in shared memory and the active-set
+//       iterations of dlsc_qp.cuh run (same algebra as qp_dual_active_set), re-scanning from the sources.
+// Agents on which the active set gives up (more than kGiQ simultaneously active rows, loss of positive
+// definiteness of the Schur complement) are queued for the interior-point kernel (dlsc_qp.cuh qp_agent).
+#pragma once
+#include "dlsc_qp.cuh"
+
+namespace dlsc {
+
+DLSC_HD size_t gi_smem_doubles(const QpTab& T) {
+    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + 96;
+}
+DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
+    double* p = base;
+    s.W = p; p += gi_doubles(T);
+    s.y = p; p += T.ny; s.dy = p; p += T.ny; s.ax1 = p; p += T.ny;
+    s.x = p; p += T.nx;
+    s.cst = p; p += 16;
+    s.red = p; p += 96;
+    s.invp = s.pan = s.rd = s.dx = s.ax2 = s.V1 = s.V2 = s.DD = s.S = nullptr;
+    s.off = nullptr; s.act = nullptr;
+}
+
+struct PairRowD { int fam, k, pa, pb; };
+DLSC_HD PairRowD pair_desc(const QpTab& T, int r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t d = __ldg(T.pr_desc + r);
+#else
+    const uint32_t d = T.pr_desc[r];
+#endif
+    PairRowD o; o.fam = d & 3; o.k = (d >> 2) & 3; o.pa = (d >> 4) & 0xff; o.pb = (d >> 12) & 0xff;
+    return o;
+}
+
+// violation of the two sides of pattern row r at x
+DLSC_HD void pair_violation(const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, int r, const double* x,
+                            double& vh, double& vl) {
+    const PairRowD d = pair_desc(T, r);
+    PairRow pr; pr.fam = d.fam; pr.pa = d.pa; pr.pb = d.pb;
+    const double act = pair_eval(T, pr, x + d.k * T.npt);
+    double lo, hi;
+    pair_bounds(P, T, in, qc, d.k, pr, lo, hi);
+    vh = act - hi; vl = lo - act;
+}
+
+// most violated row over all inequality rows; every thread returns the same (vmax, id)
+//   id < 2 np: pattern row r = id >> 1, side id & 1 (0: upper, 1: lower);  else LSC row o = id - 2 np = pt * Kcap + cc
+DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
+                     double& vmax_out, double& id_out) {
+    const int npt = T.npt, np = T.np, Kc = P.K, K = in.K;
+    const bool D3 = (P.D == 3);
+    double best = -1e300, best_id = 1e300;
+    for (int r = c.tid; r < np; r += c.nthr) {
+        double vh, vl;
+        pair_violation(P, T, in, qc, r, x, vh, vl);
+        if (vh > best) { best = vh; best_id = 2.0 * r; }
+        if (vl > best) { best = vl; best_id = 2.0 * r + 1.0; }
+    }
+    const int total = K * npt;
+    for (int e = c.tid; e < total; e += c.nthr) {
+        const int cc = e / npt, pt = e - cc * npt;
+        if (pt < 3) continue;                                                       // traj_optimizer.cpp:417-419
+        const int m = pt / kP;
+        if (v3_norm(v3_load(in.normal + ((size_t)cc * P.M + m) * 3)) < kEpsF) continue;    // :422-424
+        const LscRowData rw = lsc_row_data(P, in, pt, cc);
+        const double v = -(rw.n0 * x[pt] + rw.n1 * x[npt + pt] + (D3 ? rw.n2 * x[2 * npt + pt] : 0.0)) - rw.b;
+        const double id = 2.0 * np + (double)(pt * Kc + cc);
+        if (v > best || (v == best && id < best_id)) { best = v; best_id = id; }
+    }
+    double vmax = best, d0 = 0.0, d1 = 0.0;
+    c.reduce3(vmax, 1, d0, 0, d1, 0);
+    double idsel = (best == vmax) ? best_id : 1e300;
+    d0 = 0.0; d1 = 0.0;
+    c.reduce3(idsel, 2, d0, 0, d1, 0);
+    vmax_out = vmax; id_out = idsel;
+}
+
+// Returns 0 = optimal, kStQpMaxIter = infeasible, -1 = give up.  y in sm.y, x in sm.x on return.
+DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
+                     const QpSmem& sm, int* iters_out, double* viol_out) {
+    const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, np = T.np, Kc = P.K;
+    const bool D3 = (D == 3);
+    GiSmem g;
+    gi_carve(T, sm.W, g);
+    const double tol = 1e-9;
+    int q = 0, iters = 0, status = -1;
+    double viol_p = 0.0, u_p = 0.0;
+    bool same_p = false, have_hinv = false;
+    for (int guard = 0; guard < 400; guard++) {
+        if (!same_p) {
+            map_x(c, T, sm.y, sm.cst, sm.x);
+            c.sync();
+            double vmax, idsel;
+            gi_scan(c, P, T, in, qc, sm.x, vmax, idsel);
+            *viol_out = vmax;
+            if (!(vmax > tol)) { status = 0; break; }
+            if (!have_hinv) {                                   // first violated row: stage this agent's H^-1 block
+                const double* src = T.Hinv + (size_t)(qc.ts - 1) * nyd * nyd;
+                for (int e = c.tid; e < nyd * nyd; e += c.nthr) g.Hinv[e] = src[e];
+                have_hinv = true;
+            }
+            // ---- candidate row p: x-space form -> y-space form (thread 0) ----
+            if (c.tid == 0) {
+                const int id = (int)idsel;
+                int xi[3] = {0, 0, 0}; double xc[3] = {0, 0, 0}; int nxe = 0; double bp;
+                if (id < 2 * np) {
+                    const int r = id >> 1, side = id & 1;
+                    const PairRowD pd = pair_desc(T, r);
+                    PairRow pr; pr.fam = pd.fam; pr.pa = pd.pa; pr.pb = pd.pb;
+                    double lo, hi;
+                    pair_bounds(P, T, in, qc, pd.k, pr, lo, hi);
+                    const double sg = side ? -1.0 : 1.0;
+                    const int base = pd.k * npt;
+                    if (pr.fam == 0) { xi[0] = base + pr.pa; xc[0] = sg; nxe = 1; }
+                    else if (pr.fam == 1) { xi[0] = base + pr.pa + 1; xc[0] = sg * T.scv; xi[1] = base + pr.pa; xc[1] = -sg * T.scv; nxe = 2; }
+                    else if (pr.fam == 2) {
+                        xi[0] = base + pr.pa + 2; xc[0] = sg * T.sca; xi[1] = base + pr.pa + 1; xc[1] = -2.0 * sg * T.sca;
+                        xi[2] = base + pr.pa; xc[2] = sg * T.sca; nxe = 3;
+                    } else { xi[0] = base + pr.pa; xc[0] = sg; xi[1] = base + pr.pb; xc[1] = -sg; nxe = 2; }
+                    bp = side ? -lo : hi;
+                } else {
+                    const int o = id - 2 * np, pt = o / Kc, cc = o - pt * Kc;
+                    const LscRowData rw = lsc_row_data(P, in, pt, cc);
+                    xi[0] = pt; xc[0] = -rw.n0; xi[1] = npt + pt; xc[1] = -rw.n1; nxe = 2;
+                    if (D3) { xi[2] = 2 * npt + pt; xc[2] = -rw.n2; nxe = 3; }
+                    bp = rw.b;
+                }
+                double* yc = g.yc + 9 * kGiQ; int16_t* yi = g.yi + 9 * kGiQ;
+                int nt = 0;
+                for (int e = 0; e < nxe; e++) {
+                    const int k = xi[e] / npt, pt = xi[e] - k * npt, m = pt / kP, i = pt - m * kP, yb = k * nyd;
+                    const double cf = xc[e];
+                    if (i >= 3) { yi[nt] = (int16_t)(yb + ((m == M - 1) ? 3 * (M - 1) : 3 * m + i - 3)); yc[nt++] = cf; }
+                    else if (m > 0) {
+                        const int q3 = yb + 3 * (m - 1);
+                        if (i == 0) { yi[nt] = (int16_t)(q3 + 2); yc[nt++] = cf; }
+                        else if (i == 1) { yi[nt] = (int16_t)(q3 + 2); yc[nt++] = 2.0 * cf; yi[nt] = (int16_t)(q3 + 1); yc[nt++] = -cf; }
+                        else { yi[nt] = (int16_t)(q3 + 2); yc[nt++] = 4.0 * cf; yi[nt] = (int16_t)(q3 + 1); yc[nt++] = -4.0 * cf;
+                               yi[nt] = (int16_t)q3; yc[nt++] = cf; }
+                    }
+                }
+                for (; nt < 9; nt++) { yi[nt] = -1; yc[nt] = 0.0; }
+                g.bq[kGiQ] = bp; g.id[kGiQ] = id;
+            }
+            viol_p = vmax; u_p = 0.0;
+            c.sync();
+            // ---- w = H^-1 a_p (into sm.dy) ----
+            for (int p = c.tid; p < ny; p += c.nthr) {
+                const int k = p / nyd, a = p - k * nyd;
+                const double* hr = g.Hinv + a * nyd;
+                const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+                double v = 0.0;
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    const int j = yi[t];
+                    if (j >= 0 && j / nyd == k) v += yc[t] * hr[j - k * nyd];
+                }
+                sm.dy[p] = v;
+            }
+            c.sync();
+        }
+        iters++;
+        // ---- small dense step (thread 0): r, step lengths, active-set update; t_y = A' r into sm.ax1[0..ny) ----
+        if (c.tid == 0) {
+            const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+            double apw = 0.0;
+            for (int t = 0; t < 9; t++) if (yi[t] >= 0) apw += yc[t] * sm.dy[yi[t]];
+            double ll = 0.0;
+            for (int j = 0; j < q; j++) {
+                double vj = 0.0;
+                for (int t = 0; t < 9; t++) { const int jj = g.yi[9 * j + t]; if (jj >= 0) vj += g.yc[9 * j + t] * sm.dy[jj]; }
+                g.v[j] = vj;
+                double a = vj;
+                for (int k = 0; k < j; k++) a -= g.Ls[j * (j + 1) / 2 + k] * g.l[k];
+                a /= g.Ls[j * (j + 1) / 2 + j];
+                g.l[j] = a; ll += a * a;
+            }
+            for (int j = q - 1; j >= 0; j--) {
+                double a = g.l[j];
+                for (int k = j + 1; k < q; k++) a -= g.Ls[k * (k + 1) / 2 + j] * g.r[k];
+                g.r[j] = a / g.Ls[j * (j + 1) / 2 + j];
+            }
+            const double zn = apw - ll;
+            double t1 = 1e300; int kdrop = -1;
+            for (int j = 0; j < q; j++)
+                if (g.r[j] > 0) { const double tt = g.u[j] / g.r[j]; if (tt < t1) { t1 = tt; kdrop = j; } }
+            const bool dependent = !(zn > 1e-12 * (apw > 1e-300 ? apw : 1e-300));
+            const double t2 = dependent ? 1e300 : viol_p / zn;
+            const double t = t1 < t2 ? t1 : t2;
+            double flag;             // 0: full step, new scan | 1: partial, same p | 2: infeasible | 3: give up
+            if (!(t < 1e299)) flag = 2.0;
+            else {
+                for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
+                u_p += t;
+                for (int e = 0; e < ny; e++) sm.ax1[e] = 0.0;
+                for (int j = 0; j < q; j++)
+                    for (int tt = 0; tt < 9; tt++) { const int jj = g.yi[9 * j + tt]; if (jj >= 0) sm.ax1[jj] += g.r[j] * g.yc[9 * j + tt]; }
+                if (t2 <= t1) {
+                    if (q == kGiQ) flag = 3.0;
+                    else {
+                        for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
+                        g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
+                        for (int tt = 0; tt < 9; tt++) { g.yc[9 * q + tt] = yc[tt]; g.yi[9 * q + tt] = yi[tt]; }
+                        g.bq[q] = g.bq[kGiQ]; g.id[q] = g.id[kGiQ]; g.u[q] = u_p;
+                        flag = 0.0;
+                    }
+                } else {
+                    for (int j = kdrop; j < q - 1; j++) {
+                        for (int tt = 0; tt < 9; tt++) { g.yc[9 * j + tt] = g.yc[9 * (j + 1) + tt]; g.yi[9 * j + tt] = g.yi[9 * (j + 1) + tt]; }
+                        g.bq[j] = g.bq[j + 1]; g.id[j] = g.id[j + 1]; g.u[j] = g.u[j + 1];
+                    }
+                    for (int i2 = 0, ii = 0; i2 < q; i2++) {
+                        if (i2 == kdrop) continue;
+                        for (int k2 = 0, kk = 0; k2 <= i2; k2++) {
+                            if (k2 == kdrop) continue;
+                            g.Ls[ii * (ii + 1) / 2 + kk] = g.Sm[i2 * (i2 + 1) / 2 + k2];
+                            kk++;
+                        }
+                        ii++;
+                    }
+                    for (int e = 0; e < (q - 1) * q / 2; e++) g.Sm[e] = g.Ls[e];
+                    bool okf = true;
+                    for (int j = 0; j < q - 1 && okf; j++) {
+                        double dj = g.Sm[j * (j + 1) / 2 + j];
+                        for (int k = 0; k < j; k++) dj -= g.Ls[j * (j + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
+                        if (!(dj > 0)) { okf = false; break; }
+                        dj = sqrt(dj);
+                        g.Ls[j * (j + 1) / 2 + j] = dj;
+                        for (int i2 = j + 1; i2 < q - 1; i2++) {
+                            double a = g.Sm[i2 * (i2 + 1) / 2 + j];
+                            for (int k = 0; k < j; k++) a -= g.Ls[i2 * (i2 + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
+                            g.Ls[i2 * (i2 + 1) / 2 + j] = a / dj;
+                        }
+                    }
+                    flag = okf ? 1.0 : 3.0;
+                }
+            }
+            g.ty[0] = dependent ? 0.0 : t;
+            g.ty[1] = flag;
+            g.ty[2] = zn;
+        }
+        c.sync();
+        const double tp = g.ty[0], flag = g.ty[1];
+        if (flag == 2.0) { status = kStQpMaxIter; break; }
+        if (flag == 3.0) { status = -1; break; }
+        if (tp != 0.0)
+            for (int p = c.tid; p < ny; p += c.nthr) {
+                const int k = p / nyd, a = p - k * nyd;
+                const double* hr = g.Hinv + a * nyd;
+                const double* tk = sm.ax1 + k * nyd;
+                double hz = 0.0;
+                if (q > 0 || flag == 1.0)
+                    for (int b = 0; b < nyd; b++) hz += hr[b] * tk[b];
+                sm.y[p] -= tp * (sm.dy[p] - hz);
+            }
+        if (flag == 0.0) { q++; same_p = false; }
+        else { q--; same_p = true; viol_p -= tp * g.ty[2]; }
+        c.sync();
+    }
+    map_x(c, T, sm.y, sm.cst, sm.x);
+    c.sync();
+    *iters_out = iters;
+    return status;
+}
+
+// One agent.  Returns true when the agent is finished (outputs written: optimal, or infeasible -> failsafe
+// trajectory), false when the active set gave up and the interior point must take over (nothing written).
+DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
+                         const QpSmem& sm) {
+    const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, nx = T.nx, np = T.np;
+    const int n = kP - 1;
+    const bool D3 = (D == 3);
+    QpConst qc;
+    qc.hi_v = in.max_vel; qc.hi_a = in.max_acc; qc.hi_c = 0.5 * P.comm_range - in.radius;
+    qc.wpr = 0.5 * P.comm_range - kEpsF;
+    {
+        const double ideal = v3_norm(in.goal - in.pos) / in.nominal_vel;              // traj_optimizer.cpp:543-551
+        int ts = (int)((M * P.dt - ideal + kEps) / P.dt);
+        if (ts < 1) ts = 1;
+        if (ts > M) ts = M;
+        qc.ts = ts;
+    }
+    for (int k = c.tid; k < D; k += c.nthr) {                                         // :335-352
+        const double c0 = (double)v3_get(in.pos, k);
+        const double c1 = c0 + (double)v3_get(in.vel, k) * P.dt / n;
+        const double c2 = (double)v3_get(in.acc, k) * P.dt * P.dt / (n * (n - 1)) + 2 * c1 - c0;
+        sm.cst[k * 3] = c0; sm.cst[k * 3 + 1] = c1; sm.cst[k * 3 + 2] = c2;
+    }
+    c.sync();
+    {   // unconstrained optimum y0 = -H^-1 g = Y0[ts] (c0, c1, c2, goal)
+        const double* Y = T.Y0 + (size_t)(qc.ts - 1) * nyd * 4;
+        for (int p = c.tid; p < ny; p += c.nthr) {
+            const int k = p / nyd, a = p - k * nyd;
+            const double* ya = Y + a * 4;
+            sm.y[p] = ya[0] * sm.cst[k * 3] + ya[1] * sm.cst[k * 3 + 1] + ya[2] * sm.cst[k * 3 + 2] +
+                      ya[3] * (double)v3_get(in.goal, k);
+        }
+    }
+    c.sync();
+    int iters = 0;
+    double vmax = 0.0;
+    const int status = gi_solve(c, P, T, in, qc, sm, &iters, &vmax);
+    if (status < 0) return false;
+
+    // ---- outputs: objective in x-space (constant included, like IloCplex::getObjValue :109) ----
+    const double wT = P.w_terminal, wT2 = 2.0 * P.w_terminal;
+    double obj = 0.0;
+    for (int e = c.tid; e < nx; e += c.nthr) {
+        const int k = e / npt, pt = e - k * npt;
+        const int m = pt / kP, i = pt - m * kP;
+        const double* xs = sm.x + k * npt + m * kP;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < kP; j++) v += T.Q2[i * kP + j] * xs[j];
+        obj += 0.5 * v * xs[i];
+        if (i == n && m >= M - qc.ts) {
+            const double gg = (double)v3_get(in.goal, k);
+            obj += wT * xs[n] * xs[n] - wT2 * gg * xs[n] + wT * gg * gg;
+        }
+    }
+    { double d0 = 0.0, d1 = 0.0; c.reduce3(obj, 0, d0, 0, d1, 0); }
+    if (c.tid == 0) {
+        *out.cost = obj; *out.viol = vmax > 0 ? vmax : 0.0; *out.iters = iters; *out.status |= status;
+        if (out.rows) *out.rows = 2LL * np + (long long)in.K * (npt - 3);
+    }
+    const bool ok = (status == 0);
+    for (int e = c.tid; e < npt; e += c.nthr) {
+        float* o = out.traj + e * 3;
+        if (ok) {                                                                     // :71-83
+            o[0] = (float)sm.x[e]; o[1] = (float)sm.x[npt + e];
+            o[2] = D3 ? (float)sm.x[2 * npt + e] : (float)P.z_2d;
+        } else {                                                                      // failsafe traj_planner.cpp:775-776
+            o[0] = in.init_traj[e * 3]; o[1] = in.init_traj[e * 3 + 1]; o[2] = in.init_traj[e * 3 + 2];
+        }
+    }
+    if (out.x)
+        for (int e = c.tid; e < nx; e += c.nthr) out.x[e] = sm.x[e];
+    c.sync();
+    return true;
+}
+
+}  // namespace dlsc

@@ -137,6 +137,25 @@ void build_qp_tables(int M, int D, double dt, double w_control, double w_termina
             for (int i = 0; i < nyd; i++) Hi[(size_t)i * nyd + col] = e[i];
         }
     }
+    // y0 = -H^-1 g with g = T' grad f(x(y = 0)): linear in the initial-state constants c0,c1,c2 (segment 0,
+    // points 0..2 through 2 w_u Q) and in the goal coordinate (terminal term -2 w_T goal on point n of the
+    // last ts segments)  ->  one [nyd][4] map per ts
+    T.Y0.assign((size_t)M * nyd * 4, 0.0);
+    for (int ts = 1; ts <= M; ts++) {
+        const double* Hi = T.Hinv.data() + (size_t)(ts - 1) * nyd * nyd;
+        for (int j = 0; j < 4; j++) {
+            std::vector<double> gx(T.npt, 0.0), gy(nyd, 0.0);
+            if (j < 3) { for (int i = 0; i < kP; i++) gx[i] = T.Q2[i * kP + j]; }
+            else { for (int m = M - ts; m < M; m++) gx[m * kP + n] += -2.0 * w_terminal; }
+            for (int pt = 0; pt < T.npt; pt++)
+                for (auto& t : xe[pt].t) gy[t.idx] += t.coef * gx[pt];
+            for (int a = 0; a < nyd; a++) {
+                double v = 0.0;
+                for (int b = 0; b < nyd; b++) v += Hi[(size_t)a * nyd + b] * gy[b];
+                T.Y0[((size_t)(ts - 1) * nyd + a) * 4 + j] = -v;
+            }
+        }
+    }
 
     // pair rows: (axis-local expression) replicated per axis
     struct Row { int fam, pt; Expr e; };

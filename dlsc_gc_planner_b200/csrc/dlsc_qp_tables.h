@@ -50,6 +50,7 @@ struct QpTabHost {
     double scv = 0, sca = 0;                      // velocity / acceleration row scales n/dt, n(n-1)/dt^2
     std::vector<double> H1;                       // [nyd][nyd]  2*w_u*sum_m T_m' Q T_m
     std::vector<double> Hinv;                     // [M][nyd][nyd]  inverse of the per-axis Hessian H1 + 2 w_T sum_{m >= M-ts} e e', ts = 1..M
+    std::vector<double> Y0;                       // [M][nyd][4]  unconstrained optimum of one axis: y0 = Y0[ts-1] (c0, c1, c2, goal)
     std::vector<double> Q2;                       // [6][6]      2*w_u*Q
     std::vector<double> Qb;                       // [6][6]      Q_base
 };
@@ -81,7 +82,7 @@ struct QpTab {
     int nnzw;
     int row_npl, row_bv, row_ba, row_bc;   // rows per axis, first velocity / acceleration / comm row inside an axis
     double scv, sca;                       // n/dt, n(n-1)/dt^2
-    const double *H1, *Q2, *Hinv;
+    const double *H1, *Q2, *Hinv, *Y0;
 };
 
 }  // namespace dlsc

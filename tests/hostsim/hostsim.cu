@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/dlsc_b200.h"
-#include "../../dlsc_gc_planner_b200/csrc/dlsc_qp.cuh"
+#include "../../dlsc_gc_planner_b200/csrc/dlsc_qp_gi.cuh"
 #include "../../dlsc_gc_planner_b200/csrc/dlsc_stages.cuh"
 
 using namespace dlsc;
@@ -28,7 +28,7 @@ struct dlsc_ctx {
     int seq = 0;
     std::vector<float> rec, acc, waypoint, goal_new, pred_traj, init_traj, lsc_normal, lsc_anchor_last, sfc, traj;
     std::vector<uint8_t> disturbed, sfc_init;
-    std::vector<double> radius, downwash, max_vel, max_acc, nominal_vel, lsc_d, qp_x, cost, viol, scratch, smem;
+    std::vector<double> radius, downwash, max_vel, max_acc, nominal_vel, lsc_d, qp_x, cost, viol, scratch, smem, smem_gi;
     std::vector<int32_t> nbr_idx, nbr_cnt, qp_iters, status;
     std::vector<int4> cells;
     std::vector<float> centre;
@@ -93,7 +93,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     T.wi_ptr = h.wi_ptr.data(); T.wi_row = h.wi_row.data(); T.wi_coef = h.wi_coef.data();
     T.wp_ptr = h.wp_ptr.data(); T.wp_pt = h.wp_pt.data(); T.wp_coef = h.wp_coef.data();
     T.H1 = h.H1.data(); T.Q2 = h.Q2.data(); T.tri_p = h.tri_p.data(); T.nz_e = h.nz_e.data(); T.nnzw = h.nnzw;
-    T.pr_desc = h.pr_desc.data(); T.nz_hdr = reinterpret_cast<const uint4*>(h.nz_hdr.data()); T.nz_h = h.nz_h.data(); T.Hinv = h.Hinv.data();
+    T.pr_desc = h.pr_desc.data(); T.nz_hdr = reinterpret_cast<const uint4*>(h.nz_hdr.data()); T.nz_h = h.nz_h.data(); T.Hinv = h.Hinv.data(); T.Y0 = h.Y0.data();
     {
         const int M = h.M, MP = M * kP;
         T.row_npl = h.np / h.D; T.row_bv = MP - 3; T.row_ba = T.row_bv + (M * 5 - 2); T.row_bc = T.row_ba + (M * 4 - 1);
@@ -101,6 +101,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     }
     c->scratch.assign(qp_scratch_doubles(T, P.K), 0.0);
     c->smem.assign(qp_smem_bytes(T, P.K) / 8 + 8, 0.0);
+    c->smem_gi.assign(gi_smem_doubles(T) + 8, 0.0);
     memset(&c->edt, 0, sizeof(c->edt));
     c->edt.res = hp->world_res; c->edt.inv_res = 1.0 / hp->world_res;
     *out = c;
@@ -295,7 +296,14 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             out.x = c->qp_x.data() + (size_t)la * c->T.nx;
             out.cost = &c->cost[la]; out.viol = &c->viol[la]; out.iters = &c->qp_iters[la]; out.status = &c->status[la];
             out.rows = &rows;
-            qp_agent(cta, P, c->T, in, out, sm, c->scratch.data());
+            bool done = false;
+            if (P.qp_solver != 1) {
+                QpSmem sg;
+                gi_smem_carve(c->T, c->smem_gi.data(), sg);
+                Cta cg; cg.tid = 0; cg.nthr = 1; cg.red = sg.red;
+                done = qp_agent_gi(cg, P, c->T, in, out, sg);
+            }
+            if (!done) qp_agent(cta, P, c->T, in, out, sm, c->scratch.data(), P.qp_solver != 1);
             c->counters[3] += c->qp_iters[la];
             c->counters[4] += rows;
         }
