@@ -33,21 +33,49 @@ void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_neighbours(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= P.NL) return;
-    Group g; g.lane = threadIdx.x & 31; g.width = 32; g.block = false;
-    const int cnt = neighbours_agent(g, P, S.rec, P.begin + warp, S.nbr_idx + (size_t)warp * P.K);
-    if (g.lane == 0) {
-        S.nbr_cnt[warp] = cnt < P.K ? cnt : P.K;
-        if (cnt > P.K) atomicOr(S.status + warp, kStNbrOverflow);
-        atomicAdd(S.counters + 0, (unsigned long long)(cnt < P.K ? cnt : P.K));
+// warp per agent; the 16 warps of a CTA share position tiles staged in shared memory (the positions sit inside
+// the 768-byte records: each is fetched once per CTA instead of once per warp).  Ballot compaction keeps the
+// reference's ascending neighbour order.
+constexpr int kNbrWarps = 16, kNbrTile = kNbrWarps * 32;
+__global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    __shared__ float tile[kNbrTile * 3];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int la = blockIdx.x * kNbrWarps + w;
+    const bool valid = la < P.NL;
+    const int a = P.begin + la;
+    const int off = P.M * kP * 3;
+    const V3 pa = valid ? v3_load(S.rec + (size_t)a * P.rec + off) : v3(0.f, 0.f, 0.f);
+    int32_t* idx_out = S.nbr_idx + (size_t)la * P.K;
+    int count = 0;
+    for (int base = 0; base < P.N; base += kNbrTile) {
+        const int jt = base + threadIdx.x;
+        if (jt < P.N) {
+            const float* r = S.rec + (size_t)jt * P.rec + off;
+            tile[threadIdx.x * 3] = r[0]; tile[threadIdx.x * 3 + 1] = r[1]; tile[threadIdx.x * 3 + 2] = r[2];
+        }
+        __syncthreads();
+        const int nt = (P.N - base < kNbrTile) ? P.N - base : kNbrTile;
+        if (valid)
+            for (int t = 0; t < nt; t += 32) {
+                const int j = base + t + lane;
+                bool in = false;
+                if (t + lane < nt && j != a) in = in_comm_range(P, pa, v3_load(tile + (t + lane) * 3));
+                const unsigned mask = __ballot_sync(0xffffffffu, in);
+                const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                if (in && pos < P.K) idx_out[pos] = j;
+                count += __popc(mask);
+            }
+        __syncthreads();
+    }
+    if (valid && lane == 0) {
+        S.nbr_cnt[la] = count < P.K ? count : P.K;
+        if (count > P.K) atomicOr(S.status + la, kStNbrOverflow);
+        atomicAdd(S.counters + 0, (unsigned long long)(count < P.K ? count : P.K));
     }
 }
 
 void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
-    const int warps_per_block = 8;
-    k_neighbours<<<(P.NL + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(P, S);
+    k_neighbours<<<(P.NL + kNbrWarps - 1) / kNbrWarps, kNbrTile, 0, st>>>(P, S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -115,23 +143,28 @@ void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// warp per agent: lanes over the rows of the 1-variable LP (max / any / all reductions are order-independent)
 __global__ void __launch_bounds__(128) k_goal(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    const int la = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (la >= P.NL) return;
+    Group g; g.lane = threadIdx.x & 31; g.width = 32; g.block = false;
     const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     V3 goal = v3_load(rec + npt * 3 + 6);
     const size_t pr = (size_t)la * P.K;
-    const int st = goal_agent(P, S.disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(S.waypoint + la * 3),
+    const int st = goal_agent(g, P, S.disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(S.waypoint + la * 3),
                               S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.nbr_cnt[la],
                               S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, goal);
-    v3_store(S.goal_new + la * 3, goal);     // the record keeps the previous goal until the step is published:
-                                             // the other agents' LSCs of this step must see it (broadcast semantics)
-    if (st) atomicOr(S.status + la, st);
+    if (g.lane == 0) {
+        v3_store(S.goal_new + la * 3, goal);     // the record keeps the previous goal until the step is published:
+                                                 // the other agents' LSCs of this step must see it (broadcast semantics)
+        if (st) atomicOr(S.status + la, st);
+    }
 }
 
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st) {
-    k_goal<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S);
+    const long long n = (long long)P.NL * 32;
+    k_goal<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, S);
 }
 
 __global__ void k_goal_copy(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
@@ -146,23 +179,27 @@ void launch_goal_copy(const DevParams& P, const DevState& S, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------
 // move: state := traj(dt) (AgentManager::doStep); always: record.traj := traj (prev_traj, traj_planner.cpp:57)
-__global__ void __launch_bounds__(128) k_advance(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, int move) {
-    const int la = blockIdx.x * blockDim.x + threadIdx.x;
-    if (la >= P.NL) return;
-    const int npt = P.M * kP;
+__global__ void __launch_bounds__(256) k_advance(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, int move) {
+    const int npt = P.M * kP, per = npt * 3;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.NL * per) return;
+    const int la = (int)(gid / per), e = (int)(gid - (long long)la * per);
     float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
-    const float* tr = S.traj + (size_t)la * npt * 3;
-    if (move) {
-        float st[9];
-        state_at(P, tr, P.dt, st);
-        for (int k = 0; k < 3; k++) { rec[npt * 3 + k] = st[k]; rec[npt * 3 + 3 + k] = st[3 + k]; S.acc[la * 3 + k] = st[6 + k]; }
+    const float* tr = S.traj + (size_t)la * per;
+    rec[e] = tr[e];
+    if (e == 0) {
+        if (move) {
+            float st[9];
+            state_at(P, tr, P.dt, st);
+            for (int k = 0; k < 3; k++) { rec[per + k] = st[k]; rec[per + 3 + k] = st[3 + k]; S.acc[la * 3 + k] = st[6 + k]; }
+        }
+        for (int k = 0; k < 3; k++) rec[per + 6 + k] = S.goal_new[la * 3 + k];
     }
-    for (int e = 0; e < npt * 3; e++) rec[e] = tr[e];
-    for (int k = 0; k < 3; k++) rec[npt * 3 + 6 + k] = S.goal_new[la * 3 + k];
 }
 
 void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st) {
-    k_advance<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S, move ? 1 : 0);
+    const long long n = (long long)P.NL * P.M * kP * 3;
+    k_advance<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, S, move ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

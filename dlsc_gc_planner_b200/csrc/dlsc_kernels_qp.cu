@@ -98,7 +98,7 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     L.threads = kQpThreads;
     L.smem = qp_smem_bytes(T, P.K);
     cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    L.gi_smem = gi_smem_doubles(T) * sizeof(double);
+    L.gi_smem = gi_smem_doubles(T, P.K) * sizeof(double);
     cudaFuncSetAttribute(k_qp_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
     int per_sm = 1, sms = 148;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp, kQpThreads, L.smem);

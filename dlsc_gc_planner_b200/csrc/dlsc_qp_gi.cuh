@@ -19,8 +19,8 @@
 
 namespace dlsc {
 
-DLSC_HD size_t gi_smem_doubles(const QpTab& T) {
-    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + 96;
+DLSC_HD size_t gi_smem_doubles(const QpTab& T, int Kcap) {
+    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + 96 + ((size_t)Kcap + 1) / 2;
 }
 DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     double* p = base;
@@ -29,8 +29,9 @@ DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     s.x = p; p += T.nx;
     s.cst = p; p += 16;
     s.red = p; p += 96;
+    s.off = reinterpret_cast<int*>(p);          // [Kcap] global indices of the neighbours
     s.invp = s.pan = s.rd = s.dx = s.ax2 = s.V1 = s.V2 = s.DD = s.S = nullptr;
-    s.off = nullptr; s.act = nullptr;
+    s.act = nullptr;
 }
 
 struct PairRowD { int fam, k, pa, pb; };
@@ -58,7 +59,7 @@ DLSC_HD void pair_violation(const DevParams& P, const QpTab& T, const QpIn& in, 
 // most violated row over all inequality rows; every thread returns the same (vmax, id)
 //   id < 2 np: pattern row r = id >> 1, side id & 1 (0: upper, 1: lower);  else LSC row o = id - 2 np = pt * Kcap + cc
 DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
-                     double& vmax_out, double& id_out) {
+                     const int* sm_nbr, double& vmax_out, double& id_out) {
     const int npt = T.npt, np = T.np, Kc = P.K, K = in.K;
     const bool D3 = (P.D == 3);
     double best = -1e300, best_id = 1e300;
@@ -68,16 +69,37 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
         if (vh > best) { best = vh; best_id = 2.0 * r; }
         if (vl > best) { best = vl; best_id = 2.0 * r + 1.0; }
     }
-    const int total = K * npt;
-    for (int e = c.tid; e < total; e += c.nthr) {
-        const int cc = e / npt, pt = e - cc * npt;
-        if (pt < 3) continue;                                                       // traj_optimizer.cpp:417-419
-        const int m = pt / kP;
-        if (v3_norm(v3_load(in.normal + ((size_t)cc * P.M + m) * 3)) < kEpsF) continue;    // :422-424
-        const LscRowData rw = lsc_row_data(P, in, pt, cc);
-        const double v = -(rw.n0 * x[pt] + rw.n1 * x[npt + pt] + (D3 ? rw.n2 * x[2 * npt + pt] : 0.0)) - rw.b;
-        const double id = 2.0 * np + (double)(pt * Kc + cc);
-        if (v > best || (v == best && id < best_id)) { best = v; best_id = id; }
+    // LSC rows: one work item = one (neighbour, segment) = up to 6 rows sharing a normal; its d values and
+    // anchors are contiguous in memory (traj_optimizer.cpp:412-450: -n.x <= -(n.anchor + d))
+    const int M = P.M, items = K * M;
+    for (int e = c.tid; e < items; e += c.nthr) {
+        const int cc = e / M, m = e - cc * M;
+        const float* nr = in.normal + ((size_t)cc * M + m) * 3;
+        const V3 nv = v3_load(nr);
+        const double* dd = in.d + ((size_t)cc * M + m) * kP;
+        const bool last = (m == M - 1);
+        const float* an = last ? in.anchor_last + cc * 3 : in.pred_traj + ((size_t)sm_nbr[cc] * npt + m * kP) * 3;
+        double dv[kP]; float av[kP][3];
+#pragma unroll
+        for (int i = 0; i < kP; i++) {
+            dv[i] = dd[i];
+            const float* a = last ? an : an + i * 3;
+            av[i][0] = a[0]; av[i][1] = a[1]; av[i][2] = a[2];
+        }
+        if (v3_norm(nv) < kEpsF) continue;                                          // :422-424
+        const double n0 = (double)nv.x, n1 = (double)nv.y, n2 = D3 ? (double)nv.z : 0.0;
+#pragma unroll
+        for (int i = 0; i < kP; i++) {
+            if (m == 0 && i < 3) continue;                                          // :417-419
+            const int pt = m * kP + i;
+            double b = -dv[i];                                                      // same order as lsc_row_data
+            b -= n0 * (double)av[i][0];
+            b -= n1 * (double)av[i][1];
+            if (D3) b -= n2 * (double)av[i][2];
+            const double v = -(n0 * x[pt] + n1 * x[npt + pt] + (D3 ? n2 * x[2 * npt + pt] : 0.0)) - b;
+            const double id = 2.0 * np + (double)(pt * Kc + cc);
+            if (v > best || (v == best && id < best_id)) { best = v; best_id = id; }
+        }
     }
     double vmax = best, d0 = 0.0, d1 = 0.0;
     c.reduce3(vmax, 1, d0, 0, d1, 0);
@@ -103,7 +125,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             map_x(c, T, sm.y, sm.cst, sm.x);
             c.sync();
             double vmax, idsel;
-            gi_scan(c, P, T, in, qc, sm.x, vmax, idsel);
+            gi_scan(c, P, T, in, qc, sm.x, sm.off, vmax, idsel);
             *viol_out = vmax;
             if (!(vmax > tol)) { status = 0; break; }
             if (!have_hinv) {                                   // first violated row: stage this agent's H^-1 block
@@ -298,6 +320,7 @@ DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const
         const double c2 = (double)v3_get(in.acc, k) * P.dt * P.dt / (n * (n - 1)) + 2 * c1 - c0;
         sm.cst[k * 3] = c0; sm.cst[k * 3 + 1] = c1; sm.cst[k * 3 + 2] = c2;
     }
+    for (int cc = c.tid; cc < in.K; cc += c.nthr) sm.off[cc] = in.nbr_idx[cc];
     c.sync();
     {   // unconstrained optimum y0 = -H^-1 g = Y0[ts] (c0, c1, c2, goal)
         const double* Y = T.Y0 + (size_t)(qc.ts - 1) * nyd * 4;

@@ -33,6 +33,13 @@ struct Group {
         if (block) __syncthreads(); else __syncwarp();
 #endif
     }
+    DLSC_HD double max(double v) const {         // warp mode only; order-independent, exact
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, v, o); v = (v < t) ? t : v; }
+#endif
+        return v;
+    }
     DLSC_HD unsigned ballot(bool p) const {     // warp mode only
 #ifdef __CUDA_ARCH__
         return __ballot_sync(0xffffffffu, p);
@@ -76,6 +83,10 @@ DLSC_HD void predict_point(const DevParams& P, const float* rec, int seq, int pt
 // ------------------------------------------------------------------------------------------------
 // neighbour list by Chebyshev range, ascending index (multi_sync_simulator.cpp:481-503)
 // ------------------------------------------------------------------------------------------------
+DLSC_HD bool in_comm_range(const DevParams& P, const V3& pa, const V3& pj) {
+    const double dist = linf_distance(pa, pj);
+    return !(P.comm_range > 0 && dist > P.comm_range);
+}
 DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* rec, int a_global,
                              int32_t* idx_out) {
     const int off = P.M * kP * 3;
@@ -85,8 +96,7 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
         const int j = base + g.lane;
         bool in = false;
         if (j < P.N && j != a_global) {
-            const double dist = linf_distance(pa, v3_load(rec + (size_t)j * P.rec + off));
-            in = !(P.comm_range > 0 && dist > P.comm_range);
+            in = in_comm_range(P, pa, v3_load(rec + (size_t)j * P.rec + off));
         }
         const unsigned mask = g.ballot(in);
         const int pos = count + popc_u32(mask & ((1u << g.lane) - 1u));
@@ -625,43 +635,46 @@ DLSC_HD bool goal_row(const GoalRows& R, int r, const V3& gw, const V3& wp, doub
     return true;
 }
 
-DLSC_HD int goal_agent(const DevParams& P, bool disturbed, const V3& pos, const V3& wp, const float* sfc_last,
-                       int K, const float* normal, const double* d, const float* anchor_last, V3& goal) {
+DLSC_HD int goal_agent(const Group& g, const DevParams& P, bool disturbed, const V3& pos, const V3& wp,
+                       const float* sfc_last, int K, const float* normal, const double* d, const float* anchor_last,
+                       V3& goal) {
     if (disturbed) { goal = pos; return 0; }                          // traj_planner.cpp:447-450
     if (v3_distance(goal, wp) < kEpsF) { goal = wp; return 0; }       // goal_optimizer.cpp:12-14
     const V3 gw = goal - wp;                                          // float coefficients :165
     GoalRows R; R.P = &P; R.sfc_last = sfc_last; R.K = K; R.normal = normal; R.d = d; R.anchor_last = anchor_last;
     const int nr = goal_num_rows(R);
+    // each lane keeps its rows' (a, b): one pass over memory for both the bound and the feasibility check
     double tlo = 0.0;
-    for (int r = 0; r < nr; r++) {
+    for (int r = g.lane; r < nr; r += g.width) {
         double a, b;
         if (!goal_row(R, r, gw, wp, a, b)) continue;
         if (a > 0) { const double c = -b / a; tlo = (tlo < c) ? c : tlo; }
     }
+    tlo = g.max(tlo);
     const double t = (1.0 + kEpsF < tlo) ? 1.0 + kEpsF : tlo;
-    bool feasible = true;
+    bool infeasible = false;
     const double tol = 1e-6;
-    for (int r = 0; r < nr; r++) {
+    for (int r = g.lane; r < nr; r += g.width) {
         double a, b;
         if (!goal_row(R, r, gw, wp, a, b)) continue;
-        if (a * t + b < -tol) feasible = false;
+        if (a * t + b < -tol) infeasible = true;
     }
-    if (feasible) { goal = gw * (float)t + wp; return 0; }            // :51
+    if (!g.any(infeasible)) { goal = gw * (float)t + wp; return 0; }  // :51
     // infeasible: "numerical error" rule :55-81
-    bool numerical_error = true;
+    bool not_numerical = false;
     if (P.use_sfc) {
         const Box b = box_load(sfc_last);
-        if (!point_in_box(b, goal)) numerical_error = false;
+        if (!point_in_box(b, goal)) not_numerical = true;
     }
-    for (int oi = 0; oi < K; oi++) {
+    for (int oi = g.lane; oi < K; oi += g.width) {
         const V3 nv = v3_load(normal + ((size_t)oi * P.M + (P.M - 1)) * 3);
         if (v3_norm(nv) < kEpsF) continue;
         const V3 anc = v3_load(anchor_last + oi * 3);
         const double dd = d[((size_t)oi * P.M + (P.M - 1)) * kP + (kP - 1)];
         const double delta = v3_dot(nv, goal - anc) - dd;             // :73
-        if (delta < -kEpsF) numerical_error = false;
+        if (delta < -kEpsF) not_numerical = true;
     }
-    return numerical_error ? 0 : kStGoalInfeasible;                   // keep goal :80
+    return g.any(not_numerical) ? kStGoalInfeasible : 0;              // keep goal :80
 }
 
 // ------------------------------------------------------------------------------------------------

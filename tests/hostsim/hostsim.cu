@@ -101,7 +101,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     }
     c->scratch.assign(qp_scratch_doubles(T, P.K), 0.0);
     c->smem.assign(qp_smem_bytes(T, P.K) / 8 + 8, 0.0);
-    c->smem_gi.assign(gi_smem_doubles(T) + 8, 0.0);
+    c->smem_gi.assign(gi_smem_doubles(T, P.K) + 8, 0.0);
     memset(&c->edt, 0, sizeof(c->edt));
     c->edt.res = hp->world_res; c->edt.inv_res = 1.0 / hp->world_res;
     *out = c;
@@ -259,7 +259,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             V3 goal = v3_load(rec + npt * 3 + 6);
             const size_t pr = (size_t)la * K;
-            const int st = goal_agent(P, c->disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(c->waypoint.data() + la * 3),
+            const int st = goal_agent(g, P, c->disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(c->waypoint.data() + la * 3),
                                       c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->nbr_cnt[la],
                                       c->lsc_normal.data() + pr * M * 3, c->lsc_d.data() + pr * M * kP,
                                       c->lsc_anchor_last.data() + pr * 3, goal);
