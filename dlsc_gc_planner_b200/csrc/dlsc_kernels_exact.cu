@@ -81,7 +81,7 @@ void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // thread per (agent, slot, segment): consecutive threads = consecutive segments of one pair, so a warp
 // covers ~3 pairs of the same agent (similar geometry -> similar GJK depth)
-__global__ void __launch_bounds__(128) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+__global__ void __launch_bounds__(128, 4) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     const int M = P.M, npt = M * kP;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)P.NL * P.K * M;

@@ -226,10 +226,38 @@ DLSC_HD bool vertex_blocked(const EdtDev& E, const V3& q, double margin, float h
 // reference's decision depends on that bit; the whole sequence of tests is reproduced.
 constexpr int kSfcTabMax = 96;
 constexpr int kSfcUnroll = 2;
+constexpr int kSfcZsMax = 256;
 struct alignas(16) SfcTab {
-    float q[3][kSfcTabMax];
+    float q[3][kSfcTabMax];            // record path: lattice coordinates / cells per axis
     int c[3][kSfcTabMax];
+    // mask path: per-axis entries, cached across the box tests of one expansion (keyed by the float bits of the
+    // axis' lo / hi: consecutive tests differ in one axis only)
+    alignas(16) uint32_t zm[kSfcZsMax / 4];     // per z-vertex nibble select (0x0F / 0xF0), 0 outside the box
+    int mc[3][kSfcTabMax];             // v << 3 | near << 2 | oob << 1 | s
+    uint32_t klo[3], khi[3];           // cache keys
+    int km[3];                         // entries per axis (or <= 0), -1000 = slot empty
+    int kflag[3];                      // bit 0: axis unusable (off-lattice / ambiguous), z only: bit 1 near(any), bit 2 near & oob (any)
 };
+DLSC_HD void sfc_tab_reset(const Group& g, SfcTab* t) {
+    if (g.lane < 3) t->km[g.lane] = -1000;
+    g.sync();
+}
+DLSC_HD uint32_t f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+// exact n / d for n < 2^16, 2 <= d < 2^16 with magic = floor(2^32 / d) + 1 (d == 1: magic = 0 -> n)
+DLSC_HD uint32_t fastdiv_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(0x100000000ull / d) + 1u; }
+DLSC_HD uint32_t fastdiv(uint32_t n, uint32_t magic) {
+#ifdef __CUDA_ARCH__
+    return magic ? __umulhi(n, magic) : n;
+#else
+    return magic ? (uint32_t)(((uint64_t)n * magic) >> 32) : n;
+#endif
+}
 
 DLSC_HD bool vertex_blocked_tab(const EdtDev& E, float qx, float qy, float qz, int cx, int cy, int cz,
                                 double margin, float half_res) {
@@ -267,7 +295,6 @@ DLSC_HD bool vertex_blocked_tab(const EdtDev& E, float qx, float qy, float qz, i
 // tabulated once per grid: 8 outcomes = one byte per vertex instead of a 16-byte record per test.
 // edt_vertex_mask reports any decision closer than kMaskGuard to the threshold; the mask is then not used.
 constexpr double kMaskGuard = 1e-3;
-constexpr int kSfcZsMax = 256;
 DLSC_HD int edt_mask_zs(int dims2) { return ((dims2 + 1) + 15) / 16 * 16; }
 
 DLSC_HD uint8_t edt_vertex_mask(const EdtDev& E, int vx, int vy, int vz, double margin, bool* unsafe) {
@@ -307,92 +334,135 @@ DLSC_HD uint8_t edt_vertex_mask(const EdtDev& E, int vx, int vy, int vz, double 
 struct U4 { uint32_t x, y, z, w; };
 
 // isObstacleInSFC through the vertex mask.  Returns 0 / 1, or -1 when this box cannot use the mask (a corner
-// off the lattice, ambiguous cell choice) -> the caller runs the record path.
+// off the lattice, ambiguous cell choice, oversized) -> the caller runs the record path.
 // One work item = 16 consecutive z-vertices of one (x, y) lattice column: one 16-byte load.
 // A coordinate outside the grid ("oob", e.g. z = -1e-9 under the world floor) makes the accessor return
 // dist = -1 and obstacle (0,0,0) (vertex_blocked_tab): the test is then the separable predicate
 // near_x & near_y & near_z with near = (|q - clamp(q, +-res/2)| < margin + 1e-5), evaluated per axis here.
 // Per-axis table entry: v << 3 | near << 2 | oob << 1 | s   (v = lattice index, s = v - cell in {0,1}).
 DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
-                                 int m0, int m1, int m2, SfcTab* tab, long long* lookups) {
+                                 SfcTab* tab, long long* lookups) {
     const double res = P.world_res;
     const float half_res = (float)(0.5 * res);
     const double thr = margin + kEpsF;
-    bool bad = false, nz_all = false, nz_oob = false;
-    for (int e = g.lane; e < m0 + m1 + m2; e += g.width) {
-        const int ax = (e < m0) ? 0 : (e < m0 + m1 ? 1 : 2);
-        const int i = e - (ax == 0 ? 0 : (ax == 1 ? m0 : m0 + m1));
-        const float lo = (ax == 0) ? b.lo.x : (ax == 1 ? b.lo.y : b.lo.z);
-        const float q = (float)(lo + i * res);
-        const double t = E.inv_res * (double)q;
-        const int c = (int)floor(t) - E.min_key[ax];
-        const double vr = rint(t);
-        int v = (int)vr - E.min_key[ax];
-        int s = v - c;
-        const bool oob = c < 0 || c >= E.dims[ax];
-        if (fabs(t - vr) > 1e-2 || (!oob && (s < 0 || s > 1))) bad = true;
-        if (oob) { v = 0; s = 0; }
-        const float olo = 0.f - half_res, ohi = 0.f + half_res;          // obstacle (0,0,0) +- res/2
-        const float cq = (q < olo) ? olo : (q > ohi ? ohi : q);
-        const bool near = (double)fabsf(cq - q) < thr;
-        if (ax == 2 && near) { nz_all = true; if (oob) nz_oob = true; }
-        tab->c[ax][i] = (v << 3) | (near ? 4 : 0) | (oob ? 2 : 0) | (s & 1);
+    int mm[3];
+    bool miss[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        const float lo = v3_get(b.lo, ax), hi = v3_get(b.hi, ax);
+        miss[ax] = !(tab->km[ax] != -1000 && tab->klo[ax] == f32_bits(lo) && tab->khi[ax] == f32_bits(hi));
+        mm[ax] = miss[ax] ? (int)floor(((hi - lo) + kEpsF) / res) + 1 : tab->km[ax];
     }
-    if (g.any(bad)) return -1;            // (barrier: the tables are complete)
-    nz_all = g.any(nz_all);
-    nz_oob = g.any(nz_oob);
-    const int zs = E.zs;
-    uint32_t* zm = reinterpret_cast<uint32_t*>(tab->q[0]);
-    for (int e = g.lane; e < (zs >> 2); e += g.width) zm[e] = 0u;
-    g.sync();
-    uint8_t* zb = reinterpret_cast<uint8_t*>(zm);
-    for (int i = g.lane; i < m2; i += g.width) {
-        const int ez = tab->c[2][i];
-        if (!(ez & 2)) zb[ez >> 3] = (ez & 1) ? 0xF0 : 0x0F;
+    if (mm[0] <= 0 || mm[1] <= 0 || mm[2] <= 0) return 0;
+    if (mm[0] > kSfcTabMax || mm[1] > kSfcTabMax || mm[2] > kSfcTabMax) return -1;
+    g.sync();                                           // every lane has read the keys before they change
+    if (miss[0] || miss[1] || miss[2]) {
+        const int n0 = miss[0] ? mm[0] : 0, n1 = miss[1] ? mm[1] : 0, n2 = miss[2] ? mm[2] : 0;
+        bool bad[3] = {false, false, false};
+        bool nz_all = false, nz_oob = false;
+        for (int e = g.lane; e < n0 + n1 + n2; e += g.width) {
+            const int ax = (e < n0) ? 0 : (e < n0 + n1 ? 1 : 2);
+            const int i = e - (ax == 0 ? 0 : (ax == 1 ? n0 : n0 + n1));
+            const float lo = (ax == 0) ? b.lo.x : (ax == 1 ? b.lo.y : b.lo.z);
+            const float q = (float)(lo + i * res);
+            const double t = E.inv_res * (double)q;
+            const int c = (int)floor(t) - E.min_key[ax];
+            const double vr = rint(t);
+            int v = (int)vr - E.min_key[ax];
+            int s = v - c;
+            const bool oob = c < 0 || c >= E.dims[ax];
+            if (fabs(t - vr) > 1e-2 || (!oob && (s < 0 || s > 1))) bad[ax] = true;
+            if (oob) { v = 0; s = 0; }
+            const float olo = 0.f - half_res, ohi = 0.f + half_res;          // obstacle (0,0,0) +- res/2
+            const float cq = (q < olo) ? olo : (q > ohi ? ohi : q);
+            const bool near = (double)fabsf(cq - q) < thr;
+            if (ax == 2 && near) { nz_all = true; if (oob) nz_oob = true; }
+            tab->mc[ax][i] = (v << 3) | (near ? 4 : 0) | (oob ? 2 : 0) | (s & 1);
+        }
+        const unsigned fl = (bad[0] ? 1u : 0u) | (bad[1] ? 2u : 0u) | (bad[2] ? 4u : 0u) | (nz_all ? 8u : 0u) | (nz_oob ? 16u : 0u);
+        unsigned all = 0;                               // OR over the lanes (also the barrier that completes the tables)
+#pragma unroll
+        for (int bit = 0; bit < 5; bit++) if (g.any((fl >> bit) & 1u)) all |= 1u << bit;
+        if (miss[2]) {
+            const int zs = E.zs;
+            for (int e = g.lane; e < (zs >> 2); e += g.width) tab->zm[e] = 0u;
+            g.sync();
+            uint8_t* zb = reinterpret_cast<uint8_t*>(tab->zm);
+            for (int i = g.lane; i < mm[2]; i += g.width) {
+                const int ez = tab->mc[2][i];
+                if (!(ez & 2)) zb[ez >> 3] = (ez & 1) ? 0xF0 : 0x0F;
+            }
+        }
+        if (g.lane == 0) {
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++)
+                if (miss[ax]) {
+                    tab->klo[ax] = f32_bits(v3_get(b.lo, ax)); tab->khi[ax] = f32_bits(v3_get(b.hi, ax)); tab->km[ax] = mm[ax];
+                    tab->kflag[ax] = (int)((all >> ax) & 1u) | (ax == 2 ? (int)((all >> 3) & 3u) << 1 : 0);
+                }
+        }
+        g.sync();
     }
-    g.sync();
-    int vz0 = tab->c[2][0] >> 3, vz1 = tab->c[2][m2 - 1] >> 3;
-    if (tab->c[2][0] & 2) vz0 = 0;                      // oob below: the in-grid entries start at 0 or later
-    if (tab->c[2][m2 - 1] & 2) vz1 = E.dims[2];         // oob above
+    if ((tab->kflag[0] | tab->kflag[1] | tab->kflag[2]) & 1) return -1;
+    const bool nz_all = (tab->kflag[2] & 2) != 0, nz_oob = (tab->kflag[2] & 4) != 0;
+    const int m0 = mm[0], m1 = mm[1], m2 = mm[2];
+    int vz0 = tab->mc[2][0] >> 3, vz1 = tab->mc[2][m2 - 1] >> 3;
+    if (tab->mc[2][0] & 2) vz0 = 0;                      // oob below: the in-grid entries start at 0 or later
+    if (tab->mc[2][m2 - 1] & 2) vz1 = E.dims[2];         // oob above
     const int ch0 = vz0 >> 4, nch = (vz1 >> 4) - ch0 + 1;
     const int per_x = m1 * nch, items = m0 * per_x;
-    const size_t sy = (size_t)zs, sx = (size_t)(E.dims[1] + 1) * zs;
+    const uint32_t mg_x = fastdiv_magic((uint32_t)per_x), mg_c = fastdiv_magic((uint32_t)nch);
+    const size_t sy = (size_t)E.zs, sx = (size_t)(E.dims[1] + 1) * E.zs;
+    const uint32_t* zm = tab->zm;
     if (lookups && g.lane == 0) *lookups += (long long)m0 * m1 * m2;
-    constexpr int U = 4;
-    for (int base = 0; base < items; base += g.width * U) {
+    // Most tests find nothing, so there is no early exit inside a batch: the loads of a batch are independent and
+    // stay in flight together (the serial chain of ~70 box tests per expansion is latency-bound); one vote per
+    // kVoteItems work items.
+    constexpr int U = 8, kVoteItems = 2048;
+    for (int vbase = 0; vbase < items; vbase += kVoteItems) {
+        const int vend = (vbase + kVoteItems < items) ? vbase + kVoteItems : items;
         uint32_t hit = 0;
+        for (int base = vbase; base < vend; base += g.width * U) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int idx = base + u * g.width + g.lane;
-            if (idx < items) {
-                const int ix = idx / per_x, r = idx - ix * per_x;
-                const int iy = r / nch, ch = ch0 + (r - iy * nch);
-                const int ex = tab->c[0][ix], ey = tab->c[1][iy];
-                const bool near_xy = (ex & ey & 4) != 0;
-                if ((ex | ey) & 2) {
-                    if (near_xy && nz_all) hit |= 1u;       // whole column outside the grid
-                } else {
-                    const uint8_t* p = E.vmask + (size_t)(ex >> 3) * sx + (size_t)(ey >> 3) * sy + (size_t)ch * 16;
+            for (int u = 0; u < U; u++) {
+                const int idx = base + u * g.width + g.lane;
+                if (idx < vend) {
+                    const int ix = (int)fastdiv((uint32_t)idx, mg_x), r = idx - ix * per_x;
+                    const int iy = (int)fastdiv((uint32_t)r, mg_c), ch = ch0 + (r - iy * nch);
+                    const int ex = tab->mc[0][ix], ey = tab->mc[1][iy];
+                    const bool near_xy = (ex & ey & 4) != 0;
+                    if ((ex | ey) & 2) {
+                        if (near_xy && nz_all) hit |= 1u;       // whole column outside the grid
+                    } else {
+                        const uint8_t* p = E.vmask + (size_t)(ex >> 3) * sx + (size_t)(ey >> 3) * sy + (size_t)ch * 16;
 #ifdef __CUDA_ARCH__
-                    const uint4 B = __ldg(reinterpret_cast<const uint4*>(p));
+                        const uint4 B = __ldg(reinterpret_cast<const uint4*>(p));
 #else
-                    U4 B; memcpy(&B, p, 16);
+                        U4 B; memcpy(&B, p, 16);
 #endif
-                    const uint32_t* z4 = zm + ch * 4;
-                    const uint32_t sel = 0x11111111u << ((ex & 1) | ((ey & 1) << 1));
-                    hit |= ((B.x & z4[0]) | (B.y & z4[1]) | (B.z & z4[2]) | (B.w & z4[3])) & sel;
-                    if (near_xy && nz_oob) hit |= 1u;       // the column's out-of-grid z entries
+                        const uint32_t* z4 = zm + ch * 4;
+                        const uint32_t sel = 0x11111111u << ((ex & 1) | ((ey & 1) << 1));
+                        hit |= ((B.x & z4[0]) | (B.y & z4[1]) | (B.z & z4[2]) | (B.w & z4[3])) & sel;
+                        if (near_xy && nz_oob) hit |= 1u;       // the column's out-of-grid z entries
+                    }
                 }
             }
         }
         if (g.any(hit != 0)) return 1;
     }
-    g.sync();
     return 0;
 }
 
 DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
                              SfcTab* tab, long long* lookups) {
+    // lookups: [0] lattice vertices of the tested boxes, [1] box tests through the vertex mask, [2] through the records
+    if (E.vmask && margin == E.mask_margin && E.zs <= kSfcZsMax) {
+        const int r = obstacle_in_box_mask(g, P, E, b, margin, tab, lookups);
+        if (r >= 0) {
+            if (lookups && g.lane == 0) lookups[1] += 1;
+            return r != 0;
+        }
+    }
     const double res = P.world_res;
     const float half_res = (float)(0.5 * res);
     const int m0 = (int)floor(((b.hi.x - b.lo.x) + kEpsF) / res) + 1;
@@ -400,14 +470,6 @@ DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E
     const int m2 = (int)floor(((b.hi.z - b.lo.z) + kEpsF) / res) + 1;
     if (m0 <= 0 || m1 <= 0 || m2 <= 0) return false;
     const int total = m0 * m1 * m2;
-    // lookups: [0] lattice vertices of the tested boxes, [1] box tests through the vertex mask, [2] through the records
-    if (E.vmask && margin == E.mask_margin && m0 <= kSfcTabMax && m1 <= kSfcTabMax && m2 <= kSfcTabMax) {
-        const int r = obstacle_in_box_mask(g, P, E, b, margin, m0, m1, m2, tab, lookups);
-        if (r >= 0) {
-            if (lookups && g.lane == 0) lookups[1] += 1;
-            return r != 0;
-        }
-    }
     if (lookups && g.lane == 0) lookups[2] += 1;
     if (m0 > kSfcTabMax || m1 > kSfcTabMax || m2 > kSfcTabMax) {
         // oversized box: direct evaluation
@@ -535,6 +597,7 @@ DLSC_HD int sfc_agent(const Group& g, const DevParams& P, const EdtDev& E, bool 
     const int M = P.M;
     const double res = P.world_res;
     int status = 0;
+    sfc_tab_reset(g, memo);
     if (init) {
         Box b;
         for (int k = 0; k < 3; k++) {
