@@ -79,16 +79,20 @@ void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// thread per (agent, slot, segment): consecutive threads = consecutive segments of one pair, so a warp
-// covers ~3 pairs of the same agent (similar geometry -> similar GJK depth)
+// thread per (agent, slot, segment).  The item space is split so that warps are homogeneous: first every GJK
+// item (segments 0..M-2; consecutive threads = consecutive segments of one pair, a warp covers ~3.5 pairs of
+// the same agent -> similar geometry, similar GJK depth), then every last-segment item (segment-segment
+// closest points, a different code path).
 __global__ void __launch_bounds__(128, 4) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     const int M = P.M, npt = M * kP;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)P.NL * P.K * M;
+    const long long n_gjk = (long long)P.NL * P.K * (M - 1);
+    const long long total = n_gjk + (long long)P.NL * P.K;
     int it = 0;
     if (gid < total) {
-        const int m = (int)(gid % M);
-        const long long pr = gid / M;
+        int m; long long pr;
+        if (gid < n_gjk) { m = (int)(gid % (M - 1)); pr = gid / (M - 1); }
+        else { m = M - 1; pr = gid - n_gjk; }
         const int c = (int)(pr % P.K), la = (int)(pr / P.K);
         if (c < S.nbr_cnt[la]) {
             const int j = S.nbr_idx[(size_t)la * P.K + c];
@@ -114,8 +118,11 @@ void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
 // one warp per agent: the greedy control flow is replicated in every lane (uniform), the lattice columns of
 // a box test are spread over the lanes (one 16-byte load of the vertex mask = 16 vertices) and combined with
 // a warp vote.  4096 agents = 4096 warps: the whole swarm is resident in one wave.
+#ifndef DLSC_SFC_MINB
+#define DLSC_SFC_MINB 8
+#endif
 constexpr int kSfcWarps = 4;
-__global__ void __launch_bounds__(kSfcWarps * 32, 8) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+__global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ SfcTab tabs[kSfcWarps];
     const int w = threadIdx.x >> 5;
     const int la = blockIdx.x * kSfcWarps + w;

@@ -8,7 +8,7 @@ namespace dlsc {
 
 constexpr int kQpThreads = 128;     // interior-point fallback kernel
 #ifndef DLSC_GI_THREADS
-#define DLSC_GI_THREADS 64
+#define DLSC_GI_THREADS 128
 #endif
 constexpr int kGiThreads = DLSC_GI_THREADS;
 

@@ -33,6 +33,16 @@ struct Group {
         if (block) __syncthreads(); else __syncwarp();
 #endif
     }
+    DLSC_HD unsigned reduce_or(unsigned v) const {   // OR over the group, every member gets the result (+ barrier)
+#ifdef __CUDA_ARCH__
+        if (!block) return __reduce_or_sync(0xffffffffu, v);
+        unsigned r = 0;
+        for (int bit = 0; bit < 8; bit++) if (__syncthreads_or((v >> bit) & 1u)) r |= 1u << bit;
+        return r;
+#else
+        return v;
+#endif
+    }
     DLSC_HD double max(double v) const {         // warp mode only; order-independent, exact
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -250,7 +260,13 @@ DLSC_HD uint32_t f32_bits(float f) {
 #endif
 }
 // exact n / d for n < 2^16, 2 <= d < 2^16 with magic = floor(2^32 / d) + 1 (d == 1: magic = 0 -> n)
-DLSC_HD uint32_t fastdiv_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(0x100000000ull / d) + 1u; }
+// (32-bit arithmetic: floor(2^32 / d) = floor((2^32 - 1) / d) unless d is a power of two, where the smaller
+// magic 2^32 / d is exact as well)
+DLSC_HD uint32_t fastdiv_magic(uint32_t d) {
+    if (d <= 1) return 0u;
+    const uint32_t q = 0xffffffffu / d;
+    return q + 1u;
+}
 DLSC_HD uint32_t fastdiv(uint32_t n, uint32_t magic) {
 #ifdef __CUDA_ARCH__
     return magic ? __umulhi(n, magic) : n;
@@ -351,7 +367,8 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
     for (int ax = 0; ax < 3; ax++) {
         const float lo = v3_get(b.lo, ax), hi = v3_get(b.hi, ax);
         miss[ax] = !(tab->km[ax] != -1000 && tab->klo[ax] == f32_bits(lo) && tab->khi[ax] == f32_bits(hi));
-        mm[ax] = miss[ax] ? (int)floor(((hi - lo) + kEpsF) / res) + 1 : tab->km[ax];
+        if (miss[ax]) mm[ax] = (int)floor(((hi - lo) + kEpsF) / res) + 1;
+        else mm[ax] = tab->km[ax];
     }
     if (mm[0] <= 0 || mm[1] <= 0 || mm[2] <= 0) return 0;
     if (mm[0] > kSfcTabMax || mm[1] > kSfcTabMax || mm[2] > kSfcTabMax) return -1;
@@ -380,9 +397,7 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
             tab->mc[ax][i] = (v << 3) | (near ? 4 : 0) | (oob ? 2 : 0) | (s & 1);
         }
         const unsigned fl = (bad[0] ? 1u : 0u) | (bad[1] ? 2u : 0u) | (bad[2] ? 4u : 0u) | (nz_all ? 8u : 0u) | (nz_oob ? 16u : 0u);
-        unsigned all = 0;                               // OR over the lanes (also the barrier that completes the tables)
-#pragma unroll
-        for (int bit = 0; bit < 5; bit++) if (g.any((fl >> bit) & 1u)) all |= 1u << bit;
+        const unsigned all = g.reduce_or(fl);           // OR over the lanes (also the barrier that completes the tables)
         if (miss[2]) {
             const int zs = E.zs;
             for (int e = g.lane; e < (zs >> 2); e += g.width) tab->zm[e] = 0u;
