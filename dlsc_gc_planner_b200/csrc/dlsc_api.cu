@@ -36,6 +36,7 @@ struct dlsc_ctx {
     bool have_edt = false;
     int4* edt_cells = nullptr;
     float* edt_centre = nullptr;
+    int32_t* edt_sat = nullptr;        // summed-area table over the flagged mask vertices
     uint8_t* edt_mask = nullptr;       // lattice-vertex mask of the SFC vertex test (built lazily for margin_host)
     bool mask_dirty = false;
     double margin_host = 0.0;          // radius of the first local agent (all BASELINE missions: 0.15 for every agent)
@@ -229,6 +230,7 @@ void dlsc_destroy(dlsc_ctx* c) {
     if (c->edt_cells) cudaFree(c->edt_cells);
     if (c->edt_centre) cudaFree(c->edt_centre);
     if (c->edt_mask) cudaFree(c->edt_mask);
+    if (c->edt_sat) cudaFree(c->edt_sat);
     for (auto& e : c->evpool) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -286,6 +288,8 @@ static int build_vertex_mask(dlsc_ctx* c) {
     EdtDev& E = c->S.edt;
     c->mask_dirty = false;
     if (c->edt_mask) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_mask); c->edt_mask = nullptr; }
+    if (c->edt_sat) { cudaFree(c->edt_sat); c->edt_sat = nullptr; }
+    E.sat = nullptr;
     E.vmask = nullptr; E.zs = edt_mask_zs(E.dims[2]); E.mask_margin = c->margin_host;
     const char* env = getenv("DLSC_SFC_MASK");
     if ((env && env[0] == '0') || E.zs > kSfcZsMax || !E.cells) return 0;
@@ -302,6 +306,17 @@ static int build_vertex_mask(dlsc_ctx* c) {
     cudaFree(d_unsafe);
     if (unsafe) { cudaFree(c->edt_mask); c->edt_mask = nullptr; }
     E.vmask = c->edt_mask;
+    const char* env_sat = getenv("DLSC_SFC_SAT");
+    if (E.vmask && !(env_sat && env_sat[0] == '0')) {
+        const size_t ns = (size_t)(E.dims[0] + 2) * (E.dims[1] + 2) * (E.dims[2] + 2);
+        if (ns < (size_t)1 << 31) {
+            CK(cudaMalloc(&c->edt_sat, ns * sizeof(int32_t)));
+            launch_sat_build(E, c->edt_sat, c->stream);
+            c->launches += 4;
+            CK(cudaStreamSynchronize(c->stream));
+            E.sat = c->edt_sat;
+        }
+    }
     CK(cudaGetLastError());
     return 0;
 }

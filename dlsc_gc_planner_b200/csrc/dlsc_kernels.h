@@ -50,6 +50,7 @@ void launch_goal_copy(const DevParams& P, const DevState& S, cudaStream_t st);  
 void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st);
 void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st);
 void launch_edt_mask(const EdtDev& E, double margin, uint8_t* mask, int* unsafe, cudaStream_t st);
+void launch_sat_build(const EdtDev& E, int32_t* sat, cudaStream_t st);   // 4 launches
 void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
 

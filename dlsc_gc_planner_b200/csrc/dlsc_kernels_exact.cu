@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __g
     const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     const bool init = S.sfc_init[la] != 0 || S.disturbed[la] != 0;       // traj_planner.cpp:439, 693-695
-    long long look[3] = {0, 0, 0};
+    long long look[4] = {0, 0, 0, 0};
     const int st = sfc_agent(g, P, S.edt, init, v3_load(rec + npt * 3), S.init_traj + (size_t)la * npt * 3,
                              v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3), S.radius[la],
                              S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &tabs[w], look);
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __g
         atomicAdd(S.counters + 2, (unsigned long long)tot);
         if (look[1]) atomicAdd(S.counters + 5, (unsigned long long)look[1]);
         if (look[2]) atomicAdd(S.counters + 6, (unsigned long long)look[2]);
+        if (look[3]) atomicAdd(S.counters + 7, (unsigned long long)look[3]);
     }
 }
 
@@ -240,6 +241,36 @@ __global__ void __launch_bounds__(256) k_edt_mask(const __grid_constant__ EdtDev
 void launch_edt_mask(const EdtDev& E, double margin, uint8_t* mask, int* unsafe, cudaStream_t st) {
     const size_t n = (size_t)(E.dims[0] + 1) * (E.dims[1] + 1) * E.zs;
     k_edt_mask<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, margin, mask, unsafe);
+}
+
+// summed-area table over the flagged lattice vertices (dlsc_stages.cuh sat_indicator): indicator, then one
+// running-sum pass per axis (thread per line; lines of the y / x passes are coalesced across threads)
+__global__ void __launch_bounds__(256) k_sat_init(const __grid_constant__ EdtDev E, int32_t* sat) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = E.dims[1] + 2, n2 = E.dims[2] + 2;
+    const size_t n = (size_t)(E.dims[0] + 2) * n1 * n2;
+    if (i >= n) return;
+    const int k = (int)(i % n2);
+    const size_t t = i / n2;
+    const int j = (int)(t % n1), ii = (int)(t / n1);
+    sat[i] = (ii > 0 && j > 0 && k > 0) ? sat_indicator(E, ii - 1, j - 1, k - 1) : 0;
+}
+__global__ void __launch_bounds__(256) k_sat_scan(const __grid_constant__ EdtDev E, int32_t* sat, int axis) {
+    const int n0 = E.dims[0] + 2, n1 = E.dims[1] + 2, n2 = E.dims[2] + 2;
+    const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t base, stride; int len;
+    if (axis == 2) { if (line >= (size_t)n0 * n1) return; base = line * n2; stride = 1; len = n2; }
+    else if (axis == 1) { if (line >= (size_t)n0 * n2) return; base = (line / n2) * n1 * n2 + line % n2; stride = n2; len = n1; }
+    else { if (line >= (size_t)n1 * n2) return; base = line; stride = (size_t)n1 * n2; len = n0; }
+    int acc = 0;
+    for (int t = 0; t < len; t++) { acc += sat[base + t * stride]; sat[base + t * stride] = acc; }
+}
+void launch_sat_build(const EdtDev& E, int32_t* sat, cudaStream_t st) {
+    const size_t n0 = E.dims[0] + 2, n1 = E.dims[1] + 2, n2 = E.dims[2] + 2, n = n0 * n1 * n2;
+    k_sat_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, sat);
+    k_sat_scan<<<(unsigned)((n0 * n1 + 255) / 256), 256, 0, st>>>(E, sat, 2);
+    k_sat_scan<<<(unsigned)((n0 * n2 + 255) / 256), 256, 0, st>>>(E, sat, 1);
+    k_sat_scan<<<(unsigned)((n1 * n2 + 255) / 256), 256, 0, st>>>(E, sat, 0);
 }
 
 // LSC anchors in the reference layout [NL][K][M][P][3]: predicted control points, or the segment-case

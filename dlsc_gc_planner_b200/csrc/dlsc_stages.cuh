@@ -244,12 +244,16 @@ struct alignas(16) SfcTab {
     // axis' lo / hi: consecutive tests differ in one axis only)
     alignas(16) uint32_t zm[kSfcZsMax / 4];     // per z-vertex nibble select (0x0F / 0xF0), 0 outside the box
     int mc[3][kSfcTabMax];             // v << 3 | near << 2 | oob << 1 | s
-    uint32_t klo[3], khi[3];           // cache keys
-    int km[3];                         // entries per axis (or <= 0), -1000 = slot empty
+    uint32_t klo[3], khi[3];           // keys of the per-axis scalars km / kv
+    int km[3];                         // vertices per axis (or <= 0), -1000 = slot empty
+    int kv[3];                         // lattice index of the first vertex (relative to min_key); kNoLattice = off-lattice
+    uint32_t tlo[3], thi[3];           // keys of the table content mc[ax] / zm
+    int tm[3];                         // entries in mc[ax], -1000 = table empty
     int kflag[3];                      // bit 0: axis unusable (off-lattice / ambiguous), z only: bit 1 near(any), bit 2 near & oob (any)
 };
+constexpr int kNoLattice = -(1 << 30);
 DLSC_HD void sfc_tab_reset(const Group& g, SfcTab* t) {
-    if (g.lane < 3) t->km[g.lane] = -1000;
+    if (g.lane < 3) { t->km[g.lane] = -1000; t->tm[g.lane] = -1000; }
     g.sync();
 }
 DLSC_HD uint32_t f32_bits(float f) {
@@ -349,6 +353,45 @@ DLSC_HD uint8_t edt_vertex_mask(const EdtDev& E, int vx, int vy, int vz, double 
 
 struct U4 { uint32_t x, y, z, w; };
 
+// ---- summed-area table over "mask byte != 0" ---------------------------------------------------
+// sat[i][j][k] = number of flagged lattice vertices with vx < i, vy < j, vz < k   (dims (nv+1) per axis,
+// nv = dims+1 vertices).  A vertex is flagged when any of its 8 cell choices is blocked, or when it lies on
+// the outermost vertex layer of the grid close to the world origin: there a cell choice can fall outside
+// the grid, where the accessor's error return makes (0,0,0) the "closest obstacle" (see obstacle_in_box_mask).
+DLSC_HD size_t sat_index(const EdtDev& E, int i, int j, int k) {
+    return ((size_t)i * (E.dims[1] + 2) + j) * (E.dims[2] + 2) + k;
+}
+DLSC_HD int sat_indicator(const EdtDev& E, int vx, int vy, int vz) {
+    if (E.vmask[((size_t)vx * (E.dims[1] + 1) + vy) * E.zs + vz]) return 1;
+    const bool edge = vx == 0 || vx == E.dims[0] || vy == 0 || vy == E.dims[1] || vz == 0 || vz == E.dims[2];
+    if (!edge) return 0;
+    const double lim = 0.5 + 3.0 * E.res;                  // generous: the predicate needs |coordinate| < res/2 + margin
+    const double x = (double)(vx + E.min_key[0]) * E.res, y = (double)(vy + E.min_key[1]) * E.res,
+                 z = (double)(vz + E.min_key[2]) * E.res;
+    return (fabs(x) <= lim && fabs(y) <= lim && fabs(z) <= lim) ? 1 : 0;
+}
+// flagged vertices in the inclusive lattice range; lanes 0..7 fetch one corner each
+DLSC_HD int sat_count(const Group& g, const EdtDev& E, int x0, int x1, int y0, int y1, int z0, int z1) {
+#ifdef __CUDA_ARCH__
+    if (!g.block) {
+        int v = 0;
+        if (g.lane < 8) {
+            const int i = (g.lane & 1) ? x0 : x1 + 1, j = (g.lane & 2) ? y0 : y1 + 1, k = (g.lane & 4) ? z0 : z1 + 1;
+            const int t = __ldg(E.sat + sat_index(E, i, j, k));
+            v = (__popc(g.lane) & 1) ? -t : t;
+        }
+        return __reduce_add_sync(0xffffffffu, v);
+    }
+#endif
+    int s = 0;
+    for (int c = 0; c < 8; c++) {
+        const int i = (c & 1) ? x0 : x1 + 1, j = (c & 2) ? y0 : y1 + 1, k = (c & 4) ? z0 : z1 + 1;
+        const int t = E.sat[sat_index(E, i, j, k)];
+        s += (popc_u32((unsigned)c) & 1) ? -t : t;
+    }
+    return s;
+}
+
 // isObstacleInSFC through the vertex mask.  Returns 0 / 1, or -1 when this box cannot use the mask (a corner
 // off the lattice, ambiguous cell choice, oversized) -> the caller runs the record path.
 // One work item = 16 consecutive z-vertices of one (x, y) lattice column: one 16-byte load.
@@ -361,19 +404,50 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
     const double res = P.world_res;
     const float half_res = (float)(0.5 * res);
     const double thr = margin + kEpsF;
-    int mm[3];
-    bool miss[3];
+    // ---- per-axis scalars (vertex count, first lattice index), cached: consecutive tests differ in one axis ----
+    int mm[3], vv[3];
+    bool smiss = false;
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
         const float lo = v3_get(b.lo, ax), hi = v3_get(b.hi, ax);
-        miss[ax] = !(tab->km[ax] != -1000 && tab->klo[ax] == f32_bits(lo) && tab->khi[ax] == f32_bits(hi));
-        if (miss[ax]) mm[ax] = (int)floor(((hi - lo) + kEpsF) / res) + 1;
-        else mm[ax] = tab->km[ax];
+        if (tab->km[ax] != -1000 && tab->klo[ax] == f32_bits(lo) && tab->khi[ax] == f32_bits(hi)) {
+            mm[ax] = tab->km[ax]; vv[ax] = tab->kv[ax];
+        } else {
+            smiss = true;
+            mm[ax] = (int)floor(((hi - lo) + kEpsF) / res) + 1;
+            const double t = E.inv_res * (double)lo, vr = rint(t);
+            vv[ax] = (fabs(t - vr) > 1e-2) ? kNoLattice : (int)vr - E.min_key[ax];
+        }
+    }
+    if (smiss) {
+        g.sync();                                       // every lane has read the old keys
+        if (g.lane < 3) {
+            const int ax = g.lane;
+            tab->klo[ax] = f32_bits(v3_get(b.lo, ax)); tab->khi[ax] = f32_bits(v3_get(b.hi, ax));
+            tab->km[ax] = (ax == 0) ? mm[0] : (ax == 1 ? mm[1] : mm[2]);
+            tab->kv[ax] = (ax == 0) ? vv[0] : (ax == 1 ? vv[1] : vv[2]);
+        }
+        g.sync();
     }
     if (mm[0] <= 0 || mm[1] <= 0 || mm[2] <= 0) return 0;
     if (mm[0] > kSfcTabMax || mm[1] > kSfcTabMax || mm[2] > kSfcTabMax) return -1;
-    g.sync();                                           // every lane has read the keys before they change
+    if (lookups && g.lane == 0) *lookups += (long long)mm[0] * mm[1] * mm[2];
+    // ---- O(1) emptiness query: the summed-area table counts the lattice vertices whose mask byte is non-zero
+    //      (any cell choice blocked); a box whose vertex range holds none is free whatever the float bits say ----
+    if (E.sat && vv[0] >= 0 && vv[1] >= 0 && vv[2] >= 0 && vv[0] + mm[0] - 1 <= E.dims[0] &&
+        vv[1] + mm[1] - 1 <= E.dims[1] && vv[2] + mm[2] - 1 <= E.dims[2]) {
+        if (sat_count(g, E, vv[0], vv[0] + mm[0] - 1, vv[1], vv[1] + mm[1] - 1, vv[2], vv[2] + mm[2] - 1) == 0) {
+            if (lookups && g.lane == 0) lookups[3] += 1;
+            return 0;
+        }
+    }
+    // ---- exact path: per-axis entry tables (rebuilt for the axes whose table is stale) ----
+    bool miss[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++)
+        miss[ax] = !(tab->tm[ax] != -1000 && tab->tlo[ax] == f32_bits(v3_get(b.lo, ax)) && tab->thi[ax] == f32_bits(v3_get(b.hi, ax)));
     if (miss[0] || miss[1] || miss[2]) {
+        g.sync();
         const int n0 = miss[0] ? mm[0] : 0, n1 = miss[1] ? mm[1] : 0, n2 = miss[2] ? mm[2] : 0;
         bool bad[3] = {false, false, false};
         bool nz_all = false, nz_oob = false;
@@ -412,7 +486,7 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
 #pragma unroll
             for (int ax = 0; ax < 3; ax++)
                 if (miss[ax]) {
-                    tab->klo[ax] = f32_bits(v3_get(b.lo, ax)); tab->khi[ax] = f32_bits(v3_get(b.hi, ax)); tab->km[ax] = mm[ax];
+                    tab->tlo[ax] = f32_bits(v3_get(b.lo, ax)); tab->thi[ax] = f32_bits(v3_get(b.hi, ax)); tab->tm[ax] = mm[ax];
                     tab->kflag[ax] = (int)((all >> ax) & 1u) | (ax == 2 ? (int)((all >> 3) & 3u) << 1 : 0);
                 }
         }
@@ -429,7 +503,6 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
     const uint32_t mg_x = fastdiv_magic((uint32_t)per_x), mg_c = fastdiv_magic((uint32_t)nch);
     const size_t sy = (size_t)E.zs, sx = (size_t)(E.dims[1] + 1) * E.zs;
     const uint32_t* zm = tab->zm;
-    if (lookups && g.lane == 0) *lookups += (long long)m0 * m1 * m2;
     // Most tests find nothing, so there is no early exit inside a batch: the loads of a batch are independent and
     // stay in flight together (the serial chain of ~70 box tests per expansion is latency-bound); one vote per
     // kVoteItems work items.

@@ -49,6 +49,7 @@ struct EdtDev {
     // the isObstacleInSFC vertex test when the vertex coordinate falls into cell v - (s&1, s>>1&1, s>>2).
     // Layout [dims0+1][dims1+1][zs], zs = dims2+1 rounded up to 16.  nullptr = not built / not usable.
     const uint8_t* vmask;
+    const int32_t* sat;          // summed-area table over "mask byte != 0" [(dims0+2)][(dims1+2)][(dims2+2)], or nullptr
     int zs;
     double mask_margin;          // the margin (agent radius) the mask was built for
 };

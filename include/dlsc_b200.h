@@ -196,7 +196,8 @@ int dlsc_get_timings(dlsc_ctx* ctx, double ms[DLSC_N_STAGES], int* n_steps);
 int64_t dlsc_launch_count(const dlsc_ctx* ctx);
 /* work counters of the last step summed over the local block (for roofline arithmetic):
  * [0] neighbour pairs, [1] GJK iterations, [2] lattice vertices of the tested SFC boxes, [3] QP iterations,
- * [4] QP rows, [5] SFC box tests answered from the lattice-vertex mask, [6] from the 16-byte EDT records */
+ * [4] QP rows, [5] SFC box tests answered from the lattice-vertex mask, [6] from the 16-byte EDT records,
+ * [7] of [5]: answered "free" by the O(1) summed-area query alone */
 int dlsc_get_counters(dlsc_ctx* ctx, int64_t counters[8]);
 
 /* Waypoints already resident on the device ([n_local][3] float32): stream-ordered device copy. */

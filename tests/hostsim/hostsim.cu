@@ -33,6 +33,7 @@ struct dlsc_ctx {
     std::vector<int4> cells;
     std::vector<float> centre;
     std::vector<uint8_t> vmask;
+    std::vector<int32_t> sat;
     bool mask_dirty = false;
     EdtDev edt;
     bool have_edt = false;
@@ -133,7 +134,7 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
 static void build_vertex_mask(dlsc_ctx* c) {
     EdtDev& E = c->edt;
     c->mask_dirty = false;
-    E.vmask = nullptr; E.zs = edt_mask_zs(E.dims[2]); E.mask_margin = c->radius.empty() ? 0.0 : c->radius[0];
+    E.vmask = nullptr; E.sat = nullptr; E.zs = edt_mask_zs(E.dims[2]); E.mask_margin = c->radius.empty() ? 0.0 : c->radius[0];
     const char* env = getenv("DLSC_SFC_MASK");
     if ((env && env[0] == '0') || E.zs > kSfcZsMax || !E.cells) return;
     c->vmask.assign((size_t)(E.dims[0] + 1) * (E.dims[1] + 1) * E.zs, 0);
@@ -142,7 +143,23 @@ static void build_vertex_mask(dlsc_ctx* c) {
         for (int vy = 0; vy <= E.dims[1]; vy++)
             for (int vz = 0; vz <= E.dims[2]; vz++)
                 c->vmask[((size_t)vx * (E.dims[1] + 1) + vy) * E.zs + vz] = edt_vertex_mask(E, vx, vy, vz, E.mask_margin, &unsafe);
-    if (!unsafe) E.vmask = c->vmask.data();
+    if (unsafe) return;
+    E.vmask = c->vmask.data();
+    const char* env_sat = getenv("DLSC_SFC_SAT");
+    if (env_sat && env_sat[0] == '0') return;
+    const int n0 = E.dims[0] + 2, n1 = E.dims[1] + 2, n2 = E.dims[2] + 2;
+    c->sat.assign((size_t)n0 * n1 * n2, 0);
+    for (int i = 1; i < n0; i++)
+        for (int j = 1; j < n1; j++)
+            for (int k = 1; k < n2; k++) c->sat[sat_index(E, i, j, k)] = sat_indicator(E, i - 1, j - 1, k - 1);
+    for (int axis = 2; axis >= 0; axis--)
+        for (int i = 0; i < n0; i++)
+            for (int j = 0; j < n1; j++)
+                for (int k = 0; k < n2; k++) {
+                    const int pi = i - (axis == 0), pj = j - (axis == 1), pk = k - (axis == 2);
+                    if (pi >= 0 && pj >= 0 && pk >= 0) c->sat[sat_index(E, i, j, k)] += c->sat[sat_index(E, pi, pj, pk)];
+                }
+    E.sat = c->sat.data();
 }
 
 int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
@@ -245,14 +262,14 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
         for (int la = 0; la < P.NL; la++) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             const bool init = c->sfc_init[la] != 0 || c->disturbed[la] != 0;
-            long long lookups[3] = {0, 0, 0};
+            long long lookups[4] = {0, 0, 0, 0};
             SfcTab memo;
             const int st = sfc_agent(g, P, c->edt, init, v3_load(rec + npt * 3), c->init_traj.data() + (size_t)la * npt * 3,
                                      v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3), c->radius[la],
                                      c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &memo, lookups);
             c->sfc_init[la] = 0;
             c->status[la] |= st;
-            c->counters[2] += lookups[0]; c->counters[5] += lookups[1]; c->counters[6] += lookups[2];
+            c->counters[2] += lookups[0]; c->counters[5] += lookups[1]; c->counters[6] += lookups[2]; c->counters[7] += lookups[3];
         }
     if (mask & DLSC_STAGE_GOAL)
         for (int la = 0; la < P.NL; la++) {
