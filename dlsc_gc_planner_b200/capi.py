@@ -280,10 +280,10 @@ class SwarmPlanner:
         return normal, anchor, d
 
     def counters(self):
-        out = np.zeros(8, np.int64)
+        out = np.zeros(16, np.int64)
         self._ck(self.lib.dlsc_get_counters(self.ctx, _p(out)))
         return dict(pairs=int(out[0]), gjk_iters=int(out[1]), edt_lookups=int(out[2]), qp_iters=int(out[3]),
-                    qp_rows=int(out[4]), sfc_tests_mask=int(out[5]), sfc_tests_records=int(out[6]), sfc_tests_sat=int(out[7]))
+                    qp_rows=int(out[4]), sfc_tests_mask=int(out[5]), sfc_tests_records=int(out[6]), sfc_tests_sat=int(out[7]), sfc_vertices_alg=int(out[8]))
 
     def enable_timing(self, on=True):
         self._ck(self.lib.dlsc_enable_timing(self.ctx, int(on)))

@@ -201,7 +201,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.qp_x, NL * (size_t)hp->dim * npt);
     rc |= dev_alloc(c, &S.cost, NL); rc |= dev_alloc(c, &S.viol, NL);
     rc |= dev_alloc(c, &S.qp_iters, NL); rc |= dev_alloc(c, &S.status, NL);
-    rc |= dev_alloc(c, &S.counters, 8);
+    rc |= dev_alloc(c, &S.counters, DLSC_N_COUNTERS);
     rc |= dev_alloc(c, &S.qp_next, 4);
     rc |= dev_alloc(c, &S.qp_list, NL);
     if (rc) { dlsc_destroy(c); return -1; }
@@ -431,7 +431,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
         ev = c->evpool.data() + (size_t)c->ev_used * (DLSC_N_STAGES + 1);
     }
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
-        CK(cudaMemsetAsync(c->S.counters, 0, 8 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(c->S.counters, 0, DLSC_N_COUNTERS * sizeof(unsigned long long), st));
     if (tm) CK(cudaEventRecord(ev[0], st));
     if (mask & DLSC_STAGE_PREDICT) { launch_predict(Pr, Sx, seq, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[1], st));
@@ -595,8 +595,8 @@ int dlsc_get_timings(dlsc_ctx* c, double ms[DLSC_N_STAGES], int* n_steps) {
     return 0;
 }
 int64_t dlsc_launch_count(const dlsc_ctx* c) { return c ? c->launches : 0; }
-int dlsc_get_counters(dlsc_ctx* c, int64_t counters[8]) {
-    return c ? d2h(c, counters, c->S.counters, 8 * sizeof(int64_t)) : fail("null ctx");
+int dlsc_get_counters(dlsc_ctx* c, int64_t counters[DLSC_N_COUNTERS]) {
+    return c ? d2h(c, counters, c->S.counters, DLSC_N_COUNTERS * sizeof(int64_t)) : fail("null ctx");
 }
 int dlsc_set_waypoints_device(dlsc_ctx* c, const float* p) {
     if (!c || !p) return fail("dlsc_set_waypoints_device: null argument");

@@ -131,11 +131,12 @@ __global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __g
     const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     const bool init = S.sfc_init[la] != 0 || S.disturbed[la] != 0;       // traj_planner.cpp:439, 693-695
-    long long look[4] = {0, 0, 0, 0};
+    long long look[6] = {0, 0, 0, 0, 0, 0};
     const int st = sfc_agent(g, P, S.edt, init, v3_load(rec + npt * 3), S.init_traj + (size_t)la * npt * 3,
                              v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3), S.radius[la],
                              S.max_vel[la], S.sfc + (size_t)la * P.M * 6, &tabs[w], look);
     const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)look[0]);
+    const unsigned tot_alg = __reduce_add_sync(0xffffffffu, (unsigned)look[4]);
     if (g.lane == 0) {
         S.sfc_init[la] = 0;
         if (st) atomicOr(S.status + la, st);
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __g
         if (look[1]) atomicAdd(S.counters + 5, (unsigned long long)look[1]);
         if (look[2]) atomicAdd(S.counters + 6, (unsigned long long)look[2]);
         if (look[3]) atomicAdd(S.counters + 7, (unsigned long long)look[3]);
+        atomicAdd(S.counters + 8, (unsigned long long)tot_alg);
     }
 }
 

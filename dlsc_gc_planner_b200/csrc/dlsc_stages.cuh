@@ -431,7 +431,10 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
     }
     if (mm[0] <= 0 || mm[1] <= 0 || mm[2] <= 0) return 0;
     if (mm[0] > kSfcTabMax || mm[1] > kSfcTabMax || mm[2] > kSfcTabMax) return -1;
-    if (lookups && g.lane == 0) *lookups += (long long)mm[0] * mm[1] * mm[2];
+    if (lookups && g.lane == 0) {
+        lookups[0] += (long long)mm[0] * mm[1] * mm[2];
+        if (lookups[5]) lookups[4] += (long long)mm[0] * mm[1] * mm[2];
+    }
     // ---- O(1) emptiness query: the summed-area table counts the lattice vertices whose mask byte is non-zero
     //      (any cell choice blocked); a box whose vertex range holds none is free whatever the float bits say ----
     if (E.sat && vv[0] >= 0 && vv[1] >= 0 && vv[2] >= 0 && vv[0] + mm[0] - 1 <= E.dims[0] &&
@@ -543,7 +546,8 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
 
 DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, double margin,
                              SfcTab* tab, long long* lookups) {
-    // lookups: [0] lattice vertices of the tested boxes, [1] box tests through the vertex mask, [2] through the records
+    // lookups: [0] lattice vertices of the tested boxes, [1] box tests through the vertex mask, [2] through the records,
+    // [3] answered by the summed-area query, [4] vertices of the non-redundant tests ([5] = flag set by the caller)
     if (E.vmask && margin == E.mask_margin && E.zs <= kSfcZsMax) {
         const int r = obstacle_in_box_mask(g, P, E, b, margin, tab, lookups);
         if (r >= 0) {
@@ -569,7 +573,7 @@ DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E
                 const int iy = t % m1, ix = t / m1;
                 const V3 q = v3((float)(b.lo.x + ix * res), (float)(b.lo.y + iy * res), (float)(b.lo.z + iz * res));
                 hit = vertex_blocked(E, q, margin, half_res);
-                if (lookups) *lookups += 1;
+                if (lookups) { lookups[0] += 1; if (lookups[5]) lookups[4] += 1; }
             }
             if (g.any(hit)) return true;
         }
@@ -598,7 +602,7 @@ DLSC_HD bool obstacle_in_box(const Group& g, const DevParams& P, const EdtDev& E
                 const int iy = r / m2, iz = r - iy * m2;
                 hit = vertex_blocked_tab(E, tab->q[0][ix], tab->q[1][iy], tab->q[2][iz], tab->c[0][ix], tab->c[1][iy],
                                          tab->c[2][iz], margin, half_res) || hit;
-                if (lookups) *lookups += 1;
+                if (lookups) { lookups[0] += 1; if (lookups[5]) lookups[4] += 1; }
             }
         }
         if (g.any(hit)) return true;
@@ -620,6 +624,7 @@ DLSC_HD bool box_in_boundary(const DevParams& P, const Box& b) {
 DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtDev& E, const Box& init,
                                   double margin, double max_vel, Box& out, SfcTab* memo, long long* lookups) {
     const double res = P.world_res;
+    if (lookups) lookups[5] = 1;                  // the initial box and the slabs are the algorithmic tests
     if (obstacle_in_box(g, P, E, init, margin, memo, lookups)) return false;
     int axes = 0x543210;              // packed axis list, 4 bits each: -x -y -z +x +y +z
     int n_axes = 6;
@@ -630,7 +635,9 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
     Box sfc = init, cand = init, upd = init;
     while (n_axes > 0) {
         cand = sfc; upd = sfc;
+        if (lookups) lookups[5] = 0;              // the whole-box recheck at the top of a pass is the reference's redundancy
         while (box_in_boundary(P, upd) && !obstacle_in_box(g, P, E, upd, margin, memo, lookups)) {
+            if (lookups) lookups[5] = 1;
             i++;
             if (i >= n_axes) i = 0;
             const int ax = (axes >> (4 * i)) & 0xf;

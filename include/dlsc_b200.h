@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DLSC_ABI_VERSION 1
+#define DLSC_ABI_VERSION 2
 
 /* Planner parameters: the subset of MATP::Param / MATP::Mission the hot path reads
  * (reference src/param.cpp:5-117, src/mission.cpp:104-112; launch-file values SURVEY.md s5). */
@@ -197,8 +197,10 @@ int64_t dlsc_launch_count(const dlsc_ctx* ctx);
 /* work counters of the last step summed over the local block (for roofline arithmetic):
  * [0] neighbour pairs, [1] GJK iterations, [2] lattice vertices of the tested SFC boxes, [3] QP iterations,
  * [4] QP rows, [5] SFC box tests answered from the lattice-vertex mask, [6] from the 16-byte EDT records,
- * [7] of [5]: answered "free" by the O(1) summed-area query alone */
-int dlsc_get_counters(dlsc_ctx* ctx, int64_t counters[8]);
+ * [7] of [5]: answered "free" by the O(1) summed-area query alone, [8] lattice vertices of the non-redundant
+ * SFC tests (initial box + slabs; SURVEY s8(d) algorithmic figure), [9..15] reserved */
+#define DLSC_N_COUNTERS 16
+int dlsc_get_counters(dlsc_ctx* ctx, int64_t counters[DLSC_N_COUNTERS]);
 
 /* Waypoints already resident on the device ([n_local][3] float32): stream-ordered device copy. */
 int dlsc_set_waypoints_device(dlsc_ctx* ctx, const float* device_ptr);

@@ -37,7 +37,7 @@ struct dlsc_ctx {
     bool mask_dirty = false;
     EdtDev edt;
     bool have_edt = false;
-    int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t counters[DLSC_N_COUNTERS] = {0};
 };
 
 extern "C" {
@@ -262,14 +262,14 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
         for (int la = 0; la < P.NL; la++) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             const bool init = c->sfc_init[la] != 0 || c->disturbed[la] != 0;
-            long long lookups[4] = {0, 0, 0, 0};
+            long long lookups[6] = {0, 0, 0, 0, 0, 0};
             SfcTab memo;
             const int st = sfc_agent(g, P, c->edt, init, v3_load(rec + npt * 3), c->init_traj.data() + (size_t)la * npt * 3,
                                      v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3), c->radius[la],
                                      c->max_vel[la], c->sfc.data() + (size_t)la * M * 6, &memo, lookups);
             c->sfc_init[la] = 0;
             c->status[la] |= st;
-            c->counters[2] += lookups[0]; c->counters[5] += lookups[1]; c->counters[6] += lookups[2]; c->counters[7] += lookups[3];
+            c->counters[2] += lookups[0]; c->counters[5] += lookups[1]; c->counters[6] += lookups[2]; c->counters[7] += lookups[3]; c->counters[8] += lookups[4];
         }
     if (mask & DLSC_STAGE_GOAL)
         for (int la = 0; la < P.NL; la++) {
@@ -409,7 +409,7 @@ int dlsc_set_sfc(dlsc_ctx* c, const float* sfc, const uint8_t* init_flag) {
     if (init_flag) memcpy(c->sfc_init.data(), init_flag, c->sfc_init.size());
     return 0;
 }
-int dlsc_get_counters(dlsc_ctx* c, int64_t counters[8]) { memcpy(counters, c->counters, sizeof(c->counters)); return 0; }
+int dlsc_get_counters(dlsc_ctx* c, int64_t counters[DLSC_N_COUNTERS]) { memcpy(counters, c->counters, sizeof(c->counters)); return 0; }
 int64_t dlsc_launch_count(const dlsc_ctx*) { return 0; }
 int dlsc_enable_timing(dlsc_ctx*, int) { return 0; }
 int dlsc_get_timings(dlsc_ctx*, double ms[DLSC_N_STAGES], int* n) { for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = 0; if (n) *n = 0; return 0; }
