@@ -54,7 +54,7 @@ EXPORTS = (
     "dlsc_get_pred_traj dlsc_get_neighbours dlsc_get_lsc dlsc_get_sfc dlsc_set_sfc dlsc_enable_timing "
     "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device "
     "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
-    "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc").split()
+    "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups").split()
 
 
 def build_library(force=False):
@@ -170,6 +170,12 @@ class SwarmPlanner:
         d3 = (C.c_int32 * 3)(*[int(x) for x in dims])
         k3 = (C.c_int32 * 3)(*[int(x) for x in min_key])
         self._ck(self.lib.dlsc_set_edt(self.ctx, _p(dist), _p(obst), d3, k3, C.c_double(res)))
+
+    def set_groups(self, group):
+        """Mission index per local agent (Monte-Carlo batches); call after construction / reset."""
+        g = np.ascontiguousarray(group, np.int32)
+        assert g.shape == (self.NL,)
+        self._ck(self.lib.dlsc_set_groups(self.ctx, _p(g)))
 
     def set_agents(self, pos=None, vel=None, acc=None, waypoint=None, disturbed=None):
         f = lambda x: None if x is None else np.ascontiguousarray(x, np.float32)

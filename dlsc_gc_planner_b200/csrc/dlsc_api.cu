@@ -349,6 +349,21 @@ int dlsc_reset(dlsc_ctx* c, const float* start) {
     return 0;
 }
 
+int dlsc_set_groups(dlsc_ctx* c, const int32_t* group) {
+    if (!c || !group) return fail("dlsc_set_groups: null argument");
+    CK(cudaSetDevice(c->device));
+    const DevParams& P = c->P;
+    std::vector<float> g((size_t)P.NL);
+    for (int i = 0; i < P.NL; i++) {
+        if (group[i] < 0 || group[i] >= (1 << 24)) return fail("dlsc_set_groups: group index out of range [0, 2^24)");
+        g[i] = (float)group[i];
+    }
+    float* dst = c->S.rec + (size_t)P.begin * P.rec + c->rl.group;
+    CK(cudaMemcpy2DAsync(dst, (size_t)P.rec * sizeof(float), g.data(), 4, 4, P.NL, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
     if (!c || !a) return fail("dlsc_set_agents: null argument");
     CK(cudaSetDevice(c->device));

@@ -38,20 +38,22 @@ void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t
 // reference's ascending neighbour order.
 constexpr int kNbrWarps = 16, kNbrTile = kNbrWarps * 32;
 __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    __shared__ float tile[kNbrTile * 3];
+    __shared__ float tile[kNbrTile * 4];         // position + group (mission index) of the tile's agents
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int la = blockIdx.x * kNbrWarps + w;
     const bool valid = la < P.NL;
     const int a = P.begin + la;
     const int off = P.M * kP * 3;
     const V3 pa = valid ? v3_load(S.rec + (size_t)a * P.rec + off) : v3(0.f, 0.f, 0.f);
+    const float ga = valid ? S.rec[(size_t)a * P.rec + off + 11] : 0.f;
     int32_t* idx_out = S.nbr_idx + (size_t)la * P.K;
     int count = 0;
     for (int base = 0; base < P.N; base += kNbrTile) {
         const int jt = base + threadIdx.x;
         if (jt < P.N) {
             const float* r = S.rec + (size_t)jt * P.rec + off;
-            tile[threadIdx.x * 3] = r[0]; tile[threadIdx.x * 3 + 1] = r[1]; tile[threadIdx.x * 3 + 2] = r[2];
+            tile[threadIdx.x * 4] = r[0]; tile[threadIdx.x * 4 + 1] = r[1]; tile[threadIdx.x * 4 + 2] = r[2];
+            tile[threadIdx.x * 4 + 3] = r[11];
         }
         __syncthreads();
         const int nt = (P.N - base < kNbrTile) ? P.N - base : kNbrTile;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__
             for (int t = 0; t < nt; t += 32) {
                 const int j = base + t + lane;
                 bool in = false;
-                if (t + lane < nt && j != a) in = in_comm_range(P, pa, v3_load(tile + (t + lane) * 3));
+                if (t + lane < nt && j != a && tile[(t + lane) * 4 + 3] == ga) in = in_comm_range(P, pa, v3_load(tile + (t + lane) * 4));
                 const unsigned mask = __ballot_sync(0xffffffffu, in);
                 const int pos = count + __popc(mask & ((1u << lane) - 1u));
                 if (in && pos < P.K) idx_out[pos] = j;

@@ -105,7 +105,7 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
     for (int base = 0; base < P.N; base += g.width) {
         const int j = base + g.lane;
         bool in = false;
-        if (j < P.N && j != a_global) {
+        if (j < P.N && j != a_global && rec[(size_t)j * P.rec + off + 11] == rec[(size_t)a_global * P.rec + off + 11]) {
             in = in_comm_range(P, pa, v3_load(rec + (size_t)j * P.rec + off));
         }
         const unsigned mask = g.ballot(in);
@@ -628,7 +628,7 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
     if (obstacle_in_box(g, P, E, init, margin, memo, lookups)) return false;
     int axes = 0x543210;              // packed axis list, 4 bits each: -x -y -z +x +y +z
     int n_axes = 6;
-    int iters[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long iters = 0;     // growth steps per axis, 8 bits each
     const double span = (2 * P.grid_res < max_vel * P.dt) ? max_vel * P.dt : 2 * P.grid_res;
     const int max_iter = (int)round(span / res) + 1;
     int i = -1;
@@ -636,25 +636,30 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
     while (n_axes > 0) {
         cand = sfc; upd = sfc;
         if (lookups) lookups[5] = 0;              // the whole-box recheck at the top of a pass is the reference's redundancy
-        while (box_in_boundary(P, upd) && !obstacle_in_box(g, P, E, upd, margin, memo, lookups)) {
+        // isSFCInBoundary on `upd`: the whole box at the top of a pass; afterwards `upd` is a slab that shares four
+        // faces with the already verified `cand`, so only its two faces along the growth axis are new
+        bool inside = box_in_boundary(P, upd);
+        while (inside && !obstacle_in_box(g, P, E, upd, margin, memo, lookups)) {
             if (lookups) lookups[5] = 1;
             i++;
             if (i >= n_axes) i = 0;
             const int ax = (axes >> (4 * i)) & 0xf;
+            const int a3 = (ax < 3) ? ax : ax - 3;
             sfc = cand; upd = cand;
             if (ax < 3) {
                 v3_set(upd.hi, ax, v3_get(cand.lo, ax));
                 v3_set(cand.lo, ax, (float)(v3_get(cand.lo, ax) - res));
                 v3_set(upd.lo, ax, v3_get(cand.lo, ax));
             } else {
-                v3_set(upd.lo, ax - 3, v3_get(cand.hi, ax - 3));
-                v3_set(cand.hi, ax - 3, (float)(v3_get(cand.hi, ax - 3) + res));
-                v3_set(upd.hi, ax - 3, v3_get(cand.hi, ax - 3));
+                v3_set(upd.lo, a3, v3_get(cand.hi, a3));
+                v3_set(cand.hi, a3, (float)(v3_get(cand.hi, a3) + res));
+                v3_set(upd.hi, a3, v3_get(cand.hi, a3));
             }
-            bool over = false;
-#pragma unroll
-            for (int t = 0; t < 6; t++) if (t == ax) { iters[t]++; over = iters[t] > max_iter; }
-            if (over) break;
+            const double wlo = (a3 == 0) ? P.world_min[0] : (a3 == 1 ? P.world_min[1] : P.world_min[2]);
+            const double whi = (a3 == 0) ? P.world_max[0] : (a3 == 1 ? P.world_max[1] : P.world_max[2]);
+            inside = (v3_get(upd.lo, a3) > wlo + 0.0 - kEpsF) && (v3_get(upd.hi, a3) < whi - 0.0 + kEpsF);
+            iters += 1ull << (8 * ax);
+            if ((int)((iters >> (8 * ax)) & 0xffull) > max_iter) break;
         }
         if (i < 0) return false;      // start box outside the world (the reference would erase begin()-1)
         // erase axes[i]

@@ -21,9 +21,10 @@ struct DevParams {
     float tk[kMaxPts];               // (float) of the time accumulated by `time += dt/n` (trajectory.cpp:84-90)
 };
 
-// record layout (floats): traj[M*P*3] | pos 3 | vel 3 | goal 3 | radius | downwash | pad to x4
+// record layout (floats): traj[M*P*3] | pos 3 | vel 3 | goal 3 | radius | downwash | group | pad to x4
+// group = mission index of the agent (Monte-Carlo batches: agents only see agents of their own mission)
 struct RecLayout {
-    int traj, pos, vel, goal, radius, downwash, size;
+    int traj, pos, vel, goal, radius, downwash, group, size;
 };
 inline RecLayout rec_layout(int M) {
     RecLayout r;
@@ -33,7 +34,8 @@ inline RecLayout rec_layout(int M) {
     r.goal = r.vel + 3;
     r.radius = r.goal + 3;
     r.downwash = r.radius + 1;
-    r.size = (r.downwash + 1 + 3) / 4 * 4;
+    r.group = r.downwash + 1;
+    r.size = (r.group + 1 + 3) / 4 * 4;
     return r;
 }
 

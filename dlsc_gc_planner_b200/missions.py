@@ -87,6 +87,28 @@ def load_mission(path, dim=3, z_2d=1.0):
                    f64(mv), f64(ma), f64(nv))
 
 
+def add_goal_noise(mission, max_noise, dim=3, seed=0):
+    """Mission::addNoise (reference src/mission.cpp:395-406): desired_goal(k) += (float)(U(0,1) * max_noise) for
+    the first `dim` coordinates -- seeded here (the reference draws from std::random_device) so that Monte-Carlo
+    batches are reproducible: seed = mission index."""
+    rng = np.random.default_rng(seed)
+    goal = mission.goal.astype(np.float32).copy()
+    u = rng.random((mission.n_agents, dim)).astype(np.float32)
+    goal[:, :dim] = goal[:, :dim] + (u.astype(np.float64) * max_noise).astype(np.float32)
+    return Mission(mission.world_min, mission.world_max, mission.start, goal, mission.radius, mission.downwash,
+                   mission.max_vel, mission.max_acc, mission.nominal_vel, mission.boxes)
+
+
+def concat_missions(ms):
+    """Independent missions of one world side by side in one agent array (Monte-Carlo batch); returns the batch
+    and the mission index of every agent (for dlsc_set_groups)."""
+    cat = lambda f: np.concatenate([getattr(m, f) for m in ms])
+    batch = Mission(ms[0].world_min, ms[0].world_max, cat("start"), cat("goal"), cat("radius"), cat("downwash"),
+                    cat("max_vel"), cat("max_acc"), cat("nominal_vel"), ms[0].boxes)
+    group = np.concatenate([np.full(m.n_agents, i, np.int32) for i, m in enumerate(ms)])
+    return batch, group
+
+
 def load_world_csv(path):
     """Rows ``cx,cy,cz,sx,sy,sz`` (src/map_manager.cpp:267-283; tokens go through stod then float)."""
     rows = []

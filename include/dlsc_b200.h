@@ -128,6 +128,12 @@ int dlsc_set_agent_props(dlsc_ctx* ctx, const dlsc_agent_props* props);
  * current_goal_point = start, next_waypoint = start: agent_manager.cpp:4-32) and write the
  * local records.  start [n_local][3]. */
 int dlsc_reset(dlsc_ctx* ctx, const float* start);
+/* Monte-Carlo batches (BASELINE configs[4]): several independent missions replanning in lockstep inside one
+ * context.  group[i] = mission index of local agent i (0 <= group < 2^24); agents only become neighbours of
+ * agents of the same mission (the reference runs one MultiSyncSimulator per mission).  Call after dlsc_reset
+ * (which puts every agent in mission 0); the index travels inside the agent record, so it is exchanged by
+ * the same all-gather as the trajectories. */
+int dlsc_set_groups(dlsc_ctx* ctx, const int32_t* group /* [n_local] */);
 
 /* Upload this step's agent states / waypoints (TrajPlanner::plan arguments + setNextWaypoint). */
 int dlsc_set_agents(dlsc_ctx* ctx, const dlsc_agents* agents);

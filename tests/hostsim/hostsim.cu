@@ -190,6 +190,12 @@ int dlsc_reset(dlsc_ctx* c, const float* start) {
     return 0;
 }
 
+int dlsc_set_groups(dlsc_ctx* c, const int32_t* group) {
+    const DevParams& P = c->P;
+    for (int i = 0; i < P.NL; i++) c->rec[(size_t)(P.begin + i) * P.rec + c->rl.group] = (float)group[i];
+    return 0;
+}
+
 int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
     const DevParams& P = c->P;
     for (int la = 0; la < P.NL; la++) {
