@@ -116,7 +116,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
     const bool D3 = (D == 3);
     GiSmem g;
     gi_carve(T, sm.W, g);
-    const double tol = 1e-9;
+    const double tol = 1e-10;    // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
     int q = 0, iters = 0, status = -1;
     double viol_p = 0.0, u_p = 0.0;
     bool same_p = false, have_hinv = false;

