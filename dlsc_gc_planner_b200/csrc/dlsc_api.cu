@@ -144,7 +144,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     if (hp->dim != 2 && hp->dim != 3) return fail("dlsc_create: world/dimension must be 2 or 3");
     if (hp->M < 2 || hp->M > kMaxM) return fail("dlsc_create: traj/M out of range [2,16]");
     if (hp->dim * (3 * hp->M - 2) > 128) return fail("dlsc_create: dim*(3M-2) must be <= 128");
-    if (hp->max_nbr < 1) return fail("dlsc_create: max_nbr must be >= 1");
+    if (hp->max_nbr < 1 || hp->max_nbr > 1024) return fail("dlsc_create: max_nbr must be in [1, 1024]");
     if (n_agents < 1 || agent_begin < 0 || n_local < 1 || agent_begin + n_local > n_agents)
         return fail("dlsc_create: bad agent block");
     if (!(hp->dt > 0) || !(hp->world_res > 0)) return fail("dlsc_create: dt and world_res must be positive");
@@ -196,6 +196,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.lsc_normal, NL * K * M * 3);
     rc |= dev_alloc(c, &S.lsc_d, NL * K * M * kP);
     rc |= dev_alloc(c, &S.lsc_anchor_last, NL * K * 3);
+    rc |= dev_alloc(c, &S.lsc_near, NL * K * M);
     rc |= dev_alloc(c, &S.sfc, NL * M * 6);
     rc |= dev_alloc(c, &S.traj, NL * npt * 3);
     rc |= dev_alloc(c, &S.qp_x, NL * (size_t)hp->dim * npt);
@@ -423,7 +424,7 @@ int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
     S.acc += f * 3; S.waypoint += f * 3; S.goal_new += f * 3; S.disturbed += f; S.sfc_init += f;
     S.radius += f; S.downwash += f; S.max_vel += f; S.max_acc += f; S.nominal_vel += f;
     S.init_traj += f * npt * 3; S.nbr_idx += f * K; S.nbr_cnt += f;
-    S.lsc_normal += f * K * M * 3; S.lsc_d += f * K * M * kP; S.lsc_anchor_last += f * K * 3;
+    S.lsc_normal += f * K * M * 3; S.lsc_d += f * K * M * kP; S.lsc_anchor_last += f * K * 3; S.lsc_near += f * K * M;
     S.sfc += f * M * 6; S.traj += f * npt * 3; S.qp_x += f * (size_t)P.D * npt;
     S.cost += f; S.viol += f; S.qp_iters += f; S.status += f;
     return run_stages_impl(c, mask, P, S);
@@ -557,10 +558,24 @@ static int h2d(dlsc_ctx* c, void* dev, const void* host, size_t bytes) {
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
-int dlsc_set_init_traj(dlsc_ctx* c, const float* t) { return c ? h2d(c, c->S.init_traj, t, (size_t)c->P.NL * c->P.M * kP * 12) : fail("null ctx"); }
-int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { return c ? h2d(c, c->S.pred_traj, t, (size_t)c->P.N * c->P.M * kP * 12) : fail("null ctx"); }
+// injected stage inputs invalidate the QP row screen that k_lsc derived from the previous ones: every item "near"
+static int screen_off(dlsc_ctx* c) {
+    CK(cudaMemsetAsync(c->S.lsc_near, 1, (size_t)c->P.NL * c->P.K * c->P.M, c->stream));
+    return 0;
+}
+int dlsc_set_init_traj(dlsc_ctx* c, const float* t) {
+    if (!c) return fail("null ctx");
+    if (screen_off(c)) return -1;
+    return h2d(c, c->S.init_traj, t, (size_t)c->P.NL * c->P.M * kP * 12);
+}
+int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) {
+    if (!c) return fail("null ctx");
+    if (screen_off(c)) return -1;
+    return h2d(c, c->S.pred_traj, t, (size_t)c->P.N * c->P.M * kP * 12);
+}
 int dlsc_set_neighbours(dlsc_ctx* c, const int32_t* idx, const int32_t* cnt) {
     if (!c) return fail("null ctx");
+    if (screen_off(c)) return -1;
     if (h2d(c, c->S.nbr_idx, idx, (size_t)c->P.NL * c->P.K * 4)) return -1;
     return h2d(c, c->S.nbr_cnt, cnt, (size_t)c->P.NL * 4);
 }
@@ -569,6 +584,7 @@ int dlsc_set_lsc(dlsc_ctx* c, const float* normal, const float* anchor_last, con
     const size_t pairs = (size_t)c->P.NL * c->P.K;
     if (h2d(c, c->S.lsc_normal, normal, pairs * c->P.M * 12)) return -1;
     if (h2d(c, c->S.lsc_anchor_last, anchor_last, pairs * 12)) return -1;
+    if (screen_off(c)) return -1;
     return h2d(c, c->S.lsc_d, d, pairs * c->P.M * kP * 8);
 }
 int dlsc_set_sfc(dlsc_ctx* c, const float* sfc, const uint8_t* init_flag) {

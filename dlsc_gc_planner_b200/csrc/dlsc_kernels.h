@@ -27,6 +27,7 @@ struct DevState {
     float* lsc_normal;         // [NL][K][M][3]
     double* lsc_d;             // [NL][K][M][P]
     float* lsc_anchor_last;    // [NL][K][3]
+    uint8_t* lsc_near;         // [NL][K][M] QP row screen: 1 = the item's rows can come within qp_screen of the initial trajectory
     float* sfc;                // [NL][M][6]
     float* traj;               // [NL][M][P][3]  QP result (or failsafe)
     double* qp_x;              // [NL][D][M][P]

@@ -81,39 +81,52 @@ void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// thread per (agent, slot, segment).  The item space is split so that warps are homogeneous: first every GJK
-// item (segments 0..M-2; consecutive threads = consecutive segments of one pair, a warp covers ~3.5 pairs of
-// the same agent -> similar geometry, similar GJK depth), then every last-segment item (segment-segment
-// closest points, a different code path).
-__global__ void __launch_bounds__(128, 4) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+// CTA per agent.  The agent's neighbour list, its own initial trajectory and the neighbours' (radius, downwash,
+// goal) are staged in shared memory first, so that the per-item loads (the neighbour's predicted control points)
+// are one dependent hop away; then thread per item, all GJK items (neighbour x segments 0..M-2, warps
+// homogeneous: similar geometry, similar GJK depth) before the last-segment items (segment-segment closest points,
+// a different code path).
+constexpr int kLscThreads = 128;
+__global__ void __launch_bounds__(kLscThreads, 4) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    __shared__ float s_init[kMaxPts * 3];
+    extern __shared__ int s_dyn[];                // [K] neighbour indices | [K][5] neighbour radius, downwash, goal
+    int* s_nbr = s_dyn;
+    float (*s_nj)[5] = reinterpret_cast<float (*)[5]>(s_dyn + P.K);
     const int M = P.M, npt = M * kP;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n_gjk = (long long)P.NL * P.K * (M - 1);
-    const long long total = n_gjk + (long long)P.NL * P.K;
-    int it = 0;
-    if (gid < total) {
-        int m; long long pr;
-        if (gid < n_gjk) { m = (int)(gid % (M - 1)); pr = gid / (M - 1); }
-        else { m = M - 1; pr = gid - n_gjk; }
-        const int c = (int)(pr % P.K), la = (int)(pr / P.K);
-        if (c < S.nbr_cnt[la]) {
-            const int j = S.nbr_idx[(size_t)la * P.K + c];
-            const float* rec_a = S.rec + (size_t)(P.begin + la) * P.rec;
-            const float* rec_j = S.rec + (size_t)j * P.rec;
-            const int og = npt * 3 + 6;
-            lsc_segment(P, S.init_traj + (size_t)la * npt * 3, S.pred_traj + (size_t)j * npt * 3,
-                        v3_load(rec_a + og), v3_load(rec_j + og), S.radius[la], S.downwash[la], rec_j[og + 3],
-                        rec_j[og + 4], m, S.lsc_normal + ((size_t)pr * M + m) * 3,
-                        S.lsc_d + ((size_t)pr * M + m) * kP, S.lsc_anchor_last + (size_t)pr * 3, &it);
-        }
+    const int la = blockIdx.x;
+    const int cnt = S.nbr_cnt[la];
+    const float* rec_a = S.rec + (size_t)(P.begin + la) * P.rec;
+    const int og = npt * 3 + 6;
+    for (int e = threadIdx.x; e < npt * 3; e += kLscThreads) s_init[e] = S.init_traj[(size_t)la * npt * 3 + e];
+    for (int c = threadIdx.x; c < cnt; c += kLscThreads) {
+        const int j = S.nbr_idx[(size_t)la * P.K + c];
+        const float* rec_j = S.rec + (size_t)j * P.rec;
+        s_nbr[c] = j;
+        s_nj[c][0] = rec_j[og + 3]; s_nj[c][1] = rec_j[og + 4];
+        s_nj[c][2] = rec_j[og]; s_nj[c][3] = rec_j[og + 1]; s_nj[c][4] = rec_j[og + 2];
     }
-    const int tot = __reduce_add_sync(0xffffffffu, it);
+    const V3 goal_a = v3_load(rec_a + og);
+    const double r_a = S.radius[la], dw_a = S.downwash[la];
+    __syncthreads();
+    int it_sum = 0;
+    const int n_gjk = cnt * (M - 1), total = n_gjk + cnt;
+    for (int e = threadIdx.x; e < total; e += kLscThreads) {
+        int c, m;
+        if (e < n_gjk) { c = e / (M - 1); m = e - c * (M - 1); }
+        else { c = e - n_gjk; m = M - 1; }
+        const size_t pr = (size_t)la * P.K + c;
+        int it = 0;
+        lsc_segment(P, s_init, S.pred_traj + (size_t)s_nbr[c] * npt * 3, goal_a, v3(s_nj[c][2], s_nj[c][3], s_nj[c][4]),
+                    r_a, dw_a, s_nj[c][0], s_nj[c][1], m, S.lsc_normal + (pr * M + m) * 3,
+                    S.lsc_d + (pr * M + m) * kP, S.lsc_anchor_last + pr * 3, &it, S.lsc_near + pr * M + m, P.qp_screen);
+        it_sum += it;
+    }
+    const int tot = __reduce_add_sync(0xffffffffu, it_sum);
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(S.counters + 1, (unsigned long long)tot);
 }
 
 void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
-    const long long n = (long long)P.NL * P.K * P.M;
-    k_lsc<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, S);
+    k_lsc<<<P.NL, kLscThreads, (size_t)P.K * 6 * sizeof(int), st>>>(P, S);
 }
 
 // ------------------------------------------------------------------------------------------------

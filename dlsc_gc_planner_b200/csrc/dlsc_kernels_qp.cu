@@ -29,6 +29,7 @@ __device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState
     in.d = S.lsc_d + pr * P.M * kP;
     in.anchor_last = S.lsc_anchor_last + pr * 3;
     in.pred_traj = S.pred_traj;
+    in.near = S.lsc_near + pr * P.M;
     out.traj = S.traj + (size_t)la * npt * 3;
     out.x = S.qp_x + (size_t)la * T.nx;
     out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;

@@ -73,6 +73,8 @@ struct QpIn {
     const double* d;           // [K][M][P]
     const float* anchor_last;  // [K][3]
     const float* pred_traj;    // [N][M][P][3] (anchors of segments < M-1)
+    const uint8_t* near;       // [K][M] row screen of k_lsc (or null): 0 = the item's rows stay >= qp_screen away from
+                               //        violation while |x_pt - init_pt| < qp_screen
 };
 struct QpOut {
     float* traj;               // [M][P][3]

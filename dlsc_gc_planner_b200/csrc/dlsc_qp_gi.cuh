@@ -59,7 +59,7 @@ DLSC_HD void pair_violation(const DevParams& P, const QpTab& T, const QpIn& in, 
 // most violated row over all inequality rows; every thread returns the same (vmax, id)
 //   id < 2 np: pattern row r = id >> 1, side id & 1 (0: upper, 1: lower);  else LSC row o = id - 2 np = pt * Kcap + cc
 DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
-                     const int* sm_nbr, double& vmax_out, double& id_out) {
+                     const int* sm_nbr, bool screened, double& vmax_out, double& id_out) {
     const int npt = T.npt, np = T.np, Kc = P.K, K = in.K;
     const bool D3 = (P.D == 3);
     double best = -1e300, best_id = 1e300;
@@ -73,6 +73,7 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
     // anchors are contiguous in memory (traj_optimizer.cpp:412-450: -n.x <= -(n.anchor + d))
     const int M = P.M, items = K * M;
     for (int e = c.tid; e < items; e += c.nthr) {
+        if (screened && !in.near[e]) continue;                                      // row screen of k_lsc
         const int cc = e / M, m = e - cc * M;
         const float* nr = in.normal + ((size_t)cc * M + m) * 3;
         const V3 nv = v3_load(nr);
@@ -120,12 +121,30 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
     int q = 0, iters = 0, status = -1;
     double viol_p = 0.0, u_p = 0.0;
     bool same_p = false, have_hinv = false;
+    // Row screen: k_lsc flagged the items whose rows have a (normalised) slack below qp_screen at the agent's
+    // initial trajectory.  While every control point of the iterate stays within qp_screen (minus a margin for
+    // the rounding of the two evaluations) of its initial-trajectory point the unflagged rows cannot be violated,
+    // so they are not evaluated; an iterate that leaves that ball switches this agent to full scans for good.
+    bool screened = (P.qp_screen > 0) && (in.near != nullptr);
+    const double ball = P.qp_screen - 1e-3;
     for (int guard = 0; guard < 400; guard++) {
         if (!same_p) {
             map_x(c, T, sm.y, sm.cst, sm.x);
             c.sync();
+            if (screened) {
+                double far2 = 0.0, d0 = 0.0, d1 = 0.0;
+                for (int pt = 3 + c.tid; pt < npt; pt += c.nthr) {
+                    const double ex = sm.x[pt] - (double)in.init_traj[pt * 3];
+                    const double ey = sm.x[npt + pt] - (double)in.init_traj[pt * 3 + 1];
+                    const double ez = D3 ? sm.x[2 * npt + pt] - (double)in.init_traj[pt * 3 + 2] : 0.0;
+                    const double r2 = ex * ex + ey * ey + ez * ez;
+                    far2 = (r2 > far2) ? r2 : far2;
+                }
+                c.reduce3(far2, 1, d0, 0, d1, 0);
+                if (!(far2 < ball * ball)) screened = false;
+            }
             double vmax, idsel;
-            gi_scan(c, P, T, in, qc, sm.x, sm.off, vmax, idsel);
+            gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, vmax, idsel);
             *viol_out = vmax;
             if (!(vmax > tol)) { status = 0; break; }
             if (!have_hinv) {                                   // first violated row: stage this agent's H^-1 block

@@ -124,7 +124,8 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
 // ------------------------------------------------------------------------------------------------
 DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* pred_j, const V3& goal_a,
                          const V3& goal_j, double r_a, double dw_a, float r_j_f, float dw_j_f, int m,
-                         float* normal_out, double* d_out, float* anchor_last_out, int* gjk_iters) {
+                         float* normal_out, double* d_out, float* anchor_last_out, int* gjk_iters,
+                         uint8_t* near_out = nullptr, double tau = 0.0) {
     const double r_j = (double)r_j_f, dw_j = (double)dw_j_f;
     const double collision_dist = r_j + r_a;                                   // :605
     const double downwash = (dw_a * r_a + dw_j * r_j) / (r_a + r_j);           // :1153-1154
@@ -148,6 +149,23 @@ DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* p
         normal_out[2] = (float)((double)nt.z / downwash);                             // :630-632
 #pragma unroll
         for (int i = 0; i < kP; i++) d_out[i] = 0.5 * (collision_dist + v3_dot(rel[i], nt));   // :636-637
+        if (near_out) {
+            // QP row screen (dlsc_qp_gi.cuh): slack of the rows of this item at the agent's own initial trajectory,
+            // in world coordinates, normalised by |normal|.  A row whose normalised slack is >= tau cannot be
+            // violated by any x with |x_pt - init_pt| < tau.
+            const double n0 = (double)normal_out[0], n1 = (double)normal_out[1], n2 = (double)normal_out[2];
+            const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+            double smin = 1e300;
+#pragma unroll
+            for (int i = 0; i < kP; i++) {
+                const float* a = init_a + (m * kP + i) * 3;
+                const float* b = pred_j + (m * kP + i) * 3;
+                const double sl = n0 * ((double)a[0] - (double)b[0]) + n1 * ((double)a[1] - (double)b[1]) +
+                                  n2 * ((double)a[2] - (double)b[2]) - d_out[i];
+                smin = (sl < smin) ? sl : smin;
+            }
+            *near_out = (smin < tau * nn) ? 1 : 0;
+        }
     } else {
         const int last = (P.M - 1) * kP + (kP - 1);
         V3 o_last = v3_load(pred_j + last * 3); o_last.z = o_last.z / dwf;
@@ -164,6 +182,19 @@ DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* p
 #pragma unroll
         for (int i = 0; i < kP; i++) d_out[i] = dd;
         if (gjk_iters) *gjk_iters = 0;
+        if (near_out) {
+            const double n0 = (double)normal_out[0], n1 = (double)normal_out[1], n2 = (double)normal_out[2];
+            const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+            double smin = 1e300;
+#pragma unroll
+            for (int i = 0; i < kP; i++) {
+                const float* a = init_a + ((P.M - 1) * kP + i) * 3;
+                const double sl = n0 * ((double)a[0] - (double)anchor_last_out[0]) + n1 * ((double)a[1] - (double)anchor_last_out[1]) +
+                                  n2 * ((double)a[2] - (double)anchor_last_out[2]) - dd;
+                smin = (sl < smin) ? sl : smin;
+            }
+            *near_out = (smin < tau * nn) ? 1 : 0;
+        }
     }
 }
 

@@ -173,3 +173,18 @@ def test_full_size_rollout_is_deterministic(cuda_lib, world):
         outs.append((pl.get_records().copy(), pl.sfc().copy()))
         pl.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_qp_row_screen_is_exact_at_full_size(cuda_lib, world):
+    """The QP row screen (k_lsc flags + the ball check in gi_solve) only skips rows that cannot be violated: with
+    and without it every agent gets the same solution, bit for bit."""
+    a = make(cuda_lib, world)
+    b = make(cuda_lib, world, qp_screen_slack=-1.0)              # screen off: every scan evaluates every row
+
+    def check(t):
+        assert np.array_equal(a.qp_x(), b.qp_x()), "row screen changed a QP solution at step %d" % t
+        assert np.array_equal(a.traj(), b.traj()) and np.array_equal(a.qp_iters(), b.qp_iters())
+        assert np.array_equal(a.cost(), b.cost())
+
+    rollout([a, b], world, 14, check)
+    a.close(); b.close()
