@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from dlsc_gc_planner_b200 import capi, edt as edtmod, missions, sharding  # noqa: E402
+from dlsc_gc_planner_b200 import capi, missions, sharding  # noqa: E402
 
 METRIC = "agent-replans/sec (LSC+SFC+QP), synthetic 4096-agent 3D forest"
 UNIT = "agent-replans/s"
@@ -59,8 +59,7 @@ def make_world(args):
     cfg = missions.PlannerConfig.forest3d()
     h = args.half_extent if args.half_extent else 0.5 * float(np.sqrt(args.agents))
     m = missions.synthetic_forest(n_agents=args.agents, half_extent=h, seed=4096)
-    dist, obst, dims, mk = edtmod.build_edt(m.world_min, m.world_max, cfg.world_res, m.boxes)
-    return cfg, m, (dist, obst, dims, mk)
+    return cfg, m
 
 
 class Clocks:
@@ -180,11 +179,11 @@ def pinned(shape, dtype):
 
 
 # ------------------------------------------------------------------------------------------------------
-def pilot_rollout(cfg, m, edt, args, device, n_steps):
+def pilot_rollout(cfg, m, args, device, n_steps):
     """Untimed: roll the whole swarm out on this rank's GPU, recording per-step waypoints and host states,
     and the planner state at the start of the timed region."""
     pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr, device=device)
-    pl.set_edt(*edt, cfg.world_res)
+    pl.build_edt(m.boxes)             # distance grid built on the device from the mission's obstacle boxes
     occupied = missions.occupied_nodes(m.boxes, cfg.grid_res)
     N = m.n_agents
     wp = pl.start.copy()
@@ -211,6 +210,7 @@ def pilot_rollout(cfg, m, edt, args, device, n_steps):
     snap["nbr_overflow"] = int(((st & capi.NBR_OVERFLOW) != 0).sum())
     snap["fails"] = fails
     snap["dist_to_goal"] = float(np.mean(np.max(np.abs(pl.state()[0] - goal_des), axis=1)))
+    snap["edt"] = pl.get_edt()        # the same grid arrays for the CPU baseline (oracle)
     pl.close()
     return {k: np.array(v) for k, v in rec.items()}, snap
 
@@ -269,14 +269,16 @@ def run_ours(args):
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     W, K = max(args.warmup, 3), args.steps
-    cfg, m, edt = make_world(args)
+    cfg, m = make_world(args)
     N = m.n_agents
     begin, NL = sharding.agent_block(N, world, rank)
     sl = slice(begin, begin + NL)
 
-    rec, snap = pilot_rollout(cfg, m, edt, args, dev.index, W + K)
+    rec, snap = pilot_rollout(cfg, m, args, dev.index, W + K)
+    edt = snap["edt"]
     pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr, begin=begin, n_local=NL, device=dev.index)
-    pl.set_edt(*edt, cfg.world_res)
+    pl.build_edt(m.boxes)
+    edt_ms = pl.edt_build_ms()
     pl.set_stream(torch.cuda.current_stream().cuda_stream)
     exchange = sharding.RecordExchange(pl, world, rank, device=dev)     # records live in a torch tensor NCCL gathers in place
     wp_dev = torch.from_numpy(np.ascontiguousarray(rec["wp"][:, sl])).to(dev)        # [T][NL][3] resident
@@ -415,6 +417,11 @@ def run_ours(args):
             "clocks": clk,
         }
         hbm = peaks.get("hbm_gbs") or 6650.0
+        ncell = int(edt[2][0]) * int(edt[2][1]) * int(edt[2][2])
+        out["edt_build"] = {"kernels": "k_edt_pass_z/y/x", "ms": edt_ms, "cells": ncell, "bound": "hbm",
+                            "achieved": 17.0 * ncell / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else None, "peak": hbm, "unit": "GB/s",
+                            "frac": 17.0 * ncell / (edt_ms * 1e-3) / 1e9 / hbm if edt_ms > 0 else None,
+                            "algorithmic": "once per mission: 1 B occupancy in + 16 B record out per cell"}
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -454,15 +461,20 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+def oracle_params_of(cfg, m):
+    from oracle import oracle_py as O
+    return O.make_params(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, use_sfc=cfg.use_sfc, dt=cfg.dt,
+                         world_min=m.world_min, world_max=m.world_max, world_res=cfg.world_res, grid_res=cfg.grid_res,
+                         z_2d=cfg.z_2d, comm_range=cfg.comm_range, w_control=cfg.w_control, w_terminal=cfg.w_terminal,
+                         reset_threshold=cfg.reset_threshold)
+
+
 def oracle_swarm(cfg, m, edt, snap, rec, args, n_threads):
     """The CPU oracle (oracle/: test infrastructure, here only as the timed CPU baseline) loaded with the
     planner state at the start of the timed region."""
     from oracle import oracle_py as O
     O.build()
-    p = O.make_params(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, use_sfc=cfg.use_sfc, dt=cfg.dt,
-                      world_min=m.world_min, world_max=m.world_max, world_res=cfg.world_res, grid_res=cfg.grid_res,
-                      z_2d=cfg.z_2d, comm_range=cfg.comm_range, w_control=cfg.w_control, w_terminal=cfg.w_terminal,
-                      reset_threshold=cfg.reset_threshold)
+    p = oracle_params_of(cfg, m)
     e = O.Edt(p, edt[0], edt[1], edt[2], edt[3])
     sw = O.Swarm(p, m.start, m.goal, m.radius, m.downwash, m.max_vel, m.max_acc, m.nominal_vel, edt=e,
                  max_nbr=args.max_nbr, n_threads=n_threads)
@@ -509,7 +521,7 @@ def run_reference(args):
     if rank != 0:
         return
     W, K = max(args.warmup, 1), args.steps
-    cfg, m, edt = make_world(args)
+    cfg, m = make_world(args)
     N = m.n_agents
     # state at the start of the timed region: produced by the GPU pilot when a GPU is there, else a cold start
     try:
@@ -518,8 +530,13 @@ def run_reference(args):
     except Exception:
         have_gpu = False
     if have_gpu:
-        rec, snap = pilot_rollout(cfg, m, edt, args, 0, 1)
+        rec, snap = pilot_rollout(cfg, m, args, 0, 1)
+        edt = snap["edt"]
     else:
+        from oracle import oracle_py as O
+        O.build()
+        e = O.edt_build(oracle_params_of(cfg, m), m.boxes)
+        edt = (e.dist, e.obst, e.dims, e.min_key)
         start = m.start.astype(np.float32)
         o = cfg.M * (cfg.n + 1) * 3
         records = np.zeros((N, o + 12), np.float32)

@@ -54,7 +54,8 @@ EXPORTS = (
     "dlsc_get_pred_traj dlsc_get_neighbours dlsc_get_lsc dlsc_get_sfc dlsc_set_sfc dlsc_enable_timing "
     "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device "
     "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
-    "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups").split()
+    "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups dlsc_edt_dims dlsc_build_edt "
+    "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms").split()
 
 
 def build_library(force=False):
@@ -72,6 +73,9 @@ def _declare(lib):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_void_p
             getattr(lib, name).argtypes = [C.c_void_p]
+    if hasattr(lib, "dlsc_edt_build_ms"):
+        lib.dlsc_edt_build_ms.restype = C.c_double
+        lib.dlsc_edt_build_ms.argtypes = [C.c_void_p]
     if hasattr(lib, "dlsc_launch_count"):
         lib.dlsc_launch_count.restype = C.c_int64
         lib.dlsc_launch_count.argtypes = [C.c_void_p]
@@ -170,6 +174,35 @@ class SwarmPlanner:
         d3 = (C.c_int32 * 3)(*[int(x) for x in dims])
         k3 = (C.c_int32 * 3)(*[int(x) for x in min_key])
         self._ck(self.lib.dlsc_set_edt(self.ctx, _p(dist), _p(obst), d3, k3, C.c_double(res)))
+
+    def edt_dims(self):
+        d3, k3 = (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        self._ck(self.lib.dlsc_edt_dims(self.ctx, d3, k3))
+        return tuple(d3), tuple(k3)
+
+    def build_edt(self, boxes, maxdist=1.0):
+        """Distance grid from the mission's CSV boxes [nb][6] (cx, cy, cz, sx, sy, sz), built on the device
+        (MapManager::updateOctreeFromCSV + setGlobalMap, src/map_manager.cpp:61-82, 264-316)."""
+        b = np.ascontiguousarray(np.asarray(boxes, np.float32).reshape(-1, 6))
+        self._ck(self.lib.dlsc_build_edt(self.ctx, _p(b) if len(b) else None, C.c_int(len(b)), C.c_double(maxdist)))
+
+    def build_edt_occupancy(self, occ, maxdist=1.0):
+        dims, _ = self.edt_dims()
+        o = np.ascontiguousarray(occ, np.uint8)
+        assert o.size == dims[0] * dims[1] * dims[2]
+        self._ck(self.lib.dlsc_build_edt_occupancy(self.ctx, _p(o), C.c_double(maxdist)))
+
+    def get_edt(self):
+        """-> dist [ncell] f32, obst [ncell][3] i32, dims, min_key (dlsc_set_edt layout)"""
+        dims, mk = self.edt_dims()
+        nc = dims[0] * dims[1] * dims[2]
+        dist = np.empty(nc, np.float32)
+        obst = np.empty((nc, 3), np.int32)
+        self._ck(self.lib.dlsc_get_edt(self.ctx, _p(dist), _p(obst)))
+        return dist, obst, dims, mk
+
+    def edt_build_ms(self):
+        return float(self.lib.dlsc_edt_build_ms(self.ctx))
 
     def set_groups(self, group):
         """Mission index per local agent (Monte-Carlo batches); call after construction / reset."""

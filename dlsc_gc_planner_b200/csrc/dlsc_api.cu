@@ -39,6 +39,7 @@ struct dlsc_ctx {
     int32_t* edt_sat = nullptr;        // summed-area table over the flagged mask vertices
     uint8_t* edt_mask = nullptr;       // lattice-vertex mask of the SFC vertex test (built lazily for margin_host)
     bool mask_dirty = false;
+    double edt_build_ms = 0.0;         // device time of the last dlsc_build_edt* (the three EDT passes)
     double margin_host = 0.0;          // radius of the first local agent (all BASELINE missions: 0.15 for every agent)
     int64_t launches = 0;
     bool timing = false;
@@ -246,23 +247,8 @@ int dlsc_set_stream(dlsc_ctx* c, void* s) {
 }
 void* dlsc_get_stream(dlsc_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
-int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int32_t dims[3],
-                 const int32_t min_key[3], double res) {
-    if (!c || !dist || !obst) return fail("dlsc_set_edt: null argument");
-    CK(cudaSetDevice(c->device));
-    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
-    if (nc == 0) return fail("dlsc_set_edt: empty grid");
-    float* d_dist = nullptr; int32_t* d_obst = nullptr;
-    CK(cudaMalloc(&d_dist, nc * sizeof(float)));
-    CK(cudaMalloc(&d_obst, nc * 3 * sizeof(int32_t)));
-    CK(cudaMemcpyAsync(d_dist, dist, nc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_obst, obst, nc * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    if (c->edt_cells) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_cells); c->edt_cells = nullptr; }
-    CK(cudaMalloc(&c->edt_cells, nc * sizeof(int4)));
-    launch_edt_pack(d_dist, d_obst, c->edt_cells, nc, c->stream);
-    c->launches++;
-    CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_dist); cudaFree(d_obst);
+// common tail of dlsc_set_edt / dlsc_build_edt*: publish the grid view and the per-axis cell-centre tables
+static int finish_edt(dlsc_ctx* c, const int32_t dims[3], const int32_t min_key[3], double res) {
     EdtDev& E = c->S.edt;
     for (int k = 0; k < 3; k++) { E.dims[k] = dims[k]; E.min_key[k] = min_key[k]; }
     E.res = res; E.inv_res = 1.0 / res; E.cells = c->edt_cells;
@@ -282,6 +268,122 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
     CK(cudaGetLastError());
     return 0;
 }
+
+int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int32_t dims[3],
+                 const int32_t min_key[3], double res) {
+    if (!c || !dist || !obst) return fail("dlsc_set_edt: null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+    if (nc == 0) return fail("dlsc_set_edt: empty grid");
+    float* d_dist = nullptr; int32_t* d_obst = nullptr;
+    CK(cudaMalloc(&d_dist, nc * sizeof(float)));
+    CK(cudaMalloc(&d_obst, nc * 3 * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(d_dist, dist, nc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_obst, obst, nc * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (c->edt_cells) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_cells); c->edt_cells = nullptr; }
+    CK(cudaMalloc(&c->edt_cells, nc * sizeof(int4)));
+    launch_edt_pack(d_dist, d_obst, c->edt_cells, nc, c->stream);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_dist); cudaFree(d_obst);
+    return finish_edt(c, dims, min_key, res);
+}
+
+// grid extent of the mission world: DynamicEDTOctomap(maxdist, octree, world_min, world_max) covers the octomap keys
+// floor(coord / res) of both corners (float coordinates), src/map_manager.cpp:76-78
+int dlsc_edt_dims(const dlsc_ctx* c, int32_t dims[3], int32_t min_key[3]) {
+    if (!c || !dims || !min_key) return fail("dlsc_edt_dims: null argument");
+    const double inv = 1.0 / c->hp.world_res;
+    for (int k = 0; k < 3; k++) {
+        const int lo = (int)std::floor(inv * (double)(float)c->hp.world_min[k]);
+        const int hi = (int)std::floor(inv * (double)(float)c->hp.world_max[k]);
+        min_key[k] = lo; dims[k] = hi - lo + 1;
+    }
+    return 0;
+}
+
+// occupancy (device, 1 byte per cell) -> 16-byte records; frees nothing it did not allocate
+static int edt_from_occupancy_dev(dlsc_ctx* c, const uint8_t* d_occ, const int32_t dims[3], const int32_t mk[3], double maxdist) {
+    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+    const double res = c->hp.world_res;
+    const int maxd = (int)(maxdist / res + 1);          // DynamicEDTOctomap: maxdist in cells
+    uint32_t *ta = nullptr, *tb = nullptr;
+    CK(cudaMalloc(&ta, nc * sizeof(uint32_t)));
+    CK(cudaMalloc(&tb, nc * sizeof(uint32_t)));
+    if (c->edt_cells) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_cells); c->edt_cells = nullptr; }
+    CK(cudaMalloc(&c->edt_cells, nc * sizeof(int4)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, c->stream));
+    const int nl = launch_edt_build(d_occ, ta, tb, c->edt_cells, dims, res, maxd, c->stream);
+    CK(cudaEventRecord(e1, c->stream));
+    if (nl < 0) { cudaFree(ta); cudaFree(tb); return fail("dlsc_build_edt: maxdist / resolution + 1 must be in [1, 16] cells"); }
+    c->launches += nl;
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->edt_build_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(ta); cudaFree(tb);
+    return finish_edt(c, dims, mk, res);
+}
+
+int dlsc_build_edt(dlsc_ctx* c, const float* boxes, int n_boxes, double maxdist) {
+    if (!c || (n_boxes > 0 && !boxes) || n_boxes < 0) return fail("dlsc_build_edt: bad argument");
+    CK(cudaSetDevice(c->device));
+    int32_t dims[3], mk[3];
+    dlsc_edt_dims(c, dims, mk);
+    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+    if (nc == 0 || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail("dlsc_build_edt: empty world");
+    uint8_t* d_occ = nullptr; float* d_boxes = nullptr;
+    CK(cudaMalloc(&d_occ, nc));
+    CK(cudaMemsetAsync(d_occ, 0, nc, c->stream));
+    if (n_boxes > 0) {
+        CK(cudaMalloc(&d_boxes, (size_t)n_boxes * 6 * sizeof(float)));
+        CK(cudaMemcpyAsync(d_boxes, boxes, (size_t)n_boxes * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        launch_edt_raster(d_boxes, n_boxes, c->hp.world_res, dims, mk, d_occ, c->stream);
+        c->launches++;
+    }
+    const int rc = edt_from_occupancy_dev(c, d_occ, dims, mk, maxdist);
+    cudaFree(d_occ);
+    if (d_boxes) cudaFree(d_boxes);
+    return rc;
+}
+
+int dlsc_build_edt_occupancy(dlsc_ctx* c, const uint8_t* occ, double maxdist) {
+    if (!c || !occ) return fail("dlsc_build_edt_occupancy: null argument");
+    CK(cudaSetDevice(c->device));
+    int32_t dims[3], mk[3];
+    dlsc_edt_dims(c, dims, mk);
+    const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+    if (nc == 0 || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail("dlsc_build_edt_occupancy: empty world");
+    uint8_t* d_occ = nullptr;
+    CK(cudaMalloc(&d_occ, nc));
+    CK(cudaMemcpyAsync(d_occ, occ, nc, cudaMemcpyHostToDevice, c->stream));
+    const int rc = edt_from_occupancy_dev(c, d_occ, dims, mk, maxdist);
+    cudaFree(d_occ);
+    return rc;
+}
+
+int dlsc_get_edt(dlsc_ctx* c, float* dist, int32_t* obst) {
+    if (!c || !dist || !obst) return fail("dlsc_get_edt: null argument");
+    if (!c->have_edt || !c->edt_cells) return fail("dlsc_get_edt: no grid");
+    CK(cudaSetDevice(c->device));
+    const EdtDev& E = c->S.edt;
+    const size_t nc = (size_t)E.dims[0] * E.dims[1] * E.dims[2];
+    float* d_dist = nullptr; int32_t* d_obst = nullptr;
+    CK(cudaMalloc(&d_dist, nc * sizeof(float)));
+    CK(cudaMalloc(&d_obst, nc * 3 * sizeof(int32_t)));
+    launch_edt_unpack(c->edt_cells, d_dist, d_obst, nc, c->stream);
+    c->launches++;
+    CK(cudaMemcpyAsync(dist, d_dist, nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(obst, d_obst, nc * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_dist); cudaFree(d_obst);
+    return 0;
+}
+
+double dlsc_edt_build_ms(const dlsc_ctx* c) { return c ? c->edt_build_ms : -1.0; }
 
 // (Re)build the lattice-vertex mask for the current grid and margin.  The mask is dropped (record path only)
 // when a tabulated decision is not robust (edt_vertex_mask) or the grid is too tall for the z tables.

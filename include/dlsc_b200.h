@@ -122,6 +122,22 @@ void* dlsc_get_stream(dlsc_ctx* ctx);
 int dlsc_set_edt(dlsc_ctx* ctx, const float* dist, const int32_t* obst, const int32_t dims[3],
                  const int32_t min_key[3], double res);
 
+/* Build the same grid on the device instead (once per mission), replacing MapManager::updateOctreeFromCSV
+ * (src/map_manager.cpp:264-316: CSV rows "cx,cy,cz,sx,sy,sz" -> occupied voxels) and MapManager::setGlobalMap
+ * (src/map_manager.cpp:61-82: DynamicEDTOctomap(maxdist = 1.0, octree, world_min, world_max).update()).
+ * boxes [n_boxes][6] float as parsed from the CSV; maxdist in metres (the reference passes 1.0), capped to
+ * int(maxdist/res + 1) <= 16 cells.  Exact Euclidean distances; ties between equidistant occupied cells go to the
+ * lowest linear cell index (dynamicEDT3D's own tie-breaking is third-party and unpinned).
+ * The grid extent comes from the context's world box (dlsc_edt_dims).  dlsc_build_edt_occupancy takes a ready
+ * occupancy grid instead (1 byte per cell, non-zero = occupied, layout as dlsc_set_edt), e.g. from an octomap .bt
+ * file expanded by the caller.  dlsc_get_edt reads the current grid back in the dlsc_set_edt layout. */
+int dlsc_edt_dims(const dlsc_ctx* ctx, int32_t dims[3], int32_t min_key[3]);
+int dlsc_build_edt(dlsc_ctx* ctx, const float* boxes, int n_boxes, double maxdist);
+int dlsc_build_edt_occupancy(dlsc_ctx* ctx, const uint8_t* occ, double maxdist);
+int dlsc_get_edt(dlsc_ctx* ctx, float* dist, int32_t* obst);
+/* device milliseconds of the three distance-transform passes of the last dlsc_build_edt* call */
+double dlsc_edt_build_ms(const dlsc_ctx* ctx);
+
 int dlsc_set_agent_props(dlsc_ctx* ctx, const dlsc_agent_props* props);
 
 /* Reset planner state of the local block (planner_seq = 0, initialize_sfc = true,

@@ -75,6 +75,11 @@ public:
     std::vector<int32_t> obst;        // [ncell][3]
     int32_t dims[3] = {0, 0, 0}, min_key[3] = {0, 0, 0};
     double res = 0.1;
+    // alternative: let the library build the grid on the GPU from the mission's obstacle CSV rows
+    // (MapManager::updateOctreeFromCSV + setGlobalMap, src/map_manager.cpp:61-82, 264-316 -> dlsc_build_edt)
+    std::vector<float> boxes;         // [nb][6] cx, cy, cz, sx, sy, sz; used when from_boxes
+    bool from_boxes = false;
+    double maxdist = 1.0;             // DynamicEDTOctomap(maxdist = 1.0, ...)
 };
 namespace Eigen { struct MatrixXd {}; }
 #else
@@ -291,7 +296,10 @@ public:
     void set_distmap(const std::shared_ptr<DynamicEDTOctomap>& d) {
 #ifdef DLSC_COMPAT_STANDALONE
         if (!d || d.get() == distmap_seen) return;
-        check(dlsc_set_edt(ctx, d->dist.data(), d->obst.data(), d->dims, d->min_key, d->res), "dlsc_set_edt");
+        if (d->from_boxes)
+            check(dlsc_build_edt(ctx, d->boxes.data(), (int)(d->boxes.size() / 6), d->maxdist), "dlsc_build_edt");
+        else
+            check(dlsc_set_edt(ctx, d->dist.data(), d->obst.data(), d->dims, d->min_key, d->res), "dlsc_set_edt");
         distmap_seen = d.get();
 #else
         (void)d;   // with the real dynamicEDT3D: export its grid once, see INTEGRATION.md

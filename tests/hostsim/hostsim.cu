@@ -7,12 +7,14 @@
 // (SIMT mapping, synchronisation, shuffles).  It is not a fallback: the product loader
 // (dlsc_gc_planner_b200/capi.py) only ever opens libdlsc_b200.so.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/dlsc_b200.h"
+#include "../../dlsc_gc_planner_b200/csrc/dlsc_edt.cuh"
 #include "../../dlsc_gc_planner_b200/csrc/dlsc_qp_gi.cuh"
 #include "../../dlsc_gc_planner_b200/csrc/dlsc_stages.cuh"
 
@@ -131,6 +133,67 @@ int dlsc_set_edt(dlsc_ctx* c, const float* dist, const int32_t* obst, const int3
     c->mask_dirty = true;
     return 0;
 }
+
+// the device grid construction (dlsc_kernels_edt.cu) cell by cell with the same cores
+int dlsc_edt_dims(const dlsc_ctx* c, int32_t dims[3], int32_t min_key[3]) {
+    const double inv = 1.0 / c->P.world_res;
+    for (int k = 0; k < 3; k++) {
+        const int lo = (int)std::floor(inv * c->P.world_min[k]);
+        const int hi = (int)std::floor(inv * c->P.world_max[k]);
+        min_key[k] = lo; dims[k] = hi - lo + 1;
+    }
+    return 0;
+}
+static int edt_from_occ(dlsc_ctx* c, const std::vector<uint8_t>& occ, const int32_t dims[3], const int32_t mk[3], double maxdist) {
+    const double res = c->P.world_res;
+    const int maxd = (int)(maxdist / res + 1), R = maxd - 1;
+    EdtDistTab tab; float cap;
+    if (!edt_make_tab(res, maxd, &tab, &cap)) return fail("dlsc_build_edt: maxdist / resolution + 1 must be in [1, 16] cells");
+    const size_t nc = occ.size();
+    std::vector<uint32_t> ta(nc), tb(nc);
+    for (size_t i = 0; i < nc; i++) ta[i] = edt_pass_z_cell(occ.data(), i, dims[2], R);
+    for (size_t i = 0; i < nc; i++) tb[i] = edt_pass_y_cell(ta.data(), i, dims[1], dims[2], R);
+    std::vector<float> dist(nc); std::vector<int32_t> obst(3 * nc);
+    for (size_t i = 0; i < nc; i++) {
+        const EdtRecord r = edt_pass_x_cell(tb.data(), i, dims[0], dims[1], dims[2], R, maxd * maxd, cap, tab);
+        memcpy(&dist[i], &r.x, 4); obst[3 * i] = r.y; obst[3 * i + 1] = r.z; obst[3 * i + 2] = r.w;
+    }
+    return dlsc_set_edt(c, dist.data(), obst.data(), dims, mk, res);
+}
+int dlsc_build_edt(dlsc_ctx* c, const float* boxes, int nb, double maxdist) {
+    int32_t dims[3], mk[3];
+    dlsc_edt_dims(c, dims, mk);
+    std::vector<uint8_t> occ((size_t)dims[0] * dims[1] * dims[2], 0);
+    const double res = c->P.world_res, inv = 1.0 / res;
+    for (int b = 0; b < nb; b++) {
+        int s[3], e[3];
+        for (int k = 0; k < 3; k++) edt_box_range(boxes[6 * b + k], boxes[6 * b + 3 + k], res, &s[k], &e[k]);
+        for (int i = s[0]; i < e[0]; i++)
+            for (int j = s[1]; j < e[1]; j++)
+                for (int k = s[2]; k < e[2]; k++) {
+                    const int mx = edt_voxel_cell(i, res, inv, mk[0]), my = edt_voxel_cell(j, res, inv, mk[1]),
+                              mz = edt_voxel_cell(k, res, inv, mk[2]);
+                    if (mx >= 0 && mx < dims[0] && my >= 0 && my < dims[1] && mz >= 0 && mz < dims[2])
+                        occ[((size_t)mx * dims[1] + my) * dims[2] + mz] = 1;
+                }
+    }
+    return edt_from_occ(c, occ, dims, mk, maxdist);
+}
+int dlsc_build_edt_occupancy(dlsc_ctx* c, const uint8_t* occ_in, double maxdist) {
+    int32_t dims[3], mk[3];
+    dlsc_edt_dims(c, dims, mk);
+    std::vector<uint8_t> occ(occ_in, occ_in + (size_t)dims[0] * dims[1] * dims[2]);
+    return edt_from_occ(c, occ, dims, mk, maxdist);
+}
+int dlsc_get_edt(dlsc_ctx* c, float* dist, int32_t* obst) {
+    if (!c->have_edt) return fail("dlsc_get_edt: no grid");
+    for (size_t i = 0; i < c->cells.size(); i++) {
+        memcpy(&dist[i], &c->cells[i].x, 4);
+        obst[3 * i] = c->cells[i].y; obst[3 * i + 1] = c->cells[i].z; obst[3 * i + 2] = c->cells[i].w;
+    }
+    return 0;
+}
+double dlsc_edt_build_ms(const dlsc_ctx*) { return 0.0; }
 
 // same lazy build as dlsc_api.cu build_vertex_mask
 static void build_vertex_mask(dlsc_ctx* c) {
