@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdlsc_b200.so")
+# DLSC_B200_LIB: another build of the same CUDA library (A/B variants of a kernel built with `make OUT=... OBJ=...`)
+LIB_PATH = os.environ.get("DLSC_B200_LIB") or os.path.join(_HERE, "libdlsc_b200.so")
 
 OK, QP_MAXITER, QP_NUMERIC, SFC_INIT_FAILED, GOAL_INFEASIBLE, SFC_REUSED, NBR_OVERFLOW, QP_IPM_USED = 0, 1, 2, 4, 8, 16, 32, 64
 STAGE_PREDICT, STAGE_NBR, STAGE_LSC, STAGE_SFC, STAGE_GOAL, STAGE_QP, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63

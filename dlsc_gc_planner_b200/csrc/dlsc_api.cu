@@ -32,6 +32,10 @@ struct dlsc_ctx {
     int seq = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // SFC runs beside neighbour search + LSC (both only need the prediction stage): fork / join on a second stream
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;               // DLSC_OVERLAP=0 disables; per-stage timing (dlsc_enable_timing) serialises too
     bool rec_owned = false;
     bool have_edt = false;
     int4* edt_cells = nullptr;
@@ -174,6 +178,13 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
         for (int e = 0; e < hp->M * kP; e++) { P.tk[e] = (float)time; time += hp->dt / hp->n; }
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    {
+        const char* ov = getenv("DLSC_OVERLAP");
+        c->overlap = !(ov && ov[0] == '0');
+    }
     c->own_stream = true;
     memset(c->t_ms, 0, sizeof(c->t_ms));
 
@@ -206,6 +217,8 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.counters, DLSC_N_COUNTERS);
     rc |= dev_alloc(c, &S.qp_next, 4);
     rc |= dev_alloc(c, &S.qp_list, NL);
+    rc |= dev_alloc(c, &S.qp_list_gi, (size_t)NL);
+    rc |= dev_alloc(c, &S.qp_seed, (size_t)NL * 4);
     if (rc) { dlsc_destroy(c); return -1; }
 
     build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->w_terminal, hp->comm_range > 0, c->th);
@@ -233,6 +246,9 @@ void dlsc_destroy(dlsc_ctx* c) {
     if (c->edt_centre) cudaFree(c->edt_centre);
     if (c->edt_mask) cudaFree(c->edt_mask);
     if (c->edt_sat) cudaFree(c->edt_sat);
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto& e : c->evpool) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -553,11 +569,20 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     if (tm) CK(cudaEventRecord(ev[0], st));
     if (mask & DLSC_STAGE_PREDICT) { launch_predict(Pr, Sx, seq, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[1], st));
+    const bool sfc_on = (mask & DLSC_STAGE_SFC) && c->P.use_sfc;
+    const bool fork = sfc_on && (mask & DLSC_STAGE_LSC) && !tm && c->overlap && c->side_stream;
+    if (fork) {   // k_sfc is latency bound, k_lsc FP64 bound: they share the SMs well
+        CK(cudaEventRecord(c->ev_fork, st));
+        CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+        launch_sfc(Pr, Sx, c->side_stream); c->launches++;
+        CK(cudaEventRecord(c->ev_join, c->side_stream));
+    }
     if (mask & DLSC_STAGE_NBR) { launch_neighbours(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[2], st));
     if (mask & DLSC_STAGE_LSC) { launch_lsc(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[3], st));
-    if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc) { launch_sfc(Pr, Sx, st); c->launches++; }
+    if (fork) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    else if (sfc_on) { launch_sfc(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[4], st));
     if (mask & DLSC_STAGE_GOAL) { launch_goal(Pr, Sx, st); c->launches++; }
     else if (mask & DLSC_STAGE_QP) { launch_goal_copy(Pr, Sx, st); c->launches++; }   // QP alone: goal from the record
@@ -662,7 +687,7 @@ static int h2d(dlsc_ctx* c, void* dev, const void* host, size_t bytes) {
 }
 // injected stage inputs invalidate the QP row screen that k_lsc derived from the previous ones: every item "near"
 static int screen_off(dlsc_ctx* c) {
-    CK(cudaMemsetAsync(c->S.lsc_near, 1, (size_t)c->P.NL * c->P.K * c->P.M, c->stream));
+    CK(cudaMemsetAsync(c->S.lsc_near, 0, (size_t)c->P.NL * c->P.K * c->P.M * sizeof(float), c->stream));   // slack 0: never screened
     return 0;
 }
 int dlsc_set_init_traj(dlsc_ctx* c, const float* t) {

@@ -27,7 +27,7 @@ struct DevState {
     float* lsc_normal;         // [NL][K][M][3]
     double* lsc_d;             // [NL][K][M][P]
     float* lsc_anchor_last;    // [NL][K][3]
-    uint8_t* lsc_near;         // [NL][K][M] QP row screen: 1 = the item's rows can come within qp_screen of the initial trajectory
+    float* lsc_near;           // [NL][K][M] QP row screen: smallest normalised slack of the item's rows at the initial trajectory
     float* sfc;                // [NL][M][6]
     float* traj;               // [NL][M][P][3]  QP result (or failsafe)
     double* qp_x;              // [NL][D][M][P]
@@ -35,12 +35,14 @@ struct DevState {
     int32_t *qp_iters, *status;
     unsigned long long* counters;   // [8]
     double* qp_scratch;        // [qp_ctas][qp_scratch_doubles]
-    int* qp_next;              // [4]: [1] length of qp_list, [2] work counter of the fallback kernel
+    int* qp_next;              // [4]: [0] light / [3] heavy agents in qp_list_gi, [1] length of qp_list, [2] work counter of k_qp
     int* qp_list;              // [NL] agents queued for the interior-point fallback
+    int* qp_list_gi;           // [NL] agents the fast path (k_qp_fast) could not finish: they run the dual active set
+    double* qp_seed;           // [NL][4] {violation, row id, screened, violated rows} of the scan at the unconstrained optimum
     EdtDev edt;
 };
 
-struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; };
+struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; size_t fast_smem; };
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
 void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);

@@ -87,7 +87,10 @@ void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
 // homogeneous: similar geometry, similar GJK depth) before the last-segment items (segment-segment closest points,
 // a different code path).
 constexpr int kLscThreads = 128;
-__global__ void __launch_bounds__(kLscThreads, 4) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+#ifndef DLSC_LSC_MINB
+#define DLSC_LSC_MINB 4
+#endif
+__global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float s_init[kMaxPts * 3];
     extern __shared__ int s_dyn[];                // [K] neighbour indices | [K][5] neighbour radius, downwash, goal
     int* s_nbr = s_dyn;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(kLscThreads, 4) k_lsc(const __grid_constant__ 
         int it = 0;
         lsc_segment(P, s_init, S.pred_traj + (size_t)s_nbr[c] * npt * 3, goal_a, v3(s_nj[c][2], s_nj[c][3], s_nj[c][4]),
                     r_a, dw_a, s_nj[c][0], s_nj[c][1], m, S.lsc_normal + (pr * M + m) * 3,
-                    S.lsc_d + (pr * M + m) * kP, S.lsc_anchor_last + pr * 3, &it, S.lsc_near + pr * M + m, P.qp_screen);
+                    S.lsc_d + (pr * M + m) * kP, S.lsc_anchor_last + pr * 3, &it, S.lsc_near + pr * M + m);
         it_sum += it;
     }
     const int tot = __reduce_add_sync(0xffffffffu, it_sum);

@@ -1,6 +1,8 @@
 // dlsc_kernels_qp.cu -- sm_100a kernel of the batched min-jerk QP (interior point, FP64 pipe).
 // Persistent CTAs: grid = SMs x resident CTAs, each CTA pulls agents from a device-side counter
 // (agents differ widely in neighbour count, hence in row count) and reuses one global scratch slab.
+#include <cstdlib>
+
 #include "dlsc_kernels.h"
 #include "dlsc_qp_gi.cuh"
 
@@ -11,6 +13,9 @@ constexpr int kQpThreads = 128;     // interior-point fallback kernel
 #define DLSC_GI_THREADS 128
 #endif
 constexpr int kGiThreads = DLSC_GI_THREADS;
+#ifndef DLSC_GI_MINB
+#define DLSC_GI_MINB 6
+#endif
 
 __device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState& S, const QpTab& T, int la, QpIn& in, QpOut& out) {
     const int npt = P.M * kP;
@@ -36,20 +41,80 @@ __device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState
     out.rows = nullptr;
 }
 
-// Primary kernel: one small CTA per agent, dual active set off the constraint arrays (dlsc_qp_gi.cuh).
-// Agents it cannot finish are appended to S.qp_list for k_qp.
-__global__ void __launch_bounds__(kGiThreads) k_qp_gi(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
-                                                       const __grid_constant__ QpTab T) {
+// Fast path: one warp per agent, no block-level synchronisation.  Agents whose unconstrained optimum is feasible
+// (most of a swarm in transit) are finished here; the others are queued, with the violated row found, for k_qp_gi.
+constexpr int kFastWarps = 4;
+#ifndef DLSC_GI_HEAVY_ROWS
+#define DLSC_GI_HEAVY_ROWS 3
+#endif
+constexpr int kGiHeavyRows = DLSC_GI_HEAVY_ROWS;
+#ifndef DLSC_FAST_MINB
+#define DLSC_FAST_MINB 8
+#endif
+__global__ void __launch_bounds__(kFastWarps * 32, DLSC_FAST_MINB) k_qp_fast(const __grid_constant__ DevParams P,
+                                                                             const __grid_constant__ DevState S,
+                                                                             const __grid_constant__ QpTab T, int per_warp_doubles) {
     extern __shared__ __align__(16) double smem[];
+    const int w = threadIdx.x >> 5;
+    const int la = blockIdx.x * kFastWarps + w;
+    if (la >= P.NL) return;
+    QpSmem sm;
+    fast_smem_carve(T, smem + (size_t)w * per_warp_doubles, sm);
+    Cta c; c.tid = threadIdx.x & 31; c.nthr = 32; c.red = nullptr; c.warp = true;
+    QpIn in; QpOut out;
+    qp_load_agent(P, S, T, la, in, out);
+    long long rows = 0;
+    if (c.tid == 0) out.rows = &rows;
+    double* seed = S.qp_seed + (size_t)la * 4;
+    const bool done = qp_agent_fast(c, P, T, in, out, sm, seed);
+    if (c.tid == 0) {
+        if (!done) {
+            // longest-job-first: agents with several violated rows (they iterate longest) are queued from the front
+            // of the list and started first, the others from the back; k_qp_gi's runtime is set by its tail
+            if (seed[3] >= (double)kGiHeavyRows) S.qp_list_gi[atomicAdd(S.qp_next + 3, 1)] = la;
+            else S.qp_list_gi[P.NL - 1 - atomicAdd(S.qp_next + 0, 1)] = la;
+        } else atomicAdd(S.counters + 4, (unsigned long long)rows);
+    }
+}
+
+// Dual active set (dlsc_qp_gi.cuh): one small CTA per queued agent, straight off the constraint arrays.
+// Agents it cannot finish are appended to S.qp_list for k_qp.  from_list = 0: every agent, no seed.
+__global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
+                                                                     const __grid_constant__ QpTab T, int from_list) {
+    extern __shared__ __align__(16) double smem[];
+    int la = blockIdx.x;
+    if (from_list) {
+        const int n_heavy = S.qp_next[3], n_light = S.qp_next[0], b = blockIdx.x;
+        if (b >= n_heavy + n_light) return;
+        la = (b < n_heavy) ? S.qp_list_gi[b] : S.qp_list_gi[P.NL - 1 - (b - n_heavy)];
+    }
     QpSmem sm;
     gi_smem_carve(T, smem, sm);
     Cta c; c.tid = threadIdx.x; c.nthr = blockDim.x; c.red = sm.red;
-    const int la = blockIdx.x;
+#ifdef DLSC_QP_CYCLES
+    const long long t_begin = clock64();
+    long long ticks[12] = {t_begin, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (threadIdx.x == 0) c.ticks = ticks;
+#endif
     QpIn in; QpOut out;
     qp_load_agent(P, S, T, la, in, out);
     long long rows = 0;
     if (threadIdx.x == 0) out.rows = &rows;
-    const bool done = qp_agent_gi(c, P, T, in, out, sm);
+    const bool done = qp_agent_gi(c, P, T, in, out, sm, from_list ? S.qp_seed + (size_t)la * 4 : nullptr);
+#ifdef DLSC_QP_CYCLES
+    if (threadIdx.x == 0) {                                                 // diagnostic build only (scripts/qp_hist.py)
+        S.viol[la] = (double)(clock64() - t_begin);
+        // phase sums over the agents of this kernel: counters 9..15 <- prologue (1+2), map_x (3), far2 (4), scan (5),
+        // candidate + Hinv staging (8), w = H^-1 a (9), serial step of thread 0 (10) ; y update (11) goes to counter 0 + 64-bit pack
+        atomicAdd(S.counters + 9, (unsigned long long)(ticks[1] + ticks[2]));
+        atomicAdd(S.counters + 10, (unsigned long long)ticks[3]);
+        atomicAdd(S.counters + 11, (unsigned long long)ticks[5]);
+        atomicAdd(S.counters + 12, (unsigned long long)ticks[8]);
+        atomicAdd(S.counters + 13, (unsigned long long)ticks[9]);
+        atomicAdd(S.counters + 14, (unsigned long long)ticks[10]);
+        atomicAdd(S.counters + 15, (unsigned long long)ticks[11]);
+    }
+#endif
     if (threadIdx.x == 0) {
         if (!done) S.qp_list[atomicAdd(S.qp_next + 1, 1)] = la;
         else {
@@ -101,6 +166,8 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     L.gi_smem = gi_smem_doubles(T, P.K) * sizeof(double);
     cudaFuncSetAttribute(k_qp_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
+    L.fast_smem = ((fast_smem_doubles(T, P.K) + 1) / 2 * 2) * sizeof(double) * kFastWarps;
+    cudaFuncSetAttribute(k_qp_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     int per_sm = 1, sms = 148;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp, kQpThreads, L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -115,9 +182,19 @@ int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLau
     cudaMemsetAsync(S.qp_next, 0, 4 * sizeof(int), st);
     const int ctas = L.ctas < P.NL ? L.ctas : P.NL;
     const int all = (P.qp_solver == 1) ? 1 : 0;
-    if (!all) k_qp_gi<<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T);
+    int n = 1;
+    if (!all) {
+        static const bool no_fast = [] { const char* e = getenv("DLSC_QP_FAST"); return e && e[0] == '0'; }();
+        if (no_fast) { k_qp_gi<<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 0); n = 2; }
+        else {
+            k_qp_fast<<<(P.NL + kFastWarps - 1) / kFastWarps, kFastWarps * 32, L.fast_smem, st>>>(
+                P, S, T, (int)(L.fast_smem / sizeof(double) / kFastWarps));
+            k_qp_gi<<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 1);
+            n = 3;
+        }
+    }
     k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
-    return all ? 1 : 2;
+    return n;
 }
 
 // ---- FP64 FMA peak probe: 8 independent dependent-FMA chains per thread, 1024 threads, 2 CTAs per SM ----

@@ -31,9 +31,20 @@ namespace dlsc {
 struct Cta {
     int tid, nthr;
     double* red;     // >= 3 * 32 doubles of shared scratch
+#ifdef DLSC_QP_CYCLES
+    long long* ticks = nullptr;                    // diagnostic build: cycles of thread 0 per phase; ticks[0] = last stamp
+    DLSC_HD void tick(int k) const {
+#ifdef __CUDA_ARCH__
+        if (ticks) { const long long now = clock64(); ticks[k] += now - ticks[0]; ticks[0] = now; }
+#endif
+    }
+#else
+    DLSC_HD void tick(int) const {}
+#endif
+    bool warp = false;   // true: the "CTA" is one warp (nthr == 32): warp-level synchronisation only, red unused
     DLSC_HD void sync() const {
 #ifdef __CUDA_ARCH__
-        __syncthreads();
+        if (warp) __syncwarp(); else __syncthreads();
 #endif
     }
     // op: 0 sum, 1 max, 2 min.  Deterministic (fixed tree).  All threads get the result.
@@ -46,12 +57,55 @@ struct Cta {
             const double tc = __shfl_xor_sync(0xffffffffu, c, o);
             a = comb(a, ta, opa); b = comb(b, tb, opb); c = comb(c, tc, opc);
         }
+        if (warp) return;
         const int w = tid >> 5, nw = nthr >> 5;
         __syncthreads();
         if ((tid & 31) == 0) { red[w] = a; red[32 + w] = b; red[64 + w] = c; }
         __syncthreads();
         a = red[0]; b = red[32]; c = red[64];
         for (int i = 1; i < nw; i++) { a = comb(a, red[i], opa); b = comb(b, red[32 + i], opb); c = comb(c, red[64 + i], opc); }
+#endif
+    }
+    // one value only (same tree)
+    DLSC_HD void reduce1(double& a, int opa) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = comb(a, __shfl_xor_sync(0xffffffffu, a, o), opa);
+        if (warp) return;
+        const int w = tid >> 5, nw = nthr >> 5;
+        __syncthreads();
+        if ((tid & 31) == 0) red[w] = a;
+        __syncthreads();
+        a = red[0];
+        for (int i = 1; i < nw; i++) a = comb(a, red[i], opa);
+#endif
+    }
+    // (value, id): the largest value, ties to the smallest id.  All threads get the result.
+    // m: a third value max-reduced, n: a fourth value summed, on the same tree.
+    DLSC_HD void reduce_argmax(double& v, double& id, double& m, double& n) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double tv = __shfl_xor_sync(0xffffffffu, v, o);
+            const double ti = __shfl_xor_sync(0xffffffffu, id, o);
+            const double tm = __shfl_xor_sync(0xffffffffu, m, o);
+            const double tn = __shfl_xor_sync(0xffffffffu, n, o);
+            if (tv > v || (tv == v && ti < id)) { v = tv; id = ti; }
+            m = tm > m ? tm : m;
+            n += tn;
+        }
+        if (warp) return;
+        const int w = tid >> 5, nw = nthr >> 5;
+        __syncthreads();
+        if ((tid & 31) == 0) { red[w] = v; red[32 + w] = id; red[64 + w] = m; red[16 + w] = n; }   // nw <= 16
+        __syncthreads();
+        v = red[0]; id = red[32]; m = red[64]; n = red[16];
+        for (int i = 1; i < nw; i++) {
+            const double tv = red[i], ti = red[32 + i], tm = red[64 + i];
+            if (tv > v || (tv == v && ti < id)) { v = tv; id = ti; }
+            m = tm > m ? tm : m;
+            n += red[16 + i];
+        }
 #endif
     }
     static DLSC_HD double comb(double x, double y, int op) {
@@ -73,8 +127,8 @@ struct QpIn {
     const double* d;           // [K][M][P]
     const float* anchor_last;  // [K][3]
     const float* pred_traj;    // [N][M][P][3] (anchors of segments < M-1)
-    const uint8_t* near;       // [K][M] row screen of k_lsc (or null): 0 = the item's rows stay >= qp_screen away from
-                               //        violation while |x_pt - init_pt| < qp_screen
+    const float* near;         // [K][M] row screen of k_lsc (or null): smallest normalised slack of the item's rows at the
+                               //        initial trajectory; the rows cannot be violated while |x_pt - init_pt| stays below it
 };
 struct QpOut {
     float* traj;               // [M][P][3]
@@ -86,6 +140,8 @@ struct QpOut {
 // shared-memory carve-up (doubles unless noted)
 struct QpSmem {
     double *W, *invp, *pan, *y, *dy, *rd, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
+    float* sfcs;               // dual active set only: staged copy of the agent's SFC boxes [M][6]
+    double* dev;               // dual active set only: [M] largest |x_pt - init_pt| per segment of the current iterate
     int* off;                  // [npt + 2] segment offsets of the LSC row list (+ scratch word)
     uint8_t* act;              // [M][Kcap]
 };
@@ -137,6 +193,7 @@ DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     s.S = p; p += 6 * T.npt;
     s.cst = p; p += 16;
     s.red = p; p += 96;
+    s.sfcs = nullptr; s.dev = nullptr;
     s.off = reinterpret_cast<int*>(p); p += (T.npt + 4) / 2 + 1;
     s.act = reinterpret_cast<uint8_t*>(p);
     (void)Kcap;

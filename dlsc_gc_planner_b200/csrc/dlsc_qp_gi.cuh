@@ -19,8 +19,9 @@
 
 namespace dlsc {
 
+constexpr int kSfcStage = kMaxM * 6 / 2;        // doubles holding the agent's [M][6] float boxes
 DLSC_HD size_t gi_smem_doubles(const QpTab& T, int Kcap) {
-    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + 96 + ((size_t)Kcap + 1) / 2;
+    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + kSfcStage + kMaxM + 96 + ((size_t)Kcap + 1) / 2;
 }
 DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     double* p = base;
@@ -28,11 +29,31 @@ DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     s.y = p; p += T.ny; s.dy = p; p += T.ny; s.ax1 = p; p += T.ny;
     s.x = p; p += T.nx;
     s.cst = p; p += 16;
+    s.sfcs = reinterpret_cast<float*>(p); p += kSfcStage;
+    s.dev = p; p += kMaxM;
     s.red = p; p += 96;
     s.off = reinterpret_cast<int*>(p);          // [Kcap] global indices of the neighbours
     s.invp = s.pan = s.rd = s.dx = s.ax2 = s.V1 = s.V2 = s.DD = s.S = nullptr;
     s.act = nullptr;
 }
+// the fast path (qp_agent_fast, one warp per agent) only needs y, x and the staged inputs
+DLSC_HD size_t fast_smem_doubles(const QpTab& T, int Kcap) {
+    return (size_t)T.ny + (size_t)T.nx + 16 + kSfcStage + kMaxM + ((size_t)Kcap + 1) / 2;
+}
+DLSC_HD void fast_smem_carve(const QpTab& T, double* base, QpSmem& s) {
+    double* p = base;
+    s.y = p; p += T.ny;
+    s.x = p; p += T.nx;
+    s.cst = p; p += 16;
+    s.sfcs = reinterpret_cast<float*>(p); p += kSfcStage;
+    s.dev = p; p += kMaxM;
+    s.off = reinterpret_cast<int*>(p);
+    s.W = s.dy = s.ax1 = s.red = nullptr;
+    s.invp = s.pan = s.rd = s.dx = s.ax2 = s.V1 = s.V2 = s.DD = s.S = nullptr;
+    s.act = nullptr;
+}
+
+constexpr double kGiTol = 1e-10;   // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
 
 struct PairRowD { int fam, k, pa, pb; };
 DLSC_HD PairRowD pair_desc(const QpTab& T, int r) {
@@ -58,23 +79,32 @@ DLSC_HD void pair_violation(const DevParams& P, const QpTab& T, const QpIn& in, 
 
 // most violated row over all inequality rows; every thread returns the same (vmax, id)
 //   id < 2 np: pattern row r = id >> 1, side id & 1 (0: upper, 1: lower);  else LSC row o = id - 2 np = pt * Kcap + cc
+// Row screen: k_lsc stored, per (neighbour, segment) item, the smallest normalised slack of its rows at the agent's
+// initial trajectory.  With dev[m] = the largest |x_pt - init_pt| over the constrained points of segment m of the
+// iterate being scanned, a row of slack s can only be violated when dev[m] >= s (Cauchy-Schwarz), so items with
+// slack > dev[m] + margin are not evaluated (margin 1e-3 m covers the rounding of the two evaluations).  Exact, and
+// it adapts to every iterate: far from the initial trajectory more rows are evaluated, never fewer than needed.
+constexpr double kScreenMargin = 1e-3;
 DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
-                     const int* sm_nbr, bool screened, double& vmax_out, double& id_out) {
+                     const int* sm_nbr, bool screened, const double* dev, double& vmax_out, double& id_out,
+                     double& nviol_out) {
     const int npt = T.npt, np = T.np, Kc = P.K, K = in.K;
     const bool D3 = (P.D == 3);
     double best = -1e300, best_id = 1e300;
+    int n_bad = 0;                                                 // violated rows seen by this thread
     for (int r = c.tid; r < np; r += c.nthr) {
         double vh, vl;
         pair_violation(P, T, in, qc, r, x, vh, vl);
         if (vh > best) { best = vh; best_id = 2.0 * r; }
         if (vl > best) { best = vl; best_id = 2.0 * r + 1.0; }
+        n_bad += (vh > kGiTol) + (vl > kGiTol);
     }
     // LSC rows: one work item = one (neighbour, segment) = up to 6 rows sharing a normal; its d values and
     // anchors are contiguous in memory (traj_optimizer.cpp:412-450: -n.x <= -(n.anchor + d))
     const int M = P.M, items = K * M;
     for (int e = c.tid; e < items; e += c.nthr) {
-        if (screened && !in.near[e]) continue;                                      // row screen of k_lsc
         const int cc = e / M, m = e - cc * M;
+        if (screened && (double)in.near[e] > dev[m] + kScreenMargin) continue;      // row screen
         const float* nr = in.normal + ((size_t)cc * M + m) * 3;
         const V3 nv = v3_load(nr);
         const double* dd = in.d + ((size_t)cc * M + m) * kP;
@@ -100,51 +130,68 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             const double v = -(n0 * x[pt] + n1 * x[npt + pt] + (D3 ? n2 * x[2 * npt + pt] : 0.0)) - b;
             const double id = 2.0 * np + (double)(pt * Kc + cc);
             if (v > best || (v == best && id < best_id)) { best = v; best_id = id; }
+            n_bad += (v > kGiTol);
         }
     }
-    double vmax = best, d0 = 0.0, d1 = 0.0;
-    c.reduce3(vmax, 1, d0, 0, d1, 0);
-    double idsel = (best == vmax) ? best_id : 1e300;
-    d0 = 0.0; d1 = 0.0;
-    c.reduce3(idsel, 2, d0, 0, d1, 0);
-    vmax_out = vmax; id_out = idsel;
+    double nvd = (double)n_bad, unused = 0.0;
+    c.reduce_argmax(best, best_id, unused, nvd);
+    vmax_out = best; id_out = best_id; nviol_out = nvd;
+}
+
+// map y -> x, the per-segment deviation of x from the initial trajectory, then one scan for the most violated row
+DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
+                             const QpSmem& sm, bool screened, double& vmax, double& idsel, double* nviol = nullptr) {
+    map_x(c, T, sm.y, sm.cst, sm.x);
+    c.sync();
+    c.tick(3);
+    if (screened) {
+        const int npt = T.npt;
+        const bool D3 = (P.D == 3);
+        for (int m = c.tid; m < P.M; m += c.nthr) {
+            double far2 = 0.0;
+            for (int i = (m == 0 ? 3 : 0); i < kP; i++) {                  // points 0..2 of segment 0 carry no LSC rows
+                const int pt = m * kP + i;
+                const double ex = sm.x[pt] - (double)in.init_traj[pt * 3];
+                const double ey = sm.x[npt + pt] - (double)in.init_traj[pt * 3 + 1];
+                const double ez = D3 ? sm.x[2 * npt + pt] - (double)in.init_traj[pt * 3 + 2] : 0.0;
+                const double r2 = ex * ex + ey * ey + ez * ez;
+                far2 = (r2 > far2) ? r2 : far2;
+            }
+            sm.dev[m] = sqrt(far2);
+        }
+        c.sync();
+    }
+    c.tick(4);
+    double nv = 0.0;
+    gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, sm.dev, vmax, idsel, nv);
+    if (nviol) *nviol = nv;
+    c.tick(5);
 }
 
 // Returns 0 = optimal, kStQpMaxIter = infeasible, -1 = give up.  y in sm.y, x in sm.x on return.
 DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
-                     const QpSmem& sm, int* iters_out, double* viol_out) {
+                     const QpSmem& sm, const double* seed, int* iters_out, double* viol_out) {
     const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, np = T.np, Kc = P.K;
     const bool D3 = (D == 3);
     GiSmem g;
     gi_carve(T, sm.W, g);
-    const double tol = 1e-10;    // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
+    const double tol = kGiTol;
     int q = 0, iters = 0, status = -1;
     double viol_p = 0.0, u_p = 0.0;
     bool same_p = false, have_hinv = false;
-    // Row screen: k_lsc flagged the items whose rows have a (normalised) slack below qp_screen at the agent's
-    // initial trajectory.  While every control point of the iterate stays within qp_screen (minus a margin for
-    // the rounding of the two evaluations) of its initial-trajectory point the unflagged rows cannot be violated,
-    // so they are not evaluated; an iterate that leaves that ball switches this agent to full scans for good.
-    bool screened = (P.qp_screen > 0) && (in.near != nullptr);
-    const double ball = P.qp_screen - 1e-3;
+    const bool screened = (P.qp_screen > 0) && (in.near != nullptr);      // row screen (gi_scan); qp_screen <= 0 disables it
+    bool x_current = false;      // sm.x == map_x(sm.y)
     for (int guard = 0; guard < 400; guard++) {
         if (!same_p) {
-            map_x(c, T, sm.y, sm.cst, sm.x);
-            c.sync();
-            if (screened) {
-                double far2 = 0.0, d0 = 0.0, d1 = 0.0;
-                for (int pt = 3 + c.tid; pt < npt; pt += c.nthr) {
-                    const double ex = sm.x[pt] - (double)in.init_traj[pt * 3];
-                    const double ey = sm.x[npt + pt] - (double)in.init_traj[pt * 3 + 1];
-                    const double ez = D3 ? sm.x[2 * npt + pt] - (double)in.init_traj[pt * 3 + 2] : 0.0;
-                    const double r2 = ex * ex + ey * ey + ez * ez;
-                    far2 = (r2 > far2) ? r2 : far2;
-                }
-                c.reduce3(far2, 1, d0, 0, d1, 0);
-                if (!(far2 < ball * ball)) screened = false;
-            }
             double vmax, idsel;
-            gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, vmax, idsel);
+            if (guard == 0 && seed) {          // the fast path already scanned the unconstrained optimum
+                map_x(c, T, sm.y, sm.cst, sm.x);
+                c.sync();
+                vmax = seed[0]; idsel = seed[1];
+            } else {
+                gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel);
+            }
+            x_current = true;
             *viol_out = vmax;
             if (!(vmax > tol)) { status = 0; break; }
             if (!have_hinv) {                                   // first violated row: stage this agent's H^-1 block
@@ -197,6 +244,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             }
             viol_p = vmax; u_p = 0.0;
             c.sync();
+            c.tick(8);
             // ---- w = H^-1 a_p (into sm.dy) ----
             for (int p = c.tid; p < ny; p += c.nthr) {
                 const int k = p / nyd, a = p - k * nyd;
@@ -211,6 +259,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                 sm.dy[p] = v;
             }
             c.sync();
+            c.tick(9);
         }
         iters++;
         // ---- small dense step (thread 0): r, step lengths, active-set update; t_y = A' r into sm.ax1[0..ny) ----
@@ -293,9 +342,11 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             g.ty[2] = zn;
         }
         c.sync();
+        c.tick(10);
         const double tp = g.ty[0], flag = g.ty[1];
         if (flag == 2.0) { status = kStQpMaxIter; break; }
         if (flag == 3.0) { status = -1; break; }
+        x_current = false;
         if (tp != 0.0)
             for (int p = c.tid; p < ny; p += c.nthr) {
                 const int k = p / nyd, a = p - k * nyd;
@@ -309,21 +360,22 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
         if (flag == 0.0) { q++; same_p = false; }
         else { q--; same_p = true; viol_p -= tp * g.ty[2]; }
         c.sync();
+        c.tick(11);
     }
-    map_x(c, T, sm.y, sm.cst, sm.x);
-    c.sync();
+    if (!x_current) {
+        map_x(c, T, sm.y, sm.cst, sm.x);
+        c.sync();
+    }
+    c.tick(6);
     *iters_out = iters;
     return status;
 }
 
-// One agent.  Returns true when the agent is finished (outputs written: optimal, or infeasible -> failsafe
-// trajectory), false when the active set gave up and the interior point must take over (nothing written).
-DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
-                         const QpSmem& sm) {
-    const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, nx = T.nx, np = T.np;
+// Per-agent constants, staged inputs and the unconstrained optimum y0 = -H^-1 g = Y0[ts] (c0, c1, c2, goal) in sm.y.
+// `in` is redirected to the staged copy of the SFC boxes.
+DLSC_HD void gi_prologue(const Cta& c, const DevParams& P, const QpTab& T, QpIn& in, const QpSmem& sm, QpConst& qc) {
+    const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd;
     const int n = kP - 1;
-    const bool D3 = (D == 3);
-    QpConst qc;
     qc.hi_v = in.max_vel; qc.hi_a = in.max_acc; qc.hi_c = 0.5 * P.comm_range - in.radius;
     qc.wpr = 0.5 * P.comm_range - kEpsF;
     {
@@ -340,8 +392,13 @@ DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const
         sm.cst[k * 3] = c0; sm.cst[k * 3 + 1] = c1; sm.cst[k * 3 + 2] = c2;
     }
     for (int cc = c.tid; cc < in.K; cc += c.nthr) sm.off[cc] = in.nbr_idx[cc];
+    if (P.use_sfc) {
+        for (int e = c.tid; e < M * 6; e += c.nthr) sm.sfcs[e] = in.sfc[e];
+        in.sfc = sm.sfcs;
+    }
     c.sync();
-    {   // unconstrained optimum y0 = -H^-1 g = Y0[ts] (c0, c1, c2, goal)
+    c.tick(1);
+    {
         const double* Y = T.Y0 + (size_t)(qc.ts - 1) * nyd * 4;
         for (int p = c.tid; p < ny; p += c.nthr) {
             const int k = p / nyd, a = p - k * nyd;
@@ -351,12 +408,15 @@ DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const
         }
     }
     c.sync();
-    int iters = 0;
-    double vmax = 0.0;
-    const int status = gi_solve(c, P, T, in, qc, sm, &iters, &vmax);
-    if (status < 0) return false;
+    c.tick(2);
+}
 
-    // ---- outputs: objective in x-space (constant included, like IloCplex::getObjValue :109) ----
+// outputs: objective in x-space (constant included, like IloCplex::getObjValue :109), trajectory or failsafe
+DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
+                         const QpConst& qc, const QpSmem& sm, int status, int iters, double vmax) {
+    const int M = P.M, D = P.D, npt = T.npt, nx = T.nx, np = T.np;
+    const int n = kP - 1;
+    const bool D3 = (D == 3);
     const double wT = P.w_terminal, wT2 = 2.0 * P.w_terminal;
     double obj = 0.0;
     for (int e = c.tid; e < nx; e += c.nthr) {
@@ -372,7 +432,8 @@ DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const
             obj += wT * xs[n] * xs[n] - wT2 * gg * xs[n] + wT * gg * gg;
         }
     }
-    { double d0 = 0.0, d1 = 0.0; c.reduce3(obj, 0, d0, 0, d1, 0); }
+    c.reduce1(obj, 0);
+    c.tick(7);
     if (c.tid == 0) {
         *out.cost = obj; *out.viol = vmax > 0 ? vmax : 0.0; *out.iters = iters; *out.status |= status;
         if (out.rows) *out.rows = 2LL * np + (long long)in.K * (npt - 3);
@@ -390,6 +451,42 @@ DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const
     if (out.x)
         for (int e = c.tid; e < nx; e += c.nthr) out.x[e] = sm.x[e];
     c.sync();
+}
+
+// One agent.  Returns true when the agent is finished (outputs written: optimal, or infeasible -> failsafe
+// trajectory), false when the active set gave up and the interior point must take over (nothing written).
+// seed: {vmax, id, screened, violated rows} of the scan at the unconstrained optimum when qp_agent_fast already did it, or null.
+DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in_, const QpOut& out,
+                         const QpSmem& sm, const double* seed = nullptr) {
+    QpIn in = in_;
+    QpConst qc;
+    gi_prologue(c, P, T, in, sm, qc);
+    int iters = 0;
+    double vmax = 0.0;
+    const int status = gi_solve(c, P, T, in, qc, sm, seed, &iters, &vmax);
+    if (status < 0) return false;
+    gi_epilogue(c, P, T, in, out, qc, sm, status, iters, vmax);
+    return true;
+}
+
+// Fast path, one warp per agent: is the unconstrained optimum feasible (60 % of the agents of a swarm in
+// transit)?  Then it is the optimum: outputs are written and true is returned.  Otherwise the most violated row
+// goes to seed_out {vmax, id, screened} for qp_agent_gi and nothing is written.  sm: fast_smem_carve.
+DLSC_HD bool qp_agent_fast(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in_, const QpOut& out,
+                           const QpSmem& sm, double* seed_out) {
+    QpIn in = in_;
+    QpConst qc;
+    gi_prologue(c, P, T, in, sm, qc);
+    const bool screened = (P.qp_screen > 0) && (in.near != nullptr);
+    double vmax, idsel, nviol = 0.0;
+    gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel, &nviol);
+    if (vmax > kGiTol) {
+        // seed[3]: number of rows violated at the unconstrained optimum -- a proxy for the active-set iterations
+        // the agent will need, used to start the expensive agents first (k_qp_gi)
+        if (c.tid == 0) { seed_out[0] = vmax; seed_out[1] = idsel; seed_out[2] = screened ? 1.0 : 0.0; seed_out[3] = nviol; }
+        return false;
+    }
+    gi_epilogue(c, P, T, in, out, qc, sm, 0, 0, vmax);
     return true;
 }
 

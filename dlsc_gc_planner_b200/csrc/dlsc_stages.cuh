@@ -116,6 +116,35 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
     return count;
 }
 
+// smallest normalised slack of an item as stored for the QP row screen (float, +inf for a zero normal: such rows
+// are not constraints, traj_optimizer.cpp:422-424)
+DLSC_HD float lsc_item_slack(double smin, double nn) {
+    if (!(nn > 0.0)) return 3.0e38f;
+    const double q = smin / nn;
+    return q > 3.0e38 ? 3.0e38f : (q < -3.0e38 ? -3.0e38f : (float)q);
+}
+// the 6 control points of one segment (18 floats, 8-byte aligned: 72-byte segments of 16-byte aligned trajectories)
+DLSC_HD void load_segment(const float* p, V3 (&out)[kP]) {
+#ifdef __CUDA_ARCH__
+    const float2* q = reinterpret_cast<const float2*>(p);
+    float f[kP * 3];
+#pragma unroll
+    for (int i = 0; i < kP * 3 / 2; i++) { const float2 t = q[i]; f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int i = 0; i < kP; i++) out[i] = v3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+#else
+    for (int i = 0; i < kP; i++) out[i] = v3_load(p + 3 * i);
+#endif
+}
+DLSC_HD bool is_pow2_f32(float f) {           // normal, positive, zero mantissa
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(f);
+#else
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x807fffffu) == 0 && ((u >> 23) - 1u) < 253u;
+}
 // ------------------------------------------------------------------------------------------------
 // LSC for one (agent, neighbour, segment) -- traj_planner.cpp:603-666, 1102-1127, 1150-1161
 //   init_a : own initial trajectory [M][P][3], pred_j : neighbour's predicted trajectory
@@ -125,46 +154,54 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
 DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* pred_j, const V3& goal_a,
                          const V3& goal_j, double r_a, double dw_a, float r_j_f, float dw_j_f, int m,
                          float* normal_out, double* d_out, float* anchor_last_out, int* gjk_iters,
-                         uint8_t* near_out = nullptr, double tau = 0.0) {
+                         float* slack_out = nullptr) {
     const double r_j = (double)r_j_f, dw_j = (double)dw_j_f;
     const double collision_dist = r_j + r_a;                                   // :605
     const double downwash = (dw_a * r_a + dw_j * r_j) / (r_a + r_j);           // :1153-1154
     const float dwf = (float)downwash;                                         // trajectory.cpp:214
     if (m < P.M - 1) {
-        V3 rel[kP];
-        gjk::D3 c[kP];
+        V3 wb[kP];                           // the neighbour's world-frame points, kept for the row screen below
+        gjk::D3 c[kP];                       // c[i] = (double)rel[i]: rel[i] is recovered exactly as (float)c[i]
+        load_segment(pred_j + m * kP * 3, wb);
+        // x / dwf == x * (1 / dwf) bit for bit when dwf is a power of two (every mission with equal downwash
+        // coefficients: 2.0); the IEEE division otherwise
+        const bool pow2 = is_pow2_f32(dwf);
+        const float inv_dwf = pow2 ? 1.0f / dwf : 0.0f;
 #pragma unroll
         for (int i = 0; i < kP; i++) {
-            V3 a = v3_load(init_a + (m * kP + i) * 3); a.z = a.z / dwf;
-            V3 b = v3_load(pred_j + (m * kP + i) * 3); b.z = b.z / dwf;
-            rel[i] = a - b;
-            c[i] = gjk::d3((double)rel[i].x, (double)rel[i].y, (double)rel[i].z);   // util.hpp:113-125
+            V3 a = v3_load(init_a + (m * kP + i) * 3); a.z = pow2 ? a.z * inv_dwf : a.z / dwf;
+            V3 b = wb[i]; b.z = pow2 ? b.z * inv_dwf : b.z / dwf;
+            const V3 rel = a - b;
+            c[i] = gjk::d3((double)rel.x, (double)rel.y, (double)rel.z);   // util.hpp:113-125
         }
         int it = 0;
         const gjk::D3 v = gjk::hull_origin<kP>(c, &it);
         if (gjk_iters) *gjk_iters = it;
         const V3 cp2 = v3(0.f, 0.f, 0.f) + v3((float)v.x, (float)v.y, (float)v.z);   // geometry.hpp:302
         const V3 nt = v3_normalized(cp2);                                             // :1118
-        normal_out[0] = nt.x; normal_out[1] = nt.y;
-        normal_out[2] = (float)((double)nt.z / downwash);                             // :630-632
+        const float nz_w = (float)((double)nt.z / downwash);                          // :630-632
+        normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
+        double dloc[kP];
 #pragma unroll
-        for (int i = 0; i < kP; i++) d_out[i] = 0.5 * (collision_dist + v3_dot(rel[i], nt));   // :636-637
-        if (near_out) {
-            // QP row screen (dlsc_qp_gi.cuh): slack of the rows of this item at the agent's own initial trajectory,
-            // in world coordinates, normalised by |normal|.  A row whose normalised slack is >= tau cannot be
-            // violated by any x with |x_pt - init_pt| < tau.
-            const double n0 = (double)normal_out[0], n1 = (double)normal_out[1], n2 = (double)normal_out[2];
+        for (int i = 0; i < kP; i++) {                                                // :636-637
+            dloc[i] = 0.5 * (collision_dist + v3_dot(v3((float)c[i].x, (float)c[i].y, (float)c[i].z), nt));
+            d_out[i] = dloc[i];
+        }
+        if (slack_out) {
+            // QP row screen (dlsc_qp_gi.cuh): smallest slack of the rows of this item at the agent's own initial
+            // trajectory, in world coordinates, normalised by |normal|.  A row with normalised slack s cannot be
+            // violated by any x with |x_pt - init_pt| < s.
+            const double n0 = (double)nt.x, n1 = (double)nt.y, n2 = (double)nz_w;
             const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
             double smin = 1e300;
 #pragma unroll
             for (int i = 0; i < kP; i++) {
                 const float* a = init_a + (m * kP + i) * 3;
-                const float* b = pred_j + (m * kP + i) * 3;
-                const double sl = n0 * ((double)a[0] - (double)b[0]) + n1 * ((double)a[1] - (double)b[1]) +
-                                  n2 * ((double)a[2] - (double)b[2]) - d_out[i];
+                const double sl = n0 * ((double)a[0] - (double)wb[i].x) + n1 * ((double)a[1] - (double)wb[i].y) +
+                                  n2 * ((double)a[2] - (double)wb[i].z) - dloc[i];
                 smin = (sl < smin) ? sl : smin;
             }
-            *near_out = (smin < tau * nn) ? 1 : 0;
+            *slack_out = lsc_item_slack(smin, nn);
         }
     } else {
         const int last = (P.M - 1) * kP + (kP - 1);
@@ -175,25 +212,25 @@ DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* p
         const Closest cp = closest_segments(o_last, og, a_last, ag);                  // :642-644
         const V3 nt = v3_normalized(cp.p2 - cp.p1);
         const double dd = 0.5 * (collision_dist + cp.dist);                           // :650
-        normal_out[0] = nt.x; normal_out[1] = nt.y;
-        normal_out[2] = (float)((double)nt.z / downwash);
-        anchor_last_out[0] = cp.p1.x; anchor_last_out[1] = cp.p1.y;
-        anchor_last_out[2] = (float)((double)cp.p1.z * downwash);                     // :657
+        const float nz_w = (float)((double)nt.z / downwash);
+        const float al_z = (float)((double)cp.p1.z * downwash);                       // :657
+        normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
+        anchor_last_out[0] = cp.p1.x; anchor_last_out[1] = cp.p1.y; anchor_last_out[2] = al_z;
 #pragma unroll
         for (int i = 0; i < kP; i++) d_out[i] = dd;
         if (gjk_iters) *gjk_iters = 0;
-        if (near_out) {
-            const double n0 = (double)normal_out[0], n1 = (double)normal_out[1], n2 = (double)normal_out[2];
+        if (slack_out) {
+            const double n0 = (double)nt.x, n1 = (double)nt.y, n2 = (double)nz_w;
             const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
             double smin = 1e300;
 #pragma unroll
             for (int i = 0; i < kP; i++) {
                 const float* a = init_a + ((P.M - 1) * kP + i) * 3;
-                const double sl = n0 * ((double)a[0] - (double)anchor_last_out[0]) + n1 * ((double)a[1] - (double)anchor_last_out[1]) +
-                                  n2 * ((double)a[2] - (double)anchor_last_out[2]) - dd;
+                const double sl = n0 * ((double)a[0] - (double)cp.p1.x) + n1 * ((double)a[1] - (double)cp.p1.y) +
+                                  n2 * ((double)a[2] - (double)al_z) - dd;
                 smin = (sl < smin) ? sl : smin;
             }
-            *near_out = (smin < tau * nn) ? 1 : 0;
+            *slack_out = lsc_item_slack(smin, nn);
         }
     }
 }

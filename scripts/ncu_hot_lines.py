@@ -45,7 +45,9 @@ for r in data:
             stalls[ln][h] += v
 print("total samples", ts, "warp-instructions", ti)
 src_cache = {}
-for ln, s in S.most_common(topn):
+order = I.most_common(topn) if os.environ.get("BY_INS") else S.most_common(topn)
+for ln, _ in order:
+    s = S[ln]
     txt = ""
     if ln:
         for d in ("dlsc_gc_planner_b200/csrc",):

@@ -30,7 +30,8 @@ struct dlsc_ctx {
     QpTab T;
     int seq = 0;
     std::vector<float> rec, acc, waypoint, goal_new, pred_traj, init_traj, lsc_normal, lsc_anchor_last, sfc, traj;
-    std::vector<uint8_t> disturbed, sfc_init, lsc_near;
+    std::vector<uint8_t> disturbed, sfc_init;
+    std::vector<float> lsc_near;
     std::vector<double> radius, downwash, max_vel, max_acc, nominal_vel, lsc_d, qp_x, cost, viol, scratch, smem, smem_gi;
     std::vector<int32_t> nbr_idx, nbr_cnt, qp_iters, status;
     std::vector<int4> cells;
@@ -81,7 +82,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     c->nbr_idx.assign(NL * K, 0); c->nbr_cnt.assign(NL, 0);
     c->lsc_normal.assign(NL * K * M * 3, 0.f); c->lsc_d.assign(NL * K * M * kP, 0.0);
     c->lsc_anchor_last.assign(NL * K * 3, 0.f);
-    c->lsc_near.assign(NL * K * M, 1);
+    c->lsc_near.assign(NL * K * M, 0.0f);
     c->sfc.assign(NL * M * 6, 0.f); c->traj.assign(NL * npt * 3, 0.f);
     c->qp_x.assign(NL * hp->dim * npt, 0.0); c->cost.assign(NL, 0); c->viol.assign(NL, 0);
     c->qp_iters.assign(NL, 0); c->status.assign(NL, 0);
@@ -325,7 +326,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
                                 v3_load(rec_a + og), v3_load(rec_j + og), c->radius[la], c->downwash[la], rec_j[og + 3],
                                 rec_j[og + 4], m, c->lsc_normal.data() + (pr * M + m) * 3,
                                 c->lsc_d.data() + (pr * M + m) * kP, c->lsc_anchor_last.data() + pr * 3, &it,
-                                c->lsc_near.data() + pr * M + m, P.qp_screen);
+                                c->lsc_near.data() + pr * M + m);
                     c->counters[1] += it;
                 }
             }
@@ -391,7 +392,14 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
                 QpSmem sg;
                 gi_smem_carve(c->T, c->smem_gi.data(), sg);
                 Cta cg; cg.tid = 0; cg.nthr = 1; cg.red = sg.red;
-                done = qp_agent_gi(cg, P, c->T, in, out, sg);
+                // same two kernels as launch_qp: the warp-per-agent fast path, then the seeded dual active set
+                std::vector<double> fast_mem(fast_smem_doubles(c->T, P.K) + 2);
+                QpSmem sf;
+                fast_smem_carve(c->T, fast_mem.data(), sf);
+                Cta cf; cf.tid = 0; cf.nthr = 1; cf.red = nullptr; cf.warp = true;
+                double seed[4] = {0, 0, 0, 0};
+                done = qp_agent_fast(cf, P, c->T, in, out, sf, seed);
+                if (!done) done = qp_agent_gi(cg, P, c->T, in, out, sg, seed);
             }
             if (!done) qp_agent(cta, P, c->T, in, out, sm, c->scratch.data(), P.qp_solver != 1);
             c->counters[3] += c->qp_iters[la];
@@ -488,15 +496,15 @@ int dlsc_enable_timing(dlsc_ctx*, int) { return 0; }
 int dlsc_get_timings(dlsc_ctx*, double ms[DLSC_N_STAGES], int* n) { for (int i = 0; i < DLSC_N_STAGES; i++) ms[i] = 0; if (n) *n = 0; return 0; }
 
 int dlsc_run_stages_subset(dlsc_ctx*, int, int, int) { return fail("hostsim: not supported"); }
-int dlsc_set_init_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 1); memcpy(c->init_traj.data(), t, c->init_traj.size() * 4); return 0; }
-int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 1); memcpy(c->pred_traj.data(), t, c->pred_traj.size() * 4); return 0; }
+int dlsc_set_init_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f); memcpy(c->init_traj.data(), t, c->init_traj.size() * 4); return 0; }
+int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f); memcpy(c->pred_traj.data(), t, c->pred_traj.size() * 4); return 0; }
 int dlsc_set_neighbours(dlsc_ctx* c, const int32_t* idx, const int32_t* cnt) {
-    std::fill(c->lsc_near.begin(), c->lsc_near.end(), 1);
+    std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f);
     memcpy(c->nbr_idx.data(), idx, c->nbr_idx.size() * 4); memcpy(c->nbr_cnt.data(), cnt, c->nbr_cnt.size() * 4); return 0;
 }
 int dlsc_set_lsc(dlsc_ctx* c, const float* normal, const float* anchor_last, const double* d) {
     memcpy(c->lsc_normal.data(), normal, c->lsc_normal.size() * 4);
-    std::fill(c->lsc_near.begin(), c->lsc_near.end(), 1);
+    std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f);
     memcpy(c->lsc_anchor_last.data(), anchor_last, c->lsc_anchor_last.size() * 4);
     memcpy(c->lsc_d.data(), d, c->lsc_d.size() * 8); return 0;
 }
