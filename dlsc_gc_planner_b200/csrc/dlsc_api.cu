@@ -217,6 +217,8 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.counters, DLSC_N_COUNTERS);
     rc |= dev_alloc(c, &S.qp_next, 4);
     rc |= dev_alloc(c, &S.qp_list, NL);
+    rc |= dev_alloc(c, &S.nbr_cell_start, (size_t)8192 + 1);
+    rc |= dev_alloc(c, &S.nbr_sorted, (size_t)N);
     rc |= dev_alloc(c, &S.qp_list_gi, (size_t)NL);
     rc |= dev_alloc(c, &S.qp_seed, (size_t)NL * 4);
     if (rc) { dlsc_destroy(c); return -1; }
@@ -577,7 +579,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
         launch_sfc(Pr, Sx, c->side_stream); c->launches++;
         CK(cudaEventRecord(c->ev_join, c->side_stream));
     }
-    if (mask & DLSC_STAGE_NBR) { launch_neighbours(Pr, Sx, st); c->launches++; }
+    if (mask & DLSC_STAGE_NBR) c->launches += launch_neighbours(Pr, Sx, st);
     if (tm) CK(cudaEventRecord(ev[2], st));
     if (mask & DLSC_STAGE_LSC) { launch_lsc(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[3], st));

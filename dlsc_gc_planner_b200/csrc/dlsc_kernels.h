@@ -24,6 +24,8 @@ struct DevState {
     float* init_traj;          // [NL][M][P][3]
     int32_t* nbr_idx;          // [NL][K]
     int32_t* nbr_cnt;          // [NL]
+    int* nbr_cell_start;       // [kNbrMaxCells + 1] uniform-grid neighbour search: first slot of every cell in nbr_sorted
+    int* nbr_sorted;           // [N] agent indices sorted by cell
     float* lsc_normal;         // [NL][K][M][3]
     double* lsc_d;             // [NL][K][M][P]
     float* lsc_anchor_last;    // [NL][K][3]
@@ -45,7 +47,7 @@ struct DevState {
 struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; size_t fast_smem; };
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
-void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);
+int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);   // returns the number of launches
 void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st);

@@ -6,6 +6,8 @@
 //   k_goal         intermediate goal line search (closed-form 1-var LP)   thread per agent
 //   k_advance      state step at t = dt + record refresh                  thread per agent
 // All arithmetic lives in dlsc_stages.cuh / dlsc_math.cuh.
+#include <cstdlib>
+
 #include "dlsc_kernels.h"
 #include "dlsc_stages.cuh"
 
@@ -76,8 +78,151 @@ __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__
     }
 }
 
-void launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
+// ---- neighbour search through a uniform grid (comm_range > 0) -----------------------------------------------
+// The all-pairs kernel above tests N candidates per agent; with a limited communication range only the agents of
+// the 3 x 3 surrounding cells of an xy grid with cell size >= range can pass the Chebyshev test.  Same result as
+// the all-pairs kernel (same exact test, ascending index order, first K kept on overflow), ~50 candidates per
+// agent instead of N.
+//   k_nbr_bin    one CTA: counting sort of all N agents by cell (shared-memory histogram + scan)
+//   k_nbr_search warp per local agent: candidates of the 3 cell rows, exact test, rank sort
+struct NbrGrid { int gx, gy; double x0, y0, inv_h; int* cell_start; int* sorted; };
+constexpr int kNbrMaxCells = 8192, kNbrBinThreads = 1024, kNbrCand = 256, kNbrSearchWarps = 8;
+
+__device__ __forceinline__ int nbr_cell(const NbrGrid& G, float x, float y) {
+    int cx = (int)floor(((double)x - G.x0) * G.inv_h), cy = (int)floor(((double)y - G.y0) * G.inv_h);
+    cx = cx < 0 ? 0 : (cx >= G.gx ? G.gx - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= G.gy ? G.gy - 1 : cy);
+    return cy * G.gx + cx;
+}
+
+__global__ void __launch_bounds__(kNbrBinThreads) k_nbr_bin(const __grid_constant__ DevParams P, const float* __restrict__ rec,
+                                                             const __grid_constant__ NbrGrid G) {
+    __shared__ int cnt[kNbrMaxCells];
+    __shared__ int wsum[32];
+    const int ncell = G.gx * G.gy, off = P.M * kP * 3;
+    for (int c = threadIdx.x; c < ncell; c += kNbrBinThreads) cnt[c] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < P.N; j += kNbrBinThreads) {
+        const float* r = rec + (size_t)j * P.rec + off;
+        atomicAdd(&cnt[nbr_cell(G, r[0], r[1])], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..ncell) in chunks of 1024 (one element per thread), carry in wsum[31] style
+    int carry = 0;
+    for (int base = 0; base < ncell; base += kNbrBinThreads) {
+        const int c = base + threadIdx.x;
+        const int v = c < ncell ? cnt[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = wsum[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
+            wsum[threadIdx.x] = wi - w;                       // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        const int excl = carry + wsum[threadIdx.x >> 5] + incl - v;
+        if (c < ncell) { cnt[c] = excl; G.cell_start[c] = excl; }
+        __syncthreads();
+        if (threadIdx.x == kNbrBinThreads - 1) wsum[0] = excl + v;   // total so far
+        __syncthreads();
+        carry = wsum[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) G.cell_start[ncell] = carry;
+    for (int j = threadIdx.x; j < P.N; j += kNbrBinThreads) {
+        const float* r = rec + (size_t)j * P.rec + off;
+        G.sorted[atomicAdd(&cnt[nbr_cell(G, r[0], r[1])], 1)] = j;     // order inside a cell is arbitrary: the search sorts
+    }
+}
+
+__global__ void __launch_bounds__(kNbrSearchWarps * 32) k_nbr_search(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
+                                                                      const __grid_constant__ NbrGrid G) {
+    __shared__ int cand[kNbrSearchWarps][kNbrCand];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int la = blockIdx.x * kNbrSearchWarps + w;
+    if (la >= P.NL) return;
+    const int a = P.begin + la, off = P.M * kP * 3;
+    const float* ra = S.rec + (size_t)a * P.rec + off;
+    const V3 pa = v3_load(ra);
+    const float ga = ra[11];
+    int32_t* idx_out = S.nbr_idx + (size_t)la * P.K;
+    const int ca = nbr_cell(G, pa.x, pa.y), cx = ca % G.gx, cy = ca / G.gx;
+    const int x_lo = cx > 0 ? cx - 1 : 0, x_hi = cx < G.gx - 1 ? cx + 1 : G.gx - 1;
+    int n = 0;                                   // in-range candidates found (all lanes agree)
+    for (int yy = (cy > 0 ? cy - 1 : 0); yy <= (cy < G.gy - 1 ? cy + 1 : G.gy - 1); yy++) {
+        const int s0 = G.cell_start[yy * G.gx + x_lo], s1 = G.cell_start[yy * G.gx + x_hi + 1];   // 3 cells, contiguous
+        for (int t = s0; t < s1; t += 32) {
+            bool in = false;
+            int j = -1;
+            if (t + lane < s1) {
+                j = G.sorted[t + lane];
+                const float* rj = S.rec + (size_t)j * P.rec + off;
+                if (j != a && rj[11] == ga) in = in_comm_range(P, pa, v3_load(rj));
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, in);
+            const int pos = n + __popc(mask & ((1u << lane) - 1u));
+            if (in && pos < kNbrCand) cand[w][pos] = j;
+            n += __popc(mask);
+        }
+    }
+    __syncwarp();
+    int count;
+    if (n <= kNbrCand) {
+        // rank sort: ascending agent index, the first K kept (multi_sync_simulator.cpp:481-503 visits j in order)
+        for (int e = lane; e < n; e += 32) {
+            const int j = cand[w][e];
+            int rank = 0;
+            for (int f = 0; f < n; f++) rank += (cand[w][f] < j);
+            if (rank < P.K) idx_out[rank] = j;
+        }
+        count = n;
+    } else {
+        // more candidates than the buffer holds (dense Monte-Carlo batches): plain scan of all agents for this one
+        count = 0;
+        for (int base = 0; base < P.N; base += 32) {
+            const int j = base + lane;
+            bool in = false;
+            if (j < P.N && j != a) {
+                const float* rj = S.rec + (size_t)j * P.rec + off;
+                if (rj[11] == ga) in = in_comm_range(P, pa, v3_load(rj));
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, in);
+            const int pos = count + __popc(mask & ((1u << lane) - 1u));
+            if (in && pos < P.K) idx_out[pos] = j;
+            count += __popc(mask);
+        }
+    }
+    if (lane == 0) {
+        S.nbr_cnt[la] = count < P.K ? count : P.K;
+        if (count > P.K) atomicOr(S.status + la, kStNbrOverflow);
+        atomicAdd(S.counters + 0, (unsigned long long)(count < P.K ? count : P.K));
+    }
+}
+
+// returns the number of kernels launched
+int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
+    static const bool no_grid = [] { const char* e = getenv("DLSC_NBR_GRID"); return e && e[0] == '0'; }();
+    if (P.comm_range > 0 && S.nbr_cell_start && !no_grid) {
+        NbrGrid G;
+        // cell size a little above the range: the test is made on float differences, which can accept a pair whose
+        // exact distance exceeds the range by one float ulp
+        const double h = P.comm_range * (1.0 + 1e-5);
+        G.x0 = P.world_min[0]; G.y0 = P.world_min[1]; G.inv_h = 1.0 / h;
+        G.gx = (int)floor((P.world_max[0] - P.world_min[0]) * G.inv_h) + 1;
+        G.gy = (int)floor((P.world_max[1] - P.world_min[1]) * G.inv_h) + 1;
+        if (G.gx >= 1 && G.gy >= 1 && (long long)G.gx * G.gy <= kNbrMaxCells) {
+            G.cell_start = S.nbr_cell_start; G.sorted = S.nbr_sorted;
+            k_nbr_bin<<<1, kNbrBinThreads, 0, st>>>(P, S.rec, G);
+            k_nbr_search<<<(P.NL + kNbrSearchWarps - 1) / kNbrSearchWarps, kNbrSearchWarps * 32, 0, st>>>(P, S, G);
+            return 2;
+        }
+    }
     k_neighbours<<<(P.NL + kNbrWarps - 1) / kNbrWarps, kNbrTile, 0, st>>>(P, S);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -181,27 +181,22 @@ DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* p
         const V3 nt = v3_normalized(cp2);                                             // :1118
         const float nz_w = (float)((double)nt.z / downwash);                          // :630-632
         normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
-        double dloc[kP];
+        double pmin = 1e300;
 #pragma unroll
         for (int i = 0; i < kP; i++) {                                                // :636-637
-            dloc[i] = 0.5 * (collision_dist + v3_dot(v3((float)c[i].x, (float)c[i].y, (float)c[i].z), nt));
-            d_out[i] = dloc[i];
+            const double pi = v3_dot(v3((float)c[i].x, (float)c[i].y, (float)c[i].z), nt);
+            d_out[i] = 0.5 * (collision_dist + pi);
+            if (m > 0 || i >= 3) pmin = (pi < pmin) ? pi : pmin;                      // rows of (m = 0, i < 3) do not exist
         }
         if (slack_out) {
             // QP row screen (dlsc_qp_gi.cuh): smallest slack of the rows of this item at the agent's own initial
-            // trajectory, in world coordinates, normalised by |normal|.  A row with normalised slack s cannot be
-            // violated by any x with |x_pt - init_pt| < s.
-            const double n0 = (double)nt.x, n1 = (double)nt.y, n2 = (double)nz_w;
-            const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
-            double smin = 1e300;
-#pragma unroll
-            for (int i = 0; i < kP; i++) {
-                const float* a = init_a + (m * kP + i) * 3;
-                const double sl = n0 * ((double)a[0] - (double)wb[i].x) + n1 * ((double)a[1] - (double)wb[i].y) +
-                                  n2 * ((double)a[2] - (double)wb[i].z) - dloc[i];
-                smin = (sl < smin) ? sl : smin;
-            }
-            *slack_out = lsc_item_slack(smin, nn);
+            // trajectory, normalised by the world-frame |normal|: a row with normalised slack s cannot be violated
+            // by any x with |x_pt - init_pt| < s.  The slack of row i at the initial trajectory is
+            // n_w.(a_i - b_i) - d_i = p_i - (collision_dist + p_i) / 2 with p_i the dot product above (the world-frame
+            // normal against world-frame points equals the scaled normal against scaled points), so it costs nothing;
+            // float rounding (1e-6 m) is far inside the screen's margin (1e-3 m).
+            const float nn = sqrtf(nt.x * nt.x + nt.y * nt.y + nz_w * nz_w);
+            *slack_out = lsc_item_slack(0.5 * (pmin - collision_dist), (double)nn);
         }
     } else {
         const int last = (P.M - 1) * kP + (kP - 1);
@@ -219,18 +214,17 @@ DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* p
 #pragma unroll
         for (int i = 0; i < kP; i++) d_out[i] = dd;
         if (gjk_iters) *gjk_iters = 0;
-        if (slack_out) {
-            const double n0 = (double)nt.x, n1 = (double)nt.y, n2 = (double)nz_w;
-            const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
-            double smin = 1e300;
+        if (slack_out) {      // same screen; rows n_w.(a_i - anchor) >= dd, evaluated in the scaled frame in float
+            const float inv = 1.0f / dwf;
+            float smin = 3.0e38f;
 #pragma unroll
             for (int i = 0; i < kP; i++) {
                 const float* a = init_a + ((P.M - 1) * kP + i) * 3;
-                const double sl = n0 * ((double)a[0] - (double)cp.p1.x) + n1 * ((double)a[1] - (double)cp.p1.y) +
-                                  n2 * ((double)a[2] - (double)al_z) - dd;
+                const float sl = (a[0] - cp.p1.x) * nt.x + (a[1] - cp.p1.y) * nt.y + (a[2] * inv - cp.p1.z) * nt.z;
                 smin = (sl < smin) ? sl : smin;
             }
-            *slack_out = lsc_item_slack(smin, nn);
+            const float nn = sqrtf(nt.x * nt.x + nt.y * nt.y + nz_w * nz_w);
+            *slack_out = lsc_item_slack((double)smin - dd, (double)nn);
         }
     }
 }
