@@ -219,6 +219,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.qp_list, NL);
     rc |= dev_alloc(c, &S.nbr_cell_start, (size_t)8192 + 1);
     rc |= dev_alloc(c, &S.nbr_sorted, (size_t)N);
+    rc |= dev_alloc(c, &S.nbr_sorted_pos, (size_t)N);
     rc |= dev_alloc(c, &S.qp_list_gi, (size_t)NL);
     rc |= dev_alloc(c, &S.qp_seed, (size_t)NL * 4);
     if (rc) { dlsc_destroy(c); return -1; }

@@ -26,6 +26,7 @@ struct DevState {
     int32_t* nbr_cnt;          // [NL]
     int* nbr_cell_start;       // [kNbrMaxCells + 1] uniform-grid neighbour search: first slot of every cell in nbr_sorted
     int* nbr_sorted;           // [N] agent indices sorted by cell
+    float4* nbr_sorted_pos;    // [N] {x, y, z, group} of the agents in the same order
     float* lsc_normal;         // [NL][K][M][3]
     double* lsc_d;             // [NL][K][M][P]
     float* lsc_anchor_last;    // [NL][K][3]

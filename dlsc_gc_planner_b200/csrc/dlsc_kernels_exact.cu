@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__
 // agent instead of N.
 //   k_nbr_bin    one CTA: counting sort of all N agents by cell (shared-memory histogram + scan)
 //   k_nbr_search warp per local agent: candidates of the 3 cell rows, exact test, rank sort
-struct NbrGrid { int gx, gy; double x0, y0, inv_h; int* cell_start; int* sorted; };
+struct NbrGrid { int gx, gy; double x0, y0, inv_h; int* cell_start; int* sorted; float4* pos; };   // pos: {x, y, z, group} in sorted order
 constexpr int kNbrMaxCells = 8192, kNbrBinThreads = 1024, kNbrCand = 256, kNbrSearchWarps = 8;
 
 __device__ __forceinline__ int nbr_cell(const NbrGrid& G, float x, float y) {
@@ -102,7 +102,22 @@ __global__ void __launch_bounds__(kNbrBinThreads) k_nbr_bin(const __grid_constan
     const int ncell = G.gx * G.gy, off = P.M * kP * 3;
     for (int c = threadIdx.x; c < ncell; c += kNbrBinThreads) cnt[c] = 0;
     __syncthreads();
-    for (int j = threadIdx.x; j < P.N; j += kNbrBinThreads) {
+    // the first kCache agents of a thread stay in registers between the two passes (all of them when N <= 4096)
+    constexpr int kCache = 4;
+    float4 pc[kCache];
+    int cc[kCache];
+#pragma unroll
+    for (int u = 0; u < kCache; u++) {
+        const int j = threadIdx.x + u * kNbrBinThreads;
+        cc[u] = -1;
+        if (j < P.N) {
+            const float* r = rec + (size_t)j * P.rec + off;
+            pc[u] = make_float4(r[0], r[1], r[2], r[11]);
+            cc[u] = nbr_cell(G, pc[u].x, pc[u].y);
+            atomicAdd(&cnt[cc[u]], 1);
+        }
+    }
+    for (int j = threadIdx.x + kCache * kNbrBinThreads; j < P.N; j += kNbrBinThreads) {
         const float* r = rec + (size_t)j * P.rec + off;
         atomicAdd(&cnt[nbr_cell(G, r[0], r[1])], 1);
     }
@@ -133,9 +148,19 @@ __global__ void __launch_bounds__(kNbrBinThreads) k_nbr_bin(const __grid_constan
         __syncthreads();
     }
     if (threadIdx.x == 0) G.cell_start[ncell] = carry;
-    for (int j = threadIdx.x; j < P.N; j += kNbrBinThreads) {
+    // order inside a cell is arbitrary: the search sorts
+#pragma unroll
+    for (int u = 0; u < kCache; u++)
+        if (cc[u] >= 0) {
+            const int slot = atomicAdd(&cnt[cc[u]], 1);
+            G.sorted[slot] = threadIdx.x + u * kNbrBinThreads;
+            G.pos[slot] = pc[u];
+        }
+    for (int j = threadIdx.x + kCache * kNbrBinThreads; j < P.N; j += kNbrBinThreads) {
         const float* r = rec + (size_t)j * P.rec + off;
-        G.sorted[atomicAdd(&cnt[nbr_cell(G, r[0], r[1])], 1)] = j;     // order inside a cell is arbitrary: the search sorts
+        const int slot = atomicAdd(&cnt[nbr_cell(G, r[0], r[1])], 1);
+        G.sorted[slot] = j;
+        G.pos[slot] = make_float4(r[0], r[1], r[2], r[11]);
     }
 }
 
@@ -160,8 +185,8 @@ __global__ void __launch_bounds__(kNbrSearchWarps * 32) k_nbr_search(const __gri
             int j = -1;
             if (t + lane < s1) {
                 j = G.sorted[t + lane];
-                const float* rj = S.rec + (size_t)j * P.rec + off;
-                if (j != a && rj[11] == ga) in = in_comm_range(P, pa, v3_load(rj));
+                const float4 q = G.pos[t + lane];
+                if (j != a && q.w == ga) in = in_comm_range(P, pa, v3(q.x, q.y, q.z));
             }
             const unsigned mask = __ballot_sync(0xffffffffu, in);
             const int pos = n + __popc(mask & ((1u << lane) - 1u));
@@ -215,7 +240,7 @@ int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
         G.gx = (int)floor((P.world_max[0] - P.world_min[0]) * G.inv_h) + 1;
         G.gy = (int)floor((P.world_max[1] - P.world_min[1]) * G.inv_h) + 1;
         if (G.gx >= 1 && G.gy >= 1 && (long long)G.gx * G.gy <= kNbrMaxCells) {
-            G.cell_start = S.nbr_cell_start; G.sorted = S.nbr_sorted;
+            G.cell_start = S.nbr_cell_start; G.sorted = S.nbr_sorted; G.pos = S.nbr_sorted_pos;
             k_nbr_bin<<<1, kNbrBinThreads, 0, st>>>(P, S.rec, G);
             k_nbr_search<<<(P.NL + kNbrSearchWarps - 1) / kNbrSearchWarps, kNbrSearchWarps * 32, 0, st>>>(P, S, G);
             return 2;

@@ -476,7 +476,11 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
             mm[ax] = tab->km[ax]; vv[ax] = tab->kv[ax];
         } else {
             smiss = true;
-            mm[ax] = (int)floor(((hi - lo) + kEpsF) / res) + 1;
+            {   // floor(x / res): the quotient sits ~eps/res = 1e-4 above an integer, so the product with 1/res has
+                // the same floor unless it lands within 1e-9 of an integer; only then the IEEE division decides
+                const double x = (hi - lo) + kEpsF, q = x * E.inv_res, f = floor(q);
+                mm[ax] = ((E.res == res && q - f > 1e-9 && q - f < 1.0 - 1e-9) ? (int)f : (int)floor(x / res)) + 1;
+            }
             const double t = E.inv_res * (double)lo, vr = rint(t);
             vv[ax] = (fabs(t - vr) > 1e-2) ? kNoLattice : (int)vr - E.min_key[ax];
         }
