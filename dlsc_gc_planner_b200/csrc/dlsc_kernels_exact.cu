@@ -41,6 +41,7 @@ void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t
 constexpr int kNbrWarps = 16, kNbrTile = kNbrWarps * 32;
 __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float tile[kNbrTile * 4];         // position + group (mission index) of the tile's agents
+    __shared__ float grange[kNbrWarps * 2];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int la = blockIdx.x * kNbrWarps + w;
     const bool valid = la < P.NL;
@@ -57,9 +58,21 @@ __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__
             tile[threadIdx.x * 4] = r[0]; tile[threadIdx.x * 4 + 1] = r[1]; tile[threadIdx.x * 4 + 2] = r[2];
             tile[threadIdx.x * 4 + 3] = r[11];
         }
+        // mission-index range of the tile: a Monte-Carlo batch keeps the missions contiguous, so all but one or two
+        // tiles hold no agent of this warp's mission and are skipped as a whole
+        float gmin = (jt < P.N) ? tile[threadIdx.x * 4 + 3] : 3.0e38f, gmax = (jt < P.N) ? tile[threadIdx.x * 4 + 3] : -3.0e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+            gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        }
+        if (lane == 0) { grange[w * 2] = gmin; grange[w * 2 + 1] = gmax; }
         __syncthreads();
+        gmin = grange[0]; gmax = grange[1];
+#pragma unroll
+        for (int i = 1; i < kNbrWarps; i++) { gmin = fminf(gmin, grange[i * 2]); gmax = fmaxf(gmax, grange[i * 2 + 1]); }
         const int nt = (P.N - base < kNbrTile) ? P.N - base : kNbrTile;
-        if (valid)
+        if (valid && ga >= gmin && ga <= gmax)
             for (int t = 0; t < nt; t += 32) {
                 const int j = base + t + lane;
                 bool in = false;
