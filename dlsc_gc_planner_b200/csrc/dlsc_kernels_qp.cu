@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
         S.viol[la] = (double)(clock64() - t_begin);
         // phase sums over the agents of this kernel: counters 9..15 <- prologue (1+2), map_x (3), far2 (4), scan (5),
         // candidate + Hinv staging (8), w = H^-1 a (9), serial step of thread 0 (10) ; y update (11) goes to counter 0 + 64-bit pack
+#ifdef DLSC_QP_CYCLES_HEAVY
+        if (S.qp_iters[la] >= DLSC_QP_CYCLES_HEAVY)
+#endif
+        {
         atomicAdd(S.counters + 9, (unsigned long long)(ticks[1] + ticks[2]));
         atomicAdd(S.counters + 10, (unsigned long long)ticks[3]);
         atomicAdd(S.counters + 11, (unsigned long long)ticks[5]);
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
         atomicAdd(S.counters + 13, (unsigned long long)ticks[9]);
         atomicAdd(S.counters + 14, (unsigned long long)ticks[10]);
         atomicAdd(S.counters + 15, (unsigned long long)ticks[11]);
+        }
     }
 #endif
     if (threadIdx.x == 0) {

@@ -53,6 +53,21 @@ DLSC_HD void fast_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     s.act = nullptr;
 }
 
+DLSC_HD float int_as_f32(int i) {
+#ifdef __CUDA_ARCH__
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+DLSC_HD int f32_as_int(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+
 constexpr double kGiTol = 1e-10;   // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
 
 struct PairRowD { int fam, k, pa, pb; };
@@ -84,10 +99,13 @@ DLSC_HD void pair_violation(const DevParams& P, const QpTab& T, const QpIn& in, 
 // iterate being scanned, a row of slack s can only be violated when dev[m] >= s (Cauchy-Schwarz), so items with
 // slack > dev[m] + margin are not evaluated (margin 1e-3 m covers the rounding of the two evaluations).  Exact, and
 // it adapts to every iterate: far from the initial trajectory more rows are evaluated, never fewer than needed.
-constexpr double kScreenMargin = 1e-3;
+constexpr float kScreenMargin = 1e-3f;
+// dev2: squared per-segment deviations as float bit patterns (positive floats order like ints: gi_map_x_dev)
+// mine: out, this thread evaluated the winning row (exactly one thread: every row is evaluated by one thread);
+// row: out (may be null), the thread's best LSC row as lsc_row_data would return it (valid when its best is an LSC row)
 DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
-                     const int* sm_nbr, bool screened, const double* dev, double& vmax_out, double& id_out,
-                     double& nviol_out) {
+                     const int* sm_nbr, bool screened, const int* dev2, double& vmax_out, double& id_out,
+                     double& nviol_out, bool& mine, LscRowData* row) {
     const int npt = T.npt, np = T.np, Kc = P.K, K = in.K;
     const bool D3 = (P.D == 3);
     double best = -1e300, best_id = 1e300;
@@ -104,7 +122,10 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
     const int M = P.M, items = K * M;
     for (int e = c.tid; e < items; e += c.nthr) {
         const int cc = e / M, m = e - cc * M;
-        if (screened && (double)in.near[e] > dev[m] + kScreenMargin) continue;      // row screen
+        if (screened) {                                                             // row screen
+            const float s = in.near[e] - kScreenMargin;
+            if (s > 0.f && s * s > int_as_f32(dev2[m])) continue;
+        }
         const float* nr = in.normal + ((size_t)cc * M + m) * 3;
         const V3 nv = v3_load(nr);
         const double* dd = in.d + ((size_t)cc * M + m) * kP;
@@ -129,41 +150,65 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             if (D3) b -= n2 * (double)av[i][2];
             const double v = -(n0 * x[pt] + n1 * x[npt + pt] + (D3 ? n2 * x[2 * npt + pt] : 0.0)) - b;
             const double id = 2.0 * np + (double)(pt * Kc + cc);
-            if (v > best || (v == best && id < best_id)) { best = v; best_id = id; }
+            if (v > best || (v == best && id < best_id)) {
+                best = v; best_id = id;
+                if (row) { row->n0 = n0; row->n1 = n1; row->n2 = n2; row->b = b; }
+            }
             n_bad += (v > kGiTol);
         }
     }
+    const double my_best = best, my_id = best_id;
     double nvd = (double)n_bad, unused = 0.0;
     c.reduce_argmax(best, best_id, unused, nvd);
+    mine = (my_best == best && my_id == best_id);
     vmax_out = best; id_out = best_id; nviol_out = nvd;
 }
 
-// map y -> x, the per-segment deviation of x from the initial trajectory, then one scan for the most violated row
+// x = c + T y (map_x), and on the way the squared deviation of every constrained control point from the initial
+// trajectory, max-reduced per segment into dev2[m] (float bit patterns through an integer atomic max: order
+// independent, hence deterministic; inflated by 1e-5 so that the float rounding can only make the screen weaker).
+// dev2 must be zero on entry (gi_prologue / the end of the previous scan).
+DLSC_HD void gi_map_x_dev(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const double* y, const double* cst,
+                          double* x, int* dev2, bool screened) {
+    const int M = T.M, nyd = T.nyd, npt = T.npt, D = T.D;
+    for (int pt = c.tid; pt < npt; pt += c.nthr) {
+        const int m = pt / kP, i = pt - m * kP;
+        double r2 = 0.0;
+        for (int k = 0; k < D; k++) {
+            const double* yk = y + k * nyd;
+            double v;
+            if (i >= 3) v = (m == M - 1) ? yk[3 * (M - 1)] : yk[3 * m + i - 3];
+            else if (m == 0) v = cst[k * 3 + i];
+            else {
+                const double* q = yk + 3 * (m - 1);
+                v = (i == 0) ? q[2] : (i == 1 ? 2.0 * q[2] - q[1] : 4.0 * q[2] - 4.0 * q[1] + q[0]);
+            }
+            x[k * npt + pt] = v;
+            if (screened) { const double e = v - (double)in.init_traj[pt * 3 + k]; r2 += e * e; }
+        }
+        if (screened && pt >= 3) {                                  // points 0..2 of segment 0 carry no LSC rows
+            const int bits = f32_as_int((float)r2 * 1.00001f + 1e-30f);
+#ifdef __CUDA_ARCH__
+            atomicMax(dev2 + m, bits);
+#else
+            if (bits > dev2[m]) dev2[m] = bits;
+#endif
+        }
+    }
+}
+
+// map y -> x with the per-segment deviations, then one scan for the most violated row; leaves dev2 zeroed
 DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
-                             const QpSmem& sm, bool screened, double& vmax, double& idsel, double* nviol = nullptr) {
-    map_x(c, T, sm.y, sm.cst, sm.x);
+                             const QpSmem& sm, bool screened, double& vmax, double& idsel, bool& mine, LscRowData* row,
+                             double* nviol = nullptr) {
+    int* dev2 = reinterpret_cast<int*>(sm.dev);
+    gi_map_x_dev(c, P, T, in, sm.y, sm.cst, sm.x, dev2, screened);
     c.sync();
     c.tick(3);
-    if (screened) {
-        const int npt = T.npt;
-        const bool D3 = (P.D == 3);
-        for (int m = c.tid; m < P.M; m += c.nthr) {
-            double far2 = 0.0;
-            for (int i = (m == 0 ? 3 : 0); i < kP; i++) {                  // points 0..2 of segment 0 carry no LSC rows
-                const int pt = m * kP + i;
-                const double ex = sm.x[pt] - (double)in.init_traj[pt * 3];
-                const double ey = sm.x[npt + pt] - (double)in.init_traj[pt * 3 + 1];
-                const double ez = D3 ? sm.x[2 * npt + pt] - (double)in.init_traj[pt * 3 + 2] : 0.0;
-                const double r2 = ex * ex + ey * ey + ez * ez;
-                far2 = (r2 > far2) ? r2 : far2;
-            }
-            sm.dev[m] = sqrt(far2);
-        }
-        c.sync();
-    }
-    c.tick(4);
     double nv = 0.0;
-    gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, sm.dev, vmax, idsel, nv);
+    gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, dev2, vmax, idsel, nv, mine, row);
+    // every thread is past the reduction, so nobody reads dev2 any more: reset it for the next map
+    for (int m = c.tid; m < P.M; m += c.nthr) dev2[m] = 0;
     if (nviol) *nviol = nv;
     c.tick(5);
 }
@@ -184,12 +229,17 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
     for (int guard = 0; guard < 400; guard++) {
         if (!same_p) {
             double vmax, idsel;
+            bool mine;                         // this thread builds the candidate row
+            LscRowData row;
+            bool have_row = false;
             if (guard == 0 && seed) {          // the fast path already scanned the unconstrained optimum
                 map_x(c, T, sm.y, sm.cst, sm.x);
                 c.sync();
                 vmax = seed[0]; idsel = seed[1];
+                mine = (c.tid == 0);
             } else {
-                gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel);
+                gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel, mine, &row);
+                have_row = true;
             }
             x_current = true;
             *viol_out = vmax;
@@ -199,8 +249,9 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                 for (int e = c.tid; e < nyd * nyd; e += c.nthr) g.Hinv[e] = src[e];
                 have_hinv = true;
             }
-            // ---- candidate row p: x-space form -> y-space form (thread 0) ----
-            if (c.tid == 0) {
+            // ---- candidate row p: x-space form -> y-space form, by the thread that evaluated it in the scan (it
+            //      still holds the row's coefficients; thread 0 re-reads them after a seeded start) ----
+            if (mine) {
                 const int id = (int)idsel;
                 int xi[3] = {0, 0, 0}; double xc[3] = {0, 0, 0}; int nxe = 0; double bp;
                 if (id < 2 * np) {
@@ -220,7 +271,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     bp = side ? -lo : hi;
                 } else {
                     const int o = id - 2 * np, pt = o / Kc, cc = o - pt * Kc;
-                    const LscRowData rw = lsc_row_data(P, in, pt, cc);
+                    const LscRowData rw = have_row ? row : lsc_row_data(P, in, pt, cc);
                     xi[0] = pt; xc[0] = -rw.n0; xi[1] = npt + pt; xc[1] = -rw.n1; nxe = 2;
                     if (D3) { xi[2] = 2 * npt + pt; xc[2] = -rw.n2; nxe = 3; }
                     bp = rw.b;
@@ -294,9 +345,11 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             else {
                 for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
                 u_p += t;
-                for (int e = 0; e < ny; e++) sm.ax1[e] = 0.0;
-                for (int j = 0; j < q; j++)
-                    for (int tt = 0; tt < 9; tt++) { const int jj = g.yi[9 * j + tt]; if (jj >= 0) sm.ax1[jj] += g.r[j] * g.yc[9 * j + tt]; }
+                if (q > 0) {                 // t_y = A' r, only read by the y update when q > 0
+                    for (int e = 0; e < ny; e++) sm.ax1[e] = 0.0;
+                    for (int j = 0; j < q; j++)
+                        for (int tt = 0; tt < 9; tt++) { const int jj = g.yi[9 * j + tt]; if (jj >= 0) sm.ax1[jj] += g.r[j] * g.yc[9 * j + tt]; }
+                }
                 if (t2 <= t1) {
                     if (q == kGiQ) flag = 3.0;
                     else {
@@ -392,6 +445,7 @@ DLSC_HD void gi_prologue(const Cta& c, const DevParams& P, const QpTab& T, QpIn&
         sm.cst[k * 3] = c0; sm.cst[k * 3 + 1] = c1; sm.cst[k * 3 + 2] = c2;
     }
     for (int cc = c.tid; cc < in.K; cc += c.nthr) sm.off[cc] = in.nbr_idx[cc];
+    for (int m = c.tid; m < kMaxM * 2; m += c.nthr) reinterpret_cast<int*>(sm.dev)[m] = 0;
     if (P.use_sfc) {
         for (int e = c.tid; e < M * 6; e += c.nthr) sm.sfcs[e] = in.sfc[e];
         in.sfc = sm.sfcs;
@@ -479,7 +533,8 @@ DLSC_HD bool qp_agent_fast(const Cta& c, const DevParams& P, const QpTab& T, con
     gi_prologue(c, P, T, in, sm, qc);
     const bool screened = (P.qp_screen > 0) && (in.near != nullptr);
     double vmax, idsel, nviol = 0.0;
-    gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel, &nviol);
+    bool mine;
+    gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel, mine, nullptr, &nviol);
     if (vmax > kGiTol) {
         // seed[3]: number of rows violated at the unconstrained optimum -- a proxy for the active-set iterations
         // the agent will need, used to start the expensive agents first (k_qp_gi)

@@ -33,6 +33,10 @@ for t in range(args.settle + 6):
                   "serial %.1f yupdate %.1f | total residency %.1f  (agents %d, iterations %d)" % (
                       tuple(raw[k] / 1e6 for k in range(9, 16)) + (cyc[it > 0].sum() / 1e6 if os.environ.get("DLSC_QP_FAST") != "0" else cyc.sum() / 1e6,
                                                                     int((it > 0).sum()), int(it.sum()))))
+            hv = int(os.environ.get("HEAVY", "0"))
+            if hv:
+                print("   (phase sums above are over the %d agents with >= %d iterations: %d iterations, residency %.1f Mcycles)" % (
+                    int((it >= hv).sum()), hv, int(it[it >= hv].sum()), cyc[it >= hv].sum() / 1e6))
             for lo, hi in ((0, 0), (1, 1), (2, 2), (3, 5), (6, 20), (21, 1000)):
                 sel = (it >= lo) & (it <= hi)
                 if sel.any():
