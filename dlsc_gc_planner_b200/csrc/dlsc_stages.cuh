@@ -454,6 +454,18 @@ DLSC_HD int sat_count(const Group& g, const EdtDev& E, int x0, int x1, int y0, i
     return s;
 }
 
+// Lattice description of one axis of a box [lo, hi]: vertex count mm = floor((hi - lo + eps) / res) + 1 (the
+// reference's loop bound, collision_constraints.cpp:868-872) and the lattice index vv of lo relative to min_key
+// (kNoLattice when lo is not within 1e-2 cells of a lattice vertex).
+DLSC_HD void lattice_axis(const EdtDev& E, double res, int ax, float lo, float hi, int& mm, int& vv) {
+    // floor(x / res): the quotient sits ~eps/res = 1e-4 above an integer, so the product with 1/res has
+    // the same floor unless it lands within 1e-9 of an integer; only then the IEEE division decides
+    const double x = (hi - lo) + kEpsF, q = x * E.inv_res, f = floor(q);
+    mm = ((E.res == res && q - f > 1e-9 && q - f < 1.0 - 1e-9) ? (int)f : (int)floor(x / res)) + 1;
+    const double t = E.inv_res * (double)lo, vr = rint(t);
+    vv = (fabs(t - vr) > 1e-2) ? kNoLattice : (int)vr - E.min_key[ax];
+}
+
 // isObstacleInSFC through the vertex mask.  Returns 0 / 1, or -1 when this box cannot use the mask (a corner
 // off the lattice, ambiguous cell choice, oversized) -> the caller runs the record path.
 // One work item = 16 consecutive z-vertices of one (x, y) lattice column: one 16-byte load.
@@ -476,13 +488,7 @@ DLSC_HD int obstacle_in_box_mask(const Group& g, const DevParams& P, const EdtDe
             mm[ax] = tab->km[ax]; vv[ax] = tab->kv[ax];
         } else {
             smiss = true;
-            {   // floor(x / res): the quotient sits ~eps/res = 1e-4 above an integer, so the product with 1/res has
-                // the same floor unless it lands within 1e-9 of an integer; only then the IEEE division decides
-                const double x = (hi - lo) + kEpsF, q = x * E.inv_res, f = floor(q);
-                mm[ax] = ((E.res == res && q - f > 1e-9 && q - f < 1.0 - 1e-9) ? (int)f : (int)floor(x / res)) + 1;
-            }
-            const double t = E.inv_res * (double)lo, vr = rint(t);
-            vv[ax] = (fabs(t - vr) > 1e-2) ? kNoLattice : (int)vr - E.min_key[ax];
+            lattice_axis(E, res, ax, lo, hi, mm[ax], vv[ax]);
         }
     }
     if (smiss) {
@@ -687,9 +693,36 @@ DLSC_HD bool box_in_boundary(const DevParams& P, const Box& b) {
 }
 
 // expandSFCIncrementally (:1023-1093)
+// Box test of the greedy growth with the lattice description of the box kept in registers.  Consecutive tests of
+// expand_incrementally differ in one face, so only the moved axis is re-derived from the floats (lattice_axis, the
+// same formulas obstacle_in_box_mask applies to all three axes); when the summed-area query over that vertex range
+// is empty the box is free -- exactly the first exit of obstacle_in_box_mask, with the same work counters.  Anything
+// else (flagged vertices, off-lattice corner, oversized or out-of-grid range, no mask) goes through obstacle_in_box.
+struct LatticeBox { int vv[3], mm[3]; };
+DLSC_HD bool box_test(const Group& g, const DevParams& P, const EdtDev& E, const Box& b, const LatticeBox& L, bool fast_ok,
+                      double margin, SfcTab* memo, long long* lookups) {
+    if (fast_ok && L.mm[0] > 0 && L.mm[1] > 0 && L.mm[2] > 0 && L.mm[0] <= kSfcTabMax && L.mm[1] <= kSfcTabMax &&
+        L.mm[2] <= kSfcTabMax && L.vv[0] >= 0 && L.vv[1] >= 0 && L.vv[2] >= 0 && L.vv[0] + L.mm[0] - 1 <= E.dims[0] &&
+        L.vv[1] + L.mm[1] - 1 <= E.dims[1] && L.vv[2] + L.mm[2] - 1 <= E.dims[2]) {
+        if (sat_count(g, E, L.vv[0], L.vv[0] + L.mm[0] - 1, L.vv[1], L.vv[1] + L.mm[1] - 1, L.vv[2],
+                      L.vv[2] + L.mm[2] - 1) == 0) {
+            if (lookups && g.lane == 0) {
+                const long long nvert = (long long)L.mm[0] * L.mm[1] * L.mm[2];
+                lookups[0] += nvert;
+                if (lookups[5]) lookups[4] += nvert;
+                lookups[3] += 1;
+                lookups[1] += 1;
+            }
+            return false;
+        }
+    }
+    return obstacle_in_box(g, P, E, b, margin, memo, lookups);
+}
+
 DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtDev& E, const Box& init,
                                   double margin, double max_vel, Box& out, SfcTab* memo, long long* lookups) {
     const double res = P.world_res;
+    const bool fast_ok = E.vmask && E.sat && margin == E.mask_margin && E.zs <= kSfcZsMax;
     if (lookups) lookups[5] = 1;                  // the initial box and the slabs are the algorithmic tests
     if (obstacle_in_box(g, P, E, init, margin, memo, lookups)) return false;
     int axes = 0x543210;              // packed axis list, 4 bits each: -x -y -z +x +y +z
@@ -699,19 +732,26 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
     const int max_iter = (int)round(span / res) + 1;
     int i = -1;
     Box sfc = init, cand = init, upd = init;
+    // lattice descriptions: Ls of `sfc`, Lc of `cand`, Lu of `upd` (Lu = Lc with the growth axis replaced by the slab)
+    LatticeBox Ls, Lc, Lu;
+#pragma unroll
+    for (int k = 0; k < 3; k++) lattice_axis(E, res, k, v3_get(init.lo, k), v3_get(init.hi, k), Ls.mm[k], Ls.vv[k]);
+    Lc = Ls; Lu = Ls;
     while (n_axes > 0) {
         cand = sfc; upd = sfc;
+        Lc = Ls; Lu = Ls;
         if (lookups) lookups[5] = 0;              // the whole-box recheck at the top of a pass is the reference's redundancy
         // isSFCInBoundary on `upd`: the whole box at the top of a pass; afterwards `upd` is a slab that shares four
         // faces with the already verified `cand`, so only its two faces along the growth axis are new
         bool inside = box_in_boundary(P, upd);
-        while (inside && !obstacle_in_box(g, P, E, upd, margin, memo, lookups)) {
+        while (inside && !box_test(g, P, E, upd, Lu, fast_ok, margin, memo, lookups)) {
             if (lookups) lookups[5] = 1;
             i++;
             if (i >= n_axes) i = 0;
             const int ax = (axes >> (4 * i)) & 0xf;
             const int a3 = (ax < 3) ? ax : ax - 3;
             sfc = cand; upd = cand;
+            Ls = Lc; Lu = Lc;
             if (ax < 3) {
                 v3_set(upd.hi, ax, v3_get(cand.lo, ax));
                 v3_set(cand.lo, ax, (float)(v3_get(cand.lo, ax) - res));
@@ -720,6 +760,14 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
                 v3_set(upd.lo, a3, v3_get(cand.hi, a3));
                 v3_set(cand.hi, a3, (float)(v3_get(cand.hi, a3) + res));
                 v3_set(upd.hi, a3, v3_get(cand.hi, a3));
+            }
+            {   // only axis a3 of `cand` and `upd` changed
+                int mc, vc, mu, vu;
+                lattice_axis(E, res, a3, v3_get(cand.lo, a3), v3_get(cand.hi, a3), mc, vc);
+                lattice_axis(E, res, a3, v3_get(upd.lo, a3), v3_get(upd.hi, a3), mu, vu);
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if (k == a3) { Lc.mm[k] = mc; Lc.vv[k] = vc; Lu.mm[k] = mu; Lu.vv[k] = vu; }
             }
             const double wlo = (a3 == 0) ? P.world_min[0] : (a3 == 1 ? P.world_min[1] : P.world_min[2]);
             const double whi = (a3 == 0) ? P.world_max[0] : (a3 == 1 ? P.world_max[1] : P.world_max[2]);
