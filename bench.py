@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--settle", type=int, default=25, help="untimed rollout steps before the timed region")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU record exchange: stores over NVLink peer memory (default) or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -282,7 +284,8 @@ def run_ours(args):
     pl.build_edt(m.boxes)
     edt_ms = pl.edt_build_ms()
     pl.set_stream(torch.cuda.current_stream().cuda_stream)
-    exchange = sharding.RecordExchange(pl, world, rank, device=dev)     # records live in a torch tensor NCCL gathers in place
+    # per-step exchange of the agent records: peer-memory stores over NVLink (default) or an in-place NCCL all-gather
+    exchange = sharding.RecordExchange(pl, world, rank, device=dev, mode=args.exchange)
     wp_dev = torch.from_numpy(np.ascontiguousarray(rec["wp"][:, sl])).to(dev)        # [T][NL][3] resident
     peak_fp64 = pl.measure_fp64_peak()
 
@@ -422,8 +425,10 @@ def run_ours(args):
             "config": {"workload": "synthetic %d-agent 3D random-forest swarm (BASELINE configs[3]): M=10 n=5 dim=3, "
                                    "SFC on a %dx%dx%d EDT grid, comm range 3, max_nbr %d" % (
                                        N, edt[2][0], edt[2][1], edt[2][2], args.max_nbr),
-                       "agents": N, "agents_per_gpu": NL, "settle_steps": args.settle, "parallelism": "agents sharded x%d, "
-                       "NCCL all-gather of %d-float records per step" % (world, pl.rec_floats),
+                       "agents": N, "agents_per_gpu": NL, "settle_steps": args.settle, "parallelism": "agents sharded x%d, %s of %d-float records per step" % (
+                           world, {"p2p": "peer-memory all-gather over NVLink (dlsc_exchange_records)",
+                                   "nccl": "NCCL all-gather", "single": "no exchange"}.get(exchange.mode, exchange.mode),
+                           pl.rec_floats),
                        "l2": "per-step working set (EDT grid %.0f MB + scratch) exceeds L2; inputs change every step" % (
                            edt[0].size * 16 / 1e6)},
             "e2e": {"value": N * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -477,9 +482,14 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, m, edt, rec, snap, args, steps=1)
     if world > 1:
+        if exchange.mode == "p2p":
+            pl.p2p_status()                      # raises if a peer ever missed an exchange
+            pl.p2p_disconnect()
+        dist.barrier()
+    pl.close()
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    pl.close()
     if rank == 0:
         print(json.dumps(out))
 

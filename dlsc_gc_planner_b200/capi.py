@@ -56,7 +56,8 @@ EXPORTS = (
     "dlsc_get_timings dlsc_launch_count dlsc_get_counters dlsc_waypoint_device dlsc_traj_device "
     "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
     "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups dlsc_edt_dims dlsc_build_edt "
-    "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms").split()
+    "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
+    "dlsc_p2p_status dlsc_p2p_disconnect").split()
 
 
 def build_library(force=False):
@@ -204,6 +205,27 @@ class SwarmPlanner:
 
     def edt_build_ms(self):
         return float(self.lib.dlsc_edt_build_ms(self.ctx))
+
+    # -- record exchange over peer memory (one process per GPU) -----------------------------------
+    def p2p_export(self):
+        h = (C.c_ubyte * 64)()
+        self._ck(self.lib.dlsc_p2p_export(self.ctx, h))
+        return bytes(h)
+
+    def p2p_connect(self, world, rank, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.dlsc_p2p_connect(self.ctx, C.c_int(world), C.c_int(rank), buf))
+
+    def exchange_records(self):
+        self._ck(self.lib.dlsc_exchange_records(self.ctx))
+
+    def p2p_status(self):
+        self._ck(self.lib.dlsc_p2p_status(self.ctx))
+
+    def p2p_disconnect(self):
+        self._ck(self.lib.dlsc_p2p_disconnect(self.ctx))
 
     def set_groups(self, group):
         """Mission index per local agent (Monte-Carlo batches); call after construction / reset."""

@@ -43,6 +43,16 @@ struct dlsc_ctx {
     int32_t* edt_sat = nullptr;        // summed-area table over the flagged mask vertices
     uint8_t* edt_mask = nullptr;       // lattice-vertex mask of the SFC vertex test (built lazily for margin_host)
     bool mask_dirty = false;
+    // record exchange over peer memory (dlsc_p2p_*): one shared block per rank = [flags 256 B][records x 2]
+    struct {
+        bool exported = false, on = false;
+        int world = 1, rank = 0, cur = 0;
+        unsigned long long step = 0;
+        void* block = nullptr;                     // own block (cudaMalloc, IPC-exported)
+        void* peer_block[kP2PMaxWorld] = {};       // mapped blocks of the peers (own entry = block)
+        unsigned* done = nullptr;
+        int* err = nullptr;
+    } p2p;
     double edt_build_ms = 0.0;         // device time of the last dlsc_build_edt* (the three EDT passes)
     double margin_host = 0.0;          // radius of the first local agent (all BASELINE missions: 0.15 for every agent)
     int64_t launches = 0;
@@ -249,6 +259,11 @@ void dlsc_destroy(dlsc_ctx* c) {
     if (c->edt_centre) cudaFree(c->edt_centre);
     if (c->edt_mask) cudaFree(c->edt_mask);
     if (c->edt_sat) cudaFree(c->edt_sat);
+    if (c->p2p.exported) {
+        for (int r = 0; r < c->p2p.world; r++)
+            if (c->p2p.on && r != c->p2p.rank && c->p2p.peer_block[r]) cudaIpcCloseMemHandle(c->p2p.peer_block[r]);
+        cudaFree(c->p2p.block); cudaFree(c->p2p.done); cudaFree(c->p2p.err);
+    }
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -504,6 +519,7 @@ float* dlsc_records_device(dlsc_ctx* c) { return c ? c->S.rec : nullptr; }
 int dlsc_record_floats(const dlsc_ctx* c) { return c ? c->P.rec : 0; }
 int dlsc_bind_records(dlsc_ctx* c, float* p) {
     if (!c || !p) return fail("dlsc_bind_records: null argument");
+    if (c->p2p.exported) return fail("dlsc_bind_records: records live in the peer-memory block (dlsc_p2p_export)");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(p, c->S.rec, (size_t)c->P.N * c->P.rec * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -511,6 +527,95 @@ int dlsc_bind_records(dlsc_ctx* c, float* p) {
     c->rec_owned = false;
     return 0;
 }
+// ---- record exchange over NVLink peer memory ------------------------------------------------------------------
+static size_t p2p_buf_floats(const dlsc_ctx* c) { return ((size_t)c->P.N * c->P.rec + 63) / 64 * 64; }
+static float* p2p_buffer(const dlsc_ctx* c, void* block, int which) {
+    return reinterpret_cast<float*>(static_cast<char*>(block) + 256) + (size_t)which * p2p_buf_floats(c);
+}
+int dlsc_p2p_export(dlsc_ctx* c, void* handle64) {
+    if (!c || !handle64) return fail("dlsc_p2p_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(c->device));
+    if (!c->p2p.exported) {
+        if (!c->rec_owned) return fail("dlsc_p2p_export: records are bound to caller memory (dlsc_bind_records)");
+        if (c->P.rec % 4 != 0) return fail("dlsc_p2p_export: record size must be a multiple of 4 floats");
+        const size_t bytes = 256 + 2 * p2p_buf_floats(c) * sizeof(float);
+        CK(cudaMalloc(&c->p2p.block, bytes));
+        CK(cudaMemset(c->p2p.block, 0, bytes));
+        CK(cudaMalloc(&c->p2p.done, sizeof(unsigned)));
+        CK(cudaMemset(c->p2p.done, 0, sizeof(unsigned)));
+        CK(cudaMalloc(&c->p2p.err, sizeof(int)));
+        CK(cudaMemset(c->p2p.err, 0, sizeof(int)));
+        CK(cudaStreamSynchronize(c->stream));
+        const size_t nb = (size_t)c->P.N * c->P.rec * sizeof(float);
+        CK(cudaMemcpy(p2p_buffer(c, c->p2p.block, 0), c->S.rec, nb, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(p2p_buffer(c, c->p2p.block, 1), c->S.rec, nb, cudaMemcpyDeviceToDevice));
+        c->S.rec = p2p_buffer(c, c->p2p.block, 0);      // the old array stays allocated until dlsc_destroy
+        c->p2p.cur = 0;
+        c->p2p.exported = true;
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->p2p.block));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int dlsc_p2p_connect(dlsc_ctx* c, int world, int rank, const void* handles) {
+    if (!c || !handles) return fail("dlsc_p2p_connect: null argument");
+    if (!c->p2p.exported) return fail("dlsc_p2p_connect: call dlsc_p2p_export first");
+    if (world < 1 || world > kP2PMaxWorld || rank < 0 || rank >= world) return fail("dlsc_p2p_connect: bad world / rank");
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { c->p2p.peer_block[r] = c->p2p.block; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)r * 64, 64);
+        CK(cudaIpcOpenMemHandle(&c->p2p.peer_block[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p.world = world; c->p2p.rank = rank; c->p2p.on = true;
+    return 0;
+}
+int dlsc_exchange_records(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    if (!c->p2p.on) return fail("dlsc_exchange_records: not connected (dlsc_p2p_connect)");
+    CK(cudaSetDevice(c->device));
+    auto& X = c->p2p;
+    const int next = X.cur ^ 1;
+    float* dst[kP2PMaxWorld]; unsigned long long* flag[kP2PMaxWorld];
+    for (int r = 0; r < X.world; r++) {
+        dst[r] = p2p_buffer(c, X.peer_block[r], next);
+        flag[r] = reinterpret_cast<unsigned long long*>(X.peer_block[r]);
+    }
+    X.step++;
+    const size_t off = (size_t)c->P.begin * c->P.rec, n = (size_t)c->P.NL * c->P.rec;
+    launch_p2p_push(c->S.rec + off, n, off, X.world, X.rank, X.step, dst, flag, X.done, c->stream);
+    launch_p2p_wait(reinterpret_cast<unsigned long long*>(X.block), X.world, X.step, X.err, c->stream);
+    c->launches += 2;
+    X.cur = next;
+    c->S.rec = p2p_buffer(c, X.block, next);
+    CK(cudaGetLastError());
+    return 0;
+}
+// unmap the peers' blocks (call on every rank, then a barrier, before any rank destroys its context)
+int dlsc_p2p_disconnect(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    if (!c->p2p.on) return 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < c->p2p.world; r++)
+        if (r != c->p2p.rank && c->p2p.peer_block[r]) { cudaIpcCloseMemHandle(c->p2p.peer_block[r]); c->p2p.peer_block[r] = nullptr; }
+    c->p2p.on = false;
+    return 0;
+}
+int dlsc_p2p_status(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    if (!c->p2p.exported) return 0;
+    CK(cudaSetDevice(c->device));
+    int e = 0;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&e, c->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return fail("dlsc_p2p_status: a peer did not publish its records within the timeout");
+    return 0;
+}
+
 int dlsc_set_records(dlsc_ctx* c, int first, int count, const float* host) {
     if (!c || !host || first < 0 || count < 0 || first + count > c->P.N) return fail("dlsc_set_records: bad argument");
     CK(cudaSetDevice(c->device));

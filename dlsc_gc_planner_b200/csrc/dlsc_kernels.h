@@ -65,6 +65,11 @@ void launch_sat_build(const EdtDev& E, int32_t* sat, cudaStream_t st);   // 4 la
 void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
 
+constexpr int kP2PMaxWorld = 16;
+void launch_p2p_push(const float* src, size_t n_floats, size_t slice_off_floats, int world, int rank, unsigned long long step,
+                     float* const* dst, unsigned long long* const* flag, unsigned* done, cudaStream_t st);
+void launch_p2p_wait(const unsigned long long* flags, int world, unsigned long long step, int* err, cudaStream_t st);
+
 double measure_fp64_peak(int device, cudaStream_t st);
 QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device);
 int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);

@@ -522,4 +522,60 @@ void launch_reset(const DevParams& P, const DevState& S, const float* start_dev,
     k_reset<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S, start_dev);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Record exchange over NVLink peer memory (one process per GPU, dlsc_p2p_*): the all-gather of the agent records as
+// direct stores.  k_p2p_push copies this rank's slice of the records into the *next* record buffer of every rank
+// (its own included); the last CTA to finish publishes the step number in every rank's flag slot (system-scope fence
+// before, so the data is visible first).  k_p2p_wait spins until every rank's flag has reached the step.  Records are
+// double buffered: a rank that runs ahead writes the buffer its peers are not reading.
+struct P2PPeers { float* dst[kP2PMaxWorld]; unsigned long long* flag[kP2PMaxWorld]; };
+
+__global__ void __launch_bounds__(256) k_p2p_push(const float4* __restrict__ src, size_t n4, size_t slice_off4, int world, int rank,
+                                                  unsigned long long step, const __grid_constant__ P2PPeers peers, unsigned* done) {
+    for (int r = 0; r < world; r++) {
+        float4* dst = reinterpret_cast<float4*>(peers.dst[r]) + slice_off4;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {                       // every CTA's stores are fenced: publish
+            *done = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; r++) {
+                volatile unsigned long long* f = peers.flag[r] + rank;
+                *f = step;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void k_p2p_wait(const unsigned long long* flags, int world, unsigned long long step, long long timeout_cycles, int* err) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const volatile unsigned long long* f = flags + r;
+    const long long t0 = clock64();
+    while (*f < step) {
+        if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+void launch_p2p_push(const float* src, size_t n_floats, size_t slice_off_floats, int world, int rank, unsigned long long step,
+                     float* const* dst, unsigned long long* const* flag, unsigned* done, cudaStream_t st) {
+    P2PPeers pp;
+    for (int r = 0; r < world; r++) { pp.dst[r] = dst[r]; pp.flag[r] = flag[r]; }
+    const size_t n4 = n_floats / 4;
+    int ctas = (int)((n4 + 255) / 256);
+    if (ctas > 64) ctas = 64;
+    if (ctas < 1) ctas = 1;
+    k_p2p_push<<<ctas, 256, 0, st>>>(reinterpret_cast<const float4*>(src), n4, slice_off_floats / 4, world, rank, step, pp, done);
+}
+void launch_p2p_wait(const unsigned long long* flags, int world, unsigned long long step, int* err, cudaStream_t st) {
+    k_p2p_wait<<<1, 32, 0, st>>>(flags, world, step, 20000000000LL, err);   // ~10 s
+}
+
 }  // namespace dlsc

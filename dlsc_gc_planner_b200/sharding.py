@@ -18,11 +18,14 @@ def agent_block(n_agents, world_size, rank):
 class RecordExchange:
     """All-gather of the records of one SwarmPlanner.
 
+    p2p mode:    (default on GPUs) every rank stores its slice straight into the peers' record arrays over NVLink
+                 (dlsc_p2p_export / dlsc_p2p_connect / dlsc_exchange_records); torch.distributed only carries the
+                 64-byte IPC handles once;
     device mode: the planner's record array is bound to a torch CUDA tensor and gathered in place (NCCL);
     host mode:   records are fetched / stored through the C ABI and gathered with the default (gloo) group.
     """
 
-    def __init__(self, planner, world_size, rank, device=None):
+    def __init__(self, planner, world_size, rank, device=None, mode="p2p"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -31,6 +34,16 @@ class RecordExchange:
         self.equal = len({n for _, n in self.blocks}) == 1
         rf = planner.rec_floats
         self.device = device
+        self.mode = "host" if device is None else mode
+        if device is not None and mode == "p2p" and self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, planner.p2p_export())
+            planner.p2p_connect(self.world, self.rank, handles)
+            return
+        if device is not None and self.world == 1:
+            self.mode = "single"
+            return
+        self.mode = "nccl" if device is not None else "host"
         if device is not None:
             self.rec = torch.zeros(planner.N * rf, dtype=torch.float32, device=device)
             planner.bind_records(self.rec.data_ptr())
@@ -40,6 +53,9 @@ class RecordExchange:
 
     def gather(self):
         if self.world == 1:
+            return
+        if self.mode == "p2p":
+            self.pl.exchange_records()
             return
         if self.device is not None:
             if self.equal:

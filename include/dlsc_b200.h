@@ -166,6 +166,23 @@ int dlsc_bind_records(dlsc_ctx* ctx, float* device_ptr);
 int dlsc_set_records(dlsc_ctx* ctx, int first, int count, const float* host);
 int dlsc_get_records(dlsc_ctx* ctx, int first, int count, float* host);
 
+/* Multi-GPU record exchange over NVLink peer memory instead of NCCL (one process per GPU on one node; replaces the
+ * copies of MultiSyncSimulator::broadcastMsgs, src/multi_sync_simulator.cpp:468-514).  Every rank moves its records
+ * into an IPC-shareable block (dlsc_p2p_export returns its 64-byte cudaIpcMemHandle_t), the handles are exchanged by
+ * the caller (any transport) and opened with dlsc_p2p_connect (handles = [world][64] bytes in rank order).
+ * dlsc_exchange_records then is the per-step all-gather: a kernel stores the local slice into every rank's record
+ * array over NVLink and raises a per-rank step flag, a second kernel waits for the flags of all ranks; stream
+ * ordered, no host synchronisation.  Records are double buffered, so ranks may run one exchange apart; every rank
+ * must call it the same number of times, and a host-side overwrite of the records (dlsc_set_records) must be
+ * separated from the peers' exchanges by dlsc_sync + a barrier of the caller.  dlsc_p2p_status synchronises and
+ * reports a peer that never arrived (10 s timeout in the wait kernel).  world <= 16. */
+int dlsc_p2p_export(dlsc_ctx* ctx, void* handle64);
+int dlsc_p2p_connect(dlsc_ctx* ctx, int world, int rank, const void* handles);
+int dlsc_exchange_records(dlsc_ctx* ctx);
+int dlsc_p2p_status(dlsc_ctx* ctx);
+/* unmap the peers' blocks: call on every rank, then barrier, before any rank calls dlsc_destroy */
+int dlsc_p2p_disconnect(dlsc_ctx* ctx);
+
 /* One replan of every local agent (= TrajPlanner::plan for each agent of the block).  Stream
  * ordered; returns after enqueueing.  dlsc_step == dlsc_run_stages(DLSC_STAGE_ALL) + seq++. */
 int dlsc_step(dlsc_ctx* ctx);
