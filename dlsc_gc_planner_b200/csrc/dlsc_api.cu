@@ -519,7 +519,7 @@ float* dlsc_records_device(dlsc_ctx* c) { return c ? c->S.rec : nullptr; }
 int dlsc_record_floats(const dlsc_ctx* c) { return c ? c->P.rec : 0; }
 int dlsc_bind_records(dlsc_ctx* c, float* p) {
     if (!c || !p) return fail("dlsc_bind_records: null argument");
-    if (c->p2p.exported) return fail("dlsc_bind_records: records live in the peer-memory block (dlsc_p2p_export)");
+    if (c->p2p.on) return fail("dlsc_bind_records: records live in the connected peer-memory block (dlsc_p2p_connect)");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(p, c->S.rec, (size_t)c->P.N * c->P.rec * sizeof(float), cudaMemcpyDeviceToDevice));

@@ -5,6 +5,8 @@ record (state, goal, previous trajectory) into every other agent (src/multi_sync
 Sharded over GPUs that copy becomes one all-gather per replan step of the fixed-size records
 (include/dlsc_b200.h "Records"): NCCL on device memory in production, gloo on host memory in the CPU tests.
 """
+import os
+
 import numpy as np
 
 
@@ -36,10 +38,30 @@ class RecordExchange:
         self.device = device
         self.mode = "host" if device is None else mode
         if device is not None and mode == "p2p" and self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, planner.p2p_export())
-            planner.p2p_connect(self.world, self.rank, handles)
-            return
+            # every rank must end up in the same mode: agree on success after each phase, else fall back to NCCL
+            def all_ok(ok):
+                t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                return bool(t.item())
+            handle, err = None, None
+            try:
+                handle = planner.p2p_export()
+            except Exception as e:                       # e.g. IPC not permitted in this container
+                err = e
+            if all_ok(handle is not None):
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle)
+                try:
+                    if os.environ.get("DLSC_P2P_FORCE_FAIL") == str(self.rank):      # test hook for the fallback path
+                        raise RuntimeError("forced failure (DLSC_P2P_FORCE_FAIL)")
+                    planner.p2p_connect(self.world, self.rank, handles)
+                except Exception as e:
+                    err = e
+                if all_ok(err is None):
+                    return
+                planner.p2p_disconnect()
+            self.fallback_reason = repr(err) if err is not None else "a peer could not set up peer-memory access"
+            mode = "nccl"
         if device is not None and self.world == 1:
             self.mode = "single"
             return
