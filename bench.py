@@ -447,7 +447,7 @@ def run_ours(args):
         }
         hbm = peaks.get("hbm_gbs") or 6650.0
         ncell = int(edt[2][0]) * int(edt[2][1]) * int(edt[2][2])
-        out["edt_build"] = {"kernels": "k_edt_pass_z/y/x", "ms": edt_ms, "cells": ncell, "bound": "hbm",
+        out["edt_build"] = {"kernels": "k_edt_pass_z_cols + k_edt_col_any/window + k_edt_pass_y/x", "ms": edt_ms, "cells": ncell, "bound": "hbm",
                             "achieved": 17.0 * ncell / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else None, "peak": hbm, "unit": "GB/s",
                             "frac": 17.0 * ncell / (edt_ms * 1e-3) / 1e9 / hbm if edt_ms > 0 else None,
                             "algorithmic": "once per mission: 1 B occupancy in + 16 B record out per cell"}

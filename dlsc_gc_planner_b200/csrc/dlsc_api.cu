@@ -342,23 +342,25 @@ static int edt_from_occupancy_dev(dlsc_ctx* c, const uint8_t* d_occ, const int32
     const double res = c->hp.world_res;
     const int maxd = (int)(maxdist / res + 1);          // DynamicEDTOctomap: maxdist in cells
     uint32_t *ta = nullptr, *tb = nullptr;
+    uint8_t* tcol = nullptr;
     CK(cudaMalloc(&ta, nc * sizeof(uint32_t)));
     CK(cudaMalloc(&tb, nc * sizeof(uint32_t)));
+    CK(cudaMalloc(&tcol, 3 * (size_t)dims[0] * dims[1]));
     if (c->edt_cells) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->edt_cells); c->edt_cells = nullptr; }
     CK(cudaMalloc(&c->edt_cells, nc * sizeof(int4)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
-    const int nl = launch_edt_build(d_occ, ta, tb, c->edt_cells, dims, res, maxd, c->stream);
+    const int nl = launch_edt_build(d_occ, ta, tb, tcol, c->edt_cells, dims, res, maxd, c->stream);
     CK(cudaEventRecord(e1, c->stream));
-    if (nl < 0) { cudaFree(ta); cudaFree(tb); return fail("dlsc_build_edt: maxdist / resolution + 1 must be in [1, 16] cells"); }
+    if (nl < 0) { cudaFree(ta); cudaFree(tb); cudaFree(tcol); return fail("dlsc_build_edt: maxdist / resolution + 1 must be in [1, 16] cells"); }
     c->launches += nl;
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     c->edt_build_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(ta); cudaFree(tb);
+    cudaFree(ta); cudaFree(tb); cudaFree(tcol);
     return finish_edt(c, dims, mk, res);
 }
 

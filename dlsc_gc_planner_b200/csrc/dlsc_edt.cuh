@@ -41,18 +41,31 @@ DLSC_HD uint32_t edt_pass_z_cell(const uint8_t* occ, size_t i, int nz, int R) {
 }
 
 // pass y: d2 (10 bits) | (yy - y + R) << 10 (5 bits) | fz << 15
+// Taps are visited outwards from the cell (0, -1, +1, -2, +2, ...) and the scan stops once k^2 exceeds the best
+// distance found: a tap k cells away cannot do better, and can only tie while k^2 <= best (ties go to the lower
+// index, as an ascending scan with a strict "<" would decide them).
 DLSC_HD uint32_t edt_pass_y_cell(const uint32_t* in, size_t i, int ny, int nz, int R) {
     const int y = (int)((i / (size_t)nz) % (size_t)ny);
-    unsigned best = kEdtNone, boff = 0, bfz = 0;
-    const int lo = y - R > 0 ? y - R : 0, hi = y + R < ny - 1 ? y + R : ny - 1;
-    for (int yy = lo; yy <= hi; yy++) {
-        const uint32_t v = in[(ptrdiff_t)i + (ptrdiff_t)(yy - y) * nz];
-        const unsigned d1 = v & 1023u;
-        if (d1 == kEdtNone) continue;
-        const unsigned dd = d1 + (unsigned)((yy - y) * (yy - y));
-        if (dd < best) { best = dd; boff = (unsigned)(yy - y + R); bfz = v >> 10; }   // ascending yy: ties keep the lower index
+    unsigned best = kEdtNone, bfz = 0;
+    int byy = 0;
+    {
+        const uint32_t v = in[i];
+        if ((v & 1023u) != kEdtNone) { best = v & 1023u; byy = y; bfz = v >> 10; }
     }
-    return best | (boff << 10) | (bfz << 15);
+    for (int k = 1; k <= R && (unsigned)(k * k) <= best; k++) {
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const int yy = y + sgn * k;
+            if (yy < 0 || yy >= ny) continue;
+            const uint32_t v = in[(ptrdiff_t)i + (ptrdiff_t)(sgn * k) * nz];
+            const unsigned d1 = v & 1023u;
+            if (d1 == kEdtNone) continue;
+            const unsigned dd = d1 + (unsigned)(k * k);
+            if (dd < best || (dd == best && yy < byy)) { best = dd; byy = yy; bfz = v >> 10; }
+        }
+    }
+    if (best == kEdtNone) return kEdtNone;
+    return best | ((unsigned)(byy - y + R) << 10) | (bfz << 15);
 }
 
 // pass x: the record {dist bits, fx, fy, fz}; ties again to the lower x, i.e. the lowest linear cell index overall
@@ -63,18 +76,29 @@ DLSC_HD EdtRecord edt_pass_x_cell(const uint32_t* in, size_t i, int nx, int ny, 
     const int x = (int)(i / plane);
     const int y = (int)((i / (size_t)nz) % (size_t)ny);
     unsigned best = 0x7fffffffu;
-    int bx = -1, by = -1, bz = -1;
-    const int lo = x - R > 0 ? x - R : 0, hi = x + R < nx - 1 ? x + R : nx - 1;
-    for (int xx = lo; xx <= hi; xx++) {
-        const uint32_t v = in[(ptrdiff_t)i + (ptrdiff_t)(xx - x) * (ptrdiff_t)plane];
-        const unsigned d2 = v & 1023u;
-        if (d2 == kEdtNone) continue;
-        const unsigned dd = d2 + (unsigned)((xx - x) * (xx - x));
-        if (dd < best) { best = dd; bx = xx; by = y + (int)((v >> 10) & 31u) - R; bz = (int)(v >> 15); }
+    int bx = -1;
+    uint32_t bv = 0;
+    {
+        const uint32_t v = in[i];
+        if ((v & 1023u) != kEdtNone) { best = v & 1023u; bx = x; bv = v; }
+    }
+    for (int k = 1; k <= R && (unsigned)(k * k) <= best; k++) {
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const int xx = x + sgn * k;
+            if (xx < 0 || xx >= nx) continue;
+            const uint32_t v = in[(ptrdiff_t)i + (ptrdiff_t)(sgn * k) * (ptrdiff_t)plane];
+            const unsigned d2 = v & 1023u;
+            if (d2 == kEdtNone) continue;
+            const unsigned dd = d2 + (unsigned)(k * k);
+            if (dd < best || (dd == best && xx < bx)) { best = dd; bx = xx; bv = v; }
+        }
     }
     EdtRecord r;
     float d = cap;
-    if (bx >= 0 && best < (unsigned)maxd2) d = tab.v[best]; else bx = by = bz = -1;
+    int by = -1, bz = -1;
+    if (bx >= 0 && best < (unsigned)maxd2) { d = tab.v[best]; by = y + (int)((bv >> 10) & 31u) - R; bz = (int)(bv >> 15); }
+    else bx = -1;
     uint32_t u; memcpy(&u, &d, 4);
     r.x = (int)u; r.y = bx; r.z = by; r.w = bz;
     return r;

@@ -57,8 +57,8 @@ void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream
 void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st);
 // dlsc_kernels_edt.cu: occupancy raster of CSV boxes and the exact capped EDT with nearest-obstacle index
 void launch_edt_raster(const float* boxes_dev, int nb, double res, const int dims[3], const int min_key[3], uint8_t* occ, cudaStream_t st);
-int launch_edt_build(const uint8_t* occ, uint32_t* tmp_a, uint32_t* tmp_b, int4* cells, const int dims[3], double res, int maxd,
-                     cudaStream_t st);   // returns the number of launches, < 0: unsupported window
+int launch_edt_build(const uint8_t* occ, uint32_t* tmp_a, uint32_t* tmp_b, uint8_t* tmp_col, int4* cells, const int dims[3], double res,
+                     int maxd, cudaStream_t st);   // returns the number of launches, < 0: unsupported window
 void launch_edt_unpack(const int4* cells, float* dist, int32_t* obst, size_t ncell, cudaStream_t st);
 void launch_edt_mask(const EdtDev& E, double margin, uint8_t* mask, int* unsafe, cudaStream_t st);
 void launch_sat_build(const EdtDev& E, int32_t* sat, cudaStream_t st);   // 4 launches
