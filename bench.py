@@ -11,7 +11,8 @@ timed steps are in-transit replans (non-trivial LSC / SFC / QP active sets), and
 the whole run are recorded by an untimed pilot rollout (the waypoint provider is host-side and out of the
 hot path's scope).  The path is deterministic, so the timed replays see exactly the pilot's states.
 
-  value : agents * K / t, inputs resident in HBM (device-chained plan -> advance [-> NCCL all-gather]),
+  value : agents * K / t, inputs resident in HBM (device-chained plan -> advance [-> record exchange over NVLink peer memory,
+          or NCCL all-gather with --exchange nccl]),
           timed with CUDA events on the launching stream, max over ranks.
   e2e   : same metric through the host-facing C-ABI calls with HOST buffers: every step uploads pos / vel /
           acc / waypoint of every agent from pinned memory (dlsc_set_agents), runs dlsc_step and reads every

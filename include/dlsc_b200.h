@@ -54,8 +54,10 @@ typedef struct dlsc_params {
     double reset_threshold; /* plan/reset_threshold                                        */
     int32_t qp_max_iter;    /* interior-point iteration cap (0 -> 80)                      */
     int32_t qp_solver;      /* 0: dual active set, interior-point fallback (default); 1: interior point only */
-    double qp_screen_slack; /* LSC working-set screen: rows with initial slack below this [m] enter the
-                               first solve (0 -> 0.5; < 0 -> all rows).  Exact: see dlsc_qp.cuh.           */
+    double qp_screen_slack; /* LSC row screens (exact, see dlsc_qp_gi.cuh / dlsc_qp.cuh).  0 -> default (0.5);
+                               > 0: the active set skips rows whose slack at the initial trajectory exceeds the
+                               iterate's deviation from it, and the interior-point fallback starts from the rows
+                               with slack below this value [m]; < 0: every row is evaluated in every scan.  */
 } dlsc_params;
 
 /* per-agent status bits (dlsc_get_status) */
