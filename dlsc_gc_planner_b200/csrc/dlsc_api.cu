@@ -642,11 +642,10 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
     return run_stages_impl(c, mask, c->P, c->S);
 }
 
-int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
-    if (!c) return fail("null ctx");
-    if (first < 0 || count < 1 || first + count > c->P.NL) return fail("dlsc_run_stages_subset: bad range");
-    DevParams P = c->P;
-    DevState S = c->S;
+// view of the local agents [first, first + count): every per-agent array offset, P.begin / P.NL adjusted
+static void make_view(const dlsc_ctx* c, int first, int count, DevParams& P, DevState& S) {
+    P = c->P;
+    S = c->S;
     const size_t f = (size_t)first, K = P.K, M = P.M, npt = (size_t)P.M * kP;
     P.begin += first; P.NL = count;
     S.acc += f * 3; S.waypoint += f * 3; S.goal_new += f * 3; S.disturbed += f; S.sfc_init += f;
@@ -655,6 +654,15 @@ int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
     S.lsc_normal += f * K * M * 3; S.lsc_d += f * K * M * kP; S.lsc_anchor_last += f * K * 3; S.lsc_near += f * K * M;
     S.sfc += f * M * 6; S.traj += f * npt * 3; S.qp_x += f * (size_t)P.D * npt;
     S.cost += f; S.viol += f; S.qp_iters += f; S.status += f;
+    S.qp_list += f; S.qp_list_gi += f; S.qp_seed += f * 4;
+}
+
+int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
+    if (!c) return fail("null ctx");
+    if (first < 0 || count < 1 || first + count > c->P.NL) return fail("dlsc_run_stages_subset: bad range");
+    DevParams P;
+    DevState S;
+    make_view(c, first, count, P, S);
     return run_stages_impl(c, mask, P, S);
 }
 

@@ -48,7 +48,7 @@ struct DevState {
 struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; size_t fast_smem; };
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
-int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st);   // returns the number of launches
+int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, int parts = 3);   // 1: grid build, 2: search; returns launches
 void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st);
@@ -72,6 +72,6 @@ void launch_p2p_wait(const unsigned long long* flags, int world, unsigned long l
 
 double measure_fp64_peak(int device, cudaStream_t st);
 QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device);
-int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);
+int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLaunch& L, cudaStream_t st);   // S.qp_next / lists / scratch of this view
 
 }  // namespace dlsc

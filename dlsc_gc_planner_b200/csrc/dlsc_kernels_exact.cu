@@ -241,24 +241,30 @@ __global__ void __launch_bounds__(kNbrSearchWarps * 32) k_nbr_search(const __gri
     }
 }
 
-// returns the number of kernels launched
-int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st) {
+// parts: 1 = build the grid (once per step, all agents), 2 = search for the local agents of (P, S), 3 = both.
+// Returns the number of kernels launched.
+static bool nbr_grid_setup(const DevParams& P, const DevState& S, NbrGrid& G) {
     static const bool no_grid = [] { const char* e = getenv("DLSC_NBR_GRID"); return e && e[0] == '0'; }();
-    if (P.comm_range > 0 && S.nbr_cell_start && !no_grid) {
-        NbrGrid G;
-        // cell size a little above the range: the test is made on float differences, which can accept a pair whose
-        // exact distance exceeds the range by one float ulp
-        const double h = P.comm_range * (1.0 + 1e-5);
-        G.x0 = P.world_min[0]; G.y0 = P.world_min[1]; G.inv_h = 1.0 / h;
-        G.gx = (int)floor((P.world_max[0] - P.world_min[0]) * G.inv_h) + 1;
-        G.gy = (int)floor((P.world_max[1] - P.world_min[1]) * G.inv_h) + 1;
-        if (G.gx >= 1 && G.gy >= 1 && (long long)G.gx * G.gy <= kNbrMaxCells) {
-            G.cell_start = S.nbr_cell_start; G.sorted = S.nbr_sorted; G.pos = S.nbr_sorted_pos;
-            k_nbr_bin<<<1, kNbrBinThreads, 0, st>>>(P, S.rec, G);
-            k_nbr_search<<<(P.NL + kNbrSearchWarps - 1) / kNbrSearchWarps, kNbrSearchWarps * 32, 0, st>>>(P, S, G);
-            return 2;
-        }
+    if (!(P.comm_range > 0) || !S.nbr_cell_start || no_grid) return false;
+    // cell size a little above the range: the test is made on float differences, which can accept a pair whose
+    // exact distance exceeds the range by one float ulp
+    const double h = P.comm_range * (1.0 + 1e-5);
+    G.x0 = P.world_min[0]; G.y0 = P.world_min[1]; G.inv_h = 1.0 / h;
+    G.gx = (int)floor((P.world_max[0] - P.world_min[0]) * G.inv_h) + 1;
+    G.gy = (int)floor((P.world_max[1] - P.world_min[1]) * G.inv_h) + 1;
+    if (!(G.gx >= 1 && G.gy >= 1 && (long long)G.gx * G.gy <= kNbrMaxCells)) return false;
+    G.cell_start = S.nbr_cell_start; G.sorted = S.nbr_sorted; G.pos = S.nbr_sorted_pos;
+    return true;
+}
+int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, int parts) {
+    NbrGrid G;
+    if (nbr_grid_setup(P, S, G)) {
+        int n = 0;
+        if (parts & 1) { k_nbr_bin<<<1, kNbrBinThreads, 0, st>>>(P, S.rec, G); n++; }
+        if (parts & 2) { k_nbr_search<<<(P.NL + kNbrSearchWarps - 1) / kNbrSearchWarps, kNbrSearchWarps * 32, 0, st>>>(P, S, G); n++; }
+        return n;
     }
+    if (!(parts & 2)) return 0;
     k_neighbours<<<(P.NL + kNbrWarps - 1) / kNbrWarps, kNbrTile, 0, st>>>(P, S);
     return 1;
 }
