@@ -326,7 +326,7 @@ void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
 // a box test are spread over the lanes (one 16-byte load of the vertex mask = 16 vertices) and combined with
 // a warp vote.  4096 agents = 4096 warps: the whole swarm is resident in one wave.
 #ifndef DLSC_SFC_MINB
-#define DLSC_SFC_MINB 8
+#define DLSC_SFC_MINB 7
 #endif
 constexpr int kSfcWarps = 4;
 __global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {

@@ -49,7 +49,7 @@ constexpr int kFastWarps = 4;
 #endif
 constexpr int kGiHeavyRows = DLSC_GI_HEAVY_ROWS;
 #ifndef DLSC_FAST_MINB
-#define DLSC_FAST_MINB 8
+#define DLSC_FAST_MINB 7
 #endif
 __global__ void __launch_bounds__(kFastWarps * 32, DLSC_FAST_MINB) k_qp_fast(const __grid_constant__ DevParams P,
                                                                              const __grid_constant__ DevState S,
