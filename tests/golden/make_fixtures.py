@@ -5,6 +5,7 @@ container, where /root/reference exists; the GPU box and the tests never read /r
                     agent properties, world box, obstacle boxes)           <- missions/*.json, world/*.csv
   golden_log.npz    the first rows of the reference's only recorded run     <- log/result_...csv
   result_head.csv   the same rows verbatim (header + 3 rows: `head -4`)       <- log/result_...csv
+  golden_log_full.npz  every row of that log (t, pos/vel/acc of the 10 agents)   <- log/result_...csv
                     (maze10_dense #1, 2-D, M=10, CPLEX path): per agent pos/vel/acc at t = 0, 0.1, 0.2
   gjk_ref.npz       known-answer vectors of the reference's own openGJK object code (oracle/_ref):
                     hull point sets -> witness vector, distance, simplex size
@@ -49,6 +50,9 @@ def main():
     rows = [l.strip().split(",") for l in open(f"{REF}/log/result_1742185870.978562_DLSCGC_10agents.csv")][1:4]
     log = np.array(rows, dtype=np.float64).reshape(3, 10, 12)
     np.savez_compressed(os.path.join(OUT, "golden_log.npz"), t=log[:, 0, 1], state=log[:, :, 2:11])
+    full = [l.strip().split(",") for l in open(f"{REF}/log/result_1742185870.978562_DLSCGC_10agents.csv")][1:]
+    full = np.array(full, dtype=np.float64).reshape(len(full), 10, 12)
+    np.savez_compressed(os.path.join(OUT, "golden_log_full.npz"), t=full[:, 0, 1], state=full[:, :, 2:11])     # all 342 rows
     with open(f"{REF}/log/result_1742185870.978562_DLSCGC_10agents.csv") as f, open(os.path.join(OUT, "result_head.csv"), "w") as o:
         for _ in range(4):
             o.write(f.readline())
