@@ -275,9 +275,12 @@ int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, in
 // are one dependent hop away; then thread per item, all GJK items (neighbour x segments 0..M-2, warps
 // homogeneous: similar geometry, similar GJK depth) before the last-segment items (segment-segment closest points,
 // a different code path).
-constexpr int kLscThreads = 128;
+#ifndef DLSC_LSC_THREADS
+#define DLSC_LSC_THREADS 64
+#endif
+constexpr int kLscThreads = DLSC_LSC_THREADS;
 #ifndef DLSC_LSC_MINB
-#define DLSC_LSC_MINB 4
+#define DLSC_LSC_MINB 8
 #endif
 __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float s_init[kMaxPts * 3];
