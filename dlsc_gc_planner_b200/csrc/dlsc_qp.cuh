@@ -47,6 +47,11 @@ struct Cta {
         if (warp) __syncwarp(); else __syncthreads();
 #endif
     }
+    DLSC_HD void wsync() const {      // threads of one warp only
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+    }
     // op: 0 sum, 1 max, 2 min.  Deterministic (fixed tree).  All threads get the result.
     DLSC_HD void reduce3(double& a, int opa, double& b, int opb, double& c, int opc) const {
 #ifdef __CUDA_ARCH__

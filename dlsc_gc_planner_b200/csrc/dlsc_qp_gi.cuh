@@ -313,86 +313,111 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             c.tick(9);
         }
         iters++;
-        // ---- small dense step (thread 0): r, step lengths, active-set update; t_y = A' r into sm.ax1[0..ny) ----
-        if (c.tid == 0) {
-            const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
-            double apw = 0.0;
-            for (int t = 0; t < 9; t++) if (yi[t] >= 0) apw += yc[t] * sm.dy[yi[t]];
-            double ll = 0.0;
-            for (int j = 0; j < q; j++) {
+        // ---- small dense step (first warp): r, step lengths, active-set update; t_y = A' r into sm.ax1[0..ny) ----
+        // The q x q algebra stays with lane 0; the two gather loops over the rows' y-space terms (v = A w before it,
+        // t_y = A' r after it) are spread over the lanes.  Every sum keeps the serial order of its terms, so the result
+        // is bit-identical to a single-thread evaluation (the host simulator runs this with one "lane").
+        const int W = c.nthr < 32 ? c.nthr : 32;
+        if (c.tid < W) {
+            for (int j = c.tid; j < q; j += W) {
                 double vj = 0.0;
                 for (int t = 0; t < 9; t++) { const int jj = g.yi[9 * j + t]; if (jj >= 0) vj += g.yc[9 * j + t] * sm.dy[jj]; }
                 g.v[j] = vj;
-                double a = vj;
-                for (int k = 0; k < j; k++) a -= g.Ls[j * (j + 1) / 2 + k] * g.l[k];
-                a /= g.Ls[j * (j + 1) / 2 + j];
-                g.l[j] = a; ll += a * a;
             }
-            for (int j = q - 1; j >= 0; j--) {
-                double a = g.l[j];
-                for (int k = j + 1; k < q; k++) a -= g.Ls[k * (k + 1) / 2 + j] * g.r[k];
-                g.r[j] = a / g.Ls[j * (j + 1) / 2 + j];
+            c.wsync();
+            const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+            if (c.tid == 0) {
+                double apw = 0.0;
+                for (int t = 0; t < 9; t++) if (yi[t] >= 0) apw += yc[t] * sm.dy[yi[t]];
+                double ll = 0.0;
+                for (int j = 0; j < q; j++) {
+                    double a = g.v[j];
+                    for (int k = 0; k < j; k++) a -= g.Ls[j * (j + 1) / 2 + k] * g.l[k];
+                    a /= g.Ls[j * (j + 1) / 2 + j];
+                    g.l[j] = a; ll += a * a;
+                }
+                for (int j = q - 1; j >= 0; j--) {
+                    double a = g.l[j];
+                    for (int k = j + 1; k < q; k++) a -= g.Ls[k * (k + 1) / 2 + j] * g.r[k];
+                    g.r[j] = a / g.Ls[j * (j + 1) / 2 + j];
+                }
+                const double zn = apw - ll;
+                double t1 = 1e300; int kdrop = -1;
+                for (int j = 0; j < q; j++)
+                    if (g.r[j] > 0) { const double tt = g.u[j] / g.r[j]; if (tt < t1) { t1 = tt; kdrop = j; } }
+                const bool dependent = !(zn > 1e-12 * (apw > 1e-300 ? apw : 1e-300));
+                const double t2 = dependent ? 1e300 : viol_p / zn;
+                const double t = t1 < t2 ? t1 : t2;
+                const bool finite = (t < 1e299);
+                if (finite) for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
+                g.ty[0] = dependent ? 0.0 : t;
+                g.ty[2] = zn;
+                g.ty[3] = finite ? 1.0 : 0.0;
+                g.ty[4] = (t2 <= t1) ? 1.0 : 0.0;          // add the candidate (else drop row kdrop)
+                g.ty[5] = (double)kdrop;
+                g.ty[6] = apw;
+                g.ty[7] = t;
             }
-            const double zn = apw - ll;
-            double t1 = 1e300; int kdrop = -1;
-            for (int j = 0; j < q; j++)
-                if (g.r[j] > 0) { const double tt = g.u[j] / g.r[j]; if (tt < t1) { t1 = tt; kdrop = j; } }
-            const bool dependent = !(zn > 1e-12 * (apw > 1e-300 ? apw : 1e-300));
-            const double t2 = dependent ? 1e300 : viol_p / zn;
-            const double t = t1 < t2 ? t1 : t2;
-            double flag;             // 0: full step, new scan | 1: partial, same p | 2: infeasible | 3: give up
-            if (!(t < 1e299)) flag = 2.0;
-            else {
-                for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
-                u_p += t;
-                if (q > 0) {                 // t_y = A' r, only read by the y update when q > 0
-                    for (int e = 0; e < ny; e++) sm.ax1[e] = 0.0;
+            c.wsync();
+            const bool finite = (g.ty[3] != 0.0);
+            if (finite && q > 0) {                          // t_y = A' r, only read by the y update when q > 0
+                for (int e = c.tid; e < ny; e += W) {
+                    double acc = 0.0;
                     for (int j = 0; j < q; j++)
-                        for (int tt = 0; tt < 9; tt++) { const int jj = g.yi[9 * j + tt]; if (jj >= 0) sm.ax1[jj] += g.r[j] * g.yc[9 * j + tt]; }
-                }
-                if (t2 <= t1) {
-                    if (q == kGiQ) flag = 3.0;
-                    else {
-                        for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
-                        g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
-                        for (int tt = 0; tt < 9; tt++) { g.yc[9 * q + tt] = yc[tt]; g.yi[9 * q + tt] = yi[tt]; }
-                        g.bq[q] = g.bq[kGiQ]; g.id[q] = g.id[kGiQ]; g.u[q] = u_p;
-                        flag = 0.0;
-                    }
-                } else {
-                    for (int j = kdrop; j < q - 1; j++) {
-                        for (int tt = 0; tt < 9; tt++) { g.yc[9 * j + tt] = g.yc[9 * (j + 1) + tt]; g.yi[9 * j + tt] = g.yi[9 * (j + 1) + tt]; }
-                        g.bq[j] = g.bq[j + 1]; g.id[j] = g.id[j + 1]; g.u[j] = g.u[j + 1];
-                    }
-                    for (int i2 = 0, ii = 0; i2 < q; i2++) {
-                        if (i2 == kdrop) continue;
-                        for (int k2 = 0, kk = 0; k2 <= i2; k2++) {
-                            if (k2 == kdrop) continue;
-                            g.Ls[ii * (ii + 1) / 2 + kk] = g.Sm[i2 * (i2 + 1) / 2 + k2];
-                            kk++;
-                        }
-                        ii++;
-                    }
-                    for (int e = 0; e < (q - 1) * q / 2; e++) g.Sm[e] = g.Ls[e];
-                    bool okf = true;
-                    for (int j = 0; j < q - 1 && okf; j++) {
-                        double dj = g.Sm[j * (j + 1) / 2 + j];
-                        for (int k = 0; k < j; k++) dj -= g.Ls[j * (j + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
-                        if (!(dj > 0)) { okf = false; break; }
-                        dj = sqrt(dj);
-                        g.Ls[j * (j + 1) / 2 + j] = dj;
-                        for (int i2 = j + 1; i2 < q - 1; i2++) {
-                            double a = g.Sm[i2 * (i2 + 1) / 2 + j];
-                            for (int k = 0; k < j; k++) a -= g.Ls[i2 * (i2 + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
-                            g.Ls[i2 * (i2 + 1) / 2 + j] = a / dj;
-                        }
-                    }
-                    flag = okf ? 1.0 : 3.0;
+                        for (int tt = 0; tt < 9; tt++) if (g.yi[9 * j + tt] == e) acc += g.r[j] * g.yc[9 * j + tt];
+                    sm.ax1[e] = acc;
                 }
             }
-            g.ty[0] = dependent ? 0.0 : t;
-            g.ty[1] = flag;
-            g.ty[2] = zn;
+            c.wsync();
+            if (c.tid == 0) {
+                double flag;             // 0: full step, new scan | 1: partial, same p | 2: infeasible | 3: give up
+                if (!finite) flag = 2.0;
+                else {
+                    const double zn = g.ty[2], apw = g.ty[6];
+                    const int kdrop = (int)g.ty[5];
+                    u_p += g.ty[7];
+                    if (g.ty[4] != 0.0) {
+                        if (q == kGiQ) flag = 3.0;
+                        else {
+                            for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
+                            g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
+                            for (int tt = 0; tt < 9; tt++) { g.yc[9 * q + tt] = yc[tt]; g.yi[9 * q + tt] = yi[tt]; }
+                            g.bq[q] = g.bq[kGiQ]; g.id[q] = g.id[kGiQ]; g.u[q] = u_p;
+                            flag = 0.0;
+                        }
+                    } else {
+                        for (int j = kdrop; j < q - 1; j++) {
+                            for (int tt = 0; tt < 9; tt++) { g.yc[9 * j + tt] = g.yc[9 * (j + 1) + tt]; g.yi[9 * j + tt] = g.yi[9 * (j + 1) + tt]; }
+                            g.bq[j] = g.bq[j + 1]; g.id[j] = g.id[j + 1]; g.u[j] = g.u[j + 1];
+                        }
+                        for (int i2 = 0, ii = 0; i2 < q; i2++) {
+                            if (i2 == kdrop) continue;
+                            for (int k2 = 0, kk = 0; k2 <= i2; k2++) {
+                                if (k2 == kdrop) continue;
+                                g.Ls[ii * (ii + 1) / 2 + kk] = g.Sm[i2 * (i2 + 1) / 2 + k2];
+                                kk++;
+                            }
+                            ii++;
+                        }
+                        for (int e = 0; e < (q - 1) * q / 2; e++) g.Sm[e] = g.Ls[e];
+                        bool okf = true;
+                        for (int j = 0; j < q - 1 && okf; j++) {
+                            double dj = g.Sm[j * (j + 1) / 2 + j];
+                            for (int k = 0; k < j; k++) dj -= g.Ls[j * (j + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
+                            if (!(dj > 0)) { okf = false; break; }
+                            dj = sqrt(dj);
+                            g.Ls[j * (j + 1) / 2 + j] = dj;
+                            for (int i2 = j + 1; i2 < q - 1; i2++) {
+                                double a = g.Sm[i2 * (i2 + 1) / 2 + j];
+                                for (int k = 0; k < j; k++) a -= g.Ls[i2 * (i2 + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
+                                g.Ls[i2 * (i2 + 1) / 2 + j] = a / dj;
+                            }
+                        }
+                        flag = okf ? 1.0 : 3.0;
+                    }
+                }
+                g.ty[1] = flag;
+            }
         }
         c.sync();
         c.tick(10);
