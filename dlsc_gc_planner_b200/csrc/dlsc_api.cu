@@ -205,6 +205,8 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.rec, N * P.rec);
     c->rec_owned = true;
     rc |= dev_alloc(c, &S.acc, NL * 3);
+    rc |= dev_alloc(c, &S.stage_pos, (size_t)NL * 3);
+    rc |= dev_alloc(c, &S.stage_vel, (size_t)NL * 3);
     rc |= dev_alloc(c, &S.waypoint, NL * 3);
     rc |= dev_alloc(c, &S.goal_new, NL * 3);
     rc |= dev_alloc(c, &S.disturbed, NL);
@@ -507,10 +509,12 @@ int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
     if (!c || !a) return fail("dlsc_set_agents: null argument");
     CK(cudaSetDevice(c->device));
     const DevParams& P = c->P;
-    float* rec0 = c->S.rec + (size_t)P.begin * P.rec + c->rl.pos;
-    const size_t pitch = (size_t)P.rec * sizeof(float);
-    if (a->pos) CK(cudaMemcpy2DAsync(rec0, pitch, a->pos, 12, 12, P.NL, cudaMemcpyHostToDevice, c->stream));
-    if (a->vel) CK(cudaMemcpy2DAsync(rec0 + 3, pitch, a->vel, 12, 12, P.NL, cudaMemcpyHostToDevice, c->stream));
+    if (a->pos) CK(cudaMemcpyAsync(c->S.stage_pos, a->pos, (size_t)P.NL * 12, cudaMemcpyHostToDevice, c->stream));
+    if (a->vel) CK(cudaMemcpyAsync(c->S.stage_vel, a->vel, (size_t)P.NL * 12, cudaMemcpyHostToDevice, c->stream));
+    if (a->pos || a->vel) {
+        launch_set_state(P, c->S.rec, a->pos ? c->S.stage_pos : nullptr, a->vel ? c->S.stage_vel : nullptr, c->stream);
+        c->launches++;
+    }
     if (a->acc) CK(cudaMemcpyAsync(c->S.acc, a->acc, (size_t)P.NL * 12, cudaMemcpyHostToDevice, c->stream));
     if (a->waypoint) CK(cudaMemcpyAsync(c->S.waypoint, a->waypoint, (size_t)P.NL * 12, cudaMemcpyHostToDevice, c->stream));
     if (a->disturbed) CK(cudaMemcpyAsync(c->S.disturbed, a->disturbed, (size_t)P.NL, cudaMemcpyHostToDevice, c->stream));
@@ -765,9 +769,12 @@ int dlsc_get_state(dlsc_ctx* c, float* pos, float* vel, float* acc) {
     if (!c) return fail("null ctx");
     CK(cudaSetDevice(c->device));
     const DevParams& P = c->P;
-    const float* rec0 = c->S.rec + (size_t)P.begin * P.rec + c->rl.pos;
-    if (pos) CK(cudaMemcpy2DAsync(pos, 12, rec0, (size_t)P.rec * 4, 12, P.NL, cudaMemcpyDeviceToHost, c->stream));
-    if (vel) CK(cudaMemcpy2DAsync(vel, 12, rec0 + 3, (size_t)P.rec * 4, 12, P.NL, cudaMemcpyDeviceToHost, c->stream));
+    if (pos || vel) {      // gather out of the 768-byte records on the device, then dense copies
+        launch_get_state(P, c->S.rec, c->S.stage_pos, c->S.stage_vel, c->stream);
+        c->launches++;
+    }
+    if (pos) CK(cudaMemcpyAsync(pos, c->S.stage_pos, (size_t)P.NL * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (vel) CK(cudaMemcpyAsync(vel, c->S.stage_vel, (size_t)P.NL * 12, cudaMemcpyDeviceToHost, c->stream));
     if (acc) CK(cudaMemcpyAsync(acc, c->S.acc, (size_t)P.NL * 12, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;

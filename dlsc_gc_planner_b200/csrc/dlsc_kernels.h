@@ -14,6 +14,7 @@ namespace dlsc {
 struct DevState {
     float* rec;                // [N][rec]  (all agents)
     float* acc;                // [NL][3]
+    float *stage_pos, *stage_vel;   // [NL][3] staging of dlsc_set_agents
     float* waypoint;           // [NL][3]
     float* goal_new;           // [NL][3] current_goal_point after this step's goal stage (committed to the
                                //         records by dlsc_advance / dlsc_publish_records)
@@ -63,6 +64,8 @@ void launch_edt_unpack(const int4* cells, float* dist, int32_t* obst, size_t nce
 void launch_edt_mask(const EdtDev& E, double margin, uint8_t* mask, int* unsafe, cudaStream_t st);
 void launch_sat_build(const EdtDev& E, int32_t* sat, cudaStream_t st);   // 4 launches
 void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);
+void launch_set_state(const DevParams& P, float* rec, const float* pos, const float* vel, cudaStream_t st);   // pos / vel [NL][3] device, or null
+void launch_get_state(const DevParams& P, const float* rec, float* pos, float* vel, cudaStream_t st);         // records -> dense pos / vel
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
 
 constexpr int kP2PMaxWorld = 16;

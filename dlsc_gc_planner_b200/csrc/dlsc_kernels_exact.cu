@@ -532,6 +532,35 @@ void launch_reset(const DevParams& P, const DevState& S, const float* start_dev,
 }
 
 // ------------------------------------------------------------------------------------------------
+// dlsc_set_agents: positions / velocities arrive as dense [NL][3] arrays (one contiguous H2D copy each into a
+// staging buffer) and are scattered into the 768-byte records here -- a strided 2-D copy would cost the DMA engine one
+// 12-byte transaction per agent.
+__global__ void k_set_state(const __grid_constant__ DevParams P, float* __restrict__ rec, const float* __restrict__ pos,
+                            const float* __restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.NL * 3) return;
+    const int la = i / 3, k = i - la * 3;
+    float* r = rec + (size_t)(P.begin + la) * P.rec + P.M * kP * 3;
+    if (pos) r[k] = pos[i];
+    if (vel) r[3 + k] = vel[i];
+}
+__global__ void k_get_state(const __grid_constant__ DevParams P, const float* __restrict__ rec, float* __restrict__ pos,
+                            float* __restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.NL * 3) return;
+    const int la = i / 3, k = i - la * 3;
+    const float* r = rec + (size_t)(P.begin + la) * P.rec + P.M * kP * 3;
+    pos[i] = r[k];
+    vel[i] = r[3 + k];
+}
+void launch_get_state(const DevParams& P, const float* rec, float* pos, float* vel, cudaStream_t st) {
+    k_get_state<<<(P.NL * 3 + 255) / 256, 256, 0, st>>>(P, rec, pos, vel);
+}
+void launch_set_state(const DevParams& P, float* rec, const float* pos, const float* vel, cudaStream_t st) {
+    k_set_state<<<(P.NL * 3 + 255) / 256, 256, 0, st>>>(P, rec, pos, vel);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Record exchange over NVLink peer memory (one process per GPU, dlsc_p2p_*): the all-gather of the agent records as
 // direct stores.  k_p2p_push copies this rank's slice of the records into the *next* record buffer of every rank
 // (its own included); the last CTA to finish publishes the step number in every rank's flag slot (system-scope fence
