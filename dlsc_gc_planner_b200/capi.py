@@ -57,7 +57,7 @@ EXPORTS = (
     "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
     "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups dlsc_edt_dims dlsc_build_edt "
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
-    "dlsc_p2p_status dlsc_p2p_disconnect").split()
+    "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch").split()
 
 
 def build_library(force=False):
@@ -340,6 +340,34 @@ class SwarmPlanner:
         anchor = np.zeros((self.NL, self.K, self.M, self.P, 3), np.float32) if with_anchor else None
         self._ck(self.lib.dlsc_get_lsc(self.ctx, _p(normal), _p(anchor), _p(d)))
         return normal, anchor, d
+
+    def set_init_traj(self, traj):
+        t = np.ascontiguousarray(traj, np.float32)
+        assert t.shape == (self.NL, self.M, self.P, 3)
+        self._ck(self.lib.dlsc_set_init_traj(self.ctx, _p(t)))
+
+    def set_pred_traj(self, traj):
+        t = np.ascontiguousarray(traj, np.float32)
+        assert t.shape == (self.N, self.M, self.P, 3)
+        self._ck(self.lib.dlsc_set_pred_traj(self.ctx, _p(t)))
+
+    def set_neighbours(self, idx, cnt):
+        i = np.ascontiguousarray(idx, np.int32)
+        n = np.ascontiguousarray(cnt, np.int32)
+        assert i.shape == (self.NL, self.K) and n.shape == (self.NL,)
+        self._ck(self.lib.dlsc_set_neighbours(self.ctx, _p(i), _p(n)))
+
+    def gjk_batch(self, pts):
+        """Per-kernel parity entry: hulls [n][6][3] f64 -> witness v [n][3], iterations, simplex size, leaf bit set."""
+        p = np.ascontiguousarray(pts, np.float64)
+        n = p.shape[0]
+        assert p.shape == (n, 6, 3)
+        v = np.zeros((n, 3), np.float64)
+        it = np.zeros(n, np.int32)
+        sn = np.zeros(n, np.int32)
+        lv = np.zeros(n, np.uint64)
+        self._ck(self.lib.dlsc_gjk_batch(self.ctx, _p(p), C.c_int(n), _p(v), _p(it), _p(sn), _p(lv)))
+        return v, it, sn, lv
 
     def counters(self):
         out = np.zeros(16, np.int64)

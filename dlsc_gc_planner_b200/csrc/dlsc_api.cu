@@ -895,6 +895,32 @@ int dlsc_measure_fp64_peak(dlsc_ctx* c, double* tflops) {
     CK(cudaGetLastError());
     return 0;
 }
+int dlsc_gjk_batch(dlsc_ctx* c, const double* pts, int n, double* v, int32_t* iters, int32_t* simplex, uint64_t* leaves) {
+    if (!c || !pts || !v || n < 0) return fail("dlsc_gjk_batch: bad argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    double *d_pts = nullptr, *d_v = nullptr;
+    int32_t *d_it = nullptr, *d_sn = nullptr;
+    unsigned long long* d_lv = nullptr;
+    int rc = 0;
+    auto body = [&]() -> int {
+        CK(cudaMalloc(&d_pts, (size_t)n * 18 * 8)); CK(cudaMalloc(&d_v, (size_t)n * 3 * 8));
+        CK(cudaMalloc(&d_it, (size_t)n * 4)); CK(cudaMalloc(&d_sn, (size_t)n * 4)); CK(cudaMalloc(&d_lv, (size_t)n * 8));
+        CK(cudaMemcpyAsync(d_pts, pts, (size_t)n * 18 * 8, cudaMemcpyHostToDevice, c->stream));
+        launch_gjk_batch(d_pts, n, d_v, d_it, d_sn, d_lv, c->stream);
+        c->launches++;
+        CK(cudaMemcpyAsync(v, d_v, (size_t)n * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (iters) CK(cudaMemcpyAsync(iters, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (simplex) CK(cudaMemcpyAsync(simplex, d_sn, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (leaves) CK(cudaMemcpyAsync(leaves, d_lv, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+        return 0;
+    };
+    rc = body();
+    cudaFree(d_pts); cudaFree(d_v); cudaFree(d_it); cudaFree(d_sn); cudaFree(d_lv);
+    return rc;
+}
 float* dlsc_waypoint_device(dlsc_ctx* c) { return c ? c->S.waypoint : nullptr; }
 float* dlsc_traj_device(dlsc_ctx* c) { return c ? c->S.traj : nullptr; }
 

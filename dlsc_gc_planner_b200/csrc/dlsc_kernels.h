@@ -68,6 +68,8 @@ void launch_set_state(const DevParams& P, float* rec, const float* pos, const fl
 void launch_get_state(const DevParams& P, const float* rec, float* pos, float* vel, cudaStream_t st);         // records -> dense pos / vel
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
 
+void launch_gjk_batch(const double* pts, int n, double* v, int32_t* iters, int32_t* simplex, unsigned long long* leaves, cudaStream_t st);
+
 constexpr int kP2PMaxWorld = 16;
 void launch_p2p_push(const float* src, size_t n_floats, size_t slice_off_floats, int world, int rank, unsigned long long step,
                      float* const* dst, unsigned long long* const* flag, unsigned* done, cudaStream_t st);

@@ -324,6 +324,27 @@ void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
     k_lsc<<<P.NL, kLscThreads, (size_t)P.K * 6 * sizeof(int), st>>>(P, S);
 }
 
+// per-kernel parity entry (dlsc_gjk_batch): the device function k_lsc calls, one hull per thread, with the leaf tracer
+__global__ void __launch_bounds__(128) k_gjk_batch(const double* __restrict__ pts, int n, double* __restrict__ v_out,
+                                                   int32_t* __restrict__ iters, int32_t* __restrict__ simplex,
+                                                   unsigned long long* __restrict__ leaves) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    gjk::D3 c[kP];
+#pragma unroll
+    for (int i = 0; i < kP; i++) c[i] = gjk::d3(pts[(size_t)h * 18 + 3 * i], pts[(size_t)h * 18 + 3 * i + 1], pts[(size_t)h * 18 + 3 * i + 2]);
+    gjk::MaskTrace tr; tr.m = 0;
+    int it = 0, sn = 0;
+    const gjk::D3 v = gjk::hull_origin<kP, gjk::MaskTrace>(c, &it, tr, &sn);
+    v_out[(size_t)h * 3] = v.x; v_out[(size_t)h * 3 + 1] = v.y; v_out[(size_t)h * 3 + 2] = v.z;
+    if (iters) iters[h] = it;
+    if (simplex) simplex[h] = sn;
+    if (leaves) leaves[h] = tr.m;
+}
+void launch_gjk_batch(const double* pts, int n, double* v, int32_t* iters, int32_t* simplex, unsigned long long* leaves, cudaStream_t st) {
+    k_gjk_batch<<<(n + 127) / 128, 128, 0, st>>>(pts, n, v, iters, simplex, leaves);
+}
+
 // ------------------------------------------------------------------------------------------------
 // one warp per agent: the greedy control flow is replicated in every lane (uniform), the lattice columns of
 // a box test are spread over the lanes (one 16-byte load of the vertex mask = 16 vertices) and combined with

@@ -111,6 +111,21 @@ DLSC_HD int hff3(const D3& p, const D3& q, const D3& r) {     // openGJK.cpp:220
     return t > 0 ? 0 : 1;
 }
 
+// Branch tracer of the distance sub-algorithm: the product kernels pass NoTrace (no code); the per-kernel parity
+// entry point dlsc_gjk_batch passes MaskTrace and returns, per hull, the set of decision-tree leaves it went
+// through, so the tests can show that every leaf is pinned against the reference's object code.
+//   0-1   sub1d: edge region, vertex          2-5   sub2d: face, edge ac, edge ab, vertex (55-56: face / edge ac
+//                                                   reached through the "ab not an edge region" side)
+//   6     sub3d: vertex a                     7     origin inside the tetrahedron
+//   8-10  two visible faces (which one is hidden)                 11-13 one visible face: rotation
+//   14-20 one face, one edge      21-29 one face, two edges       30-34 one face, three edges
+//   35-37 no face, one edge: rotation, 38-40 its leaves           41-43 no face, two edges: rotation, 44-48 leaves
+//   49    no face, three edges (simplex kept)
+//   50-54 main loop exits: relative/absolute gap, |v|^2 tiny, |v|^2 vs simplex scale, 4 vertices, 25 iterations
+struct NoTrace { DLSC_HD void hit(int) const {} };
+struct MaskTrace { unsigned long long m; DLSC_HD void hit(int id) { m |= 1ull << id; } };
+constexpr int kGjkLeaves = 57;
+
 // simplex: slots s0..s3 kept as named members so they stay in registers
 struct Simplex {
     int n;
@@ -121,15 +136,18 @@ DLSC_HD void set_edge(Simplex& s, const D3& lo, const D3& a) { s.n = 2; s.s0 = l
 DLSC_HD void set_face(Simplex& s, const D3& lo, const D3& mid, const D3& a) { s.n = 3; s.s0 = lo; s.s1 = mid; s.s2 = a; }
 
 // openGJK.cpp:243-256
-DLSC_HD D3 sub1d(Simplex& s) {
+template <class Tr>
+DLSC_HD D3 sub1d(Simplex& s, Tr& tr) {
     const D3 a = s.s1, b = s.s0;
-    if (hff1(a, b)) return proj_line(a, b);
+    if (hff1(a, b)) { tr.hit(0); return proj_line(a, b); }
+    tr.hit(1);
     s.n = 1; s.s0 = a;
     return a;
 }
 
 // openGJK.cpp:259-313
-DLSC_HD D3 sub2d(Simplex& s) {
+template <class Tr>
+DLSC_HD D3 sub2d(Simplex& s, Tr& tr) {
     const D3 a = s.s2, b = s.s1, c = s.s0;
     const int e_ab = hff1(a, b);
     const int e_ac = hff1(a, c);
@@ -137,12 +155,12 @@ DLSC_HD D3 sub2d(Simplex& s) {
     const int f_cb = !hff2(a, c, b);
     int r;   // 0 face, 1 edge ab, 2 edge ac, 3 vertex
     if (e_ab) {
-        if (f_bc) r = (e_ac && !f_cb) ? 2 : 0;
-        else r = 1;
+        if (f_bc) { r = (e_ac && !f_cb) ? 2 : 0; tr.hit(r ? 3 : 2); }
+        else { r = 1; tr.hit(4); }
     } else if (e_ac) {
-        r = f_cb ? 0 : 2;
+        r = f_cb ? 0 : 2; tr.hit(r ? 56 : 55);
     } else {
-        r = 3;
+        r = 3; tr.hit(5);
     }
     if (r == 0) return proj_plane(a, b, c);
     if (r == 2) { s.n = 2; s.s1 = a; return proj_line(a, c); }            // keeps {c, a}
@@ -152,105 +170,108 @@ DLSC_HD D3 sub2d(Simplex& s) {
 }
 
 // openGJK.cpp:315-631.  v is the previous search vector (left untouched on the do-nothing paths).
-DLSC_HDN D3 sub3d(Simplex& s, const D3& v_in) {
+template <class Tr>
+DLSC_HDN D3 sub3d(Simplex& s, const D3& v_in, Tr& tr) {
     const D3 a = s.s3;
     const D3 q2 = s.s2, q1 = s.s1, q0 = s.s0;      // q2 = s2, q1 = s3, q0 = s4 of the reference
     const D3 e2 = sub(q2, a), e3 = sub(q1, a), e4 = sub(q0, a);
     const int ed2 = hff1(a, q2), ed1 = hff1(a, q1), ed0 = hff1(a, q0);
     const int n_edge = ed2 + ed1 + ed0;
-    if (n_edge == 0) { s.n = 1; s.s0 = a; return a; }
+    if (n_edge == 0) { tr.hit(6); s.n = 1; s.s0 = a; return a; }
     const int sss = det3(e3, e4, e2) > 0 ? 0 : 1;
     int t2 = hff3(a, q1, q0) - sss; t2 *= t2;
     int t3 = hff3(a, q0, q2) - sss; t3 *= t3;
     int t4 = hff3(a, q2, q1) - sss; t4 *= t4;
     const int n_face = t2 + t3 + t4;
-    if (n_face == 3) { s.n = 4; return d3(0, 0, 0); }
+    if (n_face == 3) { tr.hit(7); s.n = 4; return d3(0, 0, 0); }
     if (n_face == 2) {
         s.n = 3;
-        if (!t2) { s.s2 = a; }                               // {s4, s3, a}
-        else if (!t3) { s.s1 = q2; s.s2 = a; }               // {s4, s2, a}
-        else { s.s0 = q1; s.s1 = q2; s.s2 = a; }             // {s3, s2, a}
-        return sub2d(s);
+        if (!t2) { tr.hit(8); s.s2 = a; }                               // {s4, s3, a}
+        else if (!t3) { tr.hit(9); s.s1 = q2; s.s2 = a; }               // {s4, s2, a}
+        else { tr.hit(10); s.s0 = q1; s.s1 = q2; s.s2 = a; }            // {s3, s2, a}
+        return sub2d(s, tr);
     }
     // rotation (k, i, j) of the slots (2,1,0)
     D3 si, sj, sk;
     int ei, ej, ek;
     if (n_face == 1) {
         s.n = 3;
-        if (t2) { sk = q2; si = q1; sj = q0; ek = ed2; ei = ed1; ej = ed0; }
-        else if (t3) { sk = q1; si = q0; sj = q2; ek = ed1; ei = ed0; ej = ed2; }
-        else { sk = q0; si = q2; sj = q1; ek = ed0; ei = ed2; ej = ed1; }
+        if (t2) { tr.hit(11); sk = q2; si = q1; sj = q0; ek = ed2; ei = ed1; ej = ed0; }
+        else if (t3) { tr.hit(12); sk = q1; si = q0; sj = q2; ek = ed1; ei = ed0; ej = ed2; }
+        else { tr.hit(13); sk = q0; si = q2; sj = q1; ek = ed0; ei = ed2; ej = ed1; }
         if (n_edge == 1) {
             if (ek) {
-                if (!hff2(a, sk, si)) { set_face(s, sk, si, a); return proj_plane(a, si, sk); }
-                if (!hff2(a, sk, sj)) { set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
-                set_edge(s, sk, a); return proj_line(a, sk);
+                if (!hff2(a, sk, si)) { tr.hit(14); set_face(s, sk, si, a); return proj_plane(a, si, sk); }
+                if (!hff2(a, sk, sj)) { tr.hit(15); set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
+                tr.hit(16); set_edge(s, sk, a); return proj_line(a, sk);
             } else if (ei) {
-                if (!hff2(a, si, sk)) { set_face(s, sk, si, a); return proj_plane(a, si, sk); }
-                set_edge(s, si, a); return proj_line(a, si);
+                if (!hff2(a, si, sk)) { tr.hit(17); set_face(s, sk, si, a); return proj_plane(a, si, sk); }
+                tr.hit(18); set_edge(s, si, a); return proj_line(a, si);
             } else {
-                if (!hff2(a, sj, sk)) { set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
-                set_edge(s, sj, a); return proj_line(a, sj);
+                if (!hff2(a, sj, sk)) { tr.hit(19); set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
+                tr.hit(20); set_edge(s, sj, a); return proj_line(a, sj);
             }
         } else if (n_edge == 2) {
             if (ei) {
                 if (!hff2(a, sk, si)) {
-                    if (!hff2(a, si, sk)) { set_face(s, sk, si, a); return proj_plane(a, si, sk); }
-                    set_edge(s, sk, a); return proj_line(a, sk);
+                    if (!hff2(a, si, sk)) { tr.hit(21); set_face(s, sk, si, a); return proj_plane(a, si, sk); }
+                    tr.hit(22); set_edge(s, sk, a); return proj_line(a, sk);
                 } else {
-                    if (!hff2(a, sk, sj)) { set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
-                    set_edge(s, sk, a); return proj_line(a, sk);
+                    if (!hff2(a, sk, sj)) { tr.hit(23); set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
+                    tr.hit(24); set_edge(s, sk, a); return proj_line(a, sk);
                 }
             } else if (ej) {
                 if (!hff2(a, sk, sj)) {
-                    if (!hff2(a, sj, sk)) { set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
-                    set_edge(s, sj, a); return proj_line(a, sj);
+                    if (!hff2(a, sj, sk)) { tr.hit(25); set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
+                    tr.hit(26); set_edge(s, sj, a); return proj_line(a, sj);
                 } else {
-                    if (!hff2(a, sk, si)) { set_face(s, sk, si, a); return proj_plane(a, si, sk); }
-                    set_edge(s, sk, a); return proj_line(a, sk);
+                    if (!hff2(a, sk, si)) { tr.hit(27); set_face(s, sk, si, a); return proj_plane(a, si, sk); }
+                    tr.hit(28); set_edge(s, sk, a); return proj_line(a, sk);
                 }
             }
+            tr.hit(29);
             return v_in;    // reference leaves {s4,s3,s2} (n = 3) and v untouched (openGJK.cpp:497-499)
         } else {
             const int d_ik = hff2(a, si, sk), d_jk = hff2(a, sj, sk);
             const int d_ki = hff2(a, sk, si), d_kj = hff2(a, sk, sj);
-            if (d_ki == 1 && d_kj == 1) { set_edge(s, sk, a); return proj_line(a, sk); }
+            if (d_ki == 1 && d_kj == 1) { tr.hit(30); set_edge(s, sk, a); return proj_line(a, sk); }
             if (d_ki) {
-                if (d_jk) { set_edge(s, sj, a); return proj_line(a, sj); }
-                set_face(s, sk, sj, a); return proj_plane(a, sk, sj);
+                if (d_jk) { tr.hit(31); set_edge(s, sj, a); return proj_line(a, sj); }
+                tr.hit(32); set_face(s, sk, sj, a); return proj_plane(a, sk, sj);
             }
-            if (d_ik) { set_edge(s, si, a); return proj_line(a, si); }
-            set_face(s, sk, si, a); return proj_plane(a, sk, si);
+            if (d_ik) { tr.hit(33); set_edge(s, si, a); return proj_line(a, si); }
+            tr.hit(34); set_face(s, sk, si, a); return proj_plane(a, sk, si);
         }
     }
     // n_face == 0
     if (n_edge == 1) {
-        if (ed1) { sk = q2; si = q1; sj = q0; }
-        else if (ed0) { sk = q1; si = q0; sj = q2; }
-        else { sk = q0; si = q2; sj = q1; }
-        if (!hff2(a, si, sj)) { set_face(s, sj, si, a); return proj_plane(a, si, sj); }
-        if (!hff2(a, si, sk)) { set_face(s, sk, si, a); return proj_plane(a, si, sk); }
-        set_edge(s, si, a); return proj_line(a, si);
+        if (ed1) { tr.hit(35); sk = q2; si = q1; sj = q0; }
+        else if (ed0) { tr.hit(36); sk = q1; si = q0; sj = q2; }
+        else { tr.hit(37); sk = q0; si = q2; sj = q1; }
+        if (!hff2(a, si, sj)) { tr.hit(38); set_face(s, sj, si, a); return proj_plane(a, si, sj); }
+        if (!hff2(a, si, sk)) { tr.hit(39); set_face(s, sk, si, a); return proj_plane(a, si, sk); }
+        tr.hit(40); set_edge(s, si, a); return proj_line(a, si);
     }
     if (n_edge == 2) {
         s.n = 3;
-        if (!ed1) { sk = q2; si = q1; sj = q0; }
-        else if (!ed0) { sk = q1; si = q0; sj = q2; }
-        else { sk = q0; si = q2; sj = q1; }
+        if (!ed1) { tr.hit(41); sk = q2; si = q1; sj = q0; }
+        else if (!ed0) { tr.hit(42); sk = q1; si = q0; sj = q2; }
+        else { tr.hit(43); sk = q0; si = q2; sj = q1; }
         if (!hff2(a, sj, sk)) {
-            if (!hff2(a, sk, sj)) { set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
-            if (!hff2(a, sk, si)) { set_face(s, sk, si, a); return proj_plane(a, sk, si); }
-            set_edge(s, sk, a); return proj_line(a, sk);
+            if (!hff2(a, sk, sj)) { tr.hit(44); set_face(s, sk, sj, a); return proj_plane(a, sj, sk); }
+            if (!hff2(a, sk, si)) { tr.hit(45); set_face(s, sk, si, a); return proj_plane(a, sk, si); }
+            tr.hit(46); set_edge(s, sk, a); return proj_line(a, sk);
         }
-        if (!hff2(a, sj, si)) { set_face(s, sj, si, a); return proj_plane(a, si, sj); }
-        set_edge(s, sj, a); return proj_line(a, sj);
+        if (!hff2(a, sj, si)) { tr.hit(47); set_face(s, sj, si, a); return proj_plane(a, si, sj); }
+        tr.hit(48); set_edge(s, sj, a); return proj_line(a, sj);
     }
+    tr.hit(49);
     return v_in;   // n_edge == 3 with no visible face: reference does nothing, n stays 4 (openGJK.cpp:545-626)
 }
 
 // openGJK.cpp:674-780 with bd2 = {origin} (include/geometry.hpp:289-298).  NP points c[0..NP).
-template <int NP>
-DLSC_HD D3 hull_origin(const D3 (&c)[NP], int* iters_out) {
+template <int NP, class Tr>
+DLSC_HD D3 hull_origin(const D3 (&c)[NP], int* iters_out, Tr& tr, int* simplex_out = nullptr) {
     const double eps_rel = 1e-10, eps_tot = 1e-12;
     const double eps_rel2 = eps_rel * eps_rel;
     Simplex s;
@@ -275,19 +296,27 @@ DLSC_HD D3 hull_origin(const D3 (&c)[NP], int* iters_out) {
         const D3 w = d3(sup.x - 0.0, sup.y - 0.0, sup.z - 0.0);
         const double vv = dot(v, v);
         const double ex = vv - dot(v, w);
-        if (ex <= eps_rel * vv || ex < eps_tot) break;
-        if (vv < eps_rel2) break;
-        if (s.n == 1) { s.s1 = w; s.n = 2; v = sub1d(s); }
-        else if (s.n == 2) { s.s2 = w; s.n = 3; v = sub2d(s); }
-        else { s.s3 = w; s.n = 4; v = sub3d(s, v); }
+        if (ex <= eps_rel * vv || ex < eps_tot) { tr.hit(50); break; }
+        if (vv < eps_rel2) { tr.hit(51); break; }
+        if (s.n == 1) { s.s1 = w; s.n = 2; v = sub1d(s, tr); }
+        else if (s.n == 2) { s.s2 = w; s.n = 3; v = sub2d(s, tr); }
+        else { s.s3 = w; s.n = 4; v = sub3d(s, v, tr); }
         double tn = dot(s.s0, s.s0); if (tn > nwmax) nwmax = tn;
         if (s.n > 1) { tn = dot(s.s1, s.s1); if (tn > nwmax) nwmax = tn; }
         if (s.n > 2) { tn = dot(s.s2, s.s2); if (tn > nwmax) nwmax = tn; }
         if (s.n > 3) { tn = dot(s.s3, s.s3); if (tn > nwmax) nwmax = tn; }
-        if (dot(v, v) <= eps_tot * eps_tot * nwmax) break;
+        if (dot(v, v) <= eps_tot * eps_tot * nwmax) { tr.hit(52); break; }
+        if (s.n == 4) tr.hit(53);
+        else if (k == 25) tr.hit(54);
     } while (s.n != 4 && k != 25);
     if (iters_out) *iters_out = k;
+    if (simplex_out) *simplex_out = s.n;
     return v;
+}
+template <int NP>
+DLSC_HD D3 hull_origin(const D3 (&c)[NP], int* iters_out) {
+    NoTrace tr;
+    return hull_origin<NP, NoTrace>(c, iters_out, tr);
 }
 }  // namespace gjk
 

@@ -249,6 +249,15 @@ int dlsc_set_waypoints_device(dlsc_ctx* ctx, const float* device_ptr);
  * denominator of the FP64 roofline of the LSC and QP kernels (MEASURED_PEAKS.json has no FP64 figure). */
 int dlsc_measure_fp64_peak(dlsc_ctx* ctx, double* tflops);
 
+/* Per-kernel parity entry point for the GJK core of the LSC stage (SURVEY s8(b) "single-stage entry points"):
+ * closest point of conv{pts[h][0..5]} to the origin for n hulls, by the very device function k_lsc calls
+ * (gjk::hull_origin, dlsc_math.cuh).  Replaces closestPointsBetweenPointAndConvexHull -> gjk
+ * (include/geometry.hpp:276-306, src/openGJK/openGJK.cpp:674-780).  Host arrays; pts [n][6][3] f64,
+ * v [n][3] f64 witness vector, iters / simplex [n] (iteration count, final simplex size; may be NULL),
+ * leaves [n] (bit set of the decision-tree leaves the call went through, numbering in dlsc_math.cuh; may be NULL). */
+int dlsc_gjk_batch(dlsc_ctx* ctx, const double* pts, int n, double* v, int32_t* iters, int32_t* simplex,
+                   uint64_t* leaves);
+
 /* Device pointers of per-step input / output arrays, for callers that keep data on the GPU. */
 float* dlsc_waypoint_device(dlsc_ctx* ctx);   /* [n_local][3] */
 float* dlsc_traj_device(dlsc_ctx* ctx);       /* [n_local][M][P][3] */

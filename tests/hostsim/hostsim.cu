@@ -510,6 +510,20 @@ int dlsc_set_lsc(dlsc_ctx* c, const float* normal, const float* anchor_last, con
 }
 int dlsc_set_waypoints_device(dlsc_ctx* c, const float* p) { memcpy(c->waypoint.data(), p, c->waypoint.size() * 4); return 0; }
 int dlsc_measure_fp64_peak(dlsc_ctx*, double* t) { *t = 0.0; return 0; }
+int dlsc_gjk_batch(dlsc_ctx*, const double* pts, int n, double* v, int32_t* iters, int32_t* simplex, uint64_t* leaves) {
+    for (int h = 0; h < n; h++) {
+        gjk::D3 c[kP];
+        for (int i = 0; i < kP; i++) c[i] = gjk::d3(pts[(size_t)h * 18 + 3 * i], pts[(size_t)h * 18 + 3 * i + 1], pts[(size_t)h * 18 + 3 * i + 2]);
+        gjk::MaskTrace tr; tr.m = 0;
+        int it = 0, sn = 0;
+        const gjk::D3 w = gjk::hull_origin<kP, gjk::MaskTrace>(c, &it, tr, &sn);
+        v[(size_t)h * 3] = w.x; v[(size_t)h * 3 + 1] = w.y; v[(size_t)h * 3 + 2] = w.z;
+        if (iters) iters[h] = it;
+        if (simplex) simplex[h] = sn;
+        if (leaves) leaves[h] = tr.m;
+    }
+    return 0;
+}
 int dlsc_set_stream(dlsc_ctx*, void*) { return 0; }
 void* dlsc_get_stream(dlsc_ctx*) { return nullptr; }
 int dlsc_bind_records(dlsc_ctx*, float*) { return fail("hostsim: not supported"); }
