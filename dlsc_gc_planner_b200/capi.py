@@ -33,6 +33,7 @@ class DlscParams(C.Structure):
         ("comm_range", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
         ("reset_threshold", C.c_double),
         ("qp_max_iter", C.c_int32), ("qp_solver", C.c_int32), ("qp_screen_slack", C.c_double),
+        ("qp_active_max", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -104,7 +105,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0, qp_screen_slack=0.0, qp_solver=0):
+def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0, qp_screen_slack=0.0, qp_solver=0, qp_active_max=0):
     """cfg: missions.PlannerConfig."""
     p = DlscParams()
     p.M, p.n, p.phi, p.dim, p.use_sfc, p.max_nbr = cfg.M, cfg.n, cfg.phi, cfg.dim, int(cfg.use_sfc), int(max_nbr)
@@ -118,6 +119,7 @@ def make_params(cfg, world_min, world_max, max_nbr, qp_max_iter=0, qp_screen_sla
     p.qp_max_iter = qp_max_iter
     p.qp_screen_slack = qp_screen_slack
     p.qp_solver = qp_solver
+    p.qp_active_max = qp_active_max
     return p
 
 
@@ -129,7 +131,7 @@ class SwarmPlanner:
     """One context = the agent block [begin, begin+n_local) of a swarm of n_agents on one GPU."""
 
     def __init__(self, cfg, mission, max_nbr=None, begin=0, n_local=None, device=0, lib=None, qp_max_iter=0,
-                 qp_screen_slack=0.0, qp_solver=0):
+                 qp_screen_slack=0.0, qp_solver=0, qp_active_max=0):
         self.lib = lib if lib is not None else load_library()
         self.cfg = cfg
         self.N = int(mission.n_agents)
@@ -137,7 +139,7 @@ class SwarmPlanner:
         self.NL = int(n_local if n_local is not None else self.N - begin)
         self.M, self.P, self.D = cfg.M, cfg.n + 1, cfg.dim
         self.K = int(max_nbr if max_nbr is not None else max(self.N - 1, 1))
-        self.params = make_params(cfg, mission.world_min, mission.world_max, self.K, qp_max_iter, qp_screen_slack, qp_solver)
+        self.params = make_params(cfg, mission.world_min, mission.world_max, self.K, qp_max_iter, qp_screen_slack, qp_solver, qp_active_max)
         self.ctx = C.c_void_p()
         self._ck(self.lib.dlsc_create(C.byref(self.params), self.N, self.begin, self.NL, int(device), C.byref(self.ctx)))
         sl = slice(self.begin, self.begin + self.NL)

@@ -207,7 +207,10 @@ DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, c
     c.tick(3);
     double nv = 0.0;
     gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, dev2, vmax, idsel, nv, mine, row);
-    // every thread is past the reduction, so nobody reads dev2 any more: reset it for the next map
+    // every thread is past the reduction, so nobody reads dev2 any more: reset it for the next map.  In warp mode the
+    // reduction is shuffles only, which order execution but are no memory barrier (racecheck flags the reset against
+    // the scan's reads): __syncwarp makes the ordering explicit.
+    if (c.warp) c.wsync();
     for (int m = c.tid; m < P.M; m += c.nthr) dev2[m] = 0;
     if (nviol) *nviol = nv;
     c.tick(5);
@@ -377,7 +380,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     const int kdrop = (int)g.ty[5];
                     u_p += g.ty[7];
                     if (g.ty[4] != 0.0) {
-                        if (q == kGiQ) flag = 3.0;
+                        if (q >= P.qp_active_max) flag = 3.0;
                         else {
                             for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
                             g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;

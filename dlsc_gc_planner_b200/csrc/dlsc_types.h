@@ -16,6 +16,7 @@ struct DevParams {
     int qp_max_iter;
     double qp_screen;                // LSC working-set screen [m]; <= 0: all rows
     int qp_solver;                   // 0: dual active set with interior-point fallback, 1: interior point only
+    int qp_active_max;               // active-set capacity before the hand-over to the interior point (<= kGiQ)
     double dt, world_res, grid_res, z_2d, comm_range, w_control, w_terminal, reset_threshold;
     double world_min[3], world_max[3];       // double(float(x))
     float tk[kMaxPts];               // (float) of the time accumulated by `time += dt/n` (trajectory.cpp:84-90)

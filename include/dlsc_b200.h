@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DLSC_ABI_VERSION 2
+#define DLSC_ABI_VERSION 3
 
 /* Planner parameters: the subset of MATP::Param / MATP::Mission the hot path reads
  * (reference src/param.cpp:5-117, src/mission.cpp:104-112; launch-file values SURVEY.md s5). */
@@ -58,6 +58,9 @@ typedef struct dlsc_params {
                                > 0: the active set skips rows whose slack at the initial trajectory exceeds the
                                iterate's deviation from it, and the interior-point fallback starts from the rows
                                with slack below this value [m]; < 0: every row is evaluated in every scan.  */
+    int32_t qp_active_max;  /* the dual active set hands an agent over to the interior point once this many rows are
+                               active at the same time (0 -> 32, the capacity; smaller values exercise the hand-over) */
+    int32_t reserved0;
 } dlsc_params;
 
 /* per-agent status bits (dlsc_get_status) */

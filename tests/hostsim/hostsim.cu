@@ -64,6 +64,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     P.qp_max_iter = hp->qp_max_iter > 0 ? hp->qp_max_iter : 80;
     P.qp_screen = hp->qp_screen_slack == 0.0 ? 0.5 : hp->qp_screen_slack;
     P.qp_solver = hp->qp_solver;
+    P.qp_active_max = (hp->qp_active_max > 0 && hp->qp_active_max < 32) ? hp->qp_active_max : 32;
     P.dt = hp->dt; P.world_res = hp->world_res; P.grid_res = hp->grid_res; P.z_2d = hp->z_2d;
     P.comm_range = hp->comm_range; P.w_control = hp->w_control; P.w_terminal = hp->w_terminal;
     P.reset_threshold = hp->reset_threshold;

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     missing = [s for s in header_symbols() if not hasattr(lib, s)]
     assert not missing, missing
-    assert lib.dlsc_abi_version() == 2
+    assert lib.dlsc_abi_version() == 3
 
 
 def test_no_cpu_fallback():
