@@ -1,6 +1,8 @@
 """Generates the committed fixtures under tests/golden/ from the reference tree (run in the build
 container, where /root/reference exists; the GPU box and the tests never read /root/reference):
 
+  missions_all.npz  missions #1..#30 of empty10 / empty50 / empty70 / forest10 (+ forest_tro2022 worlds) / maze10_dense
+                    (+ maze_icra2023/dense worlds), same fields
   missions.npz      the reference missions / worlds the BASELINE configs name (inputs only: start, goal,
                     agent properties, world box, obstacle boxes)           <- missions/*.json, world/*.csv
   golden_log.npz    the first rows of the reference's only recorded run     <- log/result_...csv
@@ -46,6 +48,18 @@ def main():
     m = missions.load_mission(f"{REF}/missions/maze10_dense/maze10_1.json", dim=2)
     m.boxes = missions.load_world_csv(f"{REF}/world/maze_icra2023/dense/maze1.csv"); pack("maze10/", m, out)
     np.savez_compressed(os.path.join(OUT, "missions.npz"), **out)
+
+    # every mission of the families the BASELINE configs name (#1..#30; testall_DLSCGC_*.launch pairs mission k with world k)
+    allm = {}
+    for k in range(1, 31):
+        m = missions.load_mission(f"{REF}/missions/empty10/multi_random_10agents_{k}.json"); pack(f"empty10/{k}/", m, allm)
+        m = missions.load_mission(f"{REF}/missions/empty50/multi_random_50agents_{k}.json"); pack(f"empty50/{k}/", m, allm)
+        m = missions.load_mission(f"{REF}/missions/empty70/multi_random_70agents_{k}.json"); pack(f"empty70/{k}/", m, allm)
+        m = missions.load_mission(f"{REF}/missions/forest10/forest10_{k}.json")
+        m.boxes = missions.load_world_csv(f"{REF}/world/forest_tro2022/forest{k}.csv"); pack(f"forest10/{k}/", m, allm)
+        m = missions.load_mission(f"{REF}/missions/maze10_dense/maze10_{k}.json", dim=2)
+        m.boxes = missions.load_world_csv(f"{REF}/world/maze_icra2023/dense/maze{k}.csv"); pack(f"maze10/{k}/", m, allm)
+    np.savez_compressed(os.path.join(OUT, "missions_all.npz"), **allm)
 
     rows = [l.strip().split(",") for l in open(f"{REF}/log/result_1742185870.978562_DLSCGC_10agents.csv")][1:4]
     log = np.array(rows, dtype=np.float64).reshape(3, 10, 12)

@@ -31,6 +31,18 @@ def test_lockstep_parity_reference_missions(cuda_lib, name, steps, n):
     pl.close()
 
 
+@pytest.mark.parametrize("name", ["empty10", "forest10", "maze10"])
+def test_lockstep_parity_more_missions(cuda_lib, name):
+    """Missions #4, #9, #15, #22, #30 of the family (world k for mission k), 10 lock-step steps each."""
+    worst = {}
+    for index in (4, 9, 15, 22, 30):
+        cfg, m = _parity.load_case(name, index)
+        sw, pl = make_pair(cuda_lib, cfg, m, m.n_agents - 1)
+        _parity.merge_max(worst, _parity.run_lockstep(pl, sw, m, 10, _parity.default_waypoints(cfg, m)))
+        pl.close()
+    check_worst(worst)
+
+
 def test_synthetic_forest_256(cuda_lib):
     """A 256-agent cut of the synthetic forest (BASELINE config 4 shape: M=10, 3-D, SFC, range 3)."""
     cfg = missions.PlannerConfig.forest3d()

@@ -1,6 +1,8 @@
 """CPU tier: the kernel cores (the same __host__ __device__ source the sm_100a kernels run), executed by the
 test-only host simulator, against the oracle on the reference missions.  Bit-exact for the float32/float64
 geometry stages; QP within the north_star tolerances."""
+import os
+
 import numpy as np
 import pytest
 
@@ -17,7 +19,13 @@ def check_worst(w):
     assert w["status_mismatch"] == 0
     assert w["obj_excess"] <= _parity.OBJ_ABS, w
     assert w["violation"] <= 1e-6, w
-    assert w["x"] <= 1e-4, w      # informational: degenerate (weakly active) rows leave x defined to O(sqrt(mu_tol))
+    # control points: the QP is strictly convex but flat (control weight 0.01 x the smallest eigenvalues of the jerk
+    # Gram matrix), so the ORACLE's interior point -- which stops at a duality gap of ~1e-12 -- fixes x only to
+    # sqrt(2 gap / lambda_min) ~ 5e-6 (observed worst 4.6e-6 over all 90 reference missions; a quarter of the agents
+    # are beyond 1e-6).  The kernels' active-set x is the accurate one: it satisfies the KKT conditions of the
+    # independently restated QP to 1e-8 (tests/test_qp_crosscheck.py).  The float32 trajectory follows x.
+    assert w["x"] <= 1e-5, w
+    assert w["traj"] <= 1e-5, w
 
 
 @pytest.mark.parametrize("name,steps,n", [("empty10", 25, 10), ("maze10", 45, 10), ("forest10", 30, 10),
@@ -32,6 +40,33 @@ def test_lockstep_parity(hostsim, name, steps, n):
         pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
     w = _parity.run_lockstep(pl, sw, m, steps, _parity.default_waypoints(cfg, m))
     check_worst(w)
+    pl.close()
+
+
+@pytest.mark.parametrize("name,steps", [("empty10", 12), ("forest10", 12), ("maze10", 12)])
+def test_lockstep_parity_all_30_missions(hostsim, name, steps):
+    """Every mission of the family (reference missions/<family>/*_{1..30}.json with world k for mission k)."""
+    worst = {}
+    for index in range(1, 31):
+        cfg, m = _parity.load_case(name, index)
+        K = m.n_agents - 1
+        sw = _parity.make_oracle(cfg, m, K, n_threads=os.cpu_count() or 1)
+        pl = capi.SwarmPlanner(cfg, m, max_nbr=K, lib=hostsim)
+        if cfg.use_sfc:
+            pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
+        _parity.merge_max(worst, _parity.run_lockstep(pl, sw, m, steps, _parity.default_waypoints(cfg, m)))
+        pl.close()
+    check_worst(worst)
+    assert worst["ok_agents"] >= 30 * steps * 10 * 0.98
+
+
+@pytest.mark.parametrize("name,index", [("empty50", 3), ("empty50", 17), ("empty70", 9), ("empty70", 30)])
+def test_lockstep_parity_large_empty_missions(hostsim, name, index):
+    cfg, m = _parity.load_case(name, index)
+    K = m.n_agents - 1
+    sw = _parity.make_oracle(cfg, m, K, n_threads=os.cpu_count() or 1)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=K, lib=hostsim)
+    check_worst(_parity.run_lockstep(pl, sw, m, 4, _parity.default_waypoints(cfg, m)))
     pl.close()
 
 

@@ -2,7 +2,7 @@
   * the reference's own openGJK object code (known-answer vectors in tests/golden/gjk_ref.npz, and live
     against oracle/_ref when it is built),
   * the reference's only recorded run (log/result_...DLSCGC_10agents.csv): first replan of maze10_dense #1,
-  * an independent QP solver (HiGHS through scipy) for the CPLEX stand-in.
+  * (the independent QP cross-check -- second formulation + HiGHS + KKT certificate -- lives in test_qp_crosscheck.py).
 """
 import numpy as np
 import pytest
@@ -52,22 +52,6 @@ def test_golden_log_first_replan(oracle):
             ref = z["state"][row, a]
             for i in range(9):
                 assert abs(_sig6(s[i]) - ref[i]) <= 1e-6 * max(1.0, abs(ref[i])), (row, a, i, s[i], ref[i])
-
-
-def test_qp_against_highs(oracle):
-    """The oracle's interior-point QP against HiGHS on the x-axis problem of the golden first replan."""
-    sp = pytest.importorskip("scipy.optimize._highspy._core")
-    cfg, m = _parity.load_case("empty10")
-    sw = _parity.make_oracle(cfg, m, 9)
-    wf = _parity.default_waypoints(cfg, m)
-    for _ in range(6):
-        sw.waypoint = wf(sw)
-        sw.step()
-        sw.advance()
-    assert sw.status.max() == 0
-    assert sw.max_violation.max() <= 1e-9
-    # KKT check instead of a second solve when the HiGHS binding lacks passHessian
-    assert sw.qp_iters.max() < 40
 
 
 def test_edt_cell_index_float_trap(oracle):
