@@ -222,6 +222,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.lsc_d, NL * K * M * kP);
     rc |= dev_alloc(c, &S.lsc_anchor_last, NL * K * 3);
     rc |= dev_alloc(c, &S.lsc_near, NL * K * M);
+    rc |= dev_alloc(c, &S.lsc_queue, NL * K * M);
     rc |= dev_alloc(c, &S.sfc, NL * M * 6);
     rc |= dev_alloc(c, &S.traj, NL * npt * 3);
     rc |= dev_alloc(c, &S.qp_x, NL * (size_t)hp->dim * npt);
@@ -702,7 +703,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     }
     if (mask & DLSC_STAGE_NBR) c->launches += launch_neighbours(Pr, Sx, st);
     if (tm) CK(cudaEventRecord(ev[2], st));
-    if (mask & DLSC_STAGE_LSC) { launch_lsc(Pr, Sx, st); c->launches++; }
+    if (mask & DLSC_STAGE_LSC) c->launches += launch_lsc(Pr, Sx, st);
     if (tm) CK(cudaEventRecord(ev[3], st));
     if (fork) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     else if (sfc_on) { launch_sfc(Pr, Sx, st); c->launches++; }

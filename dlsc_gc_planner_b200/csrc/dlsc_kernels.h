@@ -31,6 +31,7 @@ struct DevState {
     float* lsc_normal;         // [NL][K][M][3]
     double* lsc_d;             // [NL][K][M][P]
     float* lsc_anchor_last;    // [NL][K][3]
+    uint32_t* lsc_queue;       // [NL K] last-segment items | [NL K (M-1)] GJK items k_lsc could not finish (k_lsc_rest)
     float* lsc_near;           // [NL][K][M] QP row screen: smallest normalised slack of the item's rows at the initial trajectory
     float* sfc;                // [NL][M][6]
     float* traj;               // [NL][M][P][3]  QP result (or failsafe)
@@ -50,7 +51,7 @@ struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
 int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, int parts = 3);   // 1: grid build, 2: search; returns launches
-void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);
+int launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);   // returns launches
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_goal_copy(const DevParams& P, const DevState& S, cudaStream_t st);   // goal_new := record goal

@@ -270,28 +270,38 @@ int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA per agent.  The agent's neighbour list, its own initial trajectory and the neighbours' (radius, downwash,
-// goal) are staged in shared memory first, so that the per-item loads (the neighbour's predicted control points)
-// are one dependent hop away; then thread per item, all GJK items (neighbour x segments 0..M-2, warps
-// homogeneous: similar geometry, similar GJK depth) before the last-segment items (segment-segment closest points,
-// a different code path).
+// LSC in two phases.
+//   k_lsc       CTA per agent.  The agent's neighbour list, its own initial trajectory and the neighbours' (radius,
+//               downwash, goal) are staged in shared memory, then thread per (neighbour, segment < M-1) item: the
+//               two-vertex GJK (gjk::hull_origin_short) finishes ~90 % of the hulls of a swarm in one to three support
+//               evaluations; those are written out at once.  The rest -- hulls that need the triangle / tetrahedron
+//               sub-algorithms -- and the last-segment items (segment-segment closest points, a different code path)
+//               are queued: collected per CTA in shared memory, one global atomic per CTA.  Small code, 64 registers.
+//   k_lsc_rest  persistent grid over the two queues, homogeneous warps: last-segment items, then full GJK.
+// Queue entry: la << 14 | neighbour slot << 4 | segment.  Results go to fixed slots, so the (non-deterministic) queue
+// order cannot change them.
 #ifndef DLSC_LSC_THREADS
-#define DLSC_LSC_THREADS 64
+#define DLSC_LSC_THREADS 128
 #endif
-constexpr int kLscThreads = DLSC_LSC_THREADS;
 #ifndef DLSC_LSC_MINB
-#define DLSC_LSC_MINB 8
+#define DLSC_LSC_MINB 5
 #endif
+constexpr int kLscThreads = DLSC_LSC_THREADS, kLscRestThreads = 64;
+constexpr int kCntSeg = 14, kCntHard = 15;     // S.counters slots used as queue lengths (zeroed with the counters)
+__device__ __forceinline__ uint32_t lsc_pack(int la, int c, int m) { return ((uint32_t)la << 14) | ((uint32_t)c << 4) | (uint32_t)m; }
+
 __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float s_init[kMaxPts * 3];
-    extern __shared__ int s_dyn[];                // [K] neighbour indices | [K][5] neighbour radius, downwash, goal
+    __shared__ int s_nhard, s_base;
+    extern __shared__ int s_dyn[];                // [K] neighbour indices | [K][5] neighbour radius, downwash, goal | [K (M-1)] hard items
     int* s_nbr = s_dyn;
     float (*s_nj)[5] = reinterpret_cast<float (*)[5]>(s_dyn + P.K);
+    uint32_t* s_hard = reinterpret_cast<uint32_t*>(s_dyn + P.K * 6);
     const int M = P.M, npt = M * kP;
     const int la = blockIdx.x;
     const int cnt = S.nbr_cnt[la];
-    const float* rec_a = S.rec + (size_t)(P.begin + la) * P.rec;
     const int og = npt * 3 + 6;
+    if (threadIdx.x == 0) s_nhard = 0;
     for (int e = threadIdx.x; e < npt * 3; e += kLscThreads) s_init[e] = S.init_traj[(size_t)la * npt * 3 + e];
     for (int c = threadIdx.x; c < cnt; c += kLscThreads) {
         const int j = S.nbr_idx[(size_t)la * P.K + c];
@@ -300,30 +310,81 @@ __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid
         s_nj[c][0] = rec_j[og + 3]; s_nj[c][1] = rec_j[og + 4];
         s_nj[c][2] = rec_j[og]; s_nj[c][3] = rec_j[og + 1]; s_nj[c][4] = rec_j[og + 2];
     }
-    const V3 goal_a = v3_load(rec_a + og);
     const double r_a = S.radius[la], dw_a = S.downwash[la];
     __syncthreads();
     int it_sum = 0;
-    const int n_gjk = cnt * (M - 1), total = n_gjk + cnt;
-    for (int e = threadIdx.x; e < total; e += kLscThreads) {
-        int c, m;
-        if (e < n_gjk) { c = e / (M - 1); m = e - c * (M - 1); }
-        else { c = e - n_gjk; m = M - 1; }
+    const int n_gjk = cnt * (M - 1);
+    for (int e = threadIdx.x; e < n_gjk; e += kLscThreads) {
+        const int c = e / (M - 1), m = e - c * (M - 1);
         const size_t pr = (size_t)la * P.K + c;
+        const LscPair q = lsc_pair_consts(r_a, dw_a, s_nj[c][0], s_nj[c][1]);
+        gjk::D3 hc[kP], v;
+        lsc_gjk_load(s_init + m * kP * 3, S.pred_traj + ((size_t)s_nbr[c] * npt + m * kP) * 3, q, hc);
         int it = 0;
-        lsc_segment(P, s_init, S.pred_traj + (size_t)s_nbr[c] * npt * 3, goal_a, v3(s_nj[c][2], s_nj[c][3], s_nj[c][4]),
-                    r_a, dw_a, s_nj[c][0], s_nj[c][1], m, S.lsc_normal + (pr * M + m) * 3,
-                    S.lsc_d + (pr * M + m) * kP, S.lsc_anchor_last + pr * 3, &it, S.lsc_near + pr * M + m);
+        if (gjk::hull_origin_short<kP>(hc, v, &it)) {
+            lsc_gjk_finish(hc, v, q, m, S.lsc_normal + (pr * M + m) * 3, S.lsc_d + (pr * M + m) * kP, S.lsc_near + pr * M + m);
+            it_sum += it;
+        } else {
+            s_hard[atomicAdd(&s_nhard, 1)] = lsc_pack(la, c, m);
+        }
+    }
+    const int tot = __reduce_add_sync(0xffffffffu, it_sum);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(S.counters + 1, (unsigned long long)tot);
+    __syncthreads();
+    const int nh = s_nhard;
+    if (threadIdx.x == 0) {
+        s_base = nh ? (int)atomicAdd(S.counters + kCntHard, (unsigned long long)nh) : 0;
+        s_nhard = cnt ? (int)atomicAdd(S.counters + kCntSeg, (unsigned long long)cnt) : 0;     // reused: base of the segment queue
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nh; i += kLscThreads) S.lsc_queue[(size_t)P.NL * P.K + s_base + i] = s_hard[i];
+    for (int c = threadIdx.x; c < cnt; c += kLscThreads) S.lsc_queue[s_nhard + c] = lsc_pack(la, c, M - 1);
+}
+
+__global__ void __launch_bounds__(kLscRestThreads, 8) k_lsc_rest(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int M = P.M, npt = M * kP, og = npt * 3 + 6;
+    const int n_seg = (int)S.counters[kCntSeg], n_hard = (int)S.counters[kCntHard];
+    const int stride = gridDim.x * kLscRestThreads, t0 = blockIdx.x * kLscRestThreads + threadIdx.x;
+    for (int i = t0; i < n_seg; i += stride) {
+        const uint32_t e = S.lsc_queue[i];
+        const int la = (int)(e >> 14), c = (int)((e >> 4) & 1023u);
+        const size_t pr = (size_t)la * P.K + c;
+        const int j = S.nbr_idx[pr];
+        const float* rec_a = S.rec + (size_t)(P.begin + la) * P.rec;
+        const float* rec_j = S.rec + (size_t)j * P.rec;
+        const LscPair q = lsc_pair_consts(S.radius[la], S.downwash[la], rec_j[og + 3], rec_j[og + 4]);
+        lsc_last_segment(P, S.init_traj + (size_t)la * npt * 3, S.pred_traj + (size_t)j * npt * 3, v3_load(rec_a + og), v3_load(rec_j + og), q,
+                         S.lsc_normal + (pr * M + (M - 1)) * 3, S.lsc_d + (pr * M + (M - 1)) * kP, S.lsc_anchor_last + pr * 3,
+                         S.lsc_near + pr * M + (M - 1));
+    }
+    int it_sum = 0;
+    const uint32_t* hard = S.lsc_queue + (size_t)P.NL * P.K;
+    for (int i = t0; i < n_hard; i += stride) {
+        const uint32_t e = hard[i];
+        const int la = (int)(e >> 14), c = (int)((e >> 4) & 1023u), m = (int)(e & 15u);
+        const size_t pr = (size_t)la * P.K + c;
+        const int j = S.nbr_idx[pr];
+        const float* rec_j = S.rec + (size_t)j * P.rec;
+        const LscPair q = lsc_pair_consts(S.radius[la], S.downwash[la], rec_j[og + 3], rec_j[og + 4]);
+        gjk::D3 hc[kP];
+        lsc_gjk_load(S.init_traj + ((size_t)la * npt + m * kP) * 3, S.pred_traj + ((size_t)j * npt + m * kP) * 3, q, hc);
+        int it = 0;
+        const gjk::D3 v = gjk::hull_origin<kP>(hc, &it);
+        lsc_gjk_finish(hc, v, q, m, S.lsc_normal + (pr * M + m) * 3, S.lsc_d + (pr * M + m) * kP, S.lsc_near + pr * M + m);
         it_sum += it;
     }
     const int tot = __reduce_add_sync(0xffffffffu, it_sum);
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(S.counters + 1, (unsigned long long)tot);
 }
 
-void launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
-    k_lsc<<<P.NL, kLscThreads, (size_t)P.K * 6 * sizeof(int), st>>>(P, S);
+int launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
+    static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    k_lsc<<<P.NL, kLscThreads, (size_t)P.K * (6 + P.M - 1) * sizeof(int), st>>>(P, S);
+    k_lsc_rest<<<sms * 8, kLscRestThreads, 0, st>>>(P, S);
+    return 2;
 }
 
+// ------------------------------------------------------------------------------------------------
 // per-kernel parity entry (dlsc_gjk_batch): the device function k_lsc calls, one hull per thread, with the leaf tracer
 __global__ void __launch_bounds__(128) k_gjk_batch(const double* __restrict__ pts, int n, double* __restrict__ v_out,
                                                    int32_t* __restrict__ iters, int32_t* __restrict__ simplex,

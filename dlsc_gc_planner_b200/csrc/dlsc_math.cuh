@@ -318,6 +318,59 @@ DLSC_HD D3 hull_origin(const D3 (&c)[NP], int* iters_out) {
     NoTrace tr;
     return hull_origin<NP, NoTrace>(c, iters_out, tr);
 }
+// The same iteration restricted to simplices of one or two vertices: what the LSC kernel runs for EVERY hull
+// (k_lsc phase A).  The swarm's hulls are Bernstein control polygons of short trajectory pieces relative to a
+// neighbour -- nearly a point or a needle -- so the closest feature is a vertex or an edge for ~90 % of them and the
+// loop below ends through one of openGJK's exit tests after one to three support evaluations, without ever entering
+// S2D / S3D.  Operation for operation the prefix of hull_origin (same support order, same exit tests in the same
+// order, same S1D), so the returned v is bit-identical.  Returns false, with nothing to rely on, as soon as the
+// triangle sub-algorithm would be needed: the caller then runs hull_origin from scratch (phase B).
+template <int NP>
+DLSC_HD bool hull_origin_short(const D3 (&c)[NP], D3& v_out, int* iters_out) {
+    const double eps_rel = 1e-10, eps_tot = 1e-12;
+    const double eps_rel2 = eps_rel * eps_rel;
+    D3 v = c[0], sup = c[0], s0 = c[0];
+    double nwmax = 0;
+    int k = 0;
+    bool edge = false;                     // the simplex holds two vertices {s0, s1}: only the exit tests are left
+    for (;;) {
+        k++;
+        const D3 vm = d3(-v.x, -v.y, -v.z);
+        double maxs = dot(sup, vm);
+        int better = -1;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            const double sv = dot(c[i], vm);
+            if (sv > maxs) { maxs = sv; better = i; }
+        }
+        if (better != -1) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) if (i == better) sup = c[i];
+        }
+        const D3 w = d3(sup.x - 0.0, sup.y - 0.0, sup.z - 0.0);
+        const double vv = dot(v, v);
+        const double ex = vv - dot(v, w);
+        if (ex <= eps_rel * vv || ex < eps_tot) break;
+        if (vv < eps_rel2) break;
+        if (edge) return false;            // hull_origin would call sub2d here
+        // sub1d on {s0, w}
+        double tn;
+        if (hff1(w, s0)) {
+            v = proj_line(w, s0);
+            edge = true;
+            tn = dot(s0, s0); if (tn > nwmax) nwmax = tn;
+            tn = dot(w, w); if (tn > nwmax) nwmax = tn;
+        } else {
+            s0 = w; v = w;
+            tn = dot(s0, s0); if (tn > nwmax) nwmax = tn;
+        }
+        if (dot(v, v) <= eps_tot * eps_tot * nwmax) break;
+        if (k == 25) break;
+    }
+    v_out = v;
+    if (iters_out) *iters_out = k;
+    return true;
+}
 }  // namespace gjk
 
 // ------------------------------------------------------------------------------------------------

@@ -150,82 +150,106 @@ DLSC_HD bool is_pow2_f32(float f) {           // normal, positive, zero mantissa
 //   init_a : own initial trajectory [M][P][3], pred_j : neighbour's predicted trajectory
 //   r_j / dw_j arrive as float (agent_manager.cpp:256-258)
 //   normal_out[3], d_out[P]; anchor_last_out[3] written only for m == M-1
+// A GJK item (m < M-1) is load -> hull vs origin -> finish; the kernel runs the cheap two-vertex GJK for every item
+// and queues the few that need the triangle / tetrahedron sub-algorithms (k_lsc / k_lsc_rest), lsc_segment does both
+// in place (host simulator, subset stepping).
 // ------------------------------------------------------------------------------------------------
+struct LscPair { double collision_dist, downwash; float dwf; };
+DLSC_HD LscPair lsc_pair_consts(double r_a, double dw_a, float r_j_f, float dw_j_f) {
+    const double r_j = (double)r_j_f, dw_j = (double)dw_j_f;
+    LscPair q;
+    q.collision_dist = r_j + r_a;                                              // :605
+    q.downwash = (dw_a * r_a + dw_j * r_j) / (r_a + r_j);                      // :1153-1154
+    q.dwf = (float)q.downwash;                                                 // trajectory.cpp:214
+    return q;
+}
+// hull points c[i] = (double)(a_i - b_i) in the downwash frame; (float)c[i] recovers the float difference exactly
+DLSC_HD void lsc_gjk_load(const float* init_seg, const float* pred_seg, const LscPair& q, gjk::D3 (&c)[kP]) {
+    V3 wb[kP];
+    load_segment(pred_seg, wb);
+    // x / dwf == x * (1 / dwf) bit for bit when dwf is a power of two (every mission with equal downwash
+    // coefficients: 2.0); the IEEE division otherwise
+    const bool pow2 = is_pow2_f32(q.dwf);
+    const float inv_dwf = pow2 ? 1.0f / q.dwf : 0.0f;
+#pragma unroll
+    for (int i = 0; i < kP; i++) {
+        V3 a = v3_load(init_seg + i * 3); a.z = pow2 ? a.z * inv_dwf : a.z / q.dwf;
+        V3 b = wb[i]; b.z = pow2 ? b.z * inv_dwf : b.z / q.dwf;
+        const V3 rel = a - b;
+        c[i] = gjk::d3((double)rel.x, (double)rel.y, (double)rel.z);   // util.hpp:113-125
+    }
+}
+DLSC_HD void lsc_gjk_finish(const gjk::D3 (&c)[kP], const gjk::D3& v, const LscPair& q, int m, float* normal_out,
+                            double* d_out, float* slack_out) {
+    const V3 cp2 = v3(0.f, 0.f, 0.f) + v3((float)v.x, (float)v.y, (float)v.z);   // geometry.hpp:302
+    const V3 nt = v3_normalized(cp2);                                             // :1118
+    const float nz_w = (float)((double)nt.z / q.downwash);                        // :630-632
+    normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
+    double pmin = 1e300;
+#pragma unroll
+    for (int i = 0; i < kP; i++) {                                                // :636-637
+        const double pi = v3_dot(v3((float)c[i].x, (float)c[i].y, (float)c[i].z), nt);
+        d_out[i] = 0.5 * (q.collision_dist + pi);
+        if (m > 0 || i >= 3) pmin = (pi < pmin) ? pi : pmin;                      // rows of (m = 0, i < 3) do not exist
+    }
+    if (slack_out) {
+        // QP row screen (dlsc_qp_gi.cuh): smallest slack of the rows of this item at the agent's own initial
+        // trajectory, normalised by the world-frame |normal|: a row with normalised slack s cannot be violated
+        // by any x with |x_pt - init_pt| < s.  The slack of row i at the initial trajectory is
+        // n_w.(a_i - b_i) - d_i = p_i - (collision_dist + p_i) / 2 with p_i the dot product above (the world-frame
+        // normal against world-frame points equals the scaled normal against scaled points), so it costs nothing;
+        // float rounding (1e-6 m) is far inside the screen's margin (1e-3 m).
+        const float nn = sqrtf(nt.x * nt.x + nt.y * nt.y + nz_w * nz_w);
+        *slack_out = lsc_item_slack(0.5 * (pmin - q.collision_dist), (double)nn);
+    }
+}
+// last segment: goal-directed line segments, one LSC for all control points (:640-660)
+DLSC_HD void lsc_last_segment(const DevParams& P, const float* init_a, const float* pred_j, const V3& goal_a, const V3& goal_j,
+                              const LscPair& q, float* normal_out, double* d_out, float* anchor_last_out, float* slack_out) {
+    const float dwf = q.dwf;
+    const double downwash = q.downwash;
+    const int last = (P.M - 1) * kP + (kP - 1);
+    V3 o_last = v3_load(pred_j + last * 3); o_last.z = o_last.z / dwf;
+    V3 a_last = v3_load(init_a + last * 3); a_last.z = a_last.z / dwf;
+    V3 og = goal_j; og.z = (float)((double)og.z / downwash);                      // :1183-1187
+    V3 ag = goal_a; ag.z = (float)((double)ag.z / downwash);
+    const Closest cp = closest_segments(o_last, og, a_last, ag);                  // :642-644
+    const V3 nt = v3_normalized(cp.p2 - cp.p1);
+    const double dd = 0.5 * (q.collision_dist + cp.dist);                         // :650
+    const float nz_w = (float)((double)nt.z / downwash);
+    const float al_z = (float)((double)cp.p1.z * downwash);                       // :657
+    normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
+    anchor_last_out[0] = cp.p1.x; anchor_last_out[1] = cp.p1.y; anchor_last_out[2] = al_z;
+#pragma unroll
+    for (int i = 0; i < kP; i++) d_out[i] = dd;
+    if (slack_out) {      // same screen; rows n_w.(a_i - anchor) >= dd, evaluated in the scaled frame in float
+        const float inv = 1.0f / dwf;
+        float smin = 3.0e38f;
+#pragma unroll
+        for (int i = 0; i < kP; i++) {
+            const float* a = init_a + ((P.M - 1) * kP + i) * 3;
+            const float sl = (a[0] - cp.p1.x) * nt.x + (a[1] - cp.p1.y) * nt.y + (a[2] * inv - cp.p1.z) * nt.z;
+            smin = (sl < smin) ? sl : smin;
+        }
+        const float nn = sqrtf(nt.x * nt.x + nt.y * nt.y + nz_w * nz_w);
+        *slack_out = lsc_item_slack((double)smin - dd, (double)nn);
+    }
+}
 DLSC_HD void lsc_segment(const DevParams& P, const float* init_a, const float* pred_j, const V3& goal_a,
                          const V3& goal_j, double r_a, double dw_a, float r_j_f, float dw_j_f, int m,
                          float* normal_out, double* d_out, float* anchor_last_out, int* gjk_iters,
                          float* slack_out = nullptr) {
-    const double r_j = (double)r_j_f, dw_j = (double)dw_j_f;
-    const double collision_dist = r_j + r_a;                                   // :605
-    const double downwash = (dw_a * r_a + dw_j * r_j) / (r_a + r_j);           // :1153-1154
-    const float dwf = (float)downwash;                                         // trajectory.cpp:214
+    const LscPair q = lsc_pair_consts(r_a, dw_a, r_j_f, dw_j_f);
     if (m < P.M - 1) {
-        V3 wb[kP];                           // the neighbour's world-frame points, kept for the row screen below
-        gjk::D3 c[kP];                       // c[i] = (double)rel[i]: rel[i] is recovered exactly as (float)c[i]
-        load_segment(pred_j + m * kP * 3, wb);
-        // x / dwf == x * (1 / dwf) bit for bit when dwf is a power of two (every mission with equal downwash
-        // coefficients: 2.0); the IEEE division otherwise
-        const bool pow2 = is_pow2_f32(dwf);
-        const float inv_dwf = pow2 ? 1.0f / dwf : 0.0f;
-#pragma unroll
-        for (int i = 0; i < kP; i++) {
-            V3 a = v3_load(init_a + (m * kP + i) * 3); a.z = pow2 ? a.z * inv_dwf : a.z / dwf;
-            V3 b = wb[i]; b.z = pow2 ? b.z * inv_dwf : b.z / dwf;
-            const V3 rel = a - b;
-            c[i] = gjk::d3((double)rel.x, (double)rel.y, (double)rel.z);   // util.hpp:113-125
-        }
+        gjk::D3 c[kP], v;
+        lsc_gjk_load(init_a + m * kP * 3, pred_j + m * kP * 3, q, c);
         int it = 0;
-        const gjk::D3 v = gjk::hull_origin<kP>(c, &it);
+        if (!gjk::hull_origin_short<kP>(c, v, &it)) v = gjk::hull_origin<kP>(c, &it);
         if (gjk_iters) *gjk_iters = it;
-        const V3 cp2 = v3(0.f, 0.f, 0.f) + v3((float)v.x, (float)v.y, (float)v.z);   // geometry.hpp:302
-        const V3 nt = v3_normalized(cp2);                                             // :1118
-        const float nz_w = (float)((double)nt.z / downwash);                          // :630-632
-        normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
-        double pmin = 1e300;
-#pragma unroll
-        for (int i = 0; i < kP; i++) {                                                // :636-637
-            const double pi = v3_dot(v3((float)c[i].x, (float)c[i].y, (float)c[i].z), nt);
-            d_out[i] = 0.5 * (collision_dist + pi);
-            if (m > 0 || i >= 3) pmin = (pi < pmin) ? pi : pmin;                      // rows of (m = 0, i < 3) do not exist
-        }
-        if (slack_out) {
-            // QP row screen (dlsc_qp_gi.cuh): smallest slack of the rows of this item at the agent's own initial
-            // trajectory, normalised by the world-frame |normal|: a row with normalised slack s cannot be violated
-            // by any x with |x_pt - init_pt| < s.  The slack of row i at the initial trajectory is
-            // n_w.(a_i - b_i) - d_i = p_i - (collision_dist + p_i) / 2 with p_i the dot product above (the world-frame
-            // normal against world-frame points equals the scaled normal against scaled points), so it costs nothing;
-            // float rounding (1e-6 m) is far inside the screen's margin (1e-3 m).
-            const float nn = sqrtf(nt.x * nt.x + nt.y * nt.y + nz_w * nz_w);
-            *slack_out = lsc_item_slack(0.5 * (pmin - collision_dist), (double)nn);
-        }
+        lsc_gjk_finish(c, v, q, m, normal_out, d_out, slack_out);
     } else {
-        const int last = (P.M - 1) * kP + (kP - 1);
-        V3 o_last = v3_load(pred_j + last * 3); o_last.z = o_last.z / dwf;
-        V3 a_last = v3_load(init_a + last * 3); a_last.z = a_last.z / dwf;
-        V3 og = goal_j; og.z = (float)((double)og.z / downwash);                      // :1183-1187
-        V3 ag = goal_a; ag.z = (float)((double)ag.z / downwash);
-        const Closest cp = closest_segments(o_last, og, a_last, ag);                  // :642-644
-        const V3 nt = v3_normalized(cp.p2 - cp.p1);
-        const double dd = 0.5 * (collision_dist + cp.dist);                           // :650
-        const float nz_w = (float)((double)nt.z / downwash);
-        const float al_z = (float)((double)cp.p1.z * downwash);                       // :657
-        normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
-        anchor_last_out[0] = cp.p1.x; anchor_last_out[1] = cp.p1.y; anchor_last_out[2] = al_z;
-#pragma unroll
-        for (int i = 0; i < kP; i++) d_out[i] = dd;
+        lsc_last_segment(P, init_a, pred_j, goal_a, goal_j, q, normal_out, d_out, anchor_last_out, slack_out);
         if (gjk_iters) *gjk_iters = 0;
-        if (slack_out) {      // same screen; rows n_w.(a_i - anchor) >= dd, evaluated in the scaled frame in float
-            const float inv = 1.0f / dwf;
-            float smin = 3.0e38f;
-#pragma unroll
-            for (int i = 0; i < kP; i++) {
-                const float* a = init_a + ((P.M - 1) * kP + i) * 3;
-                const float sl = (a[0] - cp.p1.x) * nt.x + (a[1] - cp.p1.y) * nt.y + (a[2] * inv - cp.p1.z) * nt.z;
-                smin = (sl < smin) ? sl : smin;
-            }
-            const float nn = sqrtf(nt.x * nt.x + nt.y * nt.y + nz_w * nz_w);
-            *slack_out = lsc_item_slack((double)smin - dd, (double)nn);
-        }
     }
 }
 

@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Join an ncu report's per-SASS-instruction samples with nvdisasm line info -> hottest source lines.
-usage: ncu_hot_lines.py report.ncu-rep kernel_substr cubin_glob_substr [topn]"""
+usage: ncu_hot_lines.py report.ncu-rep mangled_kernel_substr cubin_glob_substr [topn]   (NCU_K=<regex on the demangled name> when they differ; BY_INS=1 sorts by instructions)"""
 import collections, csv, glob, os, re, subprocess, sys, tempfile
 rep, kern, cub = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "dlsc_gc_planner_b200", "libdlsc_b200.so")], cwd=tmp,
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("HOT_LIB", os.path.join(root, "dlsc_gc_planner_b200", "libdlsc_b200.so"))], cwd=tmp,
                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [f for f in glob.glob(tmp + "/*.cubin") if cub in f][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
@@ -20,7 +20,7 @@ for l in sass:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);", l)
     if m and inside:
         a2l[int(m.group(1), 16)] = (cur, m.group(2))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + os.environ.get("NCU_K", kern)], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.split("\n")))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
