@@ -292,7 +292,7 @@ __device__ __forceinline__ uint32_t lsc_pack(int la, int c, int m) { return ((ui
 
 __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float s_init[kMaxPts * 3];
-    __shared__ int s_nhard, s_base;
+    __shared__ int s_nhard, s_base, s_seg;
     extern __shared__ int s_dyn[];                // [K] neighbour indices | [K][5] neighbour radius, downwash, goal | [K (M-1)] hard items
     int* s_nbr = s_dyn;
     float (*s_nj)[5] = reinterpret_cast<float (*)[5]>(s_dyn + P.K);
@@ -334,11 +334,11 @@ __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid
     const int nh = s_nhard;
     if (threadIdx.x == 0) {
         s_base = nh ? (int)atomicAdd(S.counters + kCntHard, (unsigned long long)nh) : 0;
-        s_nhard = cnt ? (int)atomicAdd(S.counters + kCntSeg, (unsigned long long)cnt) : 0;     // reused: base of the segment queue
+        s_seg = cnt ? (int)atomicAdd(S.counters + kCntSeg, (unsigned long long)cnt) : 0;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nh; i += kLscThreads) S.lsc_queue[(size_t)P.NL * P.K + s_base + i] = s_hard[i];
-    for (int c = threadIdx.x; c < cnt; c += kLscThreads) S.lsc_queue[s_nhard + c] = lsc_pack(la, c, M - 1);
+    for (int c = threadIdx.x; c < cnt; c += kLscThreads) S.lsc_queue[s_seg + c] = lsc_pack(la, c, M - 1);
 }
 
 __global__ void __launch_bounds__(kLscRestThreads, 8) k_lsc_rest(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
