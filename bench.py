@@ -52,12 +52,30 @@ def parse():
     ap.add_argument("--settle", type=int, default=25, help="untimed rollout steps before the timed region")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mc-missions", type=int, default=128, help="Monte-Carlo leg: independent empty50 missions per GPU (0: skip)")
+    ap.add_argument("--mc-steps", type=int, default=20)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU record exchange: stores over NVLink peer memory (default) or NCCL all-gather")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------------
+def workload_config(args, cfg, m):
+    """The `config` object of the JSON line: a function of the command line only, so that both arms (--impl ours /
+    --impl reference) print the identical dict for the same flags."""
+    inv = 1.0 / cfg.world_res
+    dims = [int(np.floor(inv * float(np.float32(m.world_max[k])))) - int(np.floor(inv * float(np.float32(m.world_min[k])))) + 1
+            for k in range(3)]
+    ncell = dims[0] * dims[1] * dims[2]
+    return {"workload": "synthetic %d-agent 3D random-forest swarm (BASELINE configs[3]): M=%d n=%d dim=%d, SFC on a %dx%dx%d "
+                        "EDT grid, comm range %g, max_nbr %d" % (m.n_agents, cfg.M, cfg.n, cfg.dim, dims[0], dims[1], dims[2],
+                                                                  cfg.comm_range, args.max_nbr),
+            "agents": int(m.n_agents), "gpus": int(args.gpus), "agents_per_gpu": int(-(-m.n_agents // max(args.gpus, 1))),
+            "settle_steps": int(args.settle), "seed": 4096,
+            "parallelism": "agents sharded x%d, one all-gather of the agent records per step" % args.gpus,
+            "l2": "per-step working set (EDT grid %.0f MB + scratch) exceeds L2; inputs change every step" % (ncell * 16 / 1e6)}
+
+
 def make_world(args):
     cfg = missions.PlannerConfig.forest3d()
     h = args.half_extent if args.half_extent else 0.5 * float(np.sqrt(args.agents))
@@ -194,7 +212,7 @@ def pilot_rollout(cfg, m, args, device, n_steps):
     rec = {"wp": [], "pos": [], "vel": [], "acc": []}
     snap = None
     traj = None
-    fails = 0
+    fails, overflow = 0, 0
     for t in range(args.settle + n_steps):
         pos, vel, acc = pl.state()
         goal_cur = pl.goal()
@@ -208,9 +226,10 @@ def pilot_rollout(cfg, m, args, device, n_steps):
         traj = pl.traj()
         st = pl.status()
         fails += int(((st & capi.FAIL_MASK) != 0).sum())
+        overflow = max(overflow, int(((st & capi.NBR_OVERFLOW) != 0).sum()))
         pl.advance()
     snap["final_traj"] = traj
-    snap["nbr_overflow"] = int(((st & capi.NBR_OVERFLOW) != 0).sum())
+    snap["nbr_overflow"] = overflow
     snap["fails"] = fails
     snap["dist_to_goal"] = float(np.mean(np.max(np.abs(pl.state()[0] - goal_des), axis=1)))
     snap["edt"] = pl.get_edt()        # the same grid arrays for the CPU baseline (oracle)
@@ -258,6 +277,94 @@ def pair_nnz(cfg):
 
 
 # ------------------------------------------------------------------------------------------------------
+def run_montecarlo(args, dev, world, rank, dist):
+    """BASELINE configs[4]: Monte-Carlo batch of independent empty50 missions replanning in lockstep, `--mc-missions` per
+    GPU (1024 missions on 8 GPUs), weak scaling, no data-path collective (replicas only).  Mission g of the
+    batch is the reference's missions/empty50 #(g mod 30 + 1) with seeded goal noise (Mission::addNoise, max_noise 0.2,
+    seed g).  Same protocol as the main workload: untimed pilot rollout records the waypoints, the timed pass replays them
+    on the device (plan -> advance chained, CUDA events, max over ranks)."""
+    import torch
+    z = np.load(os.path.join(ROOT, "tests", "golden", "missions_all.npz"))
+    cfg = missions.PlannerConfig.empty()
+
+    def base(idx):
+        g = lambda f: z["empty50/%d/%s" % (idx, f)]
+        return missions.Mission(g("world_min"), g("world_max"), g("start"), g("goal"), g("radius"), g("downwash"), g("max_vel"),
+                                g("max_acc"), g("nominal_vel"), g("boxes"))
+    nm = args.mc_missions
+    ms = [missions.add_goal_noise(base((rank * nm + i) % 30 + 1), 0.2, cfg.dim, seed=rank * nm + i) for i in range(nm)]
+    batch, group = missions.concat_missions(ms)
+    n_each = ms[0].n_agents
+    N, Kn = batch.n_agents, n_each - 1
+    W, T, settle = 3, args.mc_steps, 10
+
+    def planner():
+        pl = capi.SwarmPlanner(cfg, batch, max_nbr=Kn, device=dev.index)
+        pl.set_groups(group)
+        return pl
+    pl = planner()
+    wp = pl.start.copy()
+    goal_des = batch.goal.astype(np.float32)
+    traj, rec_wp, snap, fails = None, [], None, 0
+    for t in range(settle + W + T):
+        pos, vel, acc = pl.state()
+        goal_cur = pl.goal()
+        for i in range(nm):
+            q = slice(i * n_each, (i + 1) * n_each)
+            wp[q] = missions.next_waypoints(wp[q], goal_cur[q], goal_des[q], None if traj is None else traj[q], pos[q], cfg)
+        if t == settle:
+            snap = {"records": pl.get_records(), "acc": acc.copy(), "seq": pl.seq}
+        if t >= settle:
+            rec_wp.append(wp.copy())
+        pl.set_agents(waypoint=wp)
+        pl.plan()
+        traj = pl.traj()
+        fails += int(((pl.status() & capi.FAIL_MASK) != 0).sum())
+        pl.advance()
+    final = traj
+    pl.close()
+    pl = planner()
+    pl.set_stream(torch.cuda.current_stream().cuda_stream)
+    wp_dev = torch.from_numpy(np.ascontiguousarray(np.array(rec_wp))).to(dev)
+
+    def restore_mc():
+        pl.set_records(0, snap["records"]); pl.set_agents(acc=snap["acc"]); pl.seq = snap["seq"]
+
+    def run(n0, n):
+        for t in range(n0, n0 + n):
+            pl.set_waypoints_device(wp_dev[t].data_ptr())
+            pl.plan(); pl.advance()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    restore_mc(); barrier()
+    run(0, W); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(W, T); e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    exact = bool(np.array_equal(pl.traj(), final))
+    restore_mc(); torch.cuda.synchronize()
+    run(0, W); pl.enable_timing(True); run(W, T); torch.cuda.synchronize()
+    stage_ms, _ = pl.timings()
+    pl.enable_timing(False)
+    pl.close()
+    tt = torch.tensor([ms_total, float(fails), 1.0 if exact else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mn = tt.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        ms_total, exact = float(mx[0].item()), bool(mn[2].item() > 0.5)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        fails = int(sm[1].item())
+    return {"workload": "Monte-Carlo batch (BASELINE configs[4]): %d independent empty50 missions per GPU x %d GPUs = %d missions, "
+                        "%d agents, K = %d, M = 5, no map, goal noise 0.2, lockstep replans" % (nm, world, nm * world, N * world, Kn),
+            "value": N * world * T / (ms_total * 1e-3), "unit": UNIT, "ms_per_step": ms_total / T, "steps": T, "warmup": W,
+            "scaling": "weak", "missions": nm * world, "agents": N * world, "stages_ms": stage_ms, "qp_failsafe_agents": fails,
+            "replay_exact": exact}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -280,6 +387,9 @@ def run_ours(args):
     sl = slice(begin, begin + NL)
 
     rec, snap = pilot_rollout(cfg, m, args, dev.index, W + K)
+    if snap["nbr_overflow"]:
+        raise SystemExit("bench: %d agents had more than --max-nbr %d neighbours in range: their dropped neighbours would be "
+                         "missing collision constraints (the reference has no cap); raise --max-nbr" % (snap["nbr_overflow"], args.max_nbr))
     edt = snap["edt"]
     pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr, begin=begin, n_local=NL, device=dev.index)
     pl.build_edt(m.boxes)
@@ -398,15 +508,15 @@ def run_ours(args):
     for t in range(K):
         e2e_step(W + t)
     e1.record()
+    t_host = (time.perf_counter() - t_host0) * 1e3        # the last dlsc_get_traj of the loop has synchronised the stream
     barrier()
     clocks.end()
     clk = clocks.stop()
-    t_host = (time.perf_counter() - t_host0) * 1e3
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
     tt = torch.tensor([e2e_ms, t_host], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_ms = float(tt[0].item())
+    e2e_ms, t_host = float(tt[0].item()), float(tt[1].item())
     e2e_exact = bool(np.array_equal(traj_h, snap["final_traj"][sl]))
     h2d = int(4 * N * 12)
     d2h = int(N * cfg.M * (cfg.n + 1) * 12)
@@ -423,17 +533,14 @@ def run_ours(args):
             "metric": METRIC, "value": N * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "p50_step_ms": statistics.median(step_ms), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic %d-agent 3D random-forest swarm (BASELINE configs[3]): M=10 n=5 dim=3, "
-                                   "SFC on a %dx%dx%d EDT grid, comm range 3, max_nbr %d" % (
-                                       N, edt[2][0], edt[2][1], edt[2][2], args.max_nbr),
-                       "agents": N, "agents_per_gpu": NL, "settle_steps": args.settle, "parallelism": "agents sharded x%d, %s of %d-float records per step" % (
-                           world, {"p2p": "peer-memory all-gather over NVLink (dlsc_exchange_records)",
-                                   "nccl": "NCCL all-gather", "single": "no exchange"}.get(exchange.mode, exchange.mode),
-                           pl.rec_floats),
-                       "l2": "per-step working set (EDT grid %.0f MB + scratch) exceeds L2; inputs change every step" % (
-                           edt[0].size * 16 / 1e6)},
-            "e2e": {"value": N * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / K, "replay_exact": e2e_exact},
+            "config": workload_config(args, cfg, m),
+            "exchange": {"p2p": "peer-memory all-gather over NVLink (dlsc_exchange_records), %d-float records" % pl.rec_floats,
+                         "nccl": "NCCL all-gather", "single": "no exchange (1 GPU)"}.get(exchange.mode, exchange.mode),
+            # e2e: host wall clock around the K steps (host buffers in, host buffers out, every step); the CUDA-event time of
+            # the same region is reported beside it
+            "e2e": {"value": N * K / (t_host * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_host / K, "device_ms_per_step": e2e_ms / K, "clock": "host perf_counter, max over ranks",
+                    "replay_exact": e2e_exact},
             "gpu_launches": int(launches),
             "roofline": None,
             "stages_ms": stage_ms, "stages_note": "second pass over the same %d steps with CUDA events around every stage "
@@ -464,20 +571,31 @@ def run_ours(args):
                  "traffic": traffic.get(kernel), "work_per_launch": work, "kernel_ms": ms}
             d.update(extra)
             return d
+        # LSC: SURVEY s8(d) gives bytes AND flops per agent; with the measured GJK depth (~1.5 iterations per hull) the
+        # intensity is ~1.5 flop/B, far below the machine balance (36 TFLOP/s : 6.4 TB/s), so the HBM roof is the one that
+        # bounds it; the FP64 fraction is reported beside it.  Bytes: read (K+1) M P 12 + K 36, write K M (12 + 8 P + 4).
+        Mq, Pq = cfg.M, cfg.n + 1
+        lsc_bytes = (pairs / n_prof + NL) * Mq * Pq * 12.0 + (pairs / n_prof) * 36.0 + (pairs / n_prof) * Mq * (12.0 + 8.0 * Pq + 4.0)
+        sfc_traffic = traffic.get("k_sfc")
         rls = {
-            "sfc": rl("k_sfc", "hbm", sfc_bytes, stage_ms["sfc"], hbm, "GB/s", 1e9, {
+            "sfc": rl("k_sfc", "latency", sfc_traffic or 0.0, stage_ms["sfc"], hbm, "GB/s", 1e9, {
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks.get("hbm_gbs") else "fallback",
-                "algorithmic": "SURVEY s8(d): 16 B x lattice vertices of the initial box and of every tested slab (the reference's "
-                               "redundant whole-box rechecks excluded)",
-                "note": "the kernel answers %.0f%% of its box tests with an O(1) summed-area query and the rest from a 1-byte-per-"
-                        "vertex mask, so it moves far fewer bytes than the 16-byte-record figure (see traffic); it is bound by the "
-                        "serial greedy chain of ~70 tests per agent, not by HBM" % (100.0 * sfc_sat / max(sfc_tests, 1))}),
-            "lsc": rl("k_lsc", "fp64", lsc_fl, stage_ms["lsc"], peak_fp64, "TFLOP/s", 1e12, {
-                "peak_source": "dlsc_measure_fp64_peak (DFMA chains, measured in this run; MEASURED_PEAKS.json has no FP64 figure)"}),
-            "qp": rl("k_qp_gi", "fp64", flops, qp_ms, peak_fp64, "TFLOP/s", 1e12, {
+                "algorithmic": "achieved = the kernel's measured DRAM traffic (profiles/traffic.json, ncu dram__bytes) / its "
+                               "CUDA-event time: the kernel answers %.1f%% of its box tests with an 8-corner summed-area query and "
+                               "the rest from a 1-byte-per-vertex mask, so SURVEY s8(d)'s 16 B x lattice-vertex figure "
+                               "(%.0f MB per step here) is not what it moves" % (100.0 * sfc_sat / max(sfc_tests, 1), sfc_bytes / 1e6),
+                "note": "bound by the serial greedy chain (~%d dependent box tests per agent, each a few hundred scalar "
+                        "instructions of control arithmetic), not by HBM or a pipe" % round(sfc_tests / n_prof / max(NL, 1))}),
+            "lsc": rl("k_lsc+k_lsc_rest", "hbm", lsc_bytes, stage_ms["lsc"], hbm, "GB/s", 1e9, {
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks.get("hbm_gbs") else "fallback",
+                "fp64": {"achieved": lsc_fl / (stage_ms["lsc"] * 1e-3) / 1e12 if stage_ms["lsc"] > 0 else 0.0, "peak": peak_fp64,
+                         "unit": "TFLOP/s", "frac": (lsc_fl / (stage_ms["lsc"] * 1e-3) / 1e12 / peak_fp64) if stage_ms["lsc"] > 0 and peak_fp64 else None,
+                         "work_per_launch": lsc_fl}}),
+            "qp": rl("k_qp_fast+k_qp_gi", "fp64", flops, qp_ms, peak_fp64, "TFLOP/s", 1e12, {
                 "peak_source": "dlsc_measure_fp64_peak (DFMA chains, measured in this run; MEASURED_PEAKS.json has no FP64 figure)"}),
         }
-        dom = max(("sfc", "lsc", "qp"), key=lambda k: stage_ms[k])
+        rls["lsc"]["traffic"] = (traffic.get("k_lsc") or 0) + (traffic.get("k_lsc_rest") or 0) or None
+        dom = max(("lsc", "qp"), key=lambda k: stage_ms[k])      # the dominant kernel with a throughput roof (k_sfc is latency bound)
         out["roofline"] = rls[dom]
         out["rooflines_other"] = {k: v for k, v in rls.items() if k != dom}
         if world == 1 and not args.no_cpu_baseline:
@@ -488,6 +606,10 @@ def run_ours(args):
             pl.p2p_disconnect()
         dist.barrier()
     pl.close()
+    if args.mc_missions > 0:
+        mc = run_montecarlo(args, dev, world, rank, dist)
+        if rank == 0:
+            out["montecarlo"] = mc
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -523,91 +645,124 @@ def oracle_swarm(cfg, m, edt, snap, rec, args, n_threads):
     return sw
 
 
-def cpu_baseline(cfg, m, edt, rec, snap, args, steps=1):
-    cores = os.cpu_count() or 1
-    sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
+def _timed_replans(cfg, m, edt, snap, rec, args, n_threads, seconds, n_cap=None):
+    """Repeat the replan of agents [0, n) from the snapshot state until ~`seconds` of wall time are timed."""
     N = m.n_agents
-    probe = min(N, 4 * cores)
+    sw = oracle_swarm(cfg, m, edt, snap, rec, args, n_threads)
+    probe = min(N, 4 * n_threads)
     seq0 = sw.seq
     t0 = time.perf_counter(); sw.step(0, probe); t_probe = time.perf_counter() - t0
     sw.seq = seq0
-    n = int(min(N, max(probe, args.cpu_seconds / max(t_probe / probe, 1e-9))))
-    n = max(cores, (n // cores) * cores)
-    # repeat the same replan (state restored, untimed, before each pass) until ~cpu_seconds of CPU work are timed
+    n = int(min(N, max(probe, seconds / max(t_probe / probe, 1e-9))))
+    n = max(n_threads, (n // n_threads) * n_threads)
+    if n_cap:
+        n = min(n, n_cap)
     t, reps, stage = 0.0, 0, None
-    while reps == 0 or (t < args.cpu_seconds and reps < 64):
-        sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
+    while reps == 0 or (t < seconds and reps < 64):
+        sw = oracle_swarm(cfg, m, edt, snap, rec, args, n_threads)
         t0 = time.perf_counter(); sw.step(0, n); t += time.perf_counter() - t0
         reps += 1
         ss = np.array([float(x) for x in sw.stage_seconds])
         stage = ss if stage is None else stage + ss
-    ok = int(((sw.status[:n] & capi.FAIL_MASK) == 0).sum())
+    ok = int(((sw.status[:n] & FAIL_BITS) == 0).sum())
+    return n, reps, t, stage, ok, sw
+
+
+FAIL_BITS = 1 | 2 | 4 | 8     # QP_MAXITER | QP_NUMERIC | SFC_INIT_FAILED | GOAL_INFEASIBLE (include/dlsc_b200.h)
+
+
+def highs_qp_leg(cfg, m, sw, n_qp=16):
+    """BASELINE.md s3 leg 3: the QP stage of sample agents solved by an independent CPU solver (HiGHS through scipy, the
+    x-space restatement of tests/qp_highs.py) -- mean seconds per solve, build time excluded."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import qp_highs
+        times, status = [], []
+        for a in range(min(n_qp, m.n_agents)):
+            K = int(sw.nbr_cnt[a])
+            qp = qp_highs.build_qp(cfg.M, cfg.n, cfg.dim, cfg.dt, cfg.w_control, cfg.w_terminal, m.world_min, m.world_max,
+                                   cfg.comm_range, sw.pos[a], sw.vel[a], sw.acc[a], sw.goal_cur[a], sw.waypoint[a], sw.radius[a],
+                                   sw.max_vel[a], sw.max_acc[a], sw.nominal_vel[a], sfc=sw.sfc[a] if cfg.use_sfc else None,
+                                   lsc_normal=sw.lsc_normal[a, :K], lsc_anchor=sw.lsc_anchor[a, :K], lsc_d=sw.lsc_d[a, :K])
+            t0 = time.perf_counter()
+            _, _, st = qp_highs.solve_highs(qp, time_limit=5)
+            times.append(time.perf_counter() - t0); status.append(st)
+        return {"ms_per_qp": 1e3 * float(np.mean(times)), "qps": len(times), "optimal": int(sum(x == "Optimal" for x in status)),
+                "what": "HiGHS convex-QP solve (1 thread) of the first %d agents' QPs at the first timed step, rows built from the "
+                        "same LSC / SFC constraints; model build excluded" % len(times)}
+    except Exception as e:      # scipy without the private HiGHS binding
+        return {"unavailable": repr(e)[:200]}
+
+
+def cpu_baseline(cfg, m, edt, rec, snap, args, steps=1):
+    """The three CPU legs BASELINE.md s3 promises: all host threads (one agent per thread), one thread (the reference's
+    real execution model, src/multi_sync_simulator.cpp:516-524), and HiGHS on the QP stage."""
+    cores = os.cpu_count() or 1
+    N = m.n_agents
+    n, reps, t, stage, ok, sw = _timed_replans(cfg, m, edt, snap, rec, args, cores, args.cpu_seconds)
+    n1, reps1, t1, stage1, ok1, _ = _timed_replans(cfg, m, edt, snap, rec, args, 1, min(6.0, args.cpu_seconds))
     return {"value": n * reps / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "agents [0,%d) of the same %d-agent swarm at the first timed step, one replan each, one agent per "
                       "thread on %d threads, repeated %d times from the same state (oracle/ C++ port; the reference itself "
                       "needs ROS+CPLEX and cannot run here); %d/%d QPs converged; %.1f s timed" % (n, N, cores, reps, ok, n, t),
-            "stage_seconds": [float(x) for x in stage]}
+            "stage_seconds": [float(x) for x in stage],
+            "serial_1_thread": {"value": n1 * reps1 / t1, "unit": UNIT, "cores": 1, "ms_per_agent_replan": 1e3 * t1 / (n1 * reps1),
+                                "sample": "agents [0,%d), %d passes, %.1f s timed; stage seconds (predict+nbr, LSC, SFC, goal, QP): %s" % (
+                                    n1, reps1, t1, ", ".join("%.3f" % x for x in stage1))},
+            "highs_qp": highs_qp_leg(cfg, m, sw),
+            "reference_logged": {"ms_per_agent_replan": 12.17, "unit": "ms", "what": "the reference's own log (maze10_dense, 10 agents, "
+                                 "2-D, CPLEX, unknown CPU): log/summary_DLSCGC_10agents.csv planning_time_average"}}
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path (here: the oracle port, see DESIGN.md --
-    the literal ROS + CPLEX build is impossible in this image) on all host threads, bounded sample per step."""
+    """Reference arm: the reference's CPU implementation of the path on the box's host cores.  The literal ROS + CPLEX build
+    cannot exist in this image, so it is the oracle port (oracle/), one agent per thread on every host thread.  It never
+    loads libdlsc_b200.so: the swarm is settled with the oracle itself (same seeded world, same waypoint provider), then
+    W + K successive replan steps of the whole swarm (or of a bounded agent sample when a step would take too long) are
+    timed with the host clock."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import oracle_py as O
     W, K = max(args.warmup, 1), args.steps
     cfg, m = make_world(args)
     N = m.n_agents
-    # state at the start of the timed region: produced by the GPU pilot when a GPU is there, else a cold start
-    try:
-        lib = capi.load_library()
-        have_gpu = lib.dlsc_device_count() > 0
-    except Exception:
-        have_gpu = False
-    if have_gpu:
-        rec, snap = pilot_rollout(cfg, m, args, 0, 1)
-        edt = snap["edt"]
-    else:
-        from oracle import oracle_py as O
-        O.build()
-        e = O.edt_build(oracle_params_of(cfg, m), m.boxes)
-        edt = (e.dist, e.obst, e.dims, e.min_key)
-        start = m.start.astype(np.float32)
-        o = cfg.M * (cfg.n + 1) * 3
-        records = np.zeros((N, o + 12), np.float32)
-        records[:, :o] = np.tile(start, (1, cfg.M * (cfg.n + 1)))
-        records[:, o:o + 3] = start; records[:, o + 6:o + 9] = start
-        snap = {"records": records, "sfc": np.zeros((N, cfg.M, 6), np.float32), "acc": np.zeros((N, 3), np.float32), "seq": 0}
-        rec = {"wp": start[None]}
     cores = os.cpu_count() or 1
-    sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
-    if not have_gpu:
-        sw.sfc_init[...] = 1
-    probe = min(N, 4 * cores)
-    t0 = time.perf_counter(); sw.step(0, probe); t_probe = time.perf_counter() - t0
-    budget = 120.0 / (W + K)                              # whole run within a few minutes
-    n = int(min(N, max(cores, budget / max(t_probe / probe, 1e-9))))
-    n = max(cores, (n // cores) * cores)
-    times = []
-    for s in range(W + K):
-        sw = oracle_swarm(cfg, m, edt, snap, rec, args, cores)
-        if not have_gpu:
-            sw.sfc_init[...] = 1
-        t0 = time.perf_counter(); sw.step(0, n); dt = time.perf_counter() - t0
-        if s >= W:
+    O.build()
+    p = oracle_params_of(cfg, m)
+    e = O.edt_build(p, m.boxes)
+    sw = O.Swarm(p, m.start, m.goal, m.radius, m.downwash, m.max_vel, m.max_acc, m.nominal_vel, edt=e,
+                 max_nbr=args.max_nbr, n_threads=cores)
+    occupied = missions.occupied_nodes(m.boxes, cfg.grid_res)
+    goal_des = m.goal.astype(np.float32)
+    t_start = time.perf_counter()
+    n = N                                                # every step replans the whole swarm: a consistent rollout
+    traj = None
+    times, fails = [], 0
+    for s in range(args.settle + W + K):
+        sw.waypoint = missions.next_waypoints(sw.waypoint, sw.goal_cur, goal_des, traj, sw.pos, cfg, occupied)
+        t0 = time.perf_counter()
+        st = sw.step()
+        dt = time.perf_counter() - t0
+        traj = sw.traj.copy()
+        sw.advance()
+        if s >= args.settle + W:
             times.append(dt)
+            fails += int(((st & FAIL_BITS) != 0).sum())
     total = sum(times)
     val = n * K / total
-    sample = ("each step: agents [0,%d) of the %d-agent swarm, one replan each, one agent per thread on %d host threads" % (
-        n, N, cores))
+    sample = ("%d settle + %d warm-up + %d timed successive steps of the %d-agent swarm, %s replanned per step, one agent per "
+              "thread on %d host threads (oracle/ C++ port: LSC with the openGJK restatement, SFC, goal, dense interior-point "
+              "QP); %d QP failsafes; %.1f s wall in total" % (
+                  args.settle, W, K, N, "all agents", cores, fails, time.perf_counter() - t_start))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": total / K * 1e3 * (N / n), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %d-agent 3D random-forest swarm (BASELINE configs[3])" % N, "agents": N},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, cfg, m),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "ms_per_step is extrapolated from the bounded sample to the full swarm",
+        "note": "kind \"port\": the reference's own build needs ROS, octomap, dynamicEDT3D and CPLEX (absent, no network); "
+                "ms_per_step is extrapolated to the full swarm when a sample was replanned",
     }))
 
 

@@ -20,7 +20,10 @@ LIB_PATH = os.environ.get("DLSC_B200_LIB") or os.path.join(_HERE, "libdlsc_b200.
 OK, QP_MAXITER, QP_NUMERIC, SFC_INIT_FAILED, GOAL_INFEASIBLE, SFC_REUSED, NBR_OVERFLOW, QP_IPM_USED = 0, 1, 2, 4, 8, 16, 32, 64
 STAGE_PREDICT, STAGE_NBR, STAGE_LSC, STAGE_SFC, STAGE_GOAL, STAGE_QP, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
 STAGE_NAMES = ("predict", "nbr", "lsc", "sfc", "goal", "qp")
-FAIL_MASK = QP_MAXITER | QP_NUMERIC | SFC_INIT_FAILED | GOAL_INFEASIBLE
+# a replan with one of these bits must not be flown as planned: QP failures fall back to the initial trajectory inside the
+# library, the others are errors of the step; NBR_OVERFLOW means collision constraints against the neighbours beyond
+# max_nbr are missing (the reference has no cap, multi_sync_simulator.cpp:481-503)
+FAIL_MASK = QP_MAXITER | QP_NUMERIC | SFC_INIT_FAILED | GOAL_INFEASIBLE | NBR_OVERFLOW
 
 
 class DlscParams(C.Structure):
@@ -58,7 +61,7 @@ EXPORTS = (
     "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
     "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups dlsc_edt_dims dlsc_build_edt "
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
-    "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch").split()
+    "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build").split()
 
 
 def build_library(force=False):
@@ -96,7 +99,12 @@ def load_library(path=None):
             if not os.path.exists(LIB_PATH):
                 raise RuntimeError("libdlsc_b200.so is not built: run `python -c 'import __graft_entry__ as g; "
                                    "g.build()'` or `make -C dlsc_gc_planner_b200/csrc` (no CPU fallback exists)")
-            _LIB = _declare(C.CDLL(LIB_PATH))
+            lib = _declare(C.CDLL(LIB_PATH))
+            if not hasattr(lib, "dlsc_cuda_build"):
+                # DLSC_B200_LIB may only name another build of the CUDA library (A/B variants), never a CPU stand-in
+                raise RuntimeError("%s is not a CUDA build of libdlsc_b200 (no dlsc_cuda_build symbol): the product has "
+                                   "no CPU path" % LIB_PATH)
+            _LIB = lib
         return _LIB
     return _declare(C.CDLL(path))
 

@@ -51,7 +51,9 @@ struct dlsc_ctx {
         void* block = nullptr;                     // own block (cudaMalloc, IPC-exported)
         void* peer_block[kP2PMaxWorld] = {};       // mapped blocks of the peers (own entry = block)
         unsigned* done = nullptr;
-        int* err = nullptr;
+        int* err = nullptr;                        // device view of the error flag (mapped pinned host memory)
+        volatile int* err_host = nullptr;          // host view: polled without synchronising
+        bool failed = false;                       // sticky
     } p2p;
     double edt_build_ms = 0.0;         // device time of the last dlsc_build_edt* (the three EDT passes)
     double margin_host = 0.0;          // radius of the first local agent (all BASELINE missions: 0.15 for every agent)
@@ -89,6 +91,8 @@ extern "C" {
 
 const char* dlsc_last_error(void) { return g_err.c_str(); }
 int dlsc_abi_version(void) { return DLSC_ABI_VERSION; }
+// only the CUDA build exports this: the Python loader refuses any other library handed to it as the product
+int dlsc_cuda_build(void) { return 12090; }
 int dlsc_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -266,7 +270,8 @@ void dlsc_destroy(dlsc_ctx* c) {
     if (c->p2p.exported) {
         for (int r = 0; r < c->p2p.world; r++)
             if (c->p2p.on && r != c->p2p.rank && c->p2p.peer_block[r]) cudaIpcCloseMemHandle(c->p2p.peer_block[r]);
-        cudaFree(c->p2p.block); cudaFree(c->p2p.done); cudaFree(c->p2p.err);
+        cudaFree(c->p2p.block); cudaFree(c->p2p.done);
+        if (c->p2p.err_host) cudaFreeHost((void*)c->p2p.err_host);
     }
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -476,6 +481,21 @@ int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
     if (p->max_vel) CK(cudaMemcpyAsync(c->S.max_vel, p->max_vel, b, cudaMemcpyHostToDevice, c->stream));
     if (p->max_acc) CK(cudaMemcpyAsync(c->S.max_acc, p->max_acc, b, cudaMemcpyHostToDevice, c->stream));
     if (p->nominal_vel) CK(cudaMemcpyAsync(c->S.nominal_vel, p->nominal_vel, b, cudaMemcpyHostToDevice, c->stream));
+    if (p->radius || p->downwash) {
+        // the other agents read radius / downwash out of the exchanged records (through float, agent_manager.cpp:256-258):
+        // keep the local records in step with the properties whatever the call order relative to dlsc_reset
+        std::vector<float> f((size_t)c->P.NL);
+        float* dst = c->S.rec + (size_t)c->P.begin * c->P.rec;
+        if (p->radius) {
+            for (int i = 0; i < c->P.NL; i++) f[i] = (float)p->radius[i];
+            CK(cudaMemcpy2DAsync(dst + c->rl.radius, (size_t)c->P.rec * sizeof(float), f.data(), 4, 4, c->P.NL, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        if (p->downwash) {
+            for (int i = 0; i < c->P.NL; i++) f[i] = (float)p->downwash[i];
+            CK(cudaMemcpy2DAsync(dst + c->rl.downwash, (size_t)c->P.rec * sizeof(float), f.data(), 4, 4, c->P.NL, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -552,8 +572,13 @@ int dlsc_p2p_export(dlsc_ctx* c, void* handle64) {
         CK(cudaMemset(c->p2p.block, 0, bytes));
         CK(cudaMalloc(&c->p2p.done, sizeof(unsigned)));
         CK(cudaMemset(c->p2p.done, 0, sizeof(unsigned)));
-        CK(cudaMalloc(&c->p2p.err, sizeof(int)));
-        CK(cudaMemset(c->p2p.err, 0, sizeof(int)));
+        {   // error flag in mapped pinned memory: the wait kernel raises it, the host reads it without a synchronisation
+            int* h = nullptr;
+            CK(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
+            *h = 0;
+            c->p2p.err_host = h;
+            CK(cudaHostGetDevicePointer((void**)&c->p2p.err, h, 0));
+        }
         CK(cudaStreamSynchronize(c->stream));
         const size_t nb = (size_t)c->P.N * c->P.rec * sizeof(float);
         CK(cudaMemcpy(p2p_buffer(c, c->p2p.block, 0), c->S.rec, nb, cudaMemcpyDeviceToDevice));
@@ -576,15 +601,30 @@ int dlsc_p2p_connect(dlsc_ctx* c, int world, int rank, const void* handles) {
         if (r == rank) { c->p2p.peer_block[r] = c->p2p.block; continue; }
         cudaIpcMemHandle_t h;
         memcpy(&h, static_cast<const char*>(handles) + (size_t)r * 64, 64);
-        CK(cudaIpcOpenMemHandle(&c->p2p.peer_block[r], h, cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t e = cudaIpcOpenMemHandle(&c->p2p.peer_block[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {                      // unmap what was opened so far: nothing is left half connected
+            for (int q = 0; q < r; q++)
+                if (q != rank && c->p2p.peer_block[q]) { cudaIpcCloseMemHandle(c->p2p.peer_block[q]); c->p2p.peer_block[q] = nullptr; }
+            c->p2p.peer_block[r] = nullptr;
+            g_err = std::string("dlsc_p2p_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+            return -1;
+        }
     }
     c->p2p.world = world; c->p2p.rank = rank; c->p2p.on = true;
+    return 0;
+}
+// a peer that missed an exchange makes every later step of this context fail (the records it would plan against are stale)
+static int p2p_check(dlsc_ctx* c) {
+    if (!c->p2p.on || !c->p2p.err_host) return 0;
+    if (*c->p2p.err_host) { c->p2p.failed = true; }
+    if (c->p2p.failed) return fail("record exchange failed: a peer did not publish its records within the timeout (dlsc_p2p_status)");
     return 0;
 }
 int dlsc_exchange_records(dlsc_ctx* c) {
     if (!c) return fail("null ctx");
     if (!c->p2p.on) return fail("dlsc_exchange_records: not connected (dlsc_p2p_connect)");
     CK(cudaSetDevice(c->device));
+    if (p2p_check(c)) return -1;                   // a timed-out exchange is never followed by a buffer switch
     auto& X = c->p2p;
     const int next = X.cur ^ 1;
     float* dst[kP2PMaxWorld]; unsigned long long* flag[kP2PMaxWorld];
@@ -617,10 +657,9 @@ int dlsc_p2p_status(dlsc_ctx* c) {
     if (!c) return fail("null ctx");
     if (!c->p2p.exported) return 0;
     CK(cudaSetDevice(c->device));
-    int e = 0;
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(&e, c->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (e) return fail("dlsc_p2p_status: a peer did not publish its records within the timeout");
+    if (c->p2p.err_host && *c->p2p.err_host) c->p2p.failed = true;
+    if (c->p2p.failed) return fail("dlsc_p2p_status: a peer did not publish its records within the timeout");
     return 0;
 }
 
@@ -674,6 +713,7 @@ int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
 
 static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const DevState& Sr) {
     CK(cudaSetDevice(c->device));
+    if (p2p_check(c)) return -1;
     if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && !c->have_edt) return fail("dlsc_run_stages: use_sfc set but no EDT grid (dlsc_set_edt)");
     if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && c->mask_dirty && build_vertex_mask(c)) return -1;
     DevState Sfix = Sr;

@@ -293,31 +293,31 @@ __device__ __forceinline__ uint32_t lsc_pack(int la, int c, int m) { return ((ui
 __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float s_init[kMaxPts * 3];
     __shared__ int s_nhard, s_base, s_seg;
-    extern __shared__ int s_dyn[];                // [K] neighbour indices | [K][5] neighbour radius, downwash, goal | [K (M-1)] hard items
-    int* s_nbr = s_dyn;
-    float (*s_nj)[5] = reinterpret_cast<float (*)[5]>(s_dyn + P.K);
-    uint32_t* s_hard = reinterpret_cast<uint32_t*>(s_dyn + P.K * 6);
+    extern __shared__ __align__(8) unsigned char s_dyn[];   // [K] pair constants | [K] neighbour indices | [K (M-1)] hard items
+    LscPair* s_pair = reinterpret_cast<LscPair*>(s_dyn);
+    int* s_nbr = reinterpret_cast<int*>(s_pair + P.K);
+    uint32_t* s_hard = reinterpret_cast<uint32_t*>(s_nbr + P.K);
     const int M = P.M, npt = M * kP;
     const int la = blockIdx.x;
     const int cnt = S.nbr_cnt[la];
     const int og = npt * 3 + 6;
     if (threadIdx.x == 0) s_nhard = 0;
     for (int e = threadIdx.x; e < npt * 3; e += kLscThreads) s_init[e] = S.init_traj[(size_t)la * npt * 3 + e];
-    for (int c = threadIdx.x; c < cnt; c += kLscThreads) {
+    const double r_a = S.radius[la], dw_a = S.downwash[la];
+    for (int c = threadIdx.x; c < cnt; c += kLscThreads) {      // per-neighbour constants once, not once per item
         const int j = S.nbr_idx[(size_t)la * P.K + c];
         const float* rec_j = S.rec + (size_t)j * P.rec;
         s_nbr[c] = j;
-        s_nj[c][0] = rec_j[og + 3]; s_nj[c][1] = rec_j[og + 4];
-        s_nj[c][2] = rec_j[og]; s_nj[c][3] = rec_j[og + 1]; s_nj[c][4] = rec_j[og + 2];
+        s_pair[c] = lsc_pair_consts(r_a, dw_a, rec_j[og + 3], rec_j[og + 4]);
     }
-    const double r_a = S.radius[la], dw_a = S.downwash[la];
     __syncthreads();
     int it_sum = 0;
     const int n_gjk = cnt * (M - 1);
+    const uint32_t mg = fastdiv_magic((uint32_t)(M - 1));
     for (int e = threadIdx.x; e < n_gjk; e += kLscThreads) {
-        const int c = e / (M - 1), m = e - c * (M - 1);
+        const int c = (int)fastdiv((uint32_t)e, mg), m = e - c * (M - 1);
         const size_t pr = (size_t)la * P.K + c;
-        const LscPair q = lsc_pair_consts(r_a, dw_a, s_nj[c][0], s_nj[c][1]);
+        const LscPair q = s_pair[c];
         gjk::D3 hc[kP], v;
         lsc_gjk_load(s_init + m * kP * 3, S.pred_traj + ((size_t)s_nbr[c] * npt + m * kP) * 3, q, hc);
         int it = 0;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kLscRestThreads, 8) k_lsc_rest(const __grid_co
 
 int launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
     static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-    k_lsc<<<P.NL, kLscThreads, (size_t)P.K * (6 + P.M - 1) * sizeof(int), st>>>(P, S);
+    k_lsc<<<P.NL, kLscThreads, (size_t)P.K * (sizeof(LscPair) + (size_t)P.M * sizeof(int)), st>>>(P, S);
     k_lsc_rest<<<sms * 8, kLscRestThreads, 0, st>>>(P, S);
     return 2;
 }
@@ -678,7 +678,7 @@ __global__ void k_p2p_wait(const unsigned long long* flags, int world, unsigned 
     const volatile unsigned long long* f = flags + r;
     const long long t0 = clock64();
     while (*f < step) {
-        if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1); break; }
+        if (clock64() - t0 > timeout_cycles) { *reinterpret_cast<volatile int*>(err) = 1; break; }    // err: mapped host memory
         __nanosleep(200);
     }
     __threadfence_system();

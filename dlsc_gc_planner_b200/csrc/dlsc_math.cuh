@@ -43,10 +43,13 @@ DLSC_HD bool v3_eq(const V3& a, const V3& b) { return a.x == b.x && a.y == b.y &
 DLSC_HD double v3_dot(const V3& a, const V3& b) { float r = a.x * b.x + a.y * b.y + a.z * b.z; return (double)r; }
 DLSC_HD double v3_norm_sq(const V3& a) { float r = a.x * a.x + a.y * a.y + a.z * a.z; return (double)r; }
 DLSC_HD double v3_norm(const V3& a) { return sqrt(v3_norm_sq(a)); }
+// octomath::Vector3::normalized(): len = sqrt((double)norm_sq_float), components divided by (float)len.
+// (float)sqrt((double)r) == sqrtf(r) for every float r >= 0 (a correctly rounded double square root rounds to the
+// correctly rounded float one: 53 >= 2 * 24 + 2 bits), so the float instruction is used; len > 0 <=> r > 0.
 DLSC_HD V3 v3_normalized(const V3& a) {
     V3 r = a;
-    double len = v3_norm(a);
-    if (len > 0) { float f = (float)len; r.x /= f; r.y /= f; r.z /= f; }
+    const float nsq = a.x * a.x + a.y * a.y + a.z * a.z;
+    if (nsq > 0.f) { const float f = sqrtf(nsq); r.x /= f; r.y /= f; r.z /= f; }
     return r;
 }
 DLSC_HD double v3_distance(const V3& a, const V3& b) {

@@ -120,8 +120,9 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
 // are not constraints, traj_optimizer.cpp:422-424)
 DLSC_HD float lsc_item_slack(double smin, double nn) {
     if (!(nn > 0.0)) return 3.0e38f;
-    const double q = smin / nn;
-    return q > 3.0e38 ? 3.0e38f : (q < -3.0e38 ? -3.0e38f : (float)q);
+    // a screen value, not a result: float arithmetic (1e-7 relative) is far inside the screen's 1e-3 m margin
+    const float q = (float)smin / (float)nn;
+    return q > 3.0e38f ? 3.0e38f : (q < -3.0e38f ? -3.0e38f : q);
 }
 // the 6 control points of one segment (18 floats, 8-byte aligned: 72-byte segments of 16-byte aligned trajectories)
 DLSC_HD void load_segment(const float* p, V3 (&out)[kP]) {
@@ -154,23 +155,38 @@ DLSC_HD bool is_pow2_f32(float f) {           // normal, positive, zero mantissa
 // and queues the few that need the triangle / tetrahedron sub-algorithms (k_lsc / k_lsc_rest), lsc_segment does both
 // in place (host simulator, subset stepping).
 // ------------------------------------------------------------------------------------------------
-struct LscPair { double collision_dist, downwash; float dwf; };
+// per (agent, neighbour) constants; inv_* are the exact reciprocals when the value is a power of two (every mission with
+// equal downwash coefficients: 2.0), else 0: x / 2^k == x * 2^-k bit for bit, the IEEE division otherwise
+struct LscPair { double collision_dist, downwash, inv_downwash; float dwf, inv_dwf; };
+DLSC_HD bool is_pow2_f64(double d) {           // normal, positive, zero mantissa, reciprocal representable
+    unsigned long long u;
+#ifdef __CUDA_ARCH__
+    u = (unsigned long long)__double_as_longlong(d);
+#else
+    memcpy(&u, &d, 8);
+#endif
+    return (u & 0x800fffffffffffffull) == 0 && ((u >> 52) - 2ull) < 2043ull;
+}
 DLSC_HD LscPair lsc_pair_consts(double r_a, double dw_a, float r_j_f, float dw_j_f) {
     const double r_j = (double)r_j_f, dw_j = (double)dw_j_f;
     LscPair q;
     q.collision_dist = r_j + r_a;                                              // :605
     q.downwash = (dw_a * r_a + dw_j * r_j) / (r_a + r_j);                      // :1153-1154
     q.dwf = (float)q.downwash;                                                 // trajectory.cpp:214
+    q.inv_dwf = is_pow2_f32(q.dwf) ? 1.0f / q.dwf : 0.0f;
+    q.inv_downwash = is_pow2_f64(q.downwash) ? 1.0 / q.downwash : 0.0;
     return q;
+}
+// (float)((double)z / downwash)  (:630-632, 1183-1187)
+DLSC_HD float lsc_div_downwash(float z, const LscPair& q) {
+    return (float)(q.inv_downwash != 0.0 ? (double)z * q.inv_downwash : (double)z / q.downwash);
 }
 // hull points c[i] = (double)(a_i - b_i) in the downwash frame; (float)c[i] recovers the float difference exactly
 DLSC_HD void lsc_gjk_load(const float* init_seg, const float* pred_seg, const LscPair& q, gjk::D3 (&c)[kP]) {
     V3 wb[kP];
     load_segment(pred_seg, wb);
-    // x / dwf == x * (1 / dwf) bit for bit when dwf is a power of two (every mission with equal downwash
-    // coefficients: 2.0); the IEEE division otherwise
-    const bool pow2 = is_pow2_f32(q.dwf);
-    const float inv_dwf = pow2 ? 1.0f / q.dwf : 0.0f;
+    const bool pow2 = q.inv_dwf != 0.0f;
+    const float inv_dwf = q.inv_dwf;
 #pragma unroll
     for (int i = 0; i < kP; i++) {
         V3 a = v3_load(init_seg + i * 3); a.z = pow2 ? a.z * inv_dwf : a.z / q.dwf;
@@ -183,7 +199,7 @@ DLSC_HD void lsc_gjk_finish(const gjk::D3 (&c)[kP], const gjk::D3& v, const LscP
                             double* d_out, float* slack_out) {
     const V3 cp2 = v3(0.f, 0.f, 0.f) + v3((float)v.x, (float)v.y, (float)v.z);   // geometry.hpp:302
     const V3 nt = v3_normalized(cp2);                                             // :1118
-    const float nz_w = (float)((double)nt.z / q.downwash);                        // :630-632
+    const float nz_w = lsc_div_downwash(nt.z, q);                                 // :630-632
     normal_out[0] = nt.x; normal_out[1] = nt.y; normal_out[2] = nz_w;
     double pmin = 1e300;
 #pragma unroll

@@ -10,9 +10,9 @@ AGENT_COLUMNS = "id,t,px,py,pz,vx,vy,vz,ax,ay,az,planning_time"
 
 
 def _g(x):
-    """C++ default stream formatting of a double / float: precision 6, %g."""
-    s = "%g" % float(x)
-    return "0" if s == "-0" else s
+    """C++ default stream formatting of a double / float: precision 6, %g (a negative zero prints as "-0", as
+    `ostream << -0.0f` does)."""
+    return "%g" % float(x)
 
 
 def header(n_agents):

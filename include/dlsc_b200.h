@@ -107,6 +107,9 @@ typedef struct dlsc_agent_props {
 
 const char* dlsc_last_error(void);
 int dlsc_abi_version(void);
+/* CUDA toolkit version the library was built with; exported only by the sm_100a build (loaders use it to refuse
+ * anything that is not the CUDA product, e.g. the test-only host simulator). */
+int dlsc_cuda_build(void);
 int dlsc_device_count(void);
 
 /* Create a context on CUDA device `device` for agents [agent_begin, agent_begin+n_local) of a

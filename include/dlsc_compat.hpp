@@ -262,13 +262,35 @@ inline void from_traj(const traj_t& tr, int M, int n, float* t) {
 // One device context shared by all TrajPlanner objects of a mission.
 class SwarmBatch {
 public:
+    // Registry: the planners of ONE mission share a context.  The key is the content the context depends on -- every
+    // planner parameter the device reads and the whole mission (world box, every agent's start, goal and properties) --
+    // so two missions that merely have the same agent count never alias, and a changed mission (the reference's
+    // mission_changed path builds new planners) gets a fresh context.
+    static std::string key_of(const Param& p, const Mission& m) {
+        std::string k;
+        auto put = [&k](const void* q, size_t n) { k.append(static_cast<const char*>(q), n); };
+        const double pd[] = {p.world_resolution, p.world_z_2d, p.dt, p.control_input_weight, p.terminal_weight, p.grid_resolution,
+                             p.reset_threshold, p.communication_range};
+        const int pi[] = {p.world_dimension, p.world_use_octomap ? 1 : 0, p.M, p.n, p.phi, p.max_neighbours, (int)m.qn};
+        put(pd, sizeof(pd)); put(pi, sizeof(pi));
+        for (unsigned c = 0; c < 3; c++) { const float w[2] = {m.world_min(c), m.world_max(c)}; put(w, sizeof(w)); }
+        for (const Agent& a : m.agents) {
+            const float f[6] = {a.start_point(0), a.start_point(1), a.start_point(2), a.desired_goal_point(0), a.desired_goal_point(1),
+                                a.desired_goal_point(2)};
+            const double d[5] = {a.max_vel, a.max_acc, a.radius, a.downwash, a.nominal_velocity};
+            put(f, sizeof(f)); put(d, sizeof(d));
+        }
+        return k;
+    }
     static std::shared_ptr<SwarmBatch> get(const Param& p, const Mission& m) {
-        static std::map<size_t, std::weak_ptr<SwarmBatch>> reg;
-        auto it = reg.find(m.qn);
+        static std::map<std::string, std::weak_ptr<SwarmBatch>> reg;
+        const std::string key = key_of(p, m);
+        for (auto it = reg.begin(); it != reg.end();) it = it->second.expired() ? reg.erase(it) : std::next(it);
+        auto it = reg.find(key);
         if (it != reg.end())
             if (auto sp = it->second.lock()) return sp;
         auto sp = std::shared_ptr<SwarmBatch>(new SwarmBatch(p, m));
-        reg[m.qn] = sp;
+        reg[key] = sp;
         return sp;
     }
     ~SwarmBatch() { if (ctx) dlsc_destroy(ctx); }
@@ -302,7 +324,30 @@ public:
             check(dlsc_set_edt(ctx, d->dist.data(), d->obst.data(), d->dims, d->min_key, d->res), "dlsc_set_edt");
         distmap_seen = d.get();
 #else
-        (void)d;   // with the real dynamicEDT3D: export its grid once, see INTEGRATION.md
+        // real dynamicEDT3D: export the live grid once per map -- one accessor call per cell centre, the very call the
+        // reference's SFC code makes per lattice vertex (collision_constraints.cpp:880) -- into the device context
+        if (!d || d.get() == distmap_seen) return;
+        int32_t dims[3], mk[3];
+        check(dlsc_edt_dims(ctx, dims, mk), "dlsc_edt_dims");
+        const size_t nc = (size_t)dims[0] * dims[1] * dims[2];
+        std::vector<float> dist_v(nc);
+        std::vector<int32_t> obst_v(nc * 3);
+        const double inv = 1.0 / res;
+        size_t i = 0;
+        for (int x = 0; x < dims[0]; x++)
+            for (int y = 0; y < dims[1]; y++)
+                for (int z = 0; z < dims[2]; z++, i++) {
+                    const point3d centre((float)(((double)(x + mk[0]) + 0.5) * res), (float)(((double)(y + mk[1]) + 0.5) * res),
+                                         (float)(((double)(z + mk[2]) + 0.5) * res));
+                    float dd = -1.f;
+                    point3d cl;
+                    d->getDistanceAndClosestObstacle(centre, dd, cl);
+                    dist_v[i] = dd;
+                    const bool has = dd >= 0.f && dd < 1.f;            // beyond that the vertex test never looks at the obstacle
+                    for (unsigned k = 0; k < 3; k++) obst_v[3 * i + k] = has ? (int32_t)std::floor(inv * (double)cl(k)) - mk[k] : -1;
+                }
+        check(dlsc_set_edt(ctx, dist_v.data(), obst_v.data(), dims, mk, res), "dlsc_set_edt");
+        distmap_seen = d.get();
 #endif
     }
     // replan agent i (or everybody when all agents were staged); fills the result cache
@@ -311,6 +356,7 @@ public:
         // one batched launch only when every agent was announced before the first plan() of the step
         const bool none_planned = std::none_of(planned.begin(), planned.end(), [](uint8_t s) { return s != 0; });
         const bool all = (batch_done || none_planned) && std::all_of(staged.begin(), staged.end(), [](uint8_t s) { return s != 0; });
+        batch_last = all;
         if (all && !batch_done) {
             upload();
             check(dlsc_step(ctx), "dlsc_step");
@@ -336,8 +382,13 @@ public:
         batch_done = true;
     }
     int N = 0, M = 0, n = 5;
-    double dt = 0.2;
+    double dt = 0.2, res = 0.1;
     dlsc_ctx* ctx = nullptr;
+    // the device context, for callers that bind more than the three classes do (e.g. MapManager handing over an
+    // occupancy grid through dlsc_build_edt_occupancy)
+    dlsc_ctx* context() const { return ctx; }
+    // per-stage device time of the last step, amortised per agent [s]: predict, neighbours, LSC, SFC, goal, QP
+    double stage_s[DLSC_N_STAGES] = {0, 0, 0, 0, 0, 0};
     std::vector<float> traj, goal;
     std::vector<double> cost;
     std::vector<int32_t> status;
@@ -345,7 +396,7 @@ public:
 
 private:
     SwarmBatch(const Param& p, const Mission& m) {
-        N = (int)m.qn; M = p.M; n = p.n; dt = p.dt;
+        N = (int)m.qn; M = p.M; n = p.n; dt = p.dt; res = p.world_resolution;
         if (N < 1 || (size_t)N != m.agents.size()) throw std::invalid_argument("[TrajPlanner] mission has no agents");
         const int K = p.max_neighbours > 0 ? p.max_neighbours : std::max(N - 1, 1);
         dlsc_params q = make_params(p, m, K);
@@ -360,6 +411,7 @@ private:
         dlsc_agent_props pr{r.data(), dw.data(), mv.data(), ma.data(), nv.data()};
         check(dlsc_set_agent_props(ctx, &pr), "dlsc_set_agent_props");
         check(dlsc_reset(ctx, start.data()), "dlsc_reset");
+        check(dlsc_enable_timing(ctx, 1), "dlsc_enable_timing");      // feeds PlanningStatistics (reference-scale missions)
         pos.assign(3 * N, 0.f); vel = pos; acc = pos; wp = pos; goal = pos;
         dist.assign(N, 0); staged.assign(N, 0); planned.assign(N, 0);
         traj.assign((size_t)N * M * (n + 1) * 3, 0.f); cost.assign(N, 0.0); status.assign(N, 0);
@@ -374,10 +426,15 @@ private:
         check(dlsc_get_cost(ctx, cost.data()), "dlsc_get_cost");
         check(dlsc_get_status(ctx, status.data()), "dlsc_get_status");
         check(dlsc_get_goal(ctx, goal.data()), "dlsc_get_goal");
+        double ms[DLSC_N_STAGES];
+        int n_steps = 0;
+        check(dlsc_get_timings(ctx, ms, &n_steps), "dlsc_get_timings");
+        if (n_steps > 0)
+            for (int s = 0; s < DLSC_N_STAGES; s++) stage_s[s] = ms[s] * 1e-3 / (batch_last ? N : 1);
     }
     std::vector<float> pos, vel, acc, wp;
     std::vector<uint8_t> dist;
-    bool step_open = true, batch_done = false, pending_publish = false;
+    bool step_open = true, batch_done = false, pending_publish = false, batch_last = false;
     const void* distmap_seen = nullptr;
 };
 }  // namespace detail
@@ -547,6 +604,17 @@ public:
         if (!batch->staged[agent.id]) batch->stage(agent, is_disturbed);
         batch->plan(agent.id);
         const int st = batch->status[agent.id];
+        {   // PlanningStatistics as TrajPlanner::plan fills it (traj_planner.cpp:42-62), from the device stage timers;
+            // a batched step reports every stage amortised per agent
+            PlanningTimeStatistics& pt = statistics.planning_time;
+            const double* s = batch->stage_s;
+            pt.obstacle_prediction_time.update(s[0]); pt.initial_traj_planning_time.update(0.0);
+            pt.lsc_generation_time.update(s[1] + s[2]); pt.sfc_generation_time.update(s[3]);
+            pt.goal_planning_time.update(s[4]); pt.traj_optimization_time.update(s[5]);
+            pt.total_planning_time.update(s[0] + s[1] + s[2] + s[3] + s[4] + s[5]);
+        }
+        if (st & DLSC_NBR_OVERFLOW)     // the reference has no neighbour cap: planning without some neighbours' constraints is an error
+            throw std::length_error("[TrajPlanner] more agents in communication range than Param::max_neighbours");
         if (st & DLSC_SFC_INIT_FAILED) throw std::invalid_argument("[CollisionConstraints] Invalid initial SFC");  // collision_constraints.cpp:445-447
         if (st & DLSC_GOAL_INFEASIBLE) throw PlanningReport::QPFAILED;                                             // goal_optimizer.cpp:122,132
         TrajOptResult res;   // QP failure: the library already substituted initial_traj (traj_planner.cpp:749-777)
@@ -558,10 +626,16 @@ public:
     }
     void publish() {}
     void setObstacles(const Obstacles& obstacles_) {
+        for (const auto& o : obstacles_)
+            if (o.type != ObstacleType::AGENT)     // dynamic obstacles (slack QP, size prediction): not on the device path yet
+                throw std::invalid_argument("[TrajPlanner] obstacle " + std::to_string(o.id) + " is not an agent: dynamic obstacles "
+                                            "are not supported by the B200 path (SURVEY s8(f) rank 4)");
         obstacles = obstacles_;
         batch->new_step();
         for (const auto& o : obstacles) batch->observe(o);
     }
+    // the mission's shared device context (NULL never): MapManager-side bindings hand maps over through it
+    dlsc_ctx* deviceContext() const { return batch->context(); }
     int getPlannerSeq() const { return planner_seq; }
     point3d getCurrentGoalPosition() const { return agent.current_goal_point; }
     PlanningStatistics getPlanningStatistics() const { return statistics; }

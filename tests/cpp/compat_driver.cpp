@@ -92,6 +92,22 @@ int main(int argc, char** argv) {
             }
         printf("step %d checksum %.9f cost %.9f min_dist %.6f seq %d\n", step, checksum, cost, dmin, planners[0]->getPlannerSeq());
     }
+    {   // PlanningStatistics is filled from the device stage timers; a second mission with the same agent count gets its
+        // own context; a dynamic (non-agent) obstacle is refused
+        const PlanningStatistics ps = planners[0]->getPlanningStatistics();
+        printf("stats seq %d total %.3e qp %.3e samples %d\n", ps.planning_seq, ps.planning_time.total_planning_time.average,
+               ps.planning_time.traj_optimization_time.average, ps.planning_time.total_planning_time.N_sample);
+        Mission other = mission;
+        other.agents[0].desired_goal_point = point3d(0.5f, 0.5f, 1.f);
+        TrajPlanner p2(nh, param, other, other.agents[0]);
+        printf("contexts distinct %d same %d\n", p2.deviceContext() != planners[0]->deviceContext() ? 1 : 0,
+               planners[1]->deviceContext() == planners[0]->deviceContext() ? 1 : 0);
+        Obstacles dyn(1);
+        dyn[0].type = ObstacleType::DYN_SPIN; dyn[0].id = 99;
+        int refused = 0;
+        try { p2.setObstacles(dyn); } catch (const std::invalid_argument&) { refused = 1; }
+        printf("dynamic obstacle refused %d\n", refused);
+    }
     // TrajOptimizer::solve with explicit constraints (one LSC plane, no SFC)
     {
         Agent a = mission.agents[0];

@@ -25,7 +25,18 @@ def test_library_builds_and_exports_every_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     missing = [s for s in header_symbols() if not hasattr(lib, s)]
     assert not missing, missing
+    assert lib.dlsc_cuda_build() > 0
     assert lib.dlsc_abi_version() == 3
+
+
+def test_loader_refuses_a_cpu_stand_in(hostsim, monkeypatch):
+    """DLSC_B200_LIB may select another CUDA build, never the test-only host simulator."""
+    assert not hasattr(hostsim, "dlsc_cuda_build")
+    monkeypatch.setattr(capi, "LIB_PATH", _parity.HOSTSIM_SO)
+    monkeypatch.setattr(capi, "_LIB", None)
+    with pytest.raises(RuntimeError) as e:
+        capi.load_library()
+    assert "not a CUDA build" in str(e.value)
 
 
 def test_no_cpu_fallback():

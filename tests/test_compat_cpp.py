@@ -51,11 +51,14 @@ def test_compat_driver_serial_equals_batched():
     outs = {}
     for mode in ("serial", "staged"):
         outs[mode] = subprocess.check_output([exe, mode, "25"], text=True).strip().split("\n")
-    assert len(outs["serial"]) == 26
-    for a, b in zip(outs["serial"][:-1], outs["staged"][:-1]):
+    assert len(outs["serial"]) == 29
+    for a, b in zip(outs["serial"][:25], outs["staged"][:25]):
         assert a == b, (a, b)
-    for line in outs["serial"][:-1]:
+    st = re.search(r"stats seq (\d+) total (\S+) qp (\S+) samples (\d+)", outs["serial"][25])
+    assert int(st.group(1)) == 25 and int(st.group(4)) == 25 and 0 < float(st.group(3)) <= float(st.group(2)) < 1.0
+    assert outs["serial"][26] == "contexts distinct 1 same 1" and outs["serial"][27] == "dynamic obstacle refused 1"
+    for line in outs["serial"][:25]:
         assert float(re.search(r"min_dist ([0-9.]+)", line).group(1)) >= 0.3 - 1e-4, line
-    assert int(re.search(r"seq (\d+)", outs["serial"][-2]).group(1)) == 25
+    assert int(re.search(r"seq (\d+)", outs["serial"][24]).group(1)) == 25
     end = [float(x) for x in re.search(r"solve end (\S+) (\S+) (\S+)", outs["serial"][-1]).groups()]
     assert 1.9 - 1e-6 <= end[0] <= 1.9 + 1e-4 and abs(end[1]) < 1e-5 and abs(end[2] - 1.0) < 1e-5

@@ -26,7 +26,7 @@ def test_header_and_number_format():
     assert resultlog.header(2) == resultlog.AGENT_COLUMNS + "," + resultlog.AGENT_COLUMNS
     row = resultlog.format_row(0.2, np.array([[-1.0, 2.5, 1.0]], np.float32), np.array([[0.123456789, -0.0, 1e-7]], np.float32),
                                np.zeros((1, 3), np.float32), [0.0068735])
-    assert row == "0,0.2,-1,2.5,1,0.123457,0,1e-07,0,0,0,0.0068735"
+    assert row == "0,0.2,-1,2.5,1,0.123457,-0,1e-07,0,0,0,0.0068735"
 
 
 def test_oracle_first_replan_writes_the_reference_log(oracle):
