@@ -5,7 +5,7 @@ import collections
 import csv
 import sys
 
-STEP = ("k_predict", "k_neighbours", "k_nbr_bin", "k_nbr_search", "k_lsc", "k_sfc", "k_goal", "k_qp_fast", "k_qp_gi", "k_qp", "k_advance")
+STEP = ("k_predict", "k_neighbours", "k_nbr_bin", "k_nbr_search", "k_lsc", "k_lsc_rest", "k_sfc", "k_goal", "k_qp_fast", "k_qp_gi", "k_qp", "k_advance")
 rows = list(csv.reader(open(sys.argv[1])))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 ki, vi = rows[h].index("Kernel Name"), rows[h].index("Metric Value")
