@@ -759,6 +759,25 @@ DLSC_HD bool box_test(const Group& g, const DevParams& P, const EdtDev& E, const
     return obstacle_in_box(g, P, E, b, margin, memo, lookups);
 }
 
+template <int K> DLSC_HD float& v3_comp(V3& v) { if (K == 0) return v.x; if (K == 1) return v.y; return v.z; }
+// grow face AX (0..2: low faces, 3..5: high faces) of `cand` by one cell and make `upd` the new slab (:1058-1063);
+// returns isSFCInBoundary of the slab (it shares four faces with the verified `cand`: only the growth axis is new)
+template <int AX>
+DLSC_HD bool sfc_grow_face(const DevParams& P, const EdtDev& E, double res, Box& cand, Box& upd, LatticeBox& Lc, LatticeBox& Lu) {
+    constexpr int A3 = (AX < 3) ? AX : AX - 3;
+    if (AX < 3) {
+        v3_comp<A3>(upd.hi) = v3_comp<A3>(cand.lo);
+        v3_comp<A3>(cand.lo) = (float)(v3_comp<A3>(cand.lo) - res);
+        v3_comp<A3>(upd.lo) = v3_comp<A3>(cand.lo);
+    } else {
+        v3_comp<A3>(upd.lo) = v3_comp<A3>(cand.hi);
+        v3_comp<A3>(cand.hi) = (float)(v3_comp<A3>(cand.hi) + res);
+        v3_comp<A3>(upd.hi) = v3_comp<A3>(cand.hi);
+    }
+    lattice_axis(E, res, A3, v3_comp<A3>(cand.lo), v3_comp<A3>(cand.hi), Lc.mm[A3], Lc.vv[A3]);
+    lattice_axis(E, res, A3, v3_comp<A3>(upd.lo), v3_comp<A3>(upd.hi), Lu.mm[A3], Lu.vv[A3]);
+    return (v3_comp<A3>(upd.lo) > P.world_min[A3] + 0.0 - kEpsF) && (v3_comp<A3>(upd.hi) < P.world_max[A3] - 0.0 + kEpsF);
+}
 DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtDev& E, const Box& init,
                                   double margin, double max_vel, Box& out, SfcTab* memo, long long* lookups) {
     const double res = P.world_res;
@@ -789,29 +808,18 @@ DLSC_HD bool expand_incrementally(const Group& g, const DevParams& P, const EdtD
             i++;
             if (i >= n_axes) i = 0;
             const int ax = (axes >> (4 * i)) & 0xf;
-            const int a3 = (ax < 3) ? ax : ax - 3;
             sfc = cand; upd = cand;
             Ls = Lc; Lu = Lc;
-            if (ax < 3) {
-                v3_set(upd.hi, ax, v3_get(cand.lo, ax));
-                v3_set(cand.lo, ax, (float)(v3_get(cand.lo, ax) - res));
-                v3_set(upd.lo, ax, v3_get(cand.lo, ax));
-            } else {
-                v3_set(upd.lo, a3, v3_get(cand.hi, a3));
-                v3_set(cand.hi, a3, (float)(v3_get(cand.hi, a3) + res));
-                v3_set(upd.hi, a3, v3_get(cand.hi, a3));
+            // one growth step of face `ax`, specialised per face: the control flow is uniform in the warp, so the switch
+            // costs one branch and every component / lattice slot below is addressed at compile time
+            switch (ax) {
+                case 0: inside = sfc_grow_face<0>(P, E, res, cand, upd, Lc, Lu); break;
+                case 1: inside = sfc_grow_face<1>(P, E, res, cand, upd, Lc, Lu); break;
+                case 2: inside = sfc_grow_face<2>(P, E, res, cand, upd, Lc, Lu); break;
+                case 3: inside = sfc_grow_face<3>(P, E, res, cand, upd, Lc, Lu); break;
+                case 4: inside = sfc_grow_face<4>(P, E, res, cand, upd, Lc, Lu); break;
+                default: inside = sfc_grow_face<5>(P, E, res, cand, upd, Lc, Lu); break;
             }
-            {   // only axis a3 of `cand` and `upd` changed
-                int mc, vc, mu, vu;
-                lattice_axis(E, res, a3, v3_get(cand.lo, a3), v3_get(cand.hi, a3), mc, vc);
-                lattice_axis(E, res, a3, v3_get(upd.lo, a3), v3_get(upd.hi, a3), mu, vu);
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    if (k == a3) { Lc.mm[k] = mc; Lc.vv[k] = vc; Lu.mm[k] = mu; Lu.vv[k] = vu; }
-            }
-            const double wlo = (a3 == 0) ? P.world_min[0] : (a3 == 1 ? P.world_min[1] : P.world_min[2]);
-            const double whi = (a3 == 0) ? P.world_max[0] : (a3 == 1 ? P.world_max[1] : P.world_max[2]);
-            inside = (v3_get(upd.lo, a3) > wlo + 0.0 - kEpsF) && (v3_get(upd.hi, a3) < whi - 0.0 + kEpsF);
             iters += 1ull << (8 * ax);
             if ((int)((iters >> (8 * ax)) & 0xffull) > max_iter) break;
         }
