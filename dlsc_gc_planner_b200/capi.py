@@ -61,7 +61,8 @@ EXPORTS = (
     "dlsc_set_waypoints_device dlsc_measure_fp64_peak dlsc_run_stages_subset dlsc_set_init_traj "
     "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups dlsc_edt_dims dlsc_build_edt "
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
-    "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build").split()
+    "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build dlsc_wp_last_error dlsc_wp_create dlsc_wp_destroy "
+    "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps").split()
 
 
 def build_library(force=False):
@@ -75,6 +76,11 @@ def build_library(force=False):
 
 def _declare(lib):
     lib.dlsc_last_error.restype = C.c_char_p
+    if hasattr(lib, "dlsc_wp_last_error"):
+        lib.dlsc_wp_last_error.restype = C.c_char_p
+        lib.dlsc_wp_pibt_timesteps.restype = C.c_int64
+        lib.dlsc_wp_pibt_timesteps.argtypes = [C.c_void_p]
+        lib.dlsc_wp_destroy.argtypes = [C.c_void_p]
     for name in ("dlsc_records_device", "dlsc_get_stream", "dlsc_waypoint_device", "dlsc_traj_device"):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_void_p
@@ -413,3 +419,81 @@ class SwarmPlanner:
 
     def bind_records(self, device_ptr):
         self._ck(self.lib.dlsc_bind_records(self.ctx, C.c_void_p(int(device_ptr))))
+
+
+class WaypointProvider:
+    """Host object over dlsc_wp_*: the reference's waypoint layer (comm-range groups + PIBT + update rules,
+    MultiSyncSimulator::decentralizedMAPP, reference src/multi_sync_simulator.cpp:308-466) for a whole swarm."""
+
+    def __init__(self, cfg, mission, lib=None, edt=None):
+        self.lib = lib if lib is not None else load_library()
+        self.cfg = cfg
+        self.N = int(mission.n_agents)
+        self.M, self.P = cfg.M, cfg.n + 1
+        self.params = make_params(cfg, mission.world_min, mission.world_max, 1)
+        start = np.ascontiguousarray(mission.start, np.float32).copy()
+        goal = np.ascontiguousarray(mission.goal, np.float32).copy()
+        if cfg.dim == 2:
+            start[:, 2] = np.float32(cfg.z_2d); goal[:, 2] = np.float32(cfg.z_2d)
+        self.ctx = C.c_void_p()
+        self._ck(self.lib.dlsc_wp_create(C.byref(self.params), self.N, _p(start), _p(goal), C.c_double(float(mission.radius[0])),
+                                         C.c_double(float(mission.downwash[0])), C.byref(self.ctx)))
+        if edt is not None:
+            self.set_grid(*edt)
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise DlscError((self.lib.dlsc_wp_last_error() or b"?").decode())
+        return rc
+
+    def close(self):
+        if self.ctx:
+            self.lib.dlsc_wp_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dims(self):
+        d3 = (C.c_int32 * 3)()
+        self._ck(self.lib.dlsc_wp_dims(self.ctx, d3))
+        return tuple(d3)
+
+    def set_grid(self, dist, obst, dims, min_key, res):
+        dist = np.ascontiguousarray(dist, np.float32); obst = np.ascontiguousarray(obst, np.int32)
+        d3 = (C.c_int32 * 3)(*[int(x) for x in dims]); k3 = (C.c_int32 * 3)(*[int(x) for x in min_key])
+        self._ck(self.lib.dlsc_wp_set_grid(self.ctx, _p(dist), _p(obst), d3, k3, C.c_double(res)))
+
+    def set_nodes(self, dims, exists):
+        d3 = (C.c_int32 * 3)(*[int(x) for x in dims])
+        e = np.ascontiguousarray(exists, np.uint8)
+        assert e.size == int(dims[0]) * int(dims[1]) * int(dims[2])
+        self._ck(self.lib.dlsc_wp_set_nodes(self.ctx, d3, _p(e)))
+
+    def nodes(self):
+        w, d, h = self.dims()
+        out = np.zeros(w * d * h, np.uint8)
+        self._ck(self.lib.dlsc_wp_get_nodes(self.ctx, _p(out)))
+        return out
+
+    def pibt(self, start, current, goal, max_t=6000):
+        s, c, g = (np.ascontiguousarray(x, np.int32) for x in (start, current, goal))
+        plan = np.zeros((max_t, len(s)), np.int32)
+        T = self._ck(self.lib.dlsc_wp_pibt(self.ctx, C.c_int(len(s)), _p(s), _p(c), _p(g), C.c_int(max_t), _p(plan)))
+        return plan[:T].copy()
+
+    def step(self, pos, goal_cur, traj, waypoint):
+        """-> updated waypoints [N][3] (traj None before the first replan)"""
+        pos = np.ascontiguousarray(pos, np.float32); gc = np.ascontiguousarray(goal_cur, np.float32)
+        wp = np.ascontiguousarray(waypoint, np.float32).copy()
+        tr = None if traj is None else np.ascontiguousarray(traj, np.float32)
+        assert pos.shape == (self.N, 3) and gc.shape == (self.N, 3) and wp.shape == (self.N, 3)
+        assert tr is None or tr.shape == (self.N, self.M, self.P, 3)
+        self._ck(self.lib.dlsc_wp_step(self.ctx, _p(pos), _p(gc), _p(tr), _p(wp)))
+        return wp
+
+    def pibt_timesteps(self):
+        return int(self.lib.dlsc_wp_pibt_timesteps(self.ctx))

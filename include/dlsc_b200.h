@@ -264,6 +264,30 @@ int dlsc_measure_fp64_peak(dlsc_ctx* ctx, double* tflops);
 int dlsc_gjk_batch(dlsc_ctx* ctx, const double* pts, int n, double* v, int32_t* iters, int32_t* simplex,
                    uint64_t* leaves);
 
+/* ---- waypoint provider ------------------------------------------------------------------
+ * Where every agent's next_waypoint comes from, for agent-only missions: comm-range groups, PIBT on the grid_res lattice
+ * and the waypoint update rules.  Replaces MultiSyncSimulator::decentralizedMAPP (src/multi_sync_simulator.cpp:308-466),
+ * GridBasedPlanner::planMAPF / runMAPF / updateGridMap / updatePlanResult (src/grid_based_planner.cpp:64-164, 292-453) and
+ * MAPF::PIBT (src/mapf/pibt.cpp:13-219).  Host code (a serial priority-inheritance search, once per replan step for the
+ * whole swarm); separate handle, same error convention (dlsc_wp_last_error).  start / desired_goal [n_agents][3];
+ * agent_radius / agent_downwash: agent 0's, as in the reference (multi_sync_simulator.cpp:375, grid_based_planner.cpp:31). */
+typedef struct dlsc_wp dlsc_wp;
+const char* dlsc_wp_last_error(void);
+int dlsc_wp_create(const dlsc_params* params, int n_agents, const float* start, const float* desired_goal, double agent_radius,
+                   double agent_downwash, dlsc_wp** out);
+void dlsc_wp_destroy(dlsc_wp* wp);
+int dlsc_wp_dims(const dlsc_wp* wp, int32_t dims[3]);                 /* lattice size; node id = w*d*z + w*y + x */
+/* Lattice nodes from the distance grid (dlsc_set_edt layout; NULL, NULL: no map, every node free). */
+int dlsc_wp_set_grid(dlsc_wp* wp, const float* dist, const int32_t* obst, const int32_t dims[3], const int32_t min_key[3], double res);
+int dlsc_wp_set_nodes(dlsc_wp* wp, const int32_t dims[3], const uint8_t* exists /* [w*d*h], non-zero = node present */);
+int dlsc_wp_get_nodes(const dlsc_wp* wp, uint8_t* exists /* [w*d*h] */);
+/* PIBT alone on node ids (per-kernel parity entry); plan_out [max_t][n]; returns the number of configurations or < 0. */
+int dlsc_wp_pibt(dlsc_wp* wp, int n, const int32_t* start, const int32_t* current, const int32_t* goal, int max_t, int32_t* plan_out);
+/* One decentralizedMAPP call for the whole swarm: pos / goal_cur [N][3], traj [N][M][6][3] (NULL before the first replan),
+ * waypoint [N][3] in / out. */
+int dlsc_wp_step(dlsc_wp* wp, const float* pos, const float* goal_cur, const float* traj, float* waypoint);
+int64_t dlsc_wp_pibt_timesteps(const dlsc_wp* wp);                    /* PIBT timesteps simulated by the last dlsc_wp_step */
+
 /* Device pointers of per-step input / output arrays, for callers that keep data on the GPU. */
 float* dlsc_waypoint_device(dlsc_ctx* ctx);   /* [n_local][3] */
 float* dlsc_traj_device(dlsc_ctx* ctx);       /* [n_local][M][P][3] */

@@ -1,0 +1,114 @@
+"""The waypoint provider behind the C ABI (dlsc_wp_*, dlsc_gc_planner_b200/csrc/dlsc_waypoints.cpp): comm-range groups + PIBT on
+the lattice + the waypoint update rules of the reference's MultiSyncSimulator::decentralizedMAPP.
+
+  * PIBT against the REFERENCE'S OWN object code (src/mapf/*.cpp + third_party/grid-pathfinding compiled unmodified into
+    oracle/_ref/libmapf_ref.so): 80 committed known-answer plans (tests/golden/pibt_ref.npz, 2-D / 3-D lattices, missing
+    nodes, up to 14 agents, unsolvable instances that run to the 5000-step cap) and, when oracle/_ref is built, live on
+    fresh random instances.  Plans must be identical, node by node.
+  * the whole layer against the reference's recorded run: the 137 waypoint sets recovered from the CPLEX log
+    (tests/golden/inferred_waypoints.npz) are reproduced step by step when the provider is fed the rollout's states --
+    i.e. the golden-log chain now runs with GENERATED waypoints.
+Host code: runs on the CPU tier through the product library itself (no GPU needed for dlsc_wp_*)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import _parity
+from dlsc_gc_planner_b200 import capi, missions
+
+GOLD = os.path.join(_parity.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    capi.build_library()
+    return capi.load_library()
+
+
+def _provider(lib, n):
+    cfg = missions.PlannerConfig.maze2d()
+    z = np.zeros((n, 3), np.float32)
+    one = np.ones(n)
+    m = missions.Mission(np.array([-2, -2, 0], np.float32), np.array([2, 2, 2], np.float32), z, z.copy(), 0.15 * one, 2.0 * one,
+                         one, 2 * one, one, np.zeros((0, 6), np.float32))
+    return capi.WaypointProvider(cfg, m, lib=lib)
+
+
+def test_pibt_matches_reference_known_answers(lib):
+    z = np.load(os.path.join(GOLD, "pibt_ref.npz"))
+    long_plans = 0
+    for i in range(int(z["count"])):
+        g = lambda f: z["%d/%s" % (i, f)]
+        wp = _provider(lib, len(g("cur")))
+        wp.set_nodes(g("dims"), g("exists"))
+        plan = wp.pibt(g("start"), g("cur"), g("goal"))
+        assert plan.shape == g("plan").shape and np.array_equal(plan, g("plan")), i
+        long_plans += len(plan) > 1000
+        wp.close()
+    assert long_plans >= 3          # the iteration cap is part of the pinned behaviour
+
+
+def test_pibt_matches_reference_object_code_live(lib):
+    so = os.path.join(_parity.ROOT, "oracle", "_ref", "libmapf_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_pibt_fixtures as mk
+    ref = C.CDLL(so)
+    rng = np.random.default_rng(77)
+    for (w, d, h, exists, start, cur, goal) in mk.problems(rng, 40):
+        want = mk.ref_pibt(ref, w, d, h, exists, start, cur, goal)
+        wp = _provider(lib, len(cur))
+        wp.set_nodes((w, d, h), exists)
+        got = wp.pibt(start, cur, goal)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        wp.close()
+
+
+def test_lattice_nodes_follow_the_distance_grid(lib, oracle):
+    """updateGridMap: nodes inside inflated obstacles are dropped; maze10 #1 keeps its start and goal nodes."""
+    cfg, m = _parity.load_case("maze10")
+    sw = _parity.make_oracle(cfg, m, 9)
+    wp = capi.WaypointProvider(cfg, m, lib=lib, edt=(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res))
+    w, d, h = wp.dims()
+    assert (w, d, h) == (17, 9, 1)                                  # world [-2, 6] x [-0.3, 4.3] at 0.5 m: x -2..6, y 0..4
+    ex = wp.nodes()
+    assert 0 < ex.sum() < ex.size
+    # a node is dropped exactly when its point is closer (L-infinity) than the radius to the nearest obstacle cell
+    dist, obst = sw.edt.dist, sw.edt.obst
+    for y in range(d):
+        for x in range(w):
+            q = np.array([-2.0 + 0.5 * x, 0.0 + 0.5 * y, 1.0], np.float32)
+            cell = np.floor(q.astype(np.float64) / 0.1).astype(int) - np.array(sw.edt.min_key)
+            c = (cell[0] * sw.edt.dims[1] + cell[1]) * sw.edt.dims[2] + cell[2]
+            blocked = False
+            if obst[c][0] >= 0:
+                centre = ((obst[c] + np.array(sw.edt.min_key) + 0.5) * 0.1).astype(np.float32)
+                near = np.clip(q, centre - np.float32(0.05), centre + np.float32(0.05))
+                blocked = np.abs(near - q).max() < 0.15 - 1e-5
+            assert ex[w * y + x] == (0 if blocked else 1), (x, y)
+    for a in range(m.n_agents):                                     # start and goal nodes of the mission are free
+        for pt in (m.start[a], m.goal[a]):
+            assert ex[w * int(round((pt[1] - 0.0) / 0.5)) + int(round((pt[0] + 2.0) / 0.5))] == 1
+    wp.close()
+
+
+def test_generated_waypoints_reproduce_the_reference_run(lib, oracle):
+    """Golden-log chain with generated waypoints: at every one of the 137 steps the provider, fed the oracle rollout's
+    states, issues exactly the waypoints recovered from the reference's log."""
+    cfg, m = _parity.load_case("maze10")
+    sw = _parity.make_oracle(cfg, m, 9, n_threads=os.cpu_count() or 1)
+    wp = capi.WaypointProvider(cfg, m, lib=lib, edt=(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res))
+    want = np.load(os.path.join(GOLD, "inferred_waypoints.npz"))["waypoints"]
+    for step in range(len(want)):
+        got = wp.step(sw.pos, sw.goal_cur, sw.traj if sw.seq > 0 else None, sw.waypoint)
+        assert np.array_equal(got, want[step]), (step, np.flatnonzero((got != want[step]).any(axis=1)), got, want[step])
+        sw.waypoint = got
+        st = sw.step()
+        assert (st & ~16).max() == 0
+        sw.advance()
+    assert wp.pibt_timesteps() > 0
+    wp.close()
