@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mc-missions", type=int, default=128, help="Monte-Carlo leg: independent empty50 missions per GPU (0: skip)")
     ap.add_argument("--mc-steps", type=int, default=20)
+    ap.add_argument("--closed-loop-steps", type=int, default=4, help="steps of the closed loop with the waypoint provider (0: skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU record exchange: stores over NVLink peer memory (default) or NCCL all-gather")
     return ap.parse_args()
@@ -521,6 +522,38 @@ def run_ours(args):
     h2d = int(4 * N * 12)
     d2h = int(N * cfg.M * (cfg.n + 1) * 12)
 
+    # ---------------- closed loop with the waypoint provider (1 GPU): every step, host side ----------------
+    # D2H states + trajectories -> dlsc_wp_step (comm-range groups + PIBT + update rules, the reference's own per-step host
+    # stage, src/multi_sync_simulator.cpp:308-466) -> H2D waypoints -> dlsc_step -> dlsc_advance.  Reported beside `e2e`
+    # (which replays recorded waypoints): at 4096 agents the reference's waypoint algorithm itself costs ~0.4 s per step on a
+    # host core (it replans every agent's whole lattice path to completion each step), far more than the batched replan.
+    closed = None
+    if world == 1 and args.closed_loop_steps > 0:
+        restore(pl, snap, sl)
+        wp = capi.WaypointProvider(cfg, m, edt=(edt[0], edt[1], edt[2], edt[3], cfg.world_res))
+        wcur = rec["wp"][0].copy()
+        traj_cl = None
+        t_wp, t_all = [], []
+        for t in range(args.closed_loop_steps + 1):
+            t0 = time.perf_counter()
+            pos, _, _ = pl.state()
+            goal_cur = pl.goal() if t else snap["records"][:, cfg.M * (cfg.n + 1) * 3 + 6: cfg.M * (cfg.n + 1) * 3 + 9].copy()
+            t1 = time.perf_counter()
+            wcur = wp.step(pos, goal_cur, traj_cl, wcur)
+            t2 = time.perf_counter()
+            pl.set_agents(waypoint=wcur)
+            pl.plan()
+            traj_cl = pl.traj()
+            pl.advance(); pl.sync()
+            t3 = time.perf_counter()
+            if t:                                      # the first call also builds the provider's distance tables
+                t_wp.append(t2 - t1); t_all.append(t3 - t0)
+        closed = {"steps": len(t_all), "ms_per_step": 1e3 * float(np.mean(t_all)), "waypoint_provider_ms_per_step": 1e3 * float(np.mean(t_wp)),
+                  "pibt_timesteps_last": wp.pibt_timesteps(), "value": N / float(np.mean(t_all)), "unit": UNIT,
+                  "what": "host clock; per step: states + trajectories D2H, dlsc_wp_step on one host core (comm-range groups, PIBT to "
+                          "completion for all %d agents, update rules), waypoints H2D, dlsc_step, dlsc_advance" % N}
+        wp.close()
+
     out = None
     if rank == 0:
         peaks = {}
@@ -553,6 +586,8 @@ def run_ours(args):
                       "mean_dist_to_goal_m": snap["dist_to_goal"], "replay_exact": replay_exact},
             "clocks": clk,
         }
+        if closed:
+            out["closed_loop"] = closed
         hbm = peaks.get("hbm_gbs") or 6650.0
         ncell = int(edt[2][0]) * int(edt[2][1]) * int(edt[2][2])
         out["edt_build"] = {"kernels": "k_edt_pass_z_cols + k_edt_col_any/window + k_edt_pass_y/x", "ms": edt_ms, "cells": ncell, "bound": "hbm",

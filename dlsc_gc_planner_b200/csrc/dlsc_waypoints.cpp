@@ -73,6 +73,10 @@ struct dlsc_wp {
     std::vector<std::array<int, 6>> nbr;         // neighbour ids in the reference's order (left, right, up, down, top, bottom), -1 = none
     std::vector<int8_t> nbr_n;
     PlanResult plan_result;                      // one member shared by all groups, like GridBasedPlanner::plan_result
+    // BFS distance tables by goal node: the reference rebuilds them in every call (solver.cpp:270-290), but they depend on
+    // the lattice and the goal node only, so they are kept until the lattice changes
+    std::vector<std::vector<uint16_t>> dist_cache;   // [agent][node]
+    std::vector<int> dist_goal;                      // goal node each cached table was built for (-1: none)
     std::string err;
     int64_t pibt_timesteps = 0;                  // work counter: PIBT timesteps of the last dlsc_wp_step
 
@@ -127,6 +131,7 @@ struct dlsc_wp {
     }
     void build_edges() {                                                            // Grid::Grid, graph.cpp:371-431
         const int w = gdim[0], d = gdim[1], h = gdim[2];
+        dist_goal.assign(dist_goal.size(), -1);      // the lattice changed: cached distance tables are stale
         nbr.assign(exists.size(), {-1, -1, -1, -1, -1, -1});
         nbr_n.assign(exists.size(), 0);
         for (int z = 0; z < h; z++)
@@ -149,37 +154,48 @@ namespace {
 struct PibtAgent { int id, v_now, v_next, g; int elapsed, init_d; float tie_breaker; };
 
 struct Pibt {
-    const dlsc_wp& G;
+    dlsc_wp& G;
     int n;
-    std::vector<std::vector<int>> dist;            // [agent][node] BFS distance to the agent's goal (solver.cpp:270-290)
+    std::vector<const uint16_t*> dist;             // [agent][node] BFS distance to the agent's goal (solver.cpp:270-290)
+    std::vector<std::vector<uint16_t>> own;        // tables of agents without a cache slot
     std::vector<int> occupied_now, occupied_next;  // node -> agent index or -1
     std::vector<PibtAgent> A;
     std::mt19937 mt;
     std::vector<std::vector<int>> plan;            // configurations [t][agent]
 
-    Pibt(const dlsc_wp& g, const std::vector<int>& start, const std::vector<int>& cur, const std::vector<int>& goal)
+    // slot[i]: cache slot (global agent index) of problem agent i, or -1
+    Pibt(dlsc_wp& g, const std::vector<int>& start, const std::vector<int>& cur, const std::vector<int>& goal,
+         const std::vector<int>& slot = {})
         : G(g), n((int)cur.size()), mt(0) {        // DEFAULT_SEED = 0, a fresh generator per problem (problem.cpp:85)
         const int nn = (int)G.exists.size();
-        dist.assign(n, std::vector<int>(nn, kMaxTimestep));
+        dist.assign(n, nullptr);
+        own.resize(n);
         for (int i = 0; i < n; i++) {
-            std::queue<int> open;
-            open.push(goal[i]);
-            dist[i][goal[i]] = 0;
-            while (!open.empty()) {
-                const int v = open.front(); open.pop();
-                const int dv = dist[i][v];
-                for (int k = 0; k < G.nbr_n[v]; k++) {
-                    const int m = G.nbr[v][k];
-                    if (dv + 1 >= dist[i][m]) continue;
-                    dist[i][m] = dv + 1;
-                    open.push(m);
+            const int sl = slot.empty() ? -1 : slot[i];
+            std::vector<uint16_t>& tab = (sl >= 0) ? G.dist_cache[sl] : own[i];
+            if (!(sl >= 0 && G.dist_goal[sl] == goal[i] && (int)tab.size() == nn)) {
+                tab.assign(nn, (uint16_t)kMaxTimestep);
+                std::queue<int> open;
+                open.push(goal[i]);
+                tab[goal[i]] = 0;
+                while (!open.empty()) {
+                    const int v = open.front(); open.pop();
+                    const int dv = tab[v];
+                    for (int k = 0; k < G.nbr_n[v]; k++) {
+                        const int m = G.nbr[v][k];
+                        if (dv + 1 >= tab[m]) continue;
+                        tab[m] = (uint16_t)(dv + 1);
+                        open.push(m);
+                    }
                 }
+                if (sl >= 0) G.dist_goal[sl] = goal[i];
             }
+            dist[i] = tab.data();
         }
         occupied_now.assign(nn, -1); occupied_next.assign(nn, -1);
         A.resize(n);
         for (int i = 0; i < n; i++) {
-            A[i] = PibtAgent{i, cur[i], -1, goal[i], 0, dist[i][start[i]], (float)i / (float)n};
+            A[i] = PibtAgent{i, cur[i], -1, goal[i], 0, (int)dist[i][start[i]], (float)i / (float)n};
             occupied_now[cur[i]] = i;
         }
         plan.push_back(cur);
@@ -203,7 +219,7 @@ struct Pibt {
             if (aj != -1 && A[aj].v_next == a.v_now) continue;                      // swap conflict
             if (u == a.g) return u;
             if (v == -1) { v = u; continue; }
-            const int c_v = dist[a.id][v], c_u = dist[a.id][u];
+            const int c_v = (int)dist[a.id][v], c_u = (int)dist[a.id][u];
             // no dynamic obstacle of interest: obsDist is the same constant for every node (pibt.cpp:227-234)
             const float d_v = goal_dist(a, v), d_u = goal_dist(a, u);
             if ((c_u < c_v) || (c_u == c_v && occupied_now[v] != -1 && occupied_now[u] == -1) ||
@@ -299,6 +315,7 @@ int dlsc_wp_create(const dlsc_params* p, int n_agents, const float* start, const
     w->start.resize(n_agents); w->desired_goal.resize(n_agents);
     for (int a = 0; a < n_agents; a++) { w->start[a] = p3_load(start + 3 * a); w->desired_goal[a] = p3_load(desired_goal + 3 * a); }
     w->exists.assign((size_t)w->gdim[0] * w->gdim[1] * w->gdim[2], 1);
+    w->dist_cache.resize(n_agents); w->dist_goal.assign(n_agents, -1);
     w->build_edges();
     *out = w;
     return 0;
@@ -415,7 +432,8 @@ int dlsc_wp_step(dlsc_wp* w, const float* pos, const float* goal_cur, const floa
             if (!w->exists[s[k]] || !w->exists[c[k]] || !w->exists[g[k]])           // the reference dereferences a null node here
                 return wp_fail("dlsc_wp_step: agent " + std::to_string(qi) + ": start, waypoint or goal lies on an occupied lattice node");
         }
-        Pibt solver(*w, s, c, g);
+        std::vector<int> slot(gv.begin(), gv.end());
+        Pibt solver(*w, s, c, g, slot);
         w->pibt_timesteps += solver.run();
         const auto& plan = solver.plan;
         // ---- updatePlanResult (:292-364) ----
@@ -485,18 +503,33 @@ int dlsc_wp_step(dlsc_wp* w, const float* pos, const float* goal_cur, const floa
             if (in_range && norm(sub(desired[k], nw)) > kEpsF && on_line) update_cand.insert(qi);
         }
         auto index_of = [&](size_t q) { return (int)(std::lower_bound(gv.begin(), gv.end(), q) - gv.begin()); };
-        bool update = false;
-        while (!update && !update_cand.empty() && n > 1) {
-            for (const auto& qi : update_cand) {
-                const int k = index_of(qi);
-                for (size_t qj : group) {
-                    if (qi == qj) continue;
-                    const int kj = index_of(qj);
-                    const P3 nwj = update_cand.count(qj) ? desired[kj] : p3_load(waypoint + 3 * qj);
-                    if (distance(desired[k], nwj) < kEpsF) { update_cand.erase(qi); update = false; break; }
-                    update = true;
+        // "Find valid update" (:418-447): repeatedly drop the first candidate (ascending id) whose desired waypoint
+        // coincides with where another agent of the group will be (its desired waypoint if it is still a candidate, else
+        // its current one), until none is left.  Same fixed point and same removal order as the reference's triple loop,
+        // with the "who will be at this lattice node" question answered from a per-node list instead of a scan.
+        if (n > 1 && !update_cand.empty()) {
+            std::vector<std::vector<int>> at(w->exists.size());                     // node -> members whose target lies there
+            auto target = [&](int kj) { return update_cand.count(gv[kj]) ? desired[kj] : p3_load(waypoint + 3 * gv[kj]); };
+            for (int kj = 0; kj < n; kj++) at[w->point_id(target(kj))].push_back(kj);
+            auto conflicts = [&](int k) {
+                const int node = w->point_id(desired[k]);
+                for (int kj : at[node])
+                    if (kj != k && distance(desired[k], target(kj)) < kEpsF) return true;
+                return false;
+            };
+            for (bool again = true; again;) {
+                again = false;
+                for (const auto& qi : update_cand) {
+                    const int k = index_of(qi);
+                    if (conflicts(k)) {
+                        auto& from = at[w->point_id(desired[k])];
+                        from.erase(std::find(from.begin(), from.end(), k));
+                        update_cand.erase(qi);
+                        at[w->point_id(p3_load(waypoint + 3 * qi))].push_back(k);    // it stays where it is
+                        again = true;
+                        break;
+                    }
                 }
-                if (!update) break;
             }
         }
         for (const auto& qi : update_cand) {

@@ -71,3 +71,30 @@ def test_gpu_rollout_stays_on_the_cplex_log(cuda_lib, oracle):
         check_step(oracle, p, pl.traj(), step, state, 1.0 if step < TIGHT_STEPS else scale)
         pl.advance()
     pl.close()
+
+
+@pytest.mark.gpu
+def test_gpu_rollout_with_generated_waypoints(cuda_lib, oracle):
+    """Closed loop entirely through the C ABI: waypoints from dlsc_wp_step (comm-range groups + PIBT + update rules), replans
+    and state steps on the GPU -- no recorded input at all besides the mission -- stay on the reference's CPLEX log for
+    all 137 steps, and the generated waypoints equal the ones recovered from that log."""
+    cfg, m = _parity.load_case("maze10")
+    p = _parity.oracle_params(cfg, m)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=9, lib=cuda_lib)
+    pl.build_edt(m.boxes)
+    dist, obst, dims, mk = pl.get_edt()
+    wp = capi.WaypointProvider(cfg, m, lib=cuda_lib, edt=(dist, obst, dims, mk, cfg.world_res))
+    state, wps, scale = fixtures()
+    wcur = pl.start.copy()
+    traj = None
+    for step in range(len(wps)):
+        pos, _, _ = pl.state()
+        wcur = wp.step(pos, pl.goal() if step else pl.start, traj, wcur)
+        assert np.array_equal(wcur, wps[step]), step
+        pl.set_agents(waypoint=wcur)
+        pl.plan()
+        assert (pl.status() & capi.FAIL_MASK).max() == 0
+        traj = pl.traj()
+        check_step(oracle, p, traj, step, state, 1.0 if step < TIGHT_STEPS else scale)
+        pl.advance()
+    pl.close(); wp.close()
