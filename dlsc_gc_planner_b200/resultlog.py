@@ -55,3 +55,60 @@ def read(path):
     rows = np.array([[float(c) for c in l.split(",")] for l in lines[1:]], np.float64).reshape(len(lines) - 1, n, 12)
     return (rows[:, 0, 1], rows[:, :, 2:5].astype(np.float32), rows[:, :, 5:8].astype(np.float32),
             rows[:, :, 8:11].astype(np.float32), rows[:, :, 11])
+
+
+# ---- summary file (MultiSyncSimulator::saveSummarizedResultAsCSV, reference src/multi_sync_simulator.cpp:852-900) ----
+SUMMARY_COLUMNS = ("start_time,total_flight_time,total_flight_distance,safety_ratio_agent,safety_ratio_obs,"
+                   "mapf_time_average,mapf_time_min,mapf_time_max,planning_time_average,planning_time_min,planning_time_max,"
+                   "initial_traj_planning_time,obstacle_prediction_time,goal_planning_time,lsc_generation_time,"
+                   "sfc_generation_time,traj_optimization_time,mission_file_name,world_file_name,planner_mode,goal_mode,mapf_mode,"
+                   "communication_range,world_dimension,M,dt")
+
+
+def total_flight_distance(pos):
+    """getTotalDistance (:902-911): sum over agents of the polyline length through the recorded positions [T][N][3]
+    (point3d differences are float, every norm is sqrt of a float sum of squares)."""
+    p = np.asarray(pos, np.float32)
+    d = (p[1:] - p[:-1]).astype(np.float32)
+    nsq = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32) + d[..., 2] * d[..., 2]).astype(np.float32)
+    return float(np.sqrt(nsq.astype(np.float64)).sum())
+
+
+def safety_ratio_agents(pos, radius, downwash):
+    """Minimum over recorded times and agent pairs of the downwash-scaled distance / (r_i + r_j)
+    (:653-674, ellipsoidalDistance include/util.hpp:163-167)."""
+    p = np.asarray(pos, np.float32)
+    r = np.asarray(radius, np.float64); dw = np.asarray(downwash, np.float64)
+    best = 1e9                                       # SP_INFINITY is the initial value the reference prints when nothing is closer
+    for i in range(p.shape[1]):
+        for j in range(p.shape[1]):
+            if i == j:
+                continue
+            k = (dw[i] * r[i] + dw[j] * r[j]) / (r[i] + r[j])
+            d = (p[:, i] - p[:, j]).astype(np.float32)
+            d[:, 2] = (d[:, 2].astype(np.float64) / k).astype(np.float32)
+            nsq = ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]).astype(np.float32)
+            best = min(best, float(np.sqrt(nsq.astype(np.float64)).min() / (r[i] + r[j])))
+    return best
+
+
+def format_summary(start_time, total_flight_time, total_distance, safety_agent, safety_obs, mapf, planning, stage_means,
+                   mission_file, world_file, planner_mode="DLSCGC", goal_mode="grid_based_planner", mapf_mode="pibt",
+                   communication_range=3, world_dimension=2, M=10, dt=0.2):
+    """One row.  start_time is written as the reference's string (ros::Time as "sec.usec"); mapf / planning = (average, min,
+    max) seconds; stage_means = averages of (initial_traj, obstacle_prediction, goal, lsc, sfc, traj_optimization) seconds."""
+    cells = [str(start_time), _g(total_flight_time), _g(total_distance), _g(safety_agent), _g(safety_obs)]
+    cells += [_g(x) for x in mapf] + [_g(x) for x in planning] + [_g(x) for x in stage_means]
+    cells += [mission_file, world_file, planner_mode, goal_mode, mapf_mode, _g(communication_range), str(int(world_dimension)),
+              str(int(M)), _g(dt)]
+    return ",".join(cells)
+
+
+def append_summary(path, row):
+    """Appends a row, writing the column line first when the file is new or empty (as the reference does)."""
+    import os
+    new = not os.path.exists(path) or os.path.getsize(path) == 0
+    with open(path, "a") as f:
+        if new:
+            f.write(SUMMARY_COLUMNS + "\n")
+        f.write(row + "\n")

@@ -74,3 +74,25 @@ def test_gpu_first_replan_writes_the_reference_log(cuda_lib, oracle, tmp_path):
     log.close()
     pl.close()
     assert open(out).read() == open(HEAD).read()
+
+
+def test_summary_row_reproduces_the_reference_summary_file(tmp_path):
+    """log/summary_DLSCGC_10agents.csv (fixture tests/golden/summary_ref.csv): the columns, the formatting, and the two
+    derived quantities that can be recomputed from the reference's own result log -- total flight distance and the minimum
+    inter-agent safety ratio over all recorded times -- come out as the reference printed them."""
+    ref = open(os.path.join(_parity.ROOT, "tests", "golden", "summary_ref.csv")).read().strip().split("\n")
+    assert ref[0] == resultlog.SUMMARY_COLUMNS
+    want = ref[1].split(",")
+    z = np.load(os.path.join(_parity.ROOT, "tests", "golden", "golden_log_full.npz"))
+    pos = z["state"][:, :, 0:3].astype(np.float32)
+    dist = resultlog.total_flight_distance(pos)
+    safety = resultlog.safety_ratio_agents(pos, np.full(10, 0.15), np.full(10, 2.0))
+    assert resultlog._g(dist) == want[2] == "134.096"
+    assert resultlog._g(safety) == want[3] == "1.00058"
+    f = lambda lo, hi: [float(x) for x in want[lo:hi]]
+    row = resultlog.format_summary(want[0], float(want[1]), dist, safety, 1e9, f(5, 8), f(8, 11), f(11, 17), want[17], want[18],
+                                   communication_range=3, world_dimension=2, M=10, dt=0.2)
+    assert row == ref[1]
+    p = tmp_path / "summary.csv"
+    resultlog.append_summary(str(p), row); resultlog.append_summary(str(p), row)
+    assert open(p).read() == ref[0] + "\n" + ref[1] + "\n" + ref[1] + "\n"
