@@ -20,11 +20,13 @@ def test_two_rank_bench_replays_exactly(cuda_lib, exchange):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29531" if exchange == "p2p" else "29532", os.path.join(_parity.ROOT, "bench.py"), "--gpus", "2",
-           "--agents", "512", "--steps", "6", "--warmup", "3", "--settle", "8", "--no-cpu-baseline", "--exchange", exchange]
+           "--agents", "512", "--max-nbr", "192", "--steps", "6", "--warmup", "3", "--settle", "8", "--no-cpu-baseline",
+           "--mc-missions", "4", "--mc-steps", "4", "--exchange", exchange]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=_parity.ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
     assert d["n_gpus"] == 2 and d["pilot"]["replay_exact"] and d["e2e"]["replay_exact"]
     assert d["pilot"]["qp_failsafe_agents"] == 0
-    assert exchange in d["config"]["parallelism"].lower() or (exchange == "p2p" and "peer-memory" in d["config"]["parallelism"])
+    assert ("peer-memory" if exchange == "p2p" else "NCCL") in d["exchange"]
+    assert d["montecarlo"]["replay_exact"] and d["montecarlo"]["missions"] == 8
