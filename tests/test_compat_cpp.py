@@ -62,3 +62,57 @@ def test_compat_driver_serial_equals_batched():
     assert int(re.search(r"seq (\d+)", outs["serial"][24]).group(1)) == 25
     end = [float(x) for x in re.search(r"solve end (\S+) (\S+) (\S+)", outs["serial"][-1]).groups()]
     assert 1.9 - 1e-6 <= end[0] <= 1.9 + 1e-4 and abs(end[1]) < 1e-5 and abs(end[2] - 1.0) < 1e-5
+
+
+REALTREE = os.path.join(_parity.ROOT, "tests", "cpp", "realtree")
+SIG = os.path.join(_parity.ROOT, "tests", "cpp", "signature_check.cpp")
+
+
+def test_member_signatures_are_exactly_the_references():
+    """Every public member of the three classes has exactly the reference's type -- static_asserts on member
+    pointers -- with the stand-in third-party types AND with headers that spell the real ros / octomap / dynamicEDT3D / Eigen
+    APIs (tests/cpp/realtree), which also compiles the live-DynamicEDTOctomap export."""
+    inc = "-I" + os.path.join(_parity.ROOT, "include")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", inc, "-DDLSC_COMPAT_STANDALONE", SIG])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", inc, "-I" + REALTREE, SIG])
+
+
+@pytest.mark.gpu
+def test_real_tree_map_binding(oracle):
+    """Real-tree mode: the grid reaches the device through DynamicEDTOctomap::getDistanceAndClosestObstacle (one call per
+    cell centre, SwarmBatch::set_distmap); a maze mission planned that way equals the same mission with the grid handed over
+    directly through dlsc_set_edt."""
+    import numpy as np
+    from dlsc_gc_planner_b200 import missions
+    capi.build_library()
+    libdir = os.path.dirname(capi.LIB_PATH)
+    exe = os.path.join(_parity.ROOT, "tests", "cpp", "realtree_driver")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(_parity.ROOT, "include"), "-I" + REALTREE, SIG, "-o", exe,
+                           "-L" + libdir, "-ldlsc_b200", "-Wl,-rpath," + libdir])
+    cfg, m = _parity.load_case("maze10")
+    m = _parity.subset(m, 3)
+    sw = _parity.make_oracle(cfg, m, 2)
+    tmp = os.path.join(_parity.ROOT, "tests", "cpp")
+    fd, fo = os.path.join(tmp, "_dist.bin"), os.path.join(tmp, "_obst.bin")
+    sw.edt.dist.astype(np.float32).tofile(fd); sw.edt.obst.astype(np.int32).tofile(fo)
+    start = m.start.copy(); start[:, 2] = cfg.z_2d
+    goal = m.goal.copy(); goal[:, 2] = cfg.z_2d
+    args = [exe, fd, fo] + [str(x) for x in sw.edt.dims] + [str(x) for x in sw.edt.min_key] + ["3"] + \\
+           [repr(float(x)) for x in m.world_min] + [repr(float(x)) for x in m.world_max]
+    for a in range(3):
+        args += [repr(float(x)) for x in start[a]] + [repr(float(x)) for x in goal[a]]
+    out = subprocess.check_output(args, text=True).strip().split("\\n")
+    os.remove(fd); os.remove(fo)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=2)
+    pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
+    wts = (np.arange(1, cfg.M + 1)[:, None] * np.arange(1, cfg.n + 2)[None, :]).astype(np.float64)
+    for step in range(3):
+        pl.set_agents(waypoint=pl.start)
+        pl.plan()
+        t = pl.traj().astype(np.float64)
+        checksum = float(sum((wts * (t[a, :, :, 0] + 2.0 * t[a, :, :, 1])).sum() for a in range(3)))
+        got = float(re.search(r"checksum (\\S+)", out[step]).group(1))
+        assert abs(got - checksum) < 1e-6 * max(1.0, abs(checksum)), (step, got, checksum)
+        pl.publish_records()
+        pl.set_agents(pos=pl.traj()[:, 1, 0], vel=np.zeros((3, 3), np.float32), acc=np.zeros((3, 3), np.float32))
+    pl.close()
