@@ -97,11 +97,11 @@ def test_real_tree_map_binding(oracle):
     sw.edt.dist.astype(np.float32).tofile(fd); sw.edt.obst.astype(np.int32).tofile(fo)
     start = m.start.copy(); start[:, 2] = cfg.z_2d
     goal = m.goal.copy(); goal[:, 2] = cfg.z_2d
-    args = [exe, fd, fo] + [str(x) for x in sw.edt.dims] + [str(x) for x in sw.edt.min_key] + ["3"] + \\
-           [repr(float(x)) for x in m.world_min] + [repr(float(x)) for x in m.world_max]
+    args = ([exe, fd, fo] + [str(x) for x in sw.edt.dims] + [str(x) for x in sw.edt.min_key] + ["3"] +
+            [repr(float(x)) for x in m.world_min] + [repr(float(x)) for x in m.world_max])
     for a in range(3):
         args += [repr(float(x)) for x in start[a]] + [repr(float(x)) for x in goal[a]]
-    out = subprocess.check_output(args, text=True).strip().split("\\n")
+    out = subprocess.check_output(args, text=True).strip().split("\n")
     os.remove(fd); os.remove(fo)
     pl = capi.SwarmPlanner(cfg, m, max_nbr=2)
     pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
@@ -111,7 +111,7 @@ def test_real_tree_map_binding(oracle):
         pl.plan()
         t = pl.traj().astype(np.float64)
         checksum = float(sum((wts * (t[a, :, :, 0] + 2.0 * t[a, :, :, 1])).sum() for a in range(3)))
-        got = float(re.search(r"checksum (\\S+)", out[step]).group(1))
+        got = float(re.search(r"checksum (\S+)", out[step]).group(1))
         assert abs(got - checksum) < 1e-6 * max(1.0, abs(checksum)), (step, got, checksum)
         pl.publish_records()
         pl.set_agents(pos=pl.traj()[:, 1, 0], vel=np.zeros((3, 3), np.float32), acc=np.zeros((3, 3), np.float32))
