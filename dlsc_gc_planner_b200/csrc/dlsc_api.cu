@@ -55,6 +55,13 @@ struct dlsc_ctx {
         volatile int* err_host = nullptr;          // host view: polled without synchronising
         bool failed = false;                       // sticky
     } p2p;
+    // CUDA graphs of one whole dlsc_step (all stages, both streams): replayed instead of ~12 separate launches.  Kernel
+    // parameters are baked in, so an entry is keyed by the DevParams / DevState bytes it was captured with (the record
+    // pointer alternates between the two peer-memory buffers: two entries).
+    struct StepGraph { cudaGraphExec_t exec = nullptr; DevParams P; DevState S; int kernels = 0; };
+    StepGraph graphs[2];
+    int graph_next = 0;
+    bool use_graph = true;             // DLSC_GRAPH=0 disables
     double edt_build_ms = 0.0;         // device time of the last dlsc_build_edt* (the three EDT passes)
     double margin_host = 0.0;          // radius of the first local agent (all BASELINE missions: 0.15 for every agent)
     int64_t launches = 0;
@@ -199,6 +206,8 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     {
         const char* ov = getenv("DLSC_OVERLAP");
         c->overlap = !(ov && ov[0] == '0');
+        const char* gv = getenv("DLSC_GRAPH");
+        c->use_graph = !(gv && gv[0] == '0');
     }
     c->own_stream = true;
     memset(c->t_ms, 0, sizeof(c->t_ms));
@@ -273,6 +282,7 @@ void dlsc_destroy(dlsc_ctx* c) {
         cudaFree(c->p2p.block); cudaFree(c->p2p.done);
         if (c->p2p.err_host) cudaFreeHost((void*)c->p2p.err_host);
     }
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -680,7 +690,7 @@ int dlsc_get_records(dlsc_ctx* c, int first, int count, float* host) {
     return 0;
 }
 
-static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& P, const DevState& S);
+static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& P, const DevState& S, int seq_override = -1);
 
 int dlsc_run_stages(dlsc_ctx* c, int mask) {
     if (!c) return fail("null ctx");
@@ -711,7 +721,7 @@ int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
     return run_stages_impl(c, mask, P, S);
 }
 
-static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const DevState& Sr) {
+static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const DevState& Sr, int seq_override) {
     CK(cudaSetDevice(c->device));
     if (p2p_check(c)) return -1;
     if ((mask & DLSC_STAGE_SFC) && c->P.use_sfc && !c->have_edt) return fail("dlsc_run_stages: use_sfc set but no EDT grid (dlsc_set_edt)");
@@ -720,7 +730,8 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     Sfix.edt = c->S.edt;            // the grid may have been (re)set after a subset view was built
     const DevState& Sx = Sfix;
     cudaStream_t st = c->stream;
-    const int seq = c->seq + 1;     // planner_seq after the increment in TrajPlanner::plan (traj_planner.cpp:40)
+    // planner_seq after the increment in TrajPlanner::plan (traj_planner.cpp:40); the kernels only ask "seq < 2?"
+    const int seq = seq_override >= 0 ? seq_override : c->seq + 1;
     const bool tm = c->timing;
     cudaEvent_t* ev = nullptr;
     if (tm) {
@@ -757,7 +768,47 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     return 0;
 }
 
+// One whole step as a CUDA graph.  Usable from the second replan on (the first one takes the constant-velocity branch of
+// the prediction, a different kernel argument), outside the per-stage timing mode, once the distance grid is in place.
+static int step_graph(dlsc_ctx* c, bool& done) {
+    done = false;
+    if (!c->use_graph || c->timing || c->seq + 1 < 2) return 0;
+    if (c->P.use_sfc && (!c->have_edt || c->mask_dirty)) return 0;
+    CK(cudaSetDevice(c->device));
+    if (p2p_check(c)) return -1;
+    dlsc_ctx::StepGraph* g = nullptr;
+    for (auto& e : c->graphs)
+        if (e.exec && memcmp(&e.P, &c->P, sizeof(DevParams)) == 0 && memcmp(&e.S, &c->S, sizeof(DevState)) == 0) g = &e;
+    if (!g) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return 0;   // caller is capturing
+        g = &c->graphs[c->graph_next];
+        c->graph_next ^= 1;
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        const int64_t l0 = c->launches;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+        const int rc = run_stages_impl(c, DLSC_STAGE_ALL, c->P, c->S, 2);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        g->kernels = (int)(c->launches - l0);
+        c->launches = l0;
+        if (rc != 0 || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); c->use_graph = false; return 0; }
+        const cudaError_t ei = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { g->exec = nullptr; cudaGetLastError(); c->use_graph = false; return 0; }
+        g->P = c->P; g->S = c->S;
+    }
+    CK(cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->kernels;
+    done = true;
+    return 0;
+}
+
 int dlsc_step(dlsc_ctx* c) {
+    if (!c) return fail("null ctx");
+    bool done = false;
+    if (step_graph(c, done)) return -1;
+    if (done) { c->seq++; return 0; }
     const int rc = dlsc_run_stages(c, DLSC_STAGE_ALL);
     if (rc == 0) c->seq++;
     return rc;
