@@ -50,6 +50,16 @@ class DlscAgentProps(C.Structure):
                 ("max_acc", C.c_void_p), ("nominal_vel", C.c_void_p)]
 
 
+class DlscObstacles(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos", C.c_void_p), ("vel", C.c_void_p), ("radius", C.c_void_p),
+                ("downwash", C.c_void_p), ("max_acc", C.c_void_p)]
+
+
+class DlscObstacleParams(C.Structure):
+    _fields_ = [("slack_collision_weight", C.c_double), ("uncertainty_horizon", C.c_double),
+                ("size_prediction", C.c_int32), ("reserved0", C.c_int32)]
+
+
 EXPORTS = (
     "dlsc_last_error dlsc_abi_version dlsc_device_count dlsc_create dlsc_destroy dlsc_set_stream dlsc_get_stream "
     "dlsc_set_edt dlsc_set_agent_props dlsc_reset dlsc_set_agents dlsc_records_device dlsc_record_floats "
@@ -62,7 +72,8 @@ EXPORTS = (
     "dlsc_set_pred_traj dlsc_set_neighbours dlsc_set_lsc dlsc_set_groups dlsc_edt_dims dlsc_build_edt "
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
     "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build dlsc_wp_last_error dlsc_wp_create dlsc_wp_destroy "
-    "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps").split()
+    "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps "
+    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred").split()
 
 
 def build_library(force=False):
@@ -248,6 +259,45 @@ class SwarmPlanner:
         g = np.ascontiguousarray(group, np.int32)
         assert g.shape == (self.NL,)
         self._ck(self.lib.dlsc_set_groups(self.ctx, _p(g)))
+
+    def set_obstacles(self, pos, vel=None, radius=0.15, downwash=1.0, max_acc=0.0, slack_weight=1.0,
+                      size_prediction=True, uncertainty_horizon=1.0):
+        """Dynamic (non-agent) obstacles of the next replans (dlsc_set_obstacles); pos=None removes them.  Scalars are
+        broadcast.  Mirrors the Obstacle list TrajPlanner::setObstacles receives for non-agent entries plus the three
+        Param fields the dynamic-obstacle path reads."""
+        if pos is None:
+            self._ck(self.lib.dlsc_set_obstacles(self.ctx, None, None))
+            self.n_dyn = 0
+            return
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        vel = np.ascontiguousarray(np.zeros((n, 3)) if vel is None else vel, np.float32).reshape(n, 3)
+        full = lambda v: np.full(n, v, np.float64) if np.isscalar(v) else np.ascontiguousarray(v, np.float64)
+        radius, downwash, max_acc = full(radius), full(downwash), full(max_acc)
+        o = DlscObstacles(n, _p(pos), _p(vel), _p(radius), _p(downwash), _p(max_acc))
+        op = DlscObstacleParams(float(slack_weight), float(uncertainty_horizon), int(bool(size_prediction)), 0)
+        self._ck(self.lib.dlsc_set_obstacles(self.ctx, C.byref(o), C.byref(op)))
+        self.n_dyn = n
+
+    def slack(self):
+        """[n_local][n_obstacles][M] slack variables of the last QP (<= 0)."""
+        nd = getattr(self, "n_dyn", 0)
+        out = np.zeros((self.NL, nd, self.M), np.float64)
+        if nd:
+            self._ck(self.lib.dlsc_get_slack(self.ctx, _p(out)))
+        return out
+
+    def trap(self):
+        out = np.zeros(self.NL, np.uint8)
+        self._ck(self.lib.dlsc_get_trap(self.ctx, _p(out)))
+        return out
+
+    def obstacle_pred(self):
+        nd = getattr(self, "n_dyn", 0)
+        out = np.zeros((nd, self.M, 6, 3), np.float32)
+        if nd:
+            self._ck(self.lib.dlsc_get_obstacle_pred(self.ctx, _p(out)))
+        return out
 
     def set_agents(self, pos=None, vel=None, acc=None, waypoint=None, disturbed=None):
         f = lambda x: None if x is None else np.ascontiguousarray(x, np.float32)

@@ -2,6 +2,7 @@
 // No CPU fallback: every entry point requires a usable CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -83,6 +84,7 @@ struct dlsc_ctx {
     } while (0)
 
 static int fail(const char* msg) { g_err = msg; return -1; }
+extern "C" { static int d2h_raw(dlsc_ctx* c, void* host, const void* dev, size_t bytes); }
 
 template <class T>
 static int dev_alloc(dlsc_ctx* c, T** p, size_t n) {
@@ -227,7 +229,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.sfc_init, NL);
     rc |= dev_alloc(c, &S.radius, NL); rc |= dev_alloc(c, &S.downwash, NL); rc |= dev_alloc(c, &S.max_vel, NL);
     rc |= dev_alloc(c, &S.max_acc, NL); rc |= dev_alloc(c, &S.nominal_vel, NL);
-    rc |= dev_alloc(c, &S.pred_traj, N * npt * 3);
+    rc |= dev_alloc(c, &S.pred_traj, (N + kMaxDyn) * npt * 3);
     rc |= dev_alloc(c, &S.init_traj, NL * npt * 3);
     rc |= dev_alloc(c, &S.nbr_idx, NL * K);
     rc |= dev_alloc(c, &S.nbr_cnt, NL);
@@ -249,6 +251,12 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     rc |= dev_alloc(c, &S.nbr_sorted_pos, (size_t)N);
     rc |= dev_alloc(c, &S.qp_list_gi, (size_t)NL);
     rc |= dev_alloc(c, &S.qp_seed, (size_t)NL * 4);
+    rc |= dev_alloc(c, &S.dyn_pos, (size_t)kMaxDyn * 3); rc |= dev_alloc(c, &S.dyn_vel, (size_t)kMaxDyn * 3);
+    rc |= dev_alloc(c, &S.dyn_radius, (size_t)kMaxDyn); rc |= dev_alloc(c, &S.dyn_downwash, (size_t)kMaxDyn);
+    rc |= dev_alloc(c, &S.dyn_max_acc, (size_t)kMaxDyn);
+    rc |= dev_alloc(c, &S.dyn_size, (size_t)kMaxDyn * M * kP);
+    rc |= dev_alloc(c, &S.comm_box, NL * 6);
+    rc |= dev_alloc(c, &S.trap, NL);
     if (rc) { dlsc_destroy(c); return -1; }
 
     build_qp_tables(hp->M, hp->dim, hp->dt, hp->w_control, hp->w_terminal, hp->comm_range > 0, c->th);
@@ -510,6 +518,49 @@ int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
     return 0;
 }
 
+int dlsc_set_obstacles(dlsc_ctx* c, const dlsc_obstacles* o, const dlsc_obstacle_params* op) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    const int n = o ? o->n : 0;
+    if (n < 0 || n > kMaxDyn) return fail("dlsc_set_obstacles: at most 16 dynamic obstacles");
+    if (n == 0) { c->P.n_dyn = 0; return 0; }
+    if (!o->pos || !o->vel || !o->radius || !o->downwash || !o->max_acc || !op) return fail("dlsc_set_obstacles: null member");
+    if (!(op->slack_collision_weight > 0)) return fail("dlsc_set_obstacles: slack_collision_weight must be positive");
+    if (c->P.qp_solver == 1) return fail("dlsc_set_obstacles: the interior-point-only solver (qp_solver = 1) has no slack variables");
+    if (n >= c->P.K) return fail("dlsc_set_obstacles: max_nbr must exceed the number of dynamic obstacles");
+    if (!c->S.qp_slack && dev_alloc(c, &c->S.qp_slack, (size_t)c->P.NL * kMaxDyn * c->P.M)) return -1;
+    std::vector<double> size((size_t)n * c->P.M * kP);
+    for (int i = 0; i < n; i++) {
+        if (!(o->radius[i] > 0)) return fail("dlsc_set_obstacles: radius must be positive");
+        dyn_obstacle_sizes(c->P, op->size_prediction != 0, op->uncertainty_horizon, o->radius[i], o->max_acc[i], size.data() + (size_t)i * c->P.M * kP);
+    }
+    CK(cudaMemcpyAsync(c->S.dyn_pos, o->pos, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->S.dyn_vel, o->vel, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->S.dyn_radius, o->radius, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->S.dyn_downwash, o->downwash, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->S.dyn_max_acc, o->max_acc, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->S.dyn_size, size.data(), size.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));       // the host arrays may go away after the call
+    c->P.n_dyn = n;
+    c->P.slack_w = op->slack_collision_weight;
+    c->P.dyn_horizon = op->uncertainty_horizon;
+    return 0;
+}
+int dlsc_get_slack(dlsc_ctx* c, double* slack) {
+    if (!c || !slack) return fail("dlsc_get_slack: null argument");
+    const int nd = c->P.n_dyn, M = c->P.M;
+    if (nd == 0) return 0;
+    std::vector<double> tmp((size_t)c->P.NL * kMaxDyn * M);
+    if (d2h_raw(c, tmp.data(), c->S.qp_slack, tmp.size() * 8)) return -1;
+    for (int a = 0; a < c->P.NL; a++)
+        memcpy(slack + (size_t)a * nd * M, tmp.data() + (size_t)a * kMaxDyn * M, (size_t)nd * M * 8);
+    return 0;
+}
+int dlsc_get_trap(dlsc_ctx* c, uint8_t* trap) {
+    if (!c || !trap) return fail("dlsc_get_trap: null argument");
+    return d2h_raw(c, trap, c->S.trap, (size_t)c->P.NL);
+}
+
 int dlsc_reset(dlsc_ctx* c, const float* start) {
     if (!c || !start) return fail("dlsc_reset: null argument");
     CK(cudaSetDevice(c->device));
@@ -710,6 +761,8 @@ static void make_view(const dlsc_ctx* c, int first, int count, DevParams& P, Dev
     S.sfc += f * M * 6; S.traj += f * npt * 3; S.qp_x += f * (size_t)P.D * npt;
     S.cost += f; S.viol += f; S.qp_iters += f; S.status += f;
     S.qp_list += f; S.qp_list_gi += f; S.qp_seed += f * 4;
+    S.comm_box += f * 6; S.trap += f;
+    if (S.qp_slack) S.qp_slack += f * kMaxDyn * M;
 }
 
 int dlsc_run_stages_subset(dlsc_ctx* c, int mask, int first, int count) {
@@ -742,7 +795,10 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
         CK(cudaMemsetAsync(c->S.counters, 0, DLSC_N_COUNTERS * sizeof(unsigned long long), st));
     if (tm) CK(cudaEventRecord(ev[0], st));
-    if (mask & DLSC_STAGE_PREDICT) { launch_predict(Pr, Sx, seq, st); c->launches++; }
+    if (mask & DLSC_STAGE_PREDICT) {
+        launch_predict(Pr, Sx, seq, st); c->launches++;
+        if (Pr.n_dyn > 0) { launch_dyn_predict(Pr, Sx, st); c->launches++; }
+    }
     if (tm) CK(cudaEventRecord(ev[1], st));
     const bool sfc_on = (mask & DLSC_STAGE_SFC) && c->P.use_sfc;
     const bool fork = sfc_on && (mask & DLSC_STAGE_LSC) && !tm && c->overlap && c->side_stream;
@@ -759,6 +815,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     if (fork) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     else if (sfc_on) { launch_sfc(Pr, Sx, st); c->launches++; }
     if (tm) CK(cudaEventRecord(ev[4], st));
+    if (Pr.n_dyn > 0 && (mask & DLSC_STAGE_GOAL)) { launch_trap(Pr, Sx, st); c->launches++; }   // checkWaypointTrap sits between SFC and goal
     if (mask & DLSC_STAGE_GOAL) { launch_goal(Pr, Sx, st); c->launches++; }
     else if (mask & DLSC_STAGE_QP) { launch_goal_copy(Pr, Sx, st); c->launches++; }   // QP alone: goal from the record
     if (tm) CK(cudaEventRecord(ev[5], st));
@@ -839,6 +896,8 @@ int dlsc_sync(dlsc_ctx* c) {
 int dlsc_get_seq(const dlsc_ctx* c) { return c ? c->seq : -1; }
 int dlsc_set_seq(dlsc_ctx* c, int seq) { if (!c) return fail("null ctx"); c->seq = seq; return 0; }
 
+static int d2h(dlsc_ctx* c, void* host, const void* dev, size_t bytes);
+static int d2h_raw(dlsc_ctx* c, void* host, const void* dev, size_t bytes) { return d2h(c, host, dev, bytes); }
 static int d2h(dlsc_ctx* c, void* host, const void* dev, size_t bytes) {
     if (!c || !host) return fail("null argument");
     CK(cudaSetDevice(c->device));
@@ -855,6 +914,9 @@ int dlsc_get_qp_iters(dlsc_ctx* c, int32_t* v) { return c ? d2h(c, v, c->S.qp_it
 int dlsc_get_status(dlsc_ctx* c, int32_t* v) { return c ? d2h(c, v, c->S.status, (size_t)c->P.NL * 4) : fail("null ctx"); }
 int dlsc_get_init_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.init_traj, (size_t)c->P.NL * c->P.M * kP * 12) : fail("null ctx"); }
 int dlsc_get_pred_traj(dlsc_ctx* c, float* t) { return c ? d2h(c, t, c->S.pred_traj, (size_t)c->P.N * c->P.M * kP * 12) : fail("null ctx"); }
+int dlsc_get_obstacle_pred(dlsc_ctx* c, float* t) {
+    return c ? d2h(c, t, c->S.pred_traj + (size_t)c->P.N * c->P.M * kP * 3, (size_t)c->P.n_dyn * c->P.M * kP * 12) : fail("null ctx");
+}
 int dlsc_get_sfc(dlsc_ctx* c, float* s) { return c ? d2h(c, s, c->S.sfc, (size_t)c->P.NL * c->P.M * 24) : fail("null ctx"); }
 
 int dlsc_get_goal(dlsc_ctx* c, float* goal) { return c ? d2h(c, goal, c->S.goal_new, (size_t)c->P.NL * 12) : fail("null ctx"); }

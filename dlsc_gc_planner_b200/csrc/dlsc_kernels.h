@@ -21,7 +21,7 @@ struct DevState {
     uint8_t* disturbed;        // [NL]
     uint8_t* sfc_init;         // [NL]
     double *radius, *downwash, *max_vel, *max_acc, *nominal_vel;   // [NL]
-    float* pred_traj;          // [N][M][P][3]
+    float* pred_traj;          // [N + kMaxDyn][M][P][3]  (rows N.. : constant-velocity predictions of the dynamic obstacles)
     float* init_traj;          // [NL][M][P][3]
     int32_t* nbr_idx;          // [NL][K]
     int32_t* nbr_cnt;          // [NL]
@@ -44,6 +44,13 @@ struct DevState {
     int* qp_list;              // [NL] agents queued for the interior-point fallback
     int* qp_list_gi;           // [NL] agents the fast path (k_qp_fast) could not finish: they run the dual active set
     double* qp_seed;           // [NL][4] {violation, row id, screened, violated rows} of the scan at the unconstrained optimum
+    // dynamic (non-agent) obstacles (dlsc_set_obstacles)
+    float *dyn_pos, *dyn_vel;  // [kMaxDyn][3]
+    double *dyn_radius, *dyn_downwash, *dyn_max_acc;   // [kMaxDyn]
+    double* dyn_size;          // [kMaxDyn][M][P] predicted sizes (obstacleSizePredictionWithConstAcc)
+    float* comm_box;           // [NL][6] CollisionConstraints::communication_range (zero until first built)
+    double* qp_slack;          // [NL][kMaxDyn][M] slack variables of the last QP
+    uint8_t* trap;             // [NL] checkWaypointTrap outcome of the last step
     EdtDev edt;
 };
 
@@ -54,6 +61,8 @@ int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, in
 int launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st);   // returns launches
 void launch_sfc(const DevParams& P, const DevState& S, cudaStream_t st);
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st);
+void launch_dyn_predict(const DevParams& P, const DevState& S, cudaStream_t st);   // n_dyn > 0: obstacle predictions, comm boxes, list heads
+void launch_trap(const DevParams& P, const DevState& S, cudaStream_t st);          // n_dyn > 0: checkWaypointTrap, before the goal stage
 void launch_goal_copy(const DevParams& P, const DevState& S, cudaStream_t st);   // goal_new := record goal
 void launch_advance(const DevParams& P, const DevState& S, bool move, cudaStream_t st);
 void launch_edt_pack(const float* dist, const int32_t* obst, int4* cells, size_t ncell, cudaStream_t st);

@@ -34,6 +34,26 @@ void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t
     k_predict<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, S, seq);
 }
 
+// dynamic obstacles (P.n_dyn > 0 only): constant-velocity predictions (traj_planner.cpp:303-305) into rows N.. of
+// pred_traj; per local agent the communication box of this step and the heads of the obstacle list
+__global__ void __launch_bounds__(128) k_dyn_predict(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int npt = P.M * kP, nd = P.n_dyn;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nd * npt) {
+        const int o = t / npt, pt = t - o * npt;
+        v3_store(S.pred_traj + ((size_t)(P.N + o) * npt + pt) * 3, v3_load(S.dyn_pos + 3 * o) + v3_load(S.dyn_vel + 3 * o) * P.tk[pt]);
+    }
+    if (t < P.NL) {
+        const bool init = S.sfc_init[t] != 0 || S.disturbed[t] != 0;
+        comm_box_update(P, init, v3_load(S.waypoint + t * 3), S.comm_box + (size_t)t * 6);
+        for (int o = 0; o < nd; o++) S.nbr_idx[(size_t)t * P.K + o] = P.N + o;
+    }
+}
+void launch_dyn_predict(const DevParams& P, const DevState& S, cudaStream_t st) {
+    const int n = P.n_dyn * P.M * kP > P.NL ? P.n_dyn * P.M * kP : P.NL;
+    k_dyn_predict<<<(n + 127) / 128, 128, 0, st>>>(P, S);
+}
+
 // ------------------------------------------------------------------------------------------------
 // warp per agent; the 16 warps of a CTA share position tiles staged in shared memory (the positions sit inside
 // the 768-byte records: each is fetched once per CTA instead of once per warp).  Ballot compaction keeps the
@@ -49,7 +69,8 @@ __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__
     const int off = P.M * kP * 3;
     const V3 pa = valid ? v3_load(S.rec + (size_t)a * P.rec + off) : v3(0.f, 0.f, 0.f);
     const float ga = valid ? S.rec[(size_t)a * P.rec + off + 11] : 0.f;
-    int32_t* idx_out = S.nbr_idx + (size_t)la * P.K;
+    const int Kc = P.K - P.n_dyn;                      // the dynamic obstacles hold the first slots
+    int32_t* idx_out = S.nbr_idx + (size_t)la * P.K + P.n_dyn;
     int count = 0;
     for (int base = 0; base < P.N; base += kNbrTile) {
         const int jt = base + threadIdx.x;
@@ -79,15 +100,15 @@ __global__ void __launch_bounds__(kNbrTile) k_neighbours(const __grid_constant__
                 if (t + lane < nt && j != a && tile[(t + lane) * 4 + 3] == ga) in = in_comm_range(P, pa, v3_load(tile + (t + lane) * 4));
                 const unsigned mask = __ballot_sync(0xffffffffu, in);
                 const int pos = count + __popc(mask & ((1u << lane) - 1u));
-                if (in && pos < P.K) idx_out[pos] = j;
+                if (in && pos < Kc) idx_out[pos] = j;
                 count += __popc(mask);
             }
         __syncthreads();
     }
     if (valid && lane == 0) {
-        S.nbr_cnt[la] = count < P.K ? count : P.K;
-        if (count > P.K) atomicOr(S.status + la, kStNbrOverflow);
-        atomicAdd(S.counters + 0, (unsigned long long)(count < P.K ? count : P.K));
+        S.nbr_cnt[la] = P.n_dyn + (count < Kc ? count : Kc);
+        if (count > Kc) atomicOr(S.status + la, kStNbrOverflow);
+        atomicAdd(S.counters + 0, (unsigned long long)(count < Kc ? count : Kc));
     }
 }
 
@@ -187,7 +208,8 @@ __global__ void __launch_bounds__(kNbrSearchWarps * 32) k_nbr_search(const __gri
     const float* ra = S.rec + (size_t)a * P.rec + off;
     const V3 pa = v3_load(ra);
     const float ga = ra[11];
-    int32_t* idx_out = S.nbr_idx + (size_t)la * P.K;
+    const int Kc = P.K - P.n_dyn;                      // the dynamic obstacles hold the first slots
+    int32_t* idx_out = S.nbr_idx + (size_t)la * P.K + P.n_dyn;
     const int ca = nbr_cell(G, pa.x, pa.y), cx = ca % G.gx, cy = ca / G.gx;
     const int x_lo = cx > 0 ? cx - 1 : 0, x_hi = cx < G.gx - 1 ? cx + 1 : G.gx - 1;
     int n = 0;                                   // in-range candidates found (all lanes agree)
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(kNbrSearchWarps * 32) k_nbr_search(const __gri
             const int j = cand[w][e];
             int rank = 0;
             for (int f = 0; f < n; f++) rank += (cand[w][f] < j);
-            if (rank < P.K) idx_out[rank] = j;
+            if (rank < Kc) idx_out[rank] = j;
         }
         count = n;
     } else {
@@ -230,14 +252,14 @@ __global__ void __launch_bounds__(kNbrSearchWarps * 32) k_nbr_search(const __gri
             }
             const unsigned mask = __ballot_sync(0xffffffffu, in);
             const int pos = count + __popc(mask & ((1u << lane) - 1u));
-            if (in && pos < P.K) idx_out[pos] = j;
+            if (in && pos < Kc) idx_out[pos] = j;
             count += __popc(mask);
         }
     }
     if (lane == 0) {
-        S.nbr_cnt[la] = count < P.K ? count : P.K;
-        if (count > P.K) atomicOr(S.status + la, kStNbrOverflow);
-        atomicAdd(S.counters + 0, (unsigned long long)(count < P.K ? count : P.K));
+        S.nbr_cnt[la] = P.n_dyn + (count < Kc ? count : Kc);
+        if (count > Kc) atomicOr(S.status + la, kStNbrOverflow);
+        atomicAdd(S.counters + 0, (unsigned long long)(count < Kc ? count : Kc));
     }
 }
 
@@ -299,12 +321,12 @@ __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid
     uint32_t* s_hard = reinterpret_cast<uint32_t*>(s_nbr + P.K);
     const int M = P.M, npt = M * kP;
     const int la = blockIdx.x;
-    const int cnt = S.nbr_cnt[la];
+    const int cnt = S.nbr_cnt[la], nd = P.n_dyn;           // slots [0, nd): dynamic obstacles, done by k_lsc_dyn
     const int og = npt * 3 + 6;
     if (threadIdx.x == 0) s_nhard = 0;
     for (int e = threadIdx.x; e < npt * 3; e += kLscThreads) s_init[e] = S.init_traj[(size_t)la * npt * 3 + e];
     const double r_a = S.radius[la], dw_a = S.downwash[la];
-    for (int c = threadIdx.x; c < cnt; c += kLscThreads) {      // per-neighbour constants once, not once per item
+    for (int c = nd + threadIdx.x; c < cnt; c += kLscThreads) {      // per-neighbour constants once, not once per item
         const int j = S.nbr_idx[(size_t)la * P.K + c];
         const float* rec_j = S.rec + (size_t)j * P.rec;
         s_nbr[c] = j;
@@ -312,10 +334,10 @@ __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid
     }
     __syncthreads();
     int it_sum = 0;
-    const int n_gjk = cnt * (M - 1);
+    const int n_gjk = (cnt - nd) * (M - 1);
     const uint32_t mg = fastdiv_magic((uint32_t)(M - 1));
     for (int e = threadIdx.x; e < n_gjk; e += kLscThreads) {
-        const int c = (int)fastdiv((uint32_t)e, mg), m = e - c * (M - 1);
+        const int c0 = (int)fastdiv((uint32_t)e, mg), m = e - c0 * (M - 1), c = c0 + nd;
         const size_t pr = (size_t)la * P.K + c;
         const LscPair q = s_pair[c];
         gjk::D3 hc[kP], v;
@@ -334,11 +356,11 @@ __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid
     const int nh = s_nhard;
     if (threadIdx.x == 0) {
         s_base = nh ? (int)atomicAdd(S.counters + kCntHard, (unsigned long long)nh) : 0;
-        s_seg = cnt ? (int)atomicAdd(S.counters + kCntSeg, (unsigned long long)cnt) : 0;
+        s_seg = cnt > nd ? (int)atomicAdd(S.counters + kCntSeg, (unsigned long long)(cnt - nd)) : 0;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nh; i += kLscThreads) S.lsc_queue[(size_t)P.NL * P.K + s_base + i] = s_hard[i];
-    for (int c = threadIdx.x; c < cnt; c += kLscThreads) S.lsc_queue[s_seg + c] = lsc_pack(la, c, M - 1);
+    for (int c = nd + threadIdx.x; c < cnt; c += kLscThreads) S.lsc_queue[s_seg + c - nd] = lsc_pack(la, c, M - 1);
 }
 
 __global__ void __launch_bounds__(kLscRestThreads, 8) k_lsc_rest(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
@@ -377,10 +399,27 @@ __global__ void __launch_bounds__(kLscRestThreads, 8) k_lsc_rest(const __grid_co
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(S.counters + 1, (unsigned long long)tot);
 }
 
+// dynamic obstacles: thread per (agent, obstacle, segment)
+__global__ void __launch_bounds__(128) k_lsc_dyn(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int M = P.M, npt = M * kP, nd = P.n_dyn;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.NL * nd * M) return;
+    const int la = t / (nd * M), r = t - la * nd * M, o = r / M, m = r - o * M;
+    const size_t pr = (size_t)la * P.K + o;
+    lsc_dynamic_segment(S.init_traj + ((size_t)la * npt + m * kP) * 3, S.pred_traj + ((size_t)(P.N + o) * npt + m * kP) * 3,
+                        S.dyn_size + ((size_t)o * M + m) * kP, S.radius[la], S.dyn_radius[o], S.dyn_downwash[o],
+                        S.lsc_normal + (pr * M + m) * 3, S.lsc_d + (pr * M + m) * kP, S.lsc_near + pr * M + m);
+}
+
 int launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
     static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
     k_lsc<<<P.NL, kLscThreads, (size_t)P.K * (sizeof(LscPair) + (size_t)P.M * sizeof(int)), st>>>(P, S);
     k_lsc_rest<<<sms * 8, kLscRestThreads, 0, st>>>(P, S);
+    if (P.n_dyn > 0) {
+        const int n = P.NL * P.n_dyn * P.M;
+        k_lsc_dyn<<<(n + 127) / 128, 128, 0, st>>>(P, S);
+        return 3;
+    }
     return 2;
 }
 
@@ -453,15 +492,31 @@ __global__ void __launch_bounds__(128) k_goal(const __grid_constant__ DevParams 
     const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     V3 goal = v3_load(rec + npt * 3 + 6);
-    const size_t pr = (size_t)la * P.K;
+    const size_t pr = (size_t)la * P.K + P.n_dyn;          // the goal LP skips the dynamic obstacles (goal_optimizer.cpp:176-178)
     const int st = goal_agent(g, P, S.disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(S.waypoint + la * 3),
-                              S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.nbr_cnt[la],
+                              S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.nbr_cnt[la] - P.n_dyn,
                               S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, goal);
     if (g.lane == 0) {
         v3_store(S.goal_new + la * 3, goal);     // the record keeps the previous goal until the step is published:
                                                  // the other agents' LSCs of this step must see it (broadcast semantics)
         if (st) atomicOr(S.status + la, st);
     }
+}
+
+// checkWaypointTrap (P.n_dyn > 0 only): thread per agent, after LSC and SFC, before the goal stage
+__global__ void __launch_bounds__(128) k_trap(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
+    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    if (la >= P.NL) return;
+    const int npt = P.M * kP;
+    const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
+    const size_t pr = (size_t)la * P.K;
+    DynObs O; O.pos = S.dyn_pos; O.vel = S.dyn_vel; O.radius = S.dyn_radius; O.downwash = S.dyn_downwash; O.max_acc = S.dyn_max_acc; O.size = S.dyn_size;
+    S.trap[la] = (uint8_t)waypoint_trap(P, O, v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3),
+                                        S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.comm_box + (size_t)la * 6, S.nbr_cnt[la],
+                                        S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, S.radius[la]);
+}
+void launch_trap(const DevParams& P, const DevState& S, cudaStream_t st) {
+    k_trap<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S);
 }
 
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st) {
@@ -580,7 +635,7 @@ __global__ void k_expand_anchor(const __grid_constant__ DevParams P, const __gri
     float v[3] = {0.f, 0.f, 0.f};
     if (c < S.nbr_cnt[la]) {
         const int j = S.nbr_idx[(size_t)la * P.K + c];
-        const float* src = (pt / kP < P.M - 1) ? S.pred_traj + ((size_t)j * npt + pt) * 3 : S.lsc_anchor_last + (size_t)pr * 3;
+        const float* src = (pt / kP < P.M - 1 || c < P.n_dyn) ? S.pred_traj + ((size_t)j * npt + pt) * 3 : S.lsc_anchor_last + (size_t)pr * 3;
         v[0] = src[0]; v[1] = src[1]; v[2] = src[2];
     }
     out[gid * 3] = v[0]; out[gid * 3 + 1] = v[1]; out[gid * 3 + 2] = v[2];
@@ -607,6 +662,7 @@ __global__ void k_reset(const __grid_constant__ DevParams P, const __grid_consta
     for (int e = o + 11; e < P.rec; e++) rec[e] = 0.f;
     for (int k = 0; k < 3; k++) { S.acc[la * 3 + k] = 0.f; S.waypoint[la * 3 + k] = start[la * 3 + k]; S.goal_new[la * 3 + k] = start[la * 3 + k]; }
     S.disturbed[la] = 0; S.sfc_init[la] = 1; S.status[la] = 0;
+    for (int e = 0; e < 6; e++) S.comm_box[(size_t)la * 6 + e] = 0.f;
     for (int e = 0; e < npt * 3; e++) S.traj[(size_t)la * npt * 3 + e] = rec[e];
 }
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st) {

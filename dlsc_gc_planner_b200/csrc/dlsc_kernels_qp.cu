@@ -39,6 +39,7 @@ __device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState
     out.x = S.qp_x + (size_t)la * T.nx;
     out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;
     out.rows = nullptr;
+    out.slack = P.n_dyn > 0 ? S.qp_slack + (size_t)la * kMaxDyn * P.M : nullptr;
 }
 
 // Fast path: one warp per agent, no block-level synchronisation.  Agents whose unconstrained optimum is feasible

@@ -140,6 +140,7 @@ struct QpOut {
     double* x;                 // [D][M][P] or null
     double* cost; double* viol; int32_t* iters; int32_t* status;
     long long* rows;           // active inequality rows (one-sided count) or null
+    double* slack;             // [n_dyn][M] slack variables of the dynamic-obstacle rows, or null
 };
 
 // shared-memory carve-up (doubles unless noted)
@@ -147,6 +148,7 @@ struct QpSmem {
     double *W, *invp, *pan, *y, *dy, *rd, *x, *dx, *ax1, *ax2, *V1, *V2, *DD, *S, *cst, *red;
     float* sfcs;               // dual active set only: staged copy of the agent's SFC boxes [M][6]
     double* dev;               // dual active set only: [M] largest |x_pt - init_pt| per segment of the current iterate
+    double* esl;               // dual active set only: [kMaxDyn][M] slack variables of the dynamic-obstacle rows (or null: all zero)
     int* off;                  // [npt + 2] segment offsets of the LSC row list (+ scratch word)
     uint8_t* act;              // [M][Kcap]
 };
@@ -198,7 +200,7 @@ DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
     s.S = p; p += 6 * T.npt;
     s.cst = p; p += 16;
     s.red = p; p += 96;
-    s.sfcs = nullptr; s.dev = nullptr;
+    s.sfcs = nullptr; s.dev = nullptr; s.esl = nullptr;
     s.off = reinterpret_cast<int*>(p); p += (T.npt + 4) / 2 + 1;
     s.act = reinterpret_cast<uint8_t*>(p);
     (void)Kcap;
@@ -485,8 +487,10 @@ struct LscRowData { double n0, n1, n2, b; };
 DLSC_HD LscRowData lsc_row_data(const DevParams& P, const QpIn& in, int pt, int cc) {
     const int m = pt / kP, i = pt - m * kP;
     const float* nr = in.normal + ((size_t)cc * P.M + m) * 3;
-    const float* an = (m < P.M - 1) ? in.pred_traj + ((size_t)in.nbr_idx[cc] * (P.M * kP) + pt) * 3
-                                    : in.anchor_last + cc * 3;
+    // agents: witness point of the segment case for the last segment; dynamic obstacles (slots < n_dyn): always the
+    // predicted control point (traj_planner.cpp:625)
+    const float* an = (m < P.M - 1 || cc < P.n_dyn) ? in.pred_traj + ((size_t)in.nbr_idx[cc] * (P.M * kP) + pt) * 3
+                                                    : in.anchor_last + cc * 3;
     LscRowData r;
     r.n0 = (double)nr[0]; r.n1 = (double)nr[1]; r.n2 = (P.D == 3) ? (double)nr[2] : 0.0;
     double b = -in.d[((size_t)cc * P.M + m) * kP + i];
@@ -748,6 +752,18 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     double* __restrict__ pd_zh = pr + 9 * np; double* __restrict__ pd_sl = pr + 10 * np; double* __restrict__ pd_zl = pr + 11 * np;
     double* __restrict__ p_act = pr + 12 * np;
     const int npl = T.row_npl;
+    if (P.n_dyn > 0) {
+        // The interior point has no slack variables: an agent the active set cannot finish while dynamic obstacles are
+        // present is reported as a numerical failure and keeps its initial trajectory (failsafe traj_planner.cpp:775-776).
+        if (c.tid == 0) { *out.cost = 0.0; *out.viol = 0.0; *out.iters = 0; *out.status |= kStQpNumeric; if (out.rows) *out.rows = 0; }
+        for (int e = c.tid; e < npt; e += c.nthr) {
+            float* o = out.traj + e * 3;
+            o[0] = in.init_traj[e * 3]; o[1] = in.init_traj[e * 3 + 1]; o[2] = in.init_traj[e * 3 + 2];
+        }
+        if (out.slack) for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) out.slack[e] = 0.0;
+        c.sync();
+        return;
+    }
 
     // ---- constants of this agent ----
     QpConst qc;

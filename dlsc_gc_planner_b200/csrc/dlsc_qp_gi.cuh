@@ -21,7 +21,7 @@ namespace dlsc {
 
 constexpr int kSfcStage = kMaxM * 6 / 2;        // doubles holding the agent's [M][6] float boxes
 DLSC_HD size_t gi_smem_doubles(const QpTab& T, int Kcap) {
-    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + kSfcStage + kMaxM + 96 + ((size_t)Kcap + 1) / 2;
+    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + kSfcStage + kMaxM + 96 + (size_t)kMaxDyn * T.M + ((size_t)Kcap + 1) / 2;
 }
 DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     double* p = base;
@@ -32,6 +32,7 @@ DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     s.sfcs = reinterpret_cast<float*>(p); p += kSfcStage;
     s.dev = p; p += kMaxM;
     s.red = p; p += 96;
+    s.esl = p; p += kMaxDyn * T.M;
     s.off = reinterpret_cast<int*>(p);          // [Kcap] global indices of the neighbours
     s.invp = s.pan = s.rd = s.dx = s.ax2 = s.V1 = s.V2 = s.DD = s.S = nullptr;
     s.act = nullptr;
@@ -48,7 +49,7 @@ DLSC_HD void fast_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     s.sfcs = reinterpret_cast<float*>(p); p += kSfcStage;
     s.dev = p; p += kMaxM;
     s.off = reinterpret_cast<int*>(p);
-    s.W = s.dy = s.ax1 = s.red = nullptr;
+    s.W = s.dy = s.ax1 = s.red = s.esl = nullptr;
     s.invp = s.pan = s.rd = s.dx = s.ax2 = s.V1 = s.V2 = s.DD = s.S = nullptr;
     s.act = nullptr;
 }
@@ -92,6 +93,22 @@ DLSC_HD void pair_violation(const DevParams& P, const QpTab& T, const QpIn& in, 
     vh = act - hi; vl = lo - act;
 }
 
+// Dynamic-obstacle LSC rows carry a slack variable per (obstacle, segment): -n.x + eps <= b, eps <= 0, cost
+// w (M-m)/M eps^2 (traj_optimizer.cpp:272-283, 317-331, 436-448).  The slack block of H is diagonal and every row
+// touches at most one slack with coefficient +1, so the active set keeps the slack values beside y (sm.esl) and adds
+// the slack terms to the few inner products that need them.  eps <= 0 holds by itself: eps = -(sum of the group's
+// multipliers) / h and the multipliers never go negative.
+// slack variable of inequality row `id`, or -1
+DLSC_HD int gi_slack_of(const DevParams& P, const QpTab& T, int id) {
+    if (P.n_dyn == 0 || id < 2 * T.np) return -1;
+    const int o = id - 2 * T.np, pt = o / P.K, cc = o - pt * P.K;
+    return cc < P.n_dyn ? cc * P.M + pt / kP : -1;
+}
+DLSC_HD double gi_slack_hinv(const DevParams& P, int s) {          // 1 / (2 w (M - m) / M)
+    const int m = s % P.M;
+    return 1.0 / (2.0 * P.slack_w * ((double)(P.M - m) / P.M));
+}
+
 // most violated row over all inequality rows; every thread returns the same (vmax, id)
 //   id < 2 np: pattern row r = id >> 1, side id & 1 (0: upper, 1: lower);  else LSC row o = id - 2 np = pt * Kcap + cc
 // Row screen: k_lsc stored, per (neighbour, segment) item, the smallest normalised slack of its rows at the agent's
@@ -105,8 +122,8 @@ constexpr float kScreenMargin = 1e-3f;
 // row: out (may be null), the thread's best LSC row as lsc_row_data would return it (valid when its best is an LSC row)
 DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
                      const int* sm_nbr, bool screened, const int* dev2, double& vmax_out, double& id_out,
-                     double& nviol_out, bool& mine, LscRowData* row) {
-    const int npt = T.npt, np = T.np, Kc = P.K, K = in.K;
+                     double& nviol_out, bool& mine, LscRowData* row, const double* esl) {
+    const int npt = T.npt, np = T.np, Kc = P.K, K = in.K, nd = P.n_dyn;
     const bool D3 = (P.D == 3);
     double best = -1e300, best_id = 1e300;
     int n_bad = 0;                                                 // violated rows seen by this thread
@@ -129,8 +146,9 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
         const float* nr = in.normal + ((size_t)cc * M + m) * 3;
         const V3 nv = v3_load(nr);
         const double* dd = in.d + ((size_t)cc * M + m) * kP;
-        const bool last = (m == M - 1);
+        const bool last = (m == M - 1) && cc >= nd;                                 // dynamic obstacles: predicted points throughout
         const float* an = last ? in.anchor_last + cc * 3 : in.pred_traj + ((size_t)sm_nbr[cc] * npt + m * kP) * 3;
+        const double es = (esl && cc < nd) ? esl[cc * M + m] : 0.0;
         double dv[kP]; float av[kP][3];
 #pragma unroll
         for (int i = 0; i < kP; i++) {
@@ -148,7 +166,7 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             b -= n0 * (double)av[i][0];
             b -= n1 * (double)av[i][1];
             if (D3) b -= n2 * (double)av[i][2];
-            const double v = -(n0 * x[pt] + n1 * x[npt + pt] + (D3 ? n2 * x[2 * npt + pt] : 0.0)) - b;
+            const double v = -(n0 * x[pt] + n1 * x[npt + pt] + (D3 ? n2 * x[2 * npt + pt] : 0.0)) - b + es;
             const double id = 2.0 * np + (double)(pt * Kc + cc);
             if (v > best || (v == best && id < best_id)) {
                 best = v; best_id = id;
@@ -206,7 +224,7 @@ DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, c
     c.sync();
     c.tick(3);
     double nv = 0.0;
-    gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, dev2, vmax, idsel, nv, mine, row);
+    gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, dev2, vmax, idsel, nv, mine, row, sm.esl);
     // every thread is past the reduction, so nobody reads dev2 any more: reset it for the next map.  In warp mode the
     // reduction is shuffles only, which order execution but are no memory barrier (racecheck flags the reset against
     // the scan's reads): __syncwarp makes the ordering explicit.
@@ -322,9 +340,13 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
         // is bit-identical to a single-thread evaluation (the host simulator runs this with one "lane").
         const int W = c.nthr < 32 ? c.nthr : 32;
         if (c.tid < W) {
+            // slack of the candidate row: (H^-1 a_p) has one more component, 1/h, in the slack block
+            const int sp = gi_slack_of(P, T, g.id[kGiQ]);
+            const double hp = sp >= 0 ? gi_slack_hinv(P, sp) : 0.0;
             for (int j = c.tid; j < q; j += W) {
                 double vj = 0.0;
                 for (int t = 0; t < 9; t++) { const int jj = g.yi[9 * j + t]; if (jj >= 0) vj += g.yc[9 * j + t] * sm.dy[jj]; }
+                if (sp >= 0 && gi_slack_of(P, T, g.id[j]) == sp) vj += hp;
                 g.v[j] = vj;
             }
             c.wsync();
@@ -332,6 +354,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             if (c.tid == 0) {
                 double apw = 0.0;
                 for (int t = 0; t < 9; t++) if (yi[t] >= 0) apw += yc[t] * sm.dy[yi[t]];
+                apw += hp;
                 double ll = 0.0;
                 for (int j = 0; j < q; j++) {
                     double a = g.v[j];
@@ -353,6 +376,13 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                 const double t = t1 < t2 ? t1 : t2;
                 const bool finite = (t < 1e299);
                 if (finite) for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
+                if (P.n_dyn > 0 && finite && !dependent) {      // slack block of the primal step  z = H^-1 (a_p - A' r)
+                    for (int j = 0; j < q; j++) {
+                        const int sj = gi_slack_of(P, T, g.id[j]);
+                        if (sj >= 0) sm.esl[sj] += t * g.r[j] * gi_slack_hinv(P, sj);
+                    }
+                    if (sp >= 0) sm.esl[sp] -= t * hp;
+                }
                 g.ty[0] = dependent ? 0.0 : t;
                 g.ty[2] = zn;
                 g.ty[3] = finite ? 1.0 : 0.0;
@@ -474,6 +504,7 @@ DLSC_HD void gi_prologue(const Cta& c, const DevParams& P, const QpTab& T, QpIn&
     }
     for (int cc = c.tid; cc < in.K; cc += c.nthr) sm.off[cc] = in.nbr_idx[cc];
     for (int m = c.tid; m < kMaxM * 2; m += c.nthr) reinterpret_cast<int*>(sm.dev)[m] = 0;
+    if (sm.esl) for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) sm.esl[e] = 0.0;
     if (P.use_sfc) {
         for (int e = c.tid; e < M * 6; e += c.nthr) sm.sfcs[e] = in.sfc[e];
         in.sfc = sm.sfcs;
@@ -516,6 +547,12 @@ DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const
     }
     c.reduce1(obj, 0);
     c.tick(7);
+    if (P.n_dyn > 0) {                                                                // :317-331
+        if (c.tid == 0 && sm.esl)
+            for (int e = 0; e < P.n_dyn * M; e++) obj += P.slack_w * ((double)(M - e % M) / M) * sm.esl[e] * sm.esl[e];
+        if (out.slack)
+            for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) out.slack[e] = (status == 0 && sm.esl) ? sm.esl[e] : 0.0;
+    }
     if (c.tid == 0) {
         *out.cost = obj; *out.viol = vmax > 0 ? vmax : 0.0; *out.iters = iters; *out.status |= status;
         if (out.rows) *out.rows = 2LL * np + (long long)in.K * (npt - 3);

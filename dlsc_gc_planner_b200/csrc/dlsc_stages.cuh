@@ -110,7 +110,7 @@ DLSC_HD int neighbours_agent(const Group& g, const DevParams& P, const float* re
         }
         const unsigned mask = g.ballot(in);
         const int pos = count + popc_u32(mask & ((1u << g.lane) - 1u));
-        if (in && pos < P.K) idx_out[pos] = j;
+        if (in && pos < P.K - P.n_dyn) idx_out[pos] = j;                      // idx_out points past the dynamic slots
         count += popc_u32(mask);
     }
     return count;
@@ -1000,6 +1000,122 @@ DLSC_HD int goal_agent(const Group& g, const DevParams& P, bool disturbed, const
         if (delta < -kEpsF) not_numerical = true;
     }
     return g.any(not_numerical) ? kStGoalInfeasible : 0;              // keep goal :80
+}
+
+// ------------------------------------------------------------------------------------------------
+// dynamic (non-agent) obstacles: traj_planner.cpp:617-627 + :1129-1148 + :1080-1100 (LSC), :708-735 (waypoint
+// trap), geometry.hpp:115-137, obstacle.hpp:26-36, collision_constraints.cpp:538-546, 586-598.
+// They take the first P.n_dyn obstacle slots of every agent (MultiSyncSimulator::broadcastMsgs lists them first,
+// multi_sync_simulator.cpp:476-480); their constant-velocity predictions are rows N.. of pred_traj.
+// ------------------------------------------------------------------------------------------------
+struct DynObs { const float *pos, *vel; const double *radius, *downwash, *max_acc, *size; };
+
+// Obstacle sizes over the horizon (obstacleSizePredictionWithConstAcc, traj_planner.cpp:338-368): radius + the Bernstein
+// control points of 1/2 a_max t^2 up to the uncertainty horizon, constant after it.  coef * B_inv (polynomial.hpp:280-293)
+// with B_inv(k, i) = C(i,k)/C(n,k) in closed form.  Host side: runs once per dlsc_set_obstacles.
+inline void dyn_obstacle_sizes(const DevParams& P, bool size_prediction, double horizon, double radius, double max_acc,
+                               double* out /*[M][P]*/) {
+    const int M = P.M, n = kP - 1;
+    int Mu = (int)((horizon + kEps) / P.dt);                                   // :339
+    if (Mu > M) Mu = M;
+    for (int m = 0; m < M; m++)
+        for (int i = 0; i < kP; i++) {
+            double v = radius;                                                 // :364
+            if (size_prediction) {
+                if (m < Mu) {
+                    const double a0 = 0.5 * max_acc * ((m * P.dt) * (m * P.dt));   // :349-351 (pow(x, 2) = x * x exactly)
+                    const double a1 = max_acc * m * P.dt * P.dt;
+                    const double a2 = 0.5 * max_acc * (P.dt * P.dt);
+                    v = radius + (a0 + a1 * ((double)i / n) + a2 * ((double)(i * (i - 1)) / (n * (n - 1))));
+                } else {
+                    v = radius + 0.5 * max_acc * ((Mu * P.dt) * (Mu * P.dt));   // :360-361
+                }
+            }
+            out[(size_t)m * kP + i] = v;
+        }
+}
+
+// normalVectorBetweenLines(line_obs, line_agent) on closestPointsBetweenLinePaths: both points move along their
+// segments with the same parameter
+DLSC_HD V3 normal_between_line_paths(const V3& o0, const V3& o1, const V3& a0, const V3& a1) {
+    const V3 r0 = a0 - o0, r1 = a1 - o1;                                       // rel_path = line2 - line1
+    const Closest rc = closest_point_segment(v3(0.f, 0.f, 0.f), r0, r1);
+    const double len = v3_distance(r0, r1);
+    double alpha = 0.0;
+    if (len > 0) alpha = v3_norm(rc.p2 - r0) / len;
+    const V3 c1 = o0 + (o1 - o0) * (float)alpha;
+    const V3 c2 = a0 + (a1 - a0) * (float)alpha;
+    V3 nv = v3_normalized(c2 - c1);
+    if (v3_norm(nv) == 0) {                                                    // heuristic :1089-1098
+        const V3 a = a0 - o0, b = a1 - o1;
+        if (v3_norm(a) == 0 && v3_norm(b) == 0) nv = v3(1.f, 0.f, 0.f);
+        else nv = v3_cross(b - a, v3(0.f, 0.f, 1.f));
+    }
+    return nv;
+}
+
+// one (agent, obstacle, segment) item.  The lines are NOT downwash-transformed (normalVectorDynamicObs :1144-1147);
+// only the normal's z is divided afterwards.  near_out = 0: the QP never screens these rows out.
+DLSC_HD void lsc_dynamic_segment(const float* init_seg, const float* obs_seg, const double* size_seg, double r_a,
+                                 double r_o, double dw_o, float* normal_out, double* d_out, float* near_out) {
+    const double downwash = (r_a + dw_o * r_o) / (r_a + r_o);                  // :1156-1157
+    const V3 nt = normal_between_line_paths(v3_load(obs_seg), v3_load(obs_seg + (kP - 1) * 3), v3_load(init_seg),
+                                            v3_load(init_seg + (kP - 1) * 3));
+    v3_store(normal_out, v3(nt.x, nt.y, (float)((double)nt.z / downwash)));    // :618-620
+    for (int i = 0; i < kP; i++) d_out[i] = size_seg[i] + r_a;                 // :624
+    if (near_out) *near_out = 0.f;
+}
+
+// Obstacle::isCollided
+DLSC_HD bool obstacle_collides(const V3& opos, const V3& ovel, double oradius, double omax_acc, const V3& point,
+                               double agent_radius, double horizon, double uncertainty_horizon) {
+    const double step = (0.1 * horizon < 0.1) ? 0.1 * horizon : 0.1;
+    for (double t = 0; t <= horizon; t += step) {
+        const V3 q = opos + ovel * (float)t;
+        const double tm = t < uncertainty_horizon ? t : uncertainty_horizon;
+        if (v3_distance(q, point) < agent_radius + oradius + 0.5 * omax_acc * tm * tm) return true;
+    }
+    return false;
+}
+
+// CollisionConstraints::constructCommunicationRange, reached from generateSFC's non-initial branch only
+DLSC_HD void comm_box_update(const DevParams& P, bool init, const V3& wp, float* box) {
+    if (!P.use_sfc || init || !(P.comm_range > 0)) return;
+    const float h = (float)(0.5 * P.comm_range);
+    v3_store(box, wp - v3(h, h, h));
+    v3_store(box + 3, wp + v3(h, h, h));
+}
+
+// checkWaypointTrap for one agent (one thread).  LSC arrays of this agent as in goal_agent; K counts the dynamic slots.
+// Returns 1 when the waypoint is trapped; the LSCs of the dynamic obstacles that can reach the waypoint are cleared.
+DLSC_HD int waypoint_trap(const DevParams& P, const DynObs& O, const V3& goal, const V3& wp, const float* sfc_last,
+                          const float* comm_box, int K, float* normal, double* d, const float* anchor_last,
+                          double agent_radius) {
+    const int M = P.M, nd = P.n_dyn;
+    if (K == 0) return 0;                                                      // obstacles.empty() :709
+    bool ok = true;
+    for (int which = 0; which < 2 && ok; which++) {                            // isPointInFeasibleRegion(goal) and (waypoint)
+        const V3 q = which ? wp : goal;
+        for (int oi = nd; oi < K && ok; oi++) {
+            const V3 nv = v3_load(normal + ((size_t)oi * M + (M - 1)) * 3);
+            const V3 an = v3_load(anchor_last + oi * 3);
+            const double dd = d[((size_t)oi * M + (M - 1)) * kP + (kP - 1)];
+            if (!(v3_dot(q - an, nv) - dd > -kEps)) ok = false;                // LSC::isPointInLSC
+        }
+        if (ok && P.use_sfc && !point_in_box(box_load(sfc_last), q)) ok = false;
+        if (ok && !point_in_box(box_load(comm_box), q)) ok = false;
+    }
+    if (ok) return 0;
+    for (int oi = 0; oi < nd; oi++) {
+        if (!obstacle_collides(v3_load(O.pos + 3 * oi), v3_load(O.vel + 3 * oi), O.radius[oi], O.max_acc[oi], wp,
+                               agent_radius, M * P.dt, P.dyn_horizon)) continue;
+        for (int m = 0; m < M; m++) {
+            float* nr = normal + ((size_t)oi * M + m) * 3;
+            nr[0] = nr[1] = nr[2] = 0.f;                                       // default LSC: skipped by the QP :731
+            for (int i = 0; i < kP; i++) d[((size_t)oi * M + m) * kP + i] = 0.0;
+        }
+    }
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@ namespace dlsc {
 constexpr int kP = 6;                // control points per segment (n + 1, n = 5)
 constexpr int kMaxM = 16;            // segments
 constexpr int kMaxPts = kMaxM * kP;
+constexpr int kMaxDyn = 16;          // dynamic (non-agent) obstacles per context
 
 // Device-side copy of the planner parameters plus derived constants.
 struct DevParams {
@@ -17,6 +18,10 @@ struct DevParams {
     double qp_screen;                // LSC working-set screen [m]; <= 0: all rows
     int qp_solver;                   // 0: dual active set with interior-point fallback, 1: interior point only
     int qp_active_max;               // active-set capacity before the hand-over to the interior point (<= kGiQ)
+    int n_dyn;                       // dynamic obstacles: they take the first n_dyn obstacle slots of every agent (list entries N + o)
+    int dyn_reserved;
+    double slack_w;                  // opt/slack_collision_weight
+    double dyn_horizon;              // obs/uncertainty_horizon
     double dt, world_res, grid_res, z_2d, comm_range, w_control, w_terminal, reset_threshold;
     double world_min[3], world_max[3];       // double(float(x))
     float tk[kMaxPts];               // (float) of the time accumulated by `time += dt/n` (trajectory.cpp:84-90)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DLSC_ABI_VERSION 3
+#define DLSC_ABI_VERSION 4
 
 /* Planner parameters: the subset of MATP::Param / MATP::Mission the hot path reads
  * (reference src/param.cpp:5-117, src/mission.cpp:104-112; launch-file values SURVEY.md s5). */
@@ -152,6 +152,36 @@ int dlsc_set_agent_props(dlsc_ctx* ctx, const dlsc_agent_props* props);
  * current_goal_point = start, next_waypoint = start: agent_manager.cpp:4-32) and write the
  * local records.  start [n_local][3]. */
 int dlsc_reset(dlsc_ctx* ctx, const float* start);
+
+/* Dynamic (non-agent) obstacles: what MultiSyncSimulator::broadcastMsgs puts in front of every agent's obstacle list
+ * (src/multi_sync_simulator.cpp:470-480, Obstacle in include/obstacle.hpp:13-37) and TrajPlanner::setObstacles receives.
+ * On the device path they get: constant-velocity prediction (src/traj_planner.cpp:303-305), size prediction
+ * (obstacleSizePredictionWithConstAcc :338-368), LSCs from normalVectorDynamicObs (:617-627, 1129-1148), the waypoint
+ * trap (checkWaypointTrap :708-735), no row in the goal LP (src/goal_optimizer.cpp:176-178), and one slack variable per
+ * (obstacle, segment) in the QP (src/traj_optimizer.cpp:272-283, 317-331, 436-448).  Call whenever the obstacle states
+ * change (every step for moving obstacles); n = 0 or obs = NULL removes them.  The obstacles occupy the first n slots of
+ * every agent's list (entries n_agents + o in dlsc_get_neighbours), so max_nbr must exceed n (n <= DLSC_MAX_OBSTACLES). */
+#define DLSC_MAX_OBSTACLES 16
+typedef struct dlsc_obstacles {
+    int32_t n;
+    const float* pos;          /* [n][3] Obstacle::position */
+    const float* vel;          /* [n][3] Obstacle::velocity */
+    const double* radius;      /* [n] */
+    const double* downwash;    /* [n] */
+    const double* max_acc;     /* [n] */
+} dlsc_obstacles;
+typedef struct dlsc_obstacle_params {
+    double slack_collision_weight;   /* opt/slack_collision_weight (> 0)   src/param.cpp:80  */
+    double uncertainty_horizon;      /* obs/uncertainty_horizon            src/param.cpp:66  */
+    int32_t size_prediction;         /* obs/size_prediction                src/param.cpp:65  */
+    int32_t reserved0;
+} dlsc_obstacle_params;
+int dlsc_set_obstacles(dlsc_ctx* ctx, const dlsc_obstacles* obs, const dlsc_obstacle_params* params);
+/* after a step: slack variables [n_local][n][M] (<= 0; 0 for agents that kept their initial trajectory), the
+ * checkWaypointTrap outcome [n_local], the obstacles' predicted trajectories [n][M][6][3] */
+int dlsc_get_slack(dlsc_ctx* ctx, double* slack);
+int dlsc_get_trap(dlsc_ctx* ctx, uint8_t* trapped);
+int dlsc_get_obstacle_pred(dlsc_ctx* ctx, float* traj);
 /* Monte-Carlo batches (BASELINE configs[4]): several independent missions replanning in lockstep inside one
  * context.  group[i] = mission index of local agent i (0 <= group < 2^24); agents only become neighbours of
  * agents of the same mission (the reference runs one MultiSyncSimulator per mission).  Call after dlsc_reset

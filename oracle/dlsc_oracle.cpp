@@ -563,6 +563,83 @@ void lsc_pair(const orc_params* p, const float* init_traj, const float* pred_tra
 }
 
 // ------------------------------------------------------------------------------------------
+// Dynamic (non-agent) obstacles -- traj_planner.cpp:338-368 (size prediction), :617-627 + :1129-1148 +
+// :1080-1100 (LSC), :708-735 (waypoint trap); geometry.hpp:115-137; obstacle.hpp:26-36
+// ------------------------------------------------------------------------------------------
+// obs_pred_sizes: radius + the Bernstein control points of 1/2 a_max t^2 over the uncertainty horizon, constant after it.
+// coef * B_inv (polynomial.hpp:280-293) restated with the closed form B_inv(k, i) = C(i,k)/C(n,k) (Eigen's numeric
+// inverse differs from it by rounding only: parity unpinned at the 1e-16 level).
+void obstacle_sizes(const orc_params* p, int size_prediction, double uncertainty_horizon, double radius, double max_acc,
+                    double* out /*[M][P]*/) {
+    const int M = p->M, P = P_of(p), n = p->n;
+    const int Mu = std::min((int)((uncertainty_horizon + kEps) / p->dt), M);               // :339
+    for (int m = 0; m < M; m++)
+        for (int i = 0; i < P; i++) {
+            double v = radius;                                                              // :364 planConstVelTraj(radius, 0)
+            if (size_prediction) {
+                if (m < Mu) {
+                    const double a0 = 0.5 * max_acc * std::pow(m * p->dt, 2);               // :349-351
+                    const double a1 = max_acc * m * p->dt * p->dt;
+                    const double a2 = 0.5 * max_acc * std::pow(p->dt, 2);
+                    const double cp = a0 + a1 * ((double)i / n) + a2 * ((double)(i * (i - 1)) / (n * (n - 1)));
+                    v = radius + cp;                                                        // :355
+                } else {
+                    v = radius + 0.5 * max_acc * std::pow(Mu * p->dt, 2);                   // :360-361
+                }
+            }
+            out[(size_t)m * P + i] = v;
+        }
+}
+
+// normalVectorBetweenLines(line_obs, line_agent) :1080-1100 on closestPointsBetweenLinePaths geometry.hpp:115-137
+vec3f normal_between_line_paths(const vec3f& o0, const vec3f& o1, const vec3f& a0, const vec3f& a1) {
+    const vec3f r0 = a0 - o0, r1 = a1 - o1;                                                // rel_path = line2 - line1
+    const Closest rc = closest_point_segment(vec3f(0, 0, 0), r0, r1);
+    const double len = r0.distance(r1);
+    double alpha = 0;
+    if (len > 0) alpha = (rc.p2 - r0).norm() / len;
+    const vec3f c1 = o0 + (o1 - o0) * (float)alpha;
+    const vec3f c2 = a0 + (a1 - a0) * (float)alpha;
+    vec3f nv = (c2 - c1).normalized();
+    if (nv.norm() == 0) {                                                                   // heuristic :1089-1098
+        const vec3f a = a0 - o0, b = a1 - o1;
+        if (a.norm() == 0 && b.norm() == 0) nv = vec3f(1, 0, 0);
+        else nv = (b - a).cross(vec3f(0, 0, 1));
+    }
+    return nv;
+}
+
+void lsc_dynamic(const orc_params* p, const float* init_traj, const float* obs_traj, const double* size, double r_a,
+                 double r_o, double dw_o, float* normal /*[M][3]*/, float* anchor /*[M][P][3]*/, double* d /*[M][P]*/) {
+    const int P = P_of(p), M = p->M, n = p->n;
+    const double downwash = (r_a + dw_o * r_o) / (r_a + r_o);                               // :1156-1157
+    for (int m = 0; m < M; m++) {
+        // the lines are NOT downwash-transformed (normalVectorDynamicObs :1144-1147); only z is divided afterwards
+        const vec3f nt = normal_between_line_paths(vec3f(obs_traj + ((size_t)m * P) * 3), vec3f(obs_traj + ((size_t)m * P + n) * 3),
+                                                   vec3f(init_traj + ((size_t)m * P) * 3), vec3f(init_traj + ((size_t)m * P + n) * 3));
+        vec3f nrm(nt.x, nt.y, (float)((double)nt.z / downwash));                            // :618-620
+        nrm.store(normal + (size_t)m * 3);
+        for (int i = 0; i < P; i++) {
+            d[(size_t)m * P + i] = size[(size_t)m * P + i] + r_a;                            // :624
+            const float* a = obs_traj + ((size_t)m * P + i) * 3;                             // :625
+            float* dst = anchor + ((size_t)m * P + i) * 3;
+            dst[0] = a[0]; dst[1] = a[1]; dst[2] = a[2];
+        }
+    }
+}
+
+// Obstacle::isCollided obstacle.hpp:26-36
+bool obstacle_collides(const vec3f& opos, const vec3f& ovel, double oradius, double omax_acc, const vec3f& point,
+                       double agent_radius, double horizon, double uncertainty_horizon) {
+    for (double t = 0; t <= horizon; t += std::min(0.1 * horizon, 0.1)) {
+        const vec3f q = opos + ovel * (float)t;
+        const double tm = std::min(t, uncertainty_horizon);
+        if (q.distance(point) < agent_radius + oradius + 0.5 * omax_acc * tm * tm) return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
 // SFC
 // ------------------------------------------------------------------------------------------
 struct Box { vec3f lo, hi; };
@@ -850,6 +927,42 @@ int goal_agent(const orc_params* p, bool disturbed, const vec3f& pos, const vec3
 }
 
 // ------------------------------------------------------------------------------------------
+// checkWaypointTrap (traj_planner.cpp:708-735): when the current goal or the next waypoint lies outside the region
+// the AGENT LSCs of (M-1, n), the last SFC box and the communication box leave (isPointInFeasibleRegion,
+// collision_constraints.cpp:586-598), the LSCs of every dynamic obstacle that can reach the waypoint are dropped.
+// Slots [0, n_dyn) are the dynamic obstacles.  Returns 1 when trapped.
+// ------------------------------------------------------------------------------------------
+int waypoint_trap(const orc_params* p, const vec3f& goal, const vec3f& wp, const float* sfc_last, const float* comm_box,
+                  int K, int n_dyn, float* normal, const float* anchor, double* d, size_t sn, size_t sa, size_t sd,
+                  const float* dyn_pos, const float* dyn_vel, const double* dyn_radius, const double* dyn_max_acc,
+                  double agent_radius, double uncertainty_horizon) {
+    const int M = p->M, P = P_of(p);
+    if (K == 0) return 0;                                                                   // obstacles.empty() :709
+    auto feasible = [&](const vec3f& q) {
+        for (int oi = n_dyn; oi < K; oi++) {
+            const vec3f nv(normal + oi * sn + (size_t)(M - 1) * 3);
+            const vec3f an(anchor + oi * sa + ((size_t)(M - 1) * P + p->n) * 3);
+            const double dd = d[oi * sd + (size_t)(M - 1) * P + p->n];
+            if (!((q - an).dot(nv) - dd > -kEps)) return false;                             // LSC::isPointInLSC :35-37
+        }
+        if (p->use_sfc && !point_in_box(load_box(sfc_last), q)) return false;
+        return point_in_box(load_box(comm_box), q);
+    };
+    const bool trapped = !(feasible(goal) && feasible(wp));
+    if (!trapped) return 0;
+    for (int oi = 0; oi < n_dyn; oi++) {
+        if (!obstacle_collides(vec3f(dyn_pos + 3 * oi), vec3f(dyn_vel + 3 * oi), dyn_radius[oi], dyn_max_acc[oi], wp,
+                               agent_radius, M * p->dt, uncertainty_horizon)) continue;
+        for (int m = 0; m < M; m++) {
+            float* nr = normal + oi * sn + (size_t)m * 3;
+            nr[0] = nr[1] = nr[2] = 0.f;                                                     // default LSC: skipped by the QP :731
+            for (int i = 0; i < P; i++) d[oi * sd + (size_t)m * P + i] = 0.0;
+        }
+    }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // QP
 // ------------------------------------------------------------------------------------------
 int n_choose_k(int n, int k) {      // polynomial.hpp:9-20
@@ -899,7 +1012,7 @@ void q_base(const orc_params* p, double* Q) {
 // (:338-381) and, for segment 0, from the initial state rows (:335-352).
 struct XExpr { int nv; int idx[3]; double coef[3]; double c0; };
 
-struct SparseRow { int nnz; int idx[9]; double val[9]; double rhs; };   // sum val*y <= rhs
+struct SparseRow { int nnz; int idx[10]; double val[10]; double rhs; };   // sum val*y <= rhs (9 trajectory terms + 1 slack)
 
 struct QpWork {
     int D, M, P, nx, ny;
@@ -1054,7 +1167,10 @@ int qp_solve(const orc_params* p, const vec3f& pos, const vec3f& vel, const vec3
              const vec3f& wp, double radius, double max_vel, double max_acc, double nominal_vel,
              const float* sfc, int K, const float* normal, const float* anchor, const double* d,
              size_t sn, size_t sa, size_t sd, const float* init_traj, float* traj_out, double* x_out,
-             double* cost, double* max_violation, int* iters) {
+             double* cost, double* max_violation, int* iters,
+             int n_dyn = 0, double slack_weight = 0.0, double* slack_out = nullptr) {
+    // The first n_dyn obstacle slots are dynamic (non-agent) obstacles: their LSC rows carry one slack variable per
+    // (obstacle, segment), epsilon <= 0, with cost slack_weight (M - m)/M epsilon^2 (traj_optimizer.cpp:272-283, 317-331, 436-448).
     const int M = p->M, P = P_of(p), D = p->dim, n = p->n, phi = p->phi;
     const double dt = p->dt;
     QpWork w;
@@ -1147,8 +1263,16 @@ int qp_solve(const orc_params* p, const vec3f& pos, const vec3f& vel, const vec3
                     rhs -= (double)nrm[k] * (double)anc[k];
                 }
                 add_row(w, xi, xc, D, rhs);       // -n.x <= -(n.anchor + d)
+                if (oi < n_dyn) {                 // n.(x - anchor) - (d + eps) >= 0   :443-444
+                    SparseRow& r = w.rows.back();
+                    r.idx[r.nnz] = w.ny + M * oi + m; r.val[r.nnz] = 1.0; r.nnz++;
+                }
             }
         }
+    for (int s = 0; s < n_dyn * M; s++) {                                                    // eps <= 0 :274
+        SparseRow r; r.nnz = 1; r.idx[0] = w.ny + s; r.val[0] = 1.0; r.rhs = 0.0;
+        w.rows.push_back(r);
+    }
     for (int k = 0; k < D; k++)                                                               // dynamics :452-487
         for (int m = 0; m < M; m++) {
             for (int i = 0; i < n; i++) {
@@ -1188,8 +1312,13 @@ int qp_solve(const orc_params* p, const vec3f& pos, const vec3f& vel, const vec3
             }
     }
     // reduced objective: 1/2 y'Hy + g'y + c0
-    const int ny = w.ny;
+    const int ny = w.ny + n_dyn * M;                 // trajectory unknowns, then the slack variables
     std::vector<double> H((size_t)ny * ny, 0.0), g(ny, 0.0);
+    for (int oi = 0; oi < n_dyn; oi++)                                                       // :317-331
+        for (int m = 0; m < M; m++) {
+            const int e = w.ny + M * oi + m;
+            H[(size_t)e * ny + e] = 2.0 * slack_weight * ((double)(M - m) / M);
+        }
     double c0 = w.cx;
     for (int k = 0; k < D; k++)
         for (int m = 0; m < M; m++) {
@@ -1244,6 +1373,12 @@ int qp_solve(const orc_params* p, const vec3f& pos, const vec3f& vel, const vec3
                 for (int j = 0; j < P; j++) obj += Pb[i * P + j] * x[xid(w, k, m, i)] * x[xid(w, k, m, j)];
         }
     for (int xi = 0; xi < w.nx; xi++) obj += w.qx[xi] * x[xi];
+    for (int oi = 0; oi < n_dyn; oi++)
+        for (int m = 0; m < M; m++) {
+            const double e = y[w.ny + M * oi + m];
+            obj += slack_weight * ((double)(M - m) / M) * e * e;
+            if (slack_out) slack_out[oi * M + m] = e;
+        }
     (void)c0;
     if (cost) *cost = obj;
     double viol = 0;
@@ -1314,10 +1449,11 @@ void orc_predict(const orc_params* p, int N, int seq, const float* pos, const fl
     }
 }
 
-int orc_neighbours(const orc_params* p, int N, const float* pos, int max_nbr, int32_t* nbr_idx, int32_t* nbr_cnt) {
+// slots [0, first) of every list are left to the caller (dynamic obstacles); nbr_cnt counts them
+static int neighbours_from(const orc_params* p, int N, const float* pos, int max_nbr, int first, int32_t* nbr_idx, int32_t* nbr_cnt) {
     int overflow = 0;
     for (int a = 0; a < N; a++) {
-        int c = 0;
+        int c = first;
         vec3f pa(pos + 3 * a);
         for (int j = 0; j < N; j++) {
             if (j == a) continue;
@@ -1330,6 +1466,9 @@ int orc_neighbours(const orc_params* p, int N, const float* pos, int max_nbr, in
         nbr_cnt[a] = c;
     }
     return overflow;
+}
+int orc_neighbours(const orc_params* p, int N, const float* pos, int max_nbr, int32_t* nbr_idx, int32_t* nbr_cnt) {
+    return neighbours_from(p, N, pos, max_nbr, 0, nbr_idx, nbr_cnt);
 }
 
 void orc_lsc_batch(const orc_params* p, int N, const float* init_traj, const float* pred_traj,
@@ -1410,8 +1549,20 @@ void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end
     double t0 = now_s();
     for (int a = 0; a < N; a++) io->status[a] = ORC_OK;
     orc_predict(p, N, io->seq, io->pos, io->vel, io->prev_traj, io->disturbed, io->init_traj, io->pred_traj);
-    if (orc_neighbours(p, N, io->pos, K, io->nbr_idx, io->nbr_cnt))
+    // dynamic obstacles come first in every agent's obstacle list (multi_sync_simulator.cpp:476-480): slots [0, nd),
+    // list entries N + o; constant-velocity prediction (traj_planner.cpp:303-305) and predicted sizes (:338-368)
+    const int nd = io->n_dyn > 0 ? io->n_dyn : 0;
+    std::vector<float> dyn_pred((size_t)nd * L);
+    std::vector<double> dyn_size((size_t)nd * M * P);
+    for (int o = 0; o < nd; o++) {
+        const_vel_traj(p, vec3f(io->dyn_pos + 3 * o), vec3f(io->dyn_vel + 3 * o), dyn_pred.data() + L * o);
+        obstacle_sizes(p, io->dyn_size_prediction, io->dyn_uncertainty_horizon, io->dyn_radius[o], io->dyn_max_acc[o],
+                       dyn_size.data() + (size_t)o * M * P);
+    }
+    if (neighbours_from(p, N, io->pos, K, nd, io->nbr_idx, io->nbr_cnt))
         for (int a = 0; a < N; a++) io->status[a] |= ORC_NBR_OVERFLOW;
+    for (int a = 0; a < N; a++)
+        for (int o = 0; o < nd; o++) io->nbr_idx[(size_t)a * K + o] = N + o;
     double t1 = now_s();
     const int nt = io->n_threads > 1 ? io->n_threads : 1;
     parallel_for(NR, nt, [&](int ar) {
@@ -1419,6 +1570,12 @@ void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end
         for (int c = 0; c < io->nbr_cnt[a]; c++) {
             int j = io->nbr_idx[(size_t)a * K + c];
             size_t pr = (size_t)a * K + c;
+            if (c < nd) {
+                lsc_dynamic(p, io->init_traj + L * a, dyn_pred.data() + L * c, dyn_size.data() + (size_t)c * M * P,
+                            io->radius[a], io->dyn_radius[c], io->dyn_downwash[c], io->lsc_normal + pr * M * 3,
+                            io->lsc_anchor + pr * M * P * 3, io->lsc_d + pr * M * P);
+                continue;
+            }
             lsc_pair(p, io->init_traj + L * a, io->pred_traj + L * j, vec3f(io->goal_cur + 3 * a),
                      vec3f(io->goal_cur + 3 * j), io->radius[a], io->downwash[a], io->radius[j], io->downwash[j],
                      io->lsc_normal + pr * M * 3, io->lsc_anchor + pr * M * P * 3, io->lsc_d + pr * M * P, nullptr);
@@ -1434,7 +1591,24 @@ void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end
                                io->max_vel[a], io->sfc + (size_t)a * M * 6, nullptr);
             io->sfc_init_flag[a] = 0;
             io->status[a] |= st;
+            if (!init && p->comm_range > 0 && io->comm_box) {                               // constructCommunicationRange :538-546
+                const vec3f wp(io->waypoint + 3 * a), dl((float)(0.5 * p->comm_range), (float)(0.5 * p->comm_range), (float)(0.5 * p->comm_range));
+                (wp - dl).store(io->comm_box + 6 * a); (wp + dl).store(io->comm_box + 6 * a + 3);
+            }
         });
+    }
+    if (nd > 0) {
+        static const float zero_box[6] = {0, 0, 0, 0, 0, 0};
+        for (int a = a_begin; a < a_end; a++) {
+            size_t pr = (size_t)a * K;
+            const int tr = waypoint_trap(p, vec3f(io->goal_cur + 3 * a), vec3f(io->waypoint + 3 * a),
+                                         p->use_sfc ? io->sfc + ((size_t)a * M + (M - 1)) * 6 : nullptr,
+                                         io->comm_box ? io->comm_box + 6 * a : zero_box, io->nbr_cnt[a], nd,
+                                         io->lsc_normal + pr * M * 3, io->lsc_anchor + pr * M * P * 3, io->lsc_d + pr * M * P,
+                                         (size_t)M * 3, (size_t)M * P * 3, (size_t)M * P, io->dyn_pos, io->dyn_vel,
+                                         io->dyn_radius, io->dyn_max_acc, io->radius[a], io->dyn_uncertainty_horizon);
+            if (io->trap) io->trap[a] = (uint8_t)tr;
+        }
     }
     double t3 = now_s();
     // goal planning must see every neighbour's PREVIOUS goal in the LSC stage above; update after it.
@@ -1443,9 +1617,9 @@ void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end
         vec3f g(io->goal_cur + 3 * a);
         size_t pr = (size_t)a * K;
         int st = goal_agent(p, io->disturbed && io->disturbed[a], vec3f(io->pos + 3 * a), vec3f(io->waypoint + 3 * a),
-                            p->use_sfc ? io->sfc + ((size_t)a * M + (M - 1)) * 6 : nullptr, io->nbr_cnt[a],
-                            io->lsc_normal + pr * M * 3, io->lsc_anchor + pr * M * P * 3, io->lsc_d + pr * M * P,
-                            (size_t)M * 3, (size_t)M * P * 3, (size_t)M * P, g);
+                            p->use_sfc ? io->sfc + ((size_t)a * M + (M - 1)) * 6 : nullptr, io->nbr_cnt[a] - nd,
+                            io->lsc_normal + (pr + nd) * M * 3, io->lsc_anchor + (pr + nd) * M * P * 3, io->lsc_d + (pr + nd) * M * P,
+                            (size_t)M * 3, (size_t)M * P * 3, (size_t)M * P, g);          // dynamic obstacles skipped: goal_optimizer.cpp:176-178
         g.store(new_goal.data() + 3 * a);
         io->status[a] |= st;
     }
@@ -1463,7 +1637,8 @@ void orc_step_range(const orc_params* p, orc_step_io* io, int a_begin, int a_end
                           io->max_acc[a], io->nominal_vel[a], io->sfc + (size_t)a * M * 6, io->nbr_cnt[a],
                           io->lsc_normal + pr * M * 3, io->lsc_anchor + pr * M * P * 3, io->lsc_d + pr * M * P,
                           (size_t)M * 3, (size_t)M * P * 3, (size_t)M * P, io->init_traj + L * a, out.data(),
-                          io->qp_x ? io->qp_x + (size_t)a * nxa : nullptr, &cost, &viol, &it);
+                          io->qp_x ? io->qp_x + (size_t)a * nxa : nullptr, &cost, &viol, &it, nd, io->slack_collision_weight,
+                          (nd && io->qp_slack) ? io->qp_slack + (size_t)a * nd * M : nullptr);
         if (st != ORC_OK) std::memcpy(out.data(), io->init_traj + L * a, L * sizeof(float));   // failsafe traj_planner.cpp:775-776
         std::memcpy(io->prev_traj + L * a, out.data(), L * sizeof(float));                       // :57
         io->status[a] |= st;

@@ -147,6 +147,20 @@ typedef struct orc_step_io {
     int32_t* qp_iters;       /* [N] */
     int32_t* status;         /* [N] */
     double* stage_seconds;   /* [5]: predict+nbr, lsc, sfc, goal, qp (wall) or NULL */
+    /* dynamic (non-agent) obstacles, n_dyn = 0 when absent.  They take the first n_dyn obstacle slots of every agent
+     * (list entries N + o), like the obstacle list MultiSyncSimulator::broadcastMsgs builds (multi_sync_simulator.cpp:476-480). */
+    int n_dyn;
+    int dyn_size_prediction;          /* obs/size_prediction                    */
+    double dyn_uncertainty_horizon;   /* obs/uncertainty_horizon                */
+    double slack_collision_weight;    /* opt/slack_collision_weight             */
+    const float* dyn_pos;             /* [n_dyn][3] Obstacle::position          */
+    const float* dyn_vel;             /* [n_dyn][3]                             */
+    const double* dyn_radius;         /* [n_dyn]                                */
+    const double* dyn_downwash;
+    const double* dyn_max_acc;
+    float* comm_box;         /* state in/out [N][6]: CollisionConstraints::communication_range (zero until first built) or NULL */
+    double* qp_slack;        /* out [N][n_dyn][M] slack variables of the QP, or NULL */
+    uint8_t* trap;           /* out [N] checkWaypointTrap found the waypoint trapped, or NULL */
 } orc_step_io;
 void orc_step(const orc_params* p, orc_step_io* io);
 /* replan only agents [a_begin, a_end) (bounded CPU-baseline samples of large swarms) */

@@ -47,6 +47,11 @@ class OrcStepIO(C.Structure):
         ("lsc_d", C.c_void_p), ("qp_x", C.c_void_p), ("cost", C.c_void_p),
         ("max_violation", C.c_void_p), ("qp_iters", C.c_void_p), ("status", C.c_void_p),
         ("stage_seconds", C.c_void_p),
+        ("n_dyn", C.c_int), ("dyn_size_prediction", C.c_int), ("dyn_uncertainty_horizon", C.c_double),
+        ("slack_collision_weight", C.c_double),
+        ("dyn_pos", C.c_void_p), ("dyn_vel", C.c_void_p), ("dyn_radius", C.c_void_p),
+        ("dyn_downwash", C.c_void_p), ("dyn_max_acc", C.c_void_p),
+        ("comm_box", C.c_void_p), ("qp_slack", C.c_void_p), ("trap", C.c_void_p),
     ]
 
 
@@ -221,6 +226,24 @@ class Swarm:
         self.qp_iters = np.zeros(N, np.int32)
         self.status = np.zeros(N, np.int32)
         self.stage_seconds = np.zeros(5)
+        self.comm_box = np.zeros((N, 6), np.float32)
+        self.trap = np.zeros(N, np.uint8)
+        self.set_obstacles(None)
+
+    def set_obstacles(self, pos, vel=None, radius=None, downwash=None, max_acc=None, slack_weight=1.0,
+                      size_prediction=True, uncertainty_horizon=1.0):
+        """Dynamic (non-agent) obstacles of the next replans: Obstacle::position / velocity / radius / downwash /
+        max_acc as the simulator's obstacle generator publishes them, plus opt/slack_collision_weight,
+        obs/size_prediction, obs/uncertainty_horizon.  None removes them."""
+        self.n_dyn = 0 if pos is None else int(np.asarray(pos).reshape(-1, 3).shape[0])
+        nd = self.n_dyn
+        self.dyn_pos = np.ascontiguousarray(np.zeros((0, 3)) if pos is None else pos, np.float32).reshape(nd, 3).copy()
+        self.dyn_vel = np.ascontiguousarray(np.zeros((nd, 3)) if vel is None else vel, np.float32).reshape(nd, 3).copy()
+        full = lambda v, dflt: np.full(nd, dflt if v is None else v, np.float64) if (v is None or np.isscalar(v)) \
+            else np.ascontiguousarray(v, np.float64).copy()
+        self.dyn_radius, self.dyn_downwash, self.dyn_max_acc = full(radius, 0.15), full(downwash, 1.0), full(max_acc, 0.0)
+        self.slack_weight, self.size_prediction, self.uncertainty_horizon = float(slack_weight), bool(size_prediction), float(uncertainty_horizon)
+        self.qp_slack = np.zeros((self.N, max(nd, 1), self.p.M), np.float64)
 
     def step(self, a_begin=None, a_end=None):
         """One replan of every agent (TrajPlanner::plan for all agents), or of agents [a_begin, a_end)."""
@@ -235,6 +258,10 @@ class Swarm:
         io.prev_traj = self.traj.ctypes.data
         io.sfc_init_flag = self.sfc_init.ctypes.data
         io.edt = C.addressof(self.edt.c) if self.edt is not None else None
+        io.n_dyn, io.dyn_size_prediction = self.n_dyn, int(self.size_prediction)
+        io.dyn_uncertainty_horizon, io.slack_collision_weight = self.uncertainty_horizon, self.slack_weight
+        for name in ("dyn_pos", "dyn_vel", "dyn_radius", "dyn_downwash", "dyn_max_acc", "comm_box", "qp_slack", "trap"):
+            setattr(io, name, getattr(self, name).ctypes.data)
         if a_begin is None:
             lib().orc_step(C.byref(self.p), C.byref(io))
         else:

@@ -42,6 +42,10 @@ struct dlsc_ctx {
     EdtDev edt;
     bool have_edt = false;
     int64_t counters[DLSC_N_COUNTERS] = {0};
+    // dynamic obstacles
+    std::vector<float> dyn_pos, dyn_vel, comm_box;
+    std::vector<double> dyn_radius, dyn_downwash, dyn_max_acc, dyn_size, qp_slack;
+    std::vector<uint8_t> trap;
 };
 
 extern "C" {
@@ -79,7 +83,8 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     c->disturbed.assign(NL, 0); c->sfc_init.assign(NL, 1);
     c->radius.assign(NL, 0); c->downwash.assign(NL, 0); c->max_vel.assign(NL, 0); c->max_acc.assign(NL, 0);
     c->nominal_vel.assign(NL, 0);
-    c->pred_traj.assign(N * npt * 3, 0.f); c->init_traj.assign(NL * npt * 3, 0.f);
+    c->pred_traj.assign((N + kMaxDyn) * npt * 3, 0.f);
+    c->comm_box.assign(NL * 6, 0.f); c->trap.assign(NL, 0); c->qp_slack.assign(NL * kMaxDyn * M, 0.0); c->init_traj.assign(NL * npt * 3, 0.f);
     c->nbr_idx.assign(NL * K, 0); c->nbr_cnt.assign(NL, 0);
     c->lsc_normal.assign(NL * K * M * 3, 0.f); c->lsc_d.assign(NL * K * M * kP, 0.0);
     c->lsc_anchor_last.assign(NL * K * 3, 0.f);
@@ -239,6 +244,31 @@ int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
     return 0;
 }
 
+int dlsc_set_obstacles(dlsc_ctx* c, const dlsc_obstacles* o, const dlsc_obstacle_params* op) {
+    const int n = o ? o->n : 0;
+    if (n < 0 || n > kMaxDyn) return fail("too many obstacles");
+    if (n == 0) { c->P.n_dyn = 0; return 0; }
+    if (!(op->slack_collision_weight > 0) || c->P.qp_solver == 1 || n >= c->P.K) return fail("bad obstacle setup");
+    c->dyn_pos.assign(o->pos, o->pos + 3 * n); c->dyn_vel.assign(o->vel, o->vel + 3 * n);
+    c->dyn_radius.assign(o->radius, o->radius + n); c->dyn_downwash.assign(o->downwash, o->downwash + n);
+    c->dyn_max_acc.assign(o->max_acc, o->max_acc + n);
+    c->dyn_size.assign((size_t)n * c->P.M * kP, 0.0);
+    for (int i = 0; i < n; i++)
+        dyn_obstacle_sizes(c->P, op->size_prediction != 0, op->uncertainty_horizon, o->radius[i], o->max_acc[i], c->dyn_size.data() + (size_t)i * c->P.M * kP);
+    c->P.n_dyn = n; c->P.slack_w = op->slack_collision_weight; c->P.dyn_horizon = op->uncertainty_horizon;
+    return 0;
+}
+int dlsc_get_slack(dlsc_ctx* c, double* slack) {
+    const int nd = c->P.n_dyn, M = c->P.M;
+    for (int a = 0; a < c->P.NL; a++) memcpy(slack + (size_t)a * nd * M, c->qp_slack.data() + (size_t)a * kMaxDyn * M, (size_t)nd * M * 8);
+    return 0;
+}
+int dlsc_get_trap(dlsc_ctx* c, uint8_t* trap) { memcpy(trap, c->trap.data(), c->trap.size()); return 0; }
+int dlsc_get_obstacle_pred(dlsc_ctx* c, float* t) {
+    memcpy(t, c->pred_traj.data() + (size_t)c->P.N * c->P.M * kP * 3, (size_t)c->P.n_dyn * c->P.M * kP * 12);
+    return 0;
+}
+
 int dlsc_reset(dlsc_ctx* c, const float* start) {
     const DevParams& P = c->P;
     const int npt = P.M * kP;
@@ -251,6 +281,7 @@ int dlsc_reset(dlsc_ctx* c, const float* start) {
         for (int e = o + 11; e < P.rec; e++) rec[e] = 0.f;
         for (int k = 0; k < 3; k++) { c->acc[la * 3 + k] = 0.f; c->waypoint[la * 3 + k] = start[la * 3 + k]; c->goal_new[la * 3 + k] = start[la * 3 + k]; }
         c->disturbed[la] = 0; c->sfc_init[la] = 1; c->status[la] = 0;
+        for (int e = 0; e < 6; e++) c->comm_box[(size_t)la * 6 + e] = 0.f;
         for (int e = 0; e < npt * 3; e++) c->traj[(size_t)la * npt * 3 + e] = rec[e];
     }
     c->seq = 0;
@@ -306,17 +337,37 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
                               local ? c->init_traj.data() + (size_t)la * npt * 3 : nullptr);
             if (local) c->status[la] = 0;
         }
+    const int nd = P.n_dyn;
+    if ((mask & DLSC_STAGE_PREDICT) && nd > 0) {                       // k_dyn_predict
+        for (int o = 0; o < nd; o++)
+            for (int pt = 0; pt < npt; pt++)
+                v3_store(c->pred_traj.data() + ((size_t)(P.N + o) * npt + pt) * 3,
+                         v3_load(c->dyn_pos.data() + 3 * o) + v3_load(c->dyn_vel.data() + 3 * o) * P.tk[pt]);
+        for (int la = 0; la < P.NL; la++) {
+            comm_box_update(P, c->sfc_init[la] != 0 || c->disturbed[la] != 0, v3_load(c->waypoint.data() + la * 3), c->comm_box.data() + (size_t)la * 6);
+            for (int o = 0; o < nd; o++) c->nbr_idx[(size_t)la * K + o] = P.N + o;
+        }
+    }
     if (mask & DLSC_STAGE_NBR)
         for (int la = 0; la < P.NL; la++) {
-            const int cnt = neighbours_agent(g, P, c->rec.data(), P.begin + la, c->nbr_idx.data() + (size_t)la * K);
-            c->nbr_cnt[la] = cnt < K ? cnt : K;
-            if (cnt > K) c->status[la] |= kStNbrOverflow;
-            c->counters[0] += c->nbr_cnt[la];
+            const int Kc = K - nd;
+            const int cnt = neighbours_agent(g, P, c->rec.data(), P.begin + la, c->nbr_idx.data() + (size_t)la * K + nd);
+            c->nbr_cnt[la] = nd + (cnt < Kc ? cnt : Kc);
+            if (cnt > Kc) c->status[la] |= kStNbrOverflow;
+            c->counters[0] += c->nbr_cnt[la] - nd;
         }
     if (mask & DLSC_STAGE_LSC)
         for (int la = 0; la < P.NL; la++)
             for (int cc = 0; cc < c->nbr_cnt[la]; cc++) {
                 const int j = c->nbr_idx[(size_t)la * K + cc];
+                if (cc < nd) {                                         // k_lsc_dyn
+                    const size_t prd = (size_t)la * K + cc;
+                    for (int m = 0; m < M; m++)
+                        lsc_dynamic_segment(c->init_traj.data() + ((size_t)la * npt + m * kP) * 3, c->pred_traj.data() + ((size_t)(P.N + cc) * npt + m * kP) * 3,
+                                            c->dyn_size.data() + ((size_t)cc * M + m) * kP, c->radius[la], c->dyn_radius[cc], c->dyn_downwash[cc],
+                                            c->lsc_normal.data() + (prd * M + m) * 3, c->lsc_d.data() + (prd * M + m) * kP, c->lsc_near.data() + prd * M + m);
+                    continue;
+                }
                 const float* rec_a = c->rec.data() + (size_t)(P.begin + la) * P.rec;
                 const float* rec_j = c->rec.data() + (size_t)j * P.rec;
                 const int og = npt * 3 + 6;
@@ -345,13 +396,24 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             c->status[la] |= st;
             c->counters[2] += lookups[0]; c->counters[5] += lookups[1]; c->counters[6] += lookups[2]; c->counters[7] += lookups[3]; c->counters[8] += lookups[4];
         }
+    if ((mask & DLSC_STAGE_GOAL) && nd > 0)                            // k_trap
+        for (int la = 0; la < P.NL; la++) {
+            const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
+            const size_t pr = (size_t)la * K;
+            DynObs O; O.pos = c->dyn_pos.data(); O.vel = c->dyn_vel.data(); O.radius = c->dyn_radius.data(); O.downwash = c->dyn_downwash.data();
+            O.max_acc = c->dyn_max_acc.data(); O.size = c->dyn_size.data();
+            c->trap[la] = (uint8_t)waypoint_trap(P, O, v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3),
+                                                 c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->comm_box.data() + (size_t)la * 6, c->nbr_cnt[la],
+                                                 c->lsc_normal.data() + pr * M * 3, c->lsc_d.data() + pr * M * kP, c->lsc_anchor_last.data() + pr * 3,
+                                                 c->radius[la]);
+        }
     if (mask & DLSC_STAGE_GOAL)
         for (int la = 0; la < P.NL; la++) {
             const float* rec = c->rec.data() + (size_t)(P.begin + la) * P.rec;
             V3 goal = v3_load(rec + npt * 3 + 6);
-            const size_t pr = (size_t)la * K;
+            const size_t pr = (size_t)la * K + nd;
             const int st = goal_agent(g, P, c->disturbed[la] != 0, v3_load(rec + npt * 3), v3_load(c->waypoint.data() + la * 3),
-                                      c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->nbr_cnt[la],
+                                      c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->nbr_cnt[la] - nd,
                                       c->lsc_normal.data() + pr * M * 3, c->lsc_d.data() + pr * M * kP,
                                       c->lsc_anchor_last.data() + pr * 3, goal);
             v3_store(c->goal_new.data() + la * 3, goal);
@@ -388,6 +450,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             out.x = c->qp_x.data() + (size_t)la * c->T.nx;
             out.cost = &c->cost[la]; out.viol = &c->viol[la]; out.iters = &c->qp_iters[la]; out.status = &c->status[la];
             out.rows = &rows;
+            out.slack = nd > 0 ? c->qp_slack.data() + (size_t)la * kMaxDyn * M : nullptr;
             bool done = false;
             if (P.qp_solver != 1) {
                 QpSmem sg;
@@ -445,7 +508,7 @@ GET(dlsc_get_violation, double, viol)
 GET(dlsc_get_qp_iters, int32_t, qp_iters)
 GET(dlsc_get_status, int32_t, status)
 GET(dlsc_get_init_traj, float, init_traj)
-GET(dlsc_get_pred_traj, float, pred_traj)
+int dlsc_get_pred_traj(dlsc_ctx* c, float* t) { memcpy(t, c->pred_traj.data(), (size_t)c->P.N * c->P.M * kP * 12); return 0; }
 GET(dlsc_get_sfc, float, sfc)
 #undef GET
 
@@ -478,7 +541,7 @@ int dlsc_get_lsc(dlsc_ctx* c, float* normal, float* anchor, double* d) {
                     float v[3] = {0.f, 0.f, 0.f};
                     if (cc < c->nbr_cnt[la]) {
                         const int j = c->nbr_idx[pr];
-                        const float* src = (pt / kP < P.M - 1) ? c->pred_traj.data() + ((size_t)j * npt + pt) * 3
+                        const float* src = (pt / kP < P.M - 1 || cc < P.n_dyn) ? c->pred_traj.data() + ((size_t)j * npt + pt) * 3
                                                                : c->lsc_anchor_last.data() + pr * 3;
                         v[0] = src[0]; v[1] = src[1]; v[2] = src[2];
                     }
@@ -498,7 +561,7 @@ int dlsc_get_timings(dlsc_ctx*, double ms[DLSC_N_STAGES], int* n) { for (int i =
 
 int dlsc_run_stages_subset(dlsc_ctx*, int, int, int) { return fail("hostsim: not supported"); }
 int dlsc_set_init_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f); memcpy(c->init_traj.data(), t, c->init_traj.size() * 4); return 0; }
-int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f); memcpy(c->pred_traj.data(), t, c->pred_traj.size() * 4); return 0; }
+int dlsc_set_pred_traj(dlsc_ctx* c, const float* t) { std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f); memcpy(c->pred_traj.data(), t, (size_t)c->P.N * c->P.M * kP * 12); return 0; }
 int dlsc_set_neighbours(dlsc_ctx* c, const int32_t* idx, const int32_t* cnt) {
     std::fill(c->lsc_near.begin(), c->lsc_near.end(), 0.0f);
     memcpy(c->nbr_idx.data(), idx, c->nbr_idx.size() * 4); memcpy(c->nbr_cnt.data(), cnt, c->nbr_cnt.size() * 4); return 0;

@@ -39,10 +39,15 @@ def terminal_segments(M, dt, goal, pos, nominal_vel):
 
 
 def build_qp(M, n, dim, dt, w_control, w_terminal, world_min, world_max, comm_range, pos, vel, acc, goal, waypoint,
-             radius, max_vel, max_acc, nominal_vel, sfc=None, lsc_normal=None, lsc_anchor=None, lsc_d=None):
-    """sfc [M][6] or None; lsc_* [K][M][3] / [K][M][P][3] / [K][M][P] (only real neighbours)."""
+             radius, max_vel, max_acc, nominal_vel, sfc=None, lsc_normal=None, lsc_anchor=None, lsc_d=None,
+             n_dyn=0, slack_weight=0.0):
+    """sfc [M][6] or None; lsc_* [K][M][3] / [K][M][P][3] / [K][M][P] (only real neighbours).
+    The first n_dyn obstacles are dynamic (non-agent) obstacles: M slack variables each, appended after the control
+    points, epsilon <= 0 (:272-283), cost slack_weight (M - m)/M epsilon^2 (:317-331), rows n.(x - p) - d - epsilon >= 0
+    (:436-448)."""
     P, phi = n + 1, 3
-    nx = dim * M * P
+    nxc = dim * M * P                      # control-point variables
+    nx = nxc + n_dyn * M                   # + slack variables
     vid = lambda k, m, i: k * M * P + m * P + i
     f64 = lambda a: np.asarray(a, np.float32).astype(np.float64)
     pos, vel, acc, goal, waypoint = f64(pos), f64(vel), f64(acc), f64(goal), f64(waypoint)
@@ -59,7 +64,11 @@ def build_qp(M, n, dim, dt, w_control, w_terminal, world_min, world_max, comm_ra
             Q[j, j] += 2.0 * w_terminal
             c[j] += -2.0 * w_terminal * goal[k]
             c0 += w_terminal * goal[k] * goal[k]
+    for oi in range(n_dyn):
+        for m in range(M):
+            Q[nxc + M * oi + m, nxc + M * oi + m] = 2.0 * slack_weight * (M - m) / M
     xlo = np.full(nx, -INF); xhi = np.full(nx, INF)                  # :251-265
+    xhi[nxc:] = 0.0
     for k in range(dim):
         for m in range(M):
             for i in range(P):
@@ -116,7 +125,8 @@ def build_qp(M, n, dim, dt, w_control, w_terminal, world_min, world_max, comm_ra
                     if m == 0 and i < phi:
                         continue
                     rhs = dd[oi, m, i] + sum(nv[oi, m, k] * an[oi, m, i, k] for k in range(dim))
-                    add([(vid(k, m, i), nv[oi, m, k]) for k in range(dim)], rhs, INF)
+                    slack = [(nxc + M * oi + m, -1.0)] if oi < n_dyn else []
+                    add([(vid(k, m, i), nv[oi, m, k]) for k in range(dim)] + slack, rhs, INF)
     for k in range(dim):                                             # :452-487
         for m in range(M):
             for i in range(n):

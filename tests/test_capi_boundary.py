@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_symbol():
     missing = [s for s in header_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     assert lib.dlsc_cuda_build() > 0
-    assert lib.dlsc_abi_version() == 3
+    assert lib.dlsc_abi_version() == 4
 
 
 def test_loader_refuses_a_cpu_stand_in(hostsim, monkeypatch):
