@@ -312,6 +312,9 @@ constexpr int kLscThreads = DLSC_LSC_THREADS, kLscRestThreads = 64;
 constexpr int kCntSeg = 14, kCntHard = 15;     // S.counters slots used as queue lengths (zeroed with the counters)
 __device__ __forceinline__ uint32_t lsc_pack(int la, int c, int m) { return ((uint32_t)la << 14) | ((uint32_t)c << 4) | (uint32_t)m; }
 
+// DYN: dynamic obstacles present (the first P.n_dyn slots belong to k_lsc_dyn); the DYN = false instantiation is the
+// swarm-only hot path, compiled without the slot offset
+template <bool DYN>
 __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ float s_init[kMaxPts * 3];
     __shared__ int s_nhard, s_base, s_seg;
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kLscThreads, DLSC_LSC_MINB) k_lsc(const __grid
     uint32_t* s_hard = reinterpret_cast<uint32_t*>(s_nbr + P.K);
     const int M = P.M, npt = M * kP;
     const int la = blockIdx.x;
-    const int cnt = S.nbr_cnt[la], nd = P.n_dyn;           // slots [0, nd): dynamic obstacles, done by k_lsc_dyn
+    const int cnt = S.nbr_cnt[la], nd = DYN ? P.n_dyn : 0;  // slots [0, nd): dynamic obstacles, done by k_lsc_dyn
     const int og = npt * 3 + 6;
     if (threadIdx.x == 0) s_nhard = 0;
     for (int e = threadIdx.x; e < npt * 3; e += kLscThreads) s_init[e] = S.init_traj[(size_t)la * npt * 3 + e];
@@ -413,7 +416,9 @@ __global__ void __launch_bounds__(128) k_lsc_dyn(const __grid_constant__ DevPara
 
 int launch_lsc(const DevParams& P, const DevState& S, cudaStream_t st) {
     static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-    k_lsc<<<P.NL, kLscThreads, (size_t)P.K * (sizeof(LscPair) + (size_t)P.M * sizeof(int)), st>>>(P, S);
+    const size_t lsc_smem = (size_t)P.K * (sizeof(LscPair) + (size_t)P.M * sizeof(int));
+    if (P.n_dyn > 0) k_lsc<true><<<P.NL, kLscThreads, lsc_smem, st>>>(P, S);
+    else k_lsc<false><<<P.NL, kLscThreads, lsc_smem, st>>>(P, S);
     k_lsc_rest<<<sms * 8, kLscRestThreads, 0, st>>>(P, S);
     if (P.n_dyn > 0) {
         const int n = P.NL * P.n_dyn * P.M;

