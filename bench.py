@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--mc-missions", type=int, default=128, help="Monte-Carlo leg: independent empty50 missions per GPU (0: skip)")
     ap.add_argument("--mc-steps", type=int, default=20)
     ap.add_argument("--closed-loop-steps", type=int, default=4, help="steps of the closed loop with the waypoint provider (0: skip)")
+    ap.add_argument("--dyn-obstacles", type=int, default=8, help="dynamic-obstacle leg (1 GPU): obstacles flying through the swarm (0: skip)")
+    ap.add_argument("--dyn-steps", type=int, default=20)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU record exchange: stores over NVLink peer memory (default) or NCCL all-gather")
     return ap.parse_args()
@@ -554,6 +556,41 @@ def run_ours(args):
                           "completion for all %d agents, update rules), waypoints H2D, dlsc_step, dlsc_advance" % N}
         wp.close()
 
+    # ---------------- dynamic obstacles (SURVEY s8(f4), 1 GPU): the same swarm with obstacles flying through it ----------------
+    # every step: dlsc_set_obstacles (host states in) -> dlsc_step (obstacle prediction, k_lsc_dyn, k_trap, slack QP with the
+    # 128-row second-chance kernel) -> dlsc_advance.  Obstacles: 0.3 m spheres crossing the swarm area at 1 m/s, max_acc 2,
+    # opt/slack_collision_weight 100 (launch/testall_DLSCGC_3D.launch).  Reported beside the swarm-only headline.
+    dyn = None
+    if world == 1 and args.dyn_obstacles > 0:
+        restore(pl, snap, sl)
+        nd = min(args.dyn_obstacles, 16)
+        rng = np.random.default_rng(1234)
+        he = float(m.world_max[0]) * 0.7
+        opos = np.stack([rng.uniform(-he, he, nd), rng.uniform(-he, he, nd), np.full(nd, 1.0)], axis=1).astype(np.float32)
+        ang = rng.uniform(0, 2 * np.pi, nd)
+        ovel = np.stack([np.cos(ang), np.sin(ang), np.zeros(nd)], axis=1).astype(np.float32)
+        kw = dict(radius=0.3, downwash=1.0, max_acc=2.0, slack_weight=100.0)
+        fails, slack_agents, min_slack, big = 0, 0, 0.0, 0
+        ed0, ed1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_dw = 3
+        for t in range(n_dw + args.dyn_steps):
+            if t == n_dw:
+                torch.cuda.synchronize(); td0 = time.perf_counter(); ed0.record()
+            pl.set_waypoints_device(wp_dev[t % len(wp_dev)].data_ptr())
+            pl.set_obstacles(opos, ovel, **kw)
+            pl.plan(); pl.advance()
+            opos = opos + ovel * np.float32(cfg.dt)
+        ed1.record(); pl.sync(); torch.cuda.synchronize()
+        td1 = time.perf_counter()
+        st = pl.status(); sk = pl.slack()
+        fails = int(((st & capi.FAIL_MASK & ~capi.NBR_OVERFLOW) != 0).sum())
+        dyn = {"obstacles": nd, "steps": args.dyn_steps, "ms_per_step": 1e3 * (td1 - td0) / args.dyn_steps,
+               "device_ms_per_step": ed0.elapsed_time(ed1) / args.dyn_steps, "value": N * args.dyn_steps / (td1 - td0), "unit": UNIT,
+               "last_step": {"qp_failsafe_agents": fails, "nbr_overflow_agents": int(((st & capi.NBR_OVERFLOW) != 0).sum()),
+                             "agents_using_slack": int((sk.min(axis=(1, 2)) < -1e-6).sum()), "min_slack_m": float(sk.min())},
+               "what": "host clock over dlsc_set_obstacles + dlsc_step + dlsc_advance per step, states device-resident; "
+                       "%d obstacles (r 0.3 m, 1 m/s straight lines, max_acc 2), slack weight 100" % nd}
+
     out = None
     if rank == 0:
         peaks = {}
@@ -588,6 +625,8 @@ def run_ours(args):
         }
         if closed:
             out["closed_loop"] = closed
+        if dyn:
+            out["dynamic_obstacles"] = dyn
         hbm = peaks.get("hbm_gbs") or 6650.0
         ncell = int(edt[2][0]) * int(edt[2][1]) * int(edt[2][2])
         out["edt_build"] = {"kernels": "k_edt_pass_z_cols + k_edt_col_any/window + k_edt_pass_y/x", "ms": edt_ms, "cells": ncell, "bound": "hbm",

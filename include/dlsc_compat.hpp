@@ -183,6 +183,8 @@ public:
     double dt = 0.2;
     int M = 5, n = 5, phi = 3, phi_n = 1;
     double control_input_weight = 0.01, terminal_weight = 1.0, slack_collision_weight = 1.0;
+    bool obs_size_prediction = true;
+    double obs_uncertainty_horizon = 1.0;
     double grid_resolution = 0.5;
     double goal_threshold = 0.1, reset_threshold = 0.5, slack_threshold = 0.1;
     double communication_range = -1.0;
@@ -270,8 +272,9 @@ public:
         std::string k;
         auto put = [&k](const void* q, size_t n) { k.append(static_cast<const char*>(q), n); };
         const double pd[] = {p.world_resolution, p.world_z_2d, p.dt, p.control_input_weight, p.terminal_weight, p.grid_resolution,
-                             p.reset_threshold, p.communication_range};
-        const int pi[] = {p.world_dimension, p.world_use_octomap ? 1 : 0, p.M, p.n, p.phi, p.max_neighbours, (int)m.qn};
+                             p.reset_threshold, p.communication_range, p.slack_collision_weight, p.obs_uncertainty_horizon};
+        const int pi[] = {p.world_dimension, p.world_use_octomap ? 1 : 0, p.M, p.n, p.phi, p.max_neighbours, (int)m.qn,
+                          p.obs_size_prediction ? 1 : 0};
         put(pd, sizeof(pd)); put(pi, sizeof(pi));
         for (unsigned c = 0; c < 3; c++) { const float w[2] = {m.world_min(c), m.world_max(c)}; put(w, sizeof(w)); }
         for (const Agent& a : m.agents) {
@@ -315,6 +318,26 @@ public:
         if (o.type != ObstacleType::AGENT || o.id < 0 || o.id >= N) return;
         for (unsigned k = 0; k < 3; k++) { pos[o.id * 3 + k] = o.position(k); vel[o.id * 3 + k] = o.velocity(k); }
     }
+    // the non-agent entries of the obstacle list broadcastMsgs hands to every agent (the same for all of them): position,
+    // velocity, radius, downwash, max_acc -> dlsc_set_obstacles, re-sent only when something changed
+    void set_dynamic(const Obstacles& all) {
+        std::vector<float> p, v;
+        std::vector<double> r, dw, ma;
+        for (const Obstacle& o : all) {
+            if (o.type == ObstacleType::AGENT) continue;
+            for (unsigned k = 0; k < 3; k++) { p.push_back(o.position(k)); v.push_back(o.velocity(k)); }
+            r.push_back(o.radius); dw.push_back(o.downwash); ma.push_back(o.max_acc);
+        }
+        if (r.size() > (size_t)DLSC_MAX_OBSTACLES)
+            throw std::length_error("[TrajPlanner] more than " + std::to_string(DLSC_MAX_OBSTACLES) + " dynamic obstacles");
+        if (p == dyn_pos && v == dyn_vel && r == dyn_r && dw == dyn_dw && ma == dyn_ma) return;
+        dyn_pos = p; dyn_vel = v; dyn_r = r; dyn_dw = dw; dyn_ma = ma;
+        if (r.empty()) { check(dlsc_set_obstacles(ctx, nullptr, nullptr), "dlsc_set_obstacles"); return; }
+        dlsc_obstacles o{(int32_t)r.size(), dyn_pos.data(), dyn_vel.data(), dyn_r.data(), dyn_dw.data(), dyn_ma.data()};
+        dlsc_obstacle_params op{slack_w, obs_horizon, obs_size_pred ? 1 : 0, 0};
+        check(dlsc_set_obstacles(ctx, &o, &op), "dlsc_set_obstacles");
+    }
+    int n_dynamic() const { return (int)dyn_r.size(); }
     void set_distmap(const std::shared_ptr<DynamicEDTOctomap>& d) {
 #ifdef DLSC_COMPAT_STANDALONE
         if (!d || d.get() == distmap_seen) return;
@@ -397,6 +420,7 @@ public:
 private:
     SwarmBatch(const Param& p, const Mission& m) {
         N = (int)m.qn; M = p.M; n = p.n; dt = p.dt; res = p.world_resolution;
+        slack_w = p.slack_collision_weight; obs_horizon = p.obs_uncertainty_horizon; obs_size_pred = p.obs_size_prediction;
         if (N < 1 || (size_t)N != m.agents.size()) throw std::invalid_argument("[TrajPlanner] mission has no agents");
         const int K = p.max_neighbours > 0 ? p.max_neighbours : std::max(N - 1, 1);
         dlsc_params q = make_params(p, m, K);
@@ -433,6 +457,10 @@ private:
             for (int s = 0; s < DLSC_N_STAGES; s++) stage_s[s] = ms[s] * 1e-3 / (batch_last ? N : 1);
     }
     std::vector<float> pos, vel, acc, wp;
+    std::vector<float> dyn_pos, dyn_vel;           // dynamic obstacles last sent to the device
+    std::vector<double> dyn_r, dyn_dw, dyn_ma;
+    double slack_w = 1.0, obs_horizon = 1.0;
+    bool obs_size_pred = true;
     std::vector<uint8_t> dist;
     bool step_open = true, batch_done = false, pending_publish = false, batch_last = false;
     const void* distmap_seen = nullptr;
@@ -626,12 +654,9 @@ public:
     }
     void publish() {}
     void setObstacles(const Obstacles& obstacles_) {
-        for (const auto& o : obstacles_)
-            if (o.type != ObstacleType::AGENT)     // dynamic obstacles (slack QP, size prediction): not on the device path yet
-                throw std::invalid_argument("[TrajPlanner] obstacle " + std::to_string(o.id) + " is not an agent: dynamic obstacles "
-                                            "are not supported by the B200 path (SURVEY s8(f) rank 4)");
         obstacles = obstacles_;
         batch->new_step();
+        batch->set_dynamic(obstacles);             // non-agent entries: dynamic obstacles (size prediction, slack QP) on the device
         for (const auto& o : obstacles) batch->observe(o);
     }
     // the mission's shared device context (NULL never): MapManager-side bindings hand maps over through it

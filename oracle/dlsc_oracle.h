@@ -13,6 +13,9 @@
  *     log log/result_1742185870.978562_DLSCGC_10agents.csv (tests/test_oracle_golden.py).
  *   - QP objective value / dynamicEDT3D tie-breaking / CPLEX tolerances: parity unpinned
  *     (third-party code absent from /root/reference); cross-checked against HiGHS.
+ *   - dynamic (non-agent) obstacle path: parity unpinned (the reference holds no run, vector or test
+ *     with dynamic obstacles); restated line by line, slack QP cross-checked against HiGHS
+ *     (tests/test_dynamic_obstacles.py).
  */
 #ifndef DLSC_ORACLE_H
 #define DLSC_ORACLE_H

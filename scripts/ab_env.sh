@@ -3,7 +3,7 @@
 var=$1; shift
 for v in "$@"; do
   export $var=$v
-  timeout 300 python bench.py --no-cpu-baseline --mc-missions 0 --closed-loop-steps 0 --steps 30 2> gpurun_out/ab_env.err | tail -1 > gpurun_out/ab_env.json
+  timeout 300 python bench.py --no-cpu-baseline --mc-missions 0 --closed-loop-steps 0 --dyn-obstacles 0 --steps 30 2> gpurun_out/ab_env.err | tail -1 > gpurun_out/ab_env.json
   python -c "
 import json
 d=json.load(open('gpurun_out/ab_env.json'))

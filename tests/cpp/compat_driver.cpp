@@ -93,7 +93,7 @@ int main(int argc, char** argv) {
         printf("step %d checksum %.9f cost %.9f min_dist %.6f seq %d\n", step, checksum, cost, dmin, planners[0]->getPlannerSeq());
     }
     {   // PlanningStatistics is filled from the device stage timers; a second mission with the same agent count gets its
-        // own context; a dynamic (non-agent) obstacle is refused
+        // own context; a dynamic (non-agent) obstacle changes the plan
         const PlanningStatistics ps = planners[0]->getPlanningStatistics();
         printf("stats seq %d total %.3e qp %.3e samples %d\n", ps.planning_seq, ps.planning_time.total_planning_time.average,
                ps.planning_time.traj_optimization_time.average, ps.planning_time.total_planning_time.N_sample);
@@ -102,11 +102,35 @@ int main(int argc, char** argv) {
         TrajPlanner p2(nh, param, other, other.agents[0]);
         printf("contexts distinct %d same %d\n", p2.deviceContext() != planners[0]->deviceContext() ? 1 : 0,
                planners[1]->deviceContext() == planners[0]->deviceContext() ? 1 : 0);
-        Obstacles dyn(1);
-        dyn[0].type = ObstacleType::DYN_SPIN; dyn[0].id = 99;
-        int refused = 0;
-        try { p2.setObstacles(dyn); } catch (const std::invalid_argument&) { refused = 1; }
-        printf("dynamic obstacle refused %d\n", refused);
+        // a dynamic (non-agent) obstacle in the list goes to the device path: same agent planned with and without an obstacle
+        // that flies through its start position (not near its waypoint: with comm range <= 0 checkWaypointTrap drops those)
+        Mission third = mission;
+        third.agents[0].desired_goal_point = point3d(0.5f, 0.6f, 1.f);
+        TrajPlanner p3(nh, param, third, third.agents[0]);
+        double cost[2], endy[2];
+        TrajPlanner* pp[2] = {&p2, &p3};
+        Mission* mm[2] = {&other, &third};
+        for (int w = 0; w < 2; w++) {
+            Agent a0 = mm[w]->agents[0];
+            a0.next_waypoint = point3d(1.53f, 0.16f, 1.f);
+            Obstacles obs;
+            for (int j = 1; j < N; j++) {
+                Obstacle o;
+                o.type = ObstacleType::AGENT; o.id = j; o.position = mm[w]->agents[j].start_point; o.goal_point = o.position;
+                o.radius = (float)mm[w]->agents[j].radius; o.downwash = (float)mm[w]->agents[j].downwash;
+                obs.push_back(o);
+            }
+            if (w == 0) {
+                Obstacle d;
+                d.type = ObstacleType::DYN_SPIN; d.id = 0; d.position = point3d(2.f, -0.6f, 1.f); d.velocity = point3d(0.f, 0.5f, 0.f);
+                d.radius = 0.3; d.downwash = 1.0; d.max_acc = 0.0;
+                obs.insert(obs.begin(), d);                       // broadcastMsgs lists the dynamic obstacles first
+            }
+            pp[w]->setObstacles(obs);
+            TrajOptResult r = pp[w]->plan(a0, octree, distmap, ros::Time(), false);
+            cost[w] = r.total_qp_cost; endy[w] = r.desired_traj.lastPoint().y();
+        }
+        printf("dynamic obstacle planned cost %.6f vs %.6f end_y %.4f vs %.4f\n", cost[0], cost[1], endy[0], endy[1]);
     }
     // TrajOptimizer::solve with explicit constraints (one LSC plane, no SFC)
     {
