@@ -526,7 +526,6 @@ int dlsc_set_obstacles(dlsc_ctx* c, const dlsc_obstacles* o, const dlsc_obstacle
     if (n == 0) { c->P.n_dyn = 0; return 0; }
     if (!o->pos || !o->vel || !o->radius || !o->downwash || !o->max_acc || !op) return fail("dlsc_set_obstacles: null member");
     if (!(op->slack_collision_weight > 0)) return fail("dlsc_set_obstacles: slack_collision_weight must be positive");
-    if (c->P.qp_solver == 1) return fail("dlsc_set_obstacles: the interior-point-only solver (qp_solver = 1) has no slack variables");
     if (n >= c->P.K) return fail("dlsc_set_obstacles: max_nbr must exceed the number of dynamic obstacles");
     if (!c->S.qp_slack && dev_alloc(c, &c->S.qp_slack, (size_t)c->P.NL * kMaxDyn * c->P.M)) return -1;
     std::vector<double> size((size_t)n * c->P.M * kP);

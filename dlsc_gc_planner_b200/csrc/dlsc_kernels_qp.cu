@@ -135,36 +135,9 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
     }
 }
 
-// Second chance for the agents the 32-row active set gave up on while dynamic obstacles are present: their slack groups
-// keep one or more rows active per (obstacle, segment), 40 and more at once, and the interior point has no slack
-// variables.  Same algorithm with capacity kGiQBig (~150 KB of shared memory, one CTA per SM; only a handful of agents
-// get here).  Finished agents are struck from S.qp_list.
-__global__ void __launch_bounds__(kGiThreads, 1) k_qp_gi_big(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
-                                                             const __grid_constant__ QpTab T) {
-    extern __shared__ __align__(16) double smem[];
-    const int n_list = S.qp_next[1];
-    QpSmem sm;
-    gi_smem_carve<kGiQBig>(T, smem, sm);
-    Cta c; c.tid = threadIdx.x; c.nthr = blockDim.x; c.red = sm.red;
-    for (int i = blockIdx.x; i < n_list; i += gridDim.x) {
-        const int la = S.qp_list[i];
-        QpIn in; QpOut out;
-        qp_load_agent(P, S, T, la, in, out);
-        long long rows = 0;
-        if (threadIdx.x == 0) out.rows = &rows;
-        const bool done = qp_agent_gi<kGiQBig, true>(c, P, T, in, out, sm, S.qp_seed + (size_t)la * 4);
-        if (threadIdx.x == 0 && done) {
-            S.qp_list[i] = -1;
-            const int it = S.qp_iters[la];
-            if (it) atomicAdd(S.counters + 3, (unsigned long long)it);
-            atomicAdd(S.counters + 4, (unsigned long long)rows);
-        }
-        __syncthreads();
-    }
-}
-
 // Fallback kernel (interior point, dlsc_qp.cuh): persistent CTAs pull agents from S.qp_list (or, with
 // all_agents, every agent: qp_solver = 1).
+template <bool DYN>
 __global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ DevState S,
                                                    const __grid_constant__ QpTab T, size_t scratch_doubles, int all_agents) {
@@ -184,12 +157,11 @@ __global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ De
         __syncthreads();
         if (i >= n_list) break;
         const int la = all_agents ? i : S.qp_list[i];
-        if (la < 0) continue;                      // finished by k_qp_gi_big
         QpIn in; QpOut out;
         qp_load_agent(P, S, T, la, in, out);
         long long rows = 0;
         if (threadIdx.x == 0) out.rows = &rows;
-        qp_agent(c, P, T, in, out, sm, scratch, !all_agents);
+        qp_agent<DYN>(c, P, T, in, out, sm, scratch, !all_agents);
         if (threadIdx.x == 0) { it_sum += (unsigned long long)S.qp_iters[la]; row_sum += (unsigned long long)rows; }
     }
     if (threadIdx.x == 0) {
@@ -202,19 +174,16 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     QpLaunch L;
     L.threads = kQpThreads;
     L.smem = qp_smem_bytes(T, P.K);
-    cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaFuncSetAttribute(k_qp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaFuncSetAttribute(k_qp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     L.gi_smem = gi_smem_doubles(T, P.K) * sizeof(double);
     cudaFuncSetAttribute(k_qp_gi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
     cudaFuncSetAttribute(k_qp_gi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_smem);
-    L.gi_big_smem = gi_smem_doubles<kGiQBig>(T, P.K) * sizeof(double);
-    cudaFuncSetAttribute(k_qp_gi_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.gi_big_smem);
-    L.sms = 148;
-    cudaDeviceGetAttribute(&L.sms, cudaDevAttrMultiProcessorCount, device);
     L.fast_smem = ((fast_smem_doubles(T, P.K) + 1) / 2 * 2) * sizeof(double) * kFastWarps;
     cudaFuncSetAttribute(k_qp_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     cudaFuncSetAttribute(k_qp_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     int per_sm = 1, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp, kQpThreads, L.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp<true>, kQpThreads, L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (per_sm < 1) per_sm = 1;
     L.ctas = sms * per_sm;
@@ -246,8 +215,8 @@ int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLau
             n = 3;
         }
     }
-    if (!all && P.n_dyn > 0) { k_qp_gi_big<<<L.sms, kGiThreads, L.gi_big_smem, st>>>(P, S, T); n++; }
-    k_qp<<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
+    if (P.n_dyn > 0) k_qp<true><<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
+    else k_qp<false><<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
     return n;
 }
 

@@ -155,8 +155,6 @@ struct QpSmem {
 // dual active-set (Goldfarb-Idnani, Schur-complement form) working storage; aliases the W region
 constexpr int kGiQ = 32;                               // max simultaneously active rows
 constexpr int kGiTri = kGiQ * (kGiQ + 1) / 2;
-constexpr int kGiQBig = 128;                           // capacity of the second-chance kernel (dynamic obstacles: one active
-                                                       // row per (obstacle, segment) slack group is common, 4 x 10 and more)
 struct GiSmem {
     double *Hinv;                                      // [nyd][nyd] of this agent's terminal-segment count
     double *Ls, *Sm;                                   // packed lower: Cholesky of S = A H^-1 A', and S itself
@@ -211,9 +209,20 @@ DLSC_HD void qp_smem_carve(const QpTab& T, int Kcap, double* base, QpSmem& s) {
 }
 // per-CTA global scratch (doubles): LSC row list [npt*Kcap] x {n0,n1,n2,b,s,z,c,ds,dz} + point index (int);
 // pair rows [np] x 13
+// + dynamic obstacles: slack group of every LSC row (int) and the per-slack block (kDynDoubles per slack variable)
+constexpr int kDynSlots = 18;                          // y unknowns a slack group touches: 3 axes x (3 of segment m-1, 3 of segment m)
+constexpr int kDynDoubles = 11 + kDynSlots + 3;        // e, de, sb, zb, dsb, dzb, ccb, wee, rhe, rde, pb | u[18] | row index per point (6 ints)
 DLSC_HD size_t qp_scratch_doubles(const QpTab& T, int Kcap) {
     const size_t LS = (size_t)T.npt * Kcap;
-    return 9 * LS + (LS + 1) / 2 + 13 * (size_t)T.np;
+    return 9 * LS + (LS + 1) / 2 + 13 * (size_t)T.np + (LS + 1) / 2 + (size_t)kDynDoubles * kMaxDyn * T.M;
+}
+// y index of local slot (axis k, slot) of a slack group of segment m, or -1: slots 0..2 = free points of segment m-1
+// (control points 0..2 of segment m depend on them through the continuity rows), slots 3..5 = free points of segment m
+// (one unknown for the last segment)
+DLSC_HD int dyn_slot_y(const QpTab& T, int m, int k, int slot) {
+    if (slot < 3) return m >= 1 ? k * T.nyd + 3 * (m - 1) + slot : -1;
+    if (m == T.M - 1) return slot == 3 ? k * T.nyd + 3 * (T.M - 1) : -1;
+    return k * T.nyd + 3 * m + slot - 3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -738,6 +747,11 @@ DLSC_HD int qp_dual_active_set(const Cta& c, const DevParams& P, const QpTab& T,
 
 // one agent
 // skip_gi: the dual active set already ran on this agent (dlsc_qp_gi.cuh) and gave up
+// DYN: dynamic obstacles present (slots < P.n_dyn): their LSC rows carry the slack variable of their (obstacle, segment)
+// group, eps <= 0 with cost w (M-m)/M eps^2.  The slack block is eliminated from every Newton system: with
+// u_g = sum_{r in g} D_r a_r and W_ee[g] = h_g + sum D_r + D_bound the reduced matrix is W - sum_g u_g u_g' / W_ee[g]
+// (u_g lives on <= 18 unknowns), the slack step follows from dy.  The DYN = false instantiation contains none of it.
+template <bool DYN = false>
 DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const QpIn& in, const QpOut& out,
                       const QpSmem& sm, double* scratch, bool skip_gi = false) {
     const int M = P.M, D = P.D, ny = T.ny, nyd = T.nyd, npt = T.npt, nx = T.nx, np = T.np, Kc = P.K;
@@ -756,19 +770,81 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     double* __restrict__ pd_zh = pr + 9 * np; double* __restrict__ pd_sl = pr + 10 * np; double* __restrict__ pd_zl = pr + 11 * np;
     double* __restrict__ p_act = pr + 12 * np;
     const int npl = T.row_npl;
-    if (P.n_dyn > 0) {
-        // The interior point has no slack variables: an agent the active set cannot finish while dynamic obstacles are
-        // present is reported as a numerical failure and keeps its initial trajectory (failsafe traj_planner.cpp:775-776).
-        if (c.tid == 0) { *out.cost = 0.0; *out.viol = 0.0; *out.iters = 0; *out.status |= kStQpNumeric; if (out.rows) *out.rows = 0; }
-        for (int e = c.tid; e < npt; e += c.nthr) {
-            float* o = out.traj + e * 3;
-            o[0] = in.init_traj[e * 3]; o[1] = in.init_traj[e * 3 + 1]; o[2] = in.init_traj[e * 3 + 2];
+    // dynamic-obstacle block (DYN only)
+    const int nd = DYN ? P.n_dyn : 0, NS = nd * M;
+    int* __restrict__ l_g = reinterpret_cast<int*>(pr + 13 * np);                 // slack group of a working-set row, or -1
+    double* dq = pr + 13 * np + (LS + 1) / 2;
+    const int NSm = kMaxDyn * M;
+    double* __restrict__ q_e = dq; double* __restrict__ q_de = dq + NSm; double* __restrict__ q_sb = dq + 2 * NSm;
+    double* __restrict__ q_zb = dq + 3 * NSm; double* __restrict__ q_dsb = dq + 4 * NSm; double* __restrict__ q_dzb = dq + 5 * NSm;
+    double* __restrict__ q_ccb = dq + 6 * NSm; double* __restrict__ q_wee = dq + 7 * NSm; double* __restrict__ q_rhe = dq + 8 * NSm;
+    double* __restrict__ q_rde = dq + 9 * NSm; double* __restrict__ q_pb = dq + 10 * NSm; double* __restrict__ q_u = dq + 11 * NSm;
+    int* __restrict__ q_row = reinterpret_cast<int*>(dq + (11 + kDynSlots) * NSm);   // [NS][6] working-set row of the group at point i, or -1
+    auto slack_h = [&](int g) { return 2.0 * P.slack_w * ((double)(M - g % M) / M); };
+    // group quantities from the rows' current (D, c, z): W_ee, u, dual residual, right-hand side; cb = the bound row's c
+    auto dyn_groups = [&](bool first) {
+        for (int g = c.tid; g < NS; g += c.nthr) {
+            const double Db = q_zb[g] / q_sb[g];
+            double wee = slack_h(g) + Db, zsum = q_zb[g], ce = q_ccb[g];
+            double u[kDynSlots];
+#pragma unroll
+            for (int t = 0; t < kDynSlots; t++) u[t] = 0.0;
+            for (int i = 0; i < kP; i++) {
+                const int r = q_row[g * kP + i];
+                if (r < 0) continue;
+                const double dd = l_dz[r];
+                zsum += l_z[r]; ce += l_ds[r];
+                if (!first) continue;
+                wee += dd;
+                const double w3[3] = {-l_n0[r] * dd, -l_n1[r] * dd, -l_n2[r] * dd};
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    double* uk = u + k * 6;
+                    const double w = w3[k];
+                    if (i == 0) uk[2] += w;
+                    else if (i == 1) { uk[2] += 2.0 * w; uk[1] -= w; }
+                    else if (i == 2) { uk[2] += 4.0 * w; uk[1] -= 4.0 * w; uk[0] += w; }
+                    else if (g % M == M - 1) uk[3] += w;
+                    else uk[i] += w;
+                }
+            }
+            if (first) {
+                q_wee[g] = wee;
+                for (int t = 0; t < kDynSlots; t++) q_u[g * kDynSlots + t] = u[t];
+                q_rde[g] = slack_h(g) * q_e[g] + zsum;
+            }
+            q_rhe[g] = -q_rde[g] - ce;
         }
-        if (out.slack) for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) out.slack[e] = 0.0;
-        c.sync();
-        return;
-    }
-
+    };
+    // right-hand side of the reduced system: dy[p] -= sum_g u_g[p] rhe[g] / wee[g] (every unknown belongs to <= 2 segments)
+    auto dyn_reduce_rhs = [&]() {
+        for (int p = c.tid; p < ny; p += c.nthr) {
+            const int k = p / nyd, a = p - k * nyd;
+            double acc = 0.0;
+            for (int which = 0; which < 2; which++) {
+                const int m = which ? a / 3 + 1 : a / 3, slot = which ? a % 3 : 3 + a % 3;
+                if (m > M - 1 || (which == 0 && m == M - 1 && slot != 3)) continue;
+                for (int o = 0; o < nd; o++) {
+                    const int g = o * M + m;
+                    acc += q_u[g * kDynSlots + k * 6 + slot] * (q_rhe[g] / q_wee[g]);
+                }
+            }
+            sm.dy[p] -= acc;
+        }
+    };
+    // slack step from dy
+    auto dyn_back = [&]() {
+        for (int g = c.tid; g < NS; g += c.nthr) {
+            const int m = g % M;
+            double acc = q_rhe[g];
+            for (int k = 0; k < D; k++)
+                for (int slot = 0; slot < 6; slot++) {
+                    const int yi = dyn_slot_y(T, m, k, slot);
+                    if (yi >= 0) acc -= q_u[g * kDynSlots + k * 6 + slot] * sm.dy[yi];
+                }
+            q_de[g] = acc / q_wee[g];
+        }
+    };
     // ---- constants of this agent ----
     QpConst qc;
     qc.hi_v = in.max_vel; qc.hi_a = in.max_acc; qc.hi_c = 0.5 * P.comm_range - in.radius;
@@ -876,9 +952,9 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
                 for (int cc = 0; cc < K; cc++) {
                     if (!sm.act[m * Kc + cc]) continue;
-                    const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
+                    const LscRowData r = lsc_row_data(P, in, pt, cc, nd);
                     const double s0 = r.b + (r.n0 * x0 + r.n1 * x1 + r.n2 * x2);
-                    if (all_rows || s0 < tau) cnt++;
+                    if (all_rows || s0 < tau || cc < nd) cnt++;                     // dynamic-obstacle rows: always in the working set
                 }
             }
             sm.off[pt + 1] = cnt;
@@ -890,6 +966,11 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
         }
         c.sync();
         const int nl = sm.off[npt];
+        if (DYN) {                                  // slack variables start at 0, their bound rows like every other row
+            for (int g = c.tid; g < NS; g += c.nthr) { q_e[g] = 0.0; q_sb[g] = 1e-2; q_zb[g] = 1.0; }
+            for (int e = c.tid; e < NS * kP; e += c.nthr) q_row[e] = -1;
+            c.sync();
+        }
         for (int pt = c.tid; pt < npt; pt += c.nthr) {
             if (pt < 3 || sm.off[pt + 1] == sm.off[pt]) continue;
             const int m = pt / kP;
@@ -897,13 +978,18 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
             for (int cc = 0; cc < K; cc++) {
                 if (!sm.act[m * Kc + cc]) continue;
-                const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
+                const LscRowData r = lsc_row_data(P, in, pt, cc, nd);
                 const double act = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2);
                 double s0 = r.b - act;
-                if (!(all_rows || s0 < tau)) continue;
+                if (!(all_rows || s0 < tau || cc < nd)) continue;
                 if (s0 < 1e-2) s0 = 1e-2;
                 l_n0[o] = r.n0; l_n1[o] = r.n1; l_n2[o] = r.n2; l_b[o] = r.b; l_s[o] = s0; l_z[o] = 1.0 / s0 * 1e-2;
                 l_pt[o] = pt;
+                if (DYN) {
+                    const int g = cc < nd ? cc * M + m : -1;
+                    l_g[o] = g;
+                    if (g >= 0) q_row[g * kP + (pt - m * kP)] = o;
+                }
                 o++;
             }
         }
@@ -917,7 +1003,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             s = act - pb_lo[r]; if (s < 1e-2) s = 1e-2;
             ps_lo[r] = s; pz_lo[r] = 1.0 / s * 1e-2;
         }
-        const double n_rows = 2.0 * np + nl;
+        const double n_rows = 2.0 * np + nl + NS;
         rows_total += (long long)n_rows;
         const double inv_rows = 1.0 / n_rows;
         c.sync();
@@ -945,7 +1031,8 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             for (int r = c.tid; r < nl; r += c.nthr) {
                 const int pt = l_pt[r];
                 const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
-                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
+                const double eg = (DYN && l_g[r] >= 0) ? q_e[l_g[r]] : 0.0;
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0)) + eg;
                 const double rp = act + s - l_b[r];
                 rp_inf = fmax(rp_inf, fabs(rp));
                 mu += s * z;
@@ -953,7 +1040,15 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 l_ds[r] = dd * (rp - s);      // c_aff (temporary)
                 l_dz[r] = dd;                 // D      (temporary)
             }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) {          // bound rows eps <= 0
+                    const double rpb = q_e[g] + q_sb[g];
+                    rp_inf = fmax(rp_inf, fabs(rpb));
+                    mu += q_sb[g] * q_zb[g];
+                    q_ccb[g] = q_zb[g] / q_sb[g] * (rpb - q_sb[g]);
+                }
             c.sync();
+            if (DYN) dyn_groups(true);
             for (int pt = c.tid; pt < npt; pt += c.nthr) {
                 double u10 = 0, u11 = 0, u12 = 0, u20 = 0, u21 = 0, u22 = 0, S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0;
                 for (int r = sm.off[pt]; r < sm.off[pt + 1]; r++) {
@@ -984,6 +1079,8 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 sm.dy[p] = -r1 - r2;
                 rd_inf = fmax(rd_inf, fabs(r1));
             }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) rd_inf = fmax(rd_inf, fabs(q_rde[g]));
             c.reduce3(rp_inf, 1, mu, 0, rd_inf, 1);
             mu *= inv_rows;
 #if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
@@ -1011,11 +1108,35 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 sm.W[e] = v;
             }
             c.sync();
+            if (DYN) {
+                // W -= sum_g u_g u_g' / W_ee[g]: one segment at a time (the groups of a segment share their unknowns;
+                // obstacles in a fixed order inside the thread, so the sums are deterministic)
+                for (int m = 0; m < M; m++) {
+                    for (int pq = c.tid; pq < kDynSlots * (kDynSlots + 1) / 2; pq += c.nthr) {
+                        int a = 0;
+                        while ((a + 1) * (a + 2) / 2 <= pq) a++;
+                        const int b = pq - a * (a + 1) / 2;
+                        const int ya = dyn_slot_y(T, m, a / 6, a % 6), yb = dyn_slot_y(T, m, b / 6, b % 6);
+                        if (ya < 0 || yb < 0 || a / 6 >= D || b / 6 >= D) continue;
+                        double acc = 0.0;
+                        for (int o = 0; o < nd; o++) {
+                            const int g = o * M + m;
+                            acc += q_u[g * kDynSlots + a] * q_u[g * kDynSlots + b] / q_wee[g];
+                        }
+                        const int hi = ya > yb ? ya : yb, lo = ya > yb ? yb : ya;
+                        sm.W[hi * (hi + 1) / 2 + lo] -= acc;
+                    }
+                    c.sync();
+                }
+                dyn_reduce_rhs();
+                c.sync();
+            }
             if (!ldl_factor(c, sm.W, sm.invp, sm.pan, ny, T.tri_p)) { status = acceptable ? 0 : kStQpNumeric; break; }
 
             // ============ predictor ============
             ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
             c.sync();
+            if (DYN) dyn_back();
             map_x(c, T, sm.dy, nullptr, sm.dx);
             c.sync();
             double a_aff = 1.0;
@@ -1035,14 +1156,23 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             for (int r = c.tid; r < nl; r += c.nthr) {
                 const int pt = l_pt[r];
                 const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
-                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
-                const double gd = -(n0 * sm.dx[pt] + n1 * sm.dx[npt + pt] + (D3 ? n2 * sm.dx[2 * npt + pt] : 0.0));
+                const int gr = DYN ? l_g[r] : -1;
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0)) + (gr >= 0 ? q_e[gr] : 0.0);
+                const double gd = -(n0 * sm.dx[pt] + n1 * sm.dx[npt + pt] + (D3 ? n2 * sm.dx[2 * npt + pt] : 0.0)) + (gr >= 0 ? q_de[gr] : 0.0);
                 const double ds = -(act + s - l_b[r]) - gd;
                 const double dz = -z - l_dz[r] * ds;          // l_dz still holds D = z/s
                 if (ds < 0) a_aff = fmin(a_aff, -s / ds);
                 if (dz < 0) a_aff = fmin(a_aff, -z / dz);
                 l_ds[r] = ds; l_c[r] = dz;                    // affine directions (l_c as temporary)
             }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) {
+                    const double sb = q_sb[g], zb = q_zb[g];
+                    const double ds = -(q_e[g] + sb) - q_de[g], dz = -zb - zb / sb * ds;
+                    if (ds < 0) a_aff = fmin(a_aff, -sb / ds);
+                    if (dz < 0) a_aff = fmin(a_aff, -zb / dz);
+                    q_dsb[g] = ds; q_dzb[g] = dz;
+                }
             { double d0 = 0.0, d1 = 0.0; c.reduce3(a_aff, 2, d0, 0, d1, 0); }
             double mu_aff = 0.0;
             for (int r = c.tid; r < np; r += c.nthr) {
@@ -1055,6 +1185,11 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 mu_aff += (l_s[r] + a_aff * ds) * (l_z[r] + a_aff * dz);
                 l_c[r] = ds * dz;
             }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) {
+                    mu_aff += (q_sb[g] + a_aff * q_dsb[g]) * (q_zb[g] + a_aff * q_dzb[g]);
+                    q_pb[g] = q_dsb[g] * q_dzb[g];
+                }
             { double d0 = 0.0, d1 = 0.0; c.reduce3(mu_aff, 0, d0, 0, d1, 0); }
             mu_aff *= inv_rows;
             const double ratio = mu > 0 ? mu_aff / mu : 0.0;
@@ -1071,12 +1206,19 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             for (int r = c.tid; r < nl; r += c.nthr) {
                 const int pt = l_pt[r];
                 const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
-                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
+                const double eg = (DYN && l_g[r] >= 0) ? q_e[l_g[r]] : 0.0;
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0)) + eg;
                 const double rp = act + s - l_b[r];
                 const double rc = s * z + l_c[r] - sig_mu;
                 l_ds[r] = (-rc + z * rp) / s;                 // c_corr (temporary); l_c keeps rc's corrector part
             }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) {
+                    const double sb = q_sb[g], zb = q_zb[g];
+                    q_ccb[g] = (-(sb * zb + q_pb[g] - sig_mu) + zb * (q_e[g] + sb)) / sb;
+                }
             c.sync();
+            if (DYN) dyn_groups(false);
             for (int pt = c.tid; pt < npt; pt += c.nthr) {
                 double u20 = 0, u21 = 0, u22 = 0;
                 for (int r = sm.off[pt]; r < sm.off[pt + 1]; r++) {
@@ -1090,8 +1232,10 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             c.sync();
             for (int p = c.tid; p < ny; p += c.nthr) sm.dy[p] = -sm.rd[p] - gather_y(T, p, sm.ax2);
             c.sync();
+            if (DYN) { dyn_reduce_rhs(); c.sync(); }
             ldl_solve(c, sm.W, sm.invp, sm.dy, ny);
             c.sync();
+            if (DYN) dyn_back();
             map_x(c, T, sm.dy, nullptr, sm.dx);
             c.sync();
             double a_st = 1.0;
@@ -1112,8 +1256,9 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             for (int r = c.tid; r < nl; r += c.nthr) {
                 const int pt = l_pt[r];
                 const double n0 = l_n0[r], n1 = l_n1[r], n2 = l_n2[r], s = l_s[r], z = l_z[r];
-                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0));
-                const double gd = -(n0 * sm.dx[pt] + n1 * sm.dx[npt + pt] + (D3 ? n2 * sm.dx[2 * npt + pt] : 0.0));
+                const int gr = DYN ? l_g[r] : -1;
+                const double act = -(n0 * sm.x[pt] + n1 * sm.x[npt + pt] + (D3 ? n2 * sm.x[2 * npt + pt] : 0.0)) + (gr >= 0 ? q_e[gr] : 0.0);
+                const double gd = -(n0 * sm.dx[pt] + n1 * sm.dx[npt + pt] + (D3 ? n2 * sm.dx[2 * npt + pt] : 0.0)) + (gr >= 0 ? q_de[gr] : 0.0);
                 const double rc = s * z + l_c[r] - sig_mu;
                 const double ds = -(act + s - l_b[r]) - gd;
                 const double dz = (-rc - z * ds) / s;
@@ -1121,6 +1266,15 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 if (dz < 0) a_st = fmin(a_st, -z / dz);
                 l_ds[r] = ds; l_dz[r] = dz;
             }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) {
+                    const double sb = q_sb[g], zb = q_zb[g];
+                    const double rc = sb * zb + q_pb[g] - sig_mu;
+                    const double ds = -(q_e[g] + sb) - q_de[g], dz = (-rc - zb * ds) / sb;
+                    if (ds < 0) a_st = fmin(a_st, -sb / ds);
+                    if (dz < 0) a_st = fmin(a_st, -zb / dz);
+                    q_dsb[g] = ds; q_dzb[g] = dz;
+                }
             { double d0 = 0.0, d1 = 0.0; c.reduce3(a_st, 2, d0, 0, d1, 0); }
             a_st = fmin(1.0, 0.995 * a_st);
 #if defined(DLSC_QP_TRACE) && !defined(__CUDA_ARCH__)
@@ -1132,6 +1286,8 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 ps_lo[r] += a_st * pd_sl[r]; pz_lo[r] += a_st * pd_zl[r];
             }
             for (int r = c.tid; r < nl; r += c.nthr) { l_s[r] += a_st * l_ds[r]; l_z[r] += a_st * l_dz[r]; }
+            if (DYN)
+                for (int g = c.tid; g < NS; g += c.nthr) { q_e[g] += a_st * q_de[g]; q_sb[g] += a_st * q_dsb[g]; q_zb[g] += a_st * q_dzb[g]; }
             for (int p = c.tid; p < ny; p += c.nthr) sm.y[p] += a_st * sm.dy[p];
             c.sync();
             map_x(c, T, sm.y, sm.cst, sm.x);
@@ -1148,8 +1304,8 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             const double x0 = sm.x[pt], x1 = sm.x[npt + pt], x2 = D3 ? sm.x[2 * npt + pt] : 0.0;
             for (int cc = 0; cc < K; cc++) {
                 if (!sm.act[m * Kc + cc]) continue;
-                const LscRowData r = lsc_row_data(P, in, pt, cc, 0);
-                const double v = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2) - r.b;
+                const LscRowData r = lsc_row_data(P, in, pt, cc, nd);
+                const double v = -(r.n0 * x0 + r.n1 * x1 + r.n2 * x2) - r.b + (cc < nd ? q_e[cc * M + m] : 0.0);
                 viol_lsc = fmax(viol_lsc, v);
             }
         }
@@ -1180,6 +1336,13 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             const double act = pair_eval(T, pair_decode(T, idx), sm.x + k * npt);
             viol = fmax(viol, fmax(act - pb_hi[r], pb_lo[r] - act));
         }
+    if (DYN) {
+        for (int g = c.tid; g < NS; g += c.nthr) {
+            obj += P.slack_w * ((double)(M - g % M) / M) * q_e[g] * q_e[g];
+            viol = fmax(viol, q_e[g]);                                    // eps <= 0
+            if (out.slack) out.slack[g] = (status == 0) ? q_e[g] : 0.0;
+        }
+    }
     { double d1 = 0.0; c.reduce3(obj, 0, viol, 1, d1, 0); }
     if (c.tid == 0) {
         *out.cost = obj; *out.viol = viol; *out.iters = it_total; *out.status |= status | ((P.qp_solver != 1 && !solved_by_gi) ? kStQpIpmUsed : 0);

@@ -414,6 +414,7 @@ public:
     double stage_s[DLSC_N_STAGES] = {0, 0, 0, 0, 0, 0};
     std::vector<float> traj, goal;
     std::vector<double> cost;
+    std::vector<double> slack;                     // [N][n_dynamic][M] slack variables of the last step
     std::vector<int32_t> status;
     std::vector<uint8_t> staged, planned;
 
@@ -422,7 +423,8 @@ private:
         N = (int)m.qn; M = p.M; n = p.n; dt = p.dt; res = p.world_resolution;
         slack_w = p.slack_collision_weight; obs_horizon = p.obs_uncertainty_horizon; obs_size_pred = p.obs_size_prediction;
         if (N < 1 || (size_t)N != m.agents.size()) throw std::invalid_argument("[TrajPlanner] mission has no agents");
-        const int K = p.max_neighbours > 0 ? p.max_neighbours : std::max(N - 1, 1);
+        // capacity of the per-agent obstacle list: the agents in range plus room for the mission's dynamic obstacles
+        const int K = (p.max_neighbours > 0 ? p.max_neighbours : std::max(N - 1, 1)) + DLSC_MAX_OBSTACLES;
         dlsc_params q = make_params(p, m, K);
         check(dlsc_create(&q, N, 0, N, 0, &ctx), "dlsc_create");
         std::vector<double> r(N), dw(N), mv(N), ma(N), nv(N);
@@ -450,6 +452,10 @@ private:
         check(dlsc_get_cost(ctx, cost.data()), "dlsc_get_cost");
         check(dlsc_get_status(ctx, status.data()), "dlsc_get_status");
         check(dlsc_get_goal(ctx, goal.data()), "dlsc_get_goal");
+        if (n_dynamic() > 0) {
+            slack.assign((size_t)N * n_dynamic() * M, 0.0);
+            check(dlsc_get_slack(ctx, slack.data()), "dlsc_get_slack");
+        }
         double ms[DLSC_N_STAGES];
         int n_steps = 0;
         check(dlsc_get_timings(ctx, ms, &n_steps), "dlsc_get_timings");
@@ -649,6 +655,24 @@ public:
         const size_t L = (size_t)batch->M * (batch->n + 1) * 3;
         res.desired_traj = detail::to_traj(batch->traj.data() + L * agent.id, batch->M, batch->n, batch->dt);
         res.total_qp_cost = batch->cost[agent.id];
+        // collision alert (traj_optimizer.cpp:84-105): dynamic obstacles whose slack variables sum above plan/slack_threshold
+        if (!(st & (DLSC_QP_MAXITER | DLSC_QP_NUMERIC)) && batch->n_dynamic() > 0) {
+            const int nd = batch->n_dynamic();
+            int o = 0;
+            for (size_t oi = 0; oi < obstacles.size() && o < nd; oi++) {
+                if (obstacles[oi].type == ObstacleType::AGENT) continue;
+                double slack_cost = 0;
+                for (int m = 0; m < batch->M; m++) slack_cost += std::abs(batch->slack[((size_t)agent.id * nd + o) * batch->M + m]);
+                if (slack_cost > param.slack_threshold) {
+                    res.collision_alert.agent_position = agent.current_state.position;
+                    Obstacle alert;
+                    alert.id = (int)oi;
+                    alert.position = obstacles[oi].position;
+                    res.collision_alert.obstacles.emplace_back(alert);
+                }
+                o++;
+            }
+        }
         for (unsigned k = 0; k < 3; k++) agent.current_goal_point(k) = batch->goal[3 * agent.id + k];
         return res;
     }

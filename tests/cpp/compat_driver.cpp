@@ -106,8 +106,10 @@ int main(int argc, char** argv) {
         // that flies through its start position (not near its waypoint: with comm range <= 0 checkWaypointTrap drops those)
         Mission third = mission;
         third.agents[0].desired_goal_point = point3d(0.5f, 0.6f, 1.f);
+        param.slack_threshold = 0.001;                      // src/param.cpp:104 default
         TrajPlanner p3(nh, param, third, third.agents[0]);
         double cost[2], endy[2];
+        int alerts[2] = {0, 0}, alert_id[2] = {-1, -1};
         TrajPlanner* pp[2] = {&p2, &p3};
         Mission* mm[2] = {&other, &third};
         for (int w = 0; w < 2; w++) {
@@ -129,8 +131,11 @@ int main(int argc, char** argv) {
             pp[w]->setObstacles(obs);
             TrajOptResult r = pp[w]->plan(a0, octree, distmap, ros::Time(), false);
             cost[w] = r.total_qp_cost; endy[w] = r.desired_traj.lastPoint().y();
+            alerts[w] = (int)r.collision_alert.obstacles.size();
+            alert_id[w] = alerts[w] ? r.collision_alert.obstacles[0].id : -1;
         }
-        printf("dynamic obstacle planned cost %.6f vs %.6f end_y %.4f vs %.4f\n", cost[0], cost[1], endy[0], endy[1]);
+        printf("dynamic obstacle planned cost %.6f vs %.6f end_y %.4f vs %.4f alerts %d (id %d) vs %d\n", cost[0], cost[1], endy[0], endy[1],
+               alerts[0], alert_id[0], alerts[1]);
     }
     // TrajOptimizer::solve with explicit constraints (one LSC plane, no SFC)
     {

@@ -248,7 +248,7 @@ int dlsc_set_obstacles(dlsc_ctx* c, const dlsc_obstacles* o, const dlsc_obstacle
     const int n = o ? o->n : 0;
     if (n < 0 || n > kMaxDyn) return fail("too many obstacles");
     if (n == 0) { c->P.n_dyn = 0; return 0; }
-    if (!(op->slack_collision_weight > 0) || c->P.qp_solver == 1 || n >= c->P.K) return fail("bad obstacle setup");
+    if (!(op->slack_collision_weight > 0) || n >= c->P.K) return fail("bad obstacle setup");
     c->dyn_pos.assign(o->pos, o->pos + 3 * n); c->dyn_vel.assign(o->vel, o->vel + 3 * n);
     c->dyn_radius.assign(o->radius, o->radius + n); c->dyn_downwash.assign(o->downwash, o->downwash + n);
     c->dyn_max_acc.assign(o->max_acc, o->max_acc + n);
@@ -464,15 +464,11 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
                 double seed[4] = {0, 0, 0, 0};
                 done = nd > 0 ? qp_agent_fast<true>(cf, P, c->T, in, out, sf, seed) : qp_agent_fast<false>(cf, P, c->T, in, out, sf, seed);
                 if (!done) done = nd > 0 ? qp_agent_gi<kGiQ, true>(cg, P, c->T, in, out, sg, seed) : qp_agent_gi<kGiQ, false>(cg, P, c->T, in, out, sg, seed);
-                if (!done && nd > 0) {                               // k_qp_gi_big
-                    std::vector<double> big_mem(gi_smem_doubles<kGiQBig>(c->T, P.K) + 8);
-                    QpSmem sb;
-                    gi_smem_carve<kGiQBig>(c->T, big_mem.data(), sb);
-                    Cta cb; cb.tid = 0; cb.nthr = 1; cb.red = sb.red;
-                    done = qp_agent_gi<kGiQBig, true>(cb, P, c->T, in, out, sb, seed);
-                }
             }
-            if (!done) qp_agent(cta, P, c->T, in, out, sm, c->scratch.data(), P.qp_solver != 1);
+            if (!done) {
+                if (nd > 0) qp_agent<true>(cta, P, c->T, in, out, sm, c->scratch.data(), P.qp_solver != 1);
+                else qp_agent<false>(cta, P, c->T, in, out, sm, c->scratch.data(), P.qp_solver != 1);
+            }
             c->counters[3] += c->qp_iters[la];
             c->counters[4] += rows;
         }

@@ -57,9 +57,10 @@ def test_compat_driver_serial_equals_batched():
     st = re.search(r"stats seq (\d+) total (\S+) qp (\S+) samples (\d+)", outs["serial"][25])
     assert int(st.group(1)) == 25 and int(st.group(4)) == 25 and 0 < float(st.group(3)) <= float(st.group(2)) < 1.0
     assert outs["serial"][26] == "contexts distinct 1 same 1"
-    dyn = re.search(r"dynamic obstacle planned cost (\S+) vs (\S+) end_y (\S+) vs (\S+)", outs["serial"][27])
+    dyn = re.search(r"dynamic obstacle planned cost (\S+) vs (\S+) end_y (\S+) vs (\S+) alerts (\d+) \(id (-?\d+)\) vs (\d+)", outs["serial"][27])
     assert float(dyn.group(1)) > float(dyn.group(2)) + 1e-3, outs["serial"][27]      # the obstacle costs something ...
     assert abs(float(dyn.group(3)) - float(dyn.group(4))) > 1e-3, outs["serial"][27]    # ... and bends the trajectory
+    assert int(dyn.group(7)) == 0 and int(dyn.group(5)) in (0, 1) and (int(dyn.group(5)) == 0 or int(dyn.group(6)) == 0)
     for line in outs["serial"][:25]:
         assert float(re.search(r"min_dist ([0-9.]+)", line).group(1)) >= 0.3 - 1e-4, line
     assert int(re.search(r"seq (\d+)", outs["serial"][24]).group(1)) == 25
