@@ -508,20 +508,23 @@ __global__ void __launch_bounds__(128) k_goal(const __grid_constant__ DevParams 
     }
 }
 
-// checkWaypointTrap (P.n_dyn > 0 only): thread per agent, after LSC and SFC, before the goal stage
+// checkWaypointTrap (P.n_dyn > 0 only): warp per agent, after LSC and SFC, before the goal stage
 __global__ void __launch_bounds__(128) k_trap(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    const int la = blockIdx.x * blockDim.x + threadIdx.x;
+    const int la = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (la >= P.NL) return;
+    Group g; g.lane = threadIdx.x & 31; g.width = 32; g.block = false;
     const int npt = P.M * kP;
     const float* rec = S.rec + (size_t)(P.begin + la) * P.rec;
     const size_t pr = (size_t)la * P.K;
     DynObs O; O.pos = S.dyn_pos; O.vel = S.dyn_vel; O.radius = S.dyn_radius; O.downwash = S.dyn_downwash; O.max_acc = S.dyn_max_acc; O.size = S.dyn_size;
-    S.trap[la] = (uint8_t)waypoint_trap(P, O, v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3),
-                                        S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.comm_box + (size_t)la * 6, S.nbr_cnt[la],
-                                        S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, S.radius[la]);
+    const int tr = waypoint_trap(g, P, O, v3_load(rec + npt * 3 + 6), v3_load(S.waypoint + la * 3),
+                                 S.sfc + ((size_t)la * P.M + (P.M - 1)) * 6, S.comm_box + (size_t)la * 6, S.nbr_cnt[la],
+                                 S.lsc_normal + pr * P.M * 3, S.lsc_d + pr * P.M * kP, S.lsc_anchor_last + pr * 3, S.radius[la]);
+    if (g.lane == 0) S.trap[la] = (uint8_t)tr;
 }
 void launch_trap(const DevParams& P, const DevState& S, cudaStream_t st) {
-    k_trap<<<(P.NL + 127) / 128, 128, 0, st>>>(P, S);
+    const long long n = (long long)P.NL * 32;
+    k_trap<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, S);
 }
 
 void launch_goal(const DevParams& P, const DevState& S, cudaStream_t st) {

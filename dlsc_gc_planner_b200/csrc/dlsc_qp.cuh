@@ -809,11 +809,13 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 }
             }
             if (first) {
-                q_wee[g] = wee;
-                for (int t = 0; t < kDynSlots; t++) q_u[g * kDynSlots + t] = u[t];
+                // stored scaled: u / sqrt(W_ee), rhs / sqrt(W_ee) -- the three places that use them need no division
+                const double isw = 1.0 / sqrt(wee);
+                q_wee[g] = isw;
+                for (int t = 0; t < kDynSlots; t++) q_u[g * kDynSlots + t] = u[t] * isw;
                 q_rde[g] = slack_h(g) * q_e[g] + zsum;
             }
-            q_rhe[g] = -q_rde[g] - ce;
+            q_rhe[g] = (-q_rde[g] - ce) * q_wee[g];
         }
     };
     // right-hand side of the reduced system: dy[p] -= sum_g u_g[p] rhe[g] / wee[g] (every unknown belongs to <= 2 segments)
@@ -826,7 +828,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                 if (m > M - 1 || (which == 0 && m == M - 1 && slot != 3)) continue;
                 for (int o = 0; o < nd; o++) {
                     const int g = o * M + m;
-                    acc += q_u[g * kDynSlots + k * 6 + slot] * (q_rhe[g] / q_wee[g]);
+                    acc += q_u[g * kDynSlots + k * 6 + slot] * q_rhe[g];
                 }
             }
             sm.dy[p] -= acc;
@@ -842,7 +844,7 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
                     const int yi = dyn_slot_y(T, m, k, slot);
                     if (yi >= 0) acc -= q_u[g * kDynSlots + k * 6 + slot] * sm.dy[yi];
                 }
-            q_de[g] = acc / q_wee[g];
+            q_de[g] = acc * q_wee[g];
         }
     };
     // ---- constants of this agent ----
@@ -1109,19 +1111,24 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
             }
             c.sync();
             if (DYN) {
-                // W -= sum_g u_g u_g' / W_ee[g]: one segment at a time (the groups of a segment share their unknowns;
-                // obstacles in a fixed order inside the thread, so the sums are deterministic)
-                for (int m = 0; m < M; m++) {
-                    for (int pq = c.tid; pq < kDynSlots * (kDynSlots + 1) / 2; pq += c.nthr) {
+                // W -= sum_g u_g u_g' / W_ee[g] (u stored scaled).  The groups of a segment share their 18 unknowns and
+                // adjacent segments share 9 of them, so: even segments, barrier, odd segments -- every W entry has one
+                // writer per pass; obstacles in a fixed order inside the thread, so the sums are deterministic.
+                constexpr int kPairs = kDynSlots * (kDynSlots + 1) / 2;
+                for (int par = 0; par < 2; par++) {
+                    const int nseg = (M - par + 1) / 2;
+                    for (int w = c.tid; w < nseg * kPairs; w += c.nthr) {
+                        const int m = 2 * (w / kPairs) + par, pq = w % kPairs;
                         int a = 0;
                         while ((a + 1) * (a + 2) / 2 <= pq) a++;
                         const int b = pq - a * (a + 1) / 2;
+                        if (a / 6 >= D) continue;
                         const int ya = dyn_slot_y(T, m, a / 6, a % 6), yb = dyn_slot_y(T, m, b / 6, b % 6);
-                        if (ya < 0 || yb < 0 || a / 6 >= D || b / 6 >= D) continue;
+                        if (ya < 0 || yb < 0) continue;
                         double acc = 0.0;
                         for (int o = 0; o < nd; o++) {
                             const int g = o * M + m;
-                            acc += q_u[g * kDynSlots + a] * q_u[g * kDynSlots + b] / q_wee[g];
+                            acc += q_u[g * kDynSlots + a] * q_u[g * kDynSlots + b];
                         }
                         const int hi = ya > yb ? ya : yb, lo = ya > yb ? yb : ya;
                         sm.W[hi * (hi + 1) / 2 + lo] -= acc;

@@ -71,6 +71,7 @@ DLSC_HD int f32_as_int(float f) {
 #endif
 }
 
+constexpr int kGiDynRows = 20;     // hand-over threshold of the active set when dynamic obstacles are present
 constexpr double kGiTol = 1e-10;   // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
 
 struct PairRowD { int fam, k, pa, pb; };
@@ -415,7 +416,10 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     const int kdrop = (int)g.ty[5];
                     u_p += g.ty[7];
                     if (g.ty[4] != 0.0) {
-                        if (q >= (Q > kGiQ ? Q : P.qp_active_max)) flag = 3.0;
+                        // with dynamic obstacles an agent beside an obstacle keeps a row active in most of its slack groups:
+                        // the serial q x q algebra of this kernel is the wrong tool beyond ~20 rows, the interior point
+                        // (which carries the slack variables) takes over
+                        if (q >= ((DYN && P.qp_active_max > kGiDynRows) ? kGiDynRows : P.qp_active_max)) flag = 3.0;
                         else {
                             for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
                             g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
@@ -556,7 +560,11 @@ DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const
     c.tick(7);
     if (DYN && P.n_dyn > 0) {                                                         // :317-331
         if (c.tid == 0 && sm.esl)
-            for (int e = 0; e < P.n_dyn * M; e++) obj += P.slack_w * ((double)(M - e % M) / M) * sm.esl[e] * sm.esl[e];
+            for (int o = 0; o < P.n_dyn; o++)
+                for (int m = 0; m < M; m++) {
+                    const double e = sm.esl[o * M + m];
+                    if (e != 0.0) obj += P.slack_w * ((double)(M - m) / M) * e * e;
+                }
         if (out.slack)
             for (int e = c.tid; e < P.n_dyn * M; e += c.nthr) out.slack[e] = (status == 0 && sm.esl) ? sm.esl[e] : 0.0;
     }

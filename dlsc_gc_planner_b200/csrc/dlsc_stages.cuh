@@ -1086,27 +1086,25 @@ DLSC_HD void comm_box_update(const DevParams& P, bool init, const V3& wp, float*
     v3_store(box + 3, wp + v3(h, h, h));
 }
 
-// checkWaypointTrap for one agent (one thread).  LSC arrays of this agent as in goal_agent; K counts the dynamic slots.
+// checkWaypointTrap for one agent; the lanes of the group share the agent LSCs of the feasibility test and the
+// obstacles of the clearing loop.  LSC arrays of this agent as in goal_agent; K counts the dynamic slots.
 // Returns 1 when the waypoint is trapped; the LSCs of the dynamic obstacles that can reach the waypoint are cleared.
-DLSC_HD int waypoint_trap(const DevParams& P, const DynObs& O, const V3& goal, const V3& wp, const float* sfc_last,
-                          const float* comm_box, int K, float* normal, double* d, const float* anchor_last,
-                          double agent_radius) {
+DLSC_HD int waypoint_trap(const Group& gr, const DevParams& P, const DynObs& O, const V3& goal, const V3& wp,
+                          const float* sfc_last, const float* comm_box, int K, float* normal, double* d,
+                          const float* anchor_last, double agent_radius) {
     const int M = P.M, nd = P.n_dyn;
     if (K == 0) return 0;                                                      // obstacles.empty() :709
-    bool ok = true;
-    for (int which = 0; which < 2 && ok; which++) {                            // isPointInFeasibleRegion(goal) and (waypoint)
-        const V3 q = which ? wp : goal;
-        for (int oi = nd; oi < K && ok; oi++) {
-            const V3 nv = v3_load(normal + ((size_t)oi * M + (M - 1)) * 3);
-            const V3 an = v3_load(anchor_last + oi * 3);
-            const double dd = d[((size_t)oi * M + (M - 1)) * kP + (kP - 1)];
-            if (!(v3_dot(q - an, nv) - dd > -kEps)) ok = false;                // LSC::isPointInLSC
-        }
-        if (ok && P.use_sfc && !point_in_box(box_load(sfc_last), q)) ok = false;
-        if (ok && !point_in_box(box_load(comm_box), q)) ok = false;
+    bool bad = false;                                                          // isPointInFeasibleRegion(goal) and (waypoint)
+    for (int oi = nd + gr.lane; oi < K; oi += gr.width) {
+        const V3 nv = v3_load(normal + ((size_t)oi * M + (M - 1)) * 3);
+        const V3 an = v3_load(anchor_last + oi * 3);
+        const double dd = d[((size_t)oi * M + (M - 1)) * kP + (kP - 1)];
+        if (!(v3_dot(goal - an, nv) - dd > -kEps) || !(v3_dot(wp - an, nv) - dd > -kEps)) bad = true;   // LSC::isPointInLSC
     }
-    if (ok) return 0;
-    for (int oi = 0; oi < nd; oi++) {
+    if (P.use_sfc && !(point_in_box(box_load(sfc_last), goal) && point_in_box(box_load(sfc_last), wp))) bad = true;
+    if (!(point_in_box(box_load(comm_box), goal) && point_in_box(box_load(comm_box), wp))) bad = true;
+    if (!gr.any(bad)) return 0;
+    for (int oi = gr.lane; oi < nd; oi += gr.width) {
         if (!obstacle_collides(v3_load(O.pos + 3 * oi), v3_load(O.vel + 3 * oi), O.radius[oi], O.max_acc[oi], wp,
                                agent_radius, M * P.dt, P.dyn_horizon)) continue;
         for (int m = 0; m < M; m++) {

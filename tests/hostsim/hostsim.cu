@@ -402,7 +402,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             const size_t pr = (size_t)la * K;
             DynObs O; O.pos = c->dyn_pos.data(); O.vel = c->dyn_vel.data(); O.radius = c->dyn_radius.data(); O.downwash = c->dyn_downwash.data();
             O.max_acc = c->dyn_max_acc.data(); O.size = c->dyn_size.data();
-            c->trap[la] = (uint8_t)waypoint_trap(P, O, v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3),
+            c->trap[la] = (uint8_t)waypoint_trap(g, P, O, v3_load(rec + npt * 3 + 6), v3_load(c->waypoint.data() + la * 3),
                                                  c->sfc.data() + ((size_t)la * M + (M - 1)) * 6, c->comm_box.data() + (size_t)la * 6, c->nbr_cnt[la],
                                                  c->lsc_normal.data() + pr * M * 3, c->lsc_d.data() + pr * M * kP, c->lsc_anchor_last.data() + pr * 3,
                                                  c->radius[la]);

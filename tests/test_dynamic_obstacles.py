@@ -144,7 +144,7 @@ def test_slack_qp_against_highs(hostsim):
         if s < 4:
             return
         pos, vel, acc = state
-        xk, ck, sk = pl.qp_x(), pl.cost(), pl.slack()
+        xk, ck, sk, stk = pl.qp_x(), pl.cost(), pl.slack(), pl.status()
         for a in range(m.n_agents):
             if not (sk[a].min() < -1e-3 or a == s % m.n_agents):        # every QP that uses its slack + one other per step
                 continue
@@ -161,7 +161,10 @@ def test_slack_qp_against_highs(hostsim):
                 assert abs(obj_x - c) <= 1e-6 * abs(c) + 5e-8
             xg = np.concatenate([xk[a].reshape(-1), sk[a].reshape(-1)])
             stat, comp, viol = qp_highs.kkt_certificate(qp, xg)
-            assert stat <= 1e-7 and comp <= 1e-8, (s, a, stat, comp)
+            # active-set solutions satisfy the certificate to 1e-7; an agent handed to the interior point carries that
+            # solver's duality gap (x to ~5e-6 on these flat QPs)
+            ipm = bool(stk[a] & capi.QP_IPM_USED)
+            assert stat <= (1e-4 if ipm else 1e-7) and comp <= (1e-6 if ipm else 1e-8), (s, a, stat, comp, ipm)
             seen["n"] += 1
             seen["slack_cases"] += bool(sk[a].min() < -1e-3)
             xh, obj_h, status = qp_highs.solve_highs(qp, time_limit=10)
@@ -252,7 +255,8 @@ def spin4_lockstep(lib, steps):
         assert np.all(pl.violation()[lost] <= 1e-6)
         r["status_mismatch"] = 0
         r["traj"] = float(np.abs(pl.traj() - sw.traj)[~lost].max())
-        r["slack"] = float(np.abs(pl.slack() - sw.qp_slack)[~lost].max())
+        both = (sp == 0) & (so == 0)                                   # a failed QP reports no slack values
+        r["slack"] = float(np.abs(pl.slack() - sw.qp_slack)[both].max())
         max_it = max(max_it, int(pl.qp_iters().max()))
         handed_over += int(((pl.status() & capi.QP_IPM_USED) != 0).sum())
         _parity.merge_max(worst, r)
