@@ -909,7 +909,9 @@ DLSC_HD void qp_agent(const Cta& c, const DevParams& P, const QpTab& T, const Qp
     int it_total = 0;
     double viol_lsc = 0.0;
     long long rows_total = 0;
-    double tau = P.qp_screen;
+    // agents pushed around by a dynamic obstacle end far from their initial trajectory: a wider first working set saves
+    // the second attempt
+    double tau = DYN ? 4.0 * P.qp_screen : P.qp_screen;
     const int max_it = P.qp_max_iter;
 
     // ---- primary solver: dual active set on all rows (LSC rows cached as (n, b) per (point, neighbour)) ----

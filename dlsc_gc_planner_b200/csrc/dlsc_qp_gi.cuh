@@ -71,6 +71,7 @@ DLSC_HD int f32_as_int(float f) {
 #endif
 }
 
+constexpr int kGiDynIters = 32;    // ... and its iteration cap in that case
 constexpr int kGiDynRows = 20;     // hand-over threshold of the active set when dynamic obstacles are present
 constexpr double kGiTol = 1e-10;   // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
 
@@ -340,6 +341,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
             c.tick(9);
         }
         iters++;
+        if (DYN && iters > kGiDynIters) { status = -1; break; }      // uniform: long add / drop sequences go to the interior point too
         // ---- small dense step (first warp): r, step lengths, active-set update; t_y = A' r into sm.ax1[0..ny) ----
         // The q x q algebra stays with lane 0; the two gather loops over the rows' y-space terms (v = A w before it,
         // t_y = A' r after it) are spread over the lanes.  Every sum keeps the serial order of its terms, so the result

@@ -6,7 +6,7 @@ import bench
 from dlsc_gc_planner_b200 import capi, missions
 args = argparse.Namespace(agents=int(os.environ.get("AGENTS", 4096)), half_extent=None, max_nbr=96, settle=12, steps=0)
 cfg, m = bench.make_world(args)
-rec, snap = bench.pilot_rollout(cfg, m, args, 0, 4)
+rec, snap = bench.pilot_rollout(cfg, m, args, 0, int(os.environ.get("STEPS", 4)))
 pl = capi.SwarmPlanner(cfg, m, max_nbr=args.max_nbr)
 pl.build_edt(m.boxes)
 bench.restore(pl, snap, slice(0, m.n_agents))
@@ -18,7 +18,7 @@ ang = rng.uniform(0, 2 * np.pi, nd)
 ovel = np.stack([np.cos(ang), np.sin(ang), np.zeros(nd)], axis=1).astype(np.float32)
 kw = dict(radius=0.3, downwash=1.0, max_acc=2.0, slack_weight=100.0)
 sw = bench.oracle_swarm(cfg, m, snap["edt"], snap, rec, args, os.cpu_count())
-for t in range(4):
+for t in range(int(os.environ.get("STEPS", 4))):
     wp = rec["wp"][t]
     pl.set_agents(waypoint=wp); pl.set_obstacles(opos, ovel, **kw)
     pl.enable_timing(True)
