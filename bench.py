@@ -557,8 +557,8 @@ def run_ours(args):
         wp.close()
 
     # ---------------- dynamic obstacles (SURVEY s8(f4), 1 GPU): the same swarm with obstacles flying through it ----------------
-    # every step: dlsc_set_obstacles (host states in) -> dlsc_step (obstacle prediction, k_lsc_dyn, k_trap, slack QP with the
-    # 128-row second-chance kernel) -> dlsc_advance.  Obstacles: 0.3 m spheres crossing the swarm area at 1 m/s, max_acc 2,
+    # every step: dlsc_set_obstacles (host states in) -> dlsc_step (obstacle prediction, k_lsc_dyn, k_trap, slack QP: active set,
+    # interior point for the slack-heavy agents) -> dlsc_advance.  Obstacles: 0.3 m spheres crossing the swarm area at 1 m/s, max_acc 2,
     # opt/slack_collision_weight 100 (launch/testall_DLSCGC_3D.launch).  Reported beside the swarm-only headline.
     dyn = None
     if world == 1 and args.dyn_obstacles > 0:
@@ -596,9 +596,19 @@ def run_ours(args):
                 dev_ms.append(ed0.elapsed_time(ed1)); host_ms.append(1e3 * (th1 - th0))
                 fails_total += int(((pl.status() & capi.FAIL_MASK & ~capi.NBR_OVERFLOW) != 0).sum())
         st = pl.status(); sk = pl.slack()
+        cpu_dyn = None
+        if not args.no_cpu_baseline:
+            # the CPU oracle (test infrastructure, here only as the timed baseline of this leg) on the next replan of the same state
+            snap_d = {"records": pl.get_records(), "sfc": pl.sfc(), "acc": pl.state()[2], "seq": pl.seq}
+            sw = oracle_swarm(cfg, m, edt, snap_d, {"wp": [wpc]}, args, os.cpu_count() or 1)
+            sw.set_obstacles(opos, ovel, **kw)
+            tc0 = time.perf_counter()
+            sw.step()
+            cpu_dyn = {"ms_per_step": 1e3 * (time.perf_counter() - tc0), "cores": os.cpu_count() or 1, "kind": "port",
+                       "sample": "one replan of all %d agents with the same %d obstacles, oracle on all host threads" % (N, nd)}
         dyn = {"obstacles": nd, "steps": args.dyn_steps, "ms_per_step": float(np.mean(host_ms)), "p50_step_ms": float(np.median(host_ms)),
                "device_ms_per_step": float(np.mean(dev_ms)), "value": N / (1e-3 * float(np.mean(host_ms))), "unit": UNIT,
-               "qp_failsafe_agent_steps": fails_total,
+               "qp_failsafe_agent_steps": fails_total, "cpu_baseline": cpu_dyn,
                "last_step": {"nbr_overflow_agents": int(((st & capi.NBR_OVERFLOW) != 0).sum()),
                              "agents_on_interior_point": int(((st & capi.QP_IPM_USED) != 0).sum()),
                              "agents_using_slack": int((sk.min(axis=(1, 2)) < -1e-6).sum()), "min_slack_m": float(sk.min())},

@@ -9,6 +9,9 @@
 namespace dlsc {
 
 constexpr int kQpThreads = 128;     // interior-point fallback kernel
+#ifndef DLSC_QP_THREADS_DYN
+#define DLSC_QP_THREADS_DYN 256
+#endif
 #ifndef DLSC_GI_THREADS
 #define DLSC_GI_THREADS 128
 #endif
@@ -137,8 +140,11 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
 
 // Fallback kernel (interior point, dlsc_qp.cuh): persistent CTAs pull agents from S.qp_list (or, with
 // all_agents, every agent: qp_solver = 1).
+// DYN (dynamic obstacles): the kernel then serves a handful of slack-heavy agents with ~3000-row working sets, and the step
+// waits for the slowest of them: twice the threads per agent (the row passes and the trailing updates scale with them)
+constexpr int kQpThreadsDyn = DLSC_QP_THREADS_DYN;
 template <bool DYN>
-__global__ void __launch_bounds__(kQpThreads, 4) k_qp(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(DYN ? kQpThreadsDyn : kQpThreads, DYN ? 512 / kQpThreadsDyn : 4) k_qp(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ DevState S,
                                                    const __grid_constant__ QpTab T, size_t scratch_doubles, int all_agents) {
     extern __shared__ __align__(16) double smem[];
@@ -183,7 +189,7 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     cudaFuncSetAttribute(k_qp_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     cudaFuncSetAttribute(k_qp_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     int per_sm = 1, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp<true>, kQpThreads, L.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp<false>, kQpThreads, L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (per_sm < 1) per_sm = 1;
     L.ctas = sms * per_sm;
@@ -215,7 +221,7 @@ int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLau
             n = 3;
         }
     }
-    if (P.n_dyn > 0) k_qp<true><<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
+    if (P.n_dyn > 0) k_qp<true><<<ctas, kQpThreadsDyn, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
     else k_qp<false><<<ctas, L.threads, L.smem, st>>>(P, S, T, L.scratch_doubles, all);
     return n;
 }

@@ -2,6 +2,20 @@
 """ncu_summary.py report.ncu-rep [out.csv]: per-kernel summary of a --set full capture: time, occupancy, issue, pipes, DRAM bytes
 and the top stall reasons (smsp__average_warps_issue_stalled_*_per_issue_active)."""
 import csv, subprocess, sys
+
+def kname(full):
+    """'void k_lsc<0>(DevParams, ...)' -> 'k_lsc' (the <0> instantiations are the swarm-only hot path); '<1>' -> 'k_lsc<dyn>'"""
+    n = full.split("(")[0].strip()
+    if n.startswith("void "):
+        n = n[5:]
+    n = n.replace("dlsc::", "")
+    if n.endswith("<0>") or n.endswith("<(bool)0>"):
+        n = n[:n.index("<")]
+    elif n.endswith("<1>") or n.endswith("<(bool)1>"):
+        n = n[:n.index("<")] + "<dyn>"
+    return n
+
+
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.split("\n")))
@@ -17,7 +31,7 @@ out = []
 for r in rows[2:]:
     if len(r) < len(hdr):
         continue
-    name = r[hdr.index("Kernel Name")].split("(")[0]
+    name = kname(r[hdr.index("Kernel Name")])
     d = {"kernel": name}
     for w in want:
         d[w] = r[hdr.index(w)].replace(",", "") + " " + units[hdr.index(w)]

@@ -2,6 +2,20 @@
 """Copy one gpurun result set (gpurun_out/<tag>_bench.json, _launches.csv, _prof.ncu-rep, _memcheck.log, _racecheck.log) into
 profiles/ as the round-2 evidence.   usage: python scripts/refresh_profiles.py <tag> [round-prefix, default r2]"""
 import csv, json, os, shutil, subprocess, sys
+
+def kname(full):
+    """'void k_lsc<0>(DevParams, ...)' -> 'k_lsc' (the <0> instantiations are the swarm-only hot path); '<1>' -> 'k_lsc<dyn>'"""
+    n = full.split("(")[0].strip()
+    if n.startswith("void "):
+        n = n[5:]
+    n = n.replace("dlsc::", "")
+    if n.endswith("<0>") or n.endswith("<(bool)0>"):
+        n = n[:n.index("<")]
+    elif n.endswith("<1>") or n.endswith("<(bool)1>"):
+        n = n[:n.index("<")] + "<dyn>"
+    return n
+
+
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 rp = sys.argv[2] if len(sys.argv) > 2 else "r2"
@@ -26,7 +40,7 @@ if os.path.exists(g("_prof.ncu-rep")):
     traffic = {}
     for r in rows[2:]:
         if len(r) > max(ir, iw):
-            traffic[r[ik].split("(")[0]] = f(r[ir]) * sc[units[ir]] + f(r[iw]) * sc[units[iw]]
+            traffic[kname(r[ik])] = f(r[ir]) * sc[units[ir]] + f(r[iw]) * sc[units[iw]]
     json.dump(traffic, open(P("traffic.json"), "w"), indent=1)
     print(traffic)
 for kind in ("memcheck", "racecheck"):
