@@ -10,7 +10,7 @@ namespace dlsc {
 
 constexpr int kQpThreads = 128;     // interior-point fallback kernel
 #ifndef DLSC_QP_THREADS_DYN
-#define DLSC_QP_THREADS_DYN 256
+#define DLSC_QP_THREADS_DYN 512
 #endif
 #ifndef DLSC_GI_THREADS
 #define DLSC_GI_THREADS 128
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
 // Fallback kernel (interior point, dlsc_qp.cuh): persistent CTAs pull agents from S.qp_list (or, with
 // all_agents, every agent: qp_solver = 1).
 // DYN (dynamic obstacles): the kernel then serves a handful of slack-heavy agents with ~3000-row working sets, and the step
-// waits for the slowest of them: twice the threads per agent (the row passes and the trailing updates scale with them)
+// waits for the slowest of them: four times the threads per agent (the row passes and the trailing updates scale with them: 8.0 / 6.1 / 5.0 ms per step at 128 / 256 / 512)
 constexpr int kQpThreadsDyn = DLSC_QP_THREADS_DYN;
 template <bool DYN>
 __global__ void __launch_bounds__(DYN ? kQpThreadsDyn : kQpThreads, DYN ? 512 / kQpThreadsDyn : 4) k_qp(const __grid_constant__ DevParams P,

@@ -311,3 +311,44 @@ def test_gpu_closed_loop_graph_equals_stages(cuda_lib):
         runs.append(np.array(trajs))
         pl.close()
     assert np.array_equal(runs[0], runs[1])
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_contexts_with_obstacles(cuda_lib):
+    """The multi-GPU layout with dynamic obstacles: two contexts owning half of the agents each, both given the same
+    obstacle states, records exchanged through host memory, reproduce the single-context trajectories and slack values bit
+    for bit (the obstacle slots, predictions and slack columns are per context and independent of the sharding)."""
+    from dlsc_gc_planner_b200 import missions as ms
+    from oracle import oracle_py as O
+    cfg, m = _parity.load_case("forest10")
+    edt = O.edt_build(_parity.oracle_params(cfg, m), m.boxes)
+    whole = capi.SwarmPlanner(cfg, m, max_nbr=14, lib=cuda_lib)
+    halves = [capi.SwarmPlanner(cfg, m, max_nbr=14, begin=b, n_local=5, lib=cuda_lib) for b in (0, 5)]
+    for pl in [whole] + halves:
+        pl.set_edt(edt.dist, edt.obst, edt.dims, edt.min_key, edt.res)
+    for h in halves:
+        for o in halves:
+            if o is not h:
+                h.set_records(o.begin, o.get_records(o.begin, o.NL))
+    wp = m.start.copy()
+    used = 0.0
+    for step in range(24):
+        st = ms.obstacle_states(ms.SPIN4, step * cfg.dt)
+        kw = dict(radius=st["radius"], downwash=st["downwash"], max_acc=st["max_acc"], slack_weight=100.0)
+        wp[:, :2] += np.float32(0.1) * np.sign(m.goal[:, :2] - wp[:, :2])
+        for pl in [whole] + halves:
+            pl.set_obstacles(st["pos"], st["vel"], **kw)
+            pl.set_agents(waypoint=wp[pl.begin:pl.begin + pl.NL])
+            pl.plan(); pl.advance()
+        for h in halves:
+            for o in halves:
+                if o is not h:
+                    h.set_records(o.begin, o.get_records(o.begin, o.NL))
+        t, sk = whole.traj(), whole.slack()
+        assert np.array_equal(t[:5], halves[0].traj()) and np.array_equal(t[5:], halves[1].traj()), step
+        assert np.array_equal(sk[:5], halves[0].slack()) and np.array_equal(sk[5:], halves[1].slack()), step
+        assert np.array_equal(whole.status()[:5], halves[0].status())
+        used = max(used, float(-sk.min()))
+    assert used > 0.05
+    for pl in [whole] + halves:
+        pl.close()
