@@ -493,12 +493,17 @@ def run_ours(args):
                                hb["wp"][1][t].ctypes.data, None) for t in range(W + K)]
     import ctypes as C
 
+    # the trajectories go straight into the pinned host buffer (dlsc_bind_traj_host): every agent's result is written over
+    # PCIe as soon as its QP finishes, so the device->host transfer of the step's result overlaps the QPs still running;
+    # the buffer is complete after the step's dlsc_sync
+    pl.bind_traj_host(traj_h)
+
     def e2e_step(t):
         pl.set_agents_async(structs[t])
         gather()
         pl.plan()
         pl.publish_records()
-        pl._ck(pl.lib.dlsc_get_traj(pl.ctx, C.c_void_p(traj_h.ctypes.data)))     # D2H + stream sync
+        pl.sync()                                                                 # result of this step is in traj_h
 
     barrier()
     for t in range(W):
@@ -521,6 +526,7 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_ms, t_host = float(tt[0].item()), float(tt[1].item())
     e2e_exact = bool(np.array_equal(traj_h, snap["final_traj"][sl]))
+    pl.bind_traj_host(None)
     h2d = int(4 * N * 12)
     d2h = int(N * cfg.M * (cfg.n + 1) * 12)
 

@@ -73,7 +73,7 @@ EXPORTS = (
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
     "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build dlsc_wp_last_error dlsc_wp_create dlsc_wp_destroy "
     "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps "
-    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred").split()
+    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host").split()
 
 
 def build_library(force=False):
@@ -336,6 +336,17 @@ class SwarmPlanner:
 
     def advance(self):
         self._ck(self.lib.dlsc_advance(self.ctx))
+
+    def bind_traj_host(self, array):
+        """Every replan delivers the trajectories into `array` ([n_local][M][6][3] float32, ideally pinned): complete after
+        sync().  None unbinds.  The caller keeps the array alive."""
+        if array is None:
+            self._ck(self.lib.dlsc_bind_traj_host(self.ctx, None))
+            self._traj_host = None
+            return
+        assert array.dtype == np.float32 and array.flags["C_CONTIGUOUS"] and array.size == self.NL * self.M * self.P * 3
+        self._ck(self.lib.dlsc_bind_traj_host(self.ctx, C.c_void_p(array.ctypes.data)))
+        self._traj_host = array
 
     def publish_records(self):
         self._ck(self.lib.dlsc_publish_records(self.ctx))

@@ -38,6 +38,7 @@ struct dlsc_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap = true;               // DLSC_OVERLAP=0 disables; per-stage timing (dlsc_enable_timing) serialises too
     bool rec_owned = false;
+    void* traj_host_registered = nullptr;   // host buffer pinned by dlsc_bind_traj_host (unregistered on rebind / destroy)
     bool have_edt = false;
     int4* edt_cells = nullptr;
     float* edt_centre = nullptr;
@@ -278,6 +279,7 @@ void dlsc_destroy(dlsc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->traj_host_registered) cudaHostUnregister(c->traj_host_registered);
     for (void* p : c->allocs) cudaFree(p);
     if (c->tab_blob) cudaFree(c->tab_blob);
     if (c->edt_cells) cudaFree(c->edt_cells);
@@ -603,6 +605,28 @@ int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
     return 0;
 }
 
+int dlsc_bind_traj_host(dlsc_ctx* c, float* host) {
+    if (!c) return fail("null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->traj_host_registered) { cudaHostUnregister(c->traj_host_registered); c->traj_host_registered = nullptr; }
+    c->S.traj_host = nullptr;
+    if (!host) return 0;
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) {       // not pinned yet: pin and map it here
+        cudaGetLastError();
+        const size_t bytes = (size_t)c->P.NL * c->P.M * kP * 12;
+        if (cudaHostRegister(host, bytes, cudaHostRegisterMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return fail("dlsc_bind_traj_host: the buffer is neither pinned nor registrable");
+        }
+        c->traj_host_registered = host;
+        CK(cudaHostGetDevicePointer(&dev, host, 0));
+    }
+    c->S.traj_host = static_cast<float*>(dev);
+    return 0;
+}
+
 float* dlsc_records_device(dlsc_ctx* c) { return c ? c->S.rec : nullptr; }
 int dlsc_record_floats(const dlsc_ctx* c) { return c ? c->P.rec : 0; }
 int dlsc_bind_records(dlsc_ctx* c, float* p) {
@@ -758,6 +782,7 @@ static void make_view(const dlsc_ctx* c, int first, int count, DevParams& P, Dev
     S.init_traj += f * npt * 3; S.nbr_idx += f * K; S.nbr_cnt += f;
     S.lsc_normal += f * K * M * 3; S.lsc_d += f * K * M * kP; S.lsc_anchor_last += f * K * 3; S.lsc_near += f * K * M;
     S.sfc += f * M * 6; S.traj += f * npt * 3; S.qp_x += f * (size_t)P.D * npt;
+    if (S.traj_host) S.traj_host += f * npt * 3;
     S.cost += f; S.viol += f; S.qp_iters += f; S.status += f;
     S.qp_list += f; S.qp_list_gi += f; S.qp_seed += f * 4;
     S.comm_box += f * 6; S.trap += f;

@@ -35,6 +35,7 @@ struct DevState {
     float* lsc_near;           // [NL][K][M] QP row screen: smallest normalised slack of the item's rows at the initial trajectory
     float* sfc;                // [NL][M][6]
     float* traj;               // [NL][M][P][3]  QP result (or failsafe)
+    float* traj_host;          // device view of a caller's mapped pinned buffer of the same shape (dlsc_bind_traj_host), or null
     double* qp_x;              // [NL][D][M][P]
     double *cost, *viol;       // [NL]
     int32_t *qp_iters, *status;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState
     in.pred_traj = S.pred_traj;
     in.near = S.lsc_near + pr * P.M;
     out.traj = S.traj + (size_t)la * npt * 3;
+    out.traj_host = S.traj_host ? S.traj_host + (size_t)la * npt * 3 : nullptr;
     out.x = S.qp_x + (size_t)la * T.nx;
     out.cost = S.cost + la; out.viol = S.viol + la; out.iters = S.qp_iters + la; out.status = S.status + la;
     out.rows = nullptr;

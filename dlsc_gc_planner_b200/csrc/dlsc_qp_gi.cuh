@@ -576,13 +576,16 @@ DLSC_HD void gi_epilogue(const Cta& c, const DevParams& P, const QpTab& T, const
     }
     const bool ok = (status == 0);
     for (int e = c.tid; e < npt; e += c.nthr) {
-        float* o = out.traj + e * 3;
+        float v0, v1, v2;
         if (ok) {                                                                     // :71-83
-            o[0] = (float)sm.x[e]; o[1] = (float)sm.x[npt + e];
-            o[2] = D3 ? (float)sm.x[2 * npt + e] : (float)P.z_2d;
+            v0 = (float)sm.x[e]; v1 = (float)sm.x[npt + e];
+            v2 = D3 ? (float)sm.x[2 * npt + e] : (float)P.z_2d;
         } else {                                                                      // failsafe traj_planner.cpp:775-776
-            o[0] = in.init_traj[e * 3]; o[1] = in.init_traj[e * 3 + 1]; o[2] = in.init_traj[e * 3 + 2];
+            v0 = in.init_traj[e * 3]; v1 = in.init_traj[e * 3 + 1]; v2 = in.init_traj[e * 3 + 2];
         }
+        float* o = out.traj + e * 3;
+        o[0] = v0; o[1] = v1; o[2] = v2;
+        if (out.traj_host) { float* h = out.traj_host + e * 3; h[0] = v0; h[1] = v1; h[2] = v2; }   // streams out over PCIe while the other agents solve
     }
     if (out.x)
         for (int e = c.tid; e < nx; e += c.nthr) out.x[e] = sm.x[e];

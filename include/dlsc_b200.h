@@ -246,6 +246,12 @@ int dlsc_get_violation(dlsc_ctx* ctx, double* viol /* [n_local] */);
 int dlsc_get_qp_iters(dlsc_ctx* ctx, int32_t* iters /* [n_local] */);
 int dlsc_get_status(dlsc_ctx* ctx, int32_t* status /* [n_local] */);
 int dlsc_get_goal(dlsc_ctx* ctx, float* goal /* [n_local][3] current_goal_point */);
+/* Deliver the trajectories straight into host memory: `host` is a caller-owned buffer [n_local][M][6][3] floats, pinned
+ * (cudaHostAlloc / cudaHostRegister; a pageable buffer is pinned here).  From then on every replan writes each agent's
+ * result (TrajOptResult::desired_traj, src/traj_optimizer.cpp:71-83, or the failsafe) to it as soon as that agent's QP
+ * finishes, so the device->host transfer overlaps the QPs still running; the buffer is complete after dlsc_sync().
+ * dlsc_get_traj keeps working.  NULL unbinds.  The buffer must outlive the binding. */
+int dlsc_bind_traj_host(dlsc_ctx* ctx, float* host);
 int dlsc_get_state(dlsc_ctx* ctx, float* pos, float* vel, float* acc /* each [n_local][3] or NULL */);
 int dlsc_get_init_traj(dlsc_ctx* ctx, float* traj /* [n_local][M][P][3] */);
 int dlsc_get_pred_traj(dlsc_ctx* ctx, float* traj /* [n_agents][M][P][3] */);

@@ -42,6 +42,7 @@ struct dlsc_ctx {
     EdtDev edt;
     bool have_edt = false;
     int64_t counters[DLSC_N_COUNTERS] = {0};
+    float* traj_host = nullptr;
     // dynamic obstacles
     std::vector<float> dyn_pos, dyn_vel, comm_box;
     std::vector<double> dyn_radius, dyn_downwash, dyn_max_acc, dyn_size, qp_slack;
@@ -244,6 +245,7 @@ int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
     return 0;
 }
 
+int dlsc_bind_traj_host(dlsc_ctx* c, float* host) { c->traj_host = host; return 0; }
 int dlsc_set_obstacles(dlsc_ctx* c, const dlsc_obstacles* o, const dlsc_obstacle_params* op) {
     const int n = o ? o->n : 0;
     if (n < 0 || n > kMaxDyn) return fail("too many obstacles");
@@ -447,6 +449,7 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
             long long rows = 0;
             QpOut out;
             out.traj = c->traj.data() + (size_t)la * npt * 3;
+            out.traj_host = c->traj_host ? c->traj_host + (size_t)la * npt * 3 : nullptr;
             out.x = c->qp_x.data() + (size_t)la * c->T.nx;
             out.cost = &c->cost[la]; out.viol = &c->viol[la]; out.iters = &c->qp_iters[la]; out.status = &c->status[la];
             out.rows = &rows;

@@ -162,3 +162,32 @@ def test_sharded_contexts_match_single_context(cuda_lib):
         t = whole.traj()
         assert np.array_equal(t[:5], halves[0].traj()) and np.array_equal(t[5:], halves[1].traj())
         assert np.array_equal(whole.get_records(), halves[0].get_records())
+
+
+def test_bound_host_trajectories_equal_the_device_copy(cuda_lib):
+    """dlsc_bind_traj_host: the mapped host buffer holds exactly dlsc_get_traj's result after every step (pinned through
+    torch, and a pageable numpy array that the library pins itself), also on the CUDA-graph path and after unbinding."""
+    import torch
+    cfg, m = _parity.load_case("forest10")
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=9, lib=cuda_lib)
+    pl.build_edt(m.boxes)
+    shape = (m.n_agents, cfg.M, cfg.n + 1, 3)
+    pinned = torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
+    pageable = np.zeros(shape, np.float32)
+    wf = _parity.default_waypoints(cfg, m)
+    wp = m.start.copy()
+    for step in range(12):
+        buf = pinned if step < 8 else pageable
+        if step in (0, 8):
+            pl.bind_traj_host(buf)
+        wp[:, 0] += np.float32(0.1) * np.sign(m.goal[:, 0] - wp[:, 0])
+        pl.set_agents(waypoint=wp)
+        buf[...] = -7.0
+        pl.plan(); pl.sync()
+        assert np.array_equal(buf, pl.traj()), step
+        pl.advance()
+    pl.bind_traj_host(None)
+    pageable[...] = -7.0
+    pl.plan(); pl.sync()
+    assert np.all(pageable == -7.0)
+    pl.close()
