@@ -174,6 +174,7 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     if (hp->M < 2 || hp->M > kMaxM) return fail("dlsc_create: traj/M out of range [2,16]");
     if (hp->dim * (3 * hp->M - 2) > 128) return fail("dlsc_create: dim*(3M-2) must be <= 128");
     if (hp->max_nbr < 1 || hp->max_nbr > 1024) return fail("dlsc_create: max_nbr must be in [1, 1024]");
+    if (hp->qp_solver < 0 || hp->qp_solver > 3) return fail("dlsc_create: qp_solver must be 0..3");
     if (n_agents < 1 || agent_begin < 0 || n_local < 1 || agent_begin + n_local > n_agents)
         return fail("dlsc_create: bad agent block");
     if (!(hp->dt > 0) || !(hp->world_res > 0)) return fail("dlsc_create: dt and world_res must be positive");

@@ -55,7 +55,7 @@ struct DevState {
     EdtDev edt;
 };
 
-struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; size_t fast_smem; };
+struct QpLaunch { int ctas, threads; size_t smem; size_t scratch_doubles; size_t gi_smem; size_t fast_smem; int sms; };
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st);
 int launch_neighbours(const DevParams& P, const DevState& S, cudaStream_t st, int parts = 3);   // 1: grid build, 2: search; returns launches

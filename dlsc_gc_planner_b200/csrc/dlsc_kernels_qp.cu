@@ -19,6 +19,7 @@ constexpr int kGiThreads = DLSC_GI_THREADS;
 #ifndef DLSC_GI_MINB
 #define DLSC_GI_MINB 6
 #endif
+constexpr int kGiBlocksPerSm = DLSC_GI_MINB;
 
 __device__ __forceinline__ void qp_load_agent(const DevParams& P, const DevState& S, const QpTab& T, int la, QpIn& in, QpOut& out) {
     const int npt = P.M * kP;
@@ -190,8 +191,10 @@ QpLaunch qp_launch_config(const DevParams& P, const QpTab& T, int device) {
     cudaFuncSetAttribute(k_qp_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     cudaFuncSetAttribute(k_qp_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.fast_smem);
     int per_sm = 1, sms = 148;
+    L.sms = 148;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp<false>, kQpThreads, L.smem);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    L.sms = sms;
     if (per_sm < 1) per_sm = 1;
     L.ctas = sms * per_sm;
     L.scratch_doubles = qp_scratch_doubles(T, P.K);
@@ -205,7 +208,13 @@ int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLau
     const int all = (P.qp_solver == 1) ? 1 : 0;
     int n = 1;
     if (!all) {
-        static const bool no_fast = [] { const char* e = getenv("DLSC_QP_FAST"); return e && e[0] == '0'; }();
+        // The warp-per-agent fast path pays when the agents fill the GPU several times over (4096 agents: 0.165 against
+        // 0.185 ms for the QP stage).  A small block -- one rank's share of a sharded swarm -- fits the CTA-per-agent kernel
+        // in one or two waves, and there a whole CTA per first scan is quicker than one warp (512 agents: 0.141 against
+        // 0.173 ms; 1024: 0.081 against 0.110).  qp_solver = 2 / 3 (or DLSC_QP_FAST=1 / 0) forces either way.
+        static const int fast_env = [] { const char* e = getenv("DLSC_QP_FAST"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+        const bool no_fast = P.qp_solver == 2 ? false : P.qp_solver == 3 ? true
+                             : fast_env >= 0 ? fast_env == 0 : P.NL <= 2 * kGiBlocksPerSm * L.sms;
         const bool dyn = P.n_dyn > 0;
         const int fast_grid = (P.NL + kFastWarps - 1) / kFastWarps, per_warp = (int)(L.fast_smem / sizeof(double) / kFastWarps);
         if (no_fast) {

@@ -53,7 +53,8 @@ typedef struct dlsc_params {
     double w_terminal;      /* opt/terminal_weight                                         */
     double reset_threshold; /* plan/reset_threshold                                        */
     int32_t qp_max_iter;    /* interior-point iteration cap (0 -> 80)                      */
-    int32_t qp_solver;      /* 0: dual active set, interior-point fallback (default); 1: interior point only */
+    int32_t qp_solver;      /* 0: dual active set, interior-point fallback (default); 1: interior point only;
+                               2 / 3: as 0 with the warp-per-agent first scan forced on / off (0 picks by block size) */
     double qp_screen_slack; /* LSC row screens (exact, see dlsc_qp_gi.cuh / dlsc_qp.cuh).  0 -> default (0.5);
                                > 0: the active set skips rows whose slack at the initial trajectory exceeds the
                                iterate's deviation from it, and the interior-point fallback starts from the rows

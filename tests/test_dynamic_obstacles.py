@@ -32,10 +32,10 @@ SCENES = {
 }
 
 
-def lockstep(lib, name, steps, K=12, obs=OBS, collect=None):
+def lockstep(lib, name, steps, K=12, obs=OBS, collect=None, qp_solver=0):
     cfg, m = _parity.load_case(name)
     sw = _parity.make_oracle(cfg, m, K, n_threads=os.cpu_count() or 1)
-    pl = capi.SwarmPlanner(cfg, m, max_nbr=K, lib=lib)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=K, lib=lib, qp_solver=qp_solver)
     if cfg.use_sfc:
         pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
     opos, ovel = (a.copy() for a in SCENES[name])
@@ -93,7 +93,8 @@ def test_hostsim_parity_with_dynamic_obstacles(hostsim, name, steps):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,steps", [("maze10", 30), ("forest10", 24), ("empty10", 16)])
 def test_gpu_parity_with_dynamic_obstacles(cuda_lib, name, steps):
-    check(lockstep(cuda_lib, name, steps), name)
+    for qp_solver in (2, 3):                          # warp-per-agent first scan forced on / off
+        check(lockstep(cuda_lib, name, steps, qp_solver=qp_solver), name)
 
 
 def test_interior_point_with_slack_variables(hostsim):

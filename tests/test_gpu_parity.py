@@ -11,20 +11,23 @@ from test_hostsim_parity import check_worst
 pytestmark = pytest.mark.gpu
 
 
-def make_pair(cuda_lib, cfg, m, K):
+def make_pair(cuda_lib, cfg, m, K, qp_solver=0):
     sw = _parity.make_oracle(cfg, m, K, n_threads=8)
-    pl = capi.SwarmPlanner(cfg, m, max_nbr=K, lib=cuda_lib)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=K, lib=cuda_lib, qp_solver=qp_solver)
     if cfg.use_sfc:
         pl.set_edt(sw.edt.dist, sw.edt.obst, sw.edt.dims, sw.edt.min_key, sw.edt.res)
     return sw, pl
 
 
+# qp_solver 2 / 3: the warp-per-agent first scan (k_qp_fast + seeded k_qp_gi) forced on / off -- the default picks by block
+# size and would take the second for every mission of this size
+@pytest.mark.parametrize("qp_solver", [2, 3])
 @pytest.mark.parametrize("name,steps,n", [("empty10", 30, 10), ("maze10", 60, 10), ("forest10", 40, 10),
                                            ("empty70", 12, 70), ("empty50", 8, 50)])
-def test_lockstep_parity_reference_missions(cuda_lib, name, steps, n):
+def test_lockstep_parity_reference_missions(cuda_lib, name, steps, n, qp_solver):
     cfg, m = _parity.load_case(name)
     m = _parity.subset(m, n)
-    sw, pl = make_pair(cuda_lib, cfg, m, n - 1)
+    sw, pl = make_pair(cuda_lib, cfg, m, n - 1, qp_solver)
     w = _parity.run_lockstep(pl, sw, m, steps, _parity.default_waypoints(cfg, m))
     check_worst(w)
     assert pl.launch_count() > 0
@@ -47,10 +50,11 @@ def test_synthetic_forest_256(cuda_lib):
     """A 256-agent cut of the synthetic forest (BASELINE config 4 shape: M=10, 3-D, SFC, range 3)."""
     cfg = missions.PlannerConfig.forest3d()
     m = missions.synthetic_forest(n_agents=256, half_extent=8.0, seed=11)
-    sw, pl = make_pair(cuda_lib, cfg, m, 64)
-    w = _parity.run_lockstep(pl, sw, m, 12, _parity.default_waypoints(cfg, m))
-    check_worst(w)
-    pl.close()
+    for qp_solver in (2, 0):
+        sw, pl = make_pair(cuda_lib, cfg, m, 64, qp_solver)
+        w = _parity.run_lockstep(pl, sw, m, 12, _parity.default_waypoints(cfg, m))
+        check_worst(w)
+        pl.close()
 
 
 def test_neighbour_overflow(cuda_lib):
