@@ -210,11 +210,11 @@ int launch_qp(const DevParams& P, const DevState& S, const QpTab& T, const QpLau
     if (!all) {
         // The warp-per-agent fast path pays when the agents fill the GPU several times over (4096 agents: 0.165 against
         // 0.185 ms for the QP stage).  A small block -- one rank's share of a sharded swarm -- fits the CTA-per-agent kernel
-        // in one or two waves, and there a whole CTA per first scan is quicker than one warp (512 agents: 0.141 against
-        // 0.173 ms; 1024: 0.081 against 0.110).  qp_solver = 2 / 3 (or DLSC_QP_FAST=1 / 0) forces either way.
+        // in up to three waves, and there a whole CTA per first scan is quicker than one warp (512 agents: 0.141 against
+        // 0.173 ms; 1024: 0.081 against 0.110; 2048 per rank on 2 GPUs: 0.108 against 0.134; 3072: a tie).  qp_solver = 2 / 3 (or DLSC_QP_FAST=1 / 0) forces either way.
         static const int fast_env = [] { const char* e = getenv("DLSC_QP_FAST"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
         const bool no_fast = P.qp_solver == 2 ? false : P.qp_solver == 3 ? true
-                             : fast_env >= 0 ? fast_env == 0 : P.NL <= 2 * kGiBlocksPerSm * L.sms;
+                             : fast_env >= 0 ? fast_env == 0 : P.NL <= 3 * kGiBlocksPerSm * L.sms;
         const bool dyn = P.n_dyn > 0;
         const int fast_grid = (P.NL + kFastWarps - 1) / kFastWarps, per_warp = (int)(L.fast_smem / sizeof(double) / kFastWarps);
         if (no_fast) {
