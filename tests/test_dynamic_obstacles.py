@@ -353,3 +353,26 @@ def test_gpu_sharded_contexts_with_obstacles(cuda_lib):
     assert used > 0.05
     for pl in [whole] + halves:
         pl.close()
+
+
+def test_obstacle_scenario_generator():
+    """missions.obstacle_states: the spin model keeps its radius, height and speed (include/obstacle.hpp:96-152), the
+    straight model accelerates, cruises and stops at its goal (:154-245), both report the mission's size / downwash /
+    max_acc, a zero downwash is read as 1 (src/mission.cpp:237-239), other types are refused."""
+    from dlsc_gc_planner_b200 import missions as ms
+    for t in (0.0, 0.37, 2.0, 11.3):
+        st = ms.obstacle_states(ms.SPIN4, t)
+        r = np.linalg.norm(st["pos"][:, :2].astype(np.float64), axis=1)
+        assert np.allclose(r, 2.0, atol=1e-6) and np.allclose(st["pos"][:, 2], 1.0)
+        assert np.allclose(np.linalg.norm(st["vel"].astype(np.float64), axis=1), 1.0, atol=1e-6)
+        assert np.allclose(np.sum(st["pos"][:, :2] * st["vel"][:, :2], axis=1), 0.0, atol=1e-5)      # tangential
+    a, b = ms.obstacle_states(ms.SPIN4, 1.0), ms.obstacle_states(ms.SPIN4, 1.001)
+    assert np.allclose((b["pos"] - a["pos"]) / 0.001, a["vel"], atol=2e-3)                            # velocity = d pos / dt
+    straight = [dict(type="straight", start=[0, 0, 1], goal=[4, 0, 1], speed=1.0, size=0.2, max_acc=2.0, downwash=0)]
+    p0 = ms.obstacle_states(straight, 0.0); pm = ms.obstacle_states(straight, 2.0); pe = ms.obstacle_states(straight, 100.0)
+    assert np.allclose(p0["pos"], [[0, 0, 1]]) and np.allclose(p0["vel"], 0)
+    assert np.allclose(pm["vel"], [[1, 0, 0]]) and 0 < pm["pos"][0, 0] < 4
+    assert np.allclose(pe["pos"], [[4, 0, 1]]) and np.allclose(pe["vel"], 0)
+    assert pe["downwash"][0] == 1.0 and pe["radius"][0] == 0.2 and pe["max_acc"][0] == 2.0
+    with pytest.raises(NotImplementedError):
+        ms.obstacle_states([dict(type="patrol")], 0.0)
