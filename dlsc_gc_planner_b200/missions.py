@@ -174,6 +174,66 @@ def load_world_csv(path):
     return np.array(rows, np.float32).reshape(-1, 6)
 
 
+def load_world_bt(path):
+    """Parse an octomap binary tree (.bt), the other world format MapManager::setGlobalMap accepts
+    (reference src/map_manager.cpp:66-73: OcTree::readBinary, then expand()).  octomap itself is absent here; the
+    format is the published one of octomap 1.9 (OcTreeBase::readBinary / OcTree::readBinaryNode): a text header
+    ("id OcTree", "size <nodes>", "res <m>", "data"), then the tree depth-first, two bytes per inner node = 2 bits per
+    child, bit pair (b[2i], b[2i+1]) = (1,0) free leaf, (0,1) occupied leaf, (1,1) inner node, (0,0) unknown; child i
+    sits at offset (i & 1, i >> 1 & 1, i >> 2 & 1); depth 16, key 32768 = coordinate 0.
+    -> (res, cubes) with cubes [n, 4] int64 = (kx, ky, kz, edge) per OCCUPIED leaf in cells relative to the origin
+    (cell k covers [k res, (k+1) res)); a pruned leaf above the finest depth is one cube with edge > 1.
+    Raises ValueError when the node count differs from the header (a cheap whole-file check of the reading)."""
+    data = open(path, "rb").read()
+    end = data.index(b"\ndata\n") + 6
+    head = {}
+    for line in data[:end].decode("ascii", "replace").splitlines():
+        parts = line.split()
+        if len(parts) == 2 and not line.startswith("#"):
+            head[parts[0]] = parts[1]
+    if head.get("id") != "OcTree":
+        raise ValueError("not an OcTree binary file: id %r" % head.get("id"))
+    res, n_nodes = float(head["res"]), int(head["size"])
+    pos, count, cubes = end, 1, []
+    stack = [(0, 0, 0, 65536)]                      # inner nodes still to read, depth-first in child order
+    while stack:
+        x0, y0, z0, edge = stack.pop()
+        if pos + 2 > len(data):
+            raise ValueError("truncated .bt file")
+        bits = data[pos] | (data[pos + 1] << 8)
+        pos += 2
+        h = edge // 2
+        inner = []
+        for i in range(8):
+            b0, b1 = (bits >> (2 * i)) & 1, (bits >> (2 * i + 1)) & 1
+            if not (b0 or b1):
+                continue
+            count += 1
+            cx, cy, cz = x0 + (i & 1) * h, y0 + ((i >> 1) & 1) * h, z0 + ((i >> 2) & 1) * h
+            if b0 and b1:
+                inner.append((cx, cy, cz, h))
+            elif b1:
+                cubes.append((cx - 32768, cy - 32768, cz - 32768, h))
+        stack.extend(reversed(inner))               # readBinaryNode recurses into the inner children in index order
+    if count != n_nodes:
+        raise ValueError(".bt node count %d != header size %d" % (count, n_nodes))
+    return res, np.array(cubes, np.int64).reshape(-1, 4)
+
+
+def occupancy_from_cubes(cubes, dims, min_key):
+    """Occupancy grid [dims0][dims1][dims2] uint8 of the planner's map window (dlsc_edt_dims: map index = cell key -
+    min_key) from load_world_bt cubes -- what dlsc_build_edt_occupancy takes.  Cells outside the window are dropped, like
+    the bounding-box iteration of DynamicEDTOctomap (reference src/map_manager.cpp:75-79)."""
+    occ = np.zeros(tuple(int(d) for d in dims), np.uint8)
+    for kx, ky, kz, e in np.asarray(cubes, np.int64):
+        lo = np.array([kx, ky, kz]) - np.asarray(min_key, np.int64)
+        hi = lo + e
+        lo = np.maximum(lo, 0); hi = np.minimum(hi, occ.shape)
+        if np.all(hi > lo):
+            occ[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = 1
+    return occ
+
+
 def lattice_step_waypoints(pos, goal, grid_res=0.5, occupied=None):
     """Documented stand-in for the PIBT waypoint provider (reference src/grid_based_planner.cpp:64-94):
     one greedy step on the ``grid_res`` lattice from the current waypoint toward the goal, axis with the
