@@ -303,6 +303,25 @@ public:
         step_open = false; batch_done = false;
         std::fill(staged.begin(), staged.end(), 0);
         std::fill(planned.begin(), planned.end(), 0);
+        std::fill(have_list.begin(), have_list.end(), 0);
+    }
+    // The obstacle list the caller handed to agent i defines that agent's neighbours (the reference plans against exactly
+    // the list broadcastMsgs built, src/multi_sync_simulator.cpp:481-503): dynamic obstacles first (entries N + o), then
+    // the agents in ascending id.  With the reference's own filter this equals what the device search finds.
+    void set_list(int i, const Obstacles& all) {
+        if (i < 0 || i >= N) return;
+        int32_t* row = nbr_idx.data() + (size_t)i * Kcap;
+        int c = 0, nd = 0;
+        for (const Obstacle& o : all) if (o.type != ObstacleType::AGENT) nd++;
+        for (int o = 0; o < nd && c < Kcap; o++) row[c++] = N + o;
+        std::vector<int> ids;
+        for (const Obstacle& o : all) if (o.type == ObstacleType::AGENT && o.id >= 0 && o.id < N && o.id != i) ids.push_back(o.id);
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        if (nd + (int)ids.size() > Kcap) throw std::length_error("[TrajPlanner] more obstacles than the device list holds (Param::max_neighbours)");
+        for (int id : ids) row[c++] = id;
+        nbr_cnt[i] = c;
+        have_list[i] = 1;
     }
     void stage(const Agent& a, bool disturbed) {
         const int i = a.id;
@@ -382,17 +401,27 @@ public:
         batch_last = all;
         if (all && !batch_done) {
             upload();
-            check(dlsc_step(ctx), "dlsc_step");
+            if (std::all_of(have_list.begin(), have_list.end(), [](uint8_t s) { return s != 0; })) {
+                // the callers' obstacle lists are the neighbour lists: every stage but the device neighbour search
+                check(dlsc_set_neighbours(ctx, nbr_idx.data(), nbr_cnt.data()), "dlsc_set_neighbours");
+                check(dlsc_run_stages(ctx, DLSC_STAGE_ALL & ~DLSC_STAGE_NBR), "dlsc_run_stages");
+                check(dlsc_set_seq(ctx, dlsc_get_seq(ctx) + 1), "dlsc_set_seq");
+            } else {
+                check(dlsc_step(ctx), "dlsc_step");
+            }
             check(dlsc_publish_records(ctx), "dlsc_publish_records");
             fetch();
             batch_done = true;
         } else if (!all) {
             upload();
-            const int seq = dlsc_get_seq(ctx);
-            check(dlsc_run_stages_subset(ctx, DLSC_STAGE_ALL, i, 1), "dlsc_run_stages_subset");
+            if (have_list[i]) {
+                check(dlsc_set_neighbours(ctx, nbr_idx.data(), nbr_cnt.data()), "dlsc_set_neighbours");
+                check(dlsc_run_stages_subset(ctx, DLSC_STAGE_ALL & ~DLSC_STAGE_NBR, i, 1), "dlsc_run_stages_subset");
+            } else {
+                check(dlsc_run_stages_subset(ctx, DLSC_STAGE_ALL, i, 1), "dlsc_run_stages_subset");
+            }
             pending_publish = true;
             fetch();
-            (void)seq;
         }
         planned[i] = 1;
         if (!batch_done && std::all_of(planned.begin(), planned.end(), [](uint8_t s) { return s != 0; })) finish_serial_step();
@@ -416,7 +445,9 @@ public:
     std::vector<double> cost;
     std::vector<double> slack;                     // [N][n_dynamic][M] slack variables of the last step
     std::vector<int32_t> status;
-    std::vector<uint8_t> staged, planned;
+    std::vector<uint8_t> staged, planned, have_list;
+    std::vector<int32_t> nbr_idx, nbr_cnt;         // per-agent obstacle lists as the callers passed them (set_list)
+    int Kcap = 0;
 
 private:
     SwarmBatch(const Param& p, const Mission& m) {
@@ -440,6 +471,7 @@ private:
         check(dlsc_enable_timing(ctx, 1), "dlsc_enable_timing");      // feeds PlanningStatistics (reference-scale missions)
         pos.assign(3 * N, 0.f); vel = pos; acc = pos; wp = pos; goal = pos;
         dist.assign(N, 0); staged.assign(N, 0); planned.assign(N, 0);
+        Kcap = K; have_list.assign(N, 0); nbr_idx.assign((size_t)N * K, 0); nbr_cnt.assign(N, 0);
         traj.assign((size_t)N * M * (n + 1) * 3, 0.f); cost.assign(N, 0.0); status.assign(N, 0);
     }
     void upload() {
@@ -681,6 +713,7 @@ public:
         obstacles = obstacles_;
         batch->new_step();
         batch->set_dynamic(obstacles);             // non-agent entries: dynamic obstacles (size prediction, slack QP) on the device
+        batch->set_list(agent.id, obstacles);      // agent entries: this planner's neighbours
         for (const auto& o : obstacles) batch->observe(o);
     }
     // the mission's shared device context (NULL never): MapManager-side bindings hand maps over through it

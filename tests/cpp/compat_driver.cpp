@@ -136,6 +136,25 @@ int main(int argc, char** argv) {
         }
         printf("dynamic obstacle planned cost %.6f vs %.6f end_y %.4f vs %.4f alerts %d (id %d) vs %d\n", cost[0], cost[1], endy[0], endy[1],
                alerts[0], alert_id[0], alerts[1]);
+        // the obstacle list a caller passes IS the neighbour list (a caller that filters differently from broadcastMsgs):
+        // agent 0 of a fourth mission is told about agents 2 and 5 only
+        Mission fourth = mission;
+        fourth.agents[0].desired_goal_point = point3d(0.4f, 0.7f, 1.f);
+        TrajPlanner p4(nh, param, fourth, fourth.agents[0]);
+        Obstacles few;
+        for (int j : {5, 2}) {
+            Obstacle o;
+            o.type = ObstacleType::AGENT; o.id = j; o.position = fourth.agents[j].start_point; o.goal_point = o.position;
+            o.radius = (float)fourth.agents[j].radius; o.downwash = (float)fourth.agents[j].downwash;
+            few.push_back(o);
+        }
+        p4.setObstacles(few);
+        Agent a4 = fourth.agents[0];
+        a4.next_waypoint = point3d(1.53f, 0.16f, 1.f);
+        p4.plan(a4, octree, distmap, ros::Time(), false);
+        std::vector<int32_t> nidx((size_t)N * (N - 1 + DLSC_MAX_OBSTACLES)), ncnt(N);
+        dlsc_get_neighbours(p4.deviceContext(), nidx.data(), ncnt.data());
+        printf("caller list kept %d\n", ncnt[0] == 2 && nidx[0] == 2 && nidx[1] == 5 ? 1 : 0);
     }
     // TrajOptimizer::solve with explicit constraints (one LSC plane, no SFC)
     {

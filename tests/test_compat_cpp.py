@@ -51,7 +51,7 @@ def test_compat_driver_serial_equals_batched():
     outs = {}
     for mode in ("serial", "staged"):
         outs[mode] = subprocess.check_output([exe, mode, "25"], text=True).strip().split("\n")
-    assert len(outs["serial"]) == 29
+    assert len(outs["serial"]) == 30
     for a, b in zip(outs["serial"][:25], outs["staged"][:25]):
         assert a == b, (a, b)
     st = re.search(r"stats seq (\d+) total (\S+) qp (\S+) samples (\d+)", outs["serial"][25])
@@ -61,6 +61,7 @@ def test_compat_driver_serial_equals_batched():
     assert float(dyn.group(1)) > float(dyn.group(2)) + 1e-3, outs["serial"][27]      # the obstacle costs something ...
     assert abs(float(dyn.group(3)) - float(dyn.group(4))) > 1e-3, outs["serial"][27]    # ... and bends the trajectory
     assert int(dyn.group(7)) == 0 and int(dyn.group(5)) in (0, 1) and (int(dyn.group(5)) == 0 or int(dyn.group(6)) == 0)
+    assert outs["serial"][28] == "caller list kept 1"
     for line in outs["serial"][:25]:
         assert float(re.search(r"min_dist ([0-9.]+)", line).group(1)) >= 0.3 - 1e-4, line
     assert int(re.search(r"seq (\d+)", outs["serial"][24]).group(1)) == 25
