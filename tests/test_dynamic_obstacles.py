@@ -376,3 +376,46 @@ def test_obstacle_scenario_generator():
     assert pe["downwash"][0] == 1.0 and pe["radius"][0] == 0.2 and pe["max_acc"][0] == 2.0
     with pytest.raises(NotImplementedError):
         ms.obstacle_states([dict(type="patrol")], 0.0)
+
+
+def degenerate_normals(lib):
+    """normalVectorBetweenLines' heuristic branches (reference src/traj_planner.cpp:1089-1098): an obstacle sitting exactly
+    on an agent with the same (zero) velocity -> normal (1, 0, 0); an obstacle flying exactly through an agent -> the
+    un-normalised (b - a) x (0, 0, 1).  First replan of empty10 (every initial trajectory is the start point)."""
+    cfg, m = _parity.load_case("empty10")
+    sw = _parity.make_oracle(cfg, m, 12)
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=12, lib=lib)
+    s2, s5 = m.start[2].astype(np.float32), m.start[5].astype(np.float32)
+    opos = np.array([s2, s5 - np.float32([0.25, 0, 0])], np.float32)
+    ovel = np.array([[0, 0, 0], [0.5, 0, 0]], np.float32)            # the second one reaches agent 5 half way through segment 2
+    obs = dict(radius=0.2, downwash=1.5, max_acc=0.5, slack_weight=50.0)
+    sw.waypoint = m.start.copy()
+    sw.waypoint[[2, 5], 1] += np.float32(1.2)      # waypoints the obstacles cannot reach: the trap keeps their LSCs
+    sw.set_obstacles(opos, ovel, **obs); pl.set_obstacles(opos, ovel, **obs)
+    _parity.force_state(pl, sw)
+    sw.step(); pl.plan()
+    normal, anchor, d = pl.lsc()
+    assert np.array_equal(normal[:, :2], sw.lsc_normal[:, :2]) and np.array_equal(d[:, :2], sw.lsc_d[:, :2])
+    assert np.array_equal(anchor[:, :2], sw.lsc_anchor[:, :2])
+    dw = (0.15 + 1.5 * 0.2) / (0.15 + 0.2)
+    assert np.all(sw.trap == 1)                                       # first replan, zero communication box: every agent "trapped"
+    # obstacle 0 sits on agent 2 with the same velocity: (1, 0, 0) in every segment
+    assert np.array_equal(normal[2, 0], np.tile(np.float32([1, 0, 0]), (cfg.M, 1)))
+    # obstacle 1 flies exactly through agent 5: closest points coincide -> (b - a) x (0, 0, 1), not normalised, in the
+    # segment where it passes; ordinary unit normals elsewhere
+    lens = np.linalg.norm(normal[5, 1].astype(np.float64), axis=1)
+    assert normal[5, 1, 2, 0] == 0 and abs(lens[2] - 0.1) < 1e-6                 # |b - a| = 0.5 m/s x 0.2 s
+    assert np.allclose(np.delete(lens, 2), 1.0, atol=1e-6)
+    r = _parity.compare_step(pl, sw)
+    assert r["status_mismatch"] == 0 and r["obj_excess"] <= _parity.OBJ_ABS and r["violation"] <= 1e-6
+    pl.close()
+    return dw
+
+
+def test_degenerate_obstacle_normals_hostsim(hostsim):
+    degenerate_normals(hostsim)
+
+
+@pytest.mark.gpu
+def test_degenerate_obstacle_normals_gpu(cuda_lib):
+    degenerate_normals(cuda_lib)
