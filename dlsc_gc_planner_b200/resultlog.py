@@ -2,11 +2,12 @@
 src/multi_sync_simulator.cpp:735-851), the de-facto interchange with the reference's replayer
 (src/multi_sync_replayer.cpp): one row per recorded time, per agent the twelve columns
 ``id,t,px,py,pz,vx,vy,vz,ax,ay,az,planning_time``, numbers as C++ ``ostream << double / float`` prints them
-(6 significant digits, %g).  Agents only (obstacle columns ``obs_id,t,px,py,pz,size`` follow the agents in the
-reference when a mission has dynamic obstacles: not on this path yet)."""
+(6 significant digits, %g); when the mission has dynamic obstacles their six columns ``obs_id,t,px,py,pz,size`` follow
+the agents (:755-763, 829-843)."""
 import numpy as np
 
 AGENT_COLUMNS = "id,t,px,py,pz,vx,vy,vz,ax,ay,az,planning_time"
+OBSTACLE_COLUMNS = "obs_id,t,px,py,pz,size"
 
 
 def _g(x):
@@ -15,12 +16,13 @@ def _g(x):
     return "%g" % float(x)
 
 
-def header(n_agents):
-    return ",".join([AGENT_COLUMNS] * n_agents)
+def header(n_agents, n_obstacles=0):
+    return ",".join([AGENT_COLUMNS] * n_agents + [OBSTACLE_COLUMNS] * n_obstacles)
 
 
-def format_row(t, pos, vel, acc, planning_time):
-    """pos / vel / acc [N][3] (float32 as point3d), planning_time [N] seconds."""
+def format_row(t, pos, vel, acc, planning_time, obs_pos=None, obs_radius=None):
+    """pos / vel / acc [N][3] (float32 as point3d), planning_time [N] seconds; obs_pos [n_obs][3] (float32), obs_radius
+    [n_obs] (double) of the dynamic obstacles, if any."""
     cells = []
     for a in range(len(pos)):
         cells.append(str(a))
@@ -28,33 +30,47 @@ def format_row(t, pos, vel, acc, planning_time):
         for v in (pos[a], vel[a], acc[a]):
             cells.extend(_g(np.float32(c)) for c in v)
         cells.append(_g(planning_time[a]))
+    for o in range(0 if obs_pos is None else len(obs_pos)):
+        cells.append(str(o))
+        cells.append(_g(t))
+        cells.extend(_g(np.float32(c)) for c in obs_pos[o])
+        cells.append(_g(obs_radius[o]))
     return ",".join(cells)
 
 
 class ResultLog:
-    """Append-only writer: `log.record(t, pos, vel, acc, planning_time)` once per recorded time."""
+    """Append-only writer: `log.record(t, pos, vel, acc, planning_time[, obs_pos, obs_radius])` once per recorded time."""
 
-    def __init__(self, path, n_agents):
-        self.n = int(n_agents)
+    def __init__(self, path, n_agents, n_obstacles=0):
+        self.n, self.on = int(n_agents), int(n_obstacles)
         self.f = open(path, "w")
-        self.f.write(header(self.n) + "\n")
+        self.f.write(header(self.n, self.on) + "\n")
 
-    def record(self, t, pos, vel, acc, planning_time=None):
+    def record(self, t, pos, vel, acc, planning_time=None, obs_pos=None, obs_radius=None):
         pt = np.zeros(self.n) if planning_time is None else planning_time
-        self.f.write(format_row(t, pos, vel, acc, pt) + "\n")
+        assert (0 if obs_pos is None else len(obs_pos)) == self.on
+        self.f.write(format_row(t, pos, vel, acc, pt, obs_pos, obs_radius) + "\n")
 
     def close(self):
         self.f.close()
 
 
-def read(path):
-    """-> t [T], pos / vel / acc [T][N][3] float32, planning_time [T][N] (what the replayer parses)."""
+def read(path, with_obstacles=False):
+    """-> t [T], pos / vel / acc [T][N][3] float32, planning_time [T][N] -- what MultiSyncReplayer::readCSVFile parses
+    (reference src/multi_sync_replayer.cpp:53-112: agents counted by the "id" header cells, obstacles by "obs_id");
+    with_obstacles adds obs_pos [T][n_obs][3] float32 and obs_radius [T][n_obs]."""
     with open(path) as f:
         lines = [l.strip() for l in f if l.strip()]
-    n = lines[0].count("id,t,")
-    rows = np.array([[float(c) for c in l.split(",")] for l in lines[1:]], np.float64).reshape(len(lines) - 1, n, 12)
-    return (rows[:, 0, 1], rows[:, :, 2:5].astype(np.float32), rows[:, :, 5:8].astype(np.float32),
-            rows[:, :, 8:11].astype(np.float32), rows[:, :, 11])
+    cells = lines[0].split(",")
+    n, on = cells.count("id"), cells.count("obs_id")
+    data = np.array([[float(c) for c in l.split(",")] for l in lines[1:]], np.float64)
+    rows = data[:, :12 * n].reshape(len(lines) - 1, n, 12)
+    out = (rows[:, 0, 1], rows[:, :, 2:5].astype(np.float32), rows[:, :, 5:8].astype(np.float32),
+           rows[:, :, 8:11].astype(np.float32), rows[:, :, 11])
+    if not with_obstacles:
+        return out
+    obs = data[:, 12 * n:12 * n + 6 * on].reshape(len(lines) - 1, on, 6)
+    return out + (obs[:, :, 2:5].astype(np.float32), obs[:, :, 5])
 
 
 # ---- summary file (MultiSyncSimulator::saveSummarizedResultAsCSV, reference src/multi_sync_simulator.cpp:852-900) ----

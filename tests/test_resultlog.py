@@ -96,3 +96,24 @@ def test_summary_row_reproduces_the_reference_summary_file(tmp_path):
     p = tmp_path / "summary.csv"
     resultlog.append_summary(str(p), row); resultlog.append_summary(str(p), row)
     assert open(p).read() == ref[0] + "\n" + ref[1] + "\n" + ref[1] + "\n"
+
+
+def test_result_log_with_obstacle_columns(tmp_path):
+    """Missions with dynamic obstacles: `obs_id,t,px,py,pz,size` per obstacle after the agents (reference
+    src/multi_sync_simulator.cpp:755-763, 829-843), read back the way MultiSyncReplayer::readCSVFile counts the columns."""
+    import numpy as np
+    from dlsc_gc_planner_b200 import resultlog
+    p = str(tmp_path / "r.csv")
+    log = resultlog.ResultLog(p, 2, 2)
+    pos = np.array([[1, 2, 3], [-0.5, 0.25, 1]], np.float32)
+    z = np.zeros((2, 3), np.float32)
+    log.record(0.1, pos, z, z, [0.001, 0.002], np.array([[2, 0, 1], [0, -2, 1]], np.float32), [0.3, 0.25])
+    log.record(0.2, pos + 1, z, z, None, np.array([[1.9, 0.5, 1], [0.5, -1.9, 1]], np.float32), [0.3, 0.25])
+    log.close()
+    lines = open(p).read().strip().split("\n")
+    assert lines[0] == ",".join(["id,t,px,py,pz,vx,vy,vz,ax,ay,az,planning_time"] * 2 + ["obs_id,t,px,py,pz,size"] * 2)
+    assert lines[1].endswith(",0,0.1,2,0,1,0.3,1,0.1,0,-2,1,0.25")
+    t, rp, rv, ra, pt, op, orad = resultlog.read(p, with_obstacles=True)
+    assert np.allclose(t, [0.1, 0.2]) and np.array_equal(rp[1], pos + 1) and np.allclose(pt[0], [0.001, 0.002])
+    assert np.allclose(op[1], [[1.9, 0.5, 1], [0.5, -1.9, 1]]) and np.allclose(orad, 0.3 * np.array([[1, 0.25 / 0.3]] * 2))
+    assert resultlog.read(p)[1].shape == (2, 2, 3)
