@@ -489,32 +489,21 @@ def run_ours(args):
     for k in hb:
         hb[k][1][...] = rec[k][:, sl]
     traj_t, traj_h = pinned((NL, cfg.M, cfg.n + 1, 3), torch.float32)
-    # inputs: the caller's pinned arrays are bound once (dlsc_bind_agents_host) and rewritten in place before every step;
-    # the step's graph starts by reading them and ends with the record refresh.  Results: the trajectories go straight into
-    # the pinned host buffer (dlsc_bind_traj_host) -- every agent's result is written over PCIe as soon as its QP finishes,
-    # so the device->host transfer overlaps the QPs still running.  One replan = write inputs, dlsc_step, dlsc_sync.
-    # (Sharded runs keep the explicit dlsc_set_agents in front of the record exchange: the other ranks need this step's
-    # positions before they plan.)
+    structs = [capi.DlscAgents(hb["pos"][1][t].ctypes.data, hb["vel"][1][t].ctypes.data, hb["acc"][1][t].ctypes.data,
+                               hb["wp"][1][t].ctypes.data, None) for t in range(W + K)]
+    import ctypes as C
+
+    # the trajectories go straight into the pinned host buffer (dlsc_bind_traj_host): every agent's result is written over
+    # PCIe as soon as its QP finishes, so the device->host transfer of the step's result overlaps the QPs still running;
+    # the buffer is complete after the step's dlsc_sync
     pl.bind_traj_host(traj_h)
-    if world == 1:
-        cur_in = {k: pinned((NL, 3), torch.float32) for k in ("pos", "vel", "acc", "wp")}
-        pl.bind_agents_host(cur_in["pos"][1], cur_in["vel"][1], cur_in["acc"][1], cur_in["wp"][1], publish=True)
 
-        def e2e_step(t):
-            for k in ("pos", "vel", "acc", "wp"):
-                np.copyto(cur_in[k][1], hb[k][1][t])      # this step's host inputs into the bound arrays
-            pl.plan()
-            pl.sync()                                      # result of this step is in traj_h
-    else:
-        structs = [capi.DlscAgents(hb["pos"][1][t].ctypes.data, hb["vel"][1][t].ctypes.data, hb["acc"][1][t].ctypes.data,
-                                   hb["wp"][1][t].ctypes.data, None) for t in range(W + K)]
-
-        def e2e_step(t):
-            pl.set_agents_async(structs[t])
-            gather()
-            pl.plan()
-            pl.publish_records()
-            pl.sync()
+    def e2e_step(t):
+        pl.set_agents_async(structs[t])
+        gather()
+        pl.plan()
+        pl.publish_records()
+        pl.sync()                                                                 # result of this step is in traj_h
 
     barrier()
     for t in range(W):
@@ -538,7 +527,6 @@ def run_ours(args):
     e2e_ms, t_host = float(tt[0].item()), float(tt[1].item())
     e2e_exact = bool(np.array_equal(traj_h, snap["final_traj"][sl]))
     pl.bind_traj_host(None)
-    pl.bind_agents_host()
     h2d = int(4 * N * 12)
     d2h = int(N * cfg.M * (cfg.n + 1) * 12)
 

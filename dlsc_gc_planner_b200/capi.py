@@ -73,7 +73,7 @@ EXPORTS = (
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
     "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build dlsc_wp_last_error dlsc_wp_create dlsc_wp_destroy "
     "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps "
-    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host dlsc_bind_agents_host").split()
+    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host").split()
 
 
 def build_library(force=False):
@@ -336,20 +336,6 @@ class SwarmPlanner:
 
     def advance(self):
         self._ck(self.lib.dlsc_advance(self.ctx))
-
-    def bind_agents_host(self, pos=None, vel=None, acc=None, waypoint=None, disturbed=None, publish=True):
-        """Every step reads its inputs from these PINNED arrays ([n_local][3] float32, disturbed [n_local] uint8), which the
-        caller rewrites in place; with publish the step ends with publish_records.  All None unbinds."""
-        arrs = (pos, vel, acc, waypoint, disturbed)
-        if all(a is None for a in arrs):
-            self._ck(self.lib.dlsc_bind_agents_host(self.ctx, None, 0))
-            self._in_host = None
-            return
-        for a in arrs[:4]:
-            assert a is None or (a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.size == self.NL * 3)
-        st = DlscAgents(*[None if a is None else a.ctypes.data for a in arrs])
-        self._ck(self.lib.dlsc_bind_agents_host(self.ctx, C.byref(st), int(bool(publish))))
-        self._in_host = arrs
 
     def bind_traj_host(self, array):
         """Every replan delivers the trajectories into `array` ([n_local][M][6][3] float32, ideally pinned): complete after

@@ -606,27 +606,6 @@ int dlsc_set_agents(dlsc_ctx* c, const dlsc_agents* a) {
     return 0;
 }
 
-int dlsc_bind_agents_host(dlsc_ctx* c, const dlsc_agents* a, int publish_after_step) {
-    if (!c) return fail("null ctx");
-    CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
-    DevState& S = c->S;
-    S.in_pos = S.in_vel = S.in_acc = S.in_wp = nullptr; S.in_dist = nullptr; S.in_bound = 0; S.in_publish = 0;
-    if (!a) return 0;
-    const void* src[5] = {a->pos, a->vel, a->acc, a->waypoint, a->disturbed};
-    void* dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < 5; i++)
-        if (src[i] && cudaHostGetDevicePointer(&dev[i], const_cast<void*>(src[i]), 0) != cudaSuccess) {
-            cudaGetLastError();
-            return fail("dlsc_bind_agents_host: every array must be pinned host memory (cudaHostAlloc / cudaHostRegister)");
-        }
-    S.in_pos = static_cast<const float*>(dev[0]); S.in_vel = static_cast<const float*>(dev[1]);
-    S.in_acc = static_cast<const float*>(dev[2]); S.in_wp = static_cast<const float*>(dev[3]);
-    S.in_dist = static_cast<const uint8_t*>(dev[4]);
-    S.in_bound = 1; S.in_publish = publish_after_step ? 1 : 0;
-    return 0;
-}
-
 int dlsc_bind_traj_host(dlsc_ctx* c, float* host) {
     if (!c) return fail("null ctx");
     CK(cudaSetDevice(c->device));
@@ -805,11 +784,6 @@ static void make_view(const dlsc_ctx* c, int first, int count, DevParams& P, Dev
     S.lsc_normal += f * K * M * 3; S.lsc_d += f * K * M * kP; S.lsc_anchor_last += f * K * 3; S.lsc_near += f * K * M;
     S.sfc += f * M * 6; S.traj += f * npt * 3; S.qp_x += f * (size_t)P.D * npt;
     if (S.traj_host) S.traj_host += f * npt * 3;
-    if (S.in_pos) S.in_pos += f * 3;
-    if (S.in_vel) S.in_vel += f * 3;
-    if (S.in_acc) S.in_acc += f * 3;
-    if (S.in_wp) S.in_wp += f * 3;
-    if (S.in_dist) S.in_dist += f;
     S.cost += f; S.viol += f; S.qp_iters += f; S.status += f;
     S.qp_list += f; S.qp_list_gi += f; S.qp_seed += f * 4;
     S.comm_box += f * 6; S.trap += f;
@@ -846,7 +820,6 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
         CK(cudaMemsetAsync(c->S.counters, 0, DLSC_N_COUNTERS * sizeof(unsigned long long), st));
     if (tm) CK(cudaEventRecord(ev[0], st));
-    if ((mask & DLSC_STAGE_PREDICT) && Sx.in_bound) { launch_ingest(Pr, Sx, st); c->launches++; }
     if (mask & DLSC_STAGE_PREDICT) {
         launch_predict(Pr, Sx, seq, st); c->launches++;
         if (Pr.n_dyn > 0) { launch_dyn_predict(Pr, Sx, st); c->launches++; }
@@ -873,7 +846,6 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     if (tm) CK(cudaEventRecord(ev[5], st));
     if (mask & DLSC_STAGE_QP) c->launches += launch_qp(Pr, Sx, c->T, c->qpl, st);
     if (tm) { CK(cudaEventRecord(ev[6], st)); c->ev_used++; }
-    if (mask == DLSC_STAGE_ALL && Sx.in_bound && Sx.in_publish) { launch_advance(Pr, Sx, false, st); c->launches++; }
     CK(cudaGetLastError());
     return 0;
 }

@@ -36,11 +36,6 @@ struct DevState {
     float* sfc;                // [NL][M][6]
     float* traj;               // [NL][M][P][3]  QP result (or failsafe)
     float* traj_host;          // device view of a caller's mapped pinned buffer of the same shape (dlsc_bind_traj_host), or null
-    // device views of the caller's mapped pinned input arrays (dlsc_bind_agents_host), or null: read by k_ingest at the
-    // start of every step instead of separate host->device copies
-    const float *in_pos, *in_vel, *in_acc, *in_wp;   // [NL][3]
-    const uint8_t* in_dist;    // [NL]
-    int in_bound, in_publish;  // inputs bound; publish the records at the end of every full step
     double* qp_x;              // [NL][D][M][P]
     double *cost, *viol;       // [NL]
     int32_t *qp_iters, *status;
@@ -81,7 +76,6 @@ void launch_edt_mask(const EdtDev& E, double margin, uint8_t* mask, int* unsafe,
 void launch_sat_build(const EdtDev& E, int32_t* sat, cudaStream_t st);   // 4 launches
 void launch_expand_anchor(const DevParams& P, const DevState& S, float* anchor_out, cudaStream_t st);
 void launch_set_state(const DevParams& P, float* rec, const float* pos, const float* vel, cudaStream_t st);   // pos / vel [NL][3] device, or null
-void launch_ingest(const DevParams& P, const DevState& S, cudaStream_t st);   // bound host inputs -> records / acc / waypoint / disturbed
 void launch_get_state(const DevParams& P, const float* rec, float* pos, float* vel, cudaStream_t st);         // records -> dense pos / vel
 void launch_reset(const DevParams& P, const DevState& S, const float* start_dev, cudaStream_t st);
 

@@ -702,23 +702,6 @@ __global__ void k_get_state(const __grid_constant__ DevParams P, const float* __
 void launch_get_state(const DevParams& P, const float* rec, float* pos, float* vel, cudaStream_t st) {
     k_get_state<<<(P.NL * 3 + 255) / 256, 256, 0, st>>>(P, rec, pos, vel);
 }
-// dlsc_bind_agents_host: the step's inputs straight from the caller's mapped pinned arrays (zero-copy reads over PCIe, 48 B
-// per agent), scattered to where dlsc_set_agents would have put them -- one kernel inside the step's graph instead of four
-// copies and a kernel in front of it
-__global__ void __launch_bounds__(256) k_ingest(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.NL * 3) return;
-    const int la = i / 3, k = i - la * 3;
-    float* r = S.rec + (size_t)(P.begin + la) * P.rec + P.M * kP * 3;
-    if (S.in_pos) r[k] = S.in_pos[i];
-    if (S.in_vel) r[3 + k] = S.in_vel[i];
-    if (S.in_acc) S.acc[i] = S.in_acc[i];
-    if (S.in_wp) S.waypoint[i] = S.in_wp[i];
-    if (S.in_dist && k == 0) S.disturbed[la] = S.in_dist[la];
-}
-void launch_ingest(const DevParams& P, const DevState& S, cudaStream_t st) {
-    k_ingest<<<(P.NL * 3 + 255) / 256, 256, 0, st>>>(P, S);
-}
 void launch_set_state(const DevParams& P, float* rec, const float* pos, const float* vel, cudaStream_t st) {
     k_set_state<<<(P.NL * 3 + 255) / 256, 256, 0, st>>>(P, rec, pos, vel);
 }

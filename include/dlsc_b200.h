@@ -253,12 +253,6 @@ int dlsc_get_goal(dlsc_ctx* ctx, float* goal /* [n_local][3] current_goal_point 
  * finishes, so the device->host transfer overlaps the QPs still running; the buffer is complete after dlsc_sync().
  * dlsc_get_traj keeps working.  NULL unbinds.  The buffer must outlive the binding. */
 int dlsc_bind_traj_host(dlsc_ctx* ctx, float* host);
-/* The inputs the same way: `pinned` names caller-owned PINNED host arrays (members may be NULL) that the caller rewrites
- * in place before every step.  From then on every step (dlsc_step / dlsc_run_stages with the prediction stage) starts by
- * reading them -- what dlsc_set_agents does, without the separate copies -- and, with publish_after_step, ends with
- * dlsc_publish_records, so that a host-driven replan is  write inputs -> dlsc_step -> dlsc_sync -> read the bound
- * trajectories.  NULL unbinds.  The arrays must outlive the binding. */
-int dlsc_bind_agents_host(dlsc_ctx* ctx, const dlsc_agents* pinned, int publish_after_step);
 int dlsc_get_state(dlsc_ctx* ctx, float* pos, float* vel, float* acc /* each [n_local][3] or NULL */);
 int dlsc_get_init_traj(dlsc_ctx* ctx, float* traj /* [n_local][M][P][3] */);
 int dlsc_get_pred_traj(dlsc_ctx* ctx, float* traj /* [n_agents][M][P][3] */);

@@ -43,7 +43,6 @@ struct dlsc_ctx {
     bool have_edt = false;
     int64_t counters[DLSC_N_COUNTERS] = {0};
     float* traj_host = nullptr;
-    dlsc_agents in_bound{}; bool in_on = false, in_publish = false;
     // dynamic obstacles
     std::vector<float> dyn_pos, dyn_vel, comm_box;
     std::vector<double> dyn_radius, dyn_downwash, dyn_max_acc, dyn_size, qp_slack;
@@ -247,11 +246,6 @@ int dlsc_set_agent_props(dlsc_ctx* c, const dlsc_agent_props* p) {
 }
 
 int dlsc_bind_traj_host(dlsc_ctx* c, float* host) { c->traj_host = host; return 0; }
-int dlsc_bind_agents_host(dlsc_ctx* c, const dlsc_agents* a, int publish) {
-    c->in_on = a != nullptr; c->in_publish = publish != 0;
-    if (a) c->in_bound = *a;
-    return 0;
-}
 int dlsc_set_obstacles(dlsc_ctx* c, const dlsc_obstacles* o, const dlsc_obstacle_params* op) {
     const int n = o ? o->n : 0;
     if (n < 0 || n > kMaxDyn) return fail("too many obstacles");
@@ -486,9 +480,8 @@ int dlsc_run_stages(dlsc_ctx* c, int mask) {
 }
 
 int dlsc_step(dlsc_ctx* c) {
-    if (c->in_on && dlsc_set_agents(c, &c->in_bound)) return -1;
     const int rc = dlsc_run_stages(c, DLSC_STAGE_ALL);
-    if (rc == 0) { c->seq++; if (c->in_on && c->in_publish) dlsc_publish_records(c); }
+    if (rc == 0) c->seq++;
     return rc;
 }
 

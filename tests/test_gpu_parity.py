@@ -195,43 +195,3 @@ def test_bound_host_trajectories_equal_the_device_copy(cuda_lib):
     pl.plan(); pl.sync()
     assert np.all(pageable == -7.0)
     pl.close()
-
-
-def test_bound_host_inputs_equal_set_agents(cuda_lib):
-    """dlsc_bind_agents_host: a context that reads its inputs from bound pinned arrays inside the step (and publishes its
-    records at the end of it) produces the same trajectories, bit for bit, as one driven through dlsc_set_agents +
-    dlsc_publish_records -- on the first replans and on the CUDA-graph path."""
-    import torch
-    cfg, m = _parity.load_case("forest10")
-    a = capi.SwarmPlanner(cfg, m, max_nbr=9, lib=cuda_lib)
-    b = capi.SwarmPlanner(cfg, m, max_nbr=9, lib=cuda_lib)
-    for pl in (a, b):
-        pl.build_edt(m.boxes)
-    pin = lambda: torch.zeros((m.n_agents, 3), dtype=torch.float32).pin_memory().numpy()
-    pos, vel, acc, wp = pin(), pin(), pin(), pin()
-    b.bind_agents_host(pos, vel, acc, wp, publish=True)
-    wpt = m.start.copy()
-    sw = _parity.make_oracle(cfg, m, 9)                 # only as the state stepper of the host-side "simulator"
-    for step in range(10):
-        wpt[:, 0] += np.float32(0.1) * np.sign(m.goal[:, 0] - wpt[:, 0])
-        p, v, ac = a.state()
-        a.set_agents(pos=p, vel=v, acc=ac, waypoint=wpt)
-        a.plan(); a.publish_records()
-        pos[...] = p; vel[...] = v; acc[...] = ac; wp[...] = wpt
-        b.plan(); b.sync()
-        ta, tb = a.traj(), b.traj()
-        assert np.array_equal(ta, tb), step
-        assert np.array_equal(a.get_records(), b.get_records()), step
-        # next host state: the trajectory's state at dt, as a simulator would integrate it
-        for i in range(m.n_agents):
-            st = sw_state(cfg, m, ta[i])
-            p[i], v[i], ac[i] = st
-        a.set_agents(pos=p, vel=v, acc=ac)
-    b.bind_agents_host()
-    a.close(); b.close()
-
-
-def sw_state(cfg, m, traj):
-    from oracle import oracle_py as O
-    st = O.state_at(_parity.oracle_params(cfg, m), traj, cfg.dt)
-    return st[0], st[1], st[2]
