@@ -73,7 +73,7 @@ EXPORTS = (
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
     "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build dlsc_wp_last_error dlsc_wp_create dlsc_wp_destroy "
     "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps "
-    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host").split()
+    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host dlsc_wp_set_warning dlsc_wp_pibt_obs").split()
 
 
 def build_library(force=False):
@@ -544,6 +544,21 @@ class WaypointProvider:
         s, c, g = (np.ascontiguousarray(x, np.int32) for x in (start, current, goal))
         plan = np.zeros((max_t, len(s)), np.int32)
         T = self._ck(self.lib.dlsc_wp_pibt(self.ctx, C.c_int(len(s)), _p(s), _p(c), _p(g), C.c_int(max_t), _p(plan)))
+        return plan[:T].copy()
+
+    def set_warning(self, warning):
+        """Warning flags of the lattice nodes ([w*d*h] uint8; None clears them)."""
+        if warning is None:
+            self._ck(self.lib.dlsc_wp_set_warning(self.ctx, None))
+        else:
+            wr = np.ascontiguousarray(warning, np.uint8)
+            self._ck(self.lib.dlsc_wp_set_warning(self.ctx, _p(wr)))
+
+    def pibt_obs(self, start, current, goal, obs_node, obs_dist, max_t=6000):
+        s, c, g, o = (np.ascontiguousarray(x, np.int32) for x in (start, current, goal, obs_node))
+        od = np.ascontiguousarray(obs_dist, np.float32)
+        plan = np.zeros((max_t, len(s)), np.int32)
+        T = self._ck(self.lib.dlsc_wp_pibt_obs(self.ctx, C.c_int(len(s)), _p(s), _p(c), _p(g), _p(o), _p(od), C.c_int(max_t), _p(plan)))
         return plan[:T].copy()
 
     def step(self, pos, goal_cur, traj, waypoint):

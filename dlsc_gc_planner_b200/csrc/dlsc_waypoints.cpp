@@ -70,6 +70,7 @@ struct dlsc_wp {
     std::array<int, 3> gdim{1, 1, 1};
     std::vector<P3> start, desired_goal;
     std::vector<uint8_t> exists;                 // [w * d * h], id = w * d * z + w * y + x
+    std::vector<uint8_t> warning;                // node inside a dynamic obstacle's reachable region (updateGridMap :140-150); empty = none
     std::vector<std::array<int, 6>> nbr;         // neighbour ids in the reference's order (left, right, up, down, top, bottom), -1 = none
     std::vector<int8_t> nbr_n;
     PlanResult plan_result;                      // one member shared by all groups, like GridBasedPlanner::plan_result
@@ -141,8 +142,13 @@ struct dlsc_wp {
                     const int id = w * d * z + w * y + x;
                     const int c[6][3] = {{x - 1, y, z}, {x + 1, y, z}, {x, y - 1, z}, {x, y + 1, z}, {x, y, z - 1}, {x, y, z + 1}};
                     int n = 0;
+                    const bool v_warn = !warning.empty() && warning[id];
                     for (const auto& q : c)
-                        if (node_exists(q[0], q[1], q[2])) nbr[id][n++] = w * d * q[2] + w * q[1] + q[0];
+                        if (node_exists(q[0], q[1], q[2])) {
+                            const int wid = w * d * q[2] + w * q[1] + q[0];
+                            // no edge from a clear node into a warning node (graph.cpp:389-424: v->warning || !w->warning)
+                            if (v_warn || warning.empty() || !warning[wid]) nbr[id][n++] = wid;
+                        }
                     nbr_n[id] = (int8_t)n;
                 }
     }
@@ -151,7 +157,7 @@ struct dlsc_wp {
 namespace {
 
 // ---- PIBT (src/mapf/pibt.cpp) on node ids ------------------------------------------------------------------------
-struct PibtAgent { int id, v_now, v_next, g; int elapsed, init_d; float tie_breaker; };
+struct PibtAgent { int id, v_now, v_next, g; int elapsed, init_d; float tie_breaker; int o; float obs_d; };   // o / obs_d: closest obstacle of interest
 
 struct Pibt {
     dlsc_wp& G;
@@ -165,7 +171,7 @@ struct Pibt {
 
     // slot[i]: cache slot (global agent index) of problem agent i, or -1
     Pibt(dlsc_wp& g, const std::vector<int>& start, const std::vector<int>& cur, const std::vector<int>& goal,
-         const std::vector<int>& slot = {})
+         const std::vector<int>& slot = {}, const std::vector<int>& obs_node = {}, const std::vector<float>& obs_dist = {})
         : G(g), n((int)cur.size()), mt(0) {        // DEFAULT_SEED = 0, a fresh generator per problem (problem.cpp:85)
         const int nn = (int)G.exists.size();
         dist.assign(n, nullptr);
@@ -195,18 +201,26 @@ struct Pibt {
         occupied_now.assign(nn, -1); occupied_next.assign(nn, -1);
         A.resize(n);
         for (int i = 0; i < n; i++) {
-            A[i] = PibtAgent{i, cur[i], -1, goal[i], 0, (int)dist[i][start[i]], (float)i / (float)n};
+            const bool has_o = !obs_node.empty() && obs_node[i] >= 0;
+            A[i] = PibtAgent{i, cur[i], -1, goal[i], 0, (int)dist[i][start[i]], (float)i / (float)n, has_o ? obs_node[i] : -1,
+                             has_o ? obs_dist[i] : 1e9f};                              // SP_INFINITY when there is none
             occupied_now[cur[i]] = i;
         }
         plan.push_back(cur);
     }
-    float goal_dist(const PibtAgent& a, int v) const {                              // Pos::euclideanDist, pos.cpp:27-32
+    float node_dist(int u, int v) const {                                           // Pos::euclideanDist, pos.cpp:27-32
         const int w = G.gdim[0], d = G.gdim[1];
         auto xyz = [&](int id, int* o) { o[2] = id / (w * d); o[1] = (id - o[2] * w * d) / w; o[0] = id - o[2] * w * d - o[1] * w; };
         int p[3], q[3];
-        xyz(a.g, p); xyz(v, q);
+        xyz(u, p); xyz(v, q);
         const float dx = (float)(p[0] - q[0]), dy = (float)(p[1] - q[1]), dz = (float)(p[2] - q[2]);
         return std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    float goal_dist(const PibtAgent& a, int v) const { return node_dist(a.g, v); }
+    float obs_dist_of(const PibtAgent& a, int v) const {                            // PIBT::obsDist :230-236
+        const float infinity = 10000;
+        if (a.obs_d > infinity) return infinity;
+        return node_dist(a.o, v);
     }
     int choose_node(PibtAgent& a) {                                                 // pibt.cpp:142-189
         std::vector<int> C(G.nbr[a.v_now].begin(), G.nbr[a.v_now].begin() + G.nbr_n[a.v_now]);
@@ -220,9 +234,9 @@ struct Pibt {
             if (u == a.g) return u;
             if (v == -1) { v = u; continue; }
             const int c_v = (int)dist[a.id][v], c_u = (int)dist[a.id][u];
-            // no dynamic obstacle of interest: obsDist is the same constant for every node (pibt.cpp:227-234)
+            const float o_v = obs_dist_of(a, v), o_u = obs_dist_of(a, u);           // away from the obstacle of interest
             const float d_v = goal_dist(a, v), d_u = goal_dist(a, u);
-            if ((c_u < c_v) || (c_u == c_v && occupied_now[v] != -1 && occupied_now[u] == -1) ||
+            if ((c_u < c_v) || (c_u == c_v && occupied_now[v] != -1 && occupied_now[u] == -1) || (c_u == c_v && o_u > o_v) ||
                 (c_u == c_v && occupied_now[v] == -1 && occupied_now[u] == -1 && d_u < d_v))
                 v = u;
         }
@@ -249,7 +263,8 @@ struct Pibt {
     int run() {                                                                     // :13-103; returns the timesteps made
         auto lower = [this](int x, int y) {                                         // true: x has lower priority than y
             const PibtAgent &a = A[x], &b = A[y];
-            if (a.elapsed != b.elapsed) return a.elapsed < b.elapsed;               // (obs_d is the same constant for everybody)
+            if (a.obs_d != b.obs_d) return a.obs_d > b.obs_d;                       // closer to its obstacle of interest first :16
+            if (a.elapsed != b.elapsed) return a.elapsed < b.elapsed;
             if (a.init_d != b.init_d) return a.init_d < b.init_d;
             return a.tie_breaker < b.tie_breaker;
         };
@@ -371,6 +386,13 @@ int dlsc_wp_set_nodes(dlsc_wp* w, const int32_t dims[3], const uint8_t* exists) 
     return 0;
 }
 
+int dlsc_wp_set_warning(dlsc_wp* w, const uint8_t* warning) {
+    if (!w) return wp_fail("dlsc_wp_set_warning: null argument");
+    if (warning) w->warning.assign(warning, warning + w->exists.size()); else w->warning.clear();
+    w->build_edges();
+    return 0;
+}
+
 int dlsc_wp_get_nodes(const dlsc_wp* w, uint8_t* exists) {
     if (!w || !exists) return wp_fail("dlsc_wp_get_nodes: null argument");
     memcpy(exists, w->exists.data(), w->exists.size());
@@ -388,6 +410,24 @@ int dlsc_wp_pibt(dlsc_wp* w, int n, const int32_t* start, const int32_t* current
     solver.run();
     const int T = (int)solver.plan.size();
     if (T > max_t) return wp_fail("dlsc_wp_pibt: plan longer than the output buffer");
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < n; i++) plan_out[t * n + i] = solver.plan[t][i];
+    return T;
+}
+
+// The same with the closest dynamic obstacle of interest per agent (ProblemAgent's obs_node / obs_dist; obs_node < 0: none).
+int dlsc_wp_pibt_obs(dlsc_wp* w, int n, const int32_t* start, const int32_t* current, const int32_t* goal, const int32_t* obs_node,
+                     const float* obs_dist, int max_t, int32_t* plan_out) {
+    if (!w || n < 1 || !start || !current || !goal || !obs_node || !obs_dist || !plan_out) return wp_fail("dlsc_wp_pibt_obs: bad argument");
+    std::vector<int> s(start, start + n), c(current, current + n), g(goal, goal + n), o(obs_node, obs_node + n);
+    std::vector<float> od(obs_dist, obs_dist + n);
+    for (int i = 0; i < n; i++)
+        for (int v : {s[i], c[i], g[i], o[i] < 0 ? s[i] : o[i]})
+            if (v < 0 || v >= (int)w->exists.size() || !w->exists[v]) return wp_fail("dlsc_wp_pibt_obs: a node id names a missing node");
+    Pibt solver(*w, s, c, g, {}, o, od);
+    solver.run();
+    const int T = (int)solver.plan.size();
+    if (T > max_t) return wp_fail("dlsc_wp_pibt_obs: plan longer than the output buffer");
     for (int t = 0; t < T; t++)
         for (int i = 0; i < n; i++) plan_out[t * n + i] = solver.plan[t][i];
     return T;

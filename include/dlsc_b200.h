@@ -320,6 +320,12 @@ int dlsc_wp_set_nodes(dlsc_wp* wp, const int32_t dims[3], const uint8_t* exists 
 int dlsc_wp_get_nodes(const dlsc_wp* wp, uint8_t* exists /* [w*d*h] */);
 /* PIBT alone on node ids (per-kernel parity entry); plan_out [max_t][n]; returns the number of configurations or < 0. */
 int dlsc_wp_pibt(dlsc_wp* wp, int n, const int32_t* start, const int32_t* current, const int32_t* goal, int max_t, int32_t* plan_out);
+/* per-kernel entries of the dynamic-obstacle side of the planner: warning flags of the lattice nodes (Grid drops the edges
+ * from a clear node into a warning node, third_party/grid-pathfinding/graph/src/graph.cpp:371-431; NULL clears them) and
+ * PIBT with each agent's closest obstacle of interest (src/mapf/pibt.cpp:16, 185-191, 230-236; obs_node < 0: none) */
+int dlsc_wp_set_warning(dlsc_wp* wp, const uint8_t* warning /* [w*d*h] */);
+int dlsc_wp_pibt_obs(dlsc_wp* wp, int n, const int32_t* start, const int32_t* current, const int32_t* goal, const int32_t* obs_node,
+                     const float* obs_dist, int max_t, int32_t* plan_out);
 /* One decentralizedMAPP call for the whole swarm: pos / goal_cur [N][3], traj [N][M][6][3] (NULL before the first replan),
  * waypoint [N][3] in / out. */
 int dlsc_wp_step(dlsc_wp* wp, const float* pos, const float* goal_cur, const float* traj, float* waypoint);

@@ -40,3 +40,36 @@ extern "C" int ref_pibt_solve(int w, int d, int h, const uint8_t* exists, int n,
             for (int i = 0; i < n; i++) plan_out[t * n + i] = plan.get(t, i)->id;
     return rc;      // Problem's destructor frees the grid and its nodes
 }
+
+// The same with dynamic obstacles: `warning` [w*d*h] marks the nodes inside an obstacle's reachable region (Grid then drops
+// the edges from a clear node into a warning node, graph.cpp:371-431); obs_node / obs_dist per agent = the closest
+// obstacle of interest and its distance (ProblemAgent, problem.hpp:9-19; obs_node < 0: none, distance SP_INFINITY).
+extern "C" int ref_pibt_solve_obs(int w, int d, int h, const uint8_t* exists, const uint8_t* warning, int n, const int* start,
+                                  const int* current, const int* goal, const int* obs_node, const float* obs_dist, int max_t,
+                                  int* plan_out) {
+    Nodes V(w * d * h, nullptr);
+    for (int z = 0; z < h; z++)
+        for (int y = 0; y < d; y++)
+            for (int x = 0; x < w; x++) {
+                const int id = w * d * z + w * y + x;
+                if (exists[id]) V[id] = new Node(id, x, y, z, warning && warning[id]);
+            }
+    Grid* grid = new Grid(V, w, d, h);
+    ProblemAgents agents;
+    Node* any = nullptr;
+    for (auto v : V) if (v) { any = v; break; }
+    for (int i = 0; i < n; i++)
+        agents.emplace_back(grid->getNode(start[i]), grid->getNode(current[i]), grid->getNode(goal[i]),
+                            obs_node[i] >= 0 ? grid->getNode(obs_node[i]) : any, obs_node[i] >= 0 ? obs_dist[i] : 1e9f);
+    Problem P(grid, n, agents);
+    PIBT solver(&P);
+    solver.solve();
+    Plan plan = solver.getSolution();
+    const int T = plan.size();
+    int rc = T;
+    if (T > max_t) rc = -1;
+    else
+        for (int t = 0; t < T; t++)
+            for (int i = 0; i < n; i++) plan_out[t * n + i] = plan.get(t, i)->id;
+    return rc;
+}

@@ -24,6 +24,35 @@ def ref_pibt(lib, w, d, h, exists, start, cur, goal, max_t=6000):
     return plan[:T].copy()
 
 
+def ref_pibt_obs(lib, w, d, h, exists, warning, start, cur, goal, obs_node, obs_dist, max_t=6000):
+    plan = np.zeros((max_t, len(cur)), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    T = lib.ref_pibt_solve_obs(w, d, h, p(exists), p(warning), len(cur), p(start), p(cur), p(goal), p(obs_node), p(obs_dist), max_t, p(plan))
+    assert T > 0
+    return plan[:T].copy()
+
+
+def obs_problems(rng, count):
+    """problems() plus the dynamic-obstacle inputs of the planner: warning flags on a random blob of nodes (the reachable
+    region of an obstacle) and, for some agents, a closest obstacle of interest (node + distance)."""
+    out = []
+    for (w, d, h, exists, start, cur, goal) in problems(rng, count):
+        ids = np.flatnonzero(exists)
+        warning = np.zeros(w * d * h, np.uint8)
+        for _ in range(int(rng.integers(1, 4))):
+            c = int(rng.choice(ids)); z, r = divmod(c, w * d); y, x = divmod(r, w)
+            rad = float(rng.uniform(0.8, 2.6))
+            for v in ids:
+                vz, vr = divmod(int(v), w * d); vy, vx = divmod(vr, w)
+                if (vx - x) ** 2 + (vy - y) ** 2 + (vz - z) ** 2 <= rad * rad:
+                    warning[v] = 1
+        n = len(cur)
+        obs_node = np.where(rng.random(n) < 0.5, rng.choice(ids, size=n), -1).astype(np.int32)
+        obs_dist = rng.uniform(0.3, 6.0, n).astype(np.float32)
+        out.append((w, d, h, exists, warning, start, cur, goal, obs_node, obs_dist))
+    return out
+
+
 def component(w, d, h, exists, seed):
     """node ids of the connected component of `seed` (6-neighbourhood)"""
     seen = {seed}
@@ -81,6 +110,17 @@ def main():
         data["%d/plan" % i] = plan
     data["count"] = np.array(len(probs))
     np.savez_compressed(os.path.join(OUT, "pibt_ref.npz"), **data)
+    obs = {}
+    oprobs = obs_problems(np.random.default_rng(20261020), 40)
+    for i, (w, d, h, exists, warning, start, cur, goal, obs_node, obs_dist) in enumerate(oprobs):
+        obs["%d/dims" % i] = np.array([w, d, h], np.int32)
+        for k, v in (("exists", exists), ("warning", warning), ("start", start), ("cur", cur), ("goal", goal), ("obs_node", obs_node),
+                     ("obs_dist", obs_dist)):
+            obs["%d/%s" % (i, k)] = v
+        obs["%d/plan" % i] = ref_pibt_obs(lib, w, d, h, exists, warning, start, cur, goal, obs_node, obs_dist)
+    obs["count"] = np.array(len(oprobs))
+    np.savez_compressed(os.path.join(OUT, "pibt_obs_ref.npz"), **obs)
+    print("obstacle problems", len(oprobs), "plan lengths", sorted(len(obs["%d/plan" % i]) for i in range(len(oprobs)))[-5:])
     print("problems", len(probs), "plan lengths", sorted(len(data["%d/plan" % i]) for i in range(len(probs)))[-5:])
 
 

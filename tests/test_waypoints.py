@@ -68,6 +68,41 @@ def test_pibt_matches_reference_object_code_live(lib):
         wp.close()
 
 
+def test_pibt_with_dynamic_obstacles_matches_reference(lib):
+    """The dynamic-obstacle side of the planner's PIBT: warning nodes (directed edges) and the closest obstacle of interest
+    per agent (priority, tie-breaking) -- 40 committed known-answer plans of the reference's object code, and live when
+    oracle/_ref is built."""
+    z = np.load(os.path.join(GOLD, "pibt_obs_ref.npz"))
+    differs = 0
+    for i in range(int(z["count"])):
+        g = lambda f: z["%d/%s" % (i, f)]
+        wp = _provider(lib, len(g("cur")))
+        wp.set_nodes(g("dims"), g("exists"))
+        plain = wp.pibt(g("start"), g("cur"), g("goal"))
+        wp.set_warning(g("warning"))
+        plan = wp.pibt_obs(g("start"), g("cur"), g("goal"), g("obs_node"), g("obs_dist"))
+        assert plan.shape == g("plan").shape and np.array_equal(plan, g("plan")), i
+        differs += plan.shape != plain.shape or not np.array_equal(plan, plain)
+        wp.set_warning(None)
+        assert np.array_equal(wp.pibt(g("start"), g("cur"), g("goal")), plain)          # clearing restores the plain lattice
+        wp.close()
+    assert differs >= 20                     # the obstacle inputs do change the plans
+    so = os.path.join(_parity.ROOT, "oracle", "_ref", "libmapf_ref.so")
+    if os.path.exists(so):
+        import sys
+        sys.path.insert(0, GOLD)
+        import make_pibt_fixtures as mk
+        ref = C.CDLL(so)
+        for (w, d, h, exists, warning, start, cur, goal, on, od) in mk.obs_problems(np.random.default_rng(78), 25):
+            want = mk.ref_pibt_obs(ref, w, d, h, exists, warning, start, cur, goal, on, od)
+            wp = _provider(lib, len(cur))
+            wp.set_nodes((w, d, h), exists)
+            wp.set_warning(warning)
+            got = wp.pibt_obs(start, cur, goal, on, od)
+            assert got.shape == want.shape and np.array_equal(got, want)
+            wp.close()
+
+
 def test_lattice_nodes_follow_the_distance_grid(lib, oracle):
     """updateGridMap: nodes inside inflated obstacles are dropped; maze10 #1 keeps its start and goal nodes."""
     cfg, m = _parity.load_case("maze10")
