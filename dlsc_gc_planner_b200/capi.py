@@ -73,7 +73,7 @@ EXPORTS = (
     "dlsc_build_edt_occupancy dlsc_get_edt dlsc_edt_build_ms dlsc_p2p_export dlsc_p2p_connect dlsc_exchange_records "
     "dlsc_p2p_status dlsc_p2p_disconnect dlsc_gjk_batch dlsc_cuda_build dlsc_wp_last_error dlsc_wp_create dlsc_wp_destroy "
     "dlsc_wp_dims dlsc_wp_set_grid dlsc_wp_set_nodes dlsc_wp_get_nodes dlsc_wp_pibt dlsc_wp_step dlsc_wp_pibt_timesteps "
-    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host dlsc_wp_set_warning dlsc_wp_pibt_obs").split()
+    "dlsc_set_obstacles dlsc_get_slack dlsc_get_trap dlsc_get_obstacle_pred dlsc_bind_traj_host dlsc_wp_set_warning dlsc_wp_pibt_obs dlsc_wp_set_obstacles dlsc_wp_set_alerts dlsc_wp_get_warning").split()
 
 
 def build_library(force=False):
@@ -553,6 +553,36 @@ class WaypointProvider:
         else:
             wr = np.ascontiguousarray(warning, np.uint8)
             self._ck(self.lib.dlsc_wp_set_warning(self.ctx, _p(wr)))
+
+    def set_obstacles(self, pos, vel=None, radius=0.15, max_acc=0.0, uncertainty_horizon=1.0):
+        """Dynamic obstacles of the next step() calls (None removes them)."""
+        if pos is None:
+            self._ck(self.lib.dlsc_wp_set_obstacles(self.ctx, 0, None, None, None, None, C.c_double(uncertainty_horizon)))
+            return
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        vel = np.ascontiguousarray(np.zeros((n, 3)) if vel is None else vel, np.float32).reshape(n, 3)
+        full = lambda v: np.full(n, v, np.float64) if np.isscalar(v) else np.ascontiguousarray(v, np.float64)
+        r, ma = full(radius), full(max_acc)
+        self._ck(self.lib.dlsc_wp_set_obstacles(self.ctx, n, _p(pos), _p(vel), _p(r), _p(ma), C.c_double(uncertainty_horizon)))
+
+    def warning(self):
+        w, d, h = self.dims()
+        out = np.zeros(w * d * h, np.uint8)
+        self._ck(self.lib.dlsc_wp_get_warning(self.ctx, _p(out)))
+        return out
+
+    def set_alerts(self, alerts):
+        """alerts: per agent a list of obstacle ids (TrajOptResult::collision_alert), or None."""
+        if alerts is None:
+            self._ck(self.lib.dlsc_wp_set_alerts(self.ctx, None, None, 0))
+            return
+        stride = max(1, max(len(a) for a in alerts))
+        cnt = np.array([len(a) for a in alerts], np.int32)
+        ids = np.full((len(alerts), stride), -1, np.int32)
+        for i, a in enumerate(alerts):
+            ids[i, :len(a)] = a
+        self._ck(self.lib.dlsc_wp_set_alerts(self.ctx, _p(cnt), _p(ids), stride))
 
     def pibt_obs(self, start, current, goal, obs_node, obs_dist, max_t=6000):
         s, c, g, o = (np.ascontiguousarray(x, np.int32) for x in (start, current, goal, obs_node))

@@ -78,6 +78,11 @@ struct dlsc_wp {
     // the lattice and the goal node only, so they are kept until the lattice changes
     std::vector<std::vector<uint16_t>> dist_cache;   // [agent][node]
     std::vector<int> dist_goal;                      // goal node each cached table was built for (-1: none)
+    // dynamic obstacles of the next dlsc_wp_step (dlsc_wp_set_obstacles) and the agents' collision alerts (dlsc_wp_set_alerts)
+    double dt = 0.2, obs_horizon = 1.0;
+    std::vector<P3> obs_pos, obs_vel;
+    std::vector<double> obs_radius, obs_max_acc;
+    std::vector<std::vector<int>> alerts;        // [agent] obstacle ids (CollisionAlert::obstacles after updateCollisionAlert)
     std::string err;
     int64_t pibt_timesteps = 0;                  // work counter: PIBT timesteps of the last dlsc_wp_step
 
@@ -129,6 +134,32 @@ struct dlsc_wp {
                 if (dd < best_d) { best_d = dd; best = cid; }
             }
         return best;
+    }
+    bool obstacle_reaches(int o, const P3& q) const {                               // Obstacle::isCollided, obstacle.hpp:26-36
+        const double horizon = M * dt;
+        const double step = std::min(0.1 * horizon, 0.1);
+        for (double t = 0; t <= horizon; t += step) {
+            P3 c;
+            c.x = obs_pos[o].x + obs_vel[o].x * (float)t; c.y = obs_pos[o].y + obs_vel[o].y * (float)t; c.z = obs_pos[o].z + obs_vel[o].z * (float)t;
+            const double tm = std::min(t, obs_horizon);
+            if (distance(c, q) < radius0 + obs_radius[o] + 0.5 * obs_max_acc[o] * tm * tm) return true;
+        }
+        return false;
+    }
+    std::vector<int> bfs_table(int from) const {                                    // createDistanceTable :646-670 (directed edges)
+        std::vector<int> tab(exists.size(), 1000000000);                           // (int)SP_INFINITY
+        std::queue<int> open;
+        open.push(from); tab[from] = 0;
+        while (!open.empty()) {
+            const int v = open.front(); open.pop();
+            for (int k = 0; k < nbr_n[v]; k++) {
+                const int m = nbr[v][k];
+                if (tab[v] + 1 >= tab[m]) continue;
+                tab[m] = tab[v] + 1;
+                open.push(m);
+            }
+        }
+        return tab;
     }
     void build_edges() {                                                            // Grid::Grid, graph.cpp:371-431
         const int w = gdim[0], d = gdim[1], h = gdim[2];
@@ -315,7 +346,7 @@ int dlsc_wp_create(const dlsc_params* p, int n_agents, const float* start, const
     if (!p || !start || !desired_goal || !out || n_agents < 1) return wp_fail("dlsc_wp_create: bad argument");
     dlsc_wp* w = new dlsc_wp();
     w->N = n_agents; w->dim = p->dim; w->M = p->M;
-    w->grid_res = p->grid_res; w->z_2d = p->z_2d; w->comm_range = p->comm_range;
+    w->grid_res = p->grid_res; w->z_2d = p->z_2d; w->comm_range = p->comm_range; w->dt = p->dt;
     w->downwash0 = agent_downwash; w->radius0 = agent_radius;
     for (int i = 0; i < 3; i++) {                                                   // GridBasedPlanner ctor :28-49
         const double gr = w->gres(i);
@@ -393,6 +424,29 @@ int dlsc_wp_set_warning(dlsc_wp* w, const uint8_t* warning) {
     return 0;
 }
 
+int dlsc_wp_set_obstacles(dlsc_wp* w, int n, const float* pos, const float* vel, const double* radius, const double* max_acc,
+                          double uncertainty_horizon) {
+    if (!w || n < 0 || (n > 0 && (!pos || !vel || !radius || !max_acc))) return wp_fail("dlsc_wp_set_obstacles: bad argument");
+    w->obs_pos.resize(n); w->obs_vel.resize(n); w->obs_radius.assign(radius, radius + n); w->obs_max_acc.assign(max_acc, max_acc + n);
+    for (int o = 0; o < n; o++) { w->obs_pos[o] = p3_load(pos + 3 * o); w->obs_vel[o] = p3_load(vel + 3 * o); }
+    w->obs_horizon = uncertainty_horizon;
+    return 0;
+}
+int dlsc_wp_set_alerts(dlsc_wp* w, const int32_t* count, const int32_t* ids, int stride) {
+    if (!w) return wp_fail("dlsc_wp_set_alerts: null argument");
+    w->alerts.assign(w->N, {});
+    if (!count || !ids) return 0;
+    for (int a = 0; a < w->N; a++)
+        for (int k = 0; k < count[a] && k < stride; k++) w->alerts[a].push_back(ids[(size_t)a * stride + k]);
+    return 0;
+}
+
+int dlsc_wp_get_warning(const dlsc_wp* w, uint8_t* warning) {
+    if (!w || !warning) return wp_fail("dlsc_wp_get_warning: null argument");
+    for (size_t i = 0; i < w->exists.size(); i++) warning[i] = w->warning.empty() ? 0 : w->warning[i];
+    return 0;
+}
+
 int dlsc_wp_get_nodes(const dlsc_wp* w, uint8_t* exists) {
     if (!w || !exists) return wp_fail("dlsc_wp_get_nodes: null argument");
     memcpy(exists, w->exists.data(), w->exists.size());
@@ -459,10 +513,35 @@ int dlsc_wp_step(dlsc_wp* w, const float* pos, const float* goal_cur, const floa
         }
         if (cand == -1) groups.push_back({qi});
     }
+    // ---- dynamic obstacles (GridBasedPlanner::planMAPF :64-94): warning nodes = lattice points inside an obstacle's reachable
+    //      region (updateGridMap :140-150; non-"real" obstacle types, which never remove nodes), BFS tables from every
+    //      obstacle's node (updateDistanceTables :165-174).  The same for every group of this step. ----
+    const int n_obs = (int)w->obs_pos.size();
+    std::vector<std::vector<int>> obs_tab;
+    if (n_obs > 0) {
+        std::vector<uint8_t> warn(w->exists.size(), 0);
+        for (size_t id = 0; id < warn.size(); id++) {
+            if (!w->exists[id]) continue;
+            const P3 q = w->node_point((int)id);
+            for (int o = 0; o < n_obs && !warn[id]; o++) warn[id] = w->obstacle_reaches(o, q) ? 1 : 0;
+        }
+        if (warn != w->warning) { w->warning = warn; w->build_edges(); }
+        for (int o = 0; o < n_obs; o++) obs_tab.push_back(w->bfs_table(w->closest_node(w->obs_pos[o])));
+    } else if (!w->warning.empty()) {
+        w->warning.clear(); w->build_edges();
+    }
+    auto obs_cost = [&](const std::set<int>& ids, int node) {                          // getObsCost :685-697
+        double cost = 0;
+        for (int o : ids) {
+            const int d = obs_tab[o][node];
+            cost += d == 0 ? 1e9 : 1.0 / ((double)d * d);
+        }
+        return cost;
+    };
     for (const auto& group : groups) {
         const std::vector<size_t> gv(group.begin(), group.end());
         const int n = (int)gv.size();
-        // ---- GridBasedPlanner::planMAPF / runMAPF without dynamic obstacles ----
+        // ---- GridBasedPlanner::planMAPF / runMAPF ----
         std::vector<int> s(n), c(n), g(n);
         std::vector<P3> cur_wp(n), goal_pt(n);
         for (int k = 0; k < n; k++) {
@@ -472,8 +551,67 @@ int dlsc_wp_step(dlsc_wp* w, const float* pos, const float* goal_cur, const floa
             if (!w->exists[s[k]] || !w->exists[c[k]] || !w->exists[g[k]])           // the reference dereferences a null node here
                 return wp_fail("dlsc_wp_step: agent " + std::to_string(qi) + ": start, waypoint or goal lies on an occupied lattice node");
         }
+        // ---- updateDOI (:192-247) and updateGoal (:250-299): the dynamic obstacles of interest of every agent, and for the
+        //      agents that have one an escape goal found by descending the obstacle cost from the agent's node ----
+        std::vector<int> obs_node(n, -1);
+        std::vector<float> obs_dist(n, 1e9f);
+        bool doi_exist = false;
+        for (int k = 0; k < n && n_obs > 0; k++) {
+            const size_t qi = gv[k];
+            const P3 agent_pos = p3_load(pos + 3 * qi);
+            std::vector<int> cands;
+            if (qi >= w->alerts.size() || w->alerts[qi].empty()) {
+                for (int o = 0; o < n_obs; o++) if (w->obstacle_reaches(o, cur_wp[k])) cands.push_back(o);
+            } else {
+                cands = w->alerts[qi];
+            }
+            std::set<int> doi;
+            double min_dist = 1e9;
+            int closest = -1;
+            for (int o : cands) {
+                if (o < 0 || o >= n_obs) continue;
+                doi.insert(o);
+                const double d = distance(w->obs_pos[o], agent_pos);
+                if (d < min_dist) { min_dist = d; closest = o; }
+            }
+            if (doi.empty()) continue;
+            doi_exist = true;
+            obs_node[k] = w->closest_node(w->obs_pos[closest]);
+            obs_dist[k] = (float)min_dist;
+            // updateGoal
+            int nd = w->closest_node(agent_pos);
+            const int gnode = w->closest_node(cur_wp[k]);
+            P3 new_goal = w->node_point(nd);
+            double min_cost = 1e9;
+            bool restarted = false;
+            std::queue<int> open;
+            open.push(nd);
+            while (!open.empty()) {
+                nd = open.front(); open.pop();
+                if (!restarted && nd == gnode) {                                        // restart the search at the waypoint
+                    std::queue<int>().swap(open);
+                    open.push(gnode);
+                    min_cost = 1e9;
+                    new_goal = w->node_point(gnode);
+                    restarted = true;
+                    continue;
+                }
+                const double c_n = obs_cost(doi, nd);
+                for (int e = 0; e < w->nbr_n[nd]; e++) {
+                    const int mnode = w->nbr[nd][e];
+                    const double c_m = obs_cost(doi, mnode);
+                    if (c_n < c_m + kEpsF) continue;
+                    if (c_m < min_cost) { min_cost = c_m; new_goal = w->node_point(mnode); }
+                    open.push(mnode);
+                }
+                if (min_cost < 0.01) break;
+            }
+            goal_pt[k] = new_goal;
+            g[k] = w->point_id(new_goal);
+        }
         std::vector<int> slot(gv.begin(), gv.end());
-        Pibt solver(*w, s, c, g, slot);
+        if (doi_exist) slot.assign(n, -1);                  // escape goals change from step to step: no cached distance tables
+        Pibt solver(*w, s, c, g, slot, obs_node, obs_dist);
         w->pibt_timesteps += solver.run();
         const auto& plan = solver.plan;
         // ---- updatePlanResult (:292-364) ----
@@ -516,7 +654,7 @@ int dlsc_wp_step(dlsc_wp* w, const float* pos, const float* goal_cur, const floa
         const bool valid_now = solution_valid(now), valid_prev = solution_valid(prev);
         const bool new_agent_added = now.agent_ids != prev.agent_ids;
         const bool better = now.makespan() < prev.makespan();
-        if (!new_agent_added && (!valid_now || (!better && valid_prev))) now = prev;
+        if (!doi_exist && !new_agent_added && (!valid_now || (!better && valid_prev))) now = prev;   // :354-357
         w->plan_result = now;
         // ---- waypoint update rules (:378-452) ----
         std::vector<P3> desired(n);

@@ -324,6 +324,17 @@ int dlsc_wp_pibt(dlsc_wp* wp, int n, const int32_t* start, const int32_t* curren
  * from a clear node into a warning node, third_party/grid-pathfinding/graph/src/graph.cpp:371-431; NULL clears them) and
  * PIBT with each agent's closest obstacle of interest (src/mapf/pibt.cpp:16, 185-191, 230-236; obs_node < 0: none) */
 int dlsc_wp_set_warning(dlsc_wp* wp, const uint8_t* warning /* [w*d*h] */);
+/* Dynamic obstacles of the next dlsc_wp_step calls (n = 0 removes them): GridBasedPlanner::planMAPF's obstacle argument
+ * (src/grid_based_planner.cpp:64-94) -- warning nodes (updateGridMap :140-150), obstacle distance tables (:165-174), the
+ * obstacles of interest of every agent and its escape goal (updateDOI :192-247, updateGoal :250-299).  Obstacle types other
+ * than DYN_REAL (the motion-capture type of the physical experiments, which also removes nodes) are covered.
+ * dlsc_wp_set_alerts hands over the agents' collision alerts (TrajOptResult::collision_alert, the obstacle ids; count [N],
+ * ids [N][stride]; NULL clears): an agent with alerts takes those obstacles as its candidates instead of the ones that reach
+ * its waypoint (:200-226). */
+int dlsc_wp_set_obstacles(dlsc_wp* wp, int n, const float* pos, const float* vel, const double* radius, const double* max_acc,
+                          double uncertainty_horizon);
+int dlsc_wp_set_alerts(dlsc_wp* wp, const int32_t* count, const int32_t* ids, int stride);
+int dlsc_wp_get_warning(const dlsc_wp* wp, uint8_t* warning /* [w*d*h] of the last step */);
 int dlsc_wp_pibt_obs(dlsc_wp* wp, int n, const int32_t* start, const int32_t* current, const int32_t* goal, const int32_t* obs_node,
                      const float* obs_dist, int max_t, int32_t* plan_out);
 /* One decentralizedMAPP call for the whole swarm: pos / goal_cur [N][3], traj [N][M][6][3] (NULL before the first replan),

@@ -419,3 +419,51 @@ def test_degenerate_obstacle_normals_hostsim(hostsim):
 @pytest.mark.gpu
 def test_degenerate_obstacle_normals_gpu(cuda_lib):
     degenerate_normals(cuda_lib)
+
+
+def closed_loop_spin4(plan_lib, steps):
+    """The reference's forest10_spin4 mission closed loop, everything through the C ABI: obstacle-aware waypoints
+    (dlsc_wp_set_obstacles: warning nodes, obstacles of interest, escape goals), collision alerts formed from the QP's slack
+    variables (src/traj_optimizer.cpp:84-105, plan/slack_threshold 0.1) and fed back to the waypoint layer
+    (dlsc_wp_set_alerts), replans with the dynamic-obstacle LSCs and slack QP, state steps on the device."""
+    from dlsc_gc_planner_b200 import missions as ms
+    cfg, m = _parity.load_case("forest10")
+    pl = capi.SwarmPlanner(cfg, m, max_nbr=14, lib=plan_lib)
+    pl.build_edt(m.boxes)
+    dist, obst, dims, mk = pl.get_edt()
+    wp = capi.WaypointProvider(cfg, m, lib=capi.load_library(), edt=(dist, obst, dims, mk, cfg.world_res))
+    wcur, traj, gap, fails = pl.start.copy(), None, 9.0, 0
+    dw = (0.15 * 2.0 + 0.3 * 1.0) / 0.45
+    for s in range(steps):
+        st = ms.obstacle_states(ms.SPIN4, s * cfg.dt)
+        pos, _, _ = pl.state()
+        wp.set_obstacles(st["pos"], st["vel"], radius=st["radius"], max_acc=st["max_acc"], uncertainty_horizon=0.7)
+        if s:
+            sk = pl.slack()
+            wp.set_alerts([[o for o in range(4) if np.abs(sk[a, o]).sum() > 0.1] for a in range(m.n_agents)])
+        wcur = wp.step(pos, pl.goal() if s else pl.start, traj, wcur)
+        pl.set_agents(waypoint=wcur)
+        pl.set_obstacles(st["pos"], st["vel"], radius=st["radius"], downwash=st["downwash"], max_acc=st["max_acc"], slack_weight=100.0,
+                         uncertainty_horizon=0.7)
+        pl.plan()
+        fails += int(((pl.status() & capi.FAIL_MASK) != 0).sum())
+        traj = pl.traj()
+        pl.advance()
+        p2, _, _ = pl.state()
+        d = p2[:, None, :] - ms.obstacle_states(ms.SPIN4, (s + 1) * cfg.dt)["pos"][None]
+        d[..., 2] /= dw                                                   # the agent-obstacle collision ellipsoid
+        gap = min(gap, float((np.linalg.norm(d, axis=2) - 0.45).min()))
+    done = float(np.linalg.norm(pl.state()[0] - m.goal, axis=1).max())
+    pl.close(); wp.close()
+    return gap, fails, done
+
+
+def test_closed_loop_spin4_is_collision_free_hostsim(hostsim):
+    gap, fails, done = closed_loop_spin4(hostsim, 130)
+    assert fails == 0 and gap > 0.1 and done < 1e-3, (gap, fails, done)       # (with agent-only waypoints the same run hits an obstacle: gap -0.12 m)
+
+
+@pytest.mark.gpu
+def test_closed_loop_spin4_is_collision_free_gpu(cuda_lib):
+    gap, fails, done = closed_loop_spin4(cuda_lib, 200)
+    assert fails == 0 and gap > 0.1 and done < 1e-3, (gap, fails, done)

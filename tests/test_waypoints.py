@@ -147,3 +147,75 @@ def test_generated_waypoints_reproduce_the_reference_run(lib, oracle):
         sw.advance()
     assert wp.pibt_timesteps() > 0
     wp.close()
+
+
+def _open_world(lib, starts, goals, comm_range=-1.0):
+    cfg = missions.PlannerConfig.maze2d()
+    cfg.comm_range = comm_range
+    n = len(starts)
+    one = np.ones(n)
+    s = np.array([[x, y, 1.0] for x, y in starts], np.float32); g = np.array([[x, y, 1.0] for x, y in goals], np.float32)
+    m = missions.Mission(np.array([-4, -4, 0], np.float32), np.array([4, 4, 2], np.float32), s, g, 0.15 * one, 2.0 * one, one, 2 * one,
+                         one, np.zeros((0, 6), np.float32))
+    return cfg, m, capi.WaypointProvider(cfg, m, lib=lib)
+
+
+def _walk(wp, m, steps, on_step=None):
+    """agents that follow their waypoints exactly (position = current goal = waypoint): the waypoint sequence the layer issues"""
+    cur = m.start.copy()
+    seq = [cur.copy()]
+    for s in range(steps):
+        if on_step:
+            on_step(s, cur)
+        cur = wp.step(cur, cur, None, cur)
+        seq.append(cur.copy())
+    return np.array(seq)
+
+
+def test_waypoints_go_around_an_obstacle_region(lib):
+    """GridBasedPlanner with a dynamic obstacle (src/grid_based_planner.cpp:64-150): the lattice nodes the obstacle can reach
+    within the horizon are warning nodes, no edge leads from a clear node into one, so the issued waypoints route around
+    the region; without the obstacle the agent walks the straight row."""
+    cfg, m, wp = _open_world(lib, [(-3.0, 0.0)], [(3.0, 0.0)])
+    w, d, h = wp.dims()
+    straight = _walk(wp, m, 14)
+    assert np.all(straight[:, 0, 1] == 0.0) and straight[-1, 0, 0] == 3.0
+    wp.close()
+    cfg, m, wp = _open_world(lib, [(-3.0, 0.0)], [(3.0, 0.0)])
+    wp.set_obstacles([[0.0, 0.0, 1.0]], [[0.0, 0.0, 0.0]], radius=0.6, max_acc=0.0)
+    around = _walk(wp, m, 20)
+    warn = wp.warning().reshape(d, w)
+    # reachable region: |node - obstacle| < 0.15 + 0.6: the 3 x 3 block of nodes around the origin
+    ys, xs = np.nonzero(warn)
+    assert set(zip((xs * 0.5 - 4).tolist(), (ys * 0.5 - 4).tolist())) == {(x, y) for x in (-0.5, 0.0, 0.5) for y in (-0.5, 0.0, 0.5)}
+    for q in around[:, 0]:
+        assert not warn[int(round((q[1] + 4) / 0.5)), int(round((q[0] + 4) / 0.5))], q       # never steps into the region
+    assert np.allclose(around[-1, 0, :2], [3.0, 0.0]) and np.any(around[:, 0, 1] != 0.0)     # arrives, by a detour
+    wp.set_obstacles(None)
+    again = wp.step(m.start, m.start, None, m.start)
+    assert not wp.warning().any() and again[0, 1] == 0.0
+    wp.close()
+
+
+def test_agent_inside_the_region_escapes(lib):
+    """updateDOI / updateGoal (:192-299): an agent whose waypoint lies inside an obstacle's reachable region takes that
+    obstacle as its obstacle of interest and gets an escape goal down the obstacle-cost slope: its next waypoints move away
+    from the obstacle although its desired goal lies on the other side; a collision alert makes an obstacle one of interest
+    even when the waypoint is out of its reach."""
+    cfg, m, wp = _open_world(lib, [(-0.5, 0.0)], [(3.0, 0.0)])
+    wp.set_obstacles([[0.0, 0.0, 1.0]], [[0.0, 0.0, 0.0]], radius=0.6, max_acc=0.0)
+    seq = _walk(wp, m, 4)
+    d0 = np.linalg.norm(seq[:, 0, :2], axis=1)
+    assert d0[1] > d0[0] and d0[2] >= d0[1], seq[:, 0]                   # away from the obstacle at the origin first
+    wp.close()
+    # alert: the obstacle is far from the waypoint, yet the agent treats it as its obstacle of interest
+    cfg, m, wp = _open_world(lib, [(-3.0, 0.0)], [(3.0, 0.0)])
+    wp.set_obstacles([[-1.5, 0.0, 1.0]], [[0.0, 0.0, 0.0]], radius=0.2, max_acc=0.0)
+    plain = wp.step(m.start, m.start, None, m.start)
+    wp.close()
+    cfg, m, wp = _open_world(lib, [(-3.0, 0.0)], [(3.0, 0.0)])
+    wp.set_obstacles([[-1.5, 0.0, 1.0]], [[0.0, 0.0, 0.0]], radius=0.2, max_acc=0.0)
+    wp.set_alerts([[0]])
+    alerted = wp.step(m.start, m.start, None, m.start)
+    assert plain[0, 0] == -2.5 and alerted[0, 0] <= -3.0, (plain, alerted)          # towards the goal vs. away from the obstacle
+    wp.close()
