@@ -165,6 +165,8 @@ struct GiSmem {
     int16_t* yi;                                       // [kGiQ+1][9] y indices (-1 = unused)
     int* id;                                           // [kGiQ+1] row ids
 };
+// Q: capacity of the active set (rows); a template parameter so that a larger-capacity instantiation costs nothing to add --
+// one was measured for the slack-heavy agents of dynamic-obstacle missions and lost to the interior point (profiles/r2_history.md)
 template <int Q = kGiQ>
 DLSC_HD size_t gi_doubles(const QpTab& T) {
     return (size_t)T.nyd * T.nyd + 2 * (Q * (Q + 1) / 2) + 9 * (Q + 1) + 5 * (Q + 1) + 8 + (9 * (Q + 1) + 3) / 4 + (Q + 2) / 2 + 2;

@@ -13,7 +13,8 @@
 //   (C) only if something is violated: the H^-1 block is staged in shared memory and the active-set
 //       iterations of dlsc_qp.cuh run (same algebra as qp_dual_active_set), re-scanning from the sources.
 // Agents on which the active set gives up (more than kGiQ simultaneously active rows, loss of positive
-// definiteness of the Schur complement) are queued for the interior-point kernel (dlsc_qp.cuh qp_agent).
+// definiteness of the Schur complement; with dynamic obstacles already at kGiDynRows rows or kGiDynIters iterations)
+// are queued for the interior-point kernel (dlsc_qp.cuh qp_agent), which carries the slack variables as well.
 #pragma once
 #include "dlsc_qp.cuh"
 
