@@ -72,8 +72,14 @@ DLSC_HD int f32_as_int(float f) {
 #endif
 }
 
-constexpr int kGiDynIters = 32;    // ... and its iteration cap in that case
-constexpr int kGiDynRows = 20;     // hand-over threshold of the active set when dynamic obstacles are present
+#ifndef DLSC_GI_DYN_ITERS
+#define DLSC_GI_DYN_ITERS 16
+#endif
+#ifndef DLSC_GI_DYN_ROWS
+#define DLSC_GI_DYN_ROWS 12
+#endif
+constexpr int kGiDynIters = DLSC_GI_DYN_ITERS;    // ... and its iteration cap in that case
+constexpr int kGiDynRows = DLSC_GI_DYN_ROWS;     // hand-over threshold of the active set when dynamic obstacles are present
 constexpr double kGiTol = 1e-10;   // accepted violation [m]: the objective error it admits is (multiplier x tol) <= ~1e-8
 
 struct PairRowD { int fam, k, pa, pb; };
@@ -420,8 +426,9 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                     u_p += g.ty[7];
                     if (g.ty[4] != 0.0) {
                         // with dynamic obstacles an agent beside an obstacle keeps a row active in most of its slack groups:
-                        // the serial q x q algebra of this kernel is the wrong tool beyond ~20 rows, the interior point
-                        // (which carries the slack variables) takes over
+                        // the serial q x q algebra of this kernel is the wrong tool beyond a dozen rows, the interior point
+                        // (which carries the slack variables) takes over.  Measured (4096 agents, 8 obstacles, QP stage):
+                        // 8 rows / 8 iterations 3.9 ms, 12 / 16 4.0 ms, 20 / 32 4.6 ms, 28 / 64 6.6 ms
                         if (q >= ((DYN && P.qp_active_max > kGiDynRows) ? kGiDynRows : P.qp_active_max)) flag = 3.0;
                         else {
                             for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
