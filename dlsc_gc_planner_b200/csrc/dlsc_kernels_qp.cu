@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kGiThreads, DLSC_GI_MINB) k_qp_gi(const __grid
 // waits for the slowest of them: four times the threads per agent (the row passes and the trailing updates scale with them: 8.0 / 6.1 / 5.0 ms per step at 128 / 256 / 512)
 constexpr int kQpThreadsDyn = DLSC_QP_THREADS_DYN;
 template <bool DYN>
-__global__ void __launch_bounds__(DYN ? kQpThreadsDyn : kQpThreads, DYN ? 512 / kQpThreadsDyn : 4) k_qp(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(DYN ? kQpThreadsDyn : kQpThreads, DYN ? (kQpThreadsDyn >= 512 ? 1 : 512 / kQpThreadsDyn) : 4) k_qp(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ DevState S,
                                                    const __grid_constant__ QpTab T, size_t scratch_doubles, int all_agents) {
     extern __shared__ __align__(16) double smem[];
