@@ -455,9 +455,14 @@ void launch_gjk_batch(const double* pts, int n, double* v, int32_t* iters, int32
 // a box test are spread over the lanes (one 16-byte load of the vertex mask = 16 vertices) and combined with
 // a warp vote.  4096 agents = 4096 warps: the whole swarm is resident in one wave.
 #ifndef DLSC_SFC_MINB
-#define DLSC_SFC_MINB 7
+#define DLSC_SFC_MINB 28
 #endif
-constexpr int kSfcWarps = 4;
+// one warp per CTA: k_sfc's CTAs hold the whole register file of the SMs while they run, and the LSC kernels on the other
+// stream get in only as CTAs retire -- agent by agent instead of four at a time (step 0.477 -> 0.473 ms)
+#ifndef DLSC_SFC_WARPS
+#define DLSC_SFC_WARPS 1
+#endif
+constexpr int kSfcWarps = DLSC_SFC_WARPS;
 __global__ void __launch_bounds__(kSfcWarps * 32, DLSC_SFC_MINB) k_sfc(const __grid_constant__ DevParams P, const __grid_constant__ DevState S) {
     __shared__ SfcTab tabs[kSfcWarps];
     const int w = threadIdx.x >> 5;
