@@ -37,7 +37,6 @@ struct dlsc_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap = true;               // DLSC_OVERLAP=0 disables; per-stage timing (dlsc_enable_timing) serialises too
-    bool nbr_first = true;             // DLSC_NBR_FIRST=0: neighbour search behind the prediction, as in the per-stage timing mode
     bool rec_owned = false;
     void* traj_host_registered = nullptr;   // host buffer pinned by dlsc_bind_traj_host (unregistered on rebind / destroy)
     bool have_edt = false;
@@ -211,8 +210,6 @@ int dlsc_create(const dlsc_params* hp, int n_agents, int agent_begin, int n_loca
     {
         const char* ov = getenv("DLSC_OVERLAP");
         c->overlap = !(ov && ov[0] == '0');
-        const char* nf = getenv("DLSC_NBR_FIRST");
-        c->nbr_first = !(nf && nf[0] == '0');
         const char* gv = getenv("DLSC_GRAPH");
         c->use_graph = !(gv && gv[0] == '0');
     }
@@ -822,13 +819,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
     }
     if (mask & (DLSC_STAGE_NBR | DLSC_STAGE_LSC | DLSC_STAGE_SFC | DLSC_STAGE_QP))
         CK(cudaMemsetAsync(c->S.counters, 0, DLSC_N_COUNTERS * sizeof(unsigned long long), st));
-    if (mask & DLSC_STAGE_PREDICT) CK(cudaMemsetAsync(Sx.status, 0, (size_t)Pr.NL * sizeof(int32_t), st));
     if (tm) CK(cudaEventRecord(ev[0], st));
-    // The neighbour search reads only the records' positions, not the predictions: outside the per-stage timing mode it goes
-    // first, while the GPU is still empty.  Behind the prediction it would have to squeeze in beside k_sfc, whose CTAs hold
-    // the register files of all SMs from the moment they are launched (k_nbr_bin alone wants 48 K registers on one SM).
-    const bool nbr_first = (mask & DLSC_STAGE_NBR) && (mask & DLSC_STAGE_PREDICT) && !tm && c->nbr_first;
-    if (nbr_first) c->launches += launch_neighbours(Pr, Sx, st);
     if (mask & DLSC_STAGE_PREDICT) {
         launch_predict(Pr, Sx, seq, st); c->launches++;
         if (Pr.n_dyn > 0) { launch_dyn_predict(Pr, Sx, st); c->launches++; }
@@ -842,7 +833,7 @@ static int run_stages_impl(dlsc_ctx* c, int mask, const DevParams& Pr, const Dev
         launch_sfc(Pr, Sx, c->side_stream); c->launches++;
         CK(cudaEventRecord(c->ev_join, c->side_stream));
     }
-    if ((mask & DLSC_STAGE_NBR) && !nbr_first) c->launches += launch_neighbours(Pr, Sx, st);
+    if (mask & DLSC_STAGE_NBR) c->launches += launch_neighbours(Pr, Sx, st);
     if (tm) CK(cudaEventRecord(ev[2], st));
     if (mask & DLSC_STAGE_LSC) c->launches += launch_lsc(Pr, Sx, st);
     if (tm) CK(cudaEventRecord(ev[3], st));

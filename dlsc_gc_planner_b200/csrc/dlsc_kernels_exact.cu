@@ -16,8 +16,6 @@ namespace dlsc {
 // DevParams / DevState travel as __grid_constant__ kernel parameters (constant bank, ~0.8 KB).
 
 // ------------------------------------------------------------------------------------------------
-// (the per-agent status word is cleared by the context before the step's first kernel: the neighbour search, which can raise
-// the overflow bit, may run ahead of this kernel)
 __global__ void __launch_bounds__(256) k_predict(const __grid_constant__ DevParams P, const __grid_constant__ DevState S, int seq) {
     const int npt = P.M * kP;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,6 +26,7 @@ __global__ void __launch_bounds__(256) k_predict(const __grid_constant__ DevPara
     const bool local = la >= 0 && la < P.NL;
     predict_point(P, rec, seq, pt, local ? (S.disturbed[la] != 0) : false, S.pred_traj + (size_t)a * npt * 3,
                   local ? S.init_traj + (size_t)la * npt * 3 : nullptr);
+    if (local && pt == 0) S.status[la] = 0;
 }
 
 void launch_predict(const DevParams& P, const DevState& S, int seq, cudaStream_t st) {
