@@ -164,6 +164,7 @@ struct GiSmem {
     double *Ls, *Sm;                                   // packed lower: Cholesky of S = A H^-1 A', and S itself
     double *yc;                                        // [kGiQ+1][9] y-space coefficients of the active rows (+ candidate)
     double *bq, *u, *r, *v, *l;                        // [kGiQ+1]
+    double *li;                                        // [kGiQ+1] reciprocals of the Cholesky diagonal (dlsc_qp_gi.cuh)
     double *ty;                                        // scalars: [0] step, [1] flag
     int16_t* yi;                                       // [kGiQ+1][9] y indices (-1 = unused)
     int* id;                                           // [kGiQ+1] row ids
@@ -172,7 +173,7 @@ struct GiSmem {
 // one was measured for the slack-heavy agents of dynamic-obstacle missions and lost to the interior point (profiles/r2_history.md)
 template <int Q = kGiQ>
 DLSC_HD size_t gi_doubles(const QpTab& T) {
-    return (size_t)T.nyd * T.nyd + 2 * (Q * (Q + 1) / 2) + 9 * (Q + 1) + 5 * (Q + 1) + 8 + (9 * (Q + 1) + 3) / 4 + (Q + 2) / 2 + 2;
+    return (size_t)T.nyd * T.nyd + 2 * (Q * (Q + 1) / 2) + 9 * (Q + 1) + 6 * (Q + 1) + 8 + (9 * (Q + 1) + 3) / 4 + (Q + 2) / 2 + 2;
 }
 template <int Q = kGiQ>
 DLSC_HD void gi_carve(const QpTab& T, double* base, GiSmem& g) {
@@ -180,7 +181,7 @@ DLSC_HD void gi_carve(const QpTab& T, double* base, GiSmem& g) {
     g.Hinv = p; p += T.nyd * T.nyd;
     g.Ls = p; p += Q * (Q + 1) / 2; g.Sm = p; p += Q * (Q + 1) / 2;
     g.yc = p; p += 9 * (Q + 1);
-    g.bq = p; p += Q + 1; g.u = p; p += Q + 1; g.r = p; p += Q + 1; g.v = p; p += Q + 1; g.l = p; p += Q + 1;
+    g.bq = p; p += Q + 1; g.u = p; p += Q + 1; g.r = p; p += Q + 1; g.v = p; p += Q + 1; g.l = p; p += Q + 1; g.li = p; p += Q + 1;
     g.ty = p; p += 8;
     g.yi = reinterpret_cast<int16_t*>(p); p += (9 * (Q + 1) + 3) / 4;
     g.id = reinterpret_cast<int*>(p);

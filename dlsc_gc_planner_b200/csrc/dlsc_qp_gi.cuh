@@ -374,13 +374,13 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                 for (int j = 0; j < q; j++) {
                     double a = g.v[j];
                     for (int k = 0; k < j; k++) a -= g.Ls[j * (j + 1) / 2 + k] * g.l[k];
-                    a /= g.Ls[j * (j + 1) / 2 + j];
+                    a *= g.li[j];                              // 1 / L_jj, kept beside L: no division on the dependent chain
                     g.l[j] = a; ll += a * a;
                 }
                 for (int j = q - 1; j >= 0; j--) {
                     double a = g.l[j];
                     for (int k = j + 1; k < q; k++) a -= g.Ls[k * (k + 1) / 2 + j] * g.r[k];
-                    g.r[j] = a / g.Ls[j * (j + 1) / 2 + j];
+                    g.r[j] = a * g.li[j];
                 }
                 const double zn = apw - ll;
                 double t1 = 1e300; int kdrop = -1;
@@ -433,6 +433,7 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                         else {
                             for (int k = 0; k < q; k++) { g.Ls[q * (q + 1) / 2 + k] = g.l[k]; g.Sm[q * (q + 1) / 2 + k] = g.v[k]; }
                             g.Ls[q * (q + 1) / 2 + q] = sqrt(zn); g.Sm[q * (q + 1) / 2 + q] = apw;
+                            g.li[q] = 1.0 / g.Ls[q * (q + 1) / 2 + q];
                             for (int tt = 0; tt < 9; tt++) { g.yc[9 * q + tt] = yc[tt]; g.yi[9 * q + tt] = yi[tt]; }
                             g.bq[q] = g.bq[Q]; g.id[q] = g.id[Q]; g.u[q] = u_p;
                             flag = 0.0;
@@ -459,10 +460,11 @@ DLSC_HD int gi_solve(const Cta& c, const DevParams& P, const QpTab& T, const QpI
                             if (!(dj > 0)) { okf = false; break; }
                             dj = sqrt(dj);
                             g.Ls[j * (j + 1) / 2 + j] = dj;
+                            g.li[j] = 1.0 / dj;
                             for (int i2 = j + 1; i2 < q - 1; i2++) {
                                 double a = g.Sm[i2 * (i2 + 1) / 2 + j];
                                 for (int k = 0; k < j; k++) a -= g.Ls[i2 * (i2 + 1) / 2 + k] * g.Ls[j * (j + 1) / 2 + k];
-                                g.Ls[i2 * (i2 + 1) / 2 + j] = a / dj;
+                                g.Ls[i2 * (i2 + 1) / 2 + j] = a * g.li[j];
                             }
                         }
                         flag = okf ? 1.0 : 3.0;
